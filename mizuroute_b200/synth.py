@@ -1,0 +1,246 @@
+"""Seeded synthetic river networks and runoff forcing (BASELINE.json configs).
+
+The reference ships no data (its Cameo test case is an external download), so every workload is
+generated here, reproducibly from a seed:
+
+* ``random_tree``   -- C1 substitute: small random tree, mixed in-degree.
+* ``binary_tree``   -- C2: complete binary tree truncated to n reaches (heap numbering).
+* ``conus_like``    -- C3/C4/C5: forest of uniform-random binary trees (Shreve's random-topology model,
+  height ~ 2*sqrt(pi*n)), heavy-tailed basin sizes with the largest basin ~40 % of the reaches, a few
+  percent of confluences widened to in-degree 3/4, optional lakes.
+
+All generators return reaches in shuffled order with non-trivial ids so the host topology code
+(id->index join, upstream lists, levels) is exercised the way a real network file would.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .network import RiverNetwork
+
+
+# ----------------------------------------------------------------------------------------------
+# topology generators: return parent[] (downstream index, -1 for an outlet), unshuffled
+# ----------------------------------------------------------------------------------------------
+def _uniform_binary_tree(n_internal: int, rng: np.random.Generator) -> np.ndarray:
+    """Uniform random full binary tree with n_internal confluences (2*n_internal+1 reaches).
+
+    Lukasiewicz word + cycle lemma, fully vectorised: nodes are in preorder; node i is a first
+    child iff node i-1 is internal, otherwise its parent is the previous node at the same walk height.
+    """
+    n = 2 * n_internal + 1
+    if n_internal == 0:
+        return np.array([-1], dtype=np.int64)
+    steps = np.empty(n, dtype=np.int64)
+    steps[:n_internal] = 1
+    steps[n_internal:] = -1
+    rng.shuffle(steps)
+    w = np.cumsum(steps)
+    k = int(np.argmin(w))                       # first position of the minimum
+    steps = np.roll(steps, -(k + 1))            # valid preorder degree word (deg-1)
+    W = np.concatenate(([0], np.cumsum(steps)[:-1]))   # W_i = height before visiting node i
+    parent = np.full(n, -1, dtype=np.int64)
+    idx = np.arange(n)
+    first_child = np.zeros(n, dtype=bool)
+    first_child[1:] = steps[:-1] == 1
+    parent[first_child] = idx[first_child] - 1
+    order = np.lexsort((idx, W))
+    prev = np.full(n, -1, dtype=np.int64)
+    same = W[order[1:]] == W[order[:-1]]
+    prev[order[1:][same]] = order[:-1][same]
+    second = ~first_child
+    second[0] = False
+    parent[second] = prev[second]
+    return parent
+
+
+def _contract(parent: np.ndarray, frac: float, rng: np.random.Generator) -> np.ndarray:
+    """Remove a random fraction of the confluences; their tributaries join the next confluence
+    downstream (creates in-degree 3, 4, ...)."""
+    n = parent.shape[0]
+    if frac <= 0 or n < 8:
+        return parent
+    nchild = np.bincount(parent[parent >= 0], minlength=n)
+    cand = (nchild > 0) & (parent >= 0)
+    removed = cand & (rng.random(n) < frac)
+    anc = parent.copy()
+    while True:
+        hit = (anc >= 0) & removed[np.maximum(anc, 0)]
+        if not hit.any():
+            break
+        anc[hit] = parent[anc[hit]]
+    keep = ~removed
+    new_index = np.cumsum(keep) - 1
+    out = anc[keep]
+    out = np.where(out >= 0, new_index[np.maximum(out, 0)], -1)
+    return out
+
+
+def _forest(sizes, frac_wide: float, rng: np.random.Generator) -> np.ndarray:
+    parts, off = [], 0
+    for s in sizes:
+        p = _uniform_binary_tree(max((int(s) - 1) // 2, 0), rng)
+        p = _contract(p, frac_wide, rng)
+        parts.append(np.where(p >= 0, p + off, -1))
+        off += p.shape[0]
+    return np.concatenate(parts)
+
+
+# ----------------------------------------------------------------------------------------------
+# attributes
+# ----------------------------------------------------------------------------------------------
+def _finish(parent: np.ndarray, rng: np.random.Generator, shuffle: bool, meta: dict,
+            zero_area_frac: float = 0.0) -> RiverNetwork:
+    n = parent.shape[0]
+    perm = rng.permutation(n) if shuffle else np.arange(n)      # new position of old node i
+    inv = np.empty(n, dtype=np.int64)
+    inv[perm] = np.arange(n)                                    # old node at new position p
+    segId = (np.arange(n) * 7 + 1001).astype(np.int64)          # id by new position (unique, >0, unsorted vs topology)
+    segId = segId[rng.permutation(n)] if shuffle else segId
+    down_old = parent[inv]                                      # downstream (old numbering) of the node at position p
+    downSegId = np.where(down_old >= 0, segId[perm[np.maximum(down_old, 0)]], -1)
+    length = np.clip(np.exp(rng.normal(np.log(2000.0), 0.6, n)), 100.0, 50000.0)
+    slope = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), n))
+    area = np.exp(rng.normal(np.log(5.0e6), 0.8, n))
+    # one HRU per reach, HRUs stored in their own shuffled order; optionally some reaches get no HRU
+    # at all (BASAREA = 0; exercises the goodBas / runoffMin paths, process_remap.f90:413-415)
+    hperm = rng.permutation(n) if shuffle else np.arange(n)
+    if zero_area_frac > 0:
+        hperm = hperm[rng.random(n) >= zero_area_frac]
+    hruSegId = segId[hperm]
+    hruId = (hruSegId + 50_000_000).astype(np.int64)
+    return RiverNetwork(segId=segId, downSegId=downSegId, length=length, slope=slope,
+                        hruId=hruId, hruSegId=hruSegId, area=area[hperm], meta=meta)
+
+
+def random_tree(n: int = 50, seed: int = 1, window: int = 6, shuffle: bool = True,
+                zero_area_frac: float = 0.0) -> RiverNetwork:
+    """Small random tree/forest: reach i drains to a random reach among the `window` before it."""
+    rng = np.random.default_rng(seed)
+    parent = np.full(n, -1, dtype=np.int64)
+    for i in range(1, n):
+        if rng.random() < 0.03:
+            continue                                            # another outlet
+        parent[i] = rng.integers(max(0, i - window), i)
+    return _finish(parent, rng, shuffle, {"kind": "random_tree", "n": n, "seed": seed}, zero_area_frac)
+
+
+def binary_tree(n: int = 100_000, seed: int = 2, shuffle: bool = True) -> RiverNetwork:
+    """Complete binary tree in heap numbering truncated to n reaches (C2: 100 000 reaches, 17 levels)."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(1, n + 1)
+    parent = (k // 2) - 1
+    parent[0] = -1
+    return _finish(parent.astype(np.int64), rng, shuffle, {"kind": "binary_tree", "n": n, "seed": seed})
+
+
+def conus_like(n: int = 3_000_000, seed: int = 3, largest_frac: float = 0.4, frac_wide: float = 0.04,
+               shuffle: bool = True, n_lakes: int = 0) -> RiverNetwork:
+    """CONUS-like forest (C3/C4/C5).  Basin sizes: one basin of largest_frac*n reaches, the rest
+    Pareto(alpha=0.9)-distributed between 3 and 8 % of n until n reaches are used up."""
+    rng = np.random.default_rng(seed)
+    n_gen = int(round(n / (1.0 - 0.49 * frac_wide)))            # contraction removes ~frac_wide/2 of the reaches
+    sizes = [int(largest_frac * n_gen)]
+    left = n_gen - sizes[0]
+    cap = max(int(0.08 * n_gen), 3)
+    while left > 0:
+        s = int(min(cap, 3.0 * (1.0 + rng.pareto(0.9))))
+        s = min(s, left)
+        if s % 2 == 0:
+            s = max(s - 1, 1)
+        sizes.append(s)
+        left -= s
+    parent = _forest(sizes, frac_wide, rng)
+    meta = {"kind": "conus_like", "n_target": n, "seed": seed, "n_basins": len(sizes), "largest_basin": sizes[0]}
+    net = _finish(parent, rng, shuffle, meta)
+    if n_lakes > 0:
+        add_lakes(net, n_lakes, rng)
+    return net
+
+
+def _down_index(net: RiverNetwork) -> np.ndarray:
+    n = net.nRch
+    order = np.argsort(net.segId, kind="stable")
+    sid = net.segId[order]
+    pos = np.clip(np.searchsorted(sid, net.downSegId), 0, n - 1)
+    hit = (net.downSegId > 0) & (sid[pos] == net.downSegId)
+    return np.where(hit, order[pos], -1).astype(np.int64)
+
+
+def add_lakes(net: RiverNetwork, n_lakes: int, rng: np.random.Generator, frac_endorheic: float = 0.2) -> None:
+    """C5: mark mid-network reaches as lakes.  80 % Doll-2003, 20 % endorheic.  A lake-outlet reach must
+    have the lake as its only upstream (kwt_route.f90:551), so only reaches that are the single
+    tributary of their downstream reach are eligible; lakes are kept at least one reach apart."""
+    n = net.nRch
+    down = _down_index(net)
+    nup = np.bincount(down[down >= 0], minlength=n)
+    elig = (nup > 0) & (down >= 0)
+    elig &= nup[np.maximum(down, 0)] == 1
+    cand = np.flatnonzero(elig)
+    rng.shuffle(cand)
+    # upstream CSR so neighbours of a picked lake can be blocked
+    src = np.flatnonzero(down >= 0)
+    o = np.argsort(down[src], kind="stable")
+    up_idx = src[o]
+    up_ptr = np.concatenate(([0], np.cumsum(nup)))
+    islake = np.zeros(n, dtype=np.int32)
+    blocked = np.zeros(n, dtype=bool)
+    picked = 0
+    for c in cand:
+        if picked >= n_lakes:
+            break
+        if blocked[c]:
+            continue
+        islake[c] = 1
+        picked += 1
+        blocked[down[c]] = True
+        blocked[up_idx[up_ptr[c]:up_ptr[c + 1]]] = True
+    ltype = np.ones(n, dtype=np.int32)
+    lk = np.flatnonzero(islake)
+    ltype[lk[rng.random(lk.size) < frac_endorheic]] = 0
+    net.islake = islake
+    net.lakeModelType = ltype
+    net.D03_MaxStorage = np.where(islake == 1, np.exp(rng.normal(np.log(5.0e7), 1.0, n)), 0.0)
+    net.D03_Coefficient = np.where(islake == 1, rng.uniform(0.005, 0.05, n), 0.0)
+    net.D03_Power = np.where(islake == 1, 1.5, 0.0)
+    net.D03_S0 = np.zeros(n)
+    net.meta["n_lakes"] = int(islake.sum())
+
+
+def runoff_series(net: RiverNetwork, n_steps: int, seed: int = 11, dt: float = 86400.0,
+                  mean_mm_s: float = 2.0e-5, sigma: float = 1.0) -> np.ndarray:
+    """Strictly positive runoff depth [n_steps, nHRU] in mm/s: per-HRU lognormal level x
+    seasonal factor x step-to-step lognormal noise (KWT aborts on zero flow, kwt_route.f90:1365)."""
+    rng = np.random.default_rng(seed)
+    base = np.exp(rng.normal(np.log(mean_mm_s), sigma, net.nHRU))
+    t = np.arange(n_steps) * dt
+    season = 1.0 + 0.6 * np.sin(2.0 * np.pi * t / (365.0 * 86400.0))
+    storm = np.exp(rng.normal(0.0, 0.5, n_steps))
+    out = np.empty((n_steps, net.nHRU), dtype=np.float64)
+    for k in range(n_steps):
+        out[k] = base * season[k] * storm[k] * np.exp(rng.normal(0.0, 0.3, net.nHRU))
+    return out
+
+
+def network_stats(net: RiverNetwork) -> dict:
+    """Realised topology statistics (reported next to the assumed NHDPlus-like targets)."""
+    n = net.nRch
+    down = _down_index(net)
+    nup = np.bincount(down[down >= 0], minlength=n)
+    # distance to outlet by pointer doubling
+    d = (down >= 0).astype(np.int64)
+    a = down.copy()
+    while (a >= 0).any():
+        has = a >= 0
+        ai = np.maximum(a, 0)
+        d = d + np.where(has, d[ai], 0)
+        a = np.where(has, a[ai], -1)
+    conf = nup[nup >= 2]
+    return {
+        "nRch": n, "n_outlets": int((down < 0).sum()), "headwater_frac": float((nup == 0).mean()),
+        "max_indegree": int(nup.max()),
+        "conf_deg2": float((conf == 2).mean()) if conf.size else 0.0,
+        "conf_deg3": float((conf == 3).mean()) if conf.size else 0.0,
+        "conf_deg4p": float((conf >= 4).mean()) if conf.size else 0.0,
+        "max_depth": int(d.max()) + 1,
+    }

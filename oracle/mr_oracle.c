@@ -1,0 +1,1153 @@
+/*
+ * mr_oracle.c -- CPU restatement of mizuRoute's per-timestep reach-routing path.
+ *
+ * THIS FILE IS TEST INFRASTRUCTURE.  It is the checker the CUDA path is compared
+ * against (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference
+ * legs).  Nothing under mizuroute_b200/ may include, link, import or call it.
+ *
+ * PARITY UNPINNED: the reference (ESCOMP/mizuRoute, Fortran) ships no golden vectors,
+ * unit tests or fixtures for this path and cannot be compiled in this environment
+ * (no Fortran compiler / MPI / netCDF).  This restatement follows the Fortran line by
+ * line (citations below, paths relative to /root/reference/route/build/src) and is
+ * cross-checked against an independently written Python twin (oracle/twin.py) and
+ * the invariants in tests/test_oracle_invariants.py.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
+ * -ffp-contract=off keeps a*b+c as two roundings, as gfortran does on baseline x86-64.
+ *
+ * Reference map
+ *   gamma functions            gamma_func.f90:16-121
+ *   hillslope UH (FRAC_FUTURE) process_param.f90:13-92
+ *   reach UH (make_uh)         process_param.f90:99-262
+ *   topology / areas / goodBas network_topo.f90:46-196,202-311,637-779,958-985
+ *   width, slope floor         process_ntopo.f90:176-187,359-366
+ *   basin2reach                process_remap.f90:319-422
+ *   hillslope convolution      basinUH.f90:70-178
+ *   main_route step order      main_route.f90:104-266
+ *   accum_inst_runoff          accum_runoff.f90:32-93
+ *   irf_rch / conv_upsbas_qr   irf_route.f90:40-264
+ *   kwt_rch and callees        kwt_route.f90:36-1622
+ *   lake_route (endorheic,Doll)lake_route.f90:28-229,466-470
+ *   comp_reach_wb              water_balance.f90:22-112
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXQPAR 20                 /* public_var.f90:37 */
+#define KW_CAP  24                 /* per-reach particle capacity (reference can hold 0:NQ2+1 <= 21) */
+#define VERYSMALL DBL_MIN          /* tiny(1.0_dp), public_var.f90:29 */
+#define HUGE_DP   DBL_MAX          /* huge(1.0_dp) */
+#define MIN_SLOPE 1.e-6            /* public_var.f90:30 */
+#define NEG_RUNOFF_TOL (-1.e-3)    /* public_var.f90:31 */
+#define LAKE_WB_TOL 2.e-2
+#define PI_MR 3.14159265359        /* public_var.f90:15 */
+#define SECPRDAY 86400.0
+
+enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, N_METHOD = 3 };
+
+/* path-coverage counters (tests assert that thinning / shock merging / disaggregation were exercised);
+   0 remove_rch calls, 1 shock merges, 2 merged-and-exited, 3 disaggregated groups, 4 max merged series length,
+   5 duplicate times skipped in the merge */
+static long g_cnt[8];
+long mro_counter(int k) { return g_cnt[k]; }
+void mro_reset_counters(void) { int k; for (k = 0; k < 8; k++) g_cnt[k] = 0; }
+enum { LAKE_ENDORHEIC = 0, LAKE_DOLL03 = 1, LAKE_H06 = 2, LAKE_HYPE = 3 };
+
+typedef struct {
+    int n;                         /* number of entries KWAVE(0:n-1); 0 == not allocated */
+    double QF[KW_CAP], TI[KW_CAP], TR[KW_CAP];
+    unsigned char RF[KW_CAP];
+} kwave_t;
+
+typedef struct {
+    /* sizes */
+    int nRch, nHRU;
+    /* options (control-file keys, read_control.f90; public_var.f90:100-145) */
+    double dt;
+    int doesBasinRoute, hw_drain_point, is_lake_sim, lakeRegulate, LakeInputOption;
+    double min_length_route, runoffMin, time_conv, length_conv;
+    int onRoute[N_METHOD];
+    int nRoutes, routeOrder[N_METHOD];
+    /* spatially constant parameters (param.nml) */
+    double fshape, tscale, velo, diff, mann_n, wscale;
+    /* topology */
+    int *segId, *downSegId, *downIndex;
+    int *up_ptr, *up_idx; unsigned char *goodBas; int *nGood;
+    int *hru_ptr, *hru_idx; double *hru_wgt;
+    int *order;                    /* a valid upstream->downstream processing order */
+    int nLevel, *lev_ptr, *lev_idx; /* level sets for OpenMP sweep */
+    /* reach parameters */
+    double *RLENGTH, *R_SLOPE, *R_WIDTH, *R_MAN_N, *BASAREA, *UPSAREA, *TOTAREA;
+    unsigned char *isLake, *lakeInlet; int *lakeModelType;
+    double *D03_MaxStorage, *D03_Coefficient, *D03_Power, *D03_S0;
+    /* unit hydrographs */
+    int ntdh_bas; double *FRAC_FUTURE;
+    int *uh_ptr; double *uh_val; int maxtdh;
+    /* fluxes / state */
+    double *BASIN_QI, *BASIN_QR0, *BASIN_QR1, *QFUTURE; unsigned char *qfuture_alloc;
+    double *REACH_Q[N_METHOD], *REACH_VOL0[N_METHOD], *REACH_VOL1[N_METHOD];
+    double *REACH_INFLOW[N_METHOD], *WB[N_METHOD];
+    double *QFUTURE_IRF;
+    kwave_t *KW;
+    double *reachRunoff;
+    long iTime;                    /* globalData iTime, 1 on the first step */
+    int nThreads;
+    char message[256];
+} mro_t;
+
+/* ------------------------------------------------------------------------------------------ */
+/* gamma_func.f90                                                                              */
+/* ------------------------------------------------------------------------------------------ */
+static double gammln(double xx)    /* gamma_func.f90:104-121 */
+{
+    static const double coef[6] = {76.18009172947146, -86.50532032941677, 24.01409824083091,
+                                   -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5};
+    const double stp = 2.5066282746310005;
+    double x = xx, tmp, ser = 0.0, y;
+    int j;
+    tmp = x + 5.5;
+    tmp = (x + 0.5) * log(tmp) - tmp;
+    /* sum(coef(:)/arth(x+1,1,6)): arth accumulates by repeated addition (nr_utils.f90:70-82) */
+    y = x + 1.0;
+    for (j = 0; j < 6; j++) { ser += coef[j] / y; y = y + 1.0; }
+    return tmp + log(stp * (1.000000000190015 + ser) / x);
+}
+
+static double gser(double a, double x)   /* gamma_func.f90:30-60 */
+{
+    const int ITMAX = 100; const double EPS = DBL_EPSILON;
+    double ap, del, summ; int n;
+    if (x == 0.0) return 0.0;
+    ap = a; summ = 1.0 / a; del = summ;
+    for (n = 1; n <= ITMAX; n++) {
+        ap = ap + 1.0;
+        del = del * x / ap;
+        summ = summ + del;
+        if (fabs(del) < fabs(summ) * EPS) break;
+    }
+    return summ * exp(-x + a * log(x) - gammln(a));
+}
+
+static double gcf(double a, double x)    /* gamma_func.f90:65-99 */
+{
+    const int ITMAX = 100; const double EPS = DBL_EPSILON, FPMIN = DBL_MIN / DBL_EPSILON;
+    double an, b, c, d, del, h; int i;
+    if (x == 0.0) return 1.0;
+    b = x + 1.0 - a; c = 1.0 / FPMIN; d = 1.0 / b; h = d;
+    for (i = 1; i <= ITMAX; i++) {
+        an = -i * (i - a);
+        b = b + 2.0;
+        d = an * d + b;
+        if (fabs(d) < FPMIN) d = FPMIN;
+        c = b + an / c;
+        if (fabs(c) < FPMIN) c = FPMIN;
+        d = 1.0 / d;
+        del = d * c;
+        h = h * del;
+        if (fabs(del - 1.0) <= EPS) break;
+    }
+    return exp(-x + a * log(x) - gammln(a)) * h;
+}
+
+static double gammp(double a, double x)  /* gamma_func.f90:16-25 */
+{
+    if (x < a + 1.0) return gser(a, x);
+    return 1.0 - gcf(a, x);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* process_param.f90:13-92  basinUH -> FRAC_FUTURE                                             */
+/* ------------------------------------------------------------------------------------------ */
+static int make_basin_uh(double dt, double fshape, double tscale, int *ntdh_out, double **frac_out)
+{
+    const int MAXTRY = 100;
+    double ntdh_min, ntdh_max, ntdh_try, x_value, cumprob, psave, tfuture, s;
+    int itry, ntdh, jtim; double *ff;
+    x_value = dt / tscale;
+    cumprob = gammp(fshape, x_value);
+    if (cumprob > 0.999) {
+        ntdh_try = 1.999;
+    } else {
+        ntdh_min = 1.0; ntdh_max = 1000.0;
+        ntdh_try = 0.5 * (ntdh_min + ntdh_max);
+        for (itry = 1; itry <= MAXTRY; itry++) {
+            x_value = dt * ntdh_try / tscale;
+            cumprob = gammp(fshape, x_value);
+            if (cumprob < 0.99) ntdh_min = ntdh_try;
+            if (cumprob > 0.999) ntdh_max = ntdh_try;
+            if (cumprob > 0.99 && cumprob < 0.999) break;
+            ntdh_try = 0.5 * (ntdh_min + ntdh_max);
+            if (itry == MAXTRY) return 20;
+        }
+    }
+    ntdh = (int)ceil(ntdh_try);
+    ff = (double *)malloc(sizeof(double) * ntdh);
+    psave = 0.0;
+    for (jtim = 1; jtim <= ntdh; jtim++) {
+        tfuture = (double)jtim * dt;
+        cumprob = gammp(fshape, tfuture / tscale);
+        ff[jtim - 1] = fmax(0.0, cumprob - psave);
+        psave = cumprob;
+    }
+    s = 0.0; for (jtim = 0; jtim < ntdh; jtim++) s += ff[jtim];
+    for (jtim = 0; jtim < ntdh; jtim++) ff[jtim] = ff[jtim] / s;
+    *ntdh_out = ntdh; *frac_out = ff;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* process_param.f90:99-262  make_uh for one segment; returns ntdh, writes into out[<=240]      */
+/* ------------------------------------------------------------------------------------------ */
+static int make_uh_one(double seg_length, double dt, double velo, double diff, double *out)
+{
+    enum { nTMAX = 240, nHr = 240 };
+    const double dTUH = 3600.0;
+    const double thr1 = (double)0.99999f;   /* single-precision literals, process_param.f90:205,211 */
+    const double thr2 = (double)0.9999f;    /* process_param.f90:242 */
+    double UHM[nHr + 1], UHQ[nTMAX + 1], fr[nTMAX + 1];
+    double INTE, sec, POT, H, UHQ0, d;
+    int nTsub, iHr, jHr, iHrStrt = 1, iHrLast = 1, ntdh, iTagg, k;
+
+    nTsub = (int)ceil(dt / dTUH);
+    for (k = 1; k <= nTMAX; k++) fr[k] = 0.0;
+    for (k = 1; k <= nTsub && k <= nTMAX; k++) fr[k] = 1.0 / nTsub;
+
+    INTE = 0.0; sec = 0.0;
+    for (iHr = 1; iHr <= nHr; iHr++) UHM[iHr] = 0.0;
+    for (iHr = 1; iHr <= nHr; iHr++) {
+        sec = sec + dTUH;
+        if (velo > 0.0) {
+            d = velo * sec - seg_length;
+            POT = (d * d) / (4.0 * diff * sec);
+            if (POT > 69.0) H = 0.0;
+            else H = 1.0 / (2.0 * sqrt(PI_MR * diff * sec)) * seg_length * exp(-POT);
+        } else H = 0.0;
+        UHM[iHr] = H;
+        INTE = INTE + H;
+    }
+    if (INTE > 0.0) for (iHr = 1; iHr <= nHr; iHr++) UHM[iHr] = UHM[iHr] / INTE;
+
+    INTE = 0.0;
+    for (iHr = 1; iHr <= nTMAX; iHr++) { INTE = INTE + UHM[iHr]; iHrLast = iHr; if (INTE > thr1) break; }
+    INTE = 0.0;
+    for (iHr = nTMAX; iHr >= 1; iHr--) { INTE = INTE + UHM[iHr]; iHrStrt = iHr; if (INTE > thr1) break; }
+
+    INTE = 0.0;
+    for (jHr = 1; jHr <= nTMAX; jHr++) UHQ[jHr] = 0.0;
+    for (jHr = 1; jHr <= nTMAX; jHr++) {
+        UHQ0 = 0.0;
+        for (iHr = iHrStrt; iHr <= iHrLast; iHr++) {
+            if ((jHr - iHr) > 0) {
+                if (jHr - iHr <= nTsub) UHQ0 = UHQ0 + fr[jHr - iHr] * UHM[iHr];
+            } else break;
+        }
+        UHQ[jHr] = UHQ0;
+        INTE = INTE + UHQ0;
+    }
+    if (INTE > 0.0) for (jHr = 1; jHr <= nTMAX; jHr++) UHQ[jHr] = UHQ[jHr] / INTE;
+
+    INTE = 0.0;
+    for (iHr = 1; iHr <= nTMAX; iHr++) { INTE = INTE + UHQ[iHr]; iHrLast = iHr; if (INTE > thr2) break; }
+    for (iHr = 1; iHr <= nTMAX; iHr++) UHQ[iHr] = UHQ[iHr] / INTE;
+
+    ntdh = (iHrLast + nTsub - 1) / nTsub;
+    for (k = 0; k < ntdh; k++) out[k] = 0.0;
+    for (jHr = 1; jHr <= iHrLast; jHr++) {
+        iTagg = (jHr + nTsub - 1) / nTsub;
+        out[iTagg - 1] = out[iTagg - 1] + UHQ[jHr];
+    }
+    return ntdh;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* topology helpers                                                                            */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int id, ix; } idix_t;
+static int cmp_idix(const void *a, const void *b)
+{
+    const idix_t *x = (const idix_t *)a, *y = (const idix_t *)b;
+    if (x->id != y->id) return (x->id < y->id) ? -1 : 1;
+    return (x->ix < y->ix) ? -1 : (x->ix > y->ix);
+}
+/* network_topo.f90:362-464 downReachIndex: index of the segment whose id == downId (ids <= 0 => none) */
+static void down_index(int nUp, int nSeg, const int *segId, const int *downId, int *out)
+{
+    idix_t *s = (idix_t *)malloc(sizeof(idix_t) * (nSeg > 0 ? nSeg : 1));
+    int i;
+    for (i = 0; i < nSeg; i++) { s[i].id = segId[i]; s[i].ix = i; }
+    qsort(s, nSeg, sizeof(idix_t), cmp_idix);
+    for (i = 0; i < nUp; i++) {
+        int lo = 0, hi = nSeg - 1, f = -1, id = downId[i];
+        out[i] = -1;
+        if (id <= 0) continue;
+        while (lo <= hi) { int m = (lo + hi) / 2; if (s[m].id < id) lo = m + 1; else if (s[m].id > id) hi = m - 1; else { f = m; hi = m - 1; } }
+        if (f >= 0) out[i] = s[f].ix;
+    }
+    free(s);
+}
+
+#define ALLOC(p, n) do { (p) = calloc((size_t)((n) > 0 ? (n) : 1), sizeof(*(p))); } while (0)
+
+void mro_destroy(mro_t *h);
+
+/* ------------------------------------------------------------------------------------------ */
+/* create: read_streamSeg.f90 inputs -> augment_ntopo (process_ntopo.f90:39-266) -> put_data_struct */
+/* ------------------------------------------------------------------------------------------ */
+mro_t *mro_create(int nRch, int nHRU,
+                  const int *segId, const int *downSegId,
+                  const int *hruSegId, const double *hruArea,
+                  const double *length, const double *slope,
+                  const double *width_in,      /* NULL -> wscale*sqrt(totalArea) */
+                  const double *man_n_in,      /* NULL -> mann_n */
+                  const int *islake_in,        /* NULL -> none */
+                  const int *lakeModelType_in, /* NULL -> Doll */
+                  const double *D03_MaxStorage, const double *D03_Coefficient,
+                  const double *D03_Power, const double *D03_S0,
+                  double dt, const char *route_opt,
+                  int doesBasinRoute, int hw_drain_point, double min_length_route,
+                  int is_lake_sim, int lakeRegulate, int LakeInputOption,
+                  double runoffMin, double time_conv, double length_conv,
+                  double fshape, double tscale, double velo, double diff, double mann_n, double wscale,
+                  int nThreads)
+{
+    mro_t *h = (mro_t *)calloc(1, sizeof(mro_t));
+    int i, k, m, *cnt, *hruSegIx, *indeg, *queue, qh, qt, *lev;
+    const char *c;
+    h->nRch = nRch; h->nHRU = nHRU; h->dt = dt;
+    h->doesBasinRoute = doesBasinRoute; h->hw_drain_point = hw_drain_point;
+    h->min_length_route = min_length_route; h->is_lake_sim = is_lake_sim; h->lakeRegulate = lakeRegulate;
+    h->LakeInputOption = LakeInputOption; h->runoffMin = runoffMin;
+    h->time_conv = time_conv; h->length_conv = length_conv;
+    h->fshape = fshape; h->tscale = tscale; h->velo = velo; h->diff = diff; h->mann_n = mann_n; h->wscale = wscale;
+    h->nThreads = nThreads > 0 ? nThreads : 1;
+    h->iTime = 1;
+    /* read_control.f90:583-597: digits of route_opt, in order */
+    h->nRoutes = 0;
+    for (c = route_opt; *c; c++) {
+        int id = *c - '0', mm = -1;
+        if (id == 0) mm = M_SUM; else if (id == 1) mm = M_IRF; else if (id == 2) mm = M_KWT;
+        if (mm < 0 || h->onRoute[mm]) { free(h); return NULL; }
+        h->onRoute[mm] = 1; h->routeOrder[h->nRoutes++] = mm;
+    }
+
+    ALLOC(h->segId, nRch); ALLOC(h->downSegId, nRch); ALLOC(h->downIndex, nRch);
+    memcpy(h->segId, segId, sizeof(int) * nRch); memcpy(h->downSegId, downSegId, sizeof(int) * nRch);
+    down_index(nRch, nRch, segId, downSegId, h->downIndex);
+
+    /* up2downSegment (network_topo.f90:202-311): upstream lists filled in reach-index order */
+    ALLOC(h->up_ptr, nRch + 1); ALLOC(cnt, nRch);
+    for (i = 0; i < nRch; i++) if (h->downIndex[i] >= 0) h->up_ptr[h->downIndex[i] + 1]++;
+    for (i = 0; i < nRch; i++) h->up_ptr[i + 1] += h->up_ptr[i];
+    ALLOC(h->up_idx, h->up_ptr[nRch]); ALLOC(h->goodBas, h->up_ptr[nRch]); ALLOC(h->nGood, nRch);
+    for (i = 0; i < nRch; i++) { int d = h->downIndex[i]; if (d >= 0) h->up_idx[h->up_ptr[d] + cnt[d]++] = i; }
+    free(cnt);
+
+    /* hru2segment (network_topo.f90:46-196): contributing HRUs in HRU-index order, weight = area/sum(area) */
+    ALLOC(hruSegIx, nHRU);
+    down_index(nHRU, nRch, segId, hruSegId, hruSegIx);
+    ALLOC(h->hru_ptr, nRch + 1); ALLOC(cnt, nRch);
+    for (i = 0; i < nHRU; i++) if (hruSegIx[i] >= 0) h->hru_ptr[hruSegIx[i] + 1]++;
+    for (i = 0; i < nRch; i++) h->hru_ptr[i + 1] += h->hru_ptr[i];
+    ALLOC(h->hru_idx, h->hru_ptr[nRch]); ALLOC(h->hru_wgt, h->hru_ptr[nRch]);
+    for (i = 0; i < nHRU; i++) { int s = hruSegIx[i]; if (s >= 0) h->hru_idx[h->hru_ptr[s] + cnt[s]++] = i; }
+    free(cnt); free(hruSegIx);
+
+    /* a topological order (results do not depend on which valid order is used) + level sets */
+    ALLOC(h->order, nRch); ALLOC(indeg, nRch); ALLOC(queue, nRch); ALLOC(lev, nRch);
+    for (i = 0; i < nRch; i++) indeg[i] = h->up_ptr[i + 1] - h->up_ptr[i];
+    qh = qt = 0;
+    for (i = 0; i < nRch; i++) if (indeg[i] == 0) { queue[qt++] = i; lev[i] = 0; }
+    h->nLevel = 0;
+    while (qh < qt) {
+        int r = queue[qh++], d = h->downIndex[r];
+        if (lev[r] + 1 > h->nLevel) h->nLevel = lev[r] + 1;
+        if (d >= 0) { if (lev[r] + 1 > lev[d]) lev[d] = lev[r] + 1; if (--indeg[d] == 0) queue[qt++] = d; }
+    }
+    if (qt != nRch) { snprintf(h->message, 256, "mro_create/network has a cycle"); }
+    memcpy(h->order, queue, sizeof(int) * nRch);
+    ALLOC(h->lev_ptr, h->nLevel + 1); ALLOC(h->lev_idx, nRch);
+    for (i = 0; i < qt; i++) h->lev_ptr[lev[queue[i]] + 1]++;
+    for (k = 0; k < h->nLevel; k++) h->lev_ptr[k + 1] += h->lev_ptr[k];
+    ALLOC(cnt, h->nLevel);
+    for (i = 0; i < qt; i++) { int r = queue[i]; h->lev_idx[h->lev_ptr[lev[r]] + cnt[lev[r]]++] = r; }
+    free(cnt); free(indeg); free(lev);
+
+    /* reach_list (network_topo.f90:637-779): basArea, upsArea, totalArea, goodBas */
+    ALLOC(h->RLENGTH, nRch); ALLOC(h->R_SLOPE, nRch); ALLOC(h->R_WIDTH, nRch); ALLOC(h->R_MAN_N, nRch);
+    ALLOC(h->BASAREA, nRch); ALLOC(h->UPSAREA, nRch); ALLOC(h->TOTAREA, nRch);
+    for (k = 0; k < qt; k++) {
+        int r = queue[k]; double ups = 0.0, bas = 0.0;
+        for (m = h->up_ptr[r]; m < h->up_ptr[r + 1]; m++) ups = ups + h->TOTAREA[h->up_idx[m]];
+        for (m = h->hru_ptr[r]; m < h->hru_ptr[r + 1]; m++) bas += hruArea[h->hru_idx[m]];
+        h->UPSAREA[r] = ups; h->BASAREA[r] = bas; h->TOTAREA[r] = bas + ups;
+        for (m = h->hru_ptr[r]; m < h->hru_ptr[r + 1]; m++) h->hru_wgt[m] = hruArea[h->hru_idx[m]] / bas;
+        h->nGood[r] = 0;
+        for (m = h->up_ptr[r]; m < h->up_ptr[r + 1]; m++) { h->goodBas[m] = (h->TOTAREA[r] > VERYSMALL); h->nGood[r] += h->goodBas[m]; }
+    }
+    free(queue);
+
+    /* geometry (process_ntopo.f90:176-187) and put_data_struct (process_ntopo.f90:359-366) */
+    for (i = 0; i < nRch; i++) {
+        h->RLENGTH[i] = length[i];
+        h->R_SLOPE[i] = fmax(slope[i], MIN_SLOPE);
+        h->R_WIDTH[i] = width_in ? width_in[i] : wscale * sqrt(h->TOTAREA[i]);
+        h->R_MAN_N[i] = man_n_in ? man_n_in[i] : mann_n;
+    }
+    /* lakes (process_ntopo.f90:476-485; network_topo.f90:958-985) */
+    ALLOC(h->isLake, nRch); ALLOC(h->lakeInlet, nRch); ALLOC(h->lakeModelType, nRch);
+    ALLOC(h->D03_MaxStorage, nRch); ALLOC(h->D03_Coefficient, nRch); ALLOC(h->D03_Power, nRch); ALLOC(h->D03_S0, nRch);
+    if (is_lake_sim) {
+        for (i = 0; i < nRch; i++) {
+            h->isLake[i] = islake_in ? (islake_in[i] == 1) : 0;
+            h->lakeModelType[i] = (!lakeRegulate || !lakeModelType_in) ? LAKE_DOLL03 : lakeModelType_in[i];
+            if (D03_MaxStorage) h->D03_MaxStorage[i] = D03_MaxStorage[i];
+            if (D03_Coefficient) h->D03_Coefficient[i] = D03_Coefficient[i];
+            if (D03_Power) h->D03_Power[i] = D03_Power[i];
+            if (D03_S0) h->D03_S0[i] = D03_S0[i];
+        }
+        for (i = 0; i < nRch; i++) { int d = h->downIndex[i]; h->lakeInlet[i] = (d >= 0 && h->isLake[d]); }
+    }
+
+    /* unit hydrographs */
+    if (make_basin_uh(dt, fshape, tscale, &h->ntdh_bas, &h->FRAC_FUTURE) != 0) { mro_destroy(h); return NULL; }
+    ALLOC(h->uh_ptr, nRch + 1);
+    if (h->onRoute[M_IRF]) {
+        double tmp[256]; int tot = 0;
+        for (i = 0; i < nRch; i++) { int n = make_uh_one(length[i], dt, velo, diff, tmp); h->uh_ptr[i + 1] = n; tot += n; if (n > h->maxtdh) h->maxtdh = n; }
+        for (i = 0; i < nRch; i++) h->uh_ptr[i + 1] += h->uh_ptr[i];
+        ALLOC(h->uh_val, tot); ALLOC(h->QFUTURE_IRF, tot);
+        for (i = 0; i < nRch; i++) {
+            int n = make_uh_one(length[i], dt, velo, diff, tmp);
+            /* process_ntopo.f90:496-499: lake UH is an impulse (islake is only set when is_lake_sim) */
+            if (h->isLake[i]) { for (k = 0; k < n; k++) tmp[k] = 0.0; tmp[0] = 1.0; }
+            memcpy(h->uh_val + h->uh_ptr[i], tmp, sizeof(double) * n);
+        }
+    }
+
+    /* cold start (init_model_data.f90:399-463,600) */
+    ALLOC(h->BASIN_QI, nRch); ALLOC(h->BASIN_QR0, nRch); ALLOC(h->BASIN_QR1, nRch);
+    ALLOC(h->QFUTURE, (size_t)nRch * h->ntdh_bas); ALLOC(h->qfuture_alloc, nRch);
+    ALLOC(h->reachRunoff, nRch);
+    for (m = 0; m < N_METHOD; m++) {
+        ALLOC(h->REACH_Q[m], nRch); ALLOC(h->REACH_VOL0[m], nRch); ALLOC(h->REACH_VOL1[m], nRch);
+        ALLOC(h->REACH_INFLOW[m], nRch); ALLOC(h->WB[m], nRch);
+    }
+    ALLOC(h->KW, nRch);
+    if (h->onRoute[M_KWT] && is_lake_sim)
+        for (i = 0; i < nRch; i++) if (h->isLake[i]) {
+            kwave_t *w = &h->KW[i]; w->n = 1; w->QF[0] = -9999; w->TI[0] = -9999; w->TR[0] = -9999; w->RF[0] = 0;
+        }
+    return h;
+}
+
+void mro_destroy(mro_t *h)
+{
+    int m;
+    if (!h) return;
+    free(h->segId); free(h->downSegId); free(h->downIndex); free(h->up_ptr); free(h->up_idx); free(h->goodBas); free(h->nGood);
+    free(h->hru_ptr); free(h->hru_idx); free(h->hru_wgt); free(h->order); free(h->lev_ptr); free(h->lev_idx);
+    free(h->RLENGTH); free(h->R_SLOPE); free(h->R_WIDTH); free(h->R_MAN_N); free(h->BASAREA); free(h->UPSAREA); free(h->TOTAREA);
+    free(h->isLake); free(h->lakeInlet); free(h->lakeModelType);
+    free(h->D03_MaxStorage); free(h->D03_Coefficient); free(h->D03_Power); free(h->D03_S0);
+    free(h->FRAC_FUTURE); free(h->uh_ptr); free(h->uh_val);
+    free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff);
+    for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]); }
+    free(h->QFUTURE_IRF); free(h->KW);
+    free(h);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* process_remap.f90:319-422 basin2reach                                                       */
+/* ------------------------------------------------------------------------------------------ */
+static int basin2reach(mro_t *h, const double *basinRunoff, double *reachRunoff, int limit)
+{
+    int j, ierr = 0;
+#pragma omp parallel for schedule(static) num_threads(h->nThreads) reduction(max : ierr)
+    for (j = 0; j < h->nRch; j++) {
+        int m, nContrib = h->hru_ptr[j + 1] - h->hru_ptr[j];
+        if (nContrib > 0) {
+            double r = 0.0;
+            for (m = h->hru_ptr[j]; m < h->hru_ptr[j + 1]; m++) {
+                double ro = basinRunoff[h->hru_idx[m]];
+                if (limit && ro < NEG_RUNOFF_TOL) ierr = 20;
+                r = r + h->hru_wgt[m] * ro * h->time_conv * h->length_conv;
+            }
+            if (limit && r < h->runoffMin) r = h->runoffMin;
+            reachRunoff[j] = r * h->BASAREA[j];
+        } else {
+            if (limit) reachRunoff[j] = h->runoffMin;
+        }
+    }
+    if (ierr) snprintf(h->message, 256, "basin2reach/exceeded negative runoff tolerance");
+    return ierr;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* basinUH.f90:70-178 hru_irf + irf_conv                                                       */
+/* ------------------------------------------------------------------------------------------ */
+static void hru_irf(mro_t *h, int j)
+{
+    int n = h->ntdh_bas, k; double *qf = h->QFUTURE + (size_t)j * n; double inq = h->BASIN_QI[j];
+    int lake = (h->isLake[j] && h->is_lake_sim);
+    h->BASIN_QR0[j] = h->BASIN_QR1[j];
+    for (k = 0; k < n; k++) {
+        double uh = lake ? (k == 0 ? 1.0 : 0.0) : h->FRAC_FUTURE[k];
+        qf[k] = qf[k] + uh * inq;
+    }
+    h->BASIN_QR1[j] = qf[0];
+    for (k = 1; k < n; k++) qf[k - 1] = qf[k];
+    qf[n - 1] = 0.0;
+}
+
+/* water_balance.f90:61-87 (REACH_WM_FLUX = 0; precip/evap = 0 unless LakeInputOption uses them) */
+static void comp_reach_wb(mro_t *h, int m, int j, double Qupstream, double Qlat)
+{
+    double dt = h->dt;
+    double dVol = h->REACH_VOL1[m][j] - h->REACH_VOL0[m][j];
+    double Qin = Qupstream * dt, Qlateral = Qlat * dt, precip = 0.0, evapo = 0.0;
+    double Qout = -1.0 * h->REACH_Q[m][j] * dt;
+    double Qtake_actual = -1.0 * 0.0 * dt;
+    h->WB[m][j] = dVol - (Qin + Qlateral + precip + Qtake_actual + Qout + evapo);
+}
+
+/* accum_runoff.f90:60-75 */
+static int accum_inst_runoff(mro_t *h, int j)
+{
+    int m; double q_upstream = 0.0;
+    h->REACH_Q[M_SUM][j] = h->BASIN_QR1[j];
+    if (h->up_ptr[j + 1] > h->up_ptr[j]) {
+        for (m = h->up_ptr[j]; m < h->up_ptr[j + 1]; m++) q_upstream = q_upstream + h->REACH_Q[M_SUM][h->up_idx[m]];
+        h->REACH_Q[M_SUM][j] = h->REACH_Q[M_SUM][j] + q_upstream;
+    }
+    return 0;
+}
+
+/* irf_route.f90:40-264 */
+static int irf_rch(mro_t *h, int j)
+{
+    const int M = M_IRF;
+    int nUps = h->nGood[j], m, k, ntdh; double q_upstream = 0.0, Qlat = 0.0, dt = h->dt;
+    double *QF = h->QFUTURE_IRF + h->uh_ptr[j]; const double *UH = h->uh_val + h->uh_ptr[j];
+    h->REACH_VOL0[M][j] = h->REACH_VOL1[M][j];
+    if (nUps > 0) {
+        for (k = 0; k < nUps; k++) {
+            m = h->up_ptr[j] + k;
+            if (!h->goodBas[m]) continue;
+            q_upstream = q_upstream + h->REACH_Q[M][h->up_idx[m]];
+        }
+        Qlat = h->BASIN_QR1[j];
+    } else {
+        if (h->hw_drain_point == 1) { q_upstream = q_upstream + h->BASIN_QR1[j]; Qlat = 0.0; }
+        else if (h->hw_drain_point == 2) { Qlat = h->BASIN_QR1[j]; }
+    }
+    h->REACH_INFLOW[M][j] = q_upstream;
+    ntdh = h->uh_ptr[j + 1] - h->uh_ptr[j];
+    if (h->RLENGTH[j] > h->min_length_route) {
+        for (k = 0; k < ntdh; k++) QF[k] = QF[k] + UH[k] * q_upstream;
+        QF[0] = fmin((fmax(0.0, h->REACH_VOL1[M][j]) / dt + q_upstream) * 0.999, QF[0]);
+        h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] - (QF[0] - q_upstream) * dt;
+        h->REACH_Q[M][j] = QF[0] + Qlat;
+        for (k = 1; k < ntdh; k++) QF[k - 1] = QF[k];
+        QF[ntdh - 1] = 0.0;
+    } else {
+        for (k = 0; k < ntdh; k++) QF[k] = 0.0;
+        QF[0] = q_upstream;
+        h->REACH_Q[M][j] = QF[0] + Qlat;
+        h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0;
+    }
+    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    return 0;
+}
+
+/* lake_route.f90:28-229,466-470 (endorheic and Doll03; LakeTargVol / WM / H06 / HYPE not restated) */
+static int lake_route(mro_t *h, int j, int M)
+{
+    int m; double q_upstream = 0.0, dt = h->dt, *V1 = &h->REACH_VOL1[M][j], *Q = &h->REACH_Q[M][j];
+    for (m = h->up_ptr[j]; m < h->up_ptr[j + 1]; m++) q_upstream = q_upstream + h->REACH_Q[M][h->up_idx[m]];
+    if (h->iTime == 1) {   /* cold start (isColdStart = T) */
+        switch (h->lakeModelType[j]) {
+            case LAKE_ENDORHEIC: *V1 = h->D03_S0[j]; break;
+            case LAKE_DOLL03:    *V1 = h->D03_MaxStorage[j]; break;
+            default: snprintf(h->message, 256, "lake_route/lake model type not restated in oracle"); return 20;
+        }
+    }
+    h->REACH_VOL0[M][j] = *V1;
+    *V1 = *V1 + q_upstream * dt;
+    if (h->LakeInputOption == 1 || h->LakeInputOption == 2) *V1 = *V1 + h->BASIN_QR1[j] * dt;
+    if (h->LakeInputOption == 0 || h->LakeInputOption == 2) {
+        /* basinprecip = basinevapo = 0 in this restatement (no evap/precip forcing) */
+        *V1 = *V1 + 0.0 * dt;
+        if (*V1 > 0.0 * dt) *V1 = *V1 - 0.0 * dt; else *V1 = 0.0;
+    }
+    switch (h->lakeModelType[j]) {
+        case LAKE_ENDORHEIC: *Q = 0.0; break;
+        case LAKE_DOLL03:
+            if ((*V1 - h->D03_S0[j]) > 0)
+                *Q = h->D03_Coefficient[j] * (*V1 - h->D03_S0[j]) *
+                     pow((*V1 - h->D03_S0[j]) / (h->D03_MaxStorage[j] - h->D03_S0[j]), h->D03_Power[j]);
+            else *Q = 0;
+            *Q = *Q / SECPRDAY;
+            *Q = fmin(*Q, *V1 / dt);
+            *V1 = *V1 - *Q * dt;
+            break;
+        default: snprintf(h->message, 256, "lake_route/lake model type not restated in oracle"); return 20;
+    }
+    /* lake_route does not touch REACH_INFLOW */
+    comp_reach_wb(h, M, j, q_upstream, h->BASIN_QR1[j]);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* kwt_route.f90                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { double *Q, *T, *X; int n, cap; } wave_buf_t;   /* Q_JRCH, TENTRY, T_EXIT (0:n-1) */
+
+static void wb_reserve(wave_buf_t *b, int n)
+{
+    if (n > b->cap) {
+        int c = b->cap ? b->cap : 64; while (c < n) c *= 2;
+        b->Q = (double *)realloc(b->Q, sizeof(double) * c); b->T = (double *)realloc(b->T, sizeof(double) * c);
+        b->X = (double *)realloc(b->X, sizeof(double) * c); b->cap = c;
+    }
+}
+
+/* kwt_route.f90:1444-1622, one output interval [T0,T1]; TOLD/QOLD are 1-based (NOLD entries) */
+static int interp_rch(const double *TOLD1, const double *QOLD1, int NOLD, double T0, double T1, double *QNEW)
+{
+    const double *TOLD = TOLD1 - 1, *QOLD = QOLD1 - 1;   /* 1-based views */
+    int IBEG, IEND, IMID, i; double AREAB = 0.0, AREAE = 0.0, AREAM = 0.0, SLOPE, QEST0, QEST1;
+    if (TOLD[1] > T0 || TOLD[NOLD] < T1) return 1;
+    IBEG = 1;
+    for (i = 2; i <= NOLD; i++) if (T0 <= TOLD[i]) { IBEG = i; break; }
+    IEND = 1;
+    for (i = 1; i <= NOLD; i++) if (T1 <= TOLD[i]) { IEND = i; break; }
+    if (T1 < TOLD[IBEG]) {
+        SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+        QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+        QEST1 = SLOPE * (T1 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+        *QNEW = 0.5 * (QEST0 + QEST1);
+        return 0;
+    }
+    if (T0 < TOLD[IBEG]) {
+        SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+        QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+        AREAB = (TOLD[IBEG] - T0) * 0.5 * (QEST0 + QOLD[IBEG]);
+    }
+    if (T1 < TOLD[IEND]) {
+        SLOPE = (QOLD[IEND] - QOLD[IEND - 1]) / (TOLD[IEND] - TOLD[IEND - 1]);
+        QEST1 = SLOPE * (T1 - TOLD[IEND - 1]) + QOLD[IEND - 1];
+        AREAE = (T1 - TOLD[IEND - 1]) * 0.5 * (QOLD[IEND - 1] + QEST1);
+    }
+    if (IBEG < IEND) {
+        for (IMID = IBEG + 1; IMID <= IEND; IMID++) {
+            if (IMID < IEND || (IMID == IEND && T1 == TOLD[IEND] && T0 < TOLD[IEND - 1]))
+                AREAM = AREAM + (TOLD[IMID] - TOLD[IMID - 1]) * 0.5 * (QOLD[IMID - 1] + QOLD[IMID]);
+        }
+    }
+    *QNEW = (AREAB + AREAE + AREAM) / (T1 - T0);
+    return 0;
+}
+
+/* kwt_route.f90:999-1123 */
+static double rm_interp(double T0, double Q1, double Q2, double T1, double T2)
+{
+    return Q1 + ((Q2 - Q1) / (T2 - T1)) * (T0 - T1);
+}
+static int remove_rch(wave_buf_t *b)
+{
+    int NPRT = b->n - 1, IPRT, MPRT, i, k, ISEL;
+    double *Q, *T, *Z, *ABSERR; unsigned char *PARFLG; int *INDEX1;
+#pragma omp atomic
+    g_cnt[0]++;
+    if (b->n > g_cnt[4]) g_cnt[4] = b->n;
+    Q = (double *)malloc(sizeof(double) * b->n); T = (double *)malloc(sizeof(double) * b->n);
+    Z = (double *)malloc(sizeof(double) * b->n); ABSERR = (double *)malloc(sizeof(double) * b->n);
+    PARFLG = (unsigned char *)malloc(b->n);
+    INDEX1 = (int *)malloc(sizeof(int) * b->n);
+    memcpy(Q, b->Q, sizeof(double) * b->n); memcpy(T, b->T, sizeof(double) * b->n); memcpy(Z, b->X, sizeof(double) * b->n);
+    for (i = 0; i <= NPRT; i++) { PARFLG[i] = 1; ABSERR[i] = HUGE_DP; }
+    for (IPRT = 1; IPRT <= NPRT - 1; IPRT++)
+        ABSERR[IPRT] = fabs(rm_interp(T[IPRT], Q[IPRT - 1], Q[IPRT + 1], T[IPRT - 1], T[IPRT + 1]) - Q[IPRT]);
+    for (;;) {
+        double emin;
+        MPRT = -1;
+        for (i = 0; i <= NPRT; i++) if (PARFLG[i]) INDEX1[++MPRT] = i;   /* INDEX1(0:MPRT) = pack(INDEX0,PARFLG) */
+        if (MPRT < MAXQPAR) break;
+        ISEL = 0; emin = ABSERR[INDEX1[0]];
+        for (k = 1; k <= MPRT; k++) if (ABSERR[INDEX1[k]] < emin) { emin = ABSERR[INDEX1[k]]; ISEL = k; }   /* minloc: first minimum */
+        if (INDEX1[ISEL - 1] > 0) {
+            int INEG = INDEX1[ISEL - 2], IMID = INDEX1[ISEL - 1], IPOS = INDEX1[ISEL + 1];
+            ABSERR[IMID] = fabs(rm_interp(T[IMID], Q[INEG], Q[IPOS], T[INEG], T[IPOS]) - Q[IMID]);
+        }
+        if (INDEX1[ISEL + 1] < NPRT) {
+            int INEG = INDEX1[ISEL - 1], IMID = INDEX1[ISEL + 1], IPOS = INDEX1[ISEL + 2];
+            ABSERR[IMID] = fabs(rm_interp(T[IMID], Q[INEG], Q[IPOS], T[INEG], T[IPOS]) - Q[IMID]);
+        }
+        PARFLG[INDEX1[ISEL]] = 0;
+    }
+    for (k = 0; k <= MPRT; k++) { b->Q[k] = Q[INDEX1[k]]; b->T[k] = T[INDEX1[k]]; b->X[k] = Z[INDEX1[k]]; }
+    b->n = MPRT + 1;
+    free(Q); free(T); free(Z); free(ABSERR); free(PARFLG); free(INDEX1);
+    return 0;
+}
+
+/* kwt_route.f90:1130-1439.  Arrays are the 1-based slices Q_JRCH(1:NQ1) etc. */
+static int kinwav_rch(mro_t *h, int JRCH, double T_START, double T_END,
+                      double *Q_JRCH1, double *TENTRY1, double *T_EXIT1, unsigned char *FROUTE1, int NQ1, int *NQ2)
+{
+    double *Q_JRCH = Q_JRCH1 - 1, *TENTRY = TENTRY1 - 1, *T_EXIT = T_EXIT1 - 1; unsigned char *FROUTE = FROUTE1 - 1;
+    enum { CAP = 64 };
+    int IX[CAP], MF[CAP]; double T0[CAP], T1[CAP], Q0[CAP], Q1[CAP], Q2[CAP], WC[CAP];
+    double ALFA, K, XMX, X, XB, WDIFF, XXB, A1, A2, CM, TEXIT, TNEXT = 0.0, TEXIT2;
+    int NN, NI, IW, JW, IXB = 0, JXB, IROUTE, JROUTE, ICOUNT, i;
+    double p1, p2;
+
+    *NQ2 = 0;
+    if (NQ1 + 2 > CAP) { snprintf(h->message, 256, "kinwav_rch/oracle scratch too small"); return 60; }
+    ALFA = 5.0 / 3.0;
+    K = sqrt(h->R_SLOPE[JRCH]) / h->R_MAN_N[JRCH];
+    XMX = h->RLENGTH[JRCH];
+    NN = NQ1; NI = NN;
+    if (NN == 0) return 0;
+    for (i = 1; i <= NI; i++) { MF[i] = i; IX[i] = i; Q0[i] = Q1[i] = Q2[i] = Q_JRCH[i]; T0[i] = T1[i] = TENTRY[i]; }
+    p1 = 1.0 / ALFA; p2 = (ALFA - 1.0) / ALFA;
+    for (i = 1; i <= NN; i++) WC[i] = ALFA * pow(K, p1) * pow(Q1[i], p2);
+
+    if (NN > 1) {
+        X = 0.0;
+        for (;;) {
+            XB = XMX;
+            for (IW = 2; IW <= NN; IW++) {
+                JW = IW - 1;
+                if (WC[IW] == 0.0 || WC[JW] == 0.0) continue;
+                WDIFF = 1.0 / WC[JW] - 1.0 / WC[IW];
+                if (WDIFF == 0.0) continue;
+                if (WC[IW] == WC[JW]) continue;
+                XXB = (T1[IW] - T1[JW]) / WDIFF;
+                if (XXB < X || XXB > XB) continue;
+                XB = XXB; IXB = IW;
+            }
+            if (XB == XMX) break;
+#pragma omp atomic
+            g_cnt[1]++;
+            NN = NN - 1;
+            JXB = IXB - 1;
+            Q2[JXB] = fmax(Q2[JXB], Q2[IXB]);
+            Q1[JXB] = fmin(Q1[JXB], Q1[IXB]);
+            A2 = pow(Q2[JXB] / K, p1);
+            A1 = pow(Q1[JXB] / K, p1);
+            CM = (Q2[JXB] - Q1[JXB]) / (A2 - A1);
+            T1[JXB] = T1[JXB] + XB / WC[JXB] - XB / CM;
+            WC[JXB] = CM;
+            for (i = IX[IXB]; i <= NI; i++) MF[i] = MF[i] - 1;
+            for (i = IXB; i <= NN; i++) { IX[i] = IX[i + 1]; T1[i] = T1[i + 1]; WC[i] = WC[i + 1]; Q1[i] = Q1[i + 1]; Q2[i] = Q2[i + 1]; }
+            X = XB;
+        }
+    }
+
+    ICOUNT = 0;
+#define RUPDATE(QNEW_, TOLD_, TNEW_) do { \
+        ICOUNT = ICOUNT + 1; \
+        if (ICOUNT > NQ1) { snprintf(h->message, 256, "kinwav_rch/RUPDATE/array bounds exceeded"); return 60; } \
+        Q_JRCH[ICOUNT] = (QNEW_); TENTRY[ICOUNT] = (TOLD_); T_EXIT[ICOUNT] = (TNEW_); \
+        if (ICOUNT > 1) { if (T_EXIT[ICOUNT] <= T_EXIT[ICOUNT - 1]) T_EXIT[ICOUNT] = T_EXIT[ICOUNT - 1] + 1.0; } \
+        if (ICOUNT == 1 && T_EXIT[ICOUNT] <= T_START) T_EXIT[ICOUNT] = T_START + 1.0; \
+        if (T_EXIT[ICOUNT] < T_END) FROUTE[ICOUNT] = 1; \
+    } while (0)
+
+    for (IROUTE = 1; IROUTE <= NN; IROUTE++) {
+        if (WC[IROUTE] < VERYSMALL) { snprintf(h->message, 256, "kinwav_rch/zero flow for reach id %d", h->segId[JRCH]); return 20; }
+        TEXIT = fmin(XMX / WC[IROUTE] + T1[IROUTE], HUGE_DP);
+        if (IROUTE < NN) TNEXT = fmin(XMX / WC[IROUTE + 1] + T1[IROUTE + 1], HUGE_DP);
+        if (IROUTE == NN) TNEXT = HUGE_DP;
+        if (Q1[IROUTE] != Q2[IROUTE]) {
+            if (TEXIT < T_END) {
+                TEXIT2 = fmin(TEXIT + 1.0, TEXIT + 0.5 * (fmin(TNEXT, T_END) - TEXIT));
+                if (TEXIT2 == TEXIT) { snprintf(h->message, 256, "kinwav_rch/TEXIT equals TEXIT2 in kinwav"); return 30; }
+#pragma omp atomic
+                g_cnt[2]++;
+                RUPDATE(Q1[IROUTE], T1[IROUTE], TEXIT);
+                RUPDATE(Q2[IROUTE], T1[IROUTE], TEXIT2);
+            } else {
+#pragma omp atomic
+                g_cnt[3]++;
+                for (JROUTE = 1; JROUTE <= NI; JROUTE++)
+                    if (MF[JROUTE] == IROUTE) RUPDATE(Q0[JROUTE], T0[JROUTE], TEXIT);
+            }
+        } else {
+            RUPDATE(Q1[IROUTE], T1[IROUTE], TEXIT);
+        }
+    }
+#undef RUPDATE
+    *NQ2 = ICOUNT;
+    return 0;
+}
+
+/* kwt_route.f90:619-993 */
+typedef struct { const double *QF, *TR; const unsigned char *RF; int n; double basQF[2], basTR[2]; unsigned char basRF[2]; } series_t;
+
+static int qexmul_rch(mro_t *h, int JRCH, double T0, double T1, wave_buf_t *out, int base /* write QD,TD at out[base..] */, int *ND)
+{
+    int NUPB, NUPR = 0, NUPS, IUPS, INDX, MUPR, IR, IUPR, IMAX, IPRT, JUPS, JUPS_OLD, ITIM_OLD, IWAV, IBEG, IEND, nDone, i;
+    double DT = T1 - T0, TIME_OLD, Q_AGG, SCFAC, SFLOW, SLOPE, PREDV;
+    series_t *US; double *UWIDTH, *CTIME; int *ITIM; unsigned char *MFLG;
+    kwave_t *snap;   /* copies of the upstream waves taken before they are stripped (USFLOW) */
+
+    *ND = 0;
+    if (h->nGood[JRCH] == 0) return 0;
+    NUPB = h->up_ptr[JRCH + 1] - h->up_ptr[JRCH];
+    for (IUPS = 0; IUPS < NUPB; IUPS++) { INDX = h->up_idx[h->up_ptr[JRCH] + IUPS]; MUPR = h->nGood[INDX]; if (MUPR > 0) NUPR++; }
+    NUPS = NUPB + NUPR;
+
+    if (NUPS == 1) {   /* one upstream basin that is a headwater */
+        IR = h->up_idx[h->up_ptr[JRCH]];
+        wb_reserve(out, base + 1);
+        out->Q[base] = h->BASIN_QR1[IR] / h->R_WIDTH[JRCH];
+        out->T[base] = T1;
+        *ND = 1;
+        return 0;
+    }
+
+    US = (series_t *)calloc(NUPS, sizeof(series_t)); UWIDTH = (double *)malloc(sizeof(double) * NUPS);
+    CTIME = (double *)malloc(sizeof(double) * NUPS); ITIM = (int *)malloc(sizeof(int) * NUPS);
+    MFLG = (unsigned char *)calloc(NUPS, 1); snap = (kwave_t *)malloc(sizeof(kwave_t) * (NUPR > 0 ? NUPR : 1));
+    IMAX = NUPB;
+    for (IUPS = 0; IUPS < NUPB; IUPS++) {
+        series_t *s = &US[IUPS];
+        IR = h->up_idx[h->up_ptr[JRCH] + IUPS];
+        s->basQF[0] = h->BASIN_QR0[IR]; s->basQF[1] = h->BASIN_QR1[IR];
+        s->basTR[0] = T0; s->basTR[1] = T1; s->basRF[0] = s->basRF[1] = 1;
+        s->QF = s->basQF; s->TR = s->basTR; s->RF = s->basRF; s->n = 2;
+        UWIDTH[IUPS] = 1.0;
+        CTIME[IUPS] = s->TR[1];
+    }
+    IUPR = 0;
+    for (IUPS = 0; IUPS < NUPB; IUPS++) {
+        INDX = h->up_idx[h->up_ptr[JRCH] + IUPS];
+        MUPR = h->nGood[INDX];
+        if (MUPR > 0) {
+            kwave_t *w = &h->KW[INDX]; int NS, NR = 0, NQ; series_t *s;
+            IUPR = IUPR + 1;
+            IR = INDX;
+            NS = w->n;
+            if (NS == 0) { snprintf(h->message, 256, "qexmul_rch/RCHSTA_out%%LKW_ROUTE%%KWAVE is not associated"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 20; }
+            for (i = 0; i < NS; i++) NR += w->RF[i];
+            NQ = (NR + 1 < NS) ? NR + 1 : NS;
+            snap[IUPR - 1] = *w;
+            s = &US[NUPB + IUPR - 1];
+            s->QF = snap[IUPR - 1].QF; s->TR = snap[IUPR - 1].TR; s->RF = snap[IUPR - 1].RF; s->n = NQ;
+            /* remove the routed particles from the upstream reach: KWAVE(0:NS-NR) = NEW_WAVE(NR-1:NS-1) */
+            {
+                int nn = NS - NR + 1, k;
+                if (NR - 1 < 0) { snprintf(h->message, 256, "qexmul_rch/upstream wave has no routed element"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 20; }
+                for (k = 0; k < nn; k++) { w->QF[k] = snap[IUPR - 1].QF[NR - 1 + k]; w->TI[k] = snap[IUPR - 1].TI[NR - 1 + k]; w->TR[k] = snap[IUPR - 1].TR[NR - 1 + k]; w->RF[k] = snap[IUPR - 1].RF[NR - 1 + k]; }
+                w->n = nn;
+            }
+            UWIDTH[NUPB + IUPR - 1] = h->R_WIDTH[IR];
+            CTIME[NUPB + IUPR - 1] = s->TR[1];
+            IMAX = IMAX + (NR - 1);
+        }
+    }
+
+    wb_reserve(out, base + IMAX + 1);
+    IPRT = 0;
+    for (i = 0; i < NUPS; i++) ITIM[i] = 1;
+    JUPS_OLD = 0x7fffffff; ITIM_OLD = 0x7fffffff;
+    for (;;) {
+        JUPS = 0; for (i = 1; i < NUPS; i++) if (CTIME[i] < CTIME[JUPS]) JUPS = i;   /* MINLOC: first minimum */
+        if (JUPS == JUPS_OLD && ITIM[JUPS] == ITIM_OLD) { snprintf(h->message, 256, "qexmul_rch/stuck in the continuous do-loop"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 20; }
+        JUPS_OLD = JUPS; ITIM_OLD = ITIM[JUPS];
+        if (!MFLG[JUPS]) {
+            if (!US[JUPS].RF[ITIM[JUPS]]) {
+                MFLG[JUPS] = 1; CTIME[JUPS] = HUGE_DP;
+            } else {
+                if (IPRT >= 1) TIME_OLD = out->T[base + IPRT - 1]; else TIME_OLD = -HUGE_DP;
+                if (CTIME[JUPS] < TIME_OLD) { snprintf(h->message, 256, "qexmul_rch/expect process in order of time"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 30; }
+                if (CTIME[JUPS] != TIME_OLD) {
+                    Q_AGG = 0.0;
+                    for (IUPS = 0; IUPS < NUPS; IUPS++) {
+                        const series_t *s = &US[IUPS];
+                        IWAV = ITIM[IUPS];
+                        SCFAC = UWIDTH[IUPS] / h->R_WIDTH[JRCH];
+                        if (IUPS == JUPS) {
+                            SFLOW = s->QF[IWAV] * SCFAC;
+                        } else {
+                            IBEG = IWAV; if (s->TR[IBEG] >= CTIME[JUPS]) IBEG = IWAV - 1;
+                            IEND = IBEG + 1;
+                            if (IBEG < 0 || IEND >= s->n) { snprintf(h->message, 256, "qexmul_rch/bracket beyond series"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 40; }
+                            if (s->TR[IEND] < CTIME[JUPS] || s->TR[IBEG] > CTIME[JUPS]) { snprintf(h->message, 256, "qexmul_rch/the times are not ordered as we assume"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 40; }
+                            SLOPE = (s->QF[IEND] - s->QF[IBEG]) / (s->TR[IEND] - s->TR[IBEG]);
+                            PREDV = s->QF[IBEG] + SLOPE * (CTIME[JUPS] - s->TR[IBEG]);
+                            SFLOW = PREDV * SCFAC;
+                        }
+                        Q_AGG = Q_AGG + SFLOW;
+                    }
+                    IPRT = IPRT + 1;
+                    if (IPRT > IMAX) { snprintf(h->message, 256, "qexmul_rch/QD_TEMP bounds exceeded"); free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap); return 60; }
+                    out->Q[base + IPRT - 1] = Q_AGG;
+                    out->T[base + IPRT - 1] = CTIME[JUPS];
+                } else {
+#pragma omp atomic
+                    g_cnt[5]++;
+                }
+                if (ITIM[JUPS] == US[JUPS].n - 1) { MFLG[JUPS] = 1; CTIME[JUPS] = HUGE_DP; }
+                else { ITIM[JUPS] = ITIM[JUPS] + 1; CTIME[JUPS] = US[JUPS].TR[ITIM[JUPS]]; }
+            }
+        }
+        nDone = 0; for (i = 0; i < NUPS; i++) nDone += MFLG[i];
+        if (nDone == NUPS) break;
+    }
+    free(US); free(UWIDTH); free(CTIME); free(ITIM); free(MFLG); free(snap);
+    *ND = IPRT;
+    (void)DT;
+    return 0;
+}
+
+/* kwt_route.f90:461-613 */
+static int getusq_rch(mro_t *h, int JRCH, double T0, double T1, wave_buf_t *b)
+{
+    double DT = T1 - T0; int ND = 0, NJ, ierr, i; kwave_t *w = &h->KW[JRCH];
+    /* own entries go first, so reserve their place after we know the (pre-existing) size; a cold
+       start has exactly one own entry that is defined from QD(1) */
+    int nOwn = w->n > 0 ? w->n : 1;
+    int isUpLake = 0, iUp = -1, nUps = h->up_ptr[JRCH + 1] - h->up_ptr[JRCH];
+    wb_reserve(b, nOwn + 1);
+    if (h->is_lake_sim) {
+        for (i = 0; i < nUps; i++) { int u = h->up_idx[h->up_ptr[JRCH] + i]; if (h->isLake[u]) { isUpLake = 1; iUp = u; } }
+        if (isUpLake && nUps > 1) { snprintf(h->message, 256, "getusq_rch/lake outlet reach should have one upstream lake"); return 10; }
+    }
+    if (isUpLake) {
+        ND = 1;
+        b->Q[nOwn] = h->REACH_Q[M_KWT][iUp] / h->R_WIDTH[JRCH];
+        b->T[nOwn] = T1;
+    } else {
+        ierr = qexmul_rch(h, JRCH, T0, T1, b, nOwn, &ND);
+        if (ierr) return ierr;
+    }
+    if (w->n == 0) {   /* cold start, kwt_route.f90:587-596 */
+        w->n = 1; w->QF[0] = b->Q[nOwn]; w->TI[0] = T0 - DT; w->TR[0] = T0; w->RF[0] = 1;
+    }
+    NJ = w->n - 1;
+    for (i = 0; i <= NJ; i++) { b->Q[i] = w->QF[i]; b->T[i] = w->TI[i]; b->X[i] = w->TR[i]; }
+    for (i = 0; i < ND; i++) b->X[NJ + 1 + i] = -9999.0;
+    b->n = NJ + 1 + ND;
+    return 0;
+}
+
+/* kwt_route.f90:36-346 */
+static int kwt_rch(mro_t *h, int j, double T0, double T1, wave_buf_t *b)
+{
+    const int M = M_KWT;
+    int NUPS = h->nGood[j], ierr, i, k, NQ1, NQ2, NR, NN; kwave_t *w = &h->KW[j];
+    double q_upstream, T_START, T_END, QNEW, Q_END, TIMEI; unsigned char FROUTE[64];
+    if (NUPS > 0) {
+        ierr = getusq_rch(h, j, T0, T1, b);
+        if (ierr) return ierr;
+        for (i = 0; i < b->n; i++) if (b->Q[i] < 0.0) { snprintf(h->message, 256, "kwt_rch/negative flow extracted from upstream reach"); return 20; }
+        q_upstream = 0.0;
+        for (k = 0; k < NUPS; k++) {
+            int m = h->up_ptr[j] + k;
+            if (!h->goodBas[m]) continue;
+            q_upstream = q_upstream + h->REACH_Q[M][h->up_idx[m]];
+        }
+        h->REACH_INFLOW[M][j] = q_upstream;
+    } else {
+        h->REACH_INFLOW[M][j] = 0.0;
+        h->REACH_Q[M][j] = h->BASIN_QR1[j];
+        w->n = 1; w->QF[0] = -9999; w->TI[0] = -9999; w->TR[0] = -9999; w->RF[0] = 0;
+        return 0;
+    }
+    if (b->n > MAXQPAR) { ierr = remove_rch(b); if (ierr) return ierr; }
+    NQ1 = b->n - 1;
+    T_START = T0; T_END = T1;     /* RSTEP = 0 */
+    FROUTE[0] = 1; for (i = 1; i <= NQ1; i++) FROUTE[i] = 0;
+    ierr = kinwav_rch(h, j, T_START, T_END, b->Q + 1, b->T + 1, b->X + 1, FROUTE + 1, NQ1, &NQ2);
+    if (ierr) return ierr;
+    NR = 0; for (i = 0; i <= NQ1; i++) NR += FROUTE[i]; NR -= 1;
+    NN = NQ2 - NR;
+    if (NR + 1 > NQ2) { snprintf(h->message, 256, "kwt_rch/no non-routed particle left (NR+1>NQ2)"); return 21; }
+    ierr = interp_rch(b->X, b->Q, NR + 2, T_START, T_END, &QNEW);
+    if (ierr) { snprintf(h->message, 256, "kwt_rch/interp_rch/bad bounds"); return ierr; }
+    h->REACH_Q[M][j] = QNEW * h->R_WIDTH[j] + h->BASIN_QR1[j];
+    Q_END = b->Q[NR] + ((b->Q[NR + 1] - b->Q[NR]) / (b->X[NR + 1] - b->X[NR])) * (T_END - b->X[NR]);
+    TIMEI = b->T[NR] + ((b->T[NR + 1] - b->T[NR]) / (b->X[NR + 1] - b->X[NR])) * (T_END - b->X[NR]);
+    if (NQ2 + 2 > KW_CAP) { snprintf(h->message, 256, "kwt_rch/KWAVE capacity exceeded"); return 60; }
+    w->n = NQ2 + 2;
+    w->QF[NR + 1] = Q_END; w->TI[NR + 1] = TIMEI; w->TR[NR + 1] = T_END; w->RF[NR + 1] = 1;
+    for (i = 0; i <= NR; i++) { w->QF[i] = b->Q[i]; w->TI[i] = b->T[i]; w->TR[i] = b->X[i]; w->RF[i] = FROUTE[i]; }
+    for (i = NR + 1; i <= NQ2; i++) { w->QF[i + 1] = b->Q[i]; w->TI[i + 1] = b->T[i]; w->TR[i + 1] = b->X[i]; w->RF[i + 1] = FROUTE[i]; }
+    if (h->downSegId[j] <= 0 || (h->is_lake_sim && h->lakeInlet[j])) {
+        for (i = 0; i <= NN; i++) { w->QF[i] = w->QF[NR + 1 + i]; w->TI[i] = w->TI[NR + 1 + i]; w->TR[i] = w->TR[NR + 1 + i]; w->RF[i] = w->RF[NR + 1 + i]; }
+        w->n = NN + 1;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* main_route.f90:29-268 + route_network :273-409                                             */
+/* ------------------------------------------------------------------------------------------ */
+static int route_one(mro_t *h, int M, int j, double T0, double T1, wave_buf_t *b)
+{
+    if (h->isLake[j] && h->is_lake_sim && M != M_SUM) return lake_route(h, j, M);
+    if (M == M_SUM) return accum_inst_runoff(h, j);
+    if (M == M_IRF) return irf_rch(h, j);
+    return kwt_rch(h, j, T0, T1, b);
+}
+
+int mro_step(mro_t *h, double T0, double T1, const double *basinRunoff)
+{
+    int j, r, ierr;
+    ierr = basin2reach(h, basinRunoff, h->reachRunoff, 1);
+    if (ierr) return ierr;
+    if (h->doesBasinRoute == 1) {
+#pragma omp parallel for schedule(static) num_threads(h->nThreads)
+        for (j = 0; j < h->nRch; j++) { h->BASIN_QI[j] = h->reachRunoff[j]; hru_irf(h, j); }
+    } else {
+        for (j = 0; j < h->nRch; j++) { h->BASIN_QR0[j] = h->BASIN_QR1[j]; h->BASIN_QR1[j] = h->reachRunoff[j]; }
+    }
+    for (r = 0; r < h->nRoutes; r++) {
+        int M = h->routeOrder[r];
+        if (h->nThreads <= 1) {
+            wave_buf_t b = {0, 0, 0, 0, 0};
+            for (j = 0; j < h->nRch; j++) { ierr = route_one(h, M, h->order[j], T0, T1, &b); if (ierr) break; }
+            free(b.Q); free(b.T); free(b.X);
+            if (ierr) return ierr;
+        } else {
+            int err = 0;
+#pragma omp parallel num_threads(h->nThreads)
+            {
+                wave_buf_t b = {0, 0, 0, 0, 0};
+                int lev;
+                for (lev = 0; lev < h->nLevel; lev++) {
+                    int k;
+#pragma omp for schedule(dynamic, 64)
+                    for (k = h->lev_ptr[lev]; k < h->lev_ptr[lev + 1]; k++) {
+                        int e = route_one(h, M, h->lev_idx[k], T0, T1, &b);
+                        if (e) {
+#pragma omp atomic write
+                            err = e;
+                        }
+                    }
+                }
+                free(b.Q); free(b.T); free(b.X);
+            }
+            if (err) return err;
+        }
+    }
+    h->iTime++;
+    return 0;
+}
+
+/* run nSteps with T advancing as init_model_data.f90:311-312; outputs [method slot r][step][reach] */
+int mro_run(mro_t *h, int nSteps, double T0, const double *runoff /* [nSteps][nHRU] */, double *q_out /* [nRoutes][nSteps][nRch] or NULL */)
+{
+    int t, r, ierr; double t0 = T0, t1 = T0 + h->dt;
+    for (t = 0; t < nSteps; t++) {
+        ierr = mro_step(h, t0, t1, runoff + (size_t)t * h->nHRU);
+        if (ierr) return ierr;
+        if (q_out) for (r = 0; r < h->nRoutes; r++)
+            memcpy(q_out + ((size_t)r * nSteps + t) * h->nRch, h->REACH_Q[h->routeOrder[r]], sizeof(double) * h->nRch);
+        t0 = t1; t1 = t0 + h->dt;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* accessors                                                                                   */
+/* ------------------------------------------------------------------------------------------ */
+enum { F_REACH_Q = 0, F_REACH_VOL1 = 1, F_REACH_INFLOW = 2, F_WB = 3, F_BASIN_QI = 4, F_BASIN_QR1 = 5, F_BASIN_QR0 = 6, F_REACH_VOL0 = 7,
+       F_WIDTH = 10, F_TOTAREA = 11, F_BASAREA = 12, F_SLOPE = 13 };
+
+int mro_get(mro_t *h, int method, int field, double *out)
+{
+    const double *src = NULL;
+    switch (field) {
+        case F_REACH_Q: src = h->REACH_Q[method]; break;
+        case F_REACH_VOL1: src = h->REACH_VOL1[method]; break;
+        case F_REACH_VOL0: src = h->REACH_VOL0[method]; break;
+        case F_REACH_INFLOW: src = h->REACH_INFLOW[method]; break;
+        case F_WB: src = h->WB[method]; break;
+        case F_BASIN_QI: src = h->BASIN_QI; break;
+        case F_BASIN_QR1: src = h->BASIN_QR1; break;
+        case F_BASIN_QR0: src = h->BASIN_QR0; break;
+        case F_WIDTH: src = h->R_WIDTH; break;
+        case F_TOTAREA: src = h->TOTAREA; break;
+        case F_BASAREA: src = h->BASAREA; break;
+        case F_SLOPE: src = h->R_SLOPE; break;
+        default: return 1;
+    }
+    memcpy(out, src, sizeof(double) * h->nRch);
+    return 0;
+}
+const char *mro_message(mro_t *h) { return h->message; }
+int mro_ntdh_bas(mro_t *h) { return h->ntdh_bas; }
+int mro_maxtdh(mro_t *h) { return h->maxtdh; }
+int mro_nlevel(mro_t *h) { return h->nLevel; }
+void mro_get_frac_future(mro_t *h, double *out) { memcpy(out, h->FRAC_FUTURE, sizeof(double) * h->ntdh_bas); }
+void mro_get_uh_ptr(mro_t *h, int *out) { memcpy(out, h->uh_ptr, sizeof(int) * (h->nRch + 1)); }
+void mro_get_uh_val(mro_t *h, double *out) { if (h->uh_val) memcpy(out, h->uh_val, sizeof(double) * h->uh_ptr[h->nRch]); }
+void mro_get_down_index(mro_t *h, int *out) { memcpy(out, h->downIndex, sizeof(int) * h->nRch); }
+void mro_get_qfuture(mro_t *h, double *out) { memcpy(out, h->QFUTURE, sizeof(double) * (size_t)h->nRch * h->ntdh_bas); }
+void mro_set_qfuture(mro_t *h, const double *in) { memcpy(h->QFUTURE, in, sizeof(double) * (size_t)h->nRch * h->ntdh_bas); }
+void mro_get_qfuture_irf(mro_t *h, double *out) { if (h->QFUTURE_IRF) memcpy(out, h->QFUTURE_IRF, sizeof(double) * h->uh_ptr[h->nRch]); }
+void mro_set_qfuture_irf(mro_t *h, const double *in) { if (h->QFUTURE_IRF) memcpy(h->QFUTURE_IRF, in, sizeof(double) * h->uh_ptr[h->nRch]); }
+int mro_set(mro_t *h, int method, int field, const double *in)
+{
+    double *dst = NULL;
+    switch (field) {
+        case F_REACH_Q: dst = h->REACH_Q[method]; break;
+        case F_REACH_VOL1: dst = h->REACH_VOL1[method]; break;
+        case F_REACH_VOL0: dst = h->REACH_VOL0[method]; break;
+        case F_BASIN_QR1: dst = h->BASIN_QR1; break;
+        case F_BASIN_QR0: dst = h->BASIN_QR0; break;
+        default: return 1;
+    }
+    memcpy(dst, in, sizeof(double) * h->nRch);
+    return 0;
+}
+void mro_set_itime(mro_t *h, long it) { h->iTime = it; }
+/* KWT state in the restart layout [seg][wave] (write_restart_pio.f90:1039-1134), wave dimension = cap */
+void mro_get_kwt_state(mro_t *h, int cap, int *numWaves, double *qf, double *ti, double *tr, unsigned char *rf)
+{
+    int i, k;
+    for (i = 0; i < h->nRch; i++) {
+        numWaves[i] = h->KW[i].n;
+        for (k = 0; k < cap; k++) {
+            int ok = k < h->KW[i].n;
+            qf[(size_t)i * cap + k] = ok ? h->KW[i].QF[k] : -9999.0;
+            ti[(size_t)i * cap + k] = ok ? h->KW[i].TI[k] : -9999.0;
+            tr[(size_t)i * cap + k] = ok ? h->KW[i].TR[k] : -9999.0;
+            rf[(size_t)i * cap + k] = ok ? h->KW[i].RF[k] : 0;
+        }
+    }
+}
+void mro_set_kwt_state(mro_t *h, int cap, const int *numWaves, const double *qf, const double *ti, const double *tr, const unsigned char *rf)
+{
+    int i, k;
+    for (i = 0; i < h->nRch; i++) {
+        h->KW[i].n = numWaves[i];
+        for (k = 0; k < numWaves[i] && k < KW_CAP; k++) {
+            h->KW[i].QF[k] = qf[(size_t)i * cap + k]; h->KW[i].TI[k] = ti[(size_t)i * cap + k];
+            h->KW[i].TR[k] = tr[(size_t)i * cap + k]; h->KW[i].RF[k] = rf[(size_t)i * cap + k];
+        }
+    }
+}
+/* stand-alone helpers exposed for unit tests */
+double mro_gammp(double a, double x) { return gammp(a, x); }
+int mro_make_uh_one(double len, double dt, double velo, double diff, double *out) { return make_uh_one(len, dt, velo, diff, out); }
+int mro_interp_rch(const double *T, const double *Q, int n, double T0, double T1, double *out) { return interp_rch(T, Q, n, T0, T1, out); }
+int mro_remove_rch(double *Q, double *T, double *X, int n)
+{
+    wave_buf_t b = {0, 0, 0, 0, 0}; int i;
+    wb_reserve(&b, n); memcpy(b.Q, Q, sizeof(double) * n); memcpy(b.T, T, sizeof(double) * n); memcpy(b.X, X, sizeof(double) * n); b.n = n;
+    remove_rch(&b);
+    for (i = 0; i < b.n; i++) { Q[i] = b.Q[i]; T[i] = b.T[i]; X[i] = b.X[i]; }
+    n = b.n; free(b.Q); free(b.T); free(b.X);
+    return n;
+}
