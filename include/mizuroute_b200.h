@@ -1,0 +1,149 @@
+/*
+ * mizuroute_b200.h -- C ABI of the B200-native reach-routing solver.
+ *
+ * The reference (ESCOMP/mizuRoute, Fortran) has no FFI/plug-in layer.  The seam this library sits
+ * behind is the Fortran module interface of the per-step routing driver
+ *
+ *     main_route(basinRunoff_in, ..., NETOPO_in, RPARAM_in, RCHFLX_out, RCHSTA_out, ..., ierr, message)
+ *         route/build/src/main_route.f90:29-43   (called by mpi_route, mpi_process.f90:1217,1294)
+ *
+ * and, below it, the abstract per-reach operator  base_route_rch%route  (base_route.f90:27-63)
+ * with its IRF / KWT / SUM implementations (irf_route.f90:40, kwt_route.f90:36, accum_runoff.f90:32).
+ * Each entry point below names the reference interface it replaces.  INTEGRATION.md shows the
+ * bind(C) shim a mizuRoute maintainer would add to call it from mpi_route.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, all arrays caller-owned HOST memory unless named *_dev*;
+ *   - every function returns ierr (0 = ok; reference codes 10/20/30/40/60 are kept where the
+ *     reference raises them) and writes a NUL-terminated, path-like message ("mr_step/kwt_rch/...")
+ *     into the caller's 256-byte buffer, mirroring `ierr, message` (main_route.f90:42);
+ *   - reach-dimensioned arrays are in the caller's reach order (the order of segId passed to
+ *     mr_set_network); HRU-dimensioned arrays in the caller's HRU order (NETOPO%HRUIX indexing,
+ *     main_route.f90:50);
+ *   - all reals are double (real(dp)), all integers 32-bit (integer(i4b));
+ *   - a handle is bound to one CUDA device and is not re-entrant (like the module globals it replaces).
+ */
+#ifndef MIZUROUTE_B200_H
+#define MIZUROUTE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MR_STRLEN 256            /* strLen, public_var.f90:25 */
+#define MR_MAXQPAR 20            /* MAXQPAR, public_var.f90:37 */
+#define MR_KW_SLOTS 22           /* KWAVE(0:NQ2+1) can momentarily hold 21 entries (kwt_route.f90:299) */
+
+/* routing-method ids, public_var.f90:74-80 */
+enum { MR_ACCUM_RUNOFF = 0, MR_IMPULSE_RESPONSE_FUNC = 1, MR_KINEMATIC_WAVE_TRACKING = 2 };
+
+/* flux fields of STRFLX (dataTypes.f90:346-377) readable with mr_get_flux */
+enum {
+    MR_REACH_Q = 0, MR_REACH_VOL1 = 1, MR_REACH_INFLOW = 2, MR_WB = 3,
+    MR_BASIN_QI = 4, MR_BASIN_QR1 = 5, MR_BASIN_QR0 = 6, MR_REACH_VOL0 = 7,
+    /* derived reach parameters (RCHPRP, dataTypes.f90:183-255) */
+    MR_R_WIDTH = 10, MR_TOTAREA = 11, MR_BASAREA = 12, MR_R_SLOPE = 13
+};
+
+/* lake model types, public_var.f90 / lake_route.f90:196-438 */
+enum { MR_LAKE_ENDORHEIC = 0, MR_LAKE_DOLL03 = 1 };
+
+/* state variables in the reference's restart schema (write_restart_pio.f90:544,1039-1134; read_restart.f90:402-470) */
+enum {
+    MR_ST_BASIN_QFUTURE = 0,   /* double [nRch][ntdh_bas]      "qfuture"      */
+    MR_ST_BASIN_QR      = 1,   /* double [nRch][2]             BASIN_QR(0:1)  */
+    MR_ST_IRF_QFUTURE   = 2,   /* double [nRch][maxtdh]        "irf_qfuture" (rows padded with 0 beyond ntdh(reach)) */
+    MR_ST_IRF_VOL       = 3,   /* double [nRch]                "volume_irf"   */
+    MR_ST_KWT_NWAVE     = 4,   /* int    [nRch]                "numWaves"     */
+    MR_ST_KWT_QWAVE     = 5,   /* double [nRch][MR_KW_SLOTS]   "qwave"        */
+    MR_ST_KWT_TENTRY    = 6,   /* double [nRch][MR_KW_SLOTS]   "tentry"       */
+    MR_ST_KWT_TEXIT     = 7,   /* double [nRch][MR_KW_SLOTS]   "texit"        */
+    MR_ST_KWT_ROUTED    = 8,   /* int    [nRch][MR_KW_SLOTS]   "routed"       */
+    MR_ST_LAKE_VOL      = 9    /* double [nRoutes][nRch]       REACH_VOL(1) of every active method */
+};
+
+/* integer facts about a handle, mr_get_info */
+enum {
+    MR_INFO_NRCH = 0, MR_INFO_NHRU = 1, MR_INFO_NSTAGE = 2, MR_INFO_NTDH_BAS = 3, MR_INFO_MAXTDH = 4,
+    MR_INFO_LAUNCHES_LAST = 5,   /* kernels launched by the last mr_step / mr_step_batch / mr_route_resident */
+    MR_INFO_STEPS_DONE = 6,      /* iTime-1 (globalData iTime) */
+    MR_INFO_MAX_BATCH = 7, MR_INFO_MAX_NUPS = 8, MR_INFO_KWT_PARTICLES = 9, /* live particles in the KWT state */
+    MR_INFO_DEVICE_BYTES = 10    /* bytes of HBM held by the handle (KiB) */
+};
+
+typedef struct mr_handle_s *mr_handle;
+
+/* Control-file keys the routing path reads (read_control.f90; defaults public_var.f90:100-145) and the
+ * spatially-constant parameters of namelist param_nml (read_param.f90:26-38). */
+typedef struct {
+    double dt;                   /* <dt_qsim> [s] */
+    int    n_routes;             /* number of digits in <route_opt> */
+    int    route_methods[8];     /* the digits, in order (read_control.f90:583-597) */
+    int    doesBasinRoute;       /* 1: hillslope UH (default) */
+    int    hw_drain_point;       /* 1 top / 2 bottom (default) of headwater reach, irf_route.f90:91-111 */
+    double min_length_route;     /* irf_route.f90:237 */
+    int    is_lake_sim, lakeRegulate, LakeInputOption;
+    double runoffMin;            /* public_var.f90:145 */
+    double time_conv, length_conv;   /* from <units_qsim>, read_control.f90:443-474 */
+    double fshape, tscale;       /* &HSLOPE */
+    double velo, diff;           /* &IRF_UH */
+    double mann_n, wscale;       /* &KWT    */
+    int    device;               /* CUDA device ordinal */
+    int    max_batch;            /* largest nSteps a batch call may pass (sizes the resident series) */
+} mr_options;
+
+/* Replaces init_route_method + the option globals (init_model_data.f90:753-805, public_var.f90). */
+int mr_create(const mr_options *opts, mr_handle *out, char *message);
+
+/* Replaces init_ntopo/augment_ntopo/put_data_struct (process_ntopo.f90:39-513): takes the variables
+ * read_streamSeg.f90:getData (:44) reads from the river-network file and derives topology, areas,
+ * widths, unit hydrographs, and the device layout.  Optional arrays may be NULL.  Cold-start state
+ * (init_model_data.f90:399-463). */
+int mr_set_network(mr_handle h, int nRch, int nHRU,
+                   const int *segId, const int *downSegId,
+                   const int *hruSegId, const double *hruArea,
+                   const double *length, const double *slope,
+                   const double *width, const double *man_n,
+                   const int *islake, const int *lakeModelType,
+                   const double *D03_MaxStorage, const double *D03_Coefficient,
+                   const double *D03_Power, const double *D03_S0,
+                   char *message);
+
+/* Replaces one main_route call (main_route.f90:29-268) for the time step [T0,T1] = TSEC(1:2). */
+int mr_step(mr_handle h, double T0, double T1, const double *basinRunoff /* [nHRU] */, char *message);
+
+/* nSteps consecutive main_route calls starting at T0 (T advances as update_time does,
+ * init_model_data.f90:311-312), executed as one time-skewed wavefront.  runoff is [nSteps][nHRU];
+ * q_out, if not NULL, receives REACH_Q as [n_routes][nSteps][nRch]. */
+int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message);
+
+/* The same in three stages, for callers that keep forcing resident in HBM:
+ * upload -> route (device only, no host<->device traffic) -> download. */
+int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message);
+int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
+int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
+
+/* RCHFLX_out(:)%ROUTE(method)%<field> / %BASIN_* after the last step, caller's reach order. */
+int mr_get_flux(mr_handle h, int method, int field, double *out /* [nRch] */, char *message);
+
+/* Restart-schema state access (read_restart.f90 / write_restart_pio.f90). buf sized per the enum above. */
+int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message);
+int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *message);
+/* set iTime (number of completed steps); a restart sets it > 0 so lakes skip their cold start. */
+int mr_set_steps_done(mr_handle h, long steps, char *message);
+
+/* Unit hydrographs produced by process_param.f90 (basinUH :13-92, make_uh :99-262). */
+int mr_get_basin_uh(mr_handle h, double *frac_future /* [ntdh_bas] */, char *message);
+int mr_get_reach_uh(mr_handle h, int *ntdh /* [nRch] */, double *uh /* [nRch][maxtdh] */, char *message);
+
+long mr_get_info(mr_handle h, int key);
+/* device milliseconds of the last batch call, GPTL-region style (mpi_process.f90:1184-1339):
+ * [0] whole call, [1] basin2reach+hillslope UH, [2] route_network (all methods), [3] H2D, [4] D2H */
+int mr_get_timing(mr_handle h, double *ms /* [8] */);
+
+void mr_destroy(mr_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

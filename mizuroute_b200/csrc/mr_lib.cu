@@ -1,0 +1,729 @@
+// libmizuroute_b200.so -- handle, device memory, launch schedule and the C ABI of include/mizuroute_b200.h.
+//
+// One handle = one routing domain resident on one B200.  The per-step driver the reference runs as
+//   basin2reach -> IRF_route_basin -> for each method: route_network   (main_route.f90:151-266)
+// is executed for a whole batch of K time steps as
+//   k_basin (all K steps)  ->  for each method: wavefronts w = 0 .. nStage+K-2 of k_route<M>
+// where wavefront w holds every (reach, step) pair with stage(reach) + step == w.  Legal because a reach at
+// step t needs only its upstream reaches at step t (one stage behind => one wavefront earlier) and itself at
+// t-1 (one wavefront earlier); K = 1 degenerates to the reference's upstream->downstream sweep.
+#include <cuda_runtime.h>
+#include <omp.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mr_kernels.cuh"
+#include "mr_topo.h"
+#include "mr_uh.h"
+
+using namespace mr;
+
+struct mr_handle_s {
+    mr_options opt{};
+    bool on[3] = {false, false, false};
+    bool hasNet = false;
+    Topology topo;
+    std::vector<double> fracFuture, uhHost;      // uhHost slot-major [maxtdh][N], stage order
+    std::vector<int> ntdh, flags;                // stage order
+    int maxtdh = 1, ntdhBas = 1;
+    DevNet d{};
+    std::vector<void *> allocs;
+    size_t devBytes = 0;
+    long long stepsDone = 0;
+    int lastK = 0;
+    int launchesLast = 0;
+    double timing[8] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr};
+    double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
+    int *dRch2pos = nullptr;
+    int basinBlock = 128; bool basinStaged = false; size_t basinSmem = 0;
+};
+
+namespace {
+
+void put_msg(char *message, const std::string &s) {
+    if (!message) return;
+    std::snprintf(message, MR_STRLEN, "%s", s.c_str());
+}
+int fail(char *message, int ierr, const std::string &s) { put_msg(message, s); return ierr; }
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(message, 90, std::string(where) + "/CUDA: " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(mr_handle h, T **ptr, size_t n, const char *where, char *message, bool zero = true) {
+    const size_t bytes = sizeof(T) * (n ? n : 1);
+    CU(cudaMalloc((void **)ptr, bytes));
+    h->allocs.push_back(*ptr);
+    h->devBytes += bytes;
+    if (zero) CU(cudaMemsetAsync(*ptr, 0, bytes, h->stream));
+    return 0;
+}
+template <typename T>
+int dev_upload(mr_handle h, T **ptr, const std::vector<T> &v, const char *where, char *message) {
+    int e = dev_alloc(h, ptr, v.size(), where, message, false);
+    if (e) return e;
+    if (!v.empty()) CU(cudaMemcpy(*ptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+template <typename T>
+int dev_upload_const(mr_handle h, const T *&field, const std::vector<T> &v, const char *where, char *message) {
+    T *tmp = nullptr;
+    int e = dev_upload(h, &tmp, v, where, message);
+    field = tmp;
+    return e;
+}
+
+const char *site_text(int site) {
+    switch (site) {
+        case E_NEG_RUNOFF: return "basin2reach/exceeded negative runoff tolerance";
+        case E_LAKE_UPS: return "kwt_rch/getusq_rch/lake outlet reach should have one upstream lake";
+        case E_NEG_FLOW: return "kwt_rch/negative flow extracted from upstream reach";
+        case E_SCRATCH: return "kwt_rch/qexmul_rch/particle scratch capacity exceeded";
+        case E_STUCK: return "kwt_rch/getusq_rch/qexmul_rch/stuck in the continuous do-loop";
+        case E_TIME_ORDER: return "kwt_rch/getusq_rch/qexmul_rch/expect process in order of time";
+        case E_BRACKET: return "kwt_rch/getusq_rch/qexmul_rch/the times are not ordered as we assume";
+        case E_QD_BOUNDS: return "kwt_rch/getusq_rch/qexmul_rch/QD_TEMP bounds exceeded";
+        case E_ZERO_FLOW: return "kwt_rch/kinwav_rch/zero flow";
+        case E_TEXIT2: return "kwt_rch/kinwav_rch/TEXIT equals TEXIT2 in kinwav";
+        case E_RUPDATE: return "kwt_rch/kinwav_rch/RUPDATE/array bounds exceeded";
+        case E_NO_NONROUTED: return "kwt_rch/no non-routed particle left";
+        case E_INTERP: return "kwt_rch/interp_rch/bad bounds";
+        case E_LAKE_TYPE: return "lake_route/unable to identify the parametric lake model type";
+        case E_TOO_MANY_UPS: return "kwt_rch/qexmul_rch/more upstream series than the kernel merges";
+        case E_THIN: return "kwt_rch/remove_rch/no interior particle to remove";
+        case E_NO_ROUTED_UP: return "kwt_rch/qexmul_rch/upstream wave has no routed element";
+        default: return "unknown";
+    }
+}
+
+void free_device(mr_handle h) {
+    for (void *p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->devBytes = 0;
+}
+
+template <int M>
+void launch_wavefronts(mr_handle h, int K, long long tau0) {
+    const Topology &T = h->topo;
+    const int block = (M == M_KWT) ? 128 : 256;
+    for (int w = 0; w < T.nStage + K - 1; ++w) {
+        const int slo = w - K + 1 > 0 ? w - K + 1 : 0;
+        const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
+        const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
+        if (hi <= lo) continue;
+        k_route<M><<<(hi - lo + block - 1) / block, block, 0, h->stream>>>(h->d, lo, hi, w, tau0);
+        h->launchesLast++;
+    }
+}
+
+__global__ void k_times(double T0, double dt, int K, double *T0s, double *T1s) {
+    // TSEC(1)=TSEC(2); TSEC(2)=TSEC(1)+dt, init_model_data.f90:311-312
+    double t0 = T0, t1 = T0 + dt;
+    for (int t = 0; t < K; ++t) { T0s[t] = t0; T1s[t] = t1; t0 = t1; t1 = t0 + dt; }
+}
+
+int check_ready(mr_handle h, int nSteps, const char *where, char *message) {
+    if (!h) return fail(message, 1, std::string(where) + "/null handle");
+    if (!h->hasNet) return fail(message, 1, std::string(where) + "/mr_set_network has not been called");
+    if (nSteps < 1 || nSteps > h->opt.max_batch)
+        return fail(message, 1, std::string(where) + "/nSteps outside [1, max_batch]");
+    CU(cudaSetDevice(h->opt.device));
+    return 0;
+}
+
+// device part of a batch: everything between "forcing is in HBM" and "REACH_Q series is in HBM"
+int route_device(mr_handle h, int K, double T0, const char *where, char *message) {
+    DevNet &d = h->d;
+    const int N = d.nRch;
+    h->launchesLast = 0;
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    k_times<<<1, 1, 0, h->stream>>>(T0, h->opt.dt, K, h->dT0s, h->dT1s);
+    if (h->lastK > 0 && h->lastK != 0) k_carry_qr<<<(N + 255) / 256, 256, 0, h->stream>>>(d.qrSer, N, h->lastK);
+    h->launchesLast += 2;
+    const int bb = h->basinBlock;
+    if (h->basinStaged && K > 1)
+        k_basin<true><<<(N + bb - 1) / bb, bb, h->basinSmem, h->stream>>>(d, K, h->stepsDone);
+    else
+        k_basin<false><<<(N + bb - 1) / bb, bb, 0, h->stream>>>(d, K, h->stepsDone);
+    h->launchesLast++;
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    for (int r = 0; r < h->opt.n_routes; ++r) {
+        switch (h->opt.route_methods[r]) {
+            case M_SUM: launch_wavefronts<M_SUM>(h, K, h->stepsDone); break;
+            case M_IRF: launch_wavefronts<M_IRF>(h, K, h->stepsDone); break;
+            case M_KWT: launch_wavefronts<M_KWT>(h, K, h->stepsDone); break;
+        }
+    }
+    CU(cudaEventRecord(h->ev[3], h->stream));
+    CU(cudaGetLastError());
+    h->stepsDone += K;
+    h->lastK = K;
+    return 0;
+}
+
+int check_device_error(mr_handle h, const char *where, char *message) {
+    int e[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(e, h->d.err, sizeof(e), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (e[0] != 0) {
+        const int rch = (e[1] >= 0 && e[1] < h->topo.nRch) ? h->topo.pos2rch[e[1]] : -1;
+        CU(cudaMemsetAsync(h->d.err, 0, sizeof(e), h->stream));
+        return fail(message, e[0], std::string(where) + "/main_route/" + site_text(e[2]) + " (reach index " + std::to_string(rch) + ")");
+    }
+    return 0;
+}
+
+void collect_timing(mr_handle h) {
+    float ms = 0.f;
+    auto span = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return (double)ms; };
+    h->timing[1] = span(1, 2);
+    h->timing[2] = span(2, 3);
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int mr_create(const mr_options *opts, mr_handle *out, char *message) {
+    const char *where = "mr_create";
+    if (!opts || !out) return fail(message, 1, "mr_create/null argument");
+    *out = nullptr;
+    if (opts->n_routes < 1 || opts->n_routes > 3) return fail(message, 1, "mr_create/route_opt must name 1-3 methods");
+    if (!(opts->dt > 0.0)) return fail(message, 1, "mr_create/dt_qsim must be positive");
+    if (opts->max_batch < 1) return fail(message, 1, "mr_create/max_batch must be >= 1");
+    mr_handle h = new mr_handle_s();
+    h->opt = *opts;
+    for (int r = 0; r < opts->n_routes; ++r) {
+        const int m = opts->route_methods[r];
+        if (m < 0 || m > 2 || h->on[m]) {        // read_control.f90:583-597; methods 3/4/5 are not on this path
+            delete h;
+            return fail(message, 81, "mr_create/route_opt: only 0 (SUM), 1 (IRF), 2 (KWT), each at most once");
+        }
+        h->on[m] = true;
+    }
+    int nDev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&nDev);
+    if (ce != cudaSuccess || nDev == 0 || opts->device < 0 || opts->device >= nDev) {
+        delete h;
+        return fail(message, 90, "mr_create/no usable CUDA device (this library has no CPU path)");
+    }
+    ce = cudaSetDevice(opts->device);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    if (ce != cudaSuccess) { delete h; CU(ce); }
+    put_msg(message, "");
+    *out = h;
+    return 0;
+}
+
+int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId,
+                   const double *hruArea, const double *length, const double *slope, const double *width,
+                   const double *man_n, const int *islake, const int *lakeModelType, const double *D03_MaxStorage,
+                   const double *D03_Coefficient, const double *D03_Power, const double *D03_S0, char *message) {
+    const char *where = "mr_set_network";
+    if (!h) return fail(message, 1, "mr_set_network/null handle");
+    if (nRch < 1 || nHRU < 0 || !segId || !downSegId || !length || !slope || (nHRU > 0 && (!hruSegId || !hruArea)))
+        return fail(message, 1, "mr_set_network/missing required network variable");
+    CU(cudaSetDevice(h->opt.device));
+    free_device(h);
+    h->hasNet = false; h->stepsDone = 0; h->lastK = 0;
+    const mr_options &o = h->opt;
+
+    std::string terr;
+    Topology &T = h->topo;
+    T = Topology();
+    int ierr = build_topology(nRch, nHRU, segId, downSegId, hruSegId, hruArea, T, terr);
+    if (ierr) return fail(message, ierr, "mr_set_network/" + terr);
+    const int N = nRch;
+
+    // reach parameters in stage order (process_ntopo.f90:176-187,359-366)
+    std::vector<double> rlen(N), rslp(N), rwid(N), rman(N), maxS(N, 0.0), coef(N, 0.0), pw(N, 0.0), s0(N, 0.0);
+    std::vector<int> ltype(N, MR_LAKE_DOLL03);
+    h->flags.assign(N, 0);
+    for (int p = 0; p < N; ++p) {
+        const int r = T.pos2rch[p];
+        rlen[p] = length[r];
+        rslp[p] = std::fmax(slope[r], 1.e-6);                        // min_slope, public_var.f90:30
+        rwid[p] = width ? width[r] : o.wscale * std::sqrt(T.totArea[p]);
+        rman[p] = man_n ? man_n[r] : o.mann_n;
+        if (o.is_lake_sim) {
+            if (islake && islake[r] == 1) h->flags[p] |= FLAG_LAKE;
+            ltype[p] = (!o.lakeRegulate || !lakeModelType) ? MR_LAKE_DOLL03 : lakeModelType[r];
+            if (D03_MaxStorage) maxS[p] = D03_MaxStorage[r];
+            if (D03_Coefficient) coef[p] = D03_Coefficient[r];
+            if (D03_Power) pw[p] = D03_Power[r];
+            if (D03_S0) s0[p] = D03_S0[r];
+        }
+    }
+    if (o.is_lake_sim)
+        for (int p = 0; p < N; ++p)
+            for (int m = 0; m < T.nUps[p]; ++m)
+                if (h->flags[T.upFirst[p] + m] & FLAG_LAKE) h->flags[p] |= FLAG_LAKE_UP;
+
+    // unit hydrographs (process_param.f90)
+    ierr = build_hillslope_uh(o.dt, o.fshape, o.tscale, h->fracFuture);
+    if (ierr) return fail(message, ierr, "mr_set_network/basinUH/cannot identify the maximum number of bins for the tdh");
+    h->ntdhBas = (int)h->fracFuture.size();
+    h->ntdh.assign(N, 1);
+    h->maxtdh = 1;
+    h->uhHost.clear();
+    if (h->on[M_IRF]) {
+        std::vector<double> rowMajor((size_t)N * 240);
+        int mx = 1;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(max : mx)
+        for (int p = 0; p < N; ++p) {
+            double *u = &rowMajor[(size_t)p * 240];
+            const int n = build_reach_uh(rlen[p], o.dt, o.velo, o.diff, u);
+            if (h->flags[p] & FLAG_LAKE) { for (int k = 0; k < n; ++k) u[k] = 0.0; u[0] = 1.0; }   // process_ntopo.f90:496-499
+            h->ntdh[p] = n;
+            if (n > mx) mx = n;
+        }
+        h->maxtdh = mx;
+        h->uhHost.assign((size_t)mx * N, 0.0);
+#pragma omp parallel for schedule(static)
+        for (int p = 0; p < N; ++p)
+            for (int k = 0; k < h->ntdh[p]; ++k) h->uhHost[(size_t)k * N + p] = rowMajor[(size_t)p * 240 + k];
+    }
+
+    // ---- device image
+    DevNet &d = h->d;
+    d = DevNet();
+    d.nRch = N; d.nHRU = nHRU; d.nStage = T.nStage; d.ntdhBas = h->ntdhBas; d.maxtdh = h->maxtdh;
+    d.dt = o.dt; d.runoffMin = o.runoffMin; d.tconv = o.time_conv; d.lconv = o.length_conv; d.minLengthRoute = o.min_length_route;
+    d.doesBasinRoute = o.doesBasinRoute; d.hwDrain = o.hw_drain_point; d.isLakeSim = o.is_lake_sim; d.lakeInputOption = o.LakeInputOption;
+    const int KB = o.max_batch;
+    int e = 0;
+#define UP(field, vec) do { e = dev_upload_const(h, d.field, vec, where, message); if (e) return e; } while (0)
+#define AL(ptr, n) do { e = dev_alloc(h, &(ptr), (size_t)(n), where, message); if (e) return e; } while (0)
+    UP(stageOf, T.stageOf); UP(upFirst, T.upFirst); UP(nUps, T.nUps); UP(nGood, T.nGood);
+    UP(hruPtr, T.hruPtr); UP(hruIdx, T.hruIdx); UP(flags, h->flags); UP(ntdh, h->ntdh); UP(lakeType, ltype);
+    UP(hruWgt, T.hruWgt); UP(basArea, T.basArea); UP(rlength, rlen); UP(rslope, rslp); UP(rwidth, rwid); UP(rmann, rman);
+    UP(fracFuture, h->fracFuture);
+    if (h->on[M_IRF]) UP(uh, h->uhHost);
+    UP(d03MaxS, maxS); UP(d03Coef, coef); UP(d03Pow, pw); UP(d03S0, s0);
+    AL(d.qfutBas, (size_t)h->ntdhBas * N);
+    AL(d.qrSer, (size_t)(KB + 1) * N);
+    AL(d.basinQI, N);
+    for (int m = 0; m < 3; ++m) {
+        if (!h->on[m]) continue;
+        AL(d.qSer[m], (size_t)KB * N);
+        AL(d.vol0[m], N); AL(d.vol1[m], N); AL(d.inflow[m], N); AL(d.wb[m], N);
+    }
+    if (h->on[M_IRF]) AL(d.qfutIrf, (size_t)h->maxtdh * N);
+    if (h->on[M_KWT]) {
+        for (int b = 0; b < 2; ++b) {
+            AL(d.kwN[b], N); AL(d.kwNR[b], N);
+            AL(d.kwQF[b], (size_t)KWS * N); AL(d.kwTI[b], (size_t)KWS * N); AL(d.kwTR[b], (size_t)KWS * N);
+        }
+        if (o.is_lake_sim) {                       // lake reaches hold the sentinel particle (init_model_data.f90:440-456)
+            std::vector<int> n1(N, 0);
+            std::vector<double> s9((size_t)N, 0.0);
+            bool any = false;
+            for (int p = 0; p < N; ++p) if (h->flags[p] & FLAG_LAKE) { n1[p] = 1; s9[p] = -9999.0; any = true; }
+            if (any) for (int b = 0; b < 2; ++b) {
+                CU(cudaMemcpy(d.kwN[b], n1.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwQF[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwTI[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwTR[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+            }
+        }
+    }
+    AL(d.err, 4);
+    AL(h->dRunoff, (size_t)KB * (nHRU > 0 ? nHRU : 1));
+    AL(h->dT0s, KB); AL(h->dT1s, KB);
+    AL(h->dOut, (size_t)o.n_routes * KB * N);
+    e = dev_upload(h, &h->dRch2pos, T.rch2pos, where, message); if (e) return e;
+    d.runoff = h->dRunoff; d.T0s = h->dT0s; d.T1s = h->dT1s;
+#undef UP
+#undef AL
+
+    // hillslope-UH window staged in shared memory when one CTA's windows fit (else streamed from HBM)
+    h->basinBlock = 128; h->basinStaged = false; h->basinSmem = 0;
+    {
+        int maxSmem = 0;
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device);
+        for (int bb = 128; bb >= 32; bb >>= 1) {
+            const size_t need = (size_t)h->ntdhBas * bb * sizeof(double);
+            if (need <= (size_t)maxSmem) {
+                h->basinBlock = bb; h->basinStaged = true; h->basinSmem = need;
+                CU(cudaFuncSetAttribute(k_basin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+                break;
+            }
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->hasNet = true;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message) {
+    const char *where = "mr_upload_runoff";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!runoff) return fail(message, 1, "mr_upload_runoff/null runoff");
+    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_route_resident(mr_handle h, int nSteps, double T0, char *message) {
+    const char *where = "mr_route_resident";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    e = route_device(h, nSteps, T0, where, message); if (e) return e;
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    e = check_device_error(h, where, message); if (e) return e;
+    collect_timing(h);
+    float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
+    h->timing[3] = h->timing[4] = 0.0;
+    put_msg(message, "");
+    return 0;
+}
+
+static int download_q(mr_handle h, int nSteps, double *q_out, const char *where, char *message) {
+    const int N = h->d.nRch;
+    for (int r = 0; r < h->opt.n_routes; ++r) {
+        const int m = h->opt.route_methods[r];
+        dim3 grid((N + 255) / 256, nSteps < 64 ? nSteps : 64);
+        k_unpermute_rows<<<grid, 256, 0, h->stream>>>(h->d.qSer[m], h->dOut + (size_t)r * nSteps * N, h->dRch2pos, N, nSteps);
+        h->launchesLast++;
+    }
+    CU(cudaMemcpyAsync(q_out, h->dOut, sizeof(double) * (size_t)h->opt.n_routes * nSteps * N, cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message) {
+    const char *where = "mr_download_q";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!q_out) return fail(message, 1, "mr_download_q/null output");
+    if (nSteps > h->lastK) return fail(message, 1, "mr_download_q/more steps requested than the last batch routed");
+    e = download_q(h, nSteps, q_out, where, message); if (e) return e;
+    CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message) {
+    const char *where = "mr_step_batch";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!runoff) return fail(message, 1, "mr_step_batch/null runoff");
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    e = route_device(h, nSteps, T0, where, message); if (e) return e;
+    CU(cudaEventRecord(h->ev[4], h->stream));
+    if (q_out) { e = download_q(h, nSteps, q_out, where, message); if (e) return e; }
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    e = check_device_error(h, where, message); if (e) return e;
+    collect_timing(h);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[3] = ms;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing[4] = ms;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_step(mr_handle h, double T0, double T1, const double *basinRunoff, char *message) {
+    if (h && h->hasNet && T1 - T0 != h->opt.dt) return fail(message, 1, "mr_step/T1-T0 differs from dt_qsim");
+    int e = mr_step_batch(h, 1, T0, basinRunoff, nullptr, message);
+    if (e && message) { std::string s(message); if (s.rfind("mr_step_batch", 0) == 0) put_msg(message, "mr_step" + s.substr(13)); }
+    return e;
+}
+
+int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) {
+    const char *where = "mr_get_flux";
+    if (!h || !h->hasNet || !out) return fail(message, 1, "mr_get_flux/handle has no network or null output");
+    CU(cudaSetDevice(h->opt.device));
+    const int N = h->d.nRch;
+    const Topology &T = h->topo;
+    const double *src = nullptr;
+    std::vector<double> tmp(N);
+    const bool perMethod = (field == MR_REACH_Q || field == MR_REACH_VOL1 || field == MR_REACH_VOL0 || field == MR_REACH_INFLOW || field == MR_WB);
+    if (perMethod && (method < 0 || method > 2 || !h->on[method])) return fail(message, 1, "mr_get_flux/routing method is not active");
+    switch (field) {
+        case MR_REACH_Q: src = h->lastK > 0 ? h->d.qSer[method] + (size_t)(h->lastK - 1) * N : nullptr; break;
+        case MR_REACH_VOL1: src = h->d.vol1[method]; break;
+        case MR_REACH_VOL0: src = h->d.vol0[method]; break;
+        case MR_REACH_INFLOW: src = h->d.inflow[method]; break;
+        case MR_WB: src = h->d.wb[method]; break;
+        case MR_BASIN_QI: src = h->d.basinQI; break;
+        case MR_BASIN_QR1: src = h->d.qrSer + (size_t)h->lastK * N; break;
+        case MR_BASIN_QR0: src = h->lastK > 0 ? h->d.qrSer + (size_t)(h->lastK - 1) * N : nullptr; break;
+        case MR_R_WIDTH: src = h->d.rwidth; break;
+        case MR_R_SLOPE: src = h->d.rslope; break;
+        case MR_BASAREA: for (int r = 0; r < N; ++r) out[r] = T.basArea[T.rch2pos[r]]; put_msg(message, ""); return 0;
+        case MR_TOTAREA: for (int r = 0; r < N; ++r) out[r] = T.totArea[T.rch2pos[r]]; put_msg(message, ""); return 0;
+        default: return fail(message, 1, "mr_get_flux/unknown field");
+    }
+    if (!src) { for (int r = 0; r < N; ++r) out[r] = 0.0; put_msg(message, ""); return 0; }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(tmp.data(), src, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < N; ++r) out[r] = tmp[T.rch2pos[r]];
+    put_msg(message, "");
+    return 0;
+}
+
+// ---- state in the restart schema -----------------------------------------------------------------
+static long state_bytes(mr_handle h, int var) {
+    const long N = h->d.nRch;
+    switch (var) {
+        case MR_ST_BASIN_QFUTURE: return 8L * N * h->ntdhBas;
+        case MR_ST_BASIN_QR: return 8L * N * 2;
+        case MR_ST_IRF_QFUTURE: return 8L * N * h->maxtdh;
+        case MR_ST_IRF_VOL: return 8L * N;
+        case MR_ST_KWT_NWAVE: return 4L * N;
+        case MR_ST_KWT_QWAVE: case MR_ST_KWT_TENTRY: case MR_ST_KWT_TEXIT: return 8L * N * KWS;
+        case MR_ST_KWT_ROUTED: return 4L * N * KWS;
+        case MR_ST_LAKE_VOL: return 8L * N * h->opt.n_routes;
+        default: return -1;
+    }
+}
+
+int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
+    const char *where = "mr_get_state";
+    if (!h || !h->hasNet || !buf) return fail(message, 1, "mr_get_state/handle has no network or null buffer");
+    if (state_bytes(h, var) != nbytes) return fail(message, 1, "mr_get_state/buffer size does not match the variable");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    const int N = h->d.nRch;
+    const Topology &T = h->topo;
+    const long long tau = h->stepsDone;
+    double *out = (double *)buf; int *iout = (int *)buf;
+    auto pull = [&](const void *src, void *dst, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+    switch (var) {
+        case MR_ST_BASIN_QFUTURE: {
+            const int nb = h->ntdhBas;
+            std::vector<double> tmp((size_t)nb * N);
+            CU(pull(h->d.qfutBas, tmp.data(), tmp.size() * 8));
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r];
+                for (int k = 0; k < nb; ++k) out[(size_t)r * nb + k] = tmp[(size_t)((tau + k) % nb) * N + p]; }
+            break; }
+        case MR_ST_BASIN_QR: {
+            std::vector<double> a(N, 0.0), b(N);
+            if (h->lastK > 0) CU(pull(h->d.qrSer + (size_t)(h->lastK - 1) * N, a.data(), 8L * N));
+            CU(pull(h->d.qrSer + (size_t)h->lastK * N, b.data(), 8L * N));
+            for (int r = 0; r < N; ++r) { out[2 * r] = a[T.rch2pos[r]]; out[2 * r + 1] = b[T.rch2pos[r]]; }
+            break; }
+        case MR_ST_IRF_QFUTURE: {
+            if (!h->on[M_IRF]) return fail(message, 1, "mr_get_state/IRF is not active");
+            const int mx = h->maxtdh;
+            std::vector<double> tmp((size_t)mx * N);
+            CU(pull(h->d.qfutIrf, tmp.data(), tmp.size() * 8));
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r], nt = h->ntdh[p];
+                for (int k = 0; k < mx; ++k) out[(size_t)r * mx + k] = k < nt ? tmp[(size_t)((tau + k) % nt) * N + p] : 0.0; }
+            break; }
+        case MR_ST_IRF_VOL: {
+            if (!h->on[M_IRF]) return fail(message, 1, "mr_get_state/IRF is not active");
+            std::vector<double> tmp(N);
+            CU(pull(h->d.vol1[M_IRF], tmp.data(), 8L * N));
+            for (int r = 0; r < N; ++r) out[r] = tmp[T.rch2pos[r]];
+            break; }
+        case MR_ST_LAKE_VOL: {
+            std::vector<double> tmp(N);
+            for (int q = 0; q < h->opt.n_routes; ++q) {
+                CU(pull(h->d.vol1[h->opt.route_methods[q]], tmp.data(), 8L * N));
+                for (int r = 0; r < N; ++r) out[(size_t)q * N + r] = tmp[T.rch2pos[r]];
+            }
+            break; }
+        case MR_ST_KWT_NWAVE: case MR_ST_KWT_QWAVE: case MR_ST_KWT_TENTRY: case MR_ST_KWT_TEXIT: case MR_ST_KWT_ROUTED: {
+            if (!h->on[M_KWT]) return fail(message, 1, "mr_get_state/KWT is not active");
+            const int b = (int)((tau + 1) & 1);          // buffer written by the last completed step
+            std::vector<int> n(N), nr(N);
+            CU(pull(h->d.kwN[b], n.data(), 4L * N)); CU(pull(h->d.kwNR[b], nr.data(), 4L * N));
+            std::vector<double> tmp;
+            if (var == MR_ST_KWT_QWAVE || var == MR_ST_KWT_TENTRY || var == MR_ST_KWT_TEXIT) {
+                tmp.resize((size_t)KWS * N);
+                const double *src = var == MR_ST_KWT_QWAVE ? h->d.kwQF[b] : (var == MR_ST_KWT_TENTRY ? h->d.kwTI[b] : h->d.kwTR[b]);
+                CU(pull(src, tmp.data(), tmp.size() * 8));
+            }
+            // what the reference holds between steps is KWAVE(NR-1:) (kwt_route.f90:840-844,325-344)
+            for (int r = 0; r < N; ++r) {
+                const int p = T.rch2pos[r];
+                const int first = nr[p] > 0 ? nr[p] - 1 : 0, cnt = n[p] - first;
+                if (var == MR_ST_KWT_NWAVE) { iout[r] = cnt; continue; }
+                for (int k = 0; k < KWS; ++k) {
+                    if (var == MR_ST_KWT_ROUTED) iout[(size_t)r * KWS + k] = (k < cnt && first + k < nr[p]) ? 1 : 0;
+                    else out[(size_t)r * KWS + k] = k < cnt ? tmp[(size_t)(first + k) * N + p] : -9999.0;
+                }
+            }
+            break; }
+        default: return fail(message, 1, "mr_get_state/unknown state variable");
+    }
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *message) {
+    const char *where = "mr_set_state";
+    if (!h || !h->hasNet || !buf) return fail(message, 1, "mr_set_state/handle has no network or null buffer");
+    if (state_bytes(h, var) != nbytes) return fail(message, 1, "mr_set_state/buffer size does not match the variable");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    const int N = h->d.nRch;
+    const Topology &T = h->topo;
+    const long long tau = h->stepsDone;
+    const double *in = (const double *)buf; const int *iin = (const int *)buf;
+    auto push = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); };
+    switch (var) {
+        case MR_ST_BASIN_QFUTURE: {
+            const int nb = h->ntdhBas;
+            std::vector<double> tmp((size_t)nb * N);
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r];
+                for (int k = 0; k < nb; ++k) tmp[(size_t)((tau + k) % nb) * N + p] = in[(size_t)r * nb + k]; }
+            CU(push(h->d.qfutBas, tmp.data(), tmp.size() * 8));
+            break; }
+        case MR_ST_BASIN_QR: {
+            // BASIN_QR(1) becomes the carry-in row of the next batch; BASIN_QR(0) is overwritten by it at the next step
+            std::vector<double> b(N);
+            for (int r = 0; r < N; ++r) b[T.rch2pos[r]] = in[2 * r + 1];
+            CU(push(h->d.qrSer, b.data(), 8L * N));
+            h->lastK = 0;
+            break; }
+        case MR_ST_IRF_QFUTURE: {
+            if (!h->on[M_IRF]) return fail(message, 1, "mr_set_state/IRF is not active");
+            const int mx = h->maxtdh;
+            std::vector<double> tmp((size_t)mx * N, 0.0);
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r], nt = h->ntdh[p];
+                for (int k = 0; k < nt; ++k) tmp[(size_t)((tau + k) % nt) * N + p] = in[(size_t)r * mx + k]; }
+            CU(push(h->d.qfutIrf, tmp.data(), tmp.size() * 8));
+            break; }
+        case MR_ST_IRF_VOL: {
+            if (!h->on[M_IRF]) return fail(message, 1, "mr_set_state/IRF is not active");
+            std::vector<double> tmp(N);
+            for (int r = 0; r < N; ++r) tmp[T.rch2pos[r]] = in[r];
+            CU(push(h->d.vol1[M_IRF], tmp.data(), 8L * N));
+            break; }
+        case MR_ST_LAKE_VOL: {
+            std::vector<double> tmp(N);
+            for (int q = 0; q < h->opt.n_routes; ++q) {
+                for (int r = 0; r < N; ++r) tmp[T.rch2pos[r]] = in[(size_t)q * N + r];
+                CU(push(h->d.vol1[h->opt.route_methods[q]], tmp.data(), 8L * N));
+            }
+            break; }
+        case MR_ST_KWT_NWAVE: case MR_ST_KWT_ROUTED: {
+            if (!h->on[M_KWT]) return fail(message, 1, "mr_set_state/KWT is not active");
+            const int b = (int)((tau + 1) & 1);
+            std::vector<int> tmp(N);
+            if (var == MR_ST_KWT_NWAVE) {
+                for (int r = 0; r < N; ++r) { if (iin[r] < 0 || iin[r] > KWS) return fail(message, 1, "mr_set_state/numWaves outside [0, MR_KW_SLOTS]"); tmp[T.rch2pos[r]] = iin[r]; }
+                CU(push(h->d.kwN[b], tmp.data(), 4L * N));
+            } else {                                      // routed flags must be a prefix (they always are, kwt_route.f90:303-311,1436)
+                for (int r = 0; r < N; ++r) {
+                    int nr = 0; bool gap = false;
+                    for (int k = 0; k < KWS; ++k) { const int f = iin[(size_t)r * KWS + k] != 0; if (f && gap) return fail(message, 1, "mr_set_state/routed flags are not a prefix of the wave array"); if (f) ++nr; else gap = true; }
+                    tmp[T.rch2pos[r]] = nr;
+                }
+                CU(push(h->d.kwNR[b], tmp.data(), 4L * N));
+            }
+            break; }
+        case MR_ST_KWT_QWAVE: case MR_ST_KWT_TENTRY: case MR_ST_KWT_TEXIT: {
+            if (!h->on[M_KWT]) return fail(message, 1, "mr_set_state/KWT is not active");
+            const int b = (int)((tau + 1) & 1);
+            std::vector<double> tmp((size_t)KWS * N);
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r];
+                for (int k = 0; k < KWS; ++k) tmp[(size_t)k * N + p] = in[(size_t)r * KWS + k]; }
+            double *dst = var == MR_ST_KWT_QWAVE ? h->d.kwQF[b] : (var == MR_ST_KWT_TENTRY ? h->d.kwTI[b] : h->d.kwTR[b]);
+            CU(push(dst, tmp.data(), tmp.size() * 8));
+            break; }
+        default: return fail(message, 1, "mr_set_state/unknown state variable");
+    }
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_steps_done(mr_handle h, long steps, char *message) {
+    if (!h || !h->hasNet) return fail(message, 1, "mr_set_steps_done/handle has no network");
+    if (steps < 0) return fail(message, 1, "mr_set_steps_done/negative step count");
+    // ring phases and the particle buffer parity are functions of the step count: re-seat the state
+    const char *where = "mr_set_steps_done";
+    if (steps == h->stepsDone) { put_msg(message, ""); return 0; }
+    std::vector<std::vector<char>> keep;
+    std::vector<int> vars = {MR_ST_BASIN_QFUTURE};
+    if (h->on[M_IRF]) vars.push_back(MR_ST_IRF_QFUTURE);
+    if (h->on[M_KWT]) { vars.push_back(MR_ST_KWT_NWAVE); vars.push_back(MR_ST_KWT_ROUTED); vars.push_back(MR_ST_KWT_QWAVE); vars.push_back(MR_ST_KWT_TENTRY); vars.push_back(MR_ST_KWT_TEXIT); }
+    for (int v : vars) { keep.emplace_back(state_bytes(h, v)); int e = mr_get_state(h, v, keep.back().data(), (long)keep.back().size(), message); if (e) return e; }
+    // carry row of BASIN_QR(1)
+    if (h->lastK > 0) { CU(cudaMemcpy(h->d.qrSer, h->d.qrSer + (size_t)h->lastK * h->d.nRch, 8L * h->d.nRch, cudaMemcpyDeviceToDevice)); h->lastK = 0; }
+    h->stepsDone = steps;
+    for (size_t i = 0; i < vars.size(); ++i) { int e = mr_set_state(h, vars[i], keep[i].data(), (long)keep[i].size(), message); if (e) return e; }
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_get_basin_uh(mr_handle h, double *frac_future, char *message) {
+    if (!h || !h->hasNet || !frac_future) return fail(message, 1, "mr_get_basin_uh/handle has no network or null output");
+    std::memcpy(frac_future, h->fracFuture.data(), sizeof(double) * h->fracFuture.size());
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_get_reach_uh(mr_handle h, int *ntdh, double *uh, char *message) {
+    if (!h || !h->hasNet || !ntdh || !uh) return fail(message, 1, "mr_get_reach_uh/handle has no network or null output");
+    if (!h->on[M_IRF]) return fail(message, 1, "mr_get_reach_uh/IRF is not active");
+    const int N = h->d.nRch, mx = h->maxtdh;
+    for (int r = 0; r < N; ++r) {
+        const int p = h->topo.rch2pos[r];
+        ntdh[r] = h->ntdh[p];
+        for (int k = 0; k < mx; ++k) uh[(size_t)r * mx + k] = h->uhHost[(size_t)k * N + p];
+    }
+    put_msg(message, "");
+    return 0;
+}
+
+long mr_get_info(mr_handle h, int key) {
+    if (!h) return -1;
+    switch (key) {
+        case MR_INFO_NRCH: return h->d.nRch;
+        case MR_INFO_NHRU: return h->d.nHRU;
+        case MR_INFO_NSTAGE: return h->topo.nStage;
+        case MR_INFO_NTDH_BAS: return h->ntdhBas;
+        case MR_INFO_MAXTDH: return h->maxtdh;
+        case MR_INFO_LAUNCHES_LAST: return h->launchesLast;
+        case MR_INFO_STEPS_DONE: return (long)h->stepsDone;
+        case MR_INFO_MAX_BATCH: return h->opt.max_batch;
+        case MR_INFO_MAX_NUPS: return h->topo.maxUps;
+        case MR_INFO_DEVICE_BYTES: return (long)(h->devBytes >> 10);
+        case MR_INFO_KWT_PARTICLES: {
+            if (!h->hasNet || !h->on[M_KWT]) return 0;
+            cudaSetDevice(h->opt.device);
+            cudaStreamSynchronize(h->stream);
+            const int N = h->d.nRch, b = (int)((h->stepsDone + 1) & 1);
+            std::vector<int> n(N), nr(N);
+            cudaMemcpy(n.data(), h->d.kwN[b], 4L * N, cudaMemcpyDeviceToHost);
+            cudaMemcpy(nr.data(), h->d.kwNR[b], 4L * N, cudaMemcpyDeviceToHost);
+            long tot = 0;
+            for (int p = 0; p < N; ++p) tot += n[p] - (nr[p] > 0 ? nr[p] - 1 : 0);
+            return tot;
+        }
+        default: return -1;
+    }
+}
+
+int mr_get_timing(mr_handle h, double *ms) {
+    if (!h || !ms) return 1;
+    for (int i = 0; i < 8; ++i) ms[i] = h->timing[i];
+    return 0;
+}
+
+void mr_destroy(mr_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->opt.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_device(h);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+}  // extern "C"

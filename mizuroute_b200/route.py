@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference's routing interface on top of the C ABI.
+
+`Router.main_route(basinRunoff)` is one call of the reference's `main_route` (main_route.f90:29-268) for the
+current time step `TSEC` (globalData.f90:112); the caller then advances time exactly as `update_time` does
+(init_model_data.f90:311-312).  `Router.route_batch(runoff)` is the same for a block of steps in one
+time-skewed wavefront on the device.  Errors surface as `RoutingError(ierr, message)` -- the reference's
+`ierr, message` pair -- instead of `handle_err -> MPI_Abort` (model_utils.f90:45-57).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .network import RiverNetwork, RouteOptions, RouteParams
+
+
+class RoutingError(RuntimeError):
+    def __init__(self, ierr: int, message: str):
+        super().__init__(f"ierr={ierr}: {message}")
+        self.ierr = ierr
+        self.message = message
+
+
+def _ptr(a: Optional[np.ndarray], ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class Router:
+    def __init__(self, net: RiverNetwork, params: RouteParams, opts: RouteOptions, device: int = 0, max_batch: int = 1):
+        self._L = capi.load()
+        self._h = C.c_void_p()
+        self._msg = C.create_string_buffer(capi.MR_STRLEN)
+        self.net, self.params, self.opts = net, params, opts
+        self.methods = [int(c) for c in opts.route_opt]          # read_control.f90:583-597
+        tc, lc = opts.conv()
+        o = capi.mr_options()
+        o.dt = float(opts.dt)
+        o.n_routes = len(self.methods)
+        for i, m in enumerate(self.methods[:8]):
+            o.route_methods[i] = m
+        o.doesBasinRoute = int(opts.doesBasinRoute)
+        o.hw_drain_point = int(opts.hw_drain_point)
+        o.min_length_route = float(opts.min_length_route)
+        o.is_lake_sim = int(bool(opts.is_lake_sim))
+        o.lakeRegulate = int(bool(opts.lakeRegulate))
+        o.LakeInputOption = int(opts.LakeInputOption)
+        o.runoffMin = float(opts.runoffMin)
+        o.time_conv, o.length_conv = tc, lc
+        o.fshape, o.tscale = params.fshape, params.tscale
+        o.velo, o.diff = params.velo, params.diff
+        o.mann_n, o.wscale = params.mann_n, params.wscale
+        o.device = int(device)
+        o.max_batch = int(max_batch)
+        self.max_batch = int(max_batch)
+        self._check(self._L.mr_create(C.byref(o), C.byref(self._h), self._msg))
+        n = net
+        self._check(self._L.mr_set_network(
+            self._h, n.nRch, n.nHRU, _ptr(n.segId, C.c_int), _ptr(n.downSegId, C.c_int), _ptr(n.hruSegId, C.c_int),
+            _ptr(n.area, C.c_double), _ptr(n.length, C.c_double), _ptr(n.slope, C.c_double), _ptr(n.width, C.c_double),
+            _ptr(n.man_n, C.c_double), _ptr(n.islake, C.c_int), _ptr(n.lakeModelType, C.c_int),
+            _ptr(n.D03_MaxStorage, C.c_double), _ptr(n.D03_Coefficient, C.c_double), _ptr(n.D03_Power, C.c_double),
+            _ptr(n.D03_S0, C.c_double), self._msg))
+        self.nRch, self.nHRU = n.nRch, n.nHRU
+        self.TSEC = [0.0, float(opts.dt)]                        # init_model_data.f90:600
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, ierr: int):
+        if ierr != 0:
+            raise RoutingError(ierr, self._msg.value.decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.mr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _advance(self, n: int):
+        for _ in range(n):
+            self.TSEC[0] = self.TSEC[1]
+            self.TSEC[1] = self.TSEC[0] + float(self.opts.dt)
+
+    # ------------------------------------------------------------------------------------------
+    def main_route(self, basinRunoff: np.ndarray):
+        """One reference `main_route` call for [TSEC(1),TSEC(2)], then `update_time`."""
+        r = np.ascontiguousarray(basinRunoff, dtype=np.float64)
+        if r.shape != (self.nHRU,):
+            raise ValueError("basinRunoff must have one value per HRU")
+        self._check(self._L.mr_step(self._h, self.TSEC[0], self.TSEC[1], _ptr(r, C.c_double), self._msg))
+        self._advance(1)
+
+    def route_batch(self, runoff, out=None, want_q: bool = True):
+        """Route runoff[K, nHRU]; returns REACH_Q[n_routes, K, nRch] (caller's reach order) or None.
+
+        `runoff` / `out` may be numpy arrays or anything exposing `data_ptr()` (pinned torch tensors)."""
+        K, rp = self._host_ptr(runoff, self.nHRU)
+        if want_q and out is None:
+            out = np.empty((len(self.methods), K, self.nRch))
+        op = None
+        if want_q:
+            _, op = self._host_ptr(out, self.nRch, rows=len(self.methods) * K)
+        self._check(self._L.mr_step_batch(self._h, K, self.TSEC[0], rp, op, self._msg))
+        self._advance(K)
+        return out if want_q else None
+
+    def upload_runoff(self, runoff):
+        K, rp = self._host_ptr(runoff, self.nHRU)
+        self._check(self._L.mr_upload_runoff(self._h, K, rp, self._msg))
+        return K
+
+    def route_resident(self, K: int):
+        self._check(self._L.mr_route_resident(self._h, int(K), self.TSEC[0], self._msg))
+        self._advance(K)
+
+    def download_q(self, K: int, out=None):
+        if out is None:
+            out = np.empty((len(self.methods), K, self.nRch))
+        _, op = self._host_ptr(out, self.nRch, rows=len(self.methods) * K)
+        self._check(self._L.mr_download_q(self._h, int(K), op, self._msg))
+        return out
+
+    @staticmethod
+    def _host_ptr(a, ncol: int, rows: Optional[int] = None):
+        if hasattr(a, "data_ptr"):                               # torch tensor (pinned host memory)
+            if a.dtype.itemsize != 8 or not a.is_contiguous() or a.device.type != "cpu":
+                raise ValueError("expected a contiguous float64 host tensor")
+            n = a.numel()
+            ptr = C.c_void_p(a.data_ptr())
+        else:
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
+                raise ValueError("expected a C-contiguous float64 array")
+            n = a.size
+            ptr = C.c_void_p(a.ctypes.data)
+        if n % ncol != 0:
+            raise ValueError("array size is not a multiple of the reach/HRU count")
+        k = n // ncol
+        if rows is not None and k != rows:
+            raise ValueError("output array has the wrong number of rows")
+        return k, ptr
+
+    # ------------------------------------------------------------------------------------------
+    def flux(self, field: int, method: int = 1) -> np.ndarray:
+        out = np.empty(self.nRch)
+        self._check(self._L.mr_get_flux(self._h, int(method), int(field), _ptr(out, C.c_double), self._msg))
+        return out
+
+    def info(self, key: int) -> int:
+        return int(self._L.mr_get_info(self._h, int(key)))
+
+    def timing(self) -> dict:
+        ms = (C.c_double * 8)()
+        self._L.mr_get_timing(self._h, ms)
+        return {"total": ms[0], "basin": ms[1], "route_network": ms[2], "h2d": ms[3], "d2h": ms[4]}
+
+    def basin_uh(self) -> np.ndarray:
+        out = np.empty(self.info(capi.INFO_NTDH_BAS))
+        self._check(self._L.mr_get_basin_uh(self._h, _ptr(out, C.c_double), self._msg))
+        return out
+
+    def reach_uh(self):
+        ntdh = np.empty(self.nRch, dtype=np.int32)
+        uh = np.empty((self.nRch, self.info(capi.INFO_MAXTDH)))
+        self._check(self._L.mr_get_reach_uh(self._h, _ptr(ntdh, C.c_int), _ptr(uh, C.c_double), self._msg))
+        return ntdh, uh
+
+    def _state_shape(self, var: int):
+        n, w = self.nRch, capi.MR_KW_SLOTS
+        return {
+            capi.ST_BASIN_QFUTURE: ((n, self.info(capi.INFO_NTDH_BAS)), np.float64),
+            capi.ST_BASIN_QR: ((n, 2), np.float64),
+            capi.ST_IRF_QFUTURE: ((n, self.info(capi.INFO_MAXTDH)), np.float64),
+            capi.ST_IRF_VOL: ((n,), np.float64),
+            capi.ST_KWT_NWAVE: ((n,), np.int32),
+            capi.ST_KWT_QWAVE: ((n, w), np.float64),
+            capi.ST_KWT_TENTRY: ((n, w), np.float64),
+            capi.ST_KWT_TEXIT: ((n, w), np.float64),
+            capi.ST_KWT_ROUTED: ((n, w), np.int32),
+            capi.ST_LAKE_VOL: ((len(self.methods), n), np.float64),
+        }[var]
+
+    def get_state(self, var: int) -> np.ndarray:
+        shape, dt = self._state_shape(var)
+        a = np.empty(shape, dtype=dt)
+        self._check(self._L.mr_get_state(self._h, int(var), C.c_void_p(a.ctypes.data), a.nbytes, self._msg))
+        return a
+
+    def set_state(self, var: int, a: np.ndarray):
+        shape, dt = self._state_shape(var)
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.shape != shape:
+            raise ValueError(f"state variable {var} expects shape {shape}")
+        self._check(self._L.mr_set_state(self._h, int(var), C.c_void_p(a.ctypes.data), a.nbytes, self._msg))
+
+    def set_steps_done(self, steps: int):
+        self._check(self._L.mr_set_steps_done(self._h, int(steps), self._msg))
+        self.TSEC = [float(steps) * float(self.opts.dt), float(steps + 1) * float(self.opts.dt)]
