@@ -36,7 +36,8 @@ struct DevNet {
     double dt, runoffMin, tconv, lconv, minLengthRoute;
     int doesBasinRoute, hwDrain, isLakeSim, lakeInputOption;
     // topology / parameters
-    const int *stageOf, *upFirst, *nUps, *nGood, *hruPtr, *hruIdx, *flags, *ntdh, *lakeType;
+    int nHead;
+    const int *stageOf, *upPtr, *upIdx, *nGood, *hruPtr, *hruIdx, *flags, *ntdh, *lakeType;
     const double *hruWgt, *basArea, *rlength, *rslope, *rwidth, *rmann;
     const double *uh, *fracFuture;
     const double *d03MaxS, *d03Coef, *d03Pow, *d03S0;
@@ -65,74 +66,84 @@ __device__ __forceinline__ void raise(int *err, int code, int p, int site) {
 // ------------------------------------------------------------------------------------------------
 // K1 + K2
 // ------------------------------------------------------------------------------------------------
-// One thread per reach, all K steps of the batch.  tau0 = number of steps completed before this batch
-// (ring phase).  ring/stride: the reach's UH window is ring[k*stride] for physical slot k.
-template <bool STAGED>
-__global__ void __launch_bounds__(128) k_basin(DevNet d, int K, long long tau0) {
-    extern __shared__ double s_ring[];
-    const int N = d.nRch, nb = d.ntdhBas;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = p < N;
-    double *ring; size_t stride;
-    if (STAGED) {
-        ring = s_ring + threadIdx.x; stride = blockDim.x;
-        if (live && d.doesBasinRoute == 1)
-            for (int k = 0; k < nb; ++k) ring[(size_t)k * stride] = d.qfutBas[(size_t)k * N + p];
-    } else {
-        ring = d.qfutBas + p; stride = (size_t)N;
-    }
-    if (!live) return;
+// One thread per reach, all K steps of the batch, in chunks of BASIN_TC steps:
+//   phase 1  basin2reach for the chunk's steps -> s_rr[t][thread]            (process_remap.f90:386-416)
+//   phase 2  the UH window (a ring: logical slot k of step tau lives at physical slot (tau+k) mod nb) is
+//            walked slot-group by slot-group; each physical slot is loaded ONCE per chunk, accumulates its
+//            chunk's contributions  uh[k]*rr[t]  in a register in step order (the same additions, in the
+//            same order, that irf_conv basinUH.f90:165-176 applies to that slot), emits BASIN_QR(1) when it
+//            becomes logical slot 0, and is stored once.  HBM traffic per reach-step: 16*nb/BASIN_TC bytes
+//            instead of the 16*nb of a per-step sweep.
+constexpr int BASIN_TC = 64;     // steps per chunk (shared memory: BASIN_TC * blockDim * 8 B)
+constexpr int BASIN_G = 8;       // slots in flight per thread (independent accumulation chains)
+constexpr int BASIN_TPB = 128;
 
-    const int h0 = d.hruPtr[p], h1 = d.hruPtr[p + 1];
-    const double area = d.basArea[p];
-    const bool lake = (d.flags[p] & FLAG_LAKE) != 0;
-    const bool ghost = (d.flags[p] & FLAG_GHOST) != 0;
-    int head = (int)(tau0 % nb);
-    double qr1 = d.qrSer[p];
+__global__ void __launch_bounds__(BASIN_TPB) k_basin(DevNet d, int K, long long tau0) {
+    extern __shared__ double s_dyn[];
+    double (*s_rr)[BASIN_TPB] = reinterpret_cast<double (*)[BASIN_TPB]>(s_dyn);   // [BASIN_TC][BASIN_TPB] reach runoff
+    double *s_uh = s_dyn + BASIN_TC * BASIN_TPB;                                  // [nb] hillslope UH
+    const int N = d.nRch, nb = d.ntdhBas;
+    const int p = blockIdx.x * BASIN_TPB + threadIdx.x;
+    for (int k = threadIdx.x; k < nb; k += BASIN_TPB) s_uh[k] = d.fracFuture[k];
+    const bool live = p < N && !(p < N && (d.flags[p] & FLAG_GHOST));
+    int h0 = 0, h1 = 0; double area = 0.0; bool lake = false;
+    if (live) { h0 = d.hruPtr[p]; h1 = d.hruPtr[p + 1]; area = d.basArea[p]; lake = (d.flags[p] & FLAG_LAKE) != 0; }
     double rr = 0.0;
-    if (!ghost) {
-        for (int t = 0; t < K; ++t) {
-            // basin2reach, process_remap.f90:386-416
-            if (h1 > h0) {
-                double r = 0.0;
-                for (int m = h0; m < h1; ++m) {
-                    const double ro = d.runoff[(size_t)t * d.nHRU + d.hruIdx[m]];
-                    if (ro < -1.e-3) raise(d.err, 20, p, E_NEG_RUNOFF);     // negRunoffTol, public_var.f90:31
-                    r = r + d.hruWgt[m] * ro * d.tconv * d.lconv;
-                }
-                if (r < d.runoffMin) r = d.runoffMin;
-                rr = r * area;
-            } else {
-                rr = d.runoffMin;
-            }
-            if (d.doesBasinRoute == 1) {
-                // irf_conv, basinUH.f90:165-176, on a ring: logical slot k lives at (head+k) mod nb
-                int s = head;
-                if (lake) {                                                // basinUH.f90:113-116 (UH = [1,0,...])
-                    for (int k = 0; k < nb; ++k) {
-                        const double u = (k == 0) ? 1.0 : 0.0;
-                        ring[(size_t)s * stride] = ring[(size_t)s * stride] + u * rr;
-                        if (++s == nb) s = 0;
+    for (int c0 = 0; c0 < K; c0 += BASIN_TC) {
+        const int nc = (K - c0 < BASIN_TC) ? K - c0 : BASIN_TC;
+        __syncthreads();                          // s_uh ready / previous chunk's s_rr consumed
+        if (live) {
+            for (int t = 0; t < nc; ++t) {
+                if (h1 > h0) {
+                    double r = 0.0;
+                    for (int m = h0; m < h1; ++m) {
+                        const double ro = d.runoff[(size_t)(c0 + t) * d.nHRU + d.hruIdx[m]];
+                        if (ro < -1.e-3) raise(d.err, 20, p, E_NEG_RUNOFF);     // negRunoffTol, public_var.f90:31
+                        r = r + d.hruWgt[m] * ro * d.tconv * d.lconv;
                     }
+                    if (r < d.runoffMin) r = d.runoffMin;
+                    rr = r * area;
                 } else {
-#pragma unroll 4
-                    for (int k = 0; k < nb; ++k) {
-                        ring[(size_t)s * stride] = ring[(size_t)s * stride] + d.fracFuture[k] * rr;
-                        if (++s == nb) s = 0;
+                    rr = d.runoffMin;
+                }
+                s_rr[t][threadIdx.x] = rr;
+                if (d.doesBasinRoute != 1) d.qrSer[(size_t)(c0 + t + 1) * N + p] = rr;   // main_route.f90:223-226
+            }
+        }
+        if (d.doesBasinRoute != 1 || !live) continue;
+        // phase 2.  Step t of the chunk has ring head (tau0+c0+t) mod nb; physical slot s is logical
+        // k = (s - head) mod nb at that step, i.e. k decreases by one per step and wraps from 0 to nb-1.
+        const int head0 = (int)((tau0 + c0) % nb);
+        for (int s0 = 0; s0 < nb; s0 += BASIN_G) {
+            double v[BASIN_G]; int k[BASIN_G];
+#pragma unroll
+            for (int g = 0; g < BASIN_G; ++g) {
+                const int s = s0 + g;
+                v[g] = (s < nb) ? d.qfutBas[(size_t)s * N + p] : 0.0;
+                int kk = s - head0; if (kk < 0) kk += nb;
+                k[g] = kk;
+            }
+            for (int t = 0; t < nc; ++t) {
+                const double x = s_rr[t][threadIdx.x];
+#pragma unroll
+                for (int g = 0; g < BASIN_G; ++g) {
+                    if (s0 + g < nb) {
+                        const double u = lake ? (k[g] == 0 ? 1.0 : 0.0) : s_uh[k[g]];      // basinUH.f90:113-116
+                        v[g] = v[g] + u * x;
+                        if (k[g] == 0) {          // this slot is BASIN_QR(1) of step t; it re-enters as slot nb-1 = 0
+                            d.qrSer[(size_t)(c0 + t + 1) * N + p] = v[g];
+                            v[g] = 0.0;
+                            k[g] = nb;
+                        }
+                        k[g] -= 1;
                     }
                 }
-                qr1 = ring[(size_t)head * stride];
-                ring[(size_t)head * stride] = 0.0;
-                if (++head == nb) head = 0;
-            } else {
-                qr1 = rr;                                                  // main_route.f90:223-226
             }
-            d.qrSer[(size_t)(t + 1) * N + p] = qr1;
+#pragma unroll
+            for (int g = 0; g < BASIN_G; ++g) if (s0 + g < nb) d.qfutBas[(size_t)(s0 + g) * N + p] = v[g];
         }
-        d.basinQI[p] = rr;
     }
-    if (STAGED && d.doesBasinRoute == 1)
-        for (int k = 0; k < nb; ++k) d.qfutBas[(size_t)k * N + p] = ring[(size_t)k * stride];
+    if (live) d.basinQI[p] = rr;
 }
 
 // carry BASIN_QR(1) of the previous batch into row 0 of the series
@@ -157,10 +168,10 @@ template <int M>
 __device__ void lake_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
     double *Qs = d.qSer[M] + (size_t)t * N;
-    const int nUps = d.nUps[p], u0 = d.upFirst[p];
+    const int u0 = d.upPtr[p], u1 = d.upPtr[p + 1];
     const double dt = d.dt;
     double qup = 0.0;
-    for (int m = 0; m < nUps; ++m) qup = qup + Qs[u0 + m];
+    for (int m = u0; m < u1; ++m) qup = qup + Qs[d.upIdx[m]];
     const int type = d.lakeType[p];
     double v1 = d.vol1[M][p];
     if (tau == 0) {                                    // iTime==1 cold start, lake_route.f90:139-157
@@ -236,8 +247,9 @@ __device__ __forceinline__ double thin_err(const double *Q, const double *T, int
 // remove_rch (kwt_route.f90:999-1123): greedy removal of the particle whose linear interpolation error is
 // smallest until MAXQPAR remain.  The reference re-packs index arrays each pass; a doubly linked list of
 // survivors visits them in the same order, so "first minimum" picks the same particle.
-__device__ int kwt_thin(double *Q, double *T, double *X, int &n, double *ERR) {
+__device__ __noinline__ int kwt_thin(double *Q, double *T, double *X, int &n) {
     unsigned char prv[WCAP], nxt[WCAP];
+    double ERR[WCAP];
     const int last = n - 1;
     for (int i = 0; i < n; ++i) { prv[i] = (unsigned char)(i - 1); nxt[i] = (unsigned char)(i + 1); ERR[i] = DBL_MAX; }
     for (int i = 1; i < last; ++i) ERR[i] = thin_err(Q, T, i - 1, i, i + 1);
@@ -261,7 +273,7 @@ __device__ int kwt_thin(double *Q, double *T, double *X, int &n, double *ERR) {
 // kinwav_rch (kwt_route.f90:1130-1439).  Qj/Te/Tx point at element 1 of the reach arrays (the particles to
 // route); on return elements 0..NQ2-1 hold flow, entry time and exit time, routed[] the FROUTE flags.
 __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
-                          double *Qj, double *Te, double *Tx, unsigned char *routed, int NQ1, int &NQ2) {
+                          double *Qj, double *Te, double *Tx, unsigned &routed, int NQ1, int &NQ2) {
     signed char IX[NKIN], MF[NKIN];
     double T0[NKIN], T1[NKIN], Q0[NKIN], Q1[NKIN], Q2[NKIN], WC[NKIN];
     NQ2 = 0;
@@ -315,7 +327,7 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
         Qj[ICOUNT - 1] = QNEW; Te[ICOUNT - 1] = TOLD; Tx[ICOUNT - 1] = TNEW;
         if (ICOUNT > 1) { if (Tx[ICOUNT - 1] <= Tx[ICOUNT - 2]) Tx[ICOUNT - 1] = Tx[ICOUNT - 2] + 1.0; }
         if (ICOUNT == 1 && Tx[0] <= T_START) Tx[0] = T_START + 1.0;
-        if (Tx[ICOUNT - 1] < T_END) routed[ICOUNT - 1] = 1;
+        if (Tx[ICOUNT - 1] < T_END) routed |= 1u << (ICOUNT - 1);
     };
     double TNEXT = 0.0;
     for (int IR = 1; IR <= NN; ++IR) {
@@ -345,84 +357,92 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
 // particle stream QD/TD (written at Qo/To).  Upstream particle arrays are read in place from the buffer the
 // upstream reaches wrote this step; nothing upstream is modified (the reference's strip, :840-844, is applied
 // by the owner when it reads its own state back, see kwt_reach).
+//
+// The reference re-brackets every series at every emitted time (:930-957).  Times are emitted in ascending
+// order and an un-exhausted series' current particle is never earlier than the emitted time, so the bracket
+// of series s is always [itim-1, itim] and changes only when s itself advances: each upstream particle is
+// loaded once and each segment slope computed once -- the same divisions on the same operands.
 __device__ int kwt_merge_upstream(const DevNet &d, int p, int t, int b, double T0, double T1,
                                   double *Qo, double *To, int room, int &ND) {
     const int N = d.nRch;
-    const int NUPB = d.nUps[p], u0 = d.upFirst[p];
+    const int u0 = d.upPtr[p], NUPB = d.upPtr[p + 1] - u0;
     const double W = d.rwidth[p];
     const double *qr0 = d.qrSer + (size_t)t * N, *qr1 = d.qrSer + (size_t)(t + 1) * N;
     ND = 0;
     int NUPR = 0;
-    for (int i = 0; i < NUPB; ++i) if (d.nGood[u0 + i] > 0) ++NUPR;
+    for (int i = 0; i < NUPB; ++i) if (d.nGood[d.upIdx[u0 + i]] > 0) ++NUPR;
     const int NUPS = NUPB + NUPR;
     if (NUPS == 1) {                                   // single headwater upstream, kwt_route.f90:743-759
-        Qo[0] = qr1[u0] / W; To[0] = T1; ND = 1;
+        Qo[0] = qr1[d.upIdx[u0]] / W; To[0] = T1; ND = 1;
         return 0;
     }
     if (NUPS > MAXSER) return -E_TOO_MANY_UPS;
-    int upos[MAXSER], slen[MAXSER], nrt[MAXSER], itim[MAXSER];
-    double ctime[MAXSER];
+    // per-series cursor: bracket [begin,end] = particles [itim-1, itim]
+    double qb[MAXSER], tb[MAXSER], qe[MAXSER], te[MAXSER], slope[MAXSER], scfac[MAXSER];
+    int upos[MAXSER]; short slen[MAXSER], nrt[MAXSER], itim[MAXSER];
     unsigned done = 0;
     const double *QF = d.kwQF[b], *TR = d.kwTR[b];
     int IMAX = NUPB, r = NUPB;
     for (int i = 0; i < NUPB; ++i) {
-        upos[i] = u0 + i; slen[i] = 2; nrt[i] = 2; itim[i] = 1; ctime[i] = T1;
-        if (d.nGood[u0 + i] > 0) {
-            const int U = u0 + i;
+        const int U = d.upIdx[u0 + i];
+        upos[i] = U; slen[i] = 2; nrt[i] = 2; itim[i] = 1;
+        qb[i] = qr0[U]; tb[i] = T0; qe[i] = qr1[U]; te[i] = T1;
+        slope[i] = (qe[i] - qb[i]) / (te[i] - tb[i]);
+        scfac[i] = 1.0 / W;
+        if (d.nGood[U] > 0) {
             const int NS = d.kwN[b][U], NR = d.kwNR[b][U];
             if (NS < 2 || NR < 1) return -E_NO_ROUTED_UP;
-            upos[r] = U; slen[r] = (NR + 1 < NS) ? NR + 1 : NS; nrt[r] = NR; itim[r] = 1;
-            ctime[r] = TR[(size_t)1 * N + U];
+            upos[r] = U; slen[r] = (short)((NR + 1 < NS) ? NR + 1 : NS); nrt[r] = (short)NR; itim[r] = 1;
+            qb[r] = QF[U]; tb[r] = TR[U]; qe[r] = QF[(size_t)N + U]; te[r] = TR[(size_t)N + U];
+            slope[r] = (qe[r] - qb[r]) / (te[r] - tb[r]);
+            scfac[r] = d.rwidth[U] / W;
             IMAX += NR - 1;
             ++r;
         }
     }
     if (IMAX > room) return -E_SCRATCH;
-    auto sQ = [&](int s, int k) -> double { return s < NUPB ? (k == 0 ? qr0[upos[s]] : qr1[upos[s]]) : QF[(size_t)k * N + upos[s]]; };
-    auto sT = [&](int s, int k) -> double { return s < NUPB ? (k == 0 ? T0 : T1) : TR[(size_t)k * N + upos[s]]; };
     const unsigned all = (NUPS == 32) ? 0xffffffffu : ((1u << NUPS) - 1u);
     int IPRT = 0, jOld = -1, iOld = -1;
+    double TIME_OLD = -DBL_MAX;
     for (;;) {
-        int J = 0;
-        for (int s = 1; s < NUPS; ++s) if (ctime[s] < ctime[J]) J = s;      // MINLOC: first minimum
+        int J = -1; double CT = DBL_MAX;               // MINLOC over CTIME: first minimum; exhausted series hold huge
+        for (int s = 0; s < NUPS; ++s) {
+            const double c = ((done >> s) & 1u) ? DBL_MAX : te[s];
+            if (J < 0 || c < CT) { J = s; CT = c; }
+        }
         if (J == jOld && itim[J] == iOld) return -E_STUCK;
         jOld = J; iOld = itim[J];
         if (!((done >> J) & 1u)) {
             if (!(itim[J] < nrt[J])) {                 // next particle not routed yet
-                done |= 1u << J; ctime[J] = DBL_MAX;
+                done |= 1u << J;
             } else {
-                const double CT = ctime[J];
-                const double TIME_OLD = (IPRT >= 1) ? To[IPRT - 1] : -DBL_MAX;
                 if (CT < TIME_OLD) return -E_TIME_ORDER;
                 if (CT != TIME_OLD) {
                     double Q_AGG = 0.0;
                     for (int s = 0; s < NUPS; ++s) {
-                        const int IWAV = itim[s];
-                        const double wU = (s < NUPB) ? 1.0 : d.rwidth[upos[s]];
-                        const double SCFAC = wU / W;
                         double SFLOW;
                         if (s == J) {
-                            SFLOW = sQ(s, IWAV) * SCFAC;
+                            SFLOW = qe[s] * scfac[s];
                         } else {
-                            int IBEG = IWAV;
-                            if (sT(s, IBEG) >= CT) IBEG = IWAV - 1;
-                            const int IEND = IBEG + 1;
-                            if (IBEG < 0 || IEND >= slen[s]) return -E_BRACKET;
-                            const double tb = sT(s, IBEG), te = sT(s, IEND);
-                            if (te < CT || tb > CT) return -E_BRACKET;
-                            const double qb = sQ(s, IBEG), qe = sQ(s, IEND);
-                            const double SLOPE = (qe - qb) / (te - tb);
-                            const double PREDV = qb + SLOPE * (CT - tb);
-                            SFLOW = PREDV * SCFAC;
+                            if (te[s] < CT || tb[s] > CT) return -E_BRACKET;
+                            const double PREDV = qb[s] + slope[s] * (CT - tb[s]);
+                            SFLOW = PREDV * scfac[s];
                         }
                         Q_AGG = Q_AGG + SFLOW;
                     }
                     IPRT = IPRT + 1;
                     if (IPRT > IMAX) return -E_QD_BOUNDS;
                     Qo[IPRT - 1] = Q_AGG; To[IPRT - 1] = CT;
+                    TIME_OLD = CT;
                 }
-                if (itim[J] == slen[J] - 1) { done |= 1u << J; ctime[J] = DBL_MAX; }
-                else { itim[J] = itim[J] + 1; ctime[J] = sT(J, itim[J]); }
+                if (itim[J] == slen[J] - 1) {
+                    done |= 1u << J;
+                } else {                               // advance the cursor of series J (reach series only: basins have 2 points)
+                    const int k = ++itim[J];
+                    qb[J] = qe[J]; tb[J] = te[J];
+                    qe[J] = QF[(size_t)k * N + upos[J]]; te[J] = TR[(size_t)k * N + upos[J]];
+                    slope[J] = (qe[J] - qb[J]) / (te[J] - tb[J]);
+                }
             }
         }
         if (done == all) break;
@@ -431,7 +451,7 @@ __device__ int kwt_merge_upstream(const DevNet &d, int p, int t, int b, double T
     return 0;
 }
 
-// kwt_rch (kwt_route.f90:36-346) for reach p at batch step t (absolute step tau).
+// kwt_rch (kwt_route.f90:36-346) for interior reach p at batch step t (absolute step tau).
 // State buffers: a reach writes its complete post-step particle array KWAVE(0:NQ2+1) and the number of routed
 // entries NR into buffer tau&1.  What the reference removes afterwards -- the downstream reach strips
 // KWAVE(0:NR-2) (:840-844), outlets and lake inlets strip themselves (:325-344) -- always leaves
@@ -450,8 +470,8 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
         d.kwQF[b][p] = -9999.0; d.kwTI[b][p] = -9999.0; d.kwTR[b][p] = -9999.0;
         return;
     }
-    double Q[WCAP], TE[WCAP], TX[WCAP], ERR[WCAP];
-    const int u0 = d.upFirst[p];
+    double Q[WCAP], TE[WCAP], TX[WCAP];
+    const int u0 = d.upPtr[p];
     const double W = d.rwidth[p];
 
     // getusq_rch, kwt_route.f90:461-613
@@ -465,8 +485,8 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
     }
     int ND = 0;
     if (d.flags[p] & FLAG_LAKE_UP) {                   // lake outlet reach, kwt_route.f90:540-559
-        if (d.nUps[p] > 1) { raise(d.err, 10, p, E_LAKE_UPS); return; }
-        Q[nOwn] = Qs[u0] / W; TE[nOwn] = T1; ND = 1;
+        if (d.upPtr[p + 1] - u0 > 1) { raise(d.err, 10, p, E_LAKE_UPS); return; }
+        Q[nOwn] = Qs[d.upIdx[u0]] / W; TE[nOwn] = T1; ND = 1;
     } else {
         const int e = kwt_merge_upstream(d, p, t, b, T0, T1, Q + nOwn, TE + nOwn, WCAP - nOwn, ND);
         if (e) { const int site = -e; raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site); return; }
@@ -479,19 +499,17 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
     for (int i = 0; i < n; ++i) if (Q[i] < 0.0) { raise(d.err, 20, p, E_NEG_FLOW); return; }
 
     double qup = 0.0;                                  // kwt_route.f90:168-174
-    for (int m = 0; m < nGood; ++m) qup = qup + Qs[u0 + m];
+    for (int m = 0; m < nGood; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
     d.inflow[M_KWT][p] = qup;
 
-    if (n > MR_MAXQPAR) { if (kwt_thin(Q, TE, TX, n, ERR)) { raise(d.err, 60, p, E_THIN); return; } }
+    if (n > MR_MAXQPAR) { if (kwt_thin(Q, TE, TX, n)) { raise(d.err, 60, p, E_THIN); return; } }
 
     const int NQ1 = n - 1;
-    unsigned char routed[NKIN];
-    for (int i = 0; i < NKIN; ++i) routed[i] = 0;
+    unsigned routed = 0;
     int NQ2;
     const int ek = kwt_kinwav(d, p, T0, T1, Q + 1, TE + 1, TX + 1, routed, NQ1, NQ2);
     if (ek) { raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); return; }
-    int NR = 0;
-    for (int i = 0; i < NQ1; ++i) NR += routed[i];     // count(FROUTE)-1 (FROUTE(0) is always true)
+    const int NR = __popc(routed);                     // count(FROUTE)-1 (FROUTE(0) is always true)
     if (NR + 1 > NQ2) { raise(d.err, 21, p, E_NO_NONROUTED); return; }
 
     double QNEW;
@@ -512,36 +530,40 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
 }
 
 // ------------------------------------------------------------------------------------------------
-// one wavefront: positions [lo,hi) hold stages w-K+1..w; the reach at stage s does step t = w - s
+// per-reach bodies of the three methods (route_network loop body, main_route.f90:372-390)
 // ------------------------------------------------------------------------------------------------
-template <int M>
-__global__ void __launch_bounds__(M == M_KWT ? 128 : 256) k_route(DevNet d, int lo, int hi, int w, long long tau0) {
-    const int p = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= hi) return;
-    const int t = w - d.stageOf[p];
-    const long long tau = tau0 + t;
+template <int M, bool HEAD>
+__device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
     const int flags = d.flags[p];
     if (flags & FLAG_GHOST) return;
     if (M != M_SUM && (flags & FLAG_LAKE)) { lake_reach<M>(d, p, t, tau); return; }
+    if (M == M_KWT && HEAD) {                          // no upstream reach => count(goodBas)=0, kwt_route.f90:181-205
+        const int b = (int)(tau & 1);
+        d.inflow[M_KWT][p] = 0.0;
+        d.qSer[M_KWT][(size_t)t * N + p] = d.qrSer[(size_t)(t + 1) * N + p];
+        d.kwN[b][p] = 1; d.kwNR[b][p] = 0;
+        d.kwQF[b][p] = -9999.0; d.kwTI[b][p] = -9999.0; d.kwTR[b][p] = -9999.0;
+        return;
+    }
     if (M == M_SUM) {                                  // accum_runoff.f90:60-75
         double *Qs = d.qSer[M_SUM] + (size_t)t * N;
-        const int nUps = d.nUps[p], u0 = d.upFirst[p];
+        const int u0 = d.upPtr[p], u1 = d.upPtr[p + 1];
         double q = d.qrSer[(size_t)(t + 1) * N + p];
-        if (nUps > 0) {
+        if (u1 > u0) {
             double qup = 0.0;
-            for (int m = 0; m < nUps; ++m) qup = qup + Qs[u0 + m];
+            for (int m = u0; m < u1; ++m) qup = qup + Qs[d.upIdx[m]];
             q = q + qup;
         }
         Qs[p] = q;
     } else if (M == M_IRF) {                           // irf_route.f90:82-150,235-262
         double *Qs = d.qSer[M_IRF] + (size_t)t * N;
-        const int nUps = d.nGood[p], u0 = d.upFirst[p];
+        const int nUps = d.nGood[p], u0 = d.upPtr[p];
         const double qr1 = d.qrSer[(size_t)(t + 1) * N + p], dt = d.dt;
         double v1 = d.vol1[M_IRF][p], v0 = v1;
         double qup = 0.0, qlat = 0.0;
         if (nUps > 0) {
-            for (int m = 0; m < nUps; ++m) qup = qup + Qs[u0 + m];
+            for (int m = 0; m < nUps; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
             qlat = qr1;
         } else if (d.hwDrain == 1) { qup = qup + qr1; qlat = 0.0; }
         else if (d.hwDrain == 2) { qlat = qr1; }
@@ -575,6 +597,23 @@ __global__ void __launch_bounds__(M == M_KWT ? 128 : 256) k_route(DevNet d, int 
     } else {
         kwt_reach(d, p, t, tau, d.T0s[t], d.T1s[t]);
     }
+}
+
+// headwater reaches (positions [0, nHead)): no upstream dependency, so one thread routes all K steps
+template <int M>
+__global__ void __launch_bounds__(256) k_headwater(DevNet d, int K, long long tau0) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= d.nHead) return;
+    for (int t = 0; t < K; ++t) route_reach<M, true>(d, p, t, tau0 + t);
+}
+
+// one wavefront of interior reaches: positions [lo,hi) hold stages w-K+1..w; the reach at stage s does step t = w - s
+template <int M>
+__global__ void __launch_bounds__(M == M_KWT ? 128 : 256) k_route(DevNet d, int lo, int hi, int w, long long tau0) {
+    const int p = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= hi) return;
+    const int t = w - d.stageOf[p];
+    route_reach<M, false>(d, p, t, tau0 + t);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,7 +40,7 @@ struct mr_handle_s {
     cudaEvent_t ev[6] = {nullptr};
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
-    int basinBlock = 128; bool basinStaged = false; size_t basinSmem = 0;
+    size_t basinSmem = 0;
 };
 
 namespace {
@@ -119,7 +119,7 @@ void launch_wavefronts(mr_handle h, int K, long long tau0) {
         const int slo = w - K + 1 > 0 ? w - K + 1 : 0;
         const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
         const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
-        if (hi <= lo) continue;
+        if (hi <= lo) continue;                  // stages that hold only headwaters
         k_route<M><<<(hi - lo + block - 1) / block, block, 0, h->stream>>>(h->d, lo, hi, w, tau0);
         h->launchesLast++;
     }
@@ -149,18 +149,18 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     k_times<<<1, 1, 0, h->stream>>>(T0, h->opt.dt, K, h->dT0s, h->dT1s);
     if (h->lastK > 0 && h->lastK != 0) k_carry_qr<<<(N + 255) / 256, 256, 0, h->stream>>>(d.qrSer, N, h->lastK);
     h->launchesLast += 2;
-    const int bb = h->basinBlock;
-    if (h->basinStaged && K > 1)
-        k_basin<true><<<(N + bb - 1) / bb, bb, h->basinSmem, h->stream>>>(d, K, h->stepsDone);
-    else
-        k_basin<false><<<(N + bb - 1) / bb, bb, 0, h->stream>>>(d, K, h->stepsDone);
+    k_basin<<<(N + BASIN_TPB - 1) / BASIN_TPB, BASIN_TPB, h->basinSmem, h->stream>>>(d, K, h->stepsDone);
     h->launchesLast++;
     CU(cudaEventRecord(h->ev[2], h->stream));
+    const int hb = (d.nHead + 255) / 256;
     for (int r = 0; r < h->opt.n_routes; ++r) {
         switch (h->opt.route_methods[r]) {
-            case M_SUM: launch_wavefronts<M_SUM>(h, K, h->stepsDone); break;
-            case M_IRF: launch_wavefronts<M_IRF>(h, K, h->stepsDone); break;
-            case M_KWT: launch_wavefronts<M_KWT>(h, K, h->stepsDone); break;
+            case M_SUM: if (hb) { k_headwater<M_SUM><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
+                        launch_wavefronts<M_SUM>(h, K, h->stepsDone); break;
+            case M_IRF: if (hb) { k_headwater<M_IRF><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
+                        launch_wavefronts<M_IRF>(h, K, h->stepsDone); break;
+            case M_KWT: if (hb) { k_headwater<M_KWT><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
+                        launch_wavefronts<M_KWT>(h, K, h->stepsDone); break;
         }
     }
     CU(cudaEventRecord(h->ev[3], h->stream));
@@ -267,8 +267,8 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     }
     if (o.is_lake_sim)
         for (int p = 0; p < N; ++p)
-            for (int m = 0; m < T.nUps[p]; ++m)
-                if (h->flags[T.upFirst[p] + m] & FLAG_LAKE) h->flags[p] |= FLAG_LAKE_UP;
+            for (int m = T.upPtr[p]; m < T.upPtr[p + 1]; ++m)
+                if (h->flags[T.upIdx[m]] & FLAG_LAKE) h->flags[p] |= FLAG_LAKE_UP;
 
     // unit hydrographs (process_param.f90)
     ierr = build_hillslope_uh(o.dt, o.fshape, o.tscale, h->fracFuture);
@@ -298,14 +298,14 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     // ---- device image
     DevNet &d = h->d;
     d = DevNet();
-    d.nRch = N; d.nHRU = nHRU; d.nStage = T.nStage; d.ntdhBas = h->ntdhBas; d.maxtdh = h->maxtdh;
+    d.nRch = N; d.nHRU = nHRU; d.nStage = T.nStage; d.nHead = T.nHead; d.ntdhBas = h->ntdhBas; d.maxtdh = h->maxtdh;
     d.dt = o.dt; d.runoffMin = o.runoffMin; d.tconv = o.time_conv; d.lconv = o.length_conv; d.minLengthRoute = o.min_length_route;
     d.doesBasinRoute = o.doesBasinRoute; d.hwDrain = o.hw_drain_point; d.isLakeSim = o.is_lake_sim; d.lakeInputOption = o.LakeInputOption;
     const int KB = o.max_batch;
     int e = 0;
 #define UP(field, vec) do { e = dev_upload_const(h, d.field, vec, where, message); if (e) return e; } while (0)
 #define AL(ptr, n) do { e = dev_alloc(h, &(ptr), (size_t)(n), where, message); if (e) return e; } while (0)
-    UP(stageOf, T.stageOf); UP(upFirst, T.upFirst); UP(nUps, T.nUps); UP(nGood, T.nGood);
+    UP(stageOf, T.stageOf); UP(upPtr, T.upPtr); UP(upIdx, T.upIdx); UP(nGood, T.nGood);
     UP(hruPtr, T.hruPtr); UP(hruIdx, T.hruIdx); UP(flags, h->flags); UP(ntdh, h->ntdh); UP(lakeType, ltype);
     UP(hruWgt, T.hruWgt); UP(basArea, T.basArea); UP(rlength, rlen); UP(rslope, rslp); UP(rwidth, rwid); UP(rmann, rman);
     UP(fracFuture, h->fracFuture);
@@ -347,20 +347,8 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
 #undef UP
 #undef AL
 
-    // hillslope-UH window staged in shared memory when one CTA's windows fit (else streamed from HBM)
-    h->basinBlock = 128; h->basinStaged = false; h->basinSmem = 0;
-    {
-        int maxSmem = 0;
-        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, o.device);
-        for (int bb = 128; bb >= 32; bb >>= 1) {
-            const size_t need = (size_t)h->ntdhBas * bb * sizeof(double);
-            if (need <= (size_t)maxSmem) {
-                h->basinBlock = bb; h->basinStaged = true; h->basinSmem = need;
-                CU(cudaFuncSetAttribute(k_basin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-                break;
-            }
-        }
-    }
+    h->basinSmem = sizeof(double) * ((size_t)BASIN_TC * BASIN_TPB + h->ntdhBas);
+    CU(cudaFuncSetAttribute(k_basin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->basinSmem));
     CU(cudaStreamSynchronize(h->stream));
     h->hasNet = true;
     put_msg(message, "");

@@ -10,13 +10,17 @@
 //   lake inlets                          network_topo.f90:958-985
 //
 // Device order ("stage order").  The reference sweeps reaches upstream->downstream in Strahler-order /
-// branch lists (main_route.f90:356-403).  Here every reach gets  stage = Dmax - (hops to its outlet),
-// so that stage(upstream) == stage(downstream) - 1 EXACTLY.  Reaches are stored stage by stage, and
-// inside a stage in the order their downstream reaches appear in the next stage, siblings in the
-// reference's UREACHI order.  Consequences the kernels rely on:
-//   * the upstream reaches of position p are the contiguous positions [up_first[p], up_first[p]+nUps[p]);
-//   * a time-skewed wavefront  w = stage + step  touches a contiguous position range;
-//   * a producer is exactly one wavefront ahead of its consumer, so 2-deep buffers suffice.
+// branch lists (main_route.f90:356-403).  Here
+//   * reaches WITHOUT upstream reaches ("headwaters", ~half of a river network) depend on nothing but their
+//     own lateral inflow; they are stored first and routed for all steps of a batch in one launch;
+//   * every other ("interior") reach gets  stage = Dmax - (hops to its outlet), so that
+//     stage(upstream interior reach) == stage(downstream) - 1 EXACTLY.  Interior reaches are stored stage by
+//     stage, inside a stage in the order their downstream reaches appear in the next stage.
+// Consequences the kernels rely on:
+//   * a time-skewed wavefront  w = stage + step  touches a contiguous position range of interior reaches only
+//     (warps are not diluted by trivial headwater lanes);
+//   * an interior producer is exactly one wavefront ahead of its consumer, so 2-deep particle buffers suffice;
+//   * upstream gathers (CSR upPtr/upIdx, kept in the reference's UREACHI order) are monotone in position.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -28,11 +32,11 @@
 namespace mr {
 
 struct Topology {
-    int nRch = 0, nHRU = 0, nStage = 0, maxUps = 0;
+    int nRch = 0, nHRU = 0, nStage = 0, maxUps = 0, nHead = 0;
     std::vector<int> pos2rch, rch2pos;          // device position <-> caller's reach index
     std::vector<int> stagePtr;                  // [nStage+1] position range of each stage
     std::vector<int> stageOf;                   // [nRch] by position
-    std::vector<int> upFirst, nUps, nGood;      // by position
+    std::vector<int> upPtr, upIdx, nGood;       // CSR by position (upIdx holds positions), nGood by position
     std::vector<int> downPos;                   // by position, -1 for outlets
     std::vector<int> hruPtr, hruIdx;            // CSR by position; hruIdx in caller's HRU order
     std::vector<double> hruWgt;
@@ -86,26 +90,43 @@ inline int build_topology(int nRch, int nHRU, const int *segId, const int *downS
     if (visited != nRch) { err = "build_topology/river network has a cycle or a dangling downstream id"; return 20; }
     T.nStage = (int)byHops.size();
 
-    T.pos2rch.resize(nRch); T.rch2pos.resize(nRch); T.stagePtr.assign(T.nStage + 1, 0); T.stageOf.resize(nRch);
+    // interior reaches stage by stage (upstream-most stage first), headwaters pulled out in front
+    auto isHead = [&](int r) { return uPtr[r + 1] == uPtr[r]; };
+    std::vector<int> interior;                  // caller indices in device order
+    std::vector<int> stageCount(T.nStage, 0);
+    interior.reserve(nRch);
+    for (int s = 0; s < T.nStage; ++s)
+        for (int r : byHops[T.nStage - 1 - s]) if (!isHead(r)) { interior.push_back(r); stageCount[s]++; }
+    std::vector<int> heads;
+    heads.reserve(nRch - interior.size());
+    for (int r : interior)
+        for (int m = uPtr[r]; m < uPtr[r + 1]; ++m) if (isHead(uIdx[m])) heads.push_back(uIdx[m]);
+    for (int i = 0; i < nRch; ++i) if (isHead(i) && down[i] < 0) heads.push_back(i);      // isolated reaches
+    T.nHead = (int)heads.size();
+    if ((size_t)T.nHead + interior.size() != (size_t)nRch) { err = "build_topology/internal: reach partition is inconsistent"; return 60; }
+
+    T.pos2rch.resize(nRch); T.rch2pos.resize(nRch); T.stagePtr.assign(T.nStage + 1, 0); T.stageOf.assign(nRch, -1);
     int p = 0;
-    for (int s = 0; s < T.nStage; ++s) {
-        const std::vector<int> &grp = byHops[T.nStage - 1 - s];
+    for (int r : heads) { T.pos2rch[p] = r; T.rch2pos[r] = p; ++p; }
+    for (int s = 0, k = 0; s < T.nStage; ++s) {
         T.stagePtr[s] = p;
-        for (int r : grp) { T.pos2rch[p] = r; T.rch2pos[r] = p; T.stageOf[p] = s; ++p; }
+        for (int c = 0; c < stageCount[s]; ++c, ++k) { const int r = interior[k]; T.pos2rch[p] = r; T.rch2pos[r] = p; T.stageOf[p] = s; ++p; }
     }
     T.stagePtr[T.nStage] = p;
 
-    T.upFirst.assign(nRch, 0); T.nUps.assign(nRch, 0); T.downPos.assign(nRch, -1);
+    T.upPtr.assign(nRch + 1, 0); T.upIdx.resize(uIdx.size()); T.downPos.assign(nRch, -1);
     T.maxUps = 0;
     for (int q = 0; q < nRch; ++q) {
         const int r = T.pos2rch[q];
         const int n = uPtr[r + 1] - uPtr[r];
-        T.nUps[q] = n;
-        T.upFirst[q] = n ? T.rch2pos[uIdx[uPtr[r]]] : 0;
+        T.upPtr[q + 1] = T.upPtr[q] + n;
+        for (int m = 0; m < n; ++m) {
+            const int up = T.rch2pos[uIdx[uPtr[r] + m]];
+            T.upIdx[T.upPtr[q] + m] = up;
+            if (T.stageOf[up] >= 0 && T.stageOf[up] != T.stageOf[q] - 1) { err = "build_topology/internal: stage lag is not one"; return 60; }
+        }
         T.downPos[q] = down[r] >= 0 ? T.rch2pos[down[r]] : -1;
         T.maxUps = std::max(T.maxUps, n);
-        for (int m = 0; m < n; ++m)
-            if (T.rch2pos[uIdx[uPtr[r] + m]] != T.upFirst[q] + m) { err = "build_topology/internal: upstream positions not contiguous"; return 60; }
     }
 
     // HRU lists in the caller's HRU order
@@ -124,11 +145,11 @@ inline int build_topology(int nRch, int nHRU, const int *segId, const int *downS
     T.basArea.assign(nRch, 0.0); T.upsArea.assign(nRch, 0.0); T.totArea.assign(nRch, 0.0); T.nGood.assign(nRch, 0);
     for (int q = 0; q < nRch; ++q) {
         double ups = 0.0, bas = 0.0;
-        for (int m = 0; m < T.nUps[q]; ++m) ups = ups + T.totArea[T.upFirst[q] + m];
+        for (int m = T.upPtr[q]; m < T.upPtr[q + 1]; ++m) ups = ups + T.totArea[T.upIdx[m]];
         for (int m = T.hruPtr[q]; m < T.hruPtr[q + 1]; ++m) bas += hruArea[T.hruIdx[m]];
         T.basArea[q] = bas; T.upsArea[q] = ups; T.totArea[q] = bas + ups;
         for (int m = T.hruPtr[q]; m < T.hruPtr[q + 1]; ++m) T.hruWgt[m] = hruArea[T.hruIdx[m]] / bas;
-        T.nGood[q] = (T.totArea[q] > DBL_MIN) ? T.nUps[q] : 0;
+        T.nGood[q] = (T.totArea[q] > DBL_MIN) ? (T.upPtr[q + 1] - T.upPtr[q]) : 0;
     }
     return 0;
 }

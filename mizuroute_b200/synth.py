@@ -168,42 +168,56 @@ def _down_index(net: RiverNetwork) -> np.ndarray:
 
 
 def add_lakes(net: RiverNetwork, n_lakes: int, rng: np.random.Generator, frac_endorheic: float = 0.2) -> None:
-    """C5: mark mid-network reaches as lakes.  80 % Doll-2003, 20 % endorheic.  A lake-outlet reach must
-    have the lake as its only upstream (kwt_route.f90:551), so only reaches that are the single
-    tributary of their downstream reach are eligible; lakes are kept at least one reach apart."""
+    """C5: turn mid-network reaches into lakes.  80 % Doll-2003, 20 % endorheic.  The reach below a lake must
+    have the lake as its only upstream (kwt_route.f90:551), so for every picked reach c a new "lake outlet"
+    reach is spliced in between c and its downstream reach (appended at the end, with its own HRU).  Lakes are
+    kept at least one reach apart."""
     n = net.nRch
     down = _down_index(net)
     nup = np.bincount(down[down >= 0], minlength=n)
-    elig = (nup > 0) & (down >= 0)
-    elig &= nup[np.maximum(down, 0)] == 1
-    cand = np.flatnonzero(elig)
+    cand = np.flatnonzero((nup > 0) & (down >= 0))
     rng.shuffle(cand)
-    # upstream CSR so neighbours of a picked lake can be blocked
     src = np.flatnonzero(down >= 0)
     o = np.argsort(down[src], kind="stable")
     up_idx = src[o]
     up_ptr = np.concatenate(([0], np.cumsum(nup)))
-    islake = np.zeros(n, dtype=np.int32)
     blocked = np.zeros(n, dtype=bool)
-    picked = 0
+    picked = []
     for c in cand:
-        if picked >= n_lakes:
+        if len(picked) >= n_lakes:
             break
         if blocked[c]:
             continue
-        islake[c] = 1
-        picked += 1
+        picked.append(int(c))
+        blocked[c] = True
         blocked[down[c]] = True
         blocked[up_idx[up_ptr[c]:up_ptr[c + 1]]] = True
-    ltype = np.ones(n, dtype=np.int32)
-    lk = np.flatnonzero(islake)
-    ltype[lk[rng.random(lk.size) < frac_endorheic]] = 0
+    picked = np.array(picked, dtype=np.int64)
+    endo = picked[rng.random(picked.size) < frac_endorheic]      # endorheic lakes are terminal: nothing flows out
+    doll = np.setdiff1d(picked, endo)
+    m = doll.size
+    new_id = (int(net.segId.max()) + 1 + np.arange(m)).astype(np.int32)
+    old_down_id = net.downSegId[doll].copy()
+    net.downSegId[doll] = new_id                                 # lake -> its outlet reach
+    net.downSegId[endo] = -1
+    net.segId = np.concatenate([net.segId, new_id])
+    net.downSegId = np.concatenate([net.downSegId, old_down_id]).astype(np.int32)
+    net.length = np.concatenate([net.length, np.clip(np.exp(rng.normal(np.log(2000.0), 0.6, m)), 100.0, 50000.0)])
+    net.slope = np.concatenate([net.slope, np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), m))])
+    net.hruSegId = np.concatenate([net.hruSegId, new_id])
+    net.hruId = np.concatenate([net.hruId, (new_id.astype(np.int64) + 50_000_000).astype(np.int32)])
+    net.area = np.concatenate([net.area, np.exp(rng.normal(np.log(5.0e6), 0.8, m))])
+    nn = n + m
+    islake = np.zeros(nn, dtype=np.int32)
+    islake[picked] = 1
+    ltype = np.ones(nn, dtype=np.int32)
+    ltype[endo] = 0
     net.islake = islake
     net.lakeModelType = ltype
-    net.D03_MaxStorage = np.where(islake == 1, np.exp(rng.normal(np.log(5.0e7), 1.0, n)), 0.0)
-    net.D03_Coefficient = np.where(islake == 1, rng.uniform(0.005, 0.05, n), 0.0)
+    net.D03_MaxStorage = np.where(islake == 1, np.exp(rng.normal(np.log(5.0e7), 1.0, nn)), 0.0)
+    net.D03_Coefficient = np.where(islake == 1, rng.uniform(0.005, 0.05, nn), 0.0)
     net.D03_Power = np.where(islake == 1, 1.5, 0.0)
-    net.D03_S0 = np.zeros(n)
+    net.D03_S0 = np.zeros(nn)
     net.meta["n_lakes"] = int(islake.sum())
 
 

@@ -17,7 +17,7 @@ def _run_both(net, params, opts, ro, batch):
     K = ro.shape[0]
     o = Oracle(net, params, opts)
     qo = o.run(ro)
-    r = Router(net, params, opts, max_batch=max(batch, 1))
+    r = Router(net, params, opts, max_batch=max(batch, 8))
     parts = []
     for s in range(0, K, batch):
         parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + batch])))
@@ -96,7 +96,7 @@ def test_state_roundtrip_and_restart():
     from mizuroute_b200 import capi
     from mizuroute_b200.route import Router
     net, params, opts, ro = case("random", n=150, seed=9, dt=3600.0, route_opt="12", steps=20)
-    o, r, qo, qg = _run_both(net, params, opts, ro[:12], 5)
+    o, r, qo, qg = _run_both(net, params, opts, ro[:12], 6)
     so = o.get_state()
     assert rel_err(r.get_state(capi.ST_BASIN_QFUTURE), so["qfuture"], 1e-30) <= IRF_RTOL
     ptr, _ = o.reach_uh()

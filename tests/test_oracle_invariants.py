@@ -1,0 +1,110 @@
+"""Physical / algebraic invariants of the routing path, checked on the oracle."""
+import numpy as np
+import pytest
+
+from mizuroute_b200 import synth
+from mizuroute_b200.network import RiverNetwork, RouteOptions, RouteParams
+from oracle import oracle as orc
+from tests.util import case, rel_err
+
+
+def test_unit_hydrographs_sum_to_one():
+    for dt in (900.0, 3600.0, 86400.0):
+        net, params, opts, ro = case("random", n=40, seed=2, dt=dt, route_opt="1", steps=1)
+        o = orc.Oracle(net, params, opts)
+        assert abs(o.frac_future().sum() - 1.0) < 1e-12          # process_param.f90:90
+        ptr, val = o.reach_uh()
+        for i in range(net.nRch):
+            assert abs(val[ptr[i]:ptr[i + 1]].sum() - 1.0) < 1e-12   # process_param.f90:246
+
+
+def test_default_uh_sizes_match_survey():
+    net, params, opts, ro = case("random", n=10, seed=2, dt=3600.0, route_opt="1", steps=1)
+    assert orc.Oracle(net, params, opts).frac_future().size == 189
+    net, params, opts, ro = case("random", n=10, seed=2, dt=86400.0, route_opt="1", steps=1)
+    assert orc.Oracle(net, params, opts).frac_future().size == 9
+
+
+def test_gammp_known_values():
+    import math
+    assert abs(orc.gammp(1.0, 2.0) - (1.0 - math.exp(-2.0))) < 1e-12            # P(1,x) = 1-exp(-x)
+    assert abs(orc.gammp(0.5, 1.0) - math.erf(1.0)) < 1e-9                      # P(1/2,x) = erf(sqrt x); Lanczos ~1e-10
+    assert orc.gammp(2.5, 0.0) == 0.0
+
+
+def test_constant_runoff_steady_state_equals_accumulation():
+    net, params, opts, _ = case("random", n=60, seed=3, dt=86400.0, route_opt="012", steps=1)
+    ro = np.full((160, net.nHRU), 3.0e-5)
+    q = orc.Oracle(net, params, opts).run(ro)
+    assert rel_err(q[1, -1], q[0, -1]) < 1e-3        # IRF (0.999 clamp and truncated UH tails)
+    assert rel_err(q[2, -1], q[0, -1]) < 1e-6        # KWT
+
+
+def test_irf_water_balance_closes():
+    net, params, opts, ro = case("random", n=80, seed=4, dt=3600.0, route_opt="1", steps=50)
+    o = orc.Oracle(net, params, opts)
+    o.run(ro)
+    assert np.max(np.abs(o.get(orc.F_WB, 1))) < 2e-5 * 50        # water_balance.f90:64 tolerance, with slack for scale
+
+
+def test_interp_rch_exact_on_linear_series_and_bad_bounds():
+    T = np.array([0.0, 10.0, 25.0, 40.0])
+    Q = 2.0 + 0.5 * T
+    ierr, q = orc.interp_rch(T, Q, 5.0, 30.0)
+    assert ierr == 0 and abs(q - (2.0 + 0.5 * 17.5)) < 1e-12
+    ierr, q = orc.interp_rch(T, Q, 12.0, 20.0)                   # both ends inside one segment (:1581-1587)
+    assert ierr == 0 and abs(q - (2.0 + 0.5 * 16.0)) < 1e-12
+    assert orc.interp_rch(T, Q, -1.0, 5.0)[0] != 0               # series does not bracket (:1548)
+    assert orc.interp_rch(T, Q, 5.0, 41.0)[0] != 0
+
+
+def test_remove_rch_keeps_ends_and_at_most_maxqpar():
+    rng = np.random.default_rng(0)
+    T = np.cumsum(rng.uniform(1, 5, 45))
+    Q = 1.0 + np.sin(T / 9.0) + 0.05 * rng.normal(size=45)
+    q2, t2, x2 = orc.remove_rch(Q, T, np.zeros(45))
+    assert q2.size == 20 and t2[0] == T[0] and t2[-1] == T[-1]
+    assert np.all(np.diff(t2) > 0)
+    # points on a straight line are removed first
+    T = np.arange(30.0); Q = np.where(T < 25, 3.0 + T, 100.0 - T)
+    q2, t2, _ = orc.remove_rch(Q, T, np.zeros(30))
+    assert 24.0 in t2 and 25.0 in t2
+
+
+def test_single_reach_kwt_step_arrives_after_travel_time():
+    """One channel reach below a headwater: a step in lateral inflow reaches the outlet after L/c,
+    c = (5/3) K^0.6 q^0.4 (kwt_route.f90:1293)."""
+    L, S, n_man, W = 20000.0, 1e-3, 0.03, 25.0
+    net = RiverNetwork(segId=[1, 2], downSegId=[2, -1], length=[1000.0, L], slope=[S, S], hruId=[11, 12], hruSegId=[1, 2],
+                       area=[1.0e9, 1.0], width=[W, W], man_n=[n_man, n_man])
+    opts = RouteOptions(dt=900.0, route_opt="2", doesBasinRoute=0, runoffMin=1e-15, units_qsim="m/s")
+    steps = 120
+    ro = np.full((steps, 2), 1.0e-9)
+    ro[20:, 0] = 2.0e-8                                          # 1 -> 20 m3/s from the headwater basin at t = 20*dt
+    q = orc.Oracle(net, RouteParams(), opts).run(ro)[0][:, 1]
+    K = np.sqrt(S) / n_man
+    c_hi = (5.0 / 3.0) * K ** 0.6 * (20.0 / W) ** 0.4
+    c_lo = (5.0 / 3.0) * K ** 0.6 * (1.0 / W) ** 0.4
+    t_arr = (np.argmax(q > 10.0) - 20) * 900.0                   # half-rise arrival after the step
+    assert L / c_hi - 1800.0 <= t_arr <= L / c_lo + 1800.0
+    assert abs(q[-1] - 20.0) / 20.0 < 1e-3
+
+
+def test_kwt_mass_conservation_over_closed_window():
+    net, params, opts, _ = case("random", n=40, seed=6, dt=3600.0, route_opt="02", steps=1, doesBasinRoute=0)
+    ro = np.full((400, net.nHRU), 1.0e-6)
+    ro[50:80] = 4.0e-5                                           # a storm, then recession back to base flow
+    q = orc.Oracle(net, params, opts).run(ro)
+    down = orc.Oracle(net, params, opts).down_index()
+    outlets = np.flatnonzero(down < 0)
+    vol_sum = q[0][:, outlets].sum()
+    vol_kwt = q[1][:, outlets].sum()
+    assert abs(vol_kwt - vol_sum) / vol_sum < 1e-2     # particle thinning and shock merging are not exactly conservative
+
+
+def test_zero_flow_aborts_kwt_like_the_reference():
+    net, params, opts, _ = case("random", n=20, seed=1, dt=86400.0, route_opt="2", steps=1)
+    opts.runoffMin = 0.0
+    with pytest.raises(orc.OracleError) as ei:                   # kwt_route.f90:1365-1368
+        orc.Oracle(net, params, opts).run(np.zeros((1, net.nHRU)))
+    assert ei.value.ierr == 20

@@ -1,0 +1,64 @@
+"""The C oracle against the independently written pure-Python twin (both restate the Fortran; parity of the
+reference itself is UNPINNED -- it ships no golden vectors and cannot be built here)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.twin import Twin
+from tests.util import case, rel_err
+
+
+def _both(net, params, opts, ro):
+    o = orc.Oracle(net, params, opts)
+    t = Twin(net, params, opts)
+    q = o.run(ro)
+    qt = {m: [] for m in t.methods}
+    for k in range(ro.shape[0]):
+        t.step(ro[k])
+        for m in t.methods:
+            qt[m].append(list(t.Q[m]))
+    return o, t, q, qt
+
+
+@pytest.mark.parametrize("dt,seed", [(3600.0, 5), (86400.0, 6), (10800.0, 7)])
+def test_all_methods_small_tree(dt, seed):
+    net, params, opts, ro = case("random", n=50, seed=seed, dt=dt, route_opt="012", steps=30, zero_area_frac=0.08)
+    o, t, q, qt = _both(net, params, opts, ro)
+    for i, m in enumerate(t.methods):
+        assert rel_err(q[i], np.array(qt[m])) <= 1e-12
+
+
+def test_thinning_shocks_disaggregation_paths_are_exercised():
+    net, params, opts, ro = case("random", n=60, seed=5, dt=3600.0, route_opt="2", steps=40)
+    orc.lib().mro_reset_counters()
+    o, t, q, qt = _both(net, params, opts, ro)
+    c = [orc.lib().mro_counter(i) for i in range(6)]
+    assert c[0] > 0 and c[1] > 0 and c[2] > 0 and c[3] > 0 and c[5] > 0, c
+    assert rel_err(q[0], np.array(qt[2])) <= 1e-12
+
+
+def test_lakes_doll_and_endorheic():
+    net, params, opts, ro = case("conus", n=1500, seed=4, dt=86400.0, route_opt="12", steps=10, lakes=15)
+    assert net.islake.sum() >= 10
+    o, t, q, qt = _both(net, params, opts, ro)
+    for i, m in enumerate(t.methods):
+        assert rel_err(q[i], np.array(qt[m])) <= 1e-12
+
+
+def test_unit_hydrographs_agree():
+    from oracle import twin
+    for dt in (900.0, 3600.0, 86400.0):
+        ff = twin.basin_uh(dt, 2.5, 86400.0)
+        net, params, opts, ro = case("random", n=5, seed=1, dt=dt, route_opt="1", steps=1)
+        o = orc.Oracle(net, params, opts)
+        assert np.array_equal(o.frac_future(), np.array(ff))
+        for L in (80.0, 1500.0, 25000.0, 120000.0):
+            assert np.array_equal(orc.make_uh_one(L, dt, 1.5, 5000.0), np.array(twin.make_uh(L, dt, 1.5, 5000.0)))
+
+
+def test_openmp_level_sweep_equals_serial_sweep():
+    """PET idea of the reference's test list: thread count must not change answers."""
+    net, params, opts, ro = case("conus", n=3000, seed=8, dt=86400.0, route_opt="12", steps=12)
+    a = orc.Oracle(net, params, opts, n_threads=1).run(ro)
+    b = orc.Oracle(net, params, opts, n_threads=4).run(ro)
+    assert np.array_equal(a, b)
