@@ -68,7 +68,8 @@ enum {
     MR_INFO_LAUNCHES_LAST = 5,   /* kernels launched by the last mr_step / mr_step_batch / mr_route_resident */
     MR_INFO_STEPS_DONE = 6,      /* iTime-1 (globalData iTime) */
     MR_INFO_MAX_BATCH = 7, MR_INFO_MAX_NUPS = 8, MR_INFO_KWT_PARTICLES = 9, /* live particles in the KWT state */
-    MR_INFO_DEVICE_BYTES = 10    /* bytes of HBM held by the handle (KiB) */
+    MR_INFO_DEVICE_BYTES = 10,   /* bytes of HBM held by the handle (KiB) */
+    MR_INFO_KWT_TOUCHED = 11, MR_INFO_NHEAD = 12, MR_INFO_SUM_NTDH = 13, MR_INFO_SUM_NUPS = 14
 };
 
 typedef struct mr_handle_s *mr_handle;
@@ -136,9 +137,19 @@ int mr_set_steps_done(mr_handle h, long steps, char *message);
 int mr_get_basin_uh(mr_handle h, double *frac_future /* [ntdh_bas] */, char *message);
 int mr_get_reach_uh(mr_handle h, int *ntdh /* [nRch] */, double *uh /* [nRch][maxtdh] */, char *message);
 
+/* Launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the handle's own stream),
+ * so callers can bracket the work with their own events and overlap it with other streams. */
+int mr_set_stream(mr_handle h, void *cuda_stream, char *message);
+
+/* Algorithmic-traffic accounting (bench only): when enabled the KWT kernel also accumulates, per reach, the
+ * number of wave particles it reads (own + upstream) and writes.  mr_get_info(MR_INFO_KWT_TOUCHED) returns and
+ * clears the total. */
+int mr_set_counting(mr_handle h, int enabled, char *message);
+
 long mr_get_info(mr_handle h, int key);
 /* device milliseconds of the last batch call, GPTL-region style (mpi_process.f90:1184-1339):
- * [0] whole call, [1] basin2reach+hillslope UH, [2] route_network (all methods), [3] H2D, [4] D2H */
+ * [0] whole call, [1] basin2reach+hillslope UH, [2] route_network (all methods), [3] H2D, [4] D2H,
+ * [5..7] route_network of the 1st..3rd method of route_opt */
 int mr_get_timing(mr_handle h, double *ms /* [8] */);
 
 void mr_destroy(mr_handle h);

@@ -22,12 +22,13 @@ R_WIDTH, TOTAREA, BASAREA, R_SLOPE = 10, 11, 12, 13
  ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL) = range(10)
 # info keys
 (INFO_NRCH, INFO_NHRU, INFO_NSTAGE, INFO_NTDH_BAS, INFO_MAXTDH, INFO_LAUNCHES_LAST, INFO_STEPS_DONE,
- INFO_MAX_BATCH, INFO_MAX_NUPS, INFO_KWT_PARTICLES, INFO_DEVICE_BYTES) = range(11)
+ INFO_MAX_BATCH, INFO_MAX_NUPS, INFO_KWT_PARTICLES, INFO_DEVICE_BYTES, INFO_KWT_TOUCHED, INFO_NHEAD, INFO_SUM_NTDH,
+ INFO_SUM_NUPS) = range(15)
 
 EXPORTS = [
     "mr_create", "mr_set_network", "mr_step", "mr_step_batch", "mr_upload_runoff", "mr_route_resident",
     "mr_download_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
-    "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy",
+    "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
 ]
 
 
@@ -92,6 +93,8 @@ def load(rebuild_if_stale: bool = True):
     L.mr_get_info.argtypes = [vp, C.c_int]
     L.mr_get_info.restype = C.c_long
     L.mr_get_timing.argtypes = [vp, dp]
+    L.mr_set_stream.argtypes = [vp, vp, cp]
+    L.mr_set_counting.argtypes = [vp, C.c_int, cp]
     L.mr_destroy.argtypes = [vp]
     L.mr_destroy.restype = None
     for name in EXPORTS:

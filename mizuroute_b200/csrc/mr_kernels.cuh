@@ -50,6 +50,7 @@ struct DevNet {
     int *kwN[2], *kwNR[2];
     double *kwQF[2], *kwTI[2], *kwTR[2];
     int *err;                       // [0] code (0 = ok) [1] position [2] site
+    unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
 };
 
 // site ids for error messages (decoded in mr_lib.cu)
@@ -292,16 +293,26 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
         WC[i] = aK * pow(Q1[i], p2);
     }
     if (NN > 1) {                                     // breaking waves, kwt_route.f90:1301-1349
+        // The reference rescans every adjacent pair after each merge; a pair's crossing point changes only when
+        // one of its two particles was merged, so the crossing points (and 1/WC) are cached and only the two
+        // pairs around a merge are recomputed -- same operands, same divisions.  +inf marks "no crossing".
+        double IWC[NKIN], XX[NKIN];
+        const double NOX = __longlong_as_double(0x7ff0000000000000LL);
+        for (int i = 1; i <= NN; ++i) IWC[i] = 1.0 / WC[i];
+        auto cross = [&](int IW) -> double {
+            const int JW = IW - 1;
+            if (WC[IW] == 0.0 || WC[JW] == 0.0) return NOX;
+            const double WDIFF = IWC[JW] - IWC[IW];
+            if (WDIFF == 0.0) return NOX;
+            if (WC[IW] == WC[JW]) return NOX;
+            return (T1[IW] - T1[JW]) / WDIFF;
+        };
+        for (int IW = 2; IW <= NN; ++IW) XX[IW] = cross(IW);
         double X = 0.0;
         for (;;) {
             double XB = XMX; int IXB = 0;
             for (int IW = 2; IW <= NN; ++IW) {
-                const int JW = IW - 1;
-                if (WC[IW] == 0.0 || WC[JW] == 0.0) continue;
-                const double WDIFF = 1.0 / WC[JW] - 1.0 / WC[IW];
-                if (WDIFF == 0.0) continue;
-                if (WC[IW] == WC[JW]) continue;
-                const double XXB = (T1[IW] - T1[JW]) / WDIFF;
+                const double XXB = XX[IW];
                 if (XXB < X || XXB > XB) continue;
                 XB = XXB; IXB = IW;
             }
@@ -314,9 +325,11 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
             const double A1 = pow(Q1[JXB] / K, p1);
             const double CM = (Q2[JXB] - Q1[JXB]) / (A2 - A1);
             T1[JXB] = T1[JXB] + XB / WC[JXB] - XB / CM;
-            WC[JXB] = CM;
+            WC[JXB] = CM; IWC[JXB] = 1.0 / CM;
             for (int i = IX[IXB]; i <= NI; ++i) MF[i] = (signed char)(MF[i] - 1);
-            for (int i = IXB; i <= NN; ++i) { IX[i] = IX[i + 1]; T1[i] = T1[i + 1]; WC[i] = WC[i + 1]; Q1[i] = Q1[i + 1]; Q2[i] = Q2[i + 1]; }
+            for (int i = IXB; i <= NN; ++i) { IX[i] = IX[i + 1]; T1[i] = T1[i + 1]; WC[i] = WC[i + 1]; IWC[i] = IWC[i + 1]; Q1[i] = Q1[i + 1]; Q2[i] = Q2[i + 1]; XX[i] = XX[i + 1]; }
+            if (JXB >= 2) XX[JXB] = cross(JXB);
+            if (IXB <= NN) XX[IXB] = cross(IXB);
             X = XB;
         }
     }
@@ -329,12 +342,14 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
         if (ICOUNT == 1 && Tx[0] <= T_START) Tx[0] = T_START + 1.0;
         if (Tx[ICOUNT - 1] < T_END) routed |= 1u << (ICOUNT - 1);
     };
-    double TNEXT = 0.0;
+    if (WC[1] < DBL_MIN) return 20;                                      // zero flow, kwt_route.f90:1365-1368
+    double TEXIT = fmin(XMX / WC[1] + T1[1], DBL_MAX);
     for (int IR = 1; IR <= NN; ++IR) {
-        if (WC[IR] < DBL_MIN) return 20;                                 // zero flow, kwt_route.f90:1365-1368
-        const double TEXIT = fmin(XMX / WC[IR] + T1[IR], DBL_MAX);
-        if (IR < NN) TNEXT = fmin(XMX / WC[IR + 1] + T1[IR + 1], DBL_MAX);
-        if (IR == NN) TNEXT = DBL_MAX;
+        double TNEXT = DBL_MAX;                                          // exit time of the next particle (computed once)
+        if (IR < NN) {
+            if (WC[IR + 1] < DBL_MIN) return 20;
+            TNEXT = fmin(XMX / WC[IR + 1] + T1[IR + 1], DBL_MAX);
+        }
         if (Q1[IR] != Q2[IR]) {
             if (TEXIT < T_END) {
                 const double TEXIT2 = fmin(TEXIT + 1.0, TEXIT + 0.5 * (fmin(TNEXT, T_END) - TEXIT));
@@ -347,6 +362,7 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
         } else {
             rupdate(Q1[IR], T1[IR], TEXIT);
         }
+        TEXIT = TNEXT;
     }
     if (bad) return 60;
     NQ2 = ICOUNT;
@@ -363,7 +379,7 @@ __device__ int kwt_kinwav(const DevNet &d, int p, double T_START, double T_END,
 // of series s is always [itim-1, itim] and changes only when s itself advances: each upstream particle is
 // loaded once and each segment slope computed once -- the same divisions on the same operands.
 __device__ int kwt_merge_upstream(const DevNet &d, int p, int t, int b, double T0, double T1,
-                                  double *Qo, double *To, int room, int &ND) {
+                                  double *Qo, double *To, int room, int &ND, int &nRead) {
     const int N = d.nRch;
     const int u0 = d.upPtr[p], NUPB = d.upPtr[p + 1] - u0;
     const double W = d.rwidth[p];
@@ -397,6 +413,7 @@ __device__ int kwt_merge_upstream(const DevNet &d, int p, int t, int b, double T
             slope[r] = (qe[r] - qb[r]) / (te[r] - tb[r]);
             scfac[r] = d.rwidth[U] / W;
             IMAX += NR - 1;
+            nRead += slen[r];
             ++r;
         }
     }
@@ -483,12 +500,12 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
         TE[i] = d.kwTI[bp][(size_t)(first + i) * N + p];
         TX[i] = d.kwTR[bp][(size_t)(first + i) * N + p];
     }
-    int ND = 0;
+    int ND = 0, ND_read = 0;
     if (d.flags[p] & FLAG_LAKE_UP) {                   // lake outlet reach, kwt_route.f90:540-559
         if (d.upPtr[p + 1] - u0 > 1) { raise(d.err, 10, p, E_LAKE_UPS); return; }
         Q[nOwn] = Qs[d.upIdx[u0]] / W; TE[nOwn] = T1; ND = 1;
     } else {
-        const int e = kwt_merge_upstream(d, p, t, b, T0, T1, Q + nOwn, TE + nOwn, WCAP - nOwn, ND);
+        const int e = kwt_merge_upstream(d, p, t, b, T0, T1, Q + nOwn, TE + nOwn, WCAP - nOwn, ND, ND_read);
         if (e) { const int site = -e; raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site); return; }
     }
     if (nPrev == 0) {                                  // cold start, kwt_route.f90:587-596
@@ -527,6 +544,7 @@ __device__ void kwt_reach(const DevNet &d, int p, int t, long long tau, double T
     for (int i = NR + 1; i <= NQ2; ++i) { oQ[(size_t)(i + 1) * N] = Q[i]; oI[(size_t)(i + 1) * N] = TE[i]; oR[(size_t)(i + 1) * N] = TX[i]; }
     d.kwN[b][p] = NQ2 + 2;
     d.kwNR[b][p] = NR + 2;
+    if (d.kwCount) d.kwCount[p] += (unsigned)(nOwn + ND_read + NQ2 + 2);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,8 +36,9 @@ struct mr_handle_s {
     int lastK = 0;
     int launchesLast = 0;
     double timing[8] = {0};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr};
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    cudaEvent_t ev[10] = {nullptr};
+    unsigned *dKwCount = nullptr;
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
@@ -109,6 +110,7 @@ void free_device(mr_handle h) {
     for (void *p : h->allocs) cudaFree(p);
     h->allocs.clear();
     h->devBytes = 0;
+    h->dKwCount = nullptr;
 }
 
 template <int M>
@@ -154,6 +156,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     CU(cudaEventRecord(h->ev[2], h->stream));
     const int hb = (d.nHead + 255) / 256;
     for (int r = 0; r < h->opt.n_routes; ++r) {
+        if (r > 0) CU(cudaEventRecord(h->ev[6 + r], h->stream));
         switch (h->opt.route_methods[r]) {
             case M_SUM: if (hb) { k_headwater<M_SUM><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
                         launch_wavefronts<M_SUM>(h, K, h->stepsDone); break;
@@ -187,6 +190,9 @@ void collect_timing(mr_handle h) {
     auto span = [&](int a, int b) { ms = 0.f; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return (double)ms; };
     h->timing[1] = span(1, 2);
     h->timing[2] = span(2, 3);
+    const int nr = h->opt.n_routes;
+    for (int r = 0; r < 3; ++r) h->timing[5 + r] = 0.0;
+    for (int r = 0; r < nr; ++r) h->timing[5 + r] = span(r == 0 ? 2 : 6 + r, r == nr - 1 ? 3 : 7 + r);
 }
 
 }  // namespace
@@ -218,8 +224,9 @@ int mr_create(const mr_options *opts, mr_handle *out, char *message) {
         return fail(message, 90, "mr_create/no usable CUDA device (this library has no CPU path)");
     }
     ce = cudaSetDevice(opts->device);
-    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking);
+    h->stream = h->ownStream;
+    for (int i = 0; i < 10 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
     if (ce != cudaSuccess) { delete h; CU(ce); }
     put_msg(message, "");
     *out = h;
@@ -682,6 +689,19 @@ long mr_get_info(mr_handle h, int key) {
         case MR_INFO_MAX_BATCH: return h->opt.max_batch;
         case MR_INFO_MAX_NUPS: return h->topo.maxUps;
         case MR_INFO_DEVICE_BYTES: return (long)(h->devBytes >> 10);
+        case MR_INFO_NHEAD: return h->topo.nHead;
+        case MR_INFO_SUM_NTDH: { long s = 0; for (int v : h->ntdh) s += v; return s; }
+        case MR_INFO_SUM_NUPS: return (long)h->topo.upIdx.size();
+        case MR_INFO_KWT_TOUCHED: {
+            if (!h->hasNet || !h->dKwCount) return 0;
+            cudaSetDevice(h->opt.device);
+            cudaStreamSynchronize(h->stream);
+            std::vector<unsigned> c(h->d.nRch);
+            cudaMemcpy(c.data(), h->dKwCount, 4L * h->d.nRch, cudaMemcpyDeviceToHost);
+            cudaMemset(h->dKwCount, 0, 4L * h->d.nRch);
+            long tot = 0; for (unsigned v : c) tot += v;
+            return tot;
+        }
         case MR_INFO_KWT_PARTICLES: {
             if (!h->hasNet || !h->on[M_KWT]) return 0;
             cudaSetDevice(h->opt.device);
@@ -698,6 +718,28 @@ long mr_get_info(mr_handle h, int key) {
     }
 }
 
+int mr_set_stream(mr_handle h, void *cuda_stream, char *message) {
+    const char *where = "mr_set_stream";
+    if (!h) return fail(message, 1, "mr_set_stream/null handle");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->ownStream;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_counting(mr_handle h, int enabled, char *message) {
+    const char *where = "mr_set_counting";
+    if (!h || !h->hasNet) return fail(message, 1, "mr_set_counting/handle has no network");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (enabled && !h->dKwCount) { int e = dev_alloc(h, &h->dKwCount, (size_t)h->d.nRch, where, message); if (e) return e; }
+    h->d.kwCount = enabled ? h->dKwCount : nullptr;
+    CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
 int mr_get_timing(mr_handle h, double *ms) {
     if (!h || !ms) return 1;
     for (int i = 0; i < 8; ++i) ms[i] = h->timing[i];
@@ -710,7 +752,7 @@ void mr_destroy(mr_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_device(h);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
 }
 

@@ -157,7 +157,17 @@ class Router:
     def timing(self) -> dict:
         ms = (C.c_double * 8)()
         self._L.mr_get_timing(self._h, ms)
-        return {"total": ms[0], "basin": ms[1], "route_network": ms[2], "h2d": ms[3], "d2h": ms[4]}
+        out = {"total": ms[0], "basin": ms[1], "route_network": ms[2], "h2d": ms[3], "d2h": ms[4]}
+        for i, m in enumerate(self.methods):
+            out["route_%s" % ("sum", "irf", "kwt")[m]] = ms[5 + i]
+        return out
+
+    def set_stream(self, cuda_stream: int):
+        """Launch on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
+        self._check(self._L.mr_set_stream(self._h, C.c_void_p(cuda_stream or None), self._msg))
+
+    def set_counting(self, on: bool):
+        self._check(self._L.mr_set_counting(self._h, int(on), self._msg))
 
     def basin_uh(self) -> np.ndarray:
         out = np.empty(self.info(capi.INFO_NTDH_BAS))

@@ -418,16 +418,22 @@ mro_t *mro_create(int nRch, int nHRU,
     if (make_basin_uh(dt, fshape, tscale, &h->ntdh_bas, &h->FRAC_FUTURE) != 0) { mro_destroy(h); return NULL; }
     ALLOC(h->uh_ptr, nRch + 1);
     if (h->onRoute[M_IRF]) {
-        double tmp[256]; int tot = 0;
-        for (i = 0; i < nRch; i++) { int n = make_uh_one(length[i], dt, velo, diff, tmp); h->uh_ptr[i + 1] = n; tot += n; if (n > h->maxtdh) h->maxtdh = n; }
-        for (i = 0; i < nRch; i++) h->uh_ptr[i + 1] += h->uh_ptr[i];
-        ALLOC(h->uh_val, tot); ALLOC(h->QFUTURE_IRF, tot);
+        /* make_uh is init-time work, independent per reach: built with all host threads (values do not depend on it) */
+        int tot = 0, mx = 0;
+        double *all = (double *)malloc(sizeof(double) * 240 * (size_t)(nRch > 0 ? nRch : 1));
+#pragma omp parallel for schedule(dynamic, 1024) reduction(max : mx)
         for (i = 0; i < nRch; i++) {
-            int n = make_uh_one(length[i], dt, velo, diff, tmp);
+            int n = make_uh_one(length[i], dt, velo, diff, all + (size_t)i * 240), kk;
             /* process_ntopo.f90:496-499: lake UH is an impulse (islake is only set when is_lake_sim) */
-            if (h->isLake[i]) { for (k = 0; k < n; k++) tmp[k] = 0.0; tmp[0] = 1.0; }
-            memcpy(h->uh_val + h->uh_ptr[i], tmp, sizeof(double) * n);
+            if (h->isLake[i]) { for (kk = 0; kk < n; kk++) all[(size_t)i * 240 + kk] = 0.0; all[(size_t)i * 240] = 1.0; }
+            h->uh_ptr[i + 1] = n;
+            if (n > mx) mx = n;
         }
+        h->maxtdh = mx;
+        for (i = 0; i < nRch; i++) { tot += h->uh_ptr[i + 1]; h->uh_ptr[i + 1] += h->uh_ptr[i]; }
+        ALLOC(h->uh_val, tot); ALLOC(h->QFUTURE_IRF, tot);
+        for (i = 0; i < nRch; i++) memcpy(h->uh_val + h->uh_ptr[i], all + (size_t)i * 240, sizeof(double) * (h->uh_ptr[i + 1] - h->uh_ptr[i]));
+        free(all);
     }
 
     /* cold start (init_model_data.f90:399-463,600) */
@@ -1112,6 +1118,7 @@ int mro_set(mro_t *h, int method, int field, const double *in)
     return 0;
 }
 void mro_set_itime(mro_t *h, long it) { h->iTime = it; }
+void mro_set_threads(mro_t *h, int n) { h->nThreads = n > 0 ? n : 1; }
 /* KWT state in the restart layout [seg][wave] (write_restart_pio.f90:1039-1134), wave dimension = cap */
 void mro_get_kwt_state(mro_t *h, int cap, int *numWaves, double *qf, double *ti, double *tr, unsigned char *rf)
 {

@@ -106,6 +106,9 @@ class Oracle:
             self.T1 = self.T0 + float(self.opts.dt)
         return q
 
+    def set_threads(self, n: int):
+        lib().mro_set_threads(self.h, C.c_int(int(n)))
+
     def get(self, field: int, method: int = M_IRF) -> np.ndarray:
         out = np.empty(self.net.nRch)
         assert lib().mro_get(self.h, C.c_int(method), C.c_int(field), _p(out, C.c_double)) == 0
@@ -155,6 +158,40 @@ class Oracle:
                                 _p(a[2], C.c_double), _p(rf, C.c_ubyte))
             st.update(kwt_n=nw, kwt_qf=a[0], kwt_ti=a[1], kwt_tr=a[2], kwt_rf=rf)
         return st
+
+
+def seed_oracle_from_router(o: "Oracle", r) -> None:
+    """Copy the complete routing state of a mizuroute_b200 Router (restart schema, mr_get_state) into an Oracle,
+    so both continue from the same spun-up state (used for full-size parity samples and the CPU baseline)."""
+    from mizuroute_b200 import capi
+    L, n = lib(), o.net.nRch
+    steps = r.info(capi.INFO_STEPS_DONE)
+    qf = np.ascontiguousarray(r.get_state(capi.ST_BASIN_QFUTURE))
+    L.mro_set_qfuture(o.h, _p(qf, C.c_double))
+    qr = r.get_state(capi.ST_BASIN_QR)
+    o.set(F_BASIN_QR0, np.ascontiguousarray(qr[:, 0])); o.set(F_BASIN_QR1, np.ascontiguousarray(qr[:, 1]))
+    if M_IRF in o.methods:
+        ptr, _ = o.reach_uh()
+        irf = r.get_state(capi.ST_IRF_QFUTURE)
+        ntdh = np.diff(ptr)
+        mask = np.arange(irf.shape[1])[None, :] < ntdh[:, None]
+        flat = np.ascontiguousarray(irf[mask])
+        assert flat.size == int(ptr[-1])
+        L.mro_set_qfuture_irf(o.h, _p(flat, C.c_double))
+        o.set(F_REACH_VOL1, r.get_state(capi.ST_IRF_VOL), M_IRF)
+    if M_KWT in o.methods:
+        nw = np.ascontiguousarray(r.get_state(capi.ST_KWT_NWAVE), dtype=np.int32)
+        qw = np.ascontiguousarray(r.get_state(capi.ST_KWT_QWAVE)); ti = np.ascontiguousarray(r.get_state(capi.ST_KWT_TENTRY))
+        tr = np.ascontiguousarray(r.get_state(capi.ST_KWT_TEXIT))
+        rf = np.ascontiguousarray(r.get_state(capi.ST_KWT_ROUTED).astype(np.uint8))
+        L.mro_set_kwt_state(o.h, C.c_int(qw.shape[1]), _p(nw, C.c_int), _p(qw, C.c_double), _p(ti, C.c_double), _p(tr, C.c_double), _p(rf, C.c_ubyte))
+    if o.opts.is_lake_sim:
+        lv = r.get_state(capi.ST_LAKE_VOL)
+        for i, m in enumerate(o.methods):
+            if m != M_SUM:
+                o.set(F_REACH_VOL1, np.ascontiguousarray(lv[i]), m)
+    L.mro_set_itime(o.h, C.c_long(steps + 1))
+    o.T0, o.T1 = r.TSEC[0], r.TSEC[1]
 
 
 def gammp(a, x):
