@@ -1,0 +1,61 @@
+// Device image of one routing domain (DevNet), constants and error plumbing shared by the kernels
+// (mr_kernels.cuh), the warp-cooperative KWT code (mr_kwt.cuh) and its single-lane host build (tests/emul).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include "../../include/mizuroute_b200.h"
+#include "mr_lanes.h"
+
+namespace mr {
+
+constexpr int KWS = MR_KW_SLOTS;      // particle slots per reach per buffer (restart schema)
+constexpr int KWP = 24;               // pitch of a reach's particle row in HBM: 192 B = 6 aligned 32-B sectors
+constexpr int WCAP = 160;             // per-warp particle scratch (own + merged upstream), see kwt_reach
+constexpr int MAXSER = 32;            // series merged at one confluence (basins + non-headwater reaches)
+constexpr int POOL = 208;             // staged upstream series points (<= WCAP + MAXSER + MAXSER/2)
+constexpr int NKIN = MR_MAXQPAR + 2;  // kinwav work arrays (1-based, <= 19 particles routed)
+
+enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
+enum { M_SUM = 0, M_IRF = 1, M_KWT = 2 };
+
+struct DevNet {
+    int nRch, nHRU, nStage, ntdhBas, maxtdh;
+    // options
+    double dt, runoffMin, tconv, lconv, minLengthRoute;
+    int doesBasinRoute, hwDrain, isLakeSim, lakeInputOption;
+    // topology / parameters
+    int nHead;
+    const int *stageOf, *upPtr, *upIdx, *nGood, *hruPtr, *hruIdx, *flags, *ntdh, *lakeType;
+    const double *hruWgt, *basArea, *rlength, *rslope, *rwidth, *rmann;
+    const double *uh, *fracFuture;
+    const double *kwK, *kwAK;       // KWT: sqrt(R_SLOPE)/R_MAN_N and ALFA*K**(1/ALFA) per reach (kwt_route.f90:1283-1296)
+    const double *d03MaxS, *d03Coef, *d03Pow, *d03S0;
+    // forcing and per-step times
+    const double *runoff, *T0s, *T1s;
+    // state and fluxes
+    double *qfutBas, *qrSer, *basinQI;
+    double *qSer[3], *vol0[3], *vol1[3], *inflow[3], *wb[3];
+    double *qfutIrf;
+    int *kwN[2], *kwNR[2];
+    double *kwQF[2], *kwTI[2], *kwTR[2];
+    int *err;                       // [0] code (0 = ok) [1] position [2] site
+    unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
+};
+
+// site ids for error messages (decoded in mr_lib.cu)
+enum {
+    E_NEG_RUNOFF = 1, E_LAKE_UPS = 2, E_NEG_FLOW = 3, E_SCRATCH = 4, E_STUCK = 5, E_TIME_ORDER = 6, E_BRACKET = 7,
+    E_QD_BOUNDS = 8, E_ZERO_FLOW = 9, E_TEXIT2 = 10, E_RUPDATE = 11, E_NO_NONROUTED = 12, E_INTERP = 13,
+    E_LAKE_TYPE = 14, E_TOO_MANY_UPS = 15, E_THIN = 16, E_NO_ROUTED_UP = 17
+};
+
+MR_DEV void raise(int *err, int code, int p, int site) {
+#if defined(__CUDACC__)
+    if (atomicCAS(&err[0], 0, code) == 0) { err[1] = p; err[2] = site; }
+#else
+    if (err[0] == 0) { err[0] = code; err[1] = p; err[2] = site; }
+#endif
+}
+
+
+}  // namespace mr

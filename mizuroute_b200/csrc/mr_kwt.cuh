@@ -1,0 +1,564 @@
+// Warp-cooperative kinematic-wave-tracking reach step: kwt_rch and callees, kwt_route.f90:36-1622.
+//
+// One team (a 32-lane warp on the device, see mr_lanes.h) routes one (reach, step).  The wave particles of the
+// reach live in the team's shared-memory scratch, one particle per lane:
+//   getusq_rch/qexmul_rch  every candidate exit time of the upstream series is ranked and evaluated by its own
+//                          lane (the reference's sequential k-way MINLOC merge, :895-976, visits candidates in
+//                          (time, series) order; rank, duplicate flag and interpolation brackets of a candidate
+//                          are functions of that order alone, so they are computed independently);
+//   remove_rch             lane-parallel error evaluation, team argmin ("first minimum", :1081) per removal;
+//   kinwav_rch             lane-parallel celerity (pow), crossing points and exit times; team argmin per shock
+//                          merge; the short order-dependent tails (rUpdate's +1 s fix-up, interp_rch) run on
+//                          lane 0 exactly as the reference's serial loops.
+// Every floating-point value is produced by the same operations on the same operands as the serial
+// restatement, so results do not depend on the lane count.
+//
+// HBM layout of the wave state (per buffer b, see kwt_reach_team): kwQF/kwTI/kwTR[b][p*KWP + k], kwN/kwNR[b][p].
+#pragma once
+#include "mr_dev.h"
+
+namespace mr {
+
+// per-team scratch (shared memory on the device)
+struct KwtScratch {
+    double Q[WCAP], TE[WCAP];          // Q_JRCH, TENTRY (0:n-1)
+    double TX[KWP];                    // T_EXIT: only element 0 is an input; 1..NQ2 are written by kinwav
+    union {
+        struct {                       // qexmul_rch: staged upstream series
+            double sq[POOL], st[POOL]; // flow and time of every staged point
+            double scf[MAXSER];        // UWIDTH / R_WIDTH(JRCH)
+            int upos[MAXSER];
+            short soff[MAXSER], slen[MAXSER], ncand[MAXSER], cmax[MAXSER], cbase[MAXSER];
+            unsigned char flag[WCAP];
+        } m;
+        struct {                       // remove_rch
+            double ERR[WCAP];
+            unsigned char prv[WCAP], nxt[WCAP];
+        } th;
+        struct {                       // kinwav_rch
+            double T0[NKIN], T1[NKIN], Q0[NKIN], Q1[NKIN], Q2[NKIN], WC[NKIN], IWC[NKIN], XX[NKIN], TEX[NKIN];
+            signed char IX[NKIN], MF[NKIN];
+        } k;
+    } u;
+};
+
+// interp_rch (kwt_route.f90:1444-1622) for a single output interval (TOLD/QOLD 0-based), as a team: the trapezoids
+// of the middle part are evaluated by the lanes and added by lane 0 in the
+// reference's order.  W is scratch of at least NOLD doubles.  QNEW is valid on lane 0.
+MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOLD, double T0, double T1, double *W, double &QNEW) {
+    const int lane = MR_LANE;
+    if (TOLD[0] > T0 || TOLD[NOLD - 1] < T1) return 1;
+    int ib = 0x7fffffff, ie = 0x7fffffff;
+    for (int i = lane; i < NOLD; i += MR_NL) {
+        const double tt = TOLD[i];
+        if (i >= 1 && T0 <= tt && i < ib) ib = i;
+        if (T1 <= tt && i < ie) ie = i;
+    }
+    int IBEG = team_min(ib), IEND = team_min(ie);
+    if (IBEG == 0x7fffffff) IBEG = 0;
+    if (IEND == 0x7fffffff) IEND = 0;
+    for (int IMID = IBEG + 1 + lane; IMID <= IEND; IMID += MR_NL)
+        W[IMID] = (TOLD[IMID] - TOLD[IMID - 1]) * 0.5 * (QOLD[IMID - 1] + QOLD[IMID]);
+    MR_SYNC();
+    if (lane == 0) {
+        if (T1 < TOLD[IBEG]) {
+            const double SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+            const double QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+            const double QEST1 = SLOPE * (T1 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+            QNEW = 0.5 * (QEST0 + QEST1);
+        } else {
+            double AREAB = 0.0, AREAE = 0.0, AREAM = 0.0;
+            if (T0 < TOLD[IBEG]) {
+                const double SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+                const double QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
+                AREAB = (TOLD[IBEG] - T0) * 0.5 * (QEST0 + QOLD[IBEG]);
+            }
+            if (T1 < TOLD[IEND]) {
+                const double SLOPE = (QOLD[IEND] - QOLD[IEND - 1]) / (TOLD[IEND] - TOLD[IEND - 1]);
+                const double QEST1 = SLOPE * (T1 - TOLD[IEND - 1]) + QOLD[IEND - 1];
+                AREAE = (T1 - TOLD[IEND - 1]) * 0.5 * (QOLD[IEND - 1] + QEST1);
+            }
+            if (IBEG < IEND) {
+                for (int IMID = IBEG + 1; IMID < IEND; ++IMID) AREAM = AREAM + W[IMID];
+                if (T1 == TOLD[IEND] && T0 < TOLD[IEND - 1]) AREAM = AREAM + W[IEND];
+            }
+            QNEW = (AREAB + AREAE + AREAM) / (T1 - T0);
+        }
+    }
+    return 0;
+}
+
+MR_DEV double thin_err(const double *Q, const double *T, int a, int m, int b) {
+    // |INTERP(T(m), Q(a), Q(b), T(a), T(b)) - Q(m)|, kwt_route.f90:1054,1062,1114-1121
+    return fabs((Q[a] + ((Q[b] - Q[a]) / (T[b] - T[a])) * (T[m] - T[a])) - Q[m]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// remove_rch (kwt_route.f90:999-1123): greedy removal of the particle whose linear-interpolation error is
+// smallest until MAXQPAR remain.  The reference re-packs index arrays each pass; a doubly linked list of
+// survivors visits them in the same order, so "first minimum" picks the same particle.  T_EXIT needs no
+// compaction: only element 0 (never removed) is read afterwards.
+// ------------------------------------------------------------------------------------------------
+MR_DEV int kwt_thin_team(KwtScratch &S, int &n) {
+    const int lane = MR_LANE;
+    double *Q = S.Q, *T = S.TE, *ERR = S.u.th.ERR;
+    unsigned char *prv = S.u.th.prv, *nxt = S.u.th.nxt;
+    const int last = n - 1;
+    for (int i = lane; i < n; i += MR_NL) {
+        prv[i] = (unsigned char)(i - 1); nxt[i] = (unsigned char)(i + 1);
+        ERR[i] = (i > 0 && i < last) ? thin_err(Q, T, i - 1, i, i + 1) : DBL_MAX;
+    }
+    MR_SYNC();
+    int count = n;
+    while (count - 1 >= MR_MAXQPAR) {
+        // removed particles hold ERR = DBL_MAX like the two ends, so a strict "<" never selects them
+        double emin = DBL_MAX; int sel = 0x7fffffff;
+        for (int i = lane; i < n; i += MR_NL) if (ERR[i] < emin) { emin = ERR[i]; sel = i; }
+        team_argmin_first(emin, sel);
+        if (sel <= 0 || sel >= last) return 1;
+        const int a = prv[sel], b = nxt[sel];
+        MR_SYNC();
+        if (lane == 0) {
+            if (a > 0) ERR[a] = thin_err(Q, T, prv[a], a, b);
+            ERR[sel] = DBL_MAX;
+        }
+        if (lane == (MR_NL > 1 ? 1 : 0)) {
+            if (b < last) ERR[b] = thin_err(Q, T, a, b, nxt[b]);
+        }
+        MR_SYNC();
+        if (lane == 0) { nxt[a] = (unsigned char)b; prv[b] = (unsigned char)a; nxt[sel] = 255; }
+        MR_SYNC();
+        --count;
+    }
+    // compact the survivors (positions only move left)
+    int pos = 0;
+    for (int base = 0; base < n; base += MR_NL) {
+        const int i = base + lane;
+        const bool keep = i < n && nxt[i] != 255;
+        double qv = 0.0, tv = 0.0;
+        if (keep) { qv = Q[i]; tv = T[i]; }
+        MR_SYNC();
+        int tot;
+        const int r = team_rank(keep, tot);
+        if (keep) { Q[pos + r] = qv; T[pos + r] = tv; }
+        pos += tot;
+        MR_SYNC();
+    }
+    n = pos;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kinwav_rch (kwt_route.f90:1130-1439) on particles S.Q/S.TE[1..NQ1]; on return elements 1..NQ2 of
+// S.Q/S.TE/S.TX hold flow, entry time and exit time, `routed` the FROUTE flags (bit i-1 = particle i).
+// Returns the reference's ierr (20 zero flow, 30 TEXIT==TEXIT2, 60 rUpdate bounds), identical on all lanes.
+// ------------------------------------------------------------------------------------------------
+MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START, double T_END, int NQ1, int &NQ2, unsigned &routed) {
+    const int lane = MR_LANE;
+    double *T0 = S.u.k.T0, *T1 = S.u.k.T1, *Q0 = S.u.k.Q0, *Q1 = S.u.k.Q1, *Q2 = S.u.k.Q2, *WC = S.u.k.WC, *IWC = S.u.k.IWC,
+           *XX = S.u.k.XX, *TEX = S.u.k.TEX;
+    signed char *IX = S.u.k.IX, *MF = S.u.k.MF;
+    NQ2 = 0; routed = 0;
+    if (NQ1 == 0) return 0;
+    const double ALFA = 5.0 / 3.0;
+    const double K = d.kwK[p];                         // sqrt(R_SLOPE)/R_MAN_N          (k_kwt_params, once per network)
+    const double aK = d.kwAK[p];                       // ALFA*K**(1/ALFA)
+    const double XMX = d.rlength[p];
+    const double p1 = 1.0 / ALFA, p2 = (ALFA - 1.0) / ALFA;
+    int NN = NQ1;
+    const int NI = NQ1;
+    for (int i = 1 + lane; i <= NI; i += MR_NL) {
+        MF[i] = (signed char)i; IX[i] = (signed char)i;
+        const double q = S.Q[i], te = S.TE[i];
+        Q0[i] = q; Q1[i] = q; Q2[i] = q;
+        T0[i] = te; T1[i] = te;
+        const double wc = aK * pow(q, p2);
+        WC[i] = wc; IWC[i] = 1.0 / wc;
+    }
+    MR_SYNC();
+    const double NOX = DBL_MAX * 2.0;                  // +inf: "no crossing"
+    // crossing point of particles IW-1 and IW (kwt_route.f90:1308-1319); 1/WC is cached per particle
+    auto cross = [&](int IW) -> double {
+        const int JW = IW - 1;
+        if (WC[IW] == 0.0 || WC[JW] == 0.0) return NOX;
+        const double WDIFF = IWC[JW] - IWC[IW];
+        if (WDIFF == 0.0) return NOX;
+        if (WC[IW] == WC[JW]) return NOX;
+        return (T1[IW] - T1[JW]) / WDIFF;
+    };
+    if (NN > 1) {                                      // breaking waves, kwt_route.f90:1301-1349
+        for (int IW = 2 + lane; IW <= NN; IW += MR_NL) XX[IW] = cross(IW);
+        MR_SYNC();
+        double X = 0.0;
+        for (;;) {
+            // serial scan: XB = XMX; for IW: if (XXB < X || XXB > XB) skip; else XB = XXB, IXB = IW  => minimum, last on ties
+            double XB = XMX; int IXB = 0;
+            for (int IW = 2 + lane; IW <= NN; IW += MR_NL) {
+                const double XXB = XX[IW];
+                if (XXB < X || XXB > XB) continue;
+                XB = XXB; IXB = IW;
+            }
+            team_argmin_last(XB, IXB);
+            if (XB == XMX) break;
+            NN = NN - 1;
+            const int JXB = IXB - 1;
+            const double q2n = fmax(Q2[JXB], Q2[IXB]), q1n = fmin(Q1[JXB], Q1[IXB]);
+            // the two pow() of a merge run on two lanes
+            double A2, A1;
+            if (MR_NL > 1) {
+                const double a = pow(((lane & 1) ? q1n : q2n) / K, p1);
+                A2 = team_bcast(a, 0); A1 = team_bcast(a, 1);
+            } else {
+                A2 = pow(q2n / K, p1); A1 = pow(q1n / K, p1);
+            }
+            const double CM = (q2n - q1n) / (A2 - A1);
+            const double t1n = T1[JXB] + XB / WC[JXB] - XB / CM;
+            const int ixb0 = IX[IXB];
+            // shifted values are read before anybody writes
+            double sT1 = 0.0, sWC = 0.0, sIWC = 0.0, sQ1 = 0.0, sQ2 = 0.0, sXX = 0.0; signed char sIX = 0;
+            const int i = IXB + lane;                  // NN <= NKIN-2 < MR_NL on the device; looped on the host
+#if defined(__CUDACC__)
+            if (i <= NN) { sIX = IX[i + 1]; sT1 = T1[i + 1]; sWC = WC[i + 1]; sIWC = IWC[i + 1]; sQ1 = Q1[i + 1]; sQ2 = Q2[i + 1]; sXX = XX[i + 1]; }
+            MR_SYNC();
+            if (i <= NN) { IX[i] = sIX; T1[i] = sT1; WC[i] = sWC; IWC[i] = sIWC; Q1[i] = sQ1; Q2[i] = sQ2; XX[i] = sXX; }
+            for (int j = ixb0 + lane; j <= NI; j += MR_NL) MF[j] = (signed char)(MF[j] - 1);
+#else
+            (void)i; (void)sT1; (void)sWC; (void)sIWC; (void)sQ1; (void)sQ2; (void)sXX; (void)sIX;
+            for (int j = ixb0; j <= NI; ++j) MF[j] = (signed char)(MF[j] - 1);
+            for (int j = IXB; j <= NN; ++j) { IX[j] = IX[j + 1]; T1[j] = T1[j + 1]; WC[j] = WC[j + 1]; IWC[j] = IWC[j + 1]; Q1[j] = Q1[j + 1]; Q2[j] = Q2[j + 1]; XX[j] = XX[j + 1]; }
+#endif
+            if (lane == 0) { Q2[JXB] = q2n; Q1[JXB] = q1n; T1[JXB] = t1n; WC[JXB] = CM; IWC[JXB] = 1.0 / CM; }
+            MR_SYNC();
+            if (lane == 0 && JXB >= 2) XX[JXB] = cross(JXB);
+            if (lane == (MR_NL > 1 ? 1 : 0) && IXB <= NN) XX[IXB] = cross(IXB);
+            MR_SYNC();
+            X = XB;
+        }
+    }
+    // exit times of the (merged) particles, kwt_route.f90:1363-1370
+    bool zero = false;
+    for (int IR = 1 + lane; IR <= NN; IR += MR_NL) {
+        if (WC[IR] < DBL_MIN) zero = true;
+        TEX[IR] = fmin(XMX / WC[IR] + T1[IR], DBL_MAX);
+    }
+    if (team_any(zero)) return 20;                     // zero flow, kwt_route.f90:1365-1368
+    MR_SYNC();
+    int ierr = 0, ICOUNT = 0;
+    if (NN == NI) {
+        // No particle merged: particle IR is emitted as entry IR with its own Q and TENTRY (already in place), so
+        // only T_EXIT is new.  rUpdate's fix-ups (:1431,1434) fire only where the raw exit times are not strictly
+        // increasing (or the first is not after T_START); when no lane sees that, the raw times are final.
+        bool viol = false;
+        for (int IR = 1 + lane; IR <= NN; IR += MR_NL) viol = viol || (IR == 1 ? TEX[1] <= T_START : TEX[IR] <= TEX[IR - 1]);
+        if (!team_any(viol)) {
+            unsigned rt = 0;
+            for (int IR = 1 + lane; IR <= NN; IR += MR_NL) {
+                const double tx = TEX[IR];
+                S.TX[IR] = tx;
+                if (tx < T_END) rt |= 1u << (IR - 1);
+            }
+            routed = team_or(rt);
+            NQ2 = NN;
+            MR_SYNC();
+            return 0;
+        }
+    }
+    if (lane == 0) {                                   // order-dependent emission + rUpdate, kwt_route.f90:1371-1437
+        int bad = 0;
+        auto rupdate = [&](double QNEW, double TOLD, double TNEW) {
+            ICOUNT = ICOUNT + 1;
+            if (ICOUNT > NQ1) { bad = 1; ICOUNT = NQ1; return; }
+            S.Q[ICOUNT] = QNEW; S.TE[ICOUNT] = TOLD; S.TX[ICOUNT] = TNEW;
+            if (ICOUNT > 1) { if (S.TX[ICOUNT] <= S.TX[ICOUNT - 1]) S.TX[ICOUNT] = S.TX[ICOUNT - 1] + 1.0; }
+            if (ICOUNT == 1 && S.TX[1] <= T_START) S.TX[1] = T_START + 1.0;
+            if (S.TX[ICOUNT] < T_END) routed |= 1u << (ICOUNT - 1);
+        };
+        for (int IR = 1; IR <= NN && !ierr; ++IR) {
+            const double TEXIT = TEX[IR];
+            const double TNEXT = IR < NN ? TEX[IR + 1] : DBL_MAX;
+            if (Q1[IR] != Q2[IR]) {
+                if (TEXIT < T_END) {
+                    const double TEXIT2 = fmin(TEXIT + 1.0, TEXIT + 0.5 * (fmin(TNEXT, T_END) - TEXIT));
+                    if (TEXIT2 == TEXIT) { ierr = 30; break; }
+                    rupdate(Q1[IR], T1[IR], TEXIT);
+                    rupdate(Q2[IR], T1[IR], TEXIT2);
+                } else {
+                    for (int JR = 1; JR <= NI; ++JR) if (MF[JR] == IR) rupdate(Q0[JR], T0[JR], TEXIT);
+                }
+            } else {
+                rupdate(Q1[IR], T1[IR], TEXIT);
+            }
+        }
+        if (!ierr && bad) ierr = 60;
+    }
+    ierr = team_bcast(ierr, 0);
+    NQ2 = team_bcast(ICOUNT, 0);
+    routed = team_bcast(routed, 0);
+    MR_SYNC();
+    return ierr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// qexmul_rch (kwt_route.f90:619-993): merge the upstream basin series and routed-particle series into one
+// particle stream QD/TD, written to S.Q/S.TE[nOwn ..].  Upstream particle rows are read in place from the buffer
+// the upstream reaches wrote this step; nothing upstream is modified (the reference's strip, :840-844, is
+// applied by the owner when it reads its own state back, see kwt_reach_team).
+//
+// Series s < NUPB: basin of upstream i, points (T0, QR0), (T1, QR1), width 1.  Series NUPB..: the wave of every
+// non-headwater upstream, points k = 0..slen-1.  A series' CANDIDATES are its points k = 1..ncand (routed, and
+// not beyond the series end); the sequential merge processes all candidates in (time, series) order, emits one
+// particle per distinct time, and interpolates every other series in the bracket [cursor-1, cursor], where
+// cursor = 1 + (number of that series' candidates already processed), capped at cmax.
+// Returns 0 or -site (identical on all lanes).
+// ------------------------------------------------------------------------------------------------
+MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, double T0, double T1, int nOwn, int &ND, int &nRead) {
+    const int lane = MR_LANE;
+    const int N = d.nRch;
+    const int u0 = d.upPtr[p], NUPB = d.upPtr[p + 1] - u0;
+    const double W = d.rwidth[p];
+    const double *qr0 = d.qrSer + (size_t)t * N, *qr1 = d.qrSer + (size_t)(t + 1) * N;
+    ND = 0;
+    if (2 * NUPB > MAXSER) return -E_TOO_MANY_UPS;
+    // series descriptors; upstream i is handled by lane i.  REACH_INFLOW (kwt_route.f90:168-174) is summed here too,
+    // while the upstream discharges are in flight with everything else.
+    int NUPR = 0, poolN = 2 * NUPB, M = NUPB;
+    bool bad = false;
+    const double *Qs = d.qSer[M_KWT] + (size_t)t * N;
+    const int nGood = d.nGood[p];
+    for (int base = 0; base < NUPB; base += MR_NL) {
+        const int i = base + lane;
+        int U = 0, NS = 0, NR = 0;
+        bool isr = false;
+        if (i < NUPB) {
+            U = d.upIdx[u0 + i];
+            const bool reach = d.nGood[U] > 0;
+            const double q0 = qr0[U], q1 = qr1[U];
+            if (i < nGood) S.TX[1 + i] = Qs[U];                      // parked in T_EXIT(1:), which kinwav fills only later
+            if (reach) { isr = true; NS = d.kwN[b][U]; NR = d.kwNR[b][U]; }
+            S.u.m.soff[i] = (short)(2 * i); S.u.m.slen[i] = 2; S.u.m.ncand[i] = 1; S.u.m.cmax[i] = 1; S.u.m.cbase[i] = (short)i;
+            S.u.m.scf[i] = 1.0 / W;
+            S.u.m.sq[2 * i] = q0; S.u.m.st[2 * i] = T0; S.u.m.sq[2 * i + 1] = q1; S.u.m.st[2 * i + 1] = T1;
+        }
+        if (isr && (NS < 2 || NR < 1)) bad = true;
+        const int sl = isr ? (NR + 1 < NS ? NR + 1 : NS) : 0;
+        int nc = isr ? (sl - 1 < NR - 1 ? sl - 1 : NR - 1) : 0;
+        if (nc < 0) nc = 0;
+        // one scan for three prefix sums: series rank (5 bits), pool offset and candidate base (10 bits each, <= 16*22)
+        int tot;
+        const int ex = team_excl_scan((isr ? 1 : 0) | (sl << 5) | (nc << 15), tot);
+        const int r = NUPB + NUPR + (ex & 31), off = poolN + ((ex >> 5) & 1023), cb = M + (ex >> 15);
+        NUPR += tot & 31; poolN += (tot >> 5) & 1023; M += tot >> 15;
+        if (isr) {
+            S.u.m.soff[r] = (short)off; S.u.m.slen[r] = (short)sl; S.u.m.ncand[r] = (short)nc;
+            S.u.m.cmax[r] = (short)(NR < sl - 1 ? NR : sl - 1); S.u.m.cbase[r] = (short)cb;
+            S.u.m.scf[r] = d.rwidth[U] / W; S.u.m.upos[r] = U;
+        }
+    }
+    MR_SYNC();
+    if (lane == 0) {
+        double qup = 0.0;
+        for (int m = 0; m < nGood; ++m) qup = qup + S.TX[1 + m];
+        d.inflow[M_KWT][p] = qup;
+    }
+    const int NUPS = NUPB + NUPR;
+    if (NUPS == 1) {                                   // single headwater upstream, kwt_route.f90:743-759
+        if (lane == 0) { S.Q[nOwn] = S.u.m.sq[1] / W; S.TE[nOwn] = T1; }
+        ND = 1;
+        MR_SYNC();
+        return 0;
+    }
+    if (NUPR == 0) {
+        // only headwater basins upstream: the merge emits the single time T1 (series 0 supplies it, the other
+        // basins are interpolated at their end point, :930-957)
+        if (lane == 0) {
+            double Q_AGG = 0.0;
+            for (int s = 0; s < NUPB; ++s) {
+                const double qb = S.u.m.sq[2 * s], qe = S.u.m.sq[2 * s + 1];
+                double SFLOW;
+                if (s == 0) SFLOW = qe * S.u.m.scf[0];
+                else { const double SLOPE = (qe - qb) / (T1 - T0); SFLOW = (qb + SLOPE * (T1 - T0)) * S.u.m.scf[s]; }
+                Q_AGG = Q_AGG + SFLOW;
+            }
+            S.Q[nOwn] = Q_AGG; S.TE[nOwn] = T1;
+        }
+        ND = 1;
+        MR_SYNC();
+        return 0;
+    }
+    if (team_any(bad)) return -E_NO_ROUTED_UP;
+    if (M > WCAP - nOwn || poolN > POOL) return -E_SCRATCH;
+    MR_SYNC();
+    // stage the upstream waves
+    for (int s = NUPB; s < NUPS; ++s) {
+        const int U = S.u.m.upos[s], o = S.u.m.soff[s], sl = S.u.m.slen[s];
+        const double *QF = d.kwQF[b] + (size_t)U * KWP, *TR = d.kwTR[b] + (size_t)U * KWP;
+        for (int k = lane; k < sl; k += MR_NL) { S.u.m.sq[o + k] = QF[k]; S.u.m.st[o + k] = TR[k]; }
+        nRead += sl;
+    }
+    MR_SYNC();
+    // one candidate per lane
+    bool ebrk = false, eord = false;
+    for (int base = 0; base < M; base += MR_NL) {
+        const int c = base + lane;
+        if (c < M) {
+            int J = 0;
+            while (J < NUPS - 1 && c >= S.u.m.cbase[J] + S.u.m.ncand[J]) ++J;
+            const int k = c - S.u.m.cbase[J] + 1;
+            const int oJ = S.u.m.soff[J];
+            const double CT = S.u.m.st[oJ + k];
+            if (k >= 2 && CT < S.u.m.st[oJ + k - 1]) eord = true;
+            int ord = 0; bool dup = false, brk = false;
+            double Q_AGG = 0.0;
+            for (int s = 0; s < NUPS; ++s) {
+                const int o = S.u.m.soff[s];
+                double SFLOW;
+                if (s == J) {
+                    ord += k - 1;
+                    SFLOW = S.u.m.sq[o + k] * S.u.m.scf[s];
+                } else {
+                    const int nc = S.u.m.ncand[s];
+                    int cnt = 0;
+                    for (int kk = 1; kk <= nc; ++kk) {
+                        const double tt = S.u.m.st[o + kk];
+                        if (tt < CT) ++cnt;
+                        else if (tt == CT && s < J) { ++cnt; dup = true; }
+                        else break;
+                    }
+                    ord += cnt;
+                    int cur = 1 + cnt;
+                    if (cur > S.u.m.cmax[s]) cur = S.u.m.cmax[s];
+                    const double tb = S.u.m.st[o + cur - 1], te = S.u.m.st[o + cur];
+                    const double qb = S.u.m.sq[o + cur - 1], qe = S.u.m.sq[o + cur];
+                    if (te < CT || tb > CT) brk = true;
+                    const double SLOPE = (qe - qb) / (te - tb);
+                    const double PREDV = qb + SLOPE * (CT - tb);
+                    SFLOW = PREDV * S.u.m.scf[s];
+                }
+                Q_AGG = Q_AGG + SFLOW;
+            }
+            if (brk && !dup) ebrk = true;
+            S.Q[nOwn + ord] = Q_AGG; S.TE[nOwn + ord] = CT; S.u.m.flag[ord] = dup ? 0 : 1;
+        }
+    }
+    if (team_any(eord)) return -E_TIME_ORDER;
+    if (team_any(ebrk)) return -E_BRACKET;
+    MR_SYNC();
+    // drop the duplicates (kwt_route.f90:926)
+    int pos = 0;
+    for (int base = 0; base < M; base += MR_NL) {
+        const int i = base + lane;
+        const bool keep = i < M && S.u.m.flag[i] != 0;
+        double qv = 0.0, tv = 0.0;
+        if (keep) { qv = S.Q[nOwn + i]; tv = S.TE[nOwn + i]; }
+        MR_SYNC();
+        int tot;
+        const int r = team_rank(keep, tot);
+        if (keep) { S.Q[nOwn + pos + r] = qv; S.TE[nOwn + pos + r] = tv; }
+        pos += tot;
+        MR_SYNC();
+    }
+    ND = pos;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kwt_rch (kwt_route.f90:36-346) for interior reach p at batch step t (absolute step tau).
+// State buffers: a reach writes its complete post-step particle array KWAVE(0:NQ2+1) and the number of routed
+// entries NR into buffer tau&1.  What the reference removes afterwards -- the downstream reach strips
+// KWAVE(0:NR-2) (:840-844), outlets and lake inlets strip themselves (:325-344) -- always leaves
+// KWAVE(NR-1:), so the owner simply starts reading at NR-1 next step, and the consumer (exactly one wavefront
+// behind, reading the same buffer) sees the unstripped array.
+// ------------------------------------------------------------------------------------------------
+MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long long tau, double T0, double T1) {
+    const int lane = MR_LANE;
+    const int N = d.nRch;
+    const int b = (int)(tau & 1), bp = b ^ 1;
+    double *Qs = d.qSer[M_KWT] + (size_t)t * N;
+    const double qr1 = d.qrSer[(size_t)(t + 1) * N + p];
+    const int nGood = d.nGood[p];
+    if (nGood == 0) {                                  // no contributing area upstream, kwt_route.f90:181-205
+        if (lane == 0) {
+            d.inflow[M_KWT][p] = 0.0;
+            Qs[p] = qr1;
+            d.kwN[b][p] = 1; d.kwNR[b][p] = 0;
+            const size_t row = (size_t)p * KWP;
+            d.kwQF[b][row] = -9999.0; d.kwTI[b][row] = -9999.0; d.kwTR[b][row] = -9999.0;
+        }
+        return;
+    }
+    const int u0 = d.upPtr[p];
+    const double W = d.rwidth[p];
+
+    // getusq_rch, kwt_route.f90:461-613
+    const int nPrev = d.kwN[bp][p], nrPrev = d.kwNR[bp][p];
+    const int first = nrPrev > 0 ? nrPrev - 1 : 0;
+    const int nOwn = nPrev > 0 ? nPrev - first : 1;
+    if (nPrev > 0) {
+        const size_t row = (size_t)p * KWP + first;
+        for (int i = lane; i < nOwn; i += MR_NL) { S.Q[i] = d.kwQF[bp][row + i]; S.TE[i] = d.kwTI[bp][row + i]; }
+        if (lane == 0) S.TX[0] = d.kwTR[bp][row];
+    }
+    int ND = 0, ND_read = 0;
+    if (d.flags[p] & FLAG_LAKE_UP) {                   // lake outlet reach, kwt_route.f90:540-559
+        if (d.upPtr[p + 1] - u0 > 1) { if (lane == 0) raise(d.err, 10, p, E_LAKE_UPS); return; }
+        if (lane == 0) {
+            S.Q[nOwn] = Qs[d.upIdx[u0]] / W; S.TE[nOwn] = T1;
+            double qup = 0.0;                          // kwt_route.f90:168-174
+            for (int m = 0; m < nGood; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
+            d.inflow[M_KWT][p] = qup;
+        }
+        ND = 1;
+    } else {
+        const int e = kwt_merge_team(d, S, p, t, b, T0, T1, nOwn, ND, ND_read);
+        if (e) {
+            const int site = -e;
+            if (lane == 0) raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site);
+            return;
+        }
+    }
+    MR_SYNC();
+    if (nPrev == 0 && lane == 0) {                     // cold start, kwt_route.f90:587-596
+        S.Q[0] = S.Q[nOwn]; S.TE[0] = T0 - (T1 - T0); S.TX[0] = T0;
+    }
+    MR_SYNC();
+    int n = nOwn + ND;
+    bool neg = false;
+    for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;
+    if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return; }
+
+    if (n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); return; } }
+
+    const int NQ1 = n - 1;
+    unsigned routed = 0;
+    int NQ2;
+    const int ek = kwt_kinwav_team(d, S, p, T0, T1, NQ1, NQ2, routed);
+    if (ek) { if (lane == 0) raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); return; }
+    const int NR = mr_popc(routed);                    // count(FROUTE)-1 (FROUTE(0) is always true)
+    if (NR + 1 > NQ2) { if (lane == 0) raise(d.err, 21, p, E_NO_NONROUTED); return; }
+
+    double QNEW = 0.0;
+    if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return; }
+    double Q_END = 0.0, TIMEI = 0.0;
+    if (lane == 0) {
+        Qs[p] = QNEW * W + qr1;                        // kwt_route.f90:273
+        // end-of-step point, kwt_route.f90:288-292
+        Q_END = S.Q[NR] + ((S.Q[NR + 1] - S.Q[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+        TIMEI = S.TE[NR] + ((S.TE[NR + 1] - S.TE[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+    }
+
+    // KWAVE(0:NQ2+1) = routed(0:NR) | end-of-step point | non-routed(NR+1:NQ2), kwt_route.f90:299-311
+    const size_t row = (size_t)p * KWP;
+    double *oQ = d.kwQF[b] + row, *oI = d.kwTI[b] + row, *oR = d.kwTR[b] + row;
+    for (int i = lane; i <= NQ2; i += MR_NL) {
+        const int j = i <= NR ? i : i + 1;
+        oQ[j] = S.Q[i]; oI[j] = S.TE[i]; oR[j] = S.TX[i];
+    }
+    if (lane == 0) {
+        oQ[NR + 1] = Q_END; oI[NR + 1] = TIMEI; oR[NR + 1] = T1;
+        d.kwN[b][p] = NQ2 + 2;
+        d.kwNR[b][p] = NR + 2;
+        if (d.kwCount) d.kwCount[p] += (unsigned)(nOwn + ND_read + NQ2 + 2);
+    }
+}
+
+}  // namespace mr

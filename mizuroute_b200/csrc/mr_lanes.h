@@ -1,0 +1,89 @@
+// Lane abstraction for warp-cooperative device code.
+//
+// Device build (nvcc): a "team" is one 32-lane warp; collectives are shuffles / ballots.
+// Host build (g++, tests/emul only): a team is ONE lane, every collective is the identity and every
+// `for (i = MR_LANE; i < n; i += MR_NL)` loop visits all items in order.  The host build exists so the
+// cooperative algorithms (which are written once, against these primitives) can be checked against the CPU
+// oracle without a GPU; it is test infrastructure and is never linked into libmizuroute_b200.so.
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define MR_DEV __device__ __forceinline__
+#define MR_DEV_NOINLINE __device__ __noinline__
+#define MR_LANE ((int)(threadIdx.x & 31u))
+#define MR_NL 32
+#define MR_SYNC() __syncwarp()
+#else
+#define MR_DEV inline
+#define MR_DEV_NOINLINE inline
+#define MR_LANE 0
+#define MR_NL 1
+#define MR_SYNC() ((void)0)
+#endif
+
+namespace mr {
+
+#if defined(__CUDACC__)
+MR_DEV bool team_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
+MR_DEV double team_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MR_DEV int team_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MR_DEV unsigned team_bcast(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+// number of lanes below this one whose pred is true; total = number of lanes with pred true
+MR_DEV int team_rank(bool pred, int &total) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    total = __popc(m);
+    return __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+}
+// exclusive prefix sum of v over lanes; total = sum over all lanes
+MR_DEV int team_excl_scan(int v, int &total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)(threadIdx.x & 31u) >= o) x += y;
+    }
+    total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+// Minimum of NON-NEGATIVE doubles (or +inf / NaN, which order above every finite value) with the warp-reduce
+// unit: for v >= 0 the IEEE bit pattern orders like the value, so two 32-bit REDUX.MIN give the 64-bit minimum.
+MR_DEV double team_min_nonneg(double v, bool &mine) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v + 0.0);     // -0.0 -> +0.0
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    mine = hi == mhi && lo == mlo;
+    return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
+}
+// lexicographic minimum of (v ascending, i ascending), v >= 0: Fortran MINLOC "first minimum"
+MR_DEV void team_argmin_first(double &v, int &i) {
+    bool mine;
+    v = team_min_nonneg(v, mine);
+    i = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)i : 0xffffffffu);
+}
+// lexicographic minimum of (v ascending, i DESCENDING), v >= 0: a serial "accept if not greater" scan keeps the last
+MR_DEV void team_argmin_last(double &v, int &i) {
+    bool mine;
+    v = team_min_nonneg(v, mine);
+    i = (int)__reduce_max_sync(0xffffffffu, mine ? (unsigned)i : 0u);
+}
+MR_DEV unsigned team_or(unsigned x) { return __reduce_or_sync(0xffffffffu, x); }
+MR_DEV int team_min(int x) { return __reduce_min_sync(0xffffffffu, x); }
+MR_DEV int mr_popc(unsigned x) { return __popc(x); }
+#else
+inline bool team_any(bool pred) { return pred; }
+inline double team_bcast(double v, int) { return v; }
+inline int team_bcast(int v, int) { return v; }
+inline unsigned team_bcast(unsigned v, int) { return v; }
+inline int team_rank(bool pred, int &total) { total = pred ? 1 : 0; return 0; }
+inline int team_excl_scan(int v, int &total) { total = v; return 0; }
+inline void team_argmin_first(double &, int &) {}
+inline void team_argmin_last(double &, int &) {}
+inline unsigned team_or(unsigned x) { return x; }
+inline int team_min(int x) { return x; }
+inline int mr_popc(unsigned x) { return __builtin_popcount(x); }
+#endif
+
+}  // namespace mr

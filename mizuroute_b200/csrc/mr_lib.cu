@@ -116,13 +116,13 @@ void free_device(mr_handle h) {
 template <int M>
 void launch_wavefronts(mr_handle h, int K, long long tau0) {
     const Topology &T = h->topo;
-    const int block = (M == M_KWT) ? 128 : 256;
     for (int w = 0; w < T.nStage + K - 1; ++w) {
         const int slo = w - K + 1 > 0 ? w - K + 1 : 0;
         const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
         const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
         if (hi <= lo) continue;                  // stages that hold only headwaters
-        k_route<M><<<(hi - lo + block - 1) / block, block, 0, h->stream>>>(h->d, lo, hi, w, tau0);
+        if constexpr (M == M_KWT) k_route_kwt<<<(hi - lo + KWT_WARPS - 1) / KWT_WARPS, 32 * KWT_WARPS, 0, h->stream>>>(h->d, lo, hi, w, tau0);
+        else k_route<M><<<(hi - lo + 255) / 256, 256, 0, h->stream>>>(h->d, lo, hi, w, tau0);
         h->launchesLast++;
     }
 }
@@ -328,20 +328,29 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     }
     if (h->on[M_IRF]) AL(d.qfutIrf, (size_t)h->maxtdh * N);
     if (h->on[M_KWT]) {
+        double *kK = nullptr, *kAK = nullptr;
+        AL(kK, N); AL(kAK, N);
+        k_kwt_params<<<(N + 255) / 256, 256, 0, h->stream>>>(N, d.rslope, d.rmann, kK, kAK);
+        d.kwK = kK; d.kwAK = kAK;
         for (int b = 0; b < 2; ++b) {
             AL(d.kwN[b], N); AL(d.kwNR[b], N);
-            AL(d.kwQF[b], (size_t)KWS * N); AL(d.kwTI[b], (size_t)KWS * N); AL(d.kwTR[b], (size_t)KWS * N);
+            AL(d.kwQF[b], (size_t)KWP * N); AL(d.kwTI[b], (size_t)KWP * N); AL(d.kwTR[b], (size_t)KWP * N);
         }
-        if (o.is_lake_sim) {                       // lake reaches hold the sentinel particle (init_model_data.f90:440-456)
+        // Reaches without contributing upstream area hold the sentinel particle (-9999, not routed; kwt_route.f90:181-205),
+        // and so do lake reaches from the start (init_model_data.f90:440-456).  Their rows never change: written once here.
+        {
             std::vector<int> n1(N, 0);
-            std::vector<double> s9((size_t)N, 0.0);
-            bool any = false;
-            for (int p = 0; p < N; ++p) if (h->flags[p] & FLAG_LAKE) { n1[p] = 1; s9[p] = -9999.0; any = true; }
-            if (any) for (int b = 0; b < 2; ++b) {
+            std::vector<double> s9((size_t)KWP * N, 0.0);
+            for (int p = 0; p < N; ++p) {
+                const bool lake = (h->flags[p] & FLAG_LAKE) != 0;
+                if (lake) n1[p] = 1;
+                if (lake || T.nGood[p] == 0) s9[(size_t)p * KWP] = -9999.0;
+            }
+            for (int b = 0; b < 2; ++b) {
                 CU(cudaMemcpy(d.kwN[b], n1.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwQF[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwTI[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwTR[b], s9.data(), sizeof(double) * N, cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwQF[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwTI[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
+                CU(cudaMemcpy(d.kwTR[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
             }
         }
     }
@@ -538,7 +547,7 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
             CU(pull(h->d.kwN[b], n.data(), 4L * N)); CU(pull(h->d.kwNR[b], nr.data(), 4L * N));
             std::vector<double> tmp;
             if (var == MR_ST_KWT_QWAVE || var == MR_ST_KWT_TENTRY || var == MR_ST_KWT_TEXIT) {
-                tmp.resize((size_t)KWS * N);
+                tmp.resize((size_t)KWP * N);
                 const double *src = var == MR_ST_KWT_QWAVE ? h->d.kwQF[b] : (var == MR_ST_KWT_TENTRY ? h->d.kwTI[b] : h->d.kwTR[b]);
                 CU(pull(src, tmp.data(), tmp.size() * 8));
             }
@@ -549,7 +558,7 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
                 if (var == MR_ST_KWT_NWAVE) { iout[r] = cnt; continue; }
                 for (int k = 0; k < KWS; ++k) {
                     if (var == MR_ST_KWT_ROUTED) iout[(size_t)r * KWS + k] = (k < cnt && first + k < nr[p]) ? 1 : 0;
-                    else out[(size_t)r * KWS + k] = k < cnt ? tmp[(size_t)(first + k) * N + p] : -9999.0;
+                    else out[(size_t)r * KWS + k] = k < cnt ? tmp[(size_t)p * KWP + first + k] : -9999.0;
                 }
             }
             break; }
@@ -625,9 +634,9 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
         case MR_ST_KWT_QWAVE: case MR_ST_KWT_TENTRY: case MR_ST_KWT_TEXIT: {
             if (!h->on[M_KWT]) return fail(message, 1, "mr_set_state/KWT is not active");
             const int b = (int)((tau + 1) & 1);
-            std::vector<double> tmp((size_t)KWS * N);
+            std::vector<double> tmp((size_t)KWP * N, -9999.0);
             for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r];
-                for (int k = 0; k < KWS; ++k) tmp[(size_t)k * N + p] = in[(size_t)r * KWS + k]; }
+                for (int k = 0; k < KWS; ++k) tmp[(size_t)p * KWP + k] = in[(size_t)r * KWS + k]; }
             double *dst = var == MR_ST_KWT_QWAVE ? h->d.kwQF[b] : (var == MR_ST_KWT_TENTRY ? h->d.kwTI[b] : h->d.kwTR[b]);
             CU(push(dst, tmp.data(), tmp.size() * 8));
             break; }

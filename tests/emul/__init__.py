@@ -1,0 +1,17 @@
+"""Host (single-lane) build of the warp-cooperative KWT code -- test infrastructure only, see kwt_emul.cpp."""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libkwt_emul.so")
+_SRC = os.path.join(_HERE, "kwt_emul.cpp")
+_CSRC = os.path.join(_HERE, "..", "..", "mizuroute_b200", "csrc")
+_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("mr_kwt.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
+
+
+def load():
+    if not os.path.exists(_SO) or any(os.path.getmtime(f) > os.path.getmtime(_SO) for f in _DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC",
+                               "-o", _SO, _SRC])
+    return C.CDLL(_SO)

@@ -1,0 +1,50 @@
+"""The warp-cooperative KWT code (mr_kwt.cuh), compiled for the host with one lane per team, against the CPU
+oracle.  Both evaluate the same operations on the same operands with libm pow(), so REACH_Q and the live
+particle counts must agree bit for bit -- including steps that thin (>20 particles) and merge shocks."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.oracle import Oracle
+from tests import emul
+from tests.util import case
+
+
+def _emul_vs_oracle(net, params, opts, ro):
+    K = ro.shape[0]
+    o = Oracle(net, params, opts)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.step(ro[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1)
+        qo[t] = o.get(orc.F_REACH_Q, orc.M_KWT)
+    L = emul.load()
+    qe = np.empty((K, net.nRch)); ne = np.empty(net.nRch, dtype=np.int32)
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
+    ierr = L.kwt_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
+                          p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
+                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double), p(ne, C.c_int), msg)
+    assert ierr == 0, msg.value.decode()
+    return o, qo, qe, ne
+
+
+@pytest.mark.parametrize("kind,n,dt,steps", [("random", 200, 3600.0, 60), ("random", 120, 86400.0, 30), ("conus", 3000, 3600.0, 48),
+                                             ("binary", 1023, 86400.0, 25)])
+def test_team_kwt_bit_exact_vs_oracle(kind, n, dt, steps):
+    net, params, opts, ro = case(kind, n=n, seed=21, dt=dt, route_opt="2", steps=steps)
+    orc.lib().mro_reset_counters()
+    o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro)
+    if kind != "binary":
+        assert orc.lib().mro_counter(0) > 0, "thinning was not exercised"
+    assert np.array_equal(qe, qo)
+    assert np.array_equal(ne, o.get_state()["kwt_n"])
+
+
+def test_team_kwt_zero_area_parents():
+    net, params, opts, ro = case("random", n=150, seed=5, dt=3600.0, route_opt="2", steps=30, zero_area_frac=0.15)
+    o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro)
+    assert np.array_equal(qe, qo)
