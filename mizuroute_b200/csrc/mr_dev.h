@@ -49,7 +49,7 @@ enum {
     E_LAKE_TYPE = 14, E_TOO_MANY_UPS = 15, E_THIN = 16, E_NO_ROUTED_UP = 17
 };
 
-MR_DEV void raise(int *err, int code, int p, int site) {
+MR_DEV_NOINLINE void raise(int *err, int code, int p, int site) {
 #if defined(__CUDACC__)
     if (atomicCAS(&err[0], 0, code) == 0) { err[1] = p; err[2] = site; }
 #else

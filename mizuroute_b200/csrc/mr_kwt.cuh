@@ -49,6 +49,7 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
     const int lane = MR_LANE;
     if (TOLD[0] > T0 || TOLD[NOLD - 1] < T1) return 1;
     int ib = 0x7fffffff, ie = 0x7fffffff;
+    MR_NOUNROLL
     for (int i = lane; i < NOLD; i += MR_NL) {
         const double tt = TOLD[i];
         if (i >= 1 && T0 <= tt && i < ib) ib = i;
@@ -57,6 +58,7 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
     int IBEG = team_min(ib), IEND = team_min(ie);
     if (IBEG == 0x7fffffff) IBEG = 0;
     if (IEND == 0x7fffffff) IEND = 0;
+    MR_NOUNROLL
     for (int IMID = IBEG + 1 + lane; IMID <= IEND; IMID += MR_NL)
         W[IMID] = (TOLD[IMID] - TOLD[IMID - 1]) * 0.5 * (QOLD[IMID - 1] + QOLD[IMID]);
     MR_SYNC();
@@ -79,6 +81,7 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
                 AREAE = (T1 - TOLD[IEND - 1]) * 0.5 * (QOLD[IEND - 1] + QEST1);
             }
             if (IBEG < IEND) {
+                MR_NOUNROLL
                 for (int IMID = IBEG + 1; IMID < IEND; ++IMID) AREAM = AREAM + W[IMID];
                 if (T1 == TOLD[IEND] && T0 < TOLD[IEND - 1]) AREAM = AREAM + W[IEND];
             }
@@ -88,7 +91,10 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
     return 0;
 }
 
-MR_DEV double thin_err(const double *Q, const double *T, int a, int m, int b) {
+// one out-of-line copy of pow(): its inlined body is ~250 instructions per call site
+MR_DEV_NOINLINE double mr_pow(double x, double y) { return pow(x, y); }
+
+MR_DEV_NOINLINE double thin_err(const double *Q, const double *T, int a, int m, int b) {
     // |INTERP(T(m), Q(a), Q(b), T(a), T(b)) - Q(m)|, kwt_route.f90:1054,1062,1114-1121
     return fabs((Q[a] + ((Q[b] - Q[a]) / (T[b] - T[a])) * (T[m] - T[a])) - Q[m]);
 }
@@ -104,15 +110,18 @@ MR_DEV int kwt_thin_team(KwtScratch &S, int &n) {
     double *Q = S.Q, *T = S.TE, *ERR = S.u.th.ERR;
     unsigned char *prv = S.u.th.prv, *nxt = S.u.th.nxt;
     const int last = n - 1;
+    MR_NOUNROLL
     for (int i = lane; i < n; i += MR_NL) {
         prv[i] = (unsigned char)(i - 1); nxt[i] = (unsigned char)(i + 1);
         ERR[i] = (i > 0 && i < last) ? thin_err(Q, T, i - 1, i, i + 1) : DBL_MAX;
     }
     MR_SYNC();
     int count = n;
+    MR_NOUNROLL
     while (count - 1 >= MR_MAXQPAR) {
         // removed particles hold ERR = DBL_MAX like the two ends, so a strict "<" never selects them
         double emin = DBL_MAX; int sel = 0x7fffffff;
+        MR_NOUNROLL
         for (int i = lane; i < n; i += MR_NL) if (ERR[i] < emin) { emin = ERR[i]; sel = i; }
         team_argmin_first(emin, sel);
         if (sel <= 0 || sel >= last) return 1;
@@ -132,6 +141,7 @@ MR_DEV int kwt_thin_team(KwtScratch &S, int &n) {
     }
     // compact the survivors (positions only move left)
     int pos = 0;
+    MR_NOUNROLL
     for (int base = 0; base < n; base += MR_NL) {
         const int i = base + lane;
         const bool keep = i < n && nxt[i] != 255;
@@ -167,12 +177,13 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
     const double p1 = 1.0 / ALFA, p2 = (ALFA - 1.0) / ALFA;
     int NN = NQ1;
     const int NI = NQ1;
+    MR_NOUNROLL
     for (int i = 1 + lane; i <= NI; i += MR_NL) {
         MF[i] = (signed char)i; IX[i] = (signed char)i;
         const double q = S.Q[i], te = S.TE[i];
         Q0[i] = q; Q1[i] = q; Q2[i] = q;
         T0[i] = te; T1[i] = te;
-        const double wc = aK * pow(q, p2);
+        const double wc = aK * mr_pow(q, p2);
         WC[i] = wc; IWC[i] = 1.0 / wc;
     }
     MR_SYNC();
@@ -187,12 +198,15 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
         return (T1[IW] - T1[JW]) / WDIFF;
     };
     if (NN > 1) {                                      // breaking waves, kwt_route.f90:1301-1349
+        MR_NOUNROLL
         for (int IW = 2 + lane; IW <= NN; IW += MR_NL) XX[IW] = cross(IW);
         MR_SYNC();
         double X = 0.0;
+        MR_NOUNROLL
         for (;;) {
             // serial scan: XB = XMX; for IW: if (XXB < X || XXB > XB) skip; else XB = XXB, IXB = IW  => minimum, last on ties
             double XB = XMX; int IXB = 0;
+            MR_NOUNROLL
             for (int IW = 2 + lane; IW <= NN; IW += MR_NL) {
                 const double XXB = XX[IW];
                 if (XXB < X || XXB > XB) continue;
@@ -203,13 +217,13 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
             NN = NN - 1;
             const int JXB = IXB - 1;
             const double q2n = fmax(Q2[JXB], Q2[IXB]), q1n = fmin(Q1[JXB], Q1[IXB]);
-            // the two pow() of a merge run on two lanes
+            // the two mr_pow() of a merge run on two lanes
             double A2, A1;
             if (MR_NL > 1) {
-                const double a = pow(((lane & 1) ? q1n : q2n) / K, p1);
+                const double a = mr_pow(((lane & 1) ? q1n : q2n) / K, p1);
                 A2 = team_bcast(a, 0); A1 = team_bcast(a, 1);
             } else {
-                A2 = pow(q2n / K, p1); A1 = pow(q1n / K, p1);
+                A2 = mr_pow(q2n / K, p1); A1 = mr_pow(q1n / K, p1);
             }
             const double CM = (q2n - q1n) / (A2 - A1);
             const double t1n = T1[JXB] + XB / WC[JXB] - XB / CM;
@@ -221,10 +235,13 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
             if (i <= NN) { sIX = IX[i + 1]; sT1 = T1[i + 1]; sWC = WC[i + 1]; sIWC = IWC[i + 1]; sQ1 = Q1[i + 1]; sQ2 = Q2[i + 1]; sXX = XX[i + 1]; }
             MR_SYNC();
             if (i <= NN) { IX[i] = sIX; T1[i] = sT1; WC[i] = sWC; IWC[i] = sIWC; Q1[i] = sQ1; Q2[i] = sQ2; XX[i] = sXX; }
+            MR_NOUNROLL
             for (int j = ixb0 + lane; j <= NI; j += MR_NL) MF[j] = (signed char)(MF[j] - 1);
 #else
             (void)i; (void)sT1; (void)sWC; (void)sIWC; (void)sQ1; (void)sQ2; (void)sXX; (void)sIX;
+            MR_NOUNROLL
             for (int j = ixb0; j <= NI; ++j) MF[j] = (signed char)(MF[j] - 1);
+            MR_NOUNROLL
             for (int j = IXB; j <= NN; ++j) { IX[j] = IX[j + 1]; T1[j] = T1[j + 1]; WC[j] = WC[j + 1]; IWC[j] = IWC[j + 1]; Q1[j] = Q1[j + 1]; Q2[j] = Q2[j + 1]; XX[j] = XX[j + 1]; }
 #endif
             if (lane == 0) { Q2[JXB] = q2n; Q1[JXB] = q1n; T1[JXB] = t1n; WC[JXB] = CM; IWC[JXB] = 1.0 / CM; }
@@ -237,6 +254,7 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
     }
     // exit times of the (merged) particles, kwt_route.f90:1363-1370
     bool zero = false;
+    MR_NOUNROLL
     for (int IR = 1 + lane; IR <= NN; IR += MR_NL) {
         if (WC[IR] < DBL_MIN) zero = true;
         TEX[IR] = fmin(XMX / WC[IR] + T1[IR], DBL_MAX);
@@ -249,9 +267,11 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
         // only T_EXIT is new.  rUpdate's fix-ups (:1431,1434) fire only where the raw exit times are not strictly
         // increasing (or the first is not after T_START); when no lane sees that, the raw times are final.
         bool viol = false;
+        MR_NOUNROLL
         for (int IR = 1 + lane; IR <= NN; IR += MR_NL) viol = viol || (IR == 1 ? TEX[1] <= T_START : TEX[IR] <= TEX[IR - 1]);
         if (!team_any(viol)) {
             unsigned rt = 0;
+            MR_NOUNROLL
             for (int IR = 1 + lane; IR <= NN; IR += MR_NL) {
                 const double tx = TEX[IR];
                 S.TX[IR] = tx;
@@ -273,6 +293,7 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
             if (ICOUNT == 1 && S.TX[1] <= T_START) S.TX[1] = T_START + 1.0;
             if (S.TX[ICOUNT] < T_END) routed |= 1u << (ICOUNT - 1);
         };
+        MR_NOUNROLL
         for (int IR = 1; IR <= NN && !ierr; ++IR) {
             const double TEXIT = TEX[IR];
             const double TNEXT = IR < NN ? TEX[IR + 1] : DBL_MAX;
@@ -283,6 +304,7 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
                     rupdate(Q1[IR], T1[IR], TEXIT);
                     rupdate(Q2[IR], T1[IR], TEXIT2);
                 } else {
+                    MR_NOUNROLL
                     for (int JR = 1; JR <= NI; ++JR) if (MF[JR] == IR) rupdate(Q0[JR], T0[JR], TEXIT);
                 }
             } else {
@@ -325,6 +347,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
     bool bad = false;
     const double *Qs = d.qSer[M_KWT] + (size_t)t * N;
     const int nGood = d.nGood[p];
+    MR_NOUNROLL
     for (int base = 0; base < NUPB; base += MR_NL) {
         const int i = base + lane;
         int U = 0, NS = 0, NR = 0;
@@ -357,6 +380,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
     MR_SYNC();
     if (lane == 0) {
         double qup = 0.0;
+        MR_NOUNROLL
         for (int m = 0; m < nGood; ++m) qup = qup + S.TX[1 + m];
         d.inflow[M_KWT][p] = qup;
     }
@@ -372,6 +396,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
         // basins are interpolated at their end point, :930-957)
         if (lane == 0) {
             double Q_AGG = 0.0;
+            MR_NOUNROLL
             for (int s = 0; s < NUPB; ++s) {
                 const double qb = S.u.m.sq[2 * s], qe = S.u.m.sq[2 * s + 1];
                 double SFLOW;
@@ -389,19 +414,23 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
     if (M > WCAP - nOwn || poolN > POOL) return -E_SCRATCH;
     MR_SYNC();
     // stage the upstream waves
+    MR_NOUNROLL
     for (int s = NUPB; s < NUPS; ++s) {
         const int U = S.u.m.upos[s], o = S.u.m.soff[s], sl = S.u.m.slen[s];
         const double *QF = d.kwQF[b] + (size_t)U * KWP, *TR = d.kwTR[b] + (size_t)U * KWP;
+        MR_NOUNROLL
         for (int k = lane; k < sl; k += MR_NL) { S.u.m.sq[o + k] = QF[k]; S.u.m.st[o + k] = TR[k]; }
         nRead += sl;
     }
     MR_SYNC();
     // one candidate per lane
     bool ebrk = false, eord = false;
+    MR_NOUNROLL
     for (int base = 0; base < M; base += MR_NL) {
         const int c = base + lane;
         if (c < M) {
             int J = 0;
+            MR_NOUNROLL
             while (J < NUPS - 1 && c >= S.u.m.cbase[J] + S.u.m.ncand[J]) ++J;
             const int k = c - S.u.m.cbase[J] + 1;
             const int oJ = S.u.m.soff[J];
@@ -409,6 +438,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
             if (k >= 2 && CT < S.u.m.st[oJ + k - 1]) eord = true;
             int ord = 0; bool dup = false, brk = false;
             double Q_AGG = 0.0;
+            MR_NOUNROLL
             for (int s = 0; s < NUPS; ++s) {
                 const int o = S.u.m.soff[s];
                 double SFLOW;
@@ -418,6 +448,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
                 } else {
                     const int nc = S.u.m.ncand[s];
                     int cnt = 0;
+                    MR_NOUNROLL
                     for (int kk = 1; kk <= nc; ++kk) {
                         const double tt = S.u.m.st[o + kk];
                         if (tt < CT) ++cnt;
@@ -445,6 +476,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
     MR_SYNC();
     // drop the duplicates (kwt_route.f90:926)
     int pos = 0;
+    MR_NOUNROLL
     for (int base = 0; base < M; base += MR_NL) {
         const int i = base + lane;
         const bool keep = i < M && S.u.m.flag[i] != 0;
@@ -495,6 +527,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
     const int nOwn = nPrev > 0 ? nPrev - first : 1;
     if (nPrev > 0) {
         const size_t row = (size_t)p * KWP + first;
+        MR_NOUNROLL
         for (int i = lane; i < nOwn; i += MR_NL) { S.Q[i] = d.kwQF[bp][row + i]; S.TE[i] = d.kwTI[bp][row + i]; }
         if (lane == 0) S.TX[0] = d.kwTR[bp][row];
     }
@@ -504,6 +537,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
         if (lane == 0) {
             S.Q[nOwn] = Qs[d.upIdx[u0]] / W; S.TE[nOwn] = T1;
             double qup = 0.0;                          // kwt_route.f90:168-174
+            MR_NOUNROLL
             for (int m = 0; m < nGood; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
             d.inflow[M_KWT][p] = qup;
         }
@@ -523,6 +557,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
     MR_SYNC();
     int n = nOwn + ND;
     bool neg = false;
+    MR_NOUNROLL
     for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;
     if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return; }
 
@@ -549,6 +584,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
     // KWAVE(0:NQ2+1) = routed(0:NR) | end-of-step point | non-routed(NR+1:NQ2), kwt_route.f90:299-311
     const size_t row = (size_t)p * KWP;
     double *oQ = d.kwQF[b] + row, *oI = d.kwTI[b] + row, *oR = d.kwTR[b] + row;
+    MR_NOUNROLL
     for (int i = lane; i <= NQ2; i += MR_NL) {
         const int j = i <= NR ? i : i + 1;
         oQ[j] = S.Q[i]; oI[j] = S.TE[i]; oR[j] = S.TX[i];

@@ -15,12 +15,14 @@
 #define MR_LANE ((int)(threadIdx.x & 31u))
 #define MR_NL 32
 #define MR_SYNC() __syncwarp()
+#define MR_NOUNROLL _Pragma("unroll 1")
 #else
 #define MR_DEV inline
 #define MR_DEV_NOINLINE inline
 #define MR_LANE 0
 #define MR_NL 1
 #define MR_SYNC() ((void)0)
+#define MR_NOUNROLL
 #endif
 
 namespace mr {
