@@ -45,7 +45,7 @@ WORKLOADS = {
     #        kind      n          route  dt       lakes  default T
     "C2": ("binary", 100_000, "1", 3600.0, 0, 240),
     "C3": ("conus", 3_000_000, "2", 86400.0, 0, 128),
-    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 96),
+    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 192),
     "C5": ("conus", 3_000_000, "2", 86400.0, 10_000, 128),
 }
 
@@ -202,7 +202,7 @@ def algorithmic_bytes(r, net, opts, T, kwt_touched_per_batch):
     if "1" in opts.route_opt:
         out["k_route<IRF>"] = T * (24 * sum_ntdh + 12 * sum_nups + 76 * N)
     if "2" in opts.route_opt:
-        out["k_route<KWT>"] = 28 * kwt_touched_per_batch + T * (28 * sum_nups + 56 * N)
+        out["k_route_kwt"] = 28 * kwt_touched_per_batch + T * (28 * sum_nups + 56 * N)
     if "0" in opts.route_opt:
         out["k_route<SUM>"] = T * (12 * sum_nups + 16 * N)
     return out
@@ -338,7 +338,7 @@ def main():
     if "1" in opts.route_opt:
         fam_ms["k_route<IRF>"] = phase.get("route_irf", 0.0) / args.steps
     if "2" in opts.route_opt:
-        fam_ms["k_route<KWT>"] = phase.get("route_kwt", 0.0) / args.steps
+        fam_ms["k_route_kwt"] = phase.get("route_kwt", 0.0) / args.steps
     if "0" in opts.route_opt:
         fam_ms["k_route<SUM>"] = phase.get("route_sum", 0.0) / args.steps
     dom = max(fam_ms, key=fam_ms.get)
