@@ -13,8 +13,10 @@ Workloads (BASELINE.json configs):
     C3            3M-reach CONUS-like forest, KWT, daily
     C5            C3 + 10k lakes (Doll / endorheic)
 
-N > 1 (torchrun, one rank per GPU): the river basins of the SAME network are bin-packed onto the ranks
-(partition.partition_basins); each rank routes its own basins, no data-path collective; time = max over ranks.
+N > 1 (torchrun, one rank per GPU): the SAME network is decomposed by the reference's rule (partition.decompose:
+reaches with more than nRch/N upstream reaches are mainstem, the subtrees hanging off it and the smaller basins
+are tributary domains bin-packed onto the ranks); every rank routes its tributaries, the tributary outlets are
+handed to rank 0 by NCCL send/recv (multi.exchange_rows), rank 0 routes the mainstem; time = max over ranks.
 
 `--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP over all host cores)
 on a bounded sample of the same workload -- the Fortran reference cannot be built in this image (no Fortran
@@ -253,24 +255,43 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- this rank's domain: whole basins, largest-first bin packing (no exchange between domains)
+    # ---- this rank's domains: tributary subtrees (+ the mainstem on rank 0), see mizuroute_b200/multi.py
     full_n = net.nRch
+    dom = rm = None
+    n_main = n_outlets = 0
     if world > 1:
-        parts = partition.partition_basins(net, world)
-        net_local = partition.subnetwork(net, parts[rank])
+        from mizuroute_b200.multi import DomainSet
+        dom = DomainSet(net, params, opts, T, rank, world, device=local_rank)
+        r, net_local, rm = dom.trib, dom.trib_net, dom.main
+        n_main, n_outlets = int(dom.dec.mainstem.size), int(dom.dec.outlets.size)
+        if r is None:
+            raise SystemExit("bench.py: this rank holds no tributary domain (network too small for this many GPUs)")
     else:
         net_local = net
+        r = Router(net_local, params, opts, device=local_rank, max_batch=T)
     ro = runoff_for(net_local, T, opts.dt)                 # [T, nHRU_local]
-
-    r = Router(net_local, params, opts, device=local_rank, max_batch=T)
+    ro_main = runoff_for(dom.main_net, T, opts.dt) if rm is not None else None
     stream = torch.cuda.Stream()
     r.set_stream(stream.cuda_stream)
+    if rm is not None:
+        rm.set_stream(stream.cuda_stream)
     has_kwt = "2" in opts.route_opt
+
+    def route_all():
+        """one bench step on this rank: tributaries, hand-off of the outlets to rank 0, mainstem"""
+        r.route_resident(T)
+        if dom is not None:
+            dom.hand_off()
+        if rm is not None:
+            rm.route_resident(T)
 
     # ---- device-resident throughput (`value`): forcing already in HBM; [T x nHRU] doubles >> L2
     r.upload_runoff(ro)
-    for _ in range(args.warmup):
-        r.route_resident(T)
+    if rm is not None:
+        rm.upload_runoff(ro_main)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            route_all()
     if has_kwt:
         r.set_counting(True)
     sampler = ClockSampler(local_rank)
@@ -283,11 +304,14 @@ def main():
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(args.steps):
-            r.route_resident(T)
+            route_all()
             tm = r.timing()
             for k, v in tm.items():
                 phase[k] = phase.get(k, 0.0) + v
             launches += r.info(capi.INFO_LAUNCHES_LAST)
+            if rm is not None:
+                phase["mainstem"] = phase.get("mainstem", 0.0) + rm.timing()["total"]
+                launches += rm.info(capi.INFO_LAUNCHES_LAST)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -307,18 +331,30 @@ def main():
         nm = len(opts.route_opt)
         ro_pin = torch.from_numpy(ro).pin_memory()
         out_pin = torch.empty((nm, T, net_local.nRch), dtype=torch.float64).pin_memory()
-        r.route_batch(ro_pin, out_pin)                     # warm the pinned path once
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
+        if rm is not None:
+            rom_pin = torch.from_numpy(ro_main).pin_memory()
+            outm_pin = torch.empty((nm, T, dom.main_net.nRch), dtype=torch.float64).pin_memory()
+
+        def e2e_all():
             r.route_batch(ro_pin, out_pin)
-        torch.cuda.synchronize()
-        e_s = time.perf_counter() - t0
+            if dom is not None:
+                dom.hand_off()
+            if rm is not None:
+                rm.route_batch(rom_pin, outm_pin)
+
+        with torch.cuda.stream(stream):
+            e2e_all()                                      # warm the pinned path once
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_all()
+            torch.cuda.synchronize()
+            e_s = time.perf_counter() - t0
         t_e = torch.tensor([e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        h2d = torch.tensor([float(ro.nbytes)], dtype=torch.float64, device="cuda")
-        d2h = torch.tensor([float(out_pin.numel() * 8)], dtype=torch.float64, device="cuda")
+        h2d = torch.tensor([float(ro.nbytes + (ro_main.nbytes if rm is not None else 0))], dtype=torch.float64, device="cuda")
+        d2h = torch.tensor([float((out_pin.numel() + (outm_pin.numel() if rm is not None else 0)) * 8)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(h2d); dist.all_reduce(d2h)
         e2e = {"value": full_n * T * args.steps / float(t_e.item()), "unit": UNIT,
@@ -387,7 +423,9 @@ def main():
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "nRch": full_n, "route_opt": opts.route_opt, "dt_qsim": opts.dt,
                    "timesteps_per_step": T, "nStage": r.info(capi.INFO_NSTAGE), "l2": "inputs larger than L2 (forcing + state per step >> 126 MB)",
-                   "parallelism": f"basins bin-packed over {world} GPU(s), no exchange", "rank0_nRch": net_local.nRch,
+                   "parallelism": ("single domain" if world == 1 else f"tributary domains bin-packed over {world} GPUs, {n_outlets} tributary outlets handed to "
+                                   f"the {n_main}-reach mainstem on rank 0 by NCCL send/recv"),
+                   "rank0_nRch": net_local.nRch, "mainstem_ms_per_step": (phase.get("mainstem", 0.0) / args.steps if world > 1 else None),
                    "kwt_particles_per_reach": particles},
         "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
     }

@@ -42,7 +42,8 @@ enum {
     MR_REACH_Q = 0, MR_REACH_VOL1 = 1, MR_REACH_INFLOW = 2, MR_WB = 3,
     MR_BASIN_QI = 4, MR_BASIN_QR1 = 5, MR_BASIN_QR0 = 6, MR_REACH_VOL0 = 7,
     /* derived reach parameters (RCHPRP, dataTypes.f90:183-255) */
-    MR_R_WIDTH = 10, MR_TOTAREA = 11, MR_BASAREA = 12, MR_R_SLOPE = 13
+    MR_R_WIDTH = 10, MR_TOTAREA = 11, MR_BASAREA = 12, MR_R_SLOPE = 13,
+    MR_NGOOD = 14                /* count(goodBas), network_topo.f90:769-775 (as a double) */
 };
 
 /* lake model types, public_var.f90 / lake_route.f90:196-438 */
@@ -136,6 +137,30 @@ int mr_set_steps_done(mr_handle h, long steps, char *message);
 /* Unit hydrographs produced by process_param.f90 (basinUH :13-92, make_uh :99-262). */
 int mr_get_basin_uh(mr_handle h, double *frac_future /* [ntdh_bas] */, char *message);
 int mr_get_reach_uh(mr_handle h, int *ntdh /* [nRch] */, double *uh /* [nRch][maxtdh] */, char *message);
+
+/* ---- multi-domain hand-off (mpi_process.f90:1238-1329) -----------------------------------------------------
+ * The reference routes tributary domains on every rank, gathers the tributary-outlet fluxes (mpi_comm_river_flux
+ * :1747-1967), BASIN_QR (mpi_comm_flux :1632-1742) and KWT wave state (mpi_comm_kwt_state :2501-2720) to rank 0,
+ * and routes the mainstem there with the outlets appended as extra reaches (:593-607).  Here:
+ *   tributary handle : mr_set_export names the outlet reaches; every routed step leaves one RECORD per outlet in
+ *                      the export buffer;
+ *   mainstem handle  : mr_set_ghosts (before mr_set_network) names the reaches that are ghosts of outlets routed
+ *                      elsewhere; their per-step values are read from the import buffer;
+ *   the caller moves export -> import (NCCL send/recv between processes, mr_copy_exchange inside one process).
+ * Buffers are device memory: [slot][max_batch][recLen] doubles, recLen = n_routes + 3 + 2*24:
+ *   REACH_Q of each route (route_opt order) | BASIN_QR(1) | numWaves | numRouted | QF[24] | TR[24].
+ * No message travels back: owners strip their own routed particles (kwt_route.f90:840-844 is a pure function of
+ * the outlet's own state). */
+int mr_set_ghosts(mr_handle h, int nGhost, const int *ghostSegId, const int *kind /* 1 headwater-like, 2 interior */,
+                  const double *totArea, const double *width, char *message);
+int mr_set_export(mr_handle h, int nExport, const int *exportSegId, char *message);
+/* which: 0 export, 1 import.  dev == NULL: the library allocates.  Otherwise the caller's device buffer is used
+ * (e.g. a torch tensor that NCCL sends/receives in place); nbytes must be >= mr_exchange_bytes. */
+long mr_exchange_bytes(mr_handle h, int which);
+int mr_set_exchange_buffer(mr_handle h, int which, void *dev, long nbytes, char *message);
+int mr_get_exchange_buffer(mr_handle h, int which, void **dev, long *nbytes, char *message);
+/* device-to-device: nSlots export records of src (from srcSlot0) -> import records of dst (from dstSlot0) */
+int mr_copy_exchange(mr_handle src, mr_handle dst, int srcSlot0, int dstSlot0, int nSlots, char *message);
 
 /* Launch on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores the handle's own stream),
  * so callers can bracket the work with their own events and overlap it with other streams. */

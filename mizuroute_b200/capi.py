@@ -16,7 +16,8 @@ MR_KW_SLOTS = 22
 
 # flux fields
 REACH_Q, REACH_VOL1, REACH_INFLOW, WB, BASIN_QI, BASIN_QR1, BASIN_QR0, REACH_VOL0 = range(8)
-R_WIDTH, TOTAREA, BASAREA, R_SLOPE = 10, 11, 12, 13
+R_WIDTH, TOTAREA, BASAREA, R_SLOPE, NGOOD = 10, 11, 12, 13, 14
+KW_PITCH = 24            # particle-row pitch of an exchange record
 # state variables
 (ST_BASIN_QFUTURE, ST_BASIN_QR, ST_IRF_QFUTURE, ST_IRF_VOL, ST_KWT_NWAVE, ST_KWT_QWAVE, ST_KWT_TENTRY,
  ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL) = range(10)
@@ -29,6 +30,7 @@ EXPORTS = [
     "mr_create", "mr_set_network", "mr_step", "mr_step_batch", "mr_upload_runoff", "mr_route_resident",
     "mr_download_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
+    "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
 ]
 
 
@@ -95,10 +97,17 @@ def load(rebuild_if_stale: bool = True):
     L.mr_get_timing.argtypes = [vp, dp]
     L.mr_set_stream.argtypes = [vp, vp, cp]
     L.mr_set_counting.argtypes = [vp, C.c_int, cp]
+    L.mr_set_ghosts.argtypes = [vp, C.c_int, ip, ip, dp, dp, cp]
+    L.mr_set_export.argtypes = [vp, C.c_int, ip, cp]
+    L.mr_exchange_bytes.argtypes = [vp, C.c_int]
+    L.mr_exchange_bytes.restype = C.c_long
+    L.mr_set_exchange_buffer.argtypes = [vp, C.c_int, vp, C.c_long, cp]
+    L.mr_get_exchange_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_long), cp]
+    L.mr_copy_exchange.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, cp]
     L.mr_destroy.argtypes = [vp]
     L.mr_destroy.restype = None
     for name in EXPORTS:
-        if name not in ("mr_get_info", "mr_destroy"):
+        if name not in ("mr_get_info", "mr_destroy", "mr_exchange_bytes"):
             getattr(L, name).restype = C.c_int
     _LIB = L
     return L

@@ -38,6 +38,10 @@ struct DevNet {
     double *qfutIrf;
     int *kwN[2], *kwNR[2];
     double *kwQF[2], *kwTI[2], *kwTR[2];
+    // multi-domain hand-off: per-step records of exported outlets / imported ghosts, [slot][kmax][recLen]
+    const int *expSlot, *impSlot;   // by position, -1 = none (nullptr = feature off)
+    double *expBuf; const double *impBuf;
+    int recLen, kmax, nRoutes, routeSlot[3];
     int *err;                       // [0] code (0 = ok) [1] position [2] site
     unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
 };

@@ -265,9 +265,40 @@ __global__ void __launch_bounds__(32 * KWT_WARPS, 8) k_route_kwt(DevNet d, int l
     if (p >= hi) return;                               // whole warps leave together
     const int t = w - d.stageOf[p];
     const int flags = d.flags[p];
-    if (flags & FLAG_GHOST) return;
+    if (flags & FLAG_GHOST) {                          // this step's wave of a tributary outlet routed in another domain
+        const int lane = threadIdx.x & 31, b = (int)((tau0 + t) & 1);
+        const double *rec = d.impBuf + ((size_t)d.impSlot[p] * d.kmax + t) * d.recLen + d.nRoutes + 1;
+        const size_t row = (size_t)p * KWP;
+        if (lane < KWP) { d.kwQF[b][row + lane] = rec[2 + lane]; d.kwTR[b][row + lane] = rec[2 + KWP + lane]; }
+        if (lane == 0) { d.kwN[b][p] = (int)rec[0]; d.kwNR[b][p] = (int)rec[1]; }
+        return;
+    }
     if (flags & FLAG_LAKE) { if ((threadIdx.x & 31) == 0) lake_reach<M_KWT>(d, p, t, tau0 + t); return; }
     kwt_reach_team(d, S[wid], p, t, tau0 + t, d.T0s[t], d.T1s[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-domain hand-off (see include/mizuroute_b200.h)
+// ------------------------------------------------------------------------------------------------
+// export: REACH_Q of every route, BASIN_QR(1) and -- for outlets without a routed wave -- the sentinel counts
+__global__ void k_export_pack(DevNet d, const int *expPos, int nExp, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nExp * K) return;
+    const int slot = i / K, t = i - slot * K, p = expPos[slot], N = d.nRch;
+    double *rec = d.expBuf + ((size_t)slot * d.kmax + t) * d.recLen;
+    for (int m = 0; m < 3; ++m) if (d.routeSlot[m] >= 0) rec[d.routeSlot[m]] = d.qSer[m][(size_t)t * N + p];
+    rec[d.nRoutes] = d.qrSer[(size_t)(t + 1) * N + p];
+    if (d.nGood[p] == 0 || d.routeSlot[M_KWT] < 0) { rec[d.nRoutes + 1] = 1.0; rec[d.nRoutes + 2] = 0.0; }
+}
+// import: the ghosts' REACH_Q and BASIN_QR(1) series for the whole batch (their waves are copied step by step
+// inside the KWT wavefronts, k_route_kwt)
+__global__ void k_import_unpack(DevNet d, const int *impPos, int nImp, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nImp * K) return;
+    const int slot = i / K, t = i - slot * K, p = impPos[slot], N = d.nRch;
+    const double *rec = d.impBuf + ((size_t)slot * d.kmax + t) * d.recLen;
+    for (int m = 0; m < 3; ++m) if (d.routeSlot[m] >= 0) d.qSer[m][(size_t)t * N + p] = rec[d.routeSlot[m]];
+    d.qrSer[(size_t)(t + 1) * N + p] = rec[d.nRoutes];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -589,6 +589,18 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
         const int j = i <= NR ? i : i + 1;
         oQ[j] = S.Q[i]; oI[j] = S.TE[i]; oR[j] = S.TX[i];
     }
+    if (d.expSlot) {                                   // tributary outlet: leave this step's wave for the mainstem domain
+        const int slot = d.expSlot[p];
+        if (slot >= 0) {
+            double *rec = d.expBuf + ((size_t)slot * d.kmax + t) * d.recLen + d.nRoutes + 1;
+            MR_NOUNROLL
+            for (int i = lane; i <= NQ2; i += MR_NL) {
+                const int j = i <= NR ? i : i + 1;
+                rec[2 + j] = S.Q[i]; rec[2 + KWP + j] = S.TX[i];
+            }
+            if (lane == 0) { rec[0] = (double)(NQ2 + 2); rec[1] = (double)(NR + 2); rec[2 + NR + 1] = Q_END; rec[2 + KWP + NR + 1] = T1; }
+        }
+    }
     if (lane == 0) {
         oQ[NR + 1] = Q_END; oI[NR + 1] = TIMEI; oR[NR + 1] = T1;
         d.kwN[b][p] = NQ2 + 2;

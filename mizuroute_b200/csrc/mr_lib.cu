@@ -28,6 +28,7 @@ struct mr_handle_s {
     Topology topo;
     std::vector<double> fracFuture, uhHost;      // uhHost slot-major [maxtdh][N], stage order
     std::vector<int> ntdh, flags;                // stage order
+    std::vector<int> segIdCopy;                  // caller order
     int maxtdh = 1, ntdhBas = 1;
     DevNet d{};
     std::vector<void *> allocs;
@@ -42,6 +43,12 @@ struct mr_handle_s {
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
+    // multi-domain hand-off
+    std::vector<int> ghostSegId, ghostKind; std::vector<double> ghostTotArea, ghostWidth;   // consumed by mr_set_network
+    int nGhost = 0, nExport = 0;
+    int *dExpPos = nullptr, *dImpPos = nullptr, *dExpSlot = nullptr, *dImpSlot = nullptr;
+    double *xbuf[2] = {nullptr, nullptr};        // [0] export, [1] import
+    bool xowned[2] = {false, false};
 };
 
 namespace {
@@ -153,6 +160,12 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     h->launchesLast += 2;
     k_basin<<<(N + BASIN_TPB - 1) / BASIN_TPB, BASIN_TPB, h->basinSmem, h->stream>>>(d, K, h->stepsDone);
     h->launchesLast++;
+    if (h->nGhost) {
+        if (!d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
+        k_import_unpack<<<(h->nGhost * K + 255) / 256, 256, 0, h->stream>>>(d, h->dImpPos, h->nGhost, K);
+        h->launchesLast++;
+    }
+    if (h->nExport && !d.expBuf) return fail(message, 1, std::string(where) + "/export reaches but no export buffer (mr_set_exchange_buffer)");
     CU(cudaEventRecord(h->ev[2], h->stream));
     const int hb = (d.nHead + 255) / 256;
     for (int r = 0; r < h->opt.n_routes; ++r) {
@@ -165,6 +178,10 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
             case M_KWT: if (hb) { k_headwater<M_KWT><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
                         launch_wavefronts<M_KWT>(h, K, h->stepsDone); break;
         }
+    }
+    if (h->nExport) {
+        k_export_pack<<<(h->nExport * K + 255) / 256, 256, 0, h->stream>>>(d, h->dExpPos, h->nExport, K);
+        h->launchesLast++;
     }
     CU(cudaEventRecord(h->ev[3], h->stream));
     CU(cudaGetLastError());
@@ -249,9 +266,24 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     std::string terr;
     Topology &T = h->topo;
     T = Topology();
-    int ierr = build_topology(nRch, nHRU, segId, downSegId, hruSegId, hruArea, T, terr);
+    std::vector<int> gKind; std::vector<double> gArea, gWidth;          // per reach, caller order
+    h->nGhost = (int)h->ghostSegId.size();
+    std::vector<int> ghostRch(h->nGhost, -1);
+    if (h->nGhost) {
+        gKind.assign(nRch, 0); gArea.assign(nRch, 0.0); gWidth.assign(nRch, 0.0);
+        join_ids(h->ghostSegId.data(), h->nGhost, segId, nRch, ghostRch);
+        for (int g = 0; g < h->nGhost; ++g) {
+            if (ghostRch[g] < 0) return fail(message, 1, "mr_set_network/ghost reach id is not in the network");
+            gKind[ghostRch[g]] = h->ghostKind[g]; gArea[ghostRch[g]] = h->ghostTotArea[g]; gWidth[ghostRch[g]] = h->ghostWidth[g];
+        }
+    }
+    int ierr = build_topology(nRch, nHRU, segId, downSegId, hruSegId, hruArea, T, terr,
+                              h->nGhost ? gKind.data() : nullptr, h->nGhost ? gArea.data() : nullptr);
     if (ierr) return fail(message, ierr, "mr_set_network/" + terr);
     const int N = nRch;
+    h->segIdCopy.assign(segId, segId + nRch);
+    h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
+    for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
     // reach parameters in stage order (process_ntopo.f90:176-187,359-366)
     std::vector<double> rlen(N), rslp(N), rwid(N), rman(N), maxS(N, 0.0), coef(N, 0.0), pw(N, 0.0), s0(N, 0.0);
@@ -263,6 +295,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         rslp[p] = std::fmax(slope[r], 1.e-6);                        // min_slope, public_var.f90:30
         rwid[p] = width ? width[r] : o.wscale * std::sqrt(T.totArea[p]);
         rman[p] = man_n ? man_n[r] : o.mann_n;
+        if (h->nGhost && gKind[r]) { h->flags[p] |= FLAG_GHOST; rwid[p] = gWidth[r]; }
         if (o.is_lake_sim) {
             if (islake && islake[r] == 1) h->flags[p] |= FLAG_LAKE;
             ltype[p] = (!o.lakeRegulate || !lakeModelType) ? MR_LAKE_DOLL03 : lakeModelType[r];
@@ -355,6 +388,17 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         }
     }
     AL(d.err, 4);
+    d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
+    d.nRoutes = o.n_routes; d.kmax = KB; d.recLen = o.n_routes + 3 + 2 * KWP;
+    for (int m = 0; m < 3; ++m) d.routeSlot[m] = -1;
+    for (int r = 0; r < o.n_routes; ++r) d.routeSlot[o.route_methods[r]] = r;
+    if (h->nGhost) {
+        std::vector<int> slot(N, -1), pos(h->nGhost);
+        for (int g = 0; g < h->nGhost; ++g) { pos[g] = T.rch2pos[ghostRch[g]]; slot[pos[g]] = g; }
+        e = dev_upload(h, &h->dImpSlot, slot, where, message); if (e) return e;
+        e = dev_upload(h, &h->dImpPos, pos, where, message); if (e) return e;
+        d.impSlot = h->dImpSlot;
+    }
     AL(h->dRunoff, (size_t)KB * (nHRU > 0 ? nHRU : 1));
     AL(h->dT0s, KB); AL(h->dT1s, KB);
     AL(h->dOut, (size_t)o.n_routes * KB * N);
@@ -468,6 +512,7 @@ int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) 
         case MR_R_SLOPE: src = h->d.rslope; break;
         case MR_BASAREA: for (int r = 0; r < N; ++r) out[r] = T.basArea[T.rch2pos[r]]; put_msg(message, ""); return 0;
         case MR_TOTAREA: for (int r = 0; r < N; ++r) out[r] = T.totArea[T.rch2pos[r]]; put_msg(message, ""); return 0;
+        case MR_NGOOD: for (int r = 0; r < N; ++r) out[r] = (double)T.nGood[T.rch2pos[r]]; put_msg(message, ""); return 0;
         default: return fail(message, 1, "mr_get_flux/unknown field");
     }
     if (!src) { for (int r = 0; r < N; ++r) out[r] = 0.0; put_msg(message, ""); return 0; }
@@ -725,6 +770,89 @@ long mr_get_info(mr_handle h, int key) {
         }
         default: return -1;
     }
+}
+
+int mr_set_ghosts(mr_handle h, int nGhost, const int *ghostSegId, const int *kind, const double *totArea, const double *width, char *message) {
+    if (!h) return fail(message, 1, "mr_set_ghosts/null handle");
+    if (nGhost < 0 || (nGhost > 0 && (!ghostSegId || !kind || !totArea || !width))) return fail(message, 1, "mr_set_ghosts/missing argument");
+    for (int g = 0; g < nGhost; ++g) if (kind[g] != 1 && kind[g] != 2) return fail(message, 1, "mr_set_ghosts/kind must be 1 or 2");
+    h->ghostSegId.assign(ghostSegId, ghostSegId + nGhost); h->ghostKind.assign(kind, kind + nGhost);
+    h->ghostTotArea.assign(totArea, totArea + nGhost); h->ghostWidth.assign(width, width + nGhost);
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_export(mr_handle h, int nExport, const int *exportSegId, char *message) {
+    const char *where = "mr_set_export";
+    if (!h || !h->hasNet) return fail(message, 1, "mr_set_export/handle has no network");
+    if (nExport < 0 || (nExport > 0 && !exportSegId)) return fail(message, 1, "mr_set_export/missing argument");
+    if (h->nExport) return fail(message, 1, "mr_set_export/already set for this network");
+    CU(cudaSetDevice(h->opt.device));
+    const Topology &T = h->topo;
+    const int N = h->d.nRch;
+    // id -> caller index through the handle's own reach ids is not kept; resolve against positions via downIndex order
+    std::vector<int> slot(N, -1), pos(nExport);
+    std::vector<int> idx;
+    join_ids(exportSegId, nExport, h->segIdCopy.data(), N, idx);
+    for (int k = 0; k < nExport; ++k) {
+        if (idx[k] < 0) return fail(message, 1, "mr_set_export/reach id is not in the network");
+        pos[k] = T.rch2pos[idx[k]]; slot[pos[k]] = k;
+    }
+    int e = dev_upload(h, &h->dExpSlot, slot, where, message); if (e) return e;
+    e = dev_upload(h, &h->dExpPos, pos, where, message); if (e) return e;
+    h->d.expSlot = h->dExpSlot;
+    h->nExport = nExport;
+    put_msg(message, "");
+    return 0;
+}
+
+long mr_exchange_bytes(mr_handle h, int which) {
+    if (!h || !h->hasNet || which < 0 || which > 1) return -1;
+    const long n = which == 0 ? h->nExport : h->nGhost;
+    return 8L * n * h->d.kmax * h->d.recLen;
+}
+
+int mr_set_exchange_buffer(mr_handle h, int which, void *dev, long nbytes, char *message) {
+    const char *where = "mr_set_exchange_buffer";
+    if (!h || !h->hasNet || which < 0 || which > 1) return fail(message, 1, "mr_set_exchange_buffer/bad handle or selector");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    const long need = mr_exchange_bytes(h, which);
+    double *ptr = (double *)dev;
+    if (!ptr) {
+        int e = dev_alloc(h, &ptr, (size_t)(need / 8), where, message); if (e) return e;
+        CU(cudaStreamSynchronize(h->stream));
+        h->xowned[which] = true;
+    } else {
+        if (nbytes < need) return fail(message, 1, "mr_set_exchange_buffer/buffer smaller than mr_exchange_bytes");
+        h->xowned[which] = false;
+    }
+    h->xbuf[which] = ptr;
+    if (which == 0) h->d.expBuf = ptr; else h->d.impBuf = ptr;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_get_exchange_buffer(mr_handle h, int which, void **dev, long *nbytes, char *message) {
+    if (!h || !h->hasNet || which < 0 || which > 1 || !dev || !nbytes) return fail(message, 1, "mr_get_exchange_buffer/bad argument");
+    *dev = h->xbuf[which]; *nbytes = mr_exchange_bytes(h, which);
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_copy_exchange(mr_handle src, mr_handle dst, int srcSlot0, int dstSlot0, int nSlots, char *message) {
+    const char *where = "mr_copy_exchange";
+    if (!src || !dst || !src->hasNet || !dst->hasNet) return fail(message, 1, "mr_copy_exchange/handle has no network");
+    if (src->d.recLen != dst->d.recLen || src->d.kmax != dst->d.kmax) return fail(message, 1, "mr_copy_exchange/route_opt or max_batch differ between the domains");
+    if (nSlots < 0 || srcSlot0 < 0 || dstSlot0 < 0 || srcSlot0 + nSlots > src->nExport || dstSlot0 + nSlots > dst->nGhost)
+        return fail(message, 1, "mr_copy_exchange/slot range outside the buffers");
+    if (!src->xbuf[0] || !dst->xbuf[1]) return fail(message, 1, "mr_copy_exchange/exchange buffers are not set");
+    const size_t rec = (size_t)src->d.kmax * src->d.recLen;
+    CU(cudaStreamSynchronize(src->stream));
+    CU(cudaMemcpyAsync(dst->xbuf[1] + (size_t)dstSlot0 * rec, src->xbuf[0] + (size_t)srcSlot0 * rec, 8 * rec * nSlots, cudaMemcpyDeviceToDevice, dst->stream));
+    CU(cudaStreamSynchronize(dst->stream));
+    put_msg(message, "");
+    return 0;
 }
 
 int mr_set_stream(mr_handle h, void *cuda_stream, char *message) {

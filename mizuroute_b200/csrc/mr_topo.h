@@ -57,8 +57,13 @@ inline void join_ids(const int *keys, int nKeys, const int *ids, int nIds, std::
     }
 }
 
+// ghostKind (may be null): 0 = ordinary reach; 1 / 2 = ghost copy of a tributary outlet that is routed in another
+// domain (the reference appends such reaches to the mainstem slab, mpi_process.f90:593-607,680), 1 if that outlet
+// has no contributing upstream reach (a "headwater" there), 2 if it has.  A ghost has no upstream reaches and no
+// HRUs here; its total area (ghostTotArea) is the one its owner computed.
 inline int build_topology(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId,
-                          const double *hruArea, Topology &T, std::string &err) {
+                          const double *hruArea, Topology &T, std::string &err,
+                          const int *ghostKind = nullptr, const double *ghostTotArea = nullptr) {
     T.nRch = nRch; T.nHRU = nHRU;
     join_ids(downSegId, nRch, segId, nRch, T.downIndex);
     const std::vector<int> &down = T.downIndex;
@@ -91,7 +96,7 @@ inline int build_topology(int nRch, int nHRU, const int *segId, const int *downS
     T.nStage = (int)byHops.size();
 
     // interior reaches stage by stage (upstream-most stage first), headwaters pulled out in front
-    auto isHead = [&](int r) { return uPtr[r + 1] == uPtr[r]; };
+    auto isHead = [&](int r) { return uPtr[r + 1] == uPtr[r] && !(ghostKind && ghostKind[r] == 2); };
     std::vector<int> interior;                  // caller indices in device order
     std::vector<int> stageCount(T.nStage, 0);
     interior.reserve(nRch);
@@ -150,6 +155,8 @@ inline int build_topology(int nRch, int nHRU, const int *segId, const int *downS
         T.basArea[q] = bas; T.upsArea[q] = ups; T.totArea[q] = bas + ups;
         for (int m = T.hruPtr[q]; m < T.hruPtr[q + 1]; ++m) T.hruWgt[m] = hruArea[T.hruIdx[m]] / bas;
         T.nGood[q] = (T.totArea[q] > DBL_MIN) ? (T.upPtr[q + 1] - T.upPtr[q]) : 0;
+        const int gk = ghostKind ? ghostKind[T.pos2rch[q]] : 0;
+        if (gk) { T.totArea[q] = ghostTotArea[T.pos2rch[q]]; T.nGood[q] = gk == 2 ? 1 : 0; }
     }
     return 0;
 }

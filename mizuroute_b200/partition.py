@@ -59,3 +59,103 @@ def subnetwork(net: RiverNetwork, reaches: np.ndarray) -> RiverNetwork:
     sub.meta["hru_index"] = np.flatnonzero(hru_keep)      # columns of the global runoff array this domain reads
     sub.meta["reach_index"] = np.asarray(reaches)
     return sub
+
+
+# ------------------------------------------------------------------------------------------------
+# tributary / mainstem decomposition (domain_decomposition.f90:450-819)
+# ------------------------------------------------------------------------------------------------
+def upstream_size(net: RiverNetwork) -> np.ndarray:
+    """size(allUpSegIndices): number of reaches upstream of each reach INCLUDING itself (O(N), level by level)."""
+    down = _down_index(net)
+    n = net.nRch
+    hops = np.where(down >= 0, 1, 0).astype(np.int64)
+    ptr = np.where(down >= 0, down, np.arange(n))
+    while True:                                   # pointer doubling: hops to the outlet
+        nh, npt = hops + hops[ptr], ptr[ptr]
+        if np.array_equal(npt, ptr):
+            break
+        hops, ptr = nh, npt
+    size = np.ones(n, dtype=np.int64)
+    order = np.argsort(-hops, kind="stable")
+    bounds = np.flatnonzero(np.diff(hops[order])) + 1
+    for idx in np.split(order, bounds):           # farthest level first
+        idx = idx[down[idx] >= 0]
+        np.add.at(size, down[idx], size[idx])
+    return size
+
+
+class Decomposition:
+    """Result of `decompose`: which reaches each rank routes as tributaries, the mainstem (routed by rank 0 after
+    the hand-off) and the tributary outlets that feed it."""
+
+    def __init__(self, nparts, trib, mainstem, outlets, outlet_owner):
+        self.nparts = nparts
+        self.trib = trib                  # list[nparts] of sorted global reach indices
+        self.mainstem = mainstem          # sorted global reach indices (may be empty)
+        self.outlets = outlets            # global reach indices of tributary outlets draining into the mainstem,
+        self.outlet_owner = outlet_owner  # ... sorted by (owner rank, reach index), and their owner ranks
+
+    def outlets_of(self, rank):
+        return self.outlets[self.outlet_owner == rank]
+
+    def slot_range(self, rank):
+        lo = int(np.searchsorted(self.outlet_owner, rank, side="left"))
+        hi = int(np.searchsorted(self.outlet_owner, rank, side="right"))
+        return lo, hi
+
+
+def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 8.0) -> Decomposition:
+    """The reference's rule: a reach with more than nRch/nparts upstream reaches is MAINSTEM
+    (domain_decomposition.f90:508-519); every maximal subtree hanging off the mainstem, and every whole basin
+    that has no mainstem, is a TRIBUTARY domain (:640-717); domains go largest-first to the least-loaded rank
+    (:791-809).  The mainstem is routed by rank 0, whose load is pre-charged with `mainstem_cost` reach
+    equivalents per mainstem reach (a mainstem wavefront holds a handful of reaches and is latency-bound)."""
+    n = net.nRch
+    down = _down_index(net)
+    size = upstream_size(net)
+    max_segs = n // nparts
+    is_main = size > max_segs if nparts > 1 else np.zeros(n, dtype=bool)
+    # root of the tributary domain of every non-mainstem reach: follow downstream until the next reach is
+    # mainstem or there is none
+    stop = (down < 0) | is_main[np.where(down >= 0, down, 0)]
+    root = np.where(stop | is_main, np.arange(n), down)
+    while True:
+        nxt = root[root]
+        if np.array_equal(nxt, root):
+            break
+        root = nxt
+    trib_mask = ~is_main
+    roots, inv, counts = np.unique(root[trib_mask], return_inverse=True, return_counts=True)
+    load = np.zeros(nparts, dtype=np.float64)
+    load[0] = mainstem_cost * float(is_main.sum())
+    owner_of_root = np.empty(roots.size, dtype=np.int64)
+    for b in np.argsort(-counts, kind="stable"):
+        k = int(np.argmin(load))
+        owner_of_root[b] = k
+        load[k] += counts[b]
+    owner = np.full(n, -1, dtype=np.int64)
+    owner[trib_mask] = owner_of_root[inv]
+    trib = [np.flatnonzero(owner == k) for k in range(nparts)]
+    mainstem = np.flatnonzero(is_main)
+    is_outlet = trib_mask & (down >= 0) & is_main[np.where(down >= 0, down, 0)]
+    out = np.flatnonzero(is_outlet)
+    key = np.lexsort((out, owner[out]))
+    out = out[key]
+    return Decomposition(nparts, trib, mainstem, out, owner[out])
+
+
+def mainstem_network(net: RiverNetwork, dec: Decomposition) -> RiverNetwork:
+    """Mainstem reaches plus the tributary outlets as ghost reaches, in the original index order (so the upstream
+    lists keep the reference's UREACHI order); only mainstem HRUs are kept."""
+    idx = np.sort(np.concatenate([dec.mainstem, dec.outlets]))
+    sub = subnetwork(net, idx)
+    ghost = np.isin(net.segId[idx], net.segId[dec.outlets])
+    order = np.argsort(net.segId, kind="stable")
+    sid = net.segId[order]
+    pos = np.clip(np.searchsorted(sid, sub.hruSegId), 0, net.nRch - 1)
+    hru_rch = order[pos]                                   # global reach index of each kept HRU
+    keep = ~np.isin(hru_rch, dec.outlets)
+    sub.meta["hru_index"] = sub.meta["hru_index"][keep]
+    sub.hruId, sub.hruSegId, sub.area = sub.hruId[keep], sub.hruSegId[keep], sub.area[keep]
+    sub.meta["ghost_mask"] = ghost
+    return sub

@@ -29,7 +29,10 @@ def _ptr(a: Optional[np.ndarray], ct):
 
 
 class Router:
-    def __init__(self, net: RiverNetwork, params: RouteParams, opts: RouteOptions, device: int = 0, max_batch: int = 1):
+    def __init__(self, net: RiverNetwork, params: RouteParams, opts: RouteOptions, device: int = 0, max_batch: int = 1,
+                 ghosts=None):
+        """`ghosts` = (segId[], kind[], totArea[], width[]) marks reaches of `net` that are copies of tributary outlets
+        routed in another domain (mr_set_ghosts)."""
         self._L = capi.load()
         self._h = C.c_void_p()
         self._msg = C.create_string_buffer(capi.MR_STRLEN)
@@ -57,6 +60,11 @@ class Router:
         self.max_batch = int(max_batch)
         self._check(self._L.mr_create(C.byref(o), C.byref(self._h), self._msg))
         n = net
+        if ghosts is not None:
+            gid, gkind, garea, gwidth = (np.ascontiguousarray(ghosts[0], dtype=np.int32), np.ascontiguousarray(ghosts[1], dtype=np.int32),
+                                         np.ascontiguousarray(ghosts[2], dtype=np.float64), np.ascontiguousarray(ghosts[3], dtype=np.float64))
+            self._check(self._L.mr_set_ghosts(self._h, len(gid), _ptr(gid, C.c_int), _ptr(gkind, C.c_int), _ptr(garea, C.c_double),
+                                              _ptr(gwidth, C.c_double), self._msg))
         self._check(self._L.mr_set_network(
             self._h, n.nRch, n.nHRU, _ptr(n.segId, C.c_int), _ptr(n.downSegId, C.c_int), _ptr(n.hruSegId, C.c_int),
             _ptr(n.area, C.c_double), _ptr(n.length, C.c_double), _ptr(n.slope, C.c_double), _ptr(n.width, C.c_double),
@@ -165,6 +173,21 @@ class Router:
     def set_stream(self, cuda_stream: int):
         """Launch on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
         self._check(self._L.mr_set_stream(self._h, C.c_void_p(cuda_stream or None), self._msg))
+
+    # ---- multi-domain hand-off -------------------------------------------------------------------
+    def set_export(self, seg_ids):
+        ids = np.ascontiguousarray(seg_ids, dtype=np.int32)
+        self._check(self._L.mr_set_export(self._h, len(ids), _ptr(ids, C.c_int), self._msg))
+
+    def exchange_bytes(self, which: int) -> int:
+        return int(self._L.mr_exchange_bytes(self._h, int(which)))
+
+    def set_exchange_buffer(self, which: int, dev_ptr: int = 0, nbytes: int = 0):
+        """which: 0 export / 1 import; dev_ptr 0 lets the library allocate."""
+        self._check(self._L.mr_set_exchange_buffer(self._h, int(which), C.c_void_p(dev_ptr or None), int(nbytes), self._msg))
+
+    def copy_exchange_to(self, dst: "Router", src_slot0: int, dst_slot0: int, n_slots: int):
+        self._check(self._L.mr_copy_exchange(self._h, dst._h, int(src_slot0), int(dst_slot0), int(n_slots), self._msg))
 
     def set_counting(self, on: bool):
         self._check(self._L.mr_set_counting(self._h, int(on), self._msg))

@@ -53,6 +53,8 @@ def test_cuda_reproduces_golden(name, batch):
     for i, c in enumerate(opts.route_opt):
         if c == "2":
             assert rel_err(q[i], z["q"][i]) <= KWT_RTOL
+        elif opts.is_lake_sim and c != "0":        # the Doll-2003 release calls pow(): device and libm differ in the last ulp
+            assert rel_err(q[i], z["q"][i]) <= IRF_RTOL
         else:
             assert np.array_equal(q[i], z["q"][i]), f"method {c} expected bit-identical"
     assert np.array_equal(r.basin_uh(), z["frac_future"])
