@@ -124,6 +124,11 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
 int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message);
 int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
 int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
+/* mr_route_resident without the final wait: the kernels are enqueued on the handle's stream and the call returns,
+ * so a caller can keep several domains (tributaries of the next batch, mainstem of this one) in flight on
+ * different streams.  mr_wait blocks until the stream is idle and reports a device-side error (ierr, message). */
+int mr_route_resident_async(mr_handle h, int nSteps, double T0, char *message);
+int mr_wait(mr_handle h, char *message);
 
 /* RCHFLX_out(:)%ROUTE(method)%<field> / %BASIN_* after the last step, caller's reach order. */
 int mr_get_flux(mr_handle h, int method, int field, double *out /* [nRch] */, char *message);

@@ -13,6 +13,8 @@ constexpr int KWP = 24;               // pitch of a reach's particle row in HBM:
 constexpr int WCAP = 160;             // per-warp particle scratch (own + merged upstream), see kwt_reach
 constexpr int MAXSER = 32;            // series merged at one confluence (basins + non-headwater reaches)
 constexpr int POOL = 208;             // staged upstream series points (<= WCAP + MAXSER + MAXSER/2)
+constexpr int WCAP_S = 64;            // the same for the shared-memory fast path (tasks that need more are re-run
+constexpr int POOL_S = 88;            // with the full-capacity scratch in the global arena)
 constexpr int NKIN = MR_MAXQPAR + 2;  // kinwav work arrays (1-based, <= 19 particles routed)
 
 enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
@@ -42,6 +44,7 @@ struct DevNet {
     const int *expSlot, *impSlot;   // by position, -1 = none (nullptr = feature off)
     double *expBuf; const double *impBuf;
     int recLen, kmax, nRoutes, routeSlot[3];
+    void *kwArena; unsigned long long *kwArenaMask;   // full-capacity KWT scratch: 64 slots per SM + their busy bits
     int *err;                       // [0] code (0 = ok) [1] position [2] site
     unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
 };

@@ -39,10 +39,10 @@ constexpr int BASIN_TPB = 128;
 __global__ void __launch_bounds__(BASIN_TPB) k_basin(DevNet d, int K, long long tau0) {
     extern __shared__ double s_dyn[];
     double (*s_rr)[BASIN_TPB] = reinterpret_cast<double (*)[BASIN_TPB]>(s_dyn);   // [BASIN_TC][BASIN_TPB] reach runoff
-    double *s_uh = s_dyn + BASIN_TC * BASIN_TPB;                                  // [nb] hillslope UH
+    double *s_uh = s_dyn + BASIN_TC * BASIN_TPB;                                  // [2][nb] hillslope UH, lake UH
     const int N = d.nRch, nb = d.ntdhBas;
     const int p = blockIdx.x * BASIN_TPB + threadIdx.x;
-    for (int k = threadIdx.x; k < nb; k += BASIN_TPB) s_uh[k] = d.fracFuture[k];
+    for (int k = threadIdx.x; k < nb; k += BASIN_TPB) { s_uh[k] = d.fracFuture[k]; s_uh[nb + k] = k == 0 ? 1.0 : 0.0; }
     const bool live = p < N && !(p < N && (d.flags[p] & FLAG_GHOST));
     int h0 = 0, h1 = 0; double area = 0.0; bool lake = false;
     if (live) { h0 = d.hruPtr[p]; h1 = d.hruPtr[p + 1]; area = d.basArea[p]; lake = (d.flags[p] & FLAG_LAKE) != 0; }
@@ -71,30 +71,56 @@ __global__ void __launch_bounds__(BASIN_TPB) k_basin(DevNet d, int K, long long 
         if (d.doesBasinRoute != 1 || !live) continue;
         // phase 2.  Step t of the chunk has ring head (tau0+c0+t) mod nb; physical slot s is logical
         // k = (s - head) mod nb at that step, i.e. k decreases by one per step and wraps from 0 to nb-1.
+        // A group of BASIN_G consecutive slots is "clean" at a step when none of them is logical slot 0 and their
+        // logical indices do not wrap inside the group: then the step is BASIN_G multiply-adds with consecutive UH
+        // ordinates and nothing else, and clean steps come in runs (k0 counts down to 1).  Runs are evaluated 8 steps
+        // at a time from a sliding window of 15 UH ordinates held in registers; the 8 steps around a wrap take the
+        // general path.  Either way every slot sees  v = v + uh[k]*rr[t]  in step order (basinUH.f90:165-176).
         const int head0 = (int)((tau0 + c0) % nb);
+        const double *uhp = lake ? s_uh + nb : s_uh;       // lakes: UH = [1, 0, 0, ...] (basinUH.f90:113-116)
+        const bool fastOK = nb >= 2 * BASIN_G;
         for (int s0 = 0; s0 < nb; s0 += BASIN_G) {
-            double v[BASIN_G]; int k[BASIN_G];
+            const bool full = s0 + BASIN_G <= nb;
+            double v[BASIN_G];
 #pragma unroll
-            for (int g = 0; g < BASIN_G; ++g) {
-                const int s = s0 + g;
-                v[g] = (s < nb) ? d.qfutBas[(size_t)s * N + p] : 0.0;
-                int kk = s - head0; if (kk < 0) kk += nb;
-                k[g] = kk;
-            }
-            for (int t = 0; t < nc; ++t) {
-                const double x = s_rr[t][threadIdx.x];
+            for (int g = 0; g < BASIN_G; ++g) v[g] = (s0 + g < nb) ? d.qfutBas[(size_t)(s0 + g) * N + p] : 0.0;
+            int t = 0;
+            while (t < nc) {
+                int k0 = (s0 - head0 - t) % nb; if (k0 < 0) k0 += nb;       // logical index of slot s0 at step t
+                if (fastOK && full && k0 >= 1 && k0 + BASIN_G - 1 <= nb - 1) {
+                    int nrun = k0 < nc - t ? k0 : nc - t;                    // clean while k0 counts down to 1
+                    int kb = k0;
+                    const int tend = t + nrun;
+                    for (; t + 8 <= tend; t += 8, kb -= 8) {
+                        double w[BASIN_G + 7];
 #pragma unroll
-                for (int g = 0; g < BASIN_G; ++g) {
-                    if (s0 + g < nb) {
-                        const double u = lake ? (k[g] == 0 ? 1.0 : 0.0) : s_uh[k[g]];      // basinUH.f90:113-116
-                        v[g] = v[g] + u * x;
-                        if (k[g] == 0) {          // this slot is BASIN_QR(1) of step t; it re-enters as slot nb-1 = 0
-                            d.qrSer[(size_t)(c0 + t + 1) * N + p] = v[g];
-                            v[g] = 0.0;
-                            k[g] = nb;
+                        for (int i = 0; i < BASIN_G + 7; ++i) w[i] = uhp[kb - 7 + i];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const double x = s_rr[t + j][threadIdx.x];
+#pragma unroll
+                            for (int g = 0; g < BASIN_G; ++g) v[g] = v[g] + w[g - j + 7] * x;
                         }
-                        k[g] -= 1;
                     }
+                    for (; t < tend; ++t, --kb) {
+                        const double x = s_rr[t][threadIdx.x];
+#pragma unroll
+                        for (int g = 0; g < BASIN_G; ++g) v[g] = v[g] + uhp[kb + g] * x;
+                    }
+                } else {
+                    const double x = s_rr[t][threadIdx.x];
+#pragma unroll
+                    for (int g = 0; g < BASIN_G; ++g) {
+                        if (s0 + g < nb) {
+                            int kk = k0 + g; if (kk >= nb) kk -= nb;
+                            v[g] = v[g] + uhp[kk] * x;
+                            if (kk == 0) {            // this slot is BASIN_QR(1) of step t; it re-enters as slot nb-1, empty
+                                d.qrSer[(size_t)(c0 + t + 1) * N + p] = v[g];
+                                v[g] = 0.0;
+                            }
+                        }
+                    }
+                    ++t;
                 }
             }
 #pragma unroll
@@ -256,25 +282,57 @@ __global__ void k_kwt_params(int N, const double *rslope, const double *rmann, d
     aK[p] = ALFA * pow(k, 1.0 / ALFA);
 }
 
-// KWT wavefront: one warp per (reach, step); the wave particles sit in the warp's shared-memory scratch
-constexpr int KWT_WARPS = 4;     // warps per block (4 x 6.8 KB scratch; 8 blocks per SM)
-__global__ void __launch_bounds__(32 * KWT_WARPS, 8) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
-    __shared__ KwtScratch S[KWT_WARPS];
-    const int wid = threadIdx.x >> 5;
-    const int p = lo + blockIdx.x * KWT_WARPS + wid;
-    if (p >= hi) return;                               // whole warps leave together
+// KWT wavefront: one team of MR_TEAM lanes per (reach, step); the wave particles sit in the team's shared-memory
+// scratch.  The rare task that needs more room than the shared scratch offers borrows a full-capacity scratch
+// from a global arena (64 slots per SM, claimed with an atomic bit mask).
+constexpr int KWT_WARPS = 4;                             // warps per block
+constexpr int KWT_TEAMS = KWT_WARPS * (32 / MR_TEAM);    // teams (tasks in flight) per block
+constexpr int KWT_ARENA_SMS = 256, KWT_ARENA_SLOTS = 64;
+// one (reach, step) task of a KWT wavefront
+__device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, int p, int w, long long tau0) {
+    const int lane = MR_LANE;
     const int t = w - d.stageOf[p];
     const int flags = d.flags[p];
     if (flags & FLAG_GHOST) {                          // this step's wave of a tributary outlet routed in another domain
-        const int lane = threadIdx.x & 31, b = (int)((tau0 + t) & 1);
+        const int b = (int)((tau0 + t) & 1);
         const double *rec = d.impBuf + ((size_t)d.impSlot[p] * d.kmax + t) * d.recLen + d.nRoutes + 1;
         const size_t row = (size_t)p * KWP;
-        if (lane < KWP) { d.kwQF[b][row + lane] = rec[2 + lane]; d.kwTR[b][row + lane] = rec[2 + KWP + lane]; }
+        for (int k = lane; k < KWP; k += MR_NL) { d.kwQF[b][row + k] = rec[2 + k]; d.kwTR[b][row + k] = rec[2 + KWP + k]; }
         if (lane == 0) { d.kwN[b][p] = (int)rec[0]; d.kwNR[b][p] = (int)rec[1]; }
         return;
     }
-    if (flags & FLAG_LAKE) { if ((threadIdx.x & 31) == 0) lake_reach<M_KWT>(d, p, t, tau0 + t); return; }
-    kwt_reach_team(d, S[wid], p, t, tau0 + t, d.T0s[t], d.T1s[t]);
+    if (flags & FLAG_LAKE) { if (lane == 0) lake_reach<M_KWT>(d, p, t, tau0 + t); return; }
+    if (kwt_reach_team(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t]) != KWT_RETRY) return;
+    // wide confluence: claim a full-capacity scratch of this SM
+    unsigned sm;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    sm &= KWT_ARENA_SMS - 1;
+    int slot = 0;
+    if (lane == 0) {
+        for (;;) {
+            const unsigned long long busy = atomicOr(&d.kwArenaMask[sm], 0ull);
+            if (~busy == 0ull) continue;
+            const int bit = __ffsll((long long)~busy) - 1;
+            if (!((atomicOr(&d.kwArenaMask[sm], 1ull << bit) >> bit) & 1ull)) { slot = bit; break; }
+        }
+    }
+    slot = team_bcast(slot, 0);
+    KwtScratch &B = reinterpret_cast<KwtScratch *>(d.kwArena)[(size_t)sm * KWT_ARENA_SLOTS + slot];
+    kwt_reach_team(d, B, p, t, tau0 + t, d.T0s[t], d.T1s[t]);
+    MR_SYNC();
+    if (lane == 0) { __threadfence(); atomicAnd(&d.kwArenaMask[sm], ~(1ull << slot)); }
+}
+
+// Tasks are dealt round-robin to the teams of a grid that is at most one resident wave (8 blocks per SM), so a
+// team works through several tasks and no block-scheduling cost is paid per task.
+__global__ void __launch_bounds__(32 * KWT_WARPS, 8) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
+    __shared__ KwtScratchSmall S[KWT_TEAMS];
+    const int team = threadIdx.x / MR_TEAM;
+    const int stride = gridDim.x * KWT_TEAMS;
+    for (int p = lo + blockIdx.x * KWT_TEAMS + team; p < hi; p += stride) {
+        kwt_task(d, S[team], p, w, tau0);
+        MR_SYNC();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

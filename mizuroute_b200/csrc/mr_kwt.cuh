@@ -1,7 +1,7 @@
 // Warp-cooperative kinematic-wave-tracking reach step: kwt_rch and callees, kwt_route.f90:36-1622.
 //
-// One team (a 32-lane warp on the device, see mr_lanes.h) routes one (reach, step).  The wave particles of the
-// reach live in the team's shared-memory scratch, one particle per lane:
+// One team (MR_TEAM lanes of a warp on the device, see mr_lanes.h) routes one (reach, step).  The wave particles of
+// the reach live in the team's shared-memory scratch, one particle per lane:
 //   getusq_rch/qexmul_rch  every candidate exit time of the upstream series is ranked and evaluated by its own
 //                          lane (the reference's sequential k-way MINLOC merge, :895-976, visits candidates in
 //                          (time, series) order; rank, duplicate flag and interpolation brackets of a candidate
@@ -19,21 +19,25 @@
 
 namespace mr {
 
-// per-team scratch (shared memory on the device)
-struct KwtScratch {
-    double Q[WCAP], TE[WCAP];          // Q_JRCH, TENTRY (0:n-1)
+// Per-team scratch.  Two sizes: the small one lives in shared memory and covers all but the widest confluences;
+// a task that does not fit (kwt_reach_team returns KWT_RETRY before it has changed any state) is re-run with the
+// full-capacity scratch, which lives in a global-memory arena (k_route_kwt).
+template <int WCAP_, int POOL_>
+struct KwtScratchT {
+    static constexpr int CAP = WCAP_, PCAP = POOL_;
+    double Q[WCAP_], TE[WCAP_];        // Q_JRCH, TENTRY (0:n-1)
     double TX[KWP];                    // T_EXIT: only element 0 is an input; 1..NQ2 are written by kinwav
     union {
         struct {                       // qexmul_rch: staged upstream series
-            double sq[POOL], st[POOL]; // flow and time of every staged point
+            double sq[POOL_], st[POOL_]; // flow and time of every staged point
             double scf[MAXSER];        // UWIDTH / R_WIDTH(JRCH)
             int upos[MAXSER];
             short soff[MAXSER], slen[MAXSER], ncand[MAXSER], cmax[MAXSER], cbase[MAXSER];
-            unsigned char flag[WCAP];
+            unsigned char flag[WCAP_];
         } m;
         struct {                       // remove_rch
-            double ERR[WCAP];
-            unsigned char prv[WCAP], nxt[WCAP];
+            double ERR[WCAP_];
+            unsigned char prv[WCAP_], nxt[WCAP_];
         } th;
         struct {                       // kinwav_rch
             double T0[NKIN], T1[NKIN], Q0[NKIN], Q1[NKIN], Q2[NKIN], WC[NKIN], IWC[NKIN], XX[NKIN], TEX[NKIN];
@@ -41,6 +45,9 @@ struct KwtScratch {
         } k;
     } u;
 };
+using KwtScratch = KwtScratchT<WCAP, POOL>;             // full capacity
+using KwtScratchSmall = KwtScratchT<WCAP_S, POOL_S>;    // shared-memory fast path
+constexpr int KWT_RETRY = 1;
 
 // interp_rch (kwt_route.f90:1444-1622) for a single output interval (TOLD/QOLD 0-based), as a team: the trapezoids
 // of the middle part are evaluated by the lanes and added by lane 0 in the
@@ -105,7 +112,8 @@ MR_DEV_NOINLINE double thin_err(const double *Q, const double *T, int a, int m, 
 // survivors visits them in the same order, so "first minimum" picks the same particle.  T_EXIT needs no
 // compaction: only element 0 (never removed) is read afterwards.
 // ------------------------------------------------------------------------------------------------
-MR_DEV int kwt_thin_team(KwtScratch &S, int &n) {
+template <class SC>
+MR_DEV int kwt_thin_team(SC &S, int &n) {
     const int lane = MR_LANE;
     double *Q = S.Q, *T = S.TE, *ERR = S.u.th.ERR;
     unsigned char *prv = S.u.th.prv, *nxt = S.u.th.nxt;
@@ -163,7 +171,8 @@ MR_DEV int kwt_thin_team(KwtScratch &S, int &n) {
 // S.Q/S.TE/S.TX hold flow, entry time and exit time, `routed` the FROUTE flags (bit i-1 = particle i).
 // Returns the reference's ierr (20 zero flow, 30 TEXIT==TEXIT2, 60 rUpdate bounds), identical on all lanes.
 // ------------------------------------------------------------------------------------------------
-MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START, double T_END, int NQ1, int &NQ2, unsigned &routed) {
+template <class SC>
+MR_DEV int kwt_kinwav_team(const DevNet &d, SC &S, int p, double T_START, double T_END, int NQ1, int &NQ2, unsigned &routed) {
     const int lane = MR_LANE;
     double *T0 = S.u.k.T0, *T1 = S.u.k.T1, *Q0 = S.u.k.Q0, *Q1 = S.u.k.Q1, *Q2 = S.u.k.Q2, *WC = S.u.k.WC, *IWC = S.u.k.IWC,
            *XX = S.u.k.XX, *TEX = S.u.k.TEX;
@@ -228,22 +237,19 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
             const double CM = (q2n - q1n) / (A2 - A1);
             const double t1n = T1[JXB] + XB / WC[JXB] - XB / CM;
             const int ixb0 = IX[IXB];
-            // shifted values are read before anybody writes
-            double sT1 = 0.0, sWC = 0.0, sIWC = 0.0, sQ1 = 0.0, sQ2 = 0.0, sXX = 0.0; signed char sIX = 0;
-            const int i = IXB + lane;                  // NN <= NKIN-2 < MR_NL on the device; looped on the host
-#if defined(__CUDACC__)
-            if (i <= NN) { sIX = IX[i + 1]; sT1 = T1[i + 1]; sWC = WC[i + 1]; sIWC = IWC[i + 1]; sQ1 = Q1[i + 1]; sQ2 = Q2[i + 1]; sXX = XX[i + 1]; }
-            MR_SYNC();
-            if (i <= NN) { IX[i] = sIX; T1[i] = sT1; WC[i] = sWC; IWC[i] = sIWC; Q1[i] = sQ1; Q2[i] = sQ2; XX[i] = sXX; }
+            // drop particle IXB: shift IXB+1.. down by one, a chunk of MR_NL entries at a time (read, sync, write)
             MR_NOUNROLL
             for (int j = ixb0 + lane; j <= NI; j += MR_NL) MF[j] = (signed char)(MF[j] - 1);
-#else
-            (void)i; (void)sT1; (void)sWC; (void)sIWC; (void)sQ1; (void)sQ2; (void)sXX; (void)sIX;
             MR_NOUNROLL
-            for (int j = ixb0; j <= NI; ++j) MF[j] = (signed char)(MF[j] - 1);
-            MR_NOUNROLL
-            for (int j = IXB; j <= NN; ++j) { IX[j] = IX[j + 1]; T1[j] = T1[j + 1]; WC[j] = WC[j + 1]; IWC[j] = IWC[j + 1]; Q1[j] = Q1[j + 1]; Q2[j] = Q2[j + 1]; XX[j] = XX[j + 1]; }
-#endif
+            for (int base = IXB; base <= NN; base += MR_NL) {
+                const int i = base + lane;
+                double sT1 = 0.0, sWC = 0.0, sIWC = 0.0, sQ1 = 0.0, sQ2 = 0.0, sXX = 0.0; signed char sIX = 0;
+                if (i <= NN) { sIX = IX[i + 1]; sT1 = T1[i + 1]; sWC = WC[i + 1]; sIWC = IWC[i + 1]; sQ1 = Q1[i + 1]; sQ2 = Q2[i + 1]; sXX = XX[i + 1]; }
+                MR_SYNC();
+                if (i <= NN) { IX[i] = sIX; T1[i] = sT1; WC[i] = sWC; IWC[i] = sIWC; Q1[i] = sQ1; Q2[i] = sQ2; XX[i] = sXX; }
+                MR_SYNC();
+            }
+            MR_SYNC();
             if (lane == 0) { Q2[JXB] = q2n; Q1[JXB] = q1n; T1[JXB] = t1n; WC[JXB] = CM; IWC[JXB] = 1.0 / CM; }
             MR_SYNC();
             if (lane == 0 && JXB >= 2) XX[JXB] = cross(JXB);
@@ -333,7 +339,8 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, KwtScratch &S, int p, double T_START
 // cursor = 1 + (number of that series' candidates already processed), capped at cmax.
 // Returns 0 or -site (identical on all lanes).
 // ------------------------------------------------------------------------------------------------
-MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, double T0, double T1, int nOwn, int &ND, int &nRead) {
+template <class SC>
+MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0, double T1, int nOwn, int &ND, int &nRead) {
     const int lane = MR_LANE;
     const int N = d.nRch;
     const int u0 = d.upPtr[p], NUPB = d.upPtr[p + 1] - u0;
@@ -411,7 +418,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
         return 0;
     }
     if (team_any(bad)) return -E_NO_ROUTED_UP;
-    if (M > WCAP - nOwn || poolN > POOL) return -E_SCRATCH;
+    if (M > SC::CAP - nOwn || poolN > SC::PCAP) return -E_SCRATCH;
     MR_SYNC();
     // stage the upstream waves
     MR_NOUNROLL
@@ -501,7 +508,8 @@ MR_DEV int kwt_merge_team(const DevNet &d, KwtScratch &S, int p, int t, int b, d
 // KWAVE(NR-1:), so the owner simply starts reading at NR-1 next step, and the consumer (exactly one wavefront
 // behind, reading the same buffer) sees the unstripped array.
 // ------------------------------------------------------------------------------------------------
-MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long long tau, double T0, double T1) {
+template <class SC>
+MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1) {
     const int lane = MR_LANE;
     const int N = d.nRch;
     const int b = (int)(tau & 1), bp = b ^ 1;
@@ -516,7 +524,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
             const size_t row = (size_t)p * KWP;
             d.kwQF[b][row] = -9999.0; d.kwTI[b][row] = -9999.0; d.kwTR[b][row] = -9999.0;
         }
-        return;
+        return 0;
     }
     const int u0 = d.upPtr[p];
     const double W = d.rwidth[p];
@@ -533,7 +541,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
     }
     int ND = 0, ND_read = 0;
     if (d.flags[p] & FLAG_LAKE_UP) {                   // lake outlet reach, kwt_route.f90:540-559
-        if (d.upPtr[p + 1] - u0 > 1) { if (lane == 0) raise(d.err, 10, p, E_LAKE_UPS); return; }
+        if (d.upPtr[p + 1] - u0 > 1) { if (lane == 0) raise(d.err, 10, p, E_LAKE_UPS); return 0; }
         if (lane == 0) {
             S.Q[nOwn] = Qs[d.upIdx[u0]] / W; S.TE[nOwn] = T1;
             double qup = 0.0;                          // kwt_route.f90:168-174
@@ -544,10 +552,11 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
         ND = 1;
     } else {
         const int e = kwt_merge_team(d, S, p, t, b, T0, T1, nOwn, ND, ND_read);
+        if (e == -E_SCRATCH && SC::CAP < WCAP) return KWT_RETRY;       // nothing has been modified yet: re-run with the full scratch
         if (e) {
             const int site = -e;
             if (lane == 0) raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site);
-            return;
+            return 0;
         }
     }
     MR_SYNC();
@@ -559,20 +568,20 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
     bool neg = false;
     MR_NOUNROLL
     for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;
-    if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return; }
+    if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return 0; }
 
-    if (n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); return; } }
+    if (n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); return 0; } }
 
     const int NQ1 = n - 1;
     unsigned routed = 0;
     int NQ2;
     const int ek = kwt_kinwav_team(d, S, p, T0, T1, NQ1, NQ2, routed);
-    if (ek) { if (lane == 0) raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); return; }
+    if (ek) { if (lane == 0) raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); return 0; }
     const int NR = mr_popc(routed);                    // count(FROUTE)-1 (FROUTE(0) is always true)
-    if (NR + 1 > NQ2) { if (lane == 0) raise(d.err, 21, p, E_NO_NONROUTED); return; }
+    if (NR + 1 > NQ2) { if (lane == 0) raise(d.err, 21, p, E_NO_NONROUTED); return 0; }
 
     double QNEW = 0.0;
-    if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return; }
+    if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return 0; }
     double Q_END = 0.0, TIMEI = 0.0;
     if (lane == 0) {
         Qs[p] = QNEW * W + qr1;                        // kwt_route.f90:273
@@ -607,6 +616,7 @@ MR_DEV void kwt_reach_team(const DevNet &d, KwtScratch &S, int p, int t, long lo
         d.kwNR[b][p] = NR + 2;
         if (d.kwCount) d.kwCount[p] += (unsigned)(nOwn + ND_read + NQ2 + 2);
     }
+    return 0;
 }
 
 }  // namespace mr

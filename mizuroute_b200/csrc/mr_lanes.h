@@ -1,6 +1,7 @@
 // Lane abstraction for warp-cooperative device code.
 //
-// Device build (nvcc): a "team" is one 32-lane warp; collectives are shuffles / ballots.
+// Device build (nvcc): a "team" is MR_TEAM consecutive lanes of a warp (a whole warp or half of one); collectives
+// are shuffles / ballots / REDUX restricted to the team's lane mask, so the teams of a warp run independently.
 // Host build (g++, tests/emul only): a team is ONE lane, every collective is the identity and every
 // `for (i = MR_LANE; i < n; i += MR_NL)` loop visits all items in order.  The host build exists so the
 // cooperative algorithms (which are written once, against these primitives) can be checked against the CPU
@@ -10,11 +11,17 @@
 #include <cmath>
 
 #if defined(__CUDACC__)
+#ifndef MR_TEAM
+#define MR_TEAM 32                       // lanes per team: 32 = a whole warp, 16 = two teams per warp (measured: the
+                                         // two teams of a warp rarely stay converged, so 16 is not faster)
+#endif
 #define MR_DEV __device__ __forceinline__
 #define MR_DEV_NOINLINE __device__ __noinline__
-#define MR_LANE ((int)(threadIdx.x & 31u))
-#define MR_NL 32
-#define MR_SYNC() __syncwarp()
+#define MR_NL MR_TEAM
+#define MR_LANE ((int)(threadIdx.x & (MR_TEAM - 1)))
+// lanes of this thread's team within its warp
+#define MR_TMASK (MR_TEAM == 32 ? 0xffffffffu : (((1u << (MR_TEAM & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(MR_TEAM - 1))))
+#define MR_SYNC() __syncwarp(MR_TMASK)
 #define MR_NOUNROLL _Pragma("unroll 1")
 #else
 #define MR_DEV inline
@@ -28,25 +35,25 @@
 namespace mr {
 
 #if defined(__CUDACC__)
-MR_DEV bool team_any(bool pred) { return __any_sync(0xffffffffu, pred) != 0; }
-MR_DEV double team_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-MR_DEV int team_bcast(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-MR_DEV unsigned team_bcast(unsigned v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+MR_DEV bool team_any(bool pred) { return __any_sync(MR_TMASK, pred) != 0; }
+MR_DEV double team_bcast(double v, int src) { return __shfl_sync(MR_TMASK, v, src, MR_TEAM); }
+MR_DEV int team_bcast(int v, int src) { return __shfl_sync(MR_TMASK, v, src, MR_TEAM); }
+MR_DEV unsigned team_bcast(unsigned v, int src) { return __shfl_sync(MR_TMASK, v, src, MR_TEAM); }
 // number of lanes below this one whose pred is true; total = number of lanes with pred true
 MR_DEV int team_rank(bool pred, int &total) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    const unsigned m = __ballot_sync(MR_TMASK, pred) >> ((threadIdx.x & 31u) & ~(unsigned)(MR_TEAM - 1));
     total = __popc(m);
-    return __popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+    return __popc(m & ((1u << MR_LANE) - 1u));
 }
 // exclusive prefix sum of v over lanes; total = sum over all lanes
 MR_DEV int team_excl_scan(int v, int &total) {
     int x = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, o);
-        if ((int)(threadIdx.x & 31u) >= o) x += y;
+    for (int o = 1; o < MR_TEAM; o <<= 1) {
+        const int y = __shfl_up_sync(MR_TMASK, x, o, MR_TEAM);
+        if (MR_LANE >= o) x += y;
     }
-    total = __shfl_sync(0xffffffffu, x, 31);
+    total = __shfl_sync(MR_TMASK, x, MR_TEAM - 1, MR_TEAM);
     return x - v;
 }
 // Minimum of NON-NEGATIVE doubles (or +inf / NaN, which order above every finite value) with the warp-reduce
@@ -54,8 +61,8 @@ MR_DEV int team_excl_scan(int v, int &total) {
 MR_DEV double team_min_nonneg(double v, bool &mine) {
     const unsigned long long u = (unsigned long long)__double_as_longlong(v + 0.0);     // -0.0 -> +0.0
     const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
-    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const unsigned mhi = __reduce_min_sync(MR_TMASK, hi);
+    const unsigned mlo = __reduce_min_sync(MR_TMASK, hi == mhi ? lo : 0xffffffffu);
     mine = hi == mhi && lo == mlo;
     return __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
 }
@@ -63,16 +70,16 @@ MR_DEV double team_min_nonneg(double v, bool &mine) {
 MR_DEV void team_argmin_first(double &v, int &i) {
     bool mine;
     v = team_min_nonneg(v, mine);
-    i = (int)__reduce_min_sync(0xffffffffu, mine ? (unsigned)i : 0xffffffffu);
+    i = (int)__reduce_min_sync(MR_TMASK, mine ? (unsigned)i : 0xffffffffu);
 }
 // lexicographic minimum of (v ascending, i DESCENDING), v >= 0: a serial "accept if not greater" scan keeps the last
 MR_DEV void team_argmin_last(double &v, int &i) {
     bool mine;
     v = team_min_nonneg(v, mine);
-    i = (int)__reduce_max_sync(0xffffffffu, mine ? (unsigned)i : 0u);
+    i = (int)__reduce_max_sync(MR_TMASK, mine ? (unsigned)i : 0u);
 }
-MR_DEV unsigned team_or(unsigned x) { return __reduce_or_sync(0xffffffffu, x); }
-MR_DEV int team_min(int x) { return __reduce_min_sync(0xffffffffu, x); }
+MR_DEV unsigned team_or(unsigned x) { return __reduce_or_sync(MR_TMASK, x); }
+MR_DEV int team_min(int x) { return __reduce_min_sync(MR_TMASK, x); }
 MR_DEV int mr_popc(unsigned x) { return __popc(x); }
 #else
 inline bool team_any(bool pred) { return pred; }

@@ -11,6 +11,7 @@
 #include <omp.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +44,7 @@ struct mr_handle_s {
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
+    int kwtGridMax = 148 * 8;                    // one resident wave of k_route_kwt blocks
     // multi-domain hand-off
     std::vector<int> ghostSegId, ghostKind; std::vector<double> ghostTotArea, ghostWidth;   // consumed by mr_set_network
     int nGhost = 0, nExport = 0;
@@ -128,7 +130,11 @@ void launch_wavefronts(mr_handle h, int K, long long tau0) {
         const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
         const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
         if (hi <= lo) continue;                  // stages that hold only headwaters
-        if constexpr (M == M_KWT) k_route_kwt<<<(hi - lo + KWT_WARPS - 1) / KWT_WARPS, 32 * KWT_WARPS, 0, h->stream>>>(h->d, lo, hi, w, tau0);
+        if constexpr (M == M_KWT) {
+            int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
+            if (grid > h->kwtGridMax) grid = h->kwtGridMax;
+            k_route_kwt<<<grid, 32 * KWT_WARPS, 0, h->stream>>>(h->d, lo, hi, w, tau0);
+        }
         else k_route<M><<<(hi - lo + 255) / 256, 256, 0, h->stream>>>(h->d, lo, hi, w, tau0);
         h->launchesLast++;
     }
@@ -365,6 +371,9 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         AL(kK, N); AL(kAK, N);
         k_kwt_params<<<(N + 255) / 256, 256, 0, h->stream>>>(N, d.rslope, d.rmann, kK, kAK);
         d.kwK = kK; d.kwAK = kAK;
+        KwtScratch *arena = nullptr; unsigned long long *amask = nullptr;
+        AL(arena, (size_t)KWT_ARENA_SMS * KWT_ARENA_SLOTS); AL(amask, KWT_ARENA_SMS);
+        d.kwArena = arena; d.kwArenaMask = amask;
         for (int b = 0; b < 2; ++b) {
             AL(d.kwN[b], N); AL(d.kwNR[b], N);
             AL(d.kwQF[b], (size_t)KWP * N); AL(d.kwTI[b], (size_t)KWP * N); AL(d.kwTR[b], (size_t)KWP * N);
@@ -407,7 +416,19 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
 #undef UP
 #undef AL
 
-    h->basinSmem = sizeof(double) * ((size_t)BASIN_TC * BASIN_TPB + h->ntdhBas);
+    {
+        int nSM = 148, perSM = 8;
+        cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, o.device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
+        h->kwtGridMax = 0x7fffffff;                // measured on C4: one block per KWT_TEAMS tasks beats a persistent grid by 3 %
+        (void)nSM; (void)perSM;
+        // tuning knob (development): MR_KWT_WAVES = resident waves the KWT grid may span; 0 = one block per KWT_TEAMS tasks
+        if (const char *ev = std::getenv("MR_KWT_WAVES")) {
+            const double wv = std::atof(ev);
+            h->kwtGridMax = wv <= 0.0 ? 0x7fffffff : (int)(wv * nSM * perSM);
+        }
+    }
+    h->basinSmem = sizeof(double) * ((size_t)BASIN_TC * BASIN_TPB + 2 * (size_t)h->ntdhBas);
     CU(cudaFuncSetAttribute(k_basin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->basinSmem));
     CU(cudaStreamSynchronize(h->stream));
     h->hasNet = true;
@@ -435,6 +456,31 @@ int mr_route_resident(mr_handle h, int nSteps, double T0, char *message) {
     collect_timing(h);
     float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
     h->timing[3] = h->timing[4] = 0.0;
+    put_msg(message, "");
+    return 0;
+}
+
+// the same without waiting: kernels are enqueued on the handle's stream and the call returns; mr_wait collects errors
+int mr_route_resident_async(mr_handle h, int nSteps, double T0, char *message) {
+    const char *where = "mr_route_resident_async";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    e = route_device(h, nSteps, T0, where, message); if (e) return e;
+    CU(cudaEventRecord(h->ev[5], h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_wait(mr_handle h, char *message) {
+    const char *where = "mr_wait";
+    if (!h || !h->hasNet) return fail(message, 1, "mr_wait/handle has no network");
+    CU(cudaSetDevice(h->opt.device));
+    int e = check_device_error(h, where, message); if (e) return e;
+    if (h->lastK > 0) {
+        collect_timing(h);
+        float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
+        h->timing[3] = h->timing[4] = 0.0;
+    }
     put_msg(message, "");
     return 0;
 }

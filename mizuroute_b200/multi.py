@@ -140,6 +140,28 @@ class DomainSet:
         if self.main is not None:
             self.main.route_resident(K)
 
+    def route_resident_pipelined(self, K: int, stream_trib, stream_main):
+        """The same, without host waits and with the mainstem on its own stream: the mainstem of this batch overlaps
+        the tributaries of the next one (tributaries never depend on the mainstem).  `stream_*` are
+        torch.cuda.Stream objects the two routers were bound to with set_stream.  Call `wait()` to collect errors."""
+        torch = self.torch
+        with torch.cuda.stream(stream_trib):
+            if self.trib is not None:
+                self.trib.route_resident_async(K)
+            if self.main is not None:
+                stream_trib.wait_stream(stream_main)       # the previous mainstem batch has consumed the import buffer
+            self.hand_off()                                # NCCL ops are ordered on stream_trib
+        if self.main is not None:
+            stream_main.wait_stream(stream_trib)
+            with torch.cuda.stream(stream_main):
+                self.main.route_resident_async(K)
+
+    def wait(self):
+        if self.trib is not None:
+            self.trib.wait()
+        if self.main is not None:
+            self.main.wait()
+
     def launches(self) -> int:
         n = self.trib.info(capi.INFO_LAUNCHES_LAST) if self.trib is not None else 0
         if self.main is not None:

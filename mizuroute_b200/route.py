@@ -127,6 +127,14 @@ class Router:
         self._check(self._L.mr_route_resident(self._h, int(K), self.TSEC[0], self._msg))
         self._advance(K)
 
+    def route_resident_async(self, K: int):
+        """Enqueue K steps and return; `wait()` blocks and raises a device-side RoutingError, if any."""
+        self._check(self._L.mr_route_resident_async(self._h, int(K), self.TSEC[0], self._msg))
+        self._advance(K)
+
+    def wait(self):
+        self._check(self._L.mr_wait(self._h, self._msg))
+
     def download_q(self, K: int, out=None):
         if out is None:
             out = np.empty((len(self.methods), K, self.nRch))

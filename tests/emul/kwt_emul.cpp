@@ -50,6 +50,8 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     double t0 = 0.0, t1 = dt;
     for (int t = 0; t < nSteps; ++t) { T0s[t] = t0; T1s[t] = t1; t0 = t1; t1 = t0 + dt; }
     static KwtScratch S;
+    static KwtScratchSmall Ssmall;
+    long retries = 0;
     for (int t = 0; t < nSteps; ++t) {
         const int b = t & 1;
         for (int p = 0; p < T.nHead; ++p) {                 // k_headwater<M_KWT>
@@ -57,13 +59,17 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
             kwN[b][p] = 1; kwNR[b][p] = 0;
         }
         for (int p = T.nHead; p < N; ++p) {                 // stage order: upstream before downstream
-            kwt_reach_team(d, S, p, t, (long long)t, T0s[t], T1s[t]);
+            // the shared-memory-sized scratch first, the full-capacity one on KWT_RETRY -- as k_route_kwt does
+            if (kwt_reach_team(d, Ssmall, p, t, (long long)t, T0s[t], T1s[t]) == KWT_RETRY) {
+                ++retries;
+                kwt_reach_team(d, S, p, t, (long long)t, T0s[t], T1s[t]);
+            }
             if (err[0]) { std::snprintf(msg, 256, "ierr %d at position %d (reach %d) site %d step %d", err[0], err[1], T.pos2rch[err[1]], err[2], t); return err[0]; }
         }
     }
     for (int t = 0; t < nSteps; ++t) for (int r = 0; r < N; ++r) q_out[(size_t)t * N + r] = qSer[(size_t)t * N + T.rch2pos[r]];
     const int b = (nSteps - 1) & 1;
     for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r]; n_out[r] = kwN[b][p] - (kwNR[b][p] > 0 ? kwNR[b][p] - 1 : 0); }
-    msg[0] = 0;
+    std::snprintf(msg, 256, "retries=%ld", retries);
     return 0;
 }

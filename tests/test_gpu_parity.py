@@ -84,6 +84,15 @@ def test_kwt_thinning_and_shocks_exercised():
     _assert_q(opts, qo, qg)
 
 
+def test_wide_confluence_uses_full_scratch():
+    """12 interior arms into one reach: more merged particles than the shared-memory scratch holds, so the task is
+    re-run with the arena scratch (k_route_kwt); also a 12-way confluence for SUM and IRF."""
+    from tests.util import star_network
+    net, params, opts, ro = star_network(route_opt="012")
+    o, r, qo, qg = _run_both(net, params, opts, ro, 8)
+    _assert_q(opts, qo, qg)
+
+
 def test_lakes():
     net, params, opts, ro = case("conus", n=5000, seed=4, dt=86400.0, route_opt="12", steps=30, lakes=40)
     assert net.islake.sum() > 0

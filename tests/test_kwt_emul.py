@@ -29,6 +29,7 @@ def _emul_vs_oracle(net, params, opts, ro):
                           p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
                           C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double), p(ne, C.c_int), msg)
     assert ierr == 0, msg.value.decode()
+    _emul_vs_oracle.retries = int(msg.value.decode().split("=")[1])
     return o, qo, qe, ne
 
 
@@ -42,6 +43,16 @@ def test_team_kwt_bit_exact_vs_oracle(kind, n, dt, steps):
         assert orc.lib().mro_counter(0) > 0, "thinning was not exercised"
     assert np.array_equal(qe, qo)
     assert np.array_equal(ne, o.get_state()["kwt_n"])
+
+
+def test_team_kwt_full_scratch_retry():
+    """A star confluence (12 interior reaches draining into one) overflows the shared-memory-sized scratch and must be
+    re-run with the full-capacity one, with the same result."""
+    from tests.util import star_network
+    net, params, opts, ro = star_network()
+    o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro)
+    assert _emul_vs_oracle.retries > 0, "the wide confluence did not exercise the full-capacity scratch"
+    assert np.array_equal(qe, qo)
 
 
 def test_team_kwt_zero_area_parents():

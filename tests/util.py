@@ -28,3 +28,26 @@ def case(kind="random", n=60, seed=5, dt=3600.0, route_opt="012", steps=24, zero
         opts.LakeInputOption = 1
     ro = synth.runoff_series(net, steps, seed=seed + 1, dt=dt)
     return net, RouteParams(), opts, ro
+
+
+def star_network(arms=12, depth=3, seed=3, steps=40, dt=3600.0, route_opt="2"):
+    """`arms` chains of `depth` interior reaches (each fed by two headwaters) draining into one hub reach: a
+    confluence wide enough to overflow the shared-memory-sized KWT scratch (full-capacity retry path)."""
+    from mizuroute_b200.network import RiverNetwork
+    rng = np.random.default_rng(seed)
+    seg, down = [1], [0]
+    sid = 2
+    for _ in range(arms):
+        prev = 1
+        for _k in range(depth):
+            me = sid; sid += 1
+            seg.append(me); down.append(prev)
+            for _h in range(2):
+                seg.append(sid); down.append(me); sid += 1
+            prev = me
+    n = len(seg)
+    net = RiverNetwork(segId=np.array(seg), downSegId=np.array(down), length=rng.uniform(500, 3000, n), slope=rng.uniform(1e-3, 1e-2, n),
+                       hruId=np.arange(1, n + 1), hruSegId=np.array(seg), area=rng.uniform(1e6, 2e7, n))
+    opts = RouteOptions(dt=dt, route_opt=route_opt, runoffMin=1e-15)
+    ro = np.abs(rng.lognormal(np.log(2e-5), 1.0, size=(steps, n))) + 1e-9
+    return net, RouteParams(), opts, ro
