@@ -403,7 +403,8 @@ def main():
             "peak_source": peak_src, "launches_per_step": n_launch_dom,
             "alg_bytes_per_launch": alg[dom] / n_launch_dom,
             "avg_launch_us": 1e3 * fam_ms[dom] / n_launch_dom,
-            "share_of_step": fam_ms[dom] / max(sum(fam_ms.values()), 1e-12)}
+            "share_of_step": fam_ms[dom] / max(ms / args.steps, 1e-12),
+            "note": "routing methods run concurrently on separate streams, so the kernel families' times overlap"}
 
     # ---- CPU baseline: the oracle, seeded with the GPU's spun-up state, routes the next steps; the GPU routes
     #      the same steps, which doubles as a full-size parity sample

@@ -19,6 +19,30 @@ NVCC_FLAGS = [
 ]
 
 
+HOST = os.path.join(HERE, "route_runoff")          # stand-alone host (control file + NetCDF-3 I/O), links the library
+HOST_DEPS = ["route_runoff.cpp", "nc3.h", os.path.join("..", "..", "include", "mizuroute_b200.h")]
+
+
+def host_stale() -> bool:
+    if not os.path.exists(HOST):
+        return True
+    t = os.path.getmtime(HOST)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in HOST_DEPS) or os.path.getmtime(LIB) > t
+
+
+def build_host(force: bool = False) -> str:
+    build()
+    if not force and not host_stale():
+        return HOST
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HOST, os.path.join(CSRC, "route_runoff.cpp"), "-L" + HERE, "-lmizuroute_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed building route_runoff")
+    return HOST
+
+
 def stale() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -42,3 +66,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

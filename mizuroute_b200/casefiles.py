@@ -1,0 +1,139 @@
+"""Writes a stand-alone mizuRoute case in the reference's file formats: control file (`<key> value ! comment`,
+route/settings/SAMPLE.control), parameter namelist (route/ancillary_data/param.nml.default), river-network netCDF
+(read_streamSeg.f90:44) and runoff netCDF [time, hru] (read_runoff.f90) -- NetCDF-3 64-bit offset through
+scipy.io.netcdf_file (there is no libnetcdf in this image).  Used by the synthetic-configuration generators and the
+host tests; `mizuroute_b200/route_runoff <control>` runs the case."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+from scipy.io import netcdf_file
+
+from .network import RiverNetwork, RouteOptions, RouteParams
+
+
+def write_network(path: str, net: RiverNetwork):
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("seg", net.nRch)
+    f.createDimension("hru", net.nHRU)
+
+    def put(name, data, dim, typ):
+        v = f.createVariable(name, typ, (dim,))
+        v[:] = data
+
+    put("segId", net.segId, "seg", "i"); put("downSegId", net.downSegId, "seg", "i")
+    put("length", net.length, "seg", "d"); put("slope", net.slope, "seg", "d")
+    put("HRUid", net.hruId, "hru", "i"); put("hruSegId", net.hruSegId, "hru", "i"); put("area", net.area, "hru", "d")
+    if net.width is not None:
+        put("width", net.width, "seg", "d")
+    if net.man_n is not None:
+        put("man_n", net.man_n, "seg", "d")
+    if net.islake is not None:
+        put("islake", net.islake, "seg", "i")
+        put("lakeModelType", net.lakeModelType if net.lakeModelType is not None else np.ones(net.nRch, np.int32), "seg", "i")
+        for k in ("D03_MaxStorage", "D03_Coefficient", "D03_Power", "D03_S0"):
+            if getattr(net, k) is not None:
+                put(k, getattr(net, k), "seg", "d")
+    f.close()
+
+
+def write_runoff(path: str, hru_ids: np.ndarray, runoff: np.ndarray, dt: float, start: str = "2000-01-01 00:00:00",
+                 t_offset_steps: int = 0, dtype: str = "d"):
+    """runoff[time, hru]; time in seconds since `start` (stamped at the start of each step)."""
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("hru", len(hru_ids))
+    t = f.createVariable("time", "d", ("time",))
+    t.units = "seconds since " + start
+    t.calendar = "standard"
+    h = f.createVariable("hruid", "i", ("hru",))
+    h[:] = hru_ids
+    q = f.createVariable("runoff", dtype, ("time", "hru"))
+    q.units = "mm/s"
+    for k in range(runoff.shape[0]):
+        t[k] = (t_offset_steps + k) * dt
+        q[k, :] = runoff[k]
+    f.close()
+
+
+def _stamp(seconds: float, start: str) -> str:
+    import datetime as _dt
+    t0 = _dt.datetime.strptime(start, "%Y-%m-%d %H:%M:%S")
+    return (t0 + _dt.timedelta(seconds=seconds)).strftime("%Y-%m-%d %H:%M:%S")
+
+
+def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
+               start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None) -> str:
+    """Creates <case_dir>/{ancillary,input,output} and returns the control-file path."""
+    anc, inp, out = (os.path.join(case_dir, d) + "/" for d in ("ancillary", "input", "output"))
+    for d in (anc, inp, out):
+        os.makedirs(d, exist_ok=True)
+    write_network(anc + "ntopo.nc", net)
+    with open(anc + "param.nml", "w") as f:
+        f.write("&HSLOPE\n  ! hillslope gamma UH\n  fshape = %r\n  tscale = %r\n/\n&IRF_UH\n  velo = %r\n  diff = %r\n/\n&KWT\n  mann_n = %r\n  wscale = %r\n/\n"
+                % (params.fshape, params.tscale, params.velo, params.diff, params.mann_n, params.wscale))
+    ids, ro = net.hruId, runoff
+    if shuffle_hru_seed is not None:                       # forcing HRUs in a different order than the network's
+        perm = np.random.default_rng(shuffle_hru_seed).permutation(net.nHRU)
+        ids, ro = ids[perm], runoff[:, perm]
+    K = runoff.shape[0]
+    if split_forcing <= 1:
+        write_runoff(inp + "runoff.nc", ids, ro, opts.dt, start)
+        fname_qsim = "runoff.nc"
+    else:
+        bounds = np.linspace(0, K, split_forcing + 1).astype(int)
+        names = []
+        for i in range(split_forcing):
+            nm = "runoff_%02d.nc" % i
+            write_runoff(inp + nm, ids, ro[bounds[i]:bounds[i + 1]], opts.dt, start, t_offset_steps=int(bounds[i]))
+            names.append(nm)
+        with open(inp + "runoff_files.txt", "w") as f:
+            f.write("! forcing files in chronological order\n" + "\n".join(names) + "\n")
+        fname_qsim = "runoff_files.txt"
+    keys = [
+        ("case_name", case_name, "name of simulation"),
+        ("ancil_dir", anc, "directory containing ancillary data"),
+        ("input_dir", inp, "directory containing input data"),
+        ("output_dir", out, "directory containing output data"),
+        ("sim_start", start, "time of simulation start"),
+        ("sim_end", _stamp((K - 1) * opts.dt, start), "time of simulation end"),
+        ("route_opt", opts.route_opt, "routing schemes"),
+        ("doesBasinRoute", opts.doesBasinRoute, "hillslope routing"),
+        ("dt_qsim", int(opts.dt), "simulation time interval [sec]"),
+        ("hw_drain_point", opts.hw_drain_point, "lateral runoff to headwater reaches"),
+        ("min_length_route", opts.min_length_route, "minimum reach length for routing"),
+        ("is_lake_sim", "T" if opts.is_lake_sim else "F", "lake simulation"),
+        ("lakeRegulate", "T" if opts.lakeRegulate else "F", "parametric lake models"),
+        ("LakeInputOption", opts.LakeInputOption, "fluxes for lake simulation"),
+        ("runoffMin", repr(float(opts.runoffMin)), "minimum runoff [m3/s]"),
+        ("fname_ntopOld", "ntopo.nc", "river network netCDF"),
+        ("dname_sseg", "seg", "dimension of segments"),
+        ("dname_nhru", "hru", "dimension of HRUs"),
+        ("fname_qsim", fname_qsim, "runoff netCDF or list of netCDFs"),
+        ("vname_qsim", "runoff", "runoff variable"),
+        ("vname_time", "time", "time variable"),
+        ("vname_hruid", "hruid", "forcing HRU id variable"),
+        ("dname_time", "time", "time dimension"),
+        ("dname_hruid", "hru", "HRU dimension"),
+        ("units_qsim", opts.units_qsim, "units of runoff"),
+        ("dt_ro", int(opts.dt), "forcing interval [sec]"),
+        ("is_remap", "F", "runoff HRUs are the river-network HRUs"),
+        ("param_nml", "param.nml", "spatially constant parameters"),
+        ("restart_write", "never", "restart write option"),
+        ("newFileFrequency", "single", "history file frequency"),
+        ("outputFrequency", 1, "output every step"),
+    ]
+    ctl = os.path.join(case_dir, case_name + ".control")
+    with open(ctl, "w") as f:
+        f.write("! mizuRoute control file written by mizuroute_b200.casefiles\n! format: <key>  value  ! comment\n")
+        for k, v, cmt in keys:
+            f.write("%-24s %-40s ! %s\n" % ("<" + k + ">", v, cmt))
+    return ctl
+
+
+def read_history(path: str) -> dict:
+    f = netcdf_file(path, "r", mmap=False)
+    out = {k: np.array(v[:]) for k, v in f.variables.items()}
+    f.close()
+    return out

@@ -40,6 +40,8 @@ struct mr_handle_s {
     double timing[8] = {0};
     cudaStream_t stream = nullptr, ownStream = nullptr;
     cudaEvent_t ev[10] = {nullptr};
+    cudaStream_t aux[2] = {nullptr, nullptr};    // the routing methods of route_opt are independent: all but the last run on these
+    cudaEvent_t mev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // start / end of each method
     unsigned *dKwCount = nullptr;
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
@@ -122,22 +124,22 @@ void free_device(mr_handle h) {
     h->dKwCount = nullptr;
 }
 
+// wavefront w of method M on stream st: every (reach, step) with stage + step == w (a contiguous position range)
 template <int M>
-void launch_wavefronts(mr_handle h, int K, long long tau0) {
+void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0) {
     const Topology &T = h->topo;
-    for (int w = 0; w < T.nStage + K - 1; ++w) {
-        const int slo = w - K + 1 > 0 ? w - K + 1 : 0;
-        const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
-        const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
-        if (hi <= lo) continue;                  // stages that hold only headwaters
-        if constexpr (M == M_KWT) {
-            int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
-            if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-            k_route_kwt<<<grid, 32 * KWT_WARPS, 0, h->stream>>>(h->d, lo, hi, w, tau0);
-        }
-        else k_route<M><<<(hi - lo + 255) / 256, 256, 0, h->stream>>>(h->d, lo, hi, w, tau0);
-        h->launchesLast++;
+    const int slo = w - K + 1 > 0 ? w - K + 1 : 0;
+    const int shi = w < T.nStage - 1 ? w : T.nStage - 1;
+    const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
+    if (hi <= lo) return;                        // stages that hold only headwaters
+    if constexpr (M == M_KWT) {
+        int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
+        if (grid > h->kwtGridMax) grid = h->kwtGridMax;
+        k_route_kwt<<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+    } else {
+        k_route<M><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
+    h->launchesLast++;
 }
 
 __global__ void k_times(double T0, double dt, int K, double *T0s, double *T1s) {
@@ -173,17 +175,33 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     }
     if (h->nExport && !d.expBuf) return fail(message, 1, std::string(where) + "/export reaches but no export buffer (mr_set_exchange_buffer)");
     CU(cudaEventRecord(h->ev[2], h->stream));
-    const int hb = (d.nHead + 255) / 256;
-    for (int r = 0; r < h->opt.n_routes; ++r) {
-        if (r > 0) CU(cudaEventRecord(h->ev[6 + r], h->stream));
-        switch (h->opt.route_methods[r]) {
-            case M_SUM: if (hb) { k_headwater<M_SUM><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
-                        launch_wavefronts<M_SUM>(h, K, h->stepsDone); break;
-            case M_IRF: if (hb) { k_headwater<M_IRF><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
-                        launch_wavefronts<M_IRF>(h, K, h->stepsDone); break;
-            case M_KWT: if (hb) { k_headwater<M_KWT><<<hb, 256, 0, h->stream>>>(d, K, h->stepsDone); h->launchesLast++; }
-                        launch_wavefronts<M_KWT>(h, K, h->stepsDone); break;
+    // The methods of route_opt share only BASIN_QR (read-only here), so they run concurrently: the last one on the
+    // handle's stream, the others on auxiliary streams forked after k_basin and joined before the export.
+    const int hb = (d.nHead + 255) / 256, nr = h->opt.n_routes;
+    cudaStream_t st[3];
+    for (int r = 0; r < nr; ++r) {
+        st[r] = r == nr - 1 ? h->stream : h->aux[r];
+        if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
+        CU(cudaEventRecord(h->mev[r][0], st[r]));
+        if (hb) {
+            switch (h->opt.route_methods[r]) {
+                case M_SUM: k_headwater<M_SUM><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_IRF: k_headwater<M_IRF><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_KWT: k_headwater<M_KWT><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+            }
+            h->launchesLast++;
         }
+    }
+    for (int w = 0; w < h->topo.nStage + K - 1; ++w)
+        for (int r = 0; r < nr; ++r)
+            switch (h->opt.route_methods[r]) {
+                case M_SUM: launch_wavefront<M_SUM>(h, st[r], w, K, h->stepsDone); break;
+                case M_IRF: launch_wavefront<M_IRF>(h, st[r], w, K, h->stepsDone); break;
+                case M_KWT: launch_wavefront<M_KWT>(h, st[r], w, K, h->stepsDone); break;
+            }
+    for (int r = 0; r < nr; ++r) {
+        CU(cudaEventRecord(h->mev[r][1], st[r]));
+        if (st[r] != h->stream) CU(cudaStreamWaitEvent(h->stream, h->mev[r][1], 0));
     }
     if (h->nExport) {
         k_export_pack<<<(h->nExport * K + 255) / 256, 256, 0, h->stream>>>(d, h->dExpPos, h->nExport, K);
@@ -215,7 +233,7 @@ void collect_timing(mr_handle h) {
     h->timing[2] = span(2, 3);
     const int nr = h->opt.n_routes;
     for (int r = 0; r < 3; ++r) h->timing[5 + r] = 0.0;
-    for (int r = 0; r < nr; ++r) h->timing[5 + r] = span(r == 0 ? 2 : 6 + r, r == nr - 1 ? 3 : 7 + r);
+    for (int r = 0; r < nr; ++r) { ms = 0.f; cudaEventElapsedTime(&ms, h->mev[r][0], h->mev[r][1]); h->timing[5 + r] = ms; }
 }
 
 }  // namespace
@@ -250,6 +268,8 @@ int mr_create(const mr_options *opts, mr_handle *out, char *message) {
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking);
     h->stream = h->ownStream;
     for (int i = 0; i < 10 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->mev[i / 2][i % 2]);
     if (ce != cudaSuccess) { delete h; CU(ce); }
     put_msg(message, "");
     *out = h;
@@ -935,6 +955,8 @@ void mr_destroy(mr_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_device(h);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto &m : h->mev) for (auto &e : m) if (e) cudaEventDestroy(e);
+    for (auto &a : h->aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
 }

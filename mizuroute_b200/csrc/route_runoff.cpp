@@ -1,0 +1,334 @@
+// route_runoff -- stand-alone host of the B200 routing library, the counterpart of the reference's
+// PROGRAM route_runoff (route/build/src/standalone/route_runoff.f90:5-117):
+//
+//     route_runoff <control file> [--batch N] [--dry-run]
+//
+//   init_model      read_control (read_control.f90:18: lines "<key> value ! comment", '!' comment lines, unknown key =
+//                   error) and the parameter namelist &HSLOPE/&IRF_UH/&KWT (read_param.f90:12)
+//   init_data       river network netCDF (read_streamSeg.f90:44: seg/hru dimensions, variable names from the
+//                   <varname_*> keys) -> mr_set_network;  runoff netCDF(s) listed by <fname_qsim> (model_setup.f90
+//                   inFile_pop): time axis, HRU ids; cold start (init_model_data.f90:399-463)
+//   time loop       get_hru_runoff (get_basin_runoff.f90:19: record read + sort_flux, process_remap.f90:271: forcing
+//                   HRU id -> network HRU index, HRUs without forcing and negative values -> 0) -> mr_step_batch
+//                   (mpi_route/main_route) -> history output (write_simoutput_pio.f90:140: float32 [time, seg])
+//
+// Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
+// The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
+// classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
+// <is_remap> must be F, <dt_qsim> must equal the forcing interval, one history file, output every step, standard /
+// proleptic_gregorian / noleap calendars.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/mizuroute_b200.h"
+#include "nc3.h"
+
+namespace {
+
+[[noreturn]] void die(int ierr, const std::string &msg) {       // handle_err, model_utils.f90:45-57
+    std::fprintf(stderr, "FATAL ERROR (ierr=%d): %s\n", ierr, msg.c_str());
+    std::exit(ierr ? ierr : 1);
+}
+
+std::string trim(const std::string &s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+}
+std::string lower(std::string s) { for (auto &c : s) c = (char)std::tolower((unsigned char)c); return s; }
+
+// ---- control file -----------------------------------------------------------------------------------------
+const char *KNOWN_KEYS[] = {
+    "ancil_dir", "input_dir", "output_dir", "restart_dir", "case_name", "sim_start", "sim_end", "continue_run", "route_opt", "doesBasinRoute",
+    "dt_qsim", "floodplain", "hw_drain_point", "tracer", "is_lake_sim", "lakeRegulate", "LakeInputOption", "is_flux_wm", "is_vol_wm",
+    "is_vol_wm_jumpstart", "scale_factor_runoff", "offset_value_runoff", "scale_factor_Ep", "offset_value_Ep", "is_Ep_upward_negative",
+    "scale_factor_prec", "offset_value_prec", "min_length_route", "ntopAugmentMode", "units_qsim", "units_cc", "dt_ro", "input_fillvalue",
+    "ro_calendar", "ro_time_units", "ro_time_stamp", "runoffMin", "dt_wm", "is_remap", "restart_write", "restart_date", "restart_month",
+    "restart_day", "restart_hour", "param_nml", "qmodOption", "qBlendPeriod", "QerrTrend", "hydGeometryOption", "topoNetworkOption",
+    "computeReachList", "gageMetaFile", "outputAtGage", "strlen_gageSite", "pio_netcdf_format", "pio_netcdf_type", "debug", "seg_outlet",
+    "desireId", "checkMassBalance", "maxPfafLen", "pfafMissing", "time_units", "newFileFrequency", "outputFrequency", "outputNameOption",
+    "histTimeStamp_offset", "basRunoff", "instRunoff", "dlayRunoff", "sumUpstreamRunoff", "KWTroutedRunoff", "IRFroutedRunoff",
+    "KWroutedRunoff", "DWroutedRunoff", "MCroutedRunoff", "IRFvolume", "KWTvolume", "KWvolume", "MCvolume", "DWvolume", "KWfloodVolume",
+    "MCfloodVolume", "DWfloodVolume", "KWheight", "MCheight", "DWheight", "localSolute", "soluteFlux", "soluteMass", "outputInflow",
+    "KWTinflow", "IRFinflow", "KWinflow", "MCinflow", "DWinflow", "qgwl_runoff_option", "bypass_routing_option", "correct_area", "ice_runoff"};
+
+struct Control {
+    std::map<std::string, std::string> kv;
+    bool has(const std::string &k) const { return kv.count(k) != 0; }
+    std::string str(const std::string &k, const std::string &dflt) const { auto it = kv.find(k); return it == kv.end() ? dflt : it->second; }
+    std::string need(const std::string &k) const { auto it = kv.find(k); if (it == kv.end()) die(20, "read_control/<" + k + "> must be given"); return it->second; }
+    double num(const std::string &k, double dflt) const { auto it = kv.find(k); if (it == kv.end()) return dflt; char *e; const double v = std::strtod(it->second.c_str(), &e); if (e == it->second.c_str()) die(20, "read_control/cannot read a number from <" + k + ">"); return v; }
+    bool flag(const std::string &k, bool dflt) const { auto it = kv.find(k); if (it == kv.end()) return dflt; const std::string v = lower(it->second); return v == "t" || v == ".true." || v == "true"; }
+};
+
+Control read_control(const std::string &path) {                 // read_control.f90:18-116
+    std::ifstream in(path);
+    if (!in) die(20, "read_control/cannot open control file " + path);
+    std::set<std::string> known(std::begin(KNOWN_KEYS), std::end(KNOWN_KEYS));
+    Control c; std::string line; int lineno = 0;
+    while (std::getline(in, line)) {
+        ++lineno;
+        if (line.find('\t') != std::string::npos) die(20, "read_control/TAB in control file, line " + std::to_string(lineno));
+        std::string s = trim(line);
+        if (s.empty() || s[0] == '!') continue;
+        if (s[0] != '<') die(20, "read_control/expect '<' at the start of line " + std::to_string(lineno));
+        const size_t gt = s.find('>');
+        if (gt == std::string::npos) die(20, "read_control/missing '>' in line " + std::to_string(lineno));
+        const std::string key = s.substr(1, gt - 1);
+        std::string val = s.substr(gt + 1);
+        const size_t bang = val.find('!');
+        if (bang == std::string::npos) die(20, "read_control/missing '!' delimiter in line " + std::to_string(lineno));   // read_control.f90:105-109
+        val = trim(val.substr(0, bang));
+        const bool nameKey = key.rfind("varname_", 0) == 0 || key.rfind("vname_", 0) == 0 || key.rfind("dname_", 0) == 0 || key.rfind("fname_", 0) == 0;
+        if (!nameKey && !known.count(key)) die(81, "read_control/unknown control key <" + key + ">");       // read_control.f90:374-377
+        c.kv[key] = val;
+    }
+    return c;
+}
+
+// &HSLOPE fshape,tscale / &IRF_UH velo,diff / &KWT mann_n,wscale /   (read_param.f90:26-38)
+void read_param_nml(const std::string &path, mr_options &o) {
+    std::ifstream in(path);
+    if (!in) die(20, "read_param/cannot open namelist " + path);
+    std::stringstream ss; ss << in.rdbuf();
+    std::string t = ss.str();
+    // strip comments
+    std::string clean; bool com = false;
+    for (char ch : t) { if (ch == '!') com = true; if (ch == '\n') com = false; if (!com) clean += ch; }
+    auto get = [&](const std::string &name, double &dst) {
+        const std::string lc = lower(clean);
+        size_t p = 0;
+        while ((p = lc.find(name, p)) != std::string::npos) {
+            const bool left = p == 0 || !(std::isalnum((unsigned char)lc[p - 1]) || lc[p - 1] == '_');
+            size_t q = p + name.size();
+            while (q < lc.size() && std::isspace((unsigned char)lc[q])) ++q;
+            if (left && q < lc.size() && lc[q] == '=') {
+                std::string v = clean.substr(q + 1, 64);
+                for (auto &ch : v) if (ch == 'd' || ch == 'D') ch = 'e';       // Fortran 1.0d0
+                dst = std::strtod(v.c_str(), nullptr);
+                return;
+            }
+            p = q;
+        }
+    };
+    get("fshape", o.fshape); get("tscale", o.tscale); get("velo", o.velo); get("diff", o.diff); get("mann_n", o.mann_n); get("wscale", o.wscale);
+}
+
+// ---- time ---------------------------------------------------------------------------------------------------
+// days since 1970-01-01 in the proleptic Gregorian calendar / in a 365-day calendar
+long long days_from_civil(long long y, int m, int d, bool noleap) {
+    if (noleap) { static const int cum[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334}; return (y - 1970) * 365 + cum[m - 1] + (d - 1); }
+    y -= m <= 2;
+    const long long era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400), doy = (153u * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1, doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (long long)doe - 719468;
+}
+double parse_datetime(const std::string &s, bool noleap) {      // "yyyy-mm-dd [hh:mm:ss]" -> seconds since 1970-01-01
+    int y = 0, mo = 1, d = 1, h = 0, mi = 0; double sec = 0.0;
+    const int n = std::sscanf(s.c_str(), "%d-%d-%d %d:%d:%lf", &y, &mo, &d, &h, &mi, &sec);
+    if (n < 3) { if (std::sscanf(s.c_str(), "%d-%d-%dT%d:%d:%lf", &y, &mo, &d, &h, &mi, &sec) < 3) die(20, "datetime/cannot parse date '" + s + "'"); }
+    return (double)days_from_civil(y, mo, d, noleap) * 86400.0 + h * 3600.0 + mi * 60.0 + sec;
+}
+// "<unit> since <date>" -> seconds per unit and reference epoch (model_setup.f90 inFile_pop: t_unit / convTime2sec)
+void parse_time_units(const std::string &units, bool noleap, double &scale, double &epoch) {
+    const std::string u = lower(trim(units));
+    const size_t p = u.find("since");
+    if (p == std::string::npos) die(20, "inFile_pop/time units must be '<unit> since yyyy-mm-dd hh:mm:ss': " + units);
+    const std::string unit = trim(u.substr(0, p));
+    if (unit.rfind("sec", 0) == 0) scale = 1.0; else if (unit.rfind("min", 0) == 0) scale = 60.0; else if (unit.rfind("hour", 0) == 0 || unit == "h" || unit == "hr") scale = 3600.0;
+    else if (unit.rfind("day", 0) == 0) scale = 86400.0; else die(20, "inFile_pop/<time_units>= " + unit + ": must be seconds, minutes, hours or days");
+    epoch = parse_datetime(trim(units.substr(p + 5)), noleap);
+}
+
+std::string join_path(const std::string &dir, const std::string &f) { return (!f.empty() && f[0] == '/') ? f : dir + f; }
+
+struct Forcing { std::string path; size_t nTime = 0; std::vector<double> tsec; };     // record times, seconds since 1970
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run]\n"); return 2; }
+    const std::string cfile = argv[1];
+    int batch = 64; bool dry = false;
+    for (int i = 2; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--dry-run")) dry = true;
+        else die(2, std::string("unknown argument ") + argv[i]);
+    }
+    if (batch < 1) die(2, "--batch must be >= 1");
+    try {
+        // ---- init_model: control file + parameter namelist
+        const Control c = read_control(cfile);
+        const std::string ancil = c.need("ancil_dir"), indir = c.need("input_dir"), outdir = c.need("output_dir");
+        mr_options o{};
+        o.dt = c.num("dt_qsim", -1.0);
+        if (!(o.dt > 0.0)) die(20, "read_control/<dt_qsim> must be given");
+        if (std::fmod(86400.0, o.dt) != 0.0 && std::fmod(o.dt, 86400.0) != 0.0) die(20, "read_control/<dt_qsim> must be a divisor or a multiple of 86400 s");
+        const std::string ropt = c.need("route_opt");
+        o.n_routes = 0;
+        for (char ch : ropt) {                                   // read_control.f90:583-597
+            if (ch < '0' || ch > '5') die(81, "read_control/route_opt must be a string of digits 0-5");
+            if (o.n_routes >= 8) die(81, "read_control/too many routing methods");
+            o.route_methods[o.n_routes++] = ch - '0';
+        }
+        o.doesBasinRoute = (int)c.num("doesBasinRoute", 1);
+        o.hw_drain_point = (int)c.num("hw_drain_point", 2);
+        o.min_length_route = c.num("min_length_route", 0.0);
+        o.is_lake_sim = c.flag("is_lake_sim", false); o.lakeRegulate = c.flag("lakeRegulate", true); o.LakeInputOption = (int)c.num("LakeInputOption", 0);
+        o.runoffMin = c.num("runoffMin", 0.0);
+        if (c.flag("is_remap", false)) die(20, "route_runoff/<is_remap> T (runoff remapping) is not supported by this host");
+        if (c.flag("is_flux_wm", false) || c.flag("is_vol_wm", false)) die(20, "route_runoff/water management is not on this path");
+        {                                                        // units_qsim -> time_conv, length_conv (read_control.f90:443-474)
+            const std::string u = c.need("units_qsim");
+            const size_t sl = u.find('/');
+            if (sl == std::string::npos) die(20, "read_control/expect the character \"/\" exists in the units string");
+            const std::string cl = trim(u.substr(0, sl)), ct = trim(u.substr(sl + 1));
+            if (cl == "m") o.length_conv = 1.0; else if (cl == "mm") o.length_conv = 1.0 / 1000.0; else die(20, "read_control/expect the length units of runoff to be m or mm");
+            if (ct == "d" || ct == "day") o.time_conv = 1.0 / 86400.0; else if (ct == "h" || ct == "hr" || ct == "hour") o.time_conv = 1.0 / 3600.0;
+            else if (ct == "s" || ct == "sec" || ct == "second") o.time_conv = 1.0; else die(20, "read_control/expect the time units of runoff to be day(d), hour(h) or second(s)");
+        }
+        o.fshape = 2.5; o.tscale = 86400.0; o.velo = 1.5; o.diff = 5000.0; o.mann_n = 0.01; o.wscale = 0.001;   // param.nml.default
+        read_param_nml(join_path(ancil, c.need("param_nml")), o);
+        o.device = std::getenv("MR_DEVICE") ? std::atoi(std::getenv("MR_DEVICE")) : 0;
+        o.max_batch = batch;
+
+        // ---- init_ntopo: river network (read_streamSeg.f90:44-276)
+        nc3::Reader nt(join_path(ancil, c.need("fname_ntopOld")));
+        const size_t nRch = nt.dim_len(c.str("dname_sseg", "seg")), nHRU = nt.dim_len(c.str("dname_nhru", "hru"));
+        std::vector<int> segId, downSegId, hruId, hruSegId, islake, lakeType;
+        std::vector<double> area, length, slope, width, man_n, d03[4];
+        nt.read_int(nt.var(c.str("varname_segId", "segId")), segId);
+        nt.read_int(nt.var(c.str("varname_downSegId", "downSegId")), downSegId);
+        nt.read_int(nt.var(c.str("varname_HRUid", "HRUid")), hruId);
+        nt.read_int(nt.var(c.str("varname_hruSegId", "hruSegId")), hruSegId);
+        nt.read_all(nt.var(c.str("varname_area", "area")), area);
+        nt.read_all(nt.var(c.str("varname_length", "length")), length);
+        nt.read_all(nt.var(c.str("varname_slope", "slope")), slope);
+        const bool geomFromFile = (int)c.num("hydGeometryOption", 1) == 0;        // 0 = read width / man_n from the file
+        if (geomFromFile) { nt.read_all(nt.var(c.str("varname_width", "width")), width); nt.read_all(nt.var(c.str("varname_man_n", "man_n")), man_n); }
+        if (o.is_lake_sim) {
+            nt.read_int(nt.var(c.str("varname_islake", "islake")), islake);
+            if (const nc3::Var *v = nt.find(c.str("varname_lakeModelType", "lakeModelType"))) nt.read_int(*v, lakeType);
+            const char *nm[4] = {"D03_MaxStorage", "D03_Coefficient", "D03_Power", "D03_S0"};
+            for (int k = 0; k < 4; ++k) if (const nc3::Var *v = nt.find(c.str(std::string("varname_") + nm[k], nm[k]))) nt.read_all(*v, d03[k]);
+        }
+        if (segId.size() != nRch || hruId.size() != nHRU) die(20, "read_streamSeg/variable sizes do not match the seg/hru dimensions");
+
+        // ---- init_inFile_pop: forcing file(s), time axis, HRU ids
+        std::vector<Forcing> files;
+        {
+            const std::string q = join_path(indir, c.need("fname_qsim"));
+            std::vector<std::string> paths;
+            { FILE *f = std::fopen(q.c_str(), "rb"); if (!f) die(30, "inFile_pop/" + q + " does not exist"); unsigned char m[3] = {0, 0, 0}; const size_t got = std::fread(m, 1, 3, f); std::fclose(f);
+              if (got == 3 && m[0] == 'C' && m[1] == 'D' && m[2] == 'F') paths.push_back(q);
+              else { std::ifstream lst(q); std::string ln; while (std::getline(lst, ln)) { ln = trim(ln); if (!ln.empty() && ln[0] != '!') paths.push_back(join_path(indir, ln)); } } }
+            if (paths.empty()) die(20, "inFile_pop/no forcing file listed in " + q);
+            for (auto &p : paths) { Forcing f; f.path = p; files.push_back(f); }
+        }
+        const std::string vtime = c.need("vname_time"), vq = c.need("vname_qsim"), vhru = c.need("vname_hruid");
+        bool noleap = false; std::vector<int> roHruId;
+        for (auto &f : files) {
+            nc3::Reader r(f.path);
+            const nc3::Var &tv = r.var(vtime);
+            std::string cal = c.str("ro_calendar", r.attr_text(tv, "calendar"));
+            cal = lower(cal); noleap = (cal == "noleap" || cal == "365_day");
+            if (!(cal.empty() || cal == "standard" || cal == "gregorian" || cal == "proleptic_gregorian" || noleap)) die(20, "inFile_pop/calendar '" + cal + "' is not supported by this host");
+            double scale, epoch; parse_time_units(c.str("ro_time_units", r.attr_text(tv, "units")), noleap, scale, epoch);
+            std::vector<double> tt; r.read_all(tv, tt);
+            f.nTime = tt.size(); f.tsec.resize(tt.size());
+            for (size_t i = 0; i < tt.size(); ++i) f.tsec[i] = epoch + tt[i] * scale;
+            if (roHruId.empty()) r.read_int(r.var(vhru), roHruId);
+        }
+        std::vector<double> tAll; std::vector<std::pair<int, size_t>> where;    // (file, record) of every forcing time
+        for (size_t k = 0; k < files.size(); ++k) for (size_t i = 0; i < files[k].nTime; ++i) { tAll.push_back(files[k].tsec[i]); where.push_back({(int)k, i}); }
+        if (tAll.size() >= 2) {
+            const double dtro = tAll[1] - tAll[0];                // dt_ro is taken from the file (model_setup.f90:502)
+            if (std::fabs(dtro - o.dt) > 1e-6 * o.dt) die(20, "route_runoff/forcing interval " + std::to_string(dtro) + " s differs from <dt_qsim>: temporal remapping is not supported by this host");
+        }
+        const double tStart = parse_datetime(c.need("sim_start"), noleap), tEnd = parse_datetime(c.need("sim_end"), noleap);
+        size_t i0 = 0; while (i0 < tAll.size() && tAll[i0] < tStart - 1e-3) ++i0;
+        size_t i1 = i0; while (i1 < tAll.size() && tAll[i1] <= tEnd + 1e-3) ++i1;
+        if (i1 <= i0) die(20, "init_time/no forcing record between <sim_start> and <sim_end>");
+        const size_t nSteps = i1 - i0;
+
+        // sort_flux index: forcing HRU -> network HRU (process_remap.f90:271-311)
+        std::vector<int> ix(roHruId.size(), -1);
+        { std::vector<std::pair<int, int>> tab(nHRU); for (size_t i = 0; i < nHRU; ++i) tab[i] = {hruId[i], (int)i}; std::sort(tab.begin(), tab.end());
+          for (size_t i = 0; i < roHruId.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(roHruId[i], -1)); if (it != tab.end() && it->first == roHruId[i]) ix[i] = it->second; } }
+
+        std::printf("{\"case\": \"%s\", \"nRch\": %zu, \"nHRU\": %zu, \"nHRU_forcing\": %zu, \"nSteps\": %zu, \"dt\": %.1f, \"route_opt\": \"%s\", \"first_record\": %zu, "
+                    "\"fshape\": %.6g, \"tscale\": %.6g, \"velo\": %.6g, \"diff\": %.6g, \"mann_n\": %.6g, \"wscale\": %.6g, \"time_conv\": %.9g, \"length_conv\": %.9g}\n",
+                    c.str("case_name", "case").c_str(), nRch, nHRU, roHruId.size(), nSteps, o.dt, ropt.c_str(), i0, o.fshape, o.tscale, o.velo, o.diff, o.mann_n, o.wscale, o.time_conv, o.length_conv);
+        if (dry) return 0;
+
+        // ---- device side
+        char msg[MR_STRLEN];
+        mr_handle h = nullptr;
+        int ierr = mr_create(&o, &h, msg); if (ierr) die(ierr, msg);
+        ierr = mr_set_network(h, (int)nRch, (int)nHRU, segId.data(), downSegId.data(), hruSegId.data(), area.data(), length.data(), slope.data(),
+                              geomFromFile ? width.data() : nullptr, geomFromFile ? man_n.data() : nullptr, islake.empty() ? nullptr : islake.data(),
+                              lakeType.empty() ? nullptr : lakeType.data(), d03[0].empty() ? nullptr : d03[0].data(), d03[1].empty() ? nullptr : d03[1].data(),
+                              d03[2].empty() ? nullptr : d03[2].data(), d03[3].empty() ? nullptr : d03[3].data(), msg);
+        if (ierr) die(ierr, msg);
+
+        // ---- history file (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
+        char stamp[64]; { int y, mo, d, hh = 0, mi = 0; double ss = 0; std::sscanf(c.need("sim_start").c_str(), "%d-%d-%d %d:%d:%lf", &y, &mo, &d, &hh, &mi, &ss);
+                          std::snprintf(stamp, sizeof stamp, "%04d-%02d-%02d-%05d", y, mo, d, hh * 3600 + mi * 60 + (int)ss); }
+        const std::string opath = join_path(outdir, c.str("case_name", "case") + ".h." + stamp + ".nc");
+        nc3::Writer w(opath);
+        const int dTime = w.def_dim("time", 0), dSeg = w.def_dim("seg", nRch);
+        const int vTime = w.def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
+        const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
+        const char *vname[3] = {"sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"};
+        const char *lname[3] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking"};
+        std::vector<int> vQ(o.n_routes, -1);
+        for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
+            vQ[r] = w.def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
+        w.global_attr("title", "mizuRoute routing (mizuroute-b200)");
+        w.end_def();
+        w.put_int(vId, segId.data());
+
+        // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
+        std::vector<double> ro((size_t)batch * nHRU), q((size_t)o.n_routes * batch * nRch), rec;
+        std::vector<nc3::Reader *> rd(files.size(), nullptr);
+        double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
+        double fillv = c.num("input_fillvalue", -9999.0);
+        for (size_t s = 0; s < nSteps; s += batch) {
+            const int nb = (int)std::min<size_t>(batch, nSteps - s);
+            for (int k = 0; k < nb; ++k) {
+                const auto wr = where[i0 + s + k];
+                if (!rd[wr.first]) rd[wr.first] = new nc3::Reader(files[wr.first].path);
+                nc3::Reader &R = *rd[wr.first];
+                const nc3::Var &qv = R.var(vq);
+                double fv; if (R.attr_value(qv, "_FillValue", fv)) fillv = fv;
+                R.read(qv, rec, wr.second, 1);
+                if (rec.size() != roHruId.size()) die(20, "read_runoff/runoff variable is not dimensioned [time, hru]");
+                double *dst = &ro[(size_t)k * nHRU];
+                std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
+                for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
+            }
+            ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
+            for (int k = 0; k < nb; ++k) {
+                const double tsec = (double)(s + k) * o.dt;
+                w.put_record(vTime, s + k, &tsec);
+                for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);
+            }
+            T0 += nb * o.dt;
+        }
+        for (auto *p : rd) delete p;
+        w.close();
+        mr_destroy(h);
+        std::printf("{\"history\": \"%s\", \"steps\": %zu}\n", opath.c_str(), nSteps);
+    } catch (const std::exception &e) {
+        die(20, e.what());
+    }
+    return 0;
+}

@@ -1,0 +1,75 @@
+"""The stand-alone host `route_runoff` (control file + namelist + NetCDF-3 network/runoff, as the reference's
+route_runoff.exe): input parsing without a GPU (--dry-run), and a full run on the GPU against the oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mizuroute_b200 import build as mrbuild
+from mizuroute_b200 import casefiles
+from mizuroute_b200.network import RouteParams
+from tests.util import case
+
+
+def _host():
+    return mrbuild.build_host()
+
+
+def test_dry_run_parses_reference_style_case(tmp_path):
+    net, params, opts, ro = case("random", n=90, seed=3, dt=3600.0, route_opt="012", steps=30)
+    params = RouteParams(fshape=2.2, tscale=70000.0, velo=1.2, diff=4000.0, mann_n=0.02, wscale=0.0015)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="dry", split_forcing=3, shuffle_hru_seed=1)
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[0])
+    assert (info["nRch"], info["nHRU"], info["nSteps"], info["route_opt"], info["dt"]) == (net.nRch, net.nHRU, 30, "012", 3600.0)
+    assert (info["fshape"], info["tscale"], info["velo"], info["diff"], info["mann_n"], info["wscale"]) == (2.2, 70000.0, 1.2, 4000.0, 0.02, 0.0015)
+    assert info["length_conv"] == 1e-3 and info["time_conv"] == 1.0 and info["first_record"] == 0
+
+
+def test_control_file_errors(tmp_path):
+    net, params, opts, ro = case("random", n=40, seed=3, dt=86400.0, route_opt="1", steps=4)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro)
+    txt = open(ctl).read()
+    bad = tmp_path / "bad.control"
+    bad.write_text(txt + "<no_such_key>   1   ! unknown\n")
+    r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 81 and "unknown control key" in r.stderr          # read_control.f90:374-377
+    import re
+    bad.write_text(re.sub(r"(<is_remap>\s+)F", r"\1T", txt))
+    r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "is_remap" in r.stderr
+    bad.write_text(re.sub(r"(<dt_qsim>\s+)86400", r"\g<1>3600 ", txt))
+    r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "forcing interval" in r.stderr
+
+
+def test_netcdf3_writer_roundtrip_through_scipy(tmp_path):
+    """nc3.h writes what scipy reads: exercised by the host's history file in the GPU test; here the network and
+    runoff files written by scipy are the reader's input (dry run) with float32 runoff and 64-bit offsets."""
+    net, params, opts, ro = case("binary", n=63, seed=2, dt=86400.0, route_opt="2", steps=6)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro.astype(np.float32).astype(np.float64))
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("route,dt,lakes", [("012", 3600.0, 0), ("12", 86400.0, 5)])
+def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=600, seed=8, dt=dt, route_opt=route, steps=40, lakes=lakes)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="gpu", split_forcing=2, shuffle_hru_seed=5)
+    r = subprocess.run([_host(), ctl, "--batch", "16"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hist = json.loads(r.stdout.strip().splitlines()[-1])["history"]
+    out = casefiles.read_history(hist)
+    qo = Oracle(net, params, opts).run(ro)
+    assert np.array_equal(out["reachID"], net.segId)
+    assert np.array_equal(out["time"], np.arange(40) * dt)
+    names = {"0": "sumUpstreamRunoff", "1": "IRFroutedRunoff", "2": "KWTroutedRunoff"}
+    for i, c in enumerate(route):
+        got = out[names[c]]
+        assert got.dtype == np.float32 and got.shape == (40, net.nRch)       # history is float32 [time, seg]
+        np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c != "2" else 1e-4, atol=1e-30)
