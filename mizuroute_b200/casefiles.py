@@ -135,5 +135,6 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
 def read_history(path: str) -> dict:
     f = netcdf_file(path, "r", mmap=False)
     out = {k: np.array(v[:]) for k, v in f.variables.items()}
+    out = {k: a.astype(a.dtype.newbyteorder("=")) for k, a in out.items()}       # netCDF is big-endian on disk
     f.close()
     return out
