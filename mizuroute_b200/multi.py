@@ -75,6 +75,7 @@ class DomainSet:
         self.main: Optional[Router] = None
         self.main_net: Optional[RiverNetwork] = None
         self.exp_t = self.imp_t = None
+        self._copy_done = None
         has_main = d.mainstem.size > 0
         if self.my_outlets.size:
             self.trib.set_export(net.segId[self.my_outlets])
@@ -143,18 +144,44 @@ class DomainSet:
     def route_resident_pipelined(self, K: int, stream_trib, stream_main):
         """The same, without host waits and with the mainstem on its own stream: the mainstem of this batch overlaps
         the tributaries of the next one (tributaries never depend on the mainstem).  `stream_*` are
-        torch.cuda.Stream objects the two routers were bound to with set_stream.  Call `wait()` to collect errors."""
+        torch.cuda.Stream objects the two routers were bound to with set_stream.  Call `wait()` to collect errors.
+
+        Rank 0 receives on the MAINSTEM stream, so its tributary stream never waits for the other ranks; its own
+        outlets are copied export -> import first, and the next tributary batch (which overwrites the export buffer)
+        waits for that copy only."""
         torch = self.torch
         with torch.cuda.stream(stream_trib):
+            if self._copy_done is not None:
+                stream_trib.wait_event(self._copy_done)
             if self.trib is not None:
                 self.trib.route_resident_async(K)
-            if self.main is not None:
-                stream_trib.wait_stream(stream_main)       # the previous mainstem batch has consumed the import buffer
-            self.hand_off()                                # NCCL ops are ordered on stream_trib
-        if self.main is not None:
-            stream_main.wait_stream(stream_trib)
-            with torch.cuda.stream(stream_main):
-                self.main.route_resident_async(K)
+            if self.main is None:
+                self.hand_off()                            # send: ordered after this rank's tributary kernels
+                return
+            trib_done = torch.cuda.Event()
+            trib_done.record(stream_trib)
+        with torch.cuda.stream(stream_main):
+            stream_main.wait_event(trib_done)              # (the previous mainstem batch precedes us on this stream)
+            lo, hi = self.dec.slot_range(0)
+            if hi > lo:
+                self.imp_t[lo:hi].copy_(self.exp_t[: hi - lo])
+            self._copy_done = torch.cuda.Event()
+            self._copy_done.record(stream_main)
+            self._recv_others()
+            self.main.route_resident_async(K)
+
+    def _recv_others(self):
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        ops = []
+        for r in range(1, self.world):
+            lo, hi = self.dec.slot_range(r)
+            if hi > lo:
+                ops.append(dist.P2POp(dist.irecv, self.imp_t[lo:hi], r))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
 
     def wait(self):
         if self.trib is not None:
