@@ -71,8 +71,8 @@ def load(rebuild_if_stale: bool = True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
-    if rebuild_if_stale and _build.stale():
+    path = os.environ.get("MR_LIB_PATH", _build.LIB)         # development: load an alternative build of the library
+    if path == _build.LIB and rebuild_if_stale and _build.stale():
         if os.path.exists("/usr/local/cuda/bin/nvcc") or os.environ.get("NVCC"):
             _build.build()
     if not os.path.exists(path):

@@ -325,7 +325,10 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
 
 // Tasks are dealt round-robin to the teams of a grid that is at most one resident wave (8 blocks per SM), so a
 // team works through several tasks and no block-scheduling cost is paid per task.
-__global__ void __launch_bounds__(32 * KWT_WARPS, 8) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
+#ifndef KWT_MIN_BLOCKS
+#define KWT_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
     __shared__ KwtScratchSmall S[KWT_TEAMS];
     const int team = threadIdx.x / MR_TEAM;
     const int stride = gridDim.x * KWT_TEAMS;
