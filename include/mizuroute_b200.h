@@ -128,6 +128,10 @@ int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
  * so a caller can keep several domains (tributaries of the next batch, mainstem of this one) in flight on
  * different streams.  mr_wait blocks until the stream is idle and reports a device-side error (ierr, message). */
 int mr_route_resident_async(mr_handle h, int nSteps, double T0, char *message);
+/* mr_step_batch as a software pipeline over consecutive calls: the forcing of this batch is uploaded on a copy stream
+ * (double-buffered), routed on the handle's stream, and its REACH_Q is downloaded on a second copy stream while the
+ * next batch is routed.  Host buffers must stay valid (pinned for real overlap) until mr_wait. */
+int mr_step_batch_async(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message);
 int mr_wait(mr_handle h, char *message);
 
 /* RCHFLX_out(:)%ROUTE(method)%<field> / %BASIN_* after the last step, caller's reach order. */

@@ -47,6 +47,12 @@ struct mr_handle_s {
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
     int kwtGridMax = 148 * 8;                    // one resident wave of k_route_kwt blocks
+    // software pipeline of mr_step_batch_async: copies on their own streams, forcing double-buffered
+    cudaStream_t copyIn = nullptr, copyOut = nullptr;
+    cudaEvent_t evIn[2] = {nullptr, nullptr}, evFree[2] = {nullptr, nullptr}, evOut = nullptr, evD2H = nullptr;
+    double *dRunoffSlot[2] = {nullptr, nullptr};
+    bool freeRec[2] = {false, false}, d2hRec = false;
+    int asyncSlot = 0;
     // multi-domain hand-off
     std::vector<int> ghostSegId, ghostKind; std::vector<double> ghostTotArea, ghostWidth;   // consumed by mr_set_network
     int nGhost = 0, nExport = 0;
@@ -308,6 +314,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     if (ierr) return fail(message, ierr, "mr_set_network/" + terr);
     const int N = nRch;
     h->segIdCopy.assign(segId, segId + nRch);
+    h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -496,6 +503,7 @@ int mr_wait(mr_handle h, char *message) {
     if (!h || !h->hasNet) return fail(message, 1, "mr_wait/handle has no network");
     CU(cudaSetDevice(h->opt.device));
     int e = check_device_error(h, where, message); if (e) return e;
+    if (h->copyOut) CU(cudaStreamSynchronize(h->copyOut));
     if (h->lastK > 0) {
         collect_timing(h);
         float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
@@ -544,6 +552,55 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->timing[0] = ms;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->timing[3] = ms;
     cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->timing[4] = ms;
+    put_msg(message, "");
+    return 0;
+}
+
+// mr_step_batch without host waits, as a three-stage software pipeline over consecutive calls:
+//   copy-in stream   H2D of this batch's forcing (double-buffered on the device)
+//   handle's stream  routing of this batch, then the re-ordering of REACH_Q into the caller's reach order
+//   copy-out stream  D2H of this batch's REACH_Q while the next batch is being routed
+// runoff / q_out must stay valid (and should be pinned) until mr_wait returns.  Results are those of mr_step_batch.
+int mr_step_batch_async(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message) {
+    const char *where = "mr_step_batch_async";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!runoff) return fail(message, 1, "mr_step_batch_async/null runoff");
+    if (!h->copyIn) {
+        CU(cudaStreamCreateWithFlags(&h->copyIn, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->copyOut, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&h->evIn[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->evFree[i], cudaEventDisableTiming)); }
+        CU(cudaEventCreateWithFlags(&h->evOut, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&h->evD2H, cudaEventDisableTiming));
+    }
+    if (!h->dRunoffSlot[1]) {
+        h->dRunoffSlot[0] = h->dRunoff;
+        e = dev_alloc(h, &h->dRunoffSlot[1], (size_t)h->opt.max_batch * (h->d.nHRU > 0 ? h->d.nHRU : 1), where, message, false); if (e) return e;
+    }
+    const int slot = h->asyncSlot; h->asyncSlot ^= 1;
+    if (h->freeRec[slot]) CU(cudaStreamWaitEvent(h->copyIn, h->evFree[slot], 0));          // the batch that used this slot has been routed
+    CU(cudaMemcpyAsync(h->dRunoffSlot[slot], runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->copyIn));
+    CU(cudaEventRecord(h->evIn[slot], h->copyIn));
+    CU(cudaStreamWaitEvent(h->stream, h->evIn[slot], 0));
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    h->d.runoff = h->dRunoffSlot[slot];
+    e = route_device(h, nSteps, T0, where, message);
+    h->d.runoff = h->dRunoff;
+    if (e) return e;
+    CU(cudaEventRecord(h->evFree[slot], h->stream)); h->freeRec[slot] = true;
+    if (q_out) {
+        const int N = h->d.nRch;
+        if (h->d2hRec) CU(cudaStreamWaitEvent(h->stream, h->evD2H, 0));                    // the staging buffer has been copied out
+        for (int r = 0; r < h->opt.n_routes; ++r) {
+            const int m = h->opt.route_methods[r];
+            dim3 grid((N + 255) / 256, nSteps < 64 ? nSteps : 64);
+            k_unpermute_rows<<<grid, 256, 0, h->stream>>>(h->d.qSer[m], h->dOut + (size_t)r * nSteps * N, h->dRch2pos, N, nSteps);
+            h->launchesLast++;
+        }
+        CU(cudaEventRecord(h->evOut, h->stream));
+        CU(cudaStreamWaitEvent(h->copyOut, h->evOut, 0));
+        CU(cudaMemcpyAsync(q_out, h->dOut, sizeof(double) * (size_t)h->opt.n_routes * nSteps * N, cudaMemcpyDeviceToHost, h->copyOut));
+        CU(cudaEventRecord(h->evD2H, h->copyOut)); h->d2hRec = true;
+    }
+    CU(cudaEventRecord(h->ev[5], h->stream));
     put_msg(message, "");
     return 0;
 }
@@ -957,6 +1014,8 @@ void mr_destroy(mr_handle h) {
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &m : h->mev) for (auto &e : m) if (e) cudaEventDestroy(e);
     for (auto &a : h->aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    for (cudaStream_t c : {h->copyIn, h->copyOut}) if (c) { cudaStreamSynchronize(c); cudaStreamDestroy(c); }
+    for (cudaEvent_t ev : {h->evIn[0], h->evIn[1], h->evFree[0], h->evFree[1], h->evOut, h->evD2H}) if (ev) cudaEventDestroy(ev);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);
     delete h;
 }

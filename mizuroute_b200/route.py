@@ -118,6 +118,16 @@ class Router:
         self._advance(K)
         return out if want_q else None
 
+    def route_batch_async(self, runoff, out=None):
+        """`route_batch` without host waits (mr_step_batch_async): upload, routing and download of consecutive calls
+        overlap.  `runoff` / `out` must be pinned host buffers that stay alive until `wait()`."""
+        K, rp = self._host_ptr(runoff, self.nHRU)
+        op = None
+        if out is not None:
+            _, op = self._host_ptr(out, self.nRch, rows=len(self.methods) * K)
+        self._check(self._L.mr_step_batch_async(self._h, K, self.TSEC[0], rp, op, self._msg))
+        self._advance(K)
+
     def upload_runoff(self, runoff):
         K, rp = self._host_ptr(runoff, self.nHRU)
         self._check(self._L.mr_upload_runoff(self._h, K, rp, self._msg))

@@ -138,6 +138,24 @@ def test_step_api_equals_batch_api():
     assert a.TSEC == b.TSEC
 
 
+def test_async_pipeline_equals_blocking_batches():
+    """mr_step_batch_async (upload / route / download overlapped over consecutive calls) returns what mr_step_batch does."""
+    import torch
+    from mizuroute_b200.route import Router
+    net, params, opts, ro = case("conus", n=3000, seed=6, dt=3600.0, route_opt="012", steps=30)
+    a = Router(net, params, opts, max_batch=10)
+    b = Router(net, params, opts, max_batch=10)
+    want = np.concatenate([a.route_batch(np.ascontiguousarray(ro[s:s + 10])) for s in (0, 10, 20)], axis=1)
+    ins = [torch.from_numpy(np.ascontiguousarray(ro[s:s + 10])).pin_memory() for s in (0, 10, 20)]
+    outs = [torch.empty((3, 10, net.nRch), dtype=torch.float64).pin_memory() for _ in range(3)]
+    for i in range(3):
+        b.route_batch_async(ins[i], outs[i])
+    b.wait()
+    got = np.concatenate([o.numpy() for o in outs], axis=1)
+    assert np.array_equal(got, want)
+    assert a.TSEC == b.TSEC
+
+
 def test_errors_surface_as_ierr_message():
     from mizuroute_b200.route import Router, RoutingError
     net, params, opts, ro = case("random", n=50, seed=1, dt=86400.0, route_opt="1", steps=2)
