@@ -47,6 +47,7 @@ struct DevNet {
     void *kwArena; unsigned long long *kwArenaMask;   // full-capacity KWT scratch: 64 slots per SM + their busy bits
     int *err;                       // [0] code (0 = ok) [1] position [2] site
     unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
+    unsigned long long *kwProf;     // optional [8][2] cycles / tasks per task class (development profile, nullptr = off)
 };
 
 // site ids for error messages (decoded in mr_lib.cu)

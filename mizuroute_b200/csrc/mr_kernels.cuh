@@ -302,7 +302,14 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
         return;
     }
     if (flags & FLAG_LAKE) { if (lane == 0) lake_reach<M_KWT>(d, p, t, tau0 + t); return; }
-    if (kwt_reach_team(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t]) != KWT_RETRY) return;
+    int nPre = 0;
+    const long long c0 = d.kwProf ? clock64() : 0;
+    const int rc = kwt_reach_team(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t], &nPre);
+    if (d.kwProf && lane == 0) {                       // classes: particles before thinning 0 (no area), <=3, <=6, <=12, <=20, <=40, >40, retry
+        const int cls = rc == KWT_RETRY ? 7 : (nPre == 0 ? 0 : nPre <= 3 ? 1 : nPre <= 6 ? 2 : nPre <= 12 ? 3 : nPre <= 20 ? 4 : nPre <= 40 ? 5 : 6);
+        atomicAdd(&d.kwProf[2 * cls], (unsigned long long)(clock64() - c0)); atomicAdd(&d.kwProf[2 * cls + 1], 1ull);
+    }
+    if (rc != KWT_RETRY) return;
     // wide confluence: claim a full-capacity scratch of this SM
     unsigned sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));

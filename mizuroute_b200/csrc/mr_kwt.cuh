@@ -15,6 +15,7 @@
 //
 // HBM layout of the wave state (per buffer b, see kwt_reach_team): kwQF/kwTI/kwTR[b][p*KWP + k], kwN/kwNR[b][p].
 #pragma once
+#include <cstring>
 #include "mr_dev.h"
 
 namespace mr {
@@ -99,7 +100,18 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
 }
 
 // one out-of-line copy of pow(): its inlined body is ~250 instructions per call site
+#if defined(MR_TEST_POW_NOISE) && !defined(__CUDACC__)
+// Host test builds only (tests/test_kwt_conditioning.py): pow() perturbed by -1/0/+1 ulp, pseudo-randomly, to measure how
+// a case reacts to the last-ulp differences between two correct pow() implementations (libm vs the device).
+inline double mr_pow(double x, double y) {
+    const double r = pow(x, y);
+    unsigned long long u; memcpy(&u, &x, 8);
+    u = (u * 0x9E3779B97F4A7C15ull + (unsigned long long)(MR_TEST_POW_NOISE)) >> 61;
+    return u < 3 ? nextafter(r, 1e300) : (u < 6 ? nextafter(r, -1e300) : r);
+}
+#else
 MR_DEV_NOINLINE double mr_pow(double x, double y) { return pow(x, y); }
+#endif
 
 MR_DEV_NOINLINE double thin_err(const double *Q, const double *T, int a, int m, int b) {
     // |INTERP(T(m), Q(a), Q(b), T(a), T(b)) - Q(m)|, kwt_route.f90:1054,1062,1114-1121
@@ -509,7 +521,7 @@ MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0
 // behind, reading the same buffer) sees the unstripped array.
 // ------------------------------------------------------------------------------------------------
 template <class SC>
-MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1) {
+MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1, int *nPre = nullptr) {
     const int lane = MR_LANE;
     const int N = d.nRch;
     const int b = (int)(tau & 1), bp = b ^ 1;
@@ -565,6 +577,7 @@ MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, d
     }
     MR_SYNC();
     int n = nOwn + ND;
+    if (nPre) *nPre = n;
     bool neg = false;
     MR_NOUNROLL
     for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;

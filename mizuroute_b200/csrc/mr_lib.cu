@@ -401,6 +401,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         KwtScratch *arena = nullptr; unsigned long long *amask = nullptr;
         AL(arena, (size_t)KWT_ARENA_SMS * KWT_ARENA_SLOTS); AL(amask, KWT_ARENA_SMS);
         d.kwArena = arena; d.kwArenaMask = amask;
+        if (std::getenv("MR_KWT_PROFILE")) { unsigned long long *pr = nullptr; AL(pr, 16); d.kwProf = pr; }
         for (int b = 0; b < 2; ++b) {
             AL(d.kwN[b], N); AL(d.kwNR[b], N);
             AL(d.kwQF[b], (size_t)KWP * N); AL(d.kwTI[b], (size_t)KWP * N); AL(d.kwTR[b], (size_t)KWP * N);
@@ -1010,6 +1011,15 @@ void mr_destroy(mr_handle h) {
     if (!h) return;
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->hasNet && h->d.kwProf) {                  // MR_KWT_PROFILE=1: cycles per task class (development)
+        unsigned long long pr[16];
+        if (cudaMemcpy(pr, h->d.kwProf, sizeof(pr), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char *nm[8] = {"n=0", "n<=3", "n<=6", "n<=12", "n<=20", "n<=40", "n>40", "retry"};
+            double tot = 0; for (int c = 0; c < 8; ++c) tot += (double)pr[2 * c];
+            for (int c = 0; c < 8; ++c) if (pr[2 * c + 1])
+                std::fprintf(stderr, "kwt tasks %-6s count %12llu  share of cycles %5.1f%%  cycles/task %9.0f\n", nm[c], pr[2 * c + 1], 100.0 * pr[2 * c] / tot, (double)pr[2 * c] / pr[2 * c + 1]);
+        }
+    }
     free_device(h);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &m : h->mev) for (auto &e : m) if (e) cudaEventDestroy(e);

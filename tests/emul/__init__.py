@@ -10,6 +10,15 @@ _CSRC = os.path.join(_HERE, "..", "..", "mizuroute_b200", "csrc")
 _DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("mr_kwt.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
 
 
+def load_noisy(seed: int = 1):
+    """The same build with pow() perturbed by at most one ulp (MR_TEST_POW_NOISE, see mr_kwt.cuh)."""
+    so = os.path.join(_HERE, "libkwt_emul_noise%d.so" % seed)
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in _DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-DMR_TEST_POW_NOISE=%d" % (7919 * seed + 1),
+                               "-x", "c++", "-shared", "-fPIC", "-o", so, _SRC])
+    return C.CDLL(so)
+
+
 def load():
     if not os.path.exists(_SO) or any(os.path.getmtime(f) > os.path.getmtime(_SO) for f in _DEPS):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC",
