@@ -64,8 +64,11 @@ def _stamp(seconds: float, start: str) -> str:
 
 
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
-               start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None) -> str:
-    """Creates <case_dir>/{ancillary,input,output} and returns the control-file path."""
+               start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
+               fname_state_in: str = "coldstart", first_step: int = 0) -> str:
+    """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
+    continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`."""
+    t_first = _stamp(first_step * opts.dt, start)
     anc, inp, out = (os.path.join(case_dir, d) + "/" for d in ("ancillary", "input", "output"))
     for d in (anc, inp, out):
         os.makedirs(d, exist_ok=True)
@@ -79,14 +82,14 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ids, ro = ids[perm], runoff[:, perm]
     K = runoff.shape[0]
     if split_forcing <= 1:
-        write_runoff(inp + "runoff.nc", ids, ro, opts.dt, start)
-        fname_qsim = "runoff.nc"
+        write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, opts.dt, start, t_offset_steps=first_step)
+        fname_qsim = "runoff_%s.nc" % case_name
     else:
         bounds = np.linspace(0, K, split_forcing + 1).astype(int)
         names = []
         for i in range(split_forcing):
             nm = "runoff_%02d.nc" % i
-            write_runoff(inp + nm, ids, ro[bounds[i]:bounds[i + 1]], opts.dt, start, t_offset_steps=int(bounds[i]))
+            write_runoff(inp + nm, ids, ro[bounds[i]:bounds[i + 1]], opts.dt, start, t_offset_steps=first_step + int(bounds[i]))
             names.append(nm)
         with open(inp + "runoff_files.txt", "w") as f:
             f.write("! forcing files in chronological order\n" + "\n".join(names) + "\n")
@@ -96,8 +99,8 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("ancil_dir", anc, "directory containing ancillary data"),
         ("input_dir", inp, "directory containing input data"),
         ("output_dir", out, "directory containing output data"),
-        ("sim_start", start, "time of simulation start"),
-        ("sim_end", _stamp((K - 1) * opts.dt, start), "time of simulation end"),
+        ("sim_start", t_first, "time of simulation start"),
+        ("sim_end", _stamp((first_step + K - 1) * opts.dt, start), "time of simulation end"),
         ("route_opt", opts.route_opt, "routing schemes"),
         ("doesBasinRoute", opts.doesBasinRoute, "hillslope routing"),
         ("dt_qsim", int(opts.dt), "simulation time interval [sec]"),
@@ -120,7 +123,8 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("dt_ro", int(opts.dt), "forcing interval [sec]"),
         ("is_remap", "F", "runoff HRUs are the river-network HRUs"),
         ("param_nml", "param.nml", "spatially constant parameters"),
-        ("restart_write", "never", "restart write option"),
+        ("restart_write", restart_write, "restart write option"),
+        ("fname_state_in", fname_state_in, "input restart netCDF ('coldstart' = none)"),
         ("newFileFrequency", "single", "history file frequency"),
         ("outputFrequency", 1, "output every step"),
     ]

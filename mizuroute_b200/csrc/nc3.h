@@ -153,6 +153,11 @@ public:
         for (uint64_t i = 0; i < v.count; ++i) { const uint32_t u = (uint32_t)data[i]; b[4 * i] = u >> 24; b[4 * i + 1] = u >> 16; b[4 * i + 2] = u >> 8; b[4 * i + 3] = u; }
         seek(v.begin); wr(b.data(), b.size());
     }
+    void put_double(int id, const double *data) {
+        const WVar &v = vars_[id]; std::vector<unsigned char> b(v.vsize, 0);
+        for (uint64_t i = 0; i < v.count; ++i) { uint64_t u; std::memcpy(&u, &data[i], 8); for (int k = 0; k < 8; ++k) b[8 * i + k] = (unsigned char)(u >> (56 - 8 * k)); }
+        seek(v.begin); wr(b.data(), b.size());
+    }
     // one record of a float (converted from double) or double record variable
     void put_record(int id, uint64_t rec, const double *data) {
         const WVar &v = vars_[id]; std::vector<unsigned char> b(v.count * type_size(v.type));

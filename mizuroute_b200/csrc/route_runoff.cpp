@@ -152,6 +152,104 @@ std::string join_path(const std::string &dir, const std::string &f) { return (!f
 
 struct Forcing { std::string path; size_t nTime = 0; std::vector<double> tsec; };     // record times, seconds since 1970
 
+// ---- restart files in the reference's schema (write_restart_pio.f90:544,983-1134; read_restart.f90:402-470) ---------
+// Fortran dimensions (seg, tdh|wave) are (tdh|wave, seg) in file order.  wave = MR_KW_SLOTS because a reach can hold
+// MAXQPAR+1 waves between steps.
+void check(int ierr, const char *msg) { if (ierr) die(ierr, msg); }
+
+void write_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, double T0, long steps) {
+    char msg[MR_STRLEN];
+    const size_t N = segId.size();
+    const int nb = (int)mr_get_info(h, MR_INFO_NTDH_BAS), mx = (int)mr_get_info(h, MR_INFO_MAXTDH), W = MR_KW_SLOTS;
+    bool irf = false, kwt = false;
+    for (int r = 0; r < o.n_routes; ++r) { irf |= o.route_methods[r] == MR_IMPULSE_RESPONSE_FUNC; kwt |= o.route_methods[r] == MR_KINEMATIC_WAVE_TRACKING; }
+    nc3::Writer w(path);
+    const int dSeg = w.def_dim("seg", N), dTdh = w.def_dim("tdh", nb), dIrf = w.def_dim("tdh_irf", mx), dWave = w.def_dim("wave", W), dTb = w.def_dim("tbound", 2);
+    const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}), vTb = w.def_var("time_bound", nc3::NC_DOUBLE, {dTb}, {{"units", "s"}, {"long_name", "TSEC(1:2) of the next step; tbound 0 / dt_qsim = steps done"}});
+    const int vBq = w.def_var("basin_q", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3/s"}}), vQf = w.def_var("qfuture", nc3::NC_DOUBLE, {dTdh, dSeg}, {{"units", "m3/s"}});
+    int vNqf = -1, vIq = -1, vIv = -1, vNw = -1, vTe = -1, vTx = -1, vQw = -1, vQm = -1, vRt = -1, vKv = -1;
+    if (irf) { vNqf = w.def_var("numQF", nc3::NC_INT, {dSeg}); vIq = w.def_var("irf_qfuture", nc3::NC_DOUBLE, {dIrf, dSeg}, {{"units", "m3/s"}}); vIv = w.def_var("volume_irf", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}}); }
+    if (kwt) { vNw = w.def_var("numWaves", nc3::NC_INT, {dSeg}); vTe = w.def_var("tentry", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "s"}}); vTx = w.def_var("texit", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "s"}});
+               vQw = w.def_var("qwave", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "m2/s"}}); vQm = w.def_var("qwave_mod", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "m2/s"}});
+               vRt = w.def_var("routed", nc3::NC_INT, {dWave, dSeg}); vKv = w.def_var("volume_kwt", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}}); }
+    w.end_def();
+    w.put_int(vId, segId.data());
+    const double tb[2] = {T0, T0 + o.dt}; w.put_double(vTb, tb); (void)steps;
+    auto transposed = [&](const std::vector<double> &a, int ncol) { std::vector<double> t(a.size()); for (size_t r = 0; r < N; ++r) for (int k = 0; k < ncol; ++k) t[(size_t)k * N + r] = a[r * ncol + k]; return t; };
+    std::vector<double> a((size_t)N * std::max(std::max(nb, mx), W)), b(N);
+    a.resize((size_t)N * 2); check(mr_get_state(h, MR_ST_BASIN_QR, a.data(), (long)a.size() * 8, msg), msg);
+    for (size_t r = 0; r < N; ++r) b[r] = a[2 * r + 1];
+    w.put_double(vBq, b.data());
+    a.resize((size_t)N * nb); check(mr_get_state(h, MR_ST_BASIN_QFUTURE, a.data(), (long)a.size() * 8, msg), msg); w.put_double(vQf, transposed(a, nb).data());
+    std::vector<double> lv((size_t)o.n_routes * N); check(mr_get_state(h, MR_ST_LAKE_VOL, lv.data(), (long)lv.size() * 8, msg), msg);
+    if (irf) {
+        std::vector<int> nt(N); std::vector<double> uh((size_t)N * mx);
+        check(mr_get_reach_uh(h, nt.data(), uh.data(), msg), msg);
+        w.put_int(vNqf, nt.data());
+        a.resize((size_t)N * mx); check(mr_get_state(h, MR_ST_IRF_QFUTURE, a.data(), (long)a.size() * 8, msg), msg);
+        for (size_t r = 0; r < N; ++r) for (int k = nt[r]; k < mx; ++k) a[r * mx + k] = -9999.0;          // realMissing beyond numQF (:1009)
+        w.put_double(vIq, transposed(a, mx).data());
+        for (int q = 0; q < o.n_routes; ++q) if (o.route_methods[q] == MR_IMPULSE_RESPONSE_FUNC) w.put_double(vIv, &lv[(size_t)q * N]);
+    }
+    if (kwt) {
+        std::vector<int> nw(N), rt((size_t)N * W), rtT((size_t)N * W);
+        check(mr_get_state(h, MR_ST_KWT_NWAVE, nw.data(), (long)N * 4, msg), msg); w.put_int(vNw, nw.data());
+        check(mr_get_state(h, MR_ST_KWT_ROUTED, rt.data(), (long)rt.size() * 4, msg), msg);
+        for (size_t r = 0; r < N; ++r) for (int k = 0; k < W; ++k) rtT[(size_t)k * N + r] = k < nw[r] ? rt[r * W + k] : -9999;
+        w.put_int(vRt, rtT.data());
+        a.resize((size_t)N * W);
+        check(mr_get_state(h, MR_ST_KWT_TENTRY, a.data(), (long)a.size() * 8, msg), msg); w.put_double(vTe, transposed(a, W).data());
+        check(mr_get_state(h, MR_ST_KWT_TEXIT, a.data(), (long)a.size() * 8, msg), msg); w.put_double(vTx, transposed(a, W).data());
+        check(mr_get_state(h, MR_ST_KWT_QWAVE, a.data(), (long)a.size() * 8, msg), msg); w.put_double(vQw, transposed(a, W).data());
+        std::fill(a.begin(), a.end(), -9999.0); w.put_double(vQm, a.data());                                  // QM is a dead field (always realMissing)
+        for (int q = 0; q < o.n_routes; ++q) if (o.route_methods[q] == MR_KINEMATIC_WAVE_TRACKING) w.put_double(vKv, &lv[(size_t)q * N]);
+    }
+    w.close();
+}
+
+// returns TSEC(1) of the next step
+double read_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId) {
+    char msg[MR_STRLEN];
+    const size_t N = segId.size();
+    nc3::Reader r(path);
+    std::vector<int> id; r.read_int(r.var("reachID"), id);
+    if (id != segId) die(20, "read_state_nc/reach ids of the restart file differ from the river network");
+    const int nb = (int)mr_get_info(h, MR_INFO_NTDH_BAS), mx = (int)mr_get_info(h, MR_INFO_MAXTDH), W = MR_KW_SLOTS;
+    if ((int)r.dim_len("tdh") != nb) die(20, "read_state_nc/tdh of the restart file differs from the hillslope UH length");
+    std::vector<double> tb; r.read_all(r.var("time_bound"), tb);
+    const long steps = std::lround(tb[0] / o.dt);
+    check(mr_set_steps_done(h, steps, msg), msg);
+    auto rowmajor = [&](const std::vector<double> &t, int ncol) { std::vector<double> a(t.size()); for (size_t q = 0; q < N; ++q) for (int k = 0; k < ncol; ++k) a[q * ncol + k] = t[(size_t)k * N + q]; return a; };
+    std::vector<double> t, a;
+    r.read_all(r.var("basin_q"), t); a.assign(2 * N, 0.0); for (size_t q = 0; q < N; ++q) a[2 * q + 1] = t[q];
+    check(mr_set_state(h, MR_ST_BASIN_QR, a.data(), (long)a.size() * 8, msg), msg);
+    r.read_all(r.var("qfuture"), t); a = rowmajor(t, nb); check(mr_set_state(h, MR_ST_BASIN_QFUTURE, a.data(), (long)a.size() * 8, msg), msg);
+    std::vector<double> lv((size_t)o.n_routes * N, 0.0);
+    for (int q = 0; q < o.n_routes; ++q) {
+        if (o.route_methods[q] == MR_IMPULSE_RESPONSE_FUNC) {
+            if ((int)r.dim_len("tdh_irf") != mx) die(20, "read_state_nc/tdh_irf of the restart file differs from the reach UH length");
+            r.read_all(r.var("irf_qfuture"), t); a = rowmajor(t, mx);
+            for (auto &v : a) if (v == -9999.0) v = 0.0;
+            check(mr_set_state(h, MR_ST_IRF_QFUTURE, a.data(), (long)a.size() * 8, msg), msg);
+            r.read_all(r.var("volume_irf"), t); std::copy(t.begin(), t.end(), lv.begin() + (size_t)q * N);
+            check(mr_set_state(h, MR_ST_IRF_VOL, t.data(), (long)N * 8, msg), msg);
+        } else if (o.route_methods[q] == MR_KINEMATIC_WAVE_TRACKING) {
+            if ((int)r.dim_len("wave") != W) die(20, "read_state_nc/wave dimension of the restart file is not MR_KW_SLOTS");
+            std::vector<int> nw, rt; r.read_int(r.var("numWaves"), nw); r.read_int(r.var("routed"), rt);
+            std::vector<int> rr((size_t)N * W);
+            for (size_t s = 0; s < N; ++s) for (int k = 0; k < W; ++k) rr[s * W + k] = (k < nw[s] && rt[(size_t)k * N + s] == 1) ? 1 : 0;
+            check(mr_set_state(h, MR_ST_KWT_NWAVE, nw.data(), (long)N * 4, msg), msg);
+            check(mr_set_state(h, MR_ST_KWT_ROUTED, rr.data(), (long)rr.size() * 4, msg), msg);
+            r.read_all(r.var("tentry"), t); a = rowmajor(t, W); check(mr_set_state(h, MR_ST_KWT_TENTRY, a.data(), (long)a.size() * 8, msg), msg);
+            r.read_all(r.var("texit"), t); a = rowmajor(t, W); check(mr_set_state(h, MR_ST_KWT_TEXIT, a.data(), (long)a.size() * 8, msg), msg);
+            r.read_all(r.var("qwave"), t); a = rowmajor(t, W); check(mr_set_state(h, MR_ST_KWT_QWAVE, a.data(), (long)a.size() * 8, msg), msg);
+            r.read_all(r.var("volume_kwt"), t); std::copy(t.begin(), t.end(), lv.begin() + (size_t)q * N);
+        }
+    }
+    check(mr_set_state(h, MR_ST_LAKE_VOL, lv.data(), (long)lv.size() * 8, msg), msg);
+    return tb[0];
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -300,6 +398,10 @@ int main(int argc, char **argv) {
         std::vector<double> ro((size_t)batch * nHRU), q((size_t)o.n_routes * batch * nRch), rec;
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
+        const std::string stateIn = c.str("fname_state_in", "coldstart");
+        if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
+            T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
+        const double Tfirst = T0;
         double fillv = c.num("input_fillvalue", -9999.0);
         for (size_t s = 0; s < nSteps; s += batch) {
             const int nb = (int)std::min<size_t>(batch, nSteps - s);
@@ -317,7 +419,7 @@ int main(int argc, char **argv) {
             }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             for (int k = 0; k < nb; ++k) {
-                const double tsec = (double)(s + k) * o.dt;
+                const double tsec = (Tfirst - std::floor(Tfirst / o.dt + 0.5) * o.dt) + (double)(s + k) * o.dt;      // seconds since <sim_start>
                 w.put_record(vTime, s + k, &tsec);
                 for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);
             }
@@ -325,6 +427,20 @@ int main(int argc, char **argv) {
         }
         for (auto *p : rd) delete p;
         w.close();
+        const std::string rw = lower(c.str("restart_write", "never"));
+        if (rw == "last") {                                                     // main_restart, route_runoff.f90:102
+            const double tEndNext = tStart + (double)nSteps * o.dt;
+            long long days = (long long)std::floor(tEndNext / 86400.0); const int sod = (int)std::llround(tEndNext - (double)days * 86400.0);
+            // civil date of `days` since 1970-01-01 (proleptic Gregorian; noleap: 365-day years)
+            int y, mo, d;
+            if (noleap) { y = 1970 + (int)(days / 365); int doy = (int)(days % 365); static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31}; mo = 0; while (doy >= ml[mo]) doy -= ml[mo++]; d = doy + 1; mo += 1; }
+            else { long long z = days + 719468; const long long era = (z >= 0 ? z : z - 146096) / 146097; const unsigned doe = (unsigned)(z - era * 146097), yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+                   const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153; d = (int)(doy - (153 * mp + 2) / 5 + 1); mo = (int)(mp < 10 ? mp + 3 : mp - 9); y = (int)(yoe + era * 400 + (mo <= 2)); }
+            char rs[64]; std::snprintf(rs, sizeof rs, "%04d-%02d-%02d-%05d", y, mo, d, sod);
+            const std::string rpath = join_path(c.str("restart_dir", outdir), c.str("case_name", "case") + ".r." + rs + ".nc");
+            write_restart(h, rpath, o, segId, T0, (long)std::lround(T0 / o.dt));
+            std::printf("{\"restart\": \"%s\"}\n", rpath.c_str());
+        } else if (rw != "never") die(20, "route_runoff/<restart_write> " + rw + ": only 'never' and 'last' are supported by this host");
         mr_destroy(h);
         std::printf("{\"history\": \"%s\", \"steps\": %zu}\n", opath.c_str(), nSteps);
     } catch (const std::exception &e) {

@@ -73,3 +73,28 @@ def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
         got = out[names[c]]
         assert got.dtype == np.float32 and got.shape == (40, net.nRch)       # history is float32 [time, seg]
         np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c != "2" else 1e-4, atol=1e-30)
+
+
+@pytest.mark.gpu
+def test_exact_restart(tmp_path):
+    """ERS, the reference's main regression idea (cime_config/testdefs/testlist_mizuRoute.xml): 40 steps in one run ==
+    20 steps + restart file (reference schema: qfuture, irf_qfuture, numWaves, tentry/texit/qwave/routed, ...) + 20 steps."""
+    net, params, opts, ro = case("conus", n=500, seed=9, dt=3600.0, route_opt="012", steps=40, lakes=4)
+    d = str(tmp_path)
+    full = casefiles.write_case(d, net, params, opts, ro, case_name="full")
+    first = casefiles.write_case(d, net, params, opts, ro[:20], case_name="first", restart_write="last")
+    run = lambda ctl: subprocess.run([_host(), ctl, "--batch", "7"], capture_output=True, text=True)
+    r = run(full); assert r.returncode == 0, r.stderr
+    h_full = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    r = run(first); assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    h_first = casefiles.read_history(next(x["history"] for x in lines if "history" in x))
+    rfile = next(x["restart"] for x in lines if "restart" in x)
+    rst = casefiles.read_history(rfile)
+    assert {"reachID", "basin_q", "qfuture", "numQF", "irf_qfuture", "volume_irf", "numWaves", "tentry", "texit", "qwave", "routed"} <= set(rst)
+    assert rst["tentry"].shape == (22, net.nRch) and rst["qfuture"].shape[1] == net.nRch          # Fortran (seg, wave) = file (wave, seg)
+    second = casefiles.write_case(d, net, params, opts, ro[20:], case_name="second", fname_state_in=os.path.basename(rfile), first_step=20)
+    r = run(second); assert r.returncode == 0, r.stderr
+    h_second = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    for v in ("sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"):
+        assert np.array_equal(np.concatenate([h_first[v], h_second[v]]), h_full[v]), v
