@@ -70,7 +70,8 @@ enum {
     MR_INFO_STEPS_DONE = 6,      /* iTime-1 (globalData iTime) */
     MR_INFO_MAX_BATCH = 7, MR_INFO_MAX_NUPS = 8, MR_INFO_KWT_PARTICLES = 9, /* live particles in the KWT state */
     MR_INFO_DEVICE_BYTES = 10,   /* bytes of HBM held by the handle (KiB) */
-    MR_INFO_KWT_TOUCHED = 11, MR_INFO_NHEAD = 12, MR_INFO_SUM_NTDH = 13, MR_INFO_SUM_NUPS = 14
+    MR_INFO_KWT_TOUCHED = 11, MR_INFO_NHEAD = 12, MR_INFO_SUM_NTDH = 13, MR_INFO_SUM_NUPS = 14,
+    MR_INFO_NFORCING = 15        /* columns of the runoff arrays the step calls expect (nHRU, or the forcing polygons of mr_set_remap) */
 };
 
 typedef struct mr_handle_s *mr_handle;
@@ -110,6 +111,15 @@ int mr_set_network(mr_handle h, int nRch, int nHRU,
                    const double *D03_MaxStorage, const double *D03_Coefficient,
                    const double *D03_Power, const double *D03_S0,
                    char *message);
+
+/* Optional: runoff arrives on other polygons than the river-network HRUs (<is_remap> T).  Replaces remap_1D_runoff
+ * (process_remap.f90:164-262, called from get_hru_runoff, get_basin_runoff.f90:91-93) ON THE DEVICE: after this call
+ * every runoff array passed to mr_step / mr_step_batch* / mr_upload_runoff is [nSteps][nForcing].
+ *   mapHruIndex[nMap]  network-HRU index (0-based, caller's HRU order) of each mapping-layer HRU, -1 = not in the network
+ *   numQhru[nMap]      overlapping forcing polygons per mapping HRU (ragged rows of the next two arrays, file order)
+ *   qhruIndex[sum]     index of the polygon in the forcing vector, -1 = polygon without forcing
+ *   weight[sum]        areal weights */
+int mr_set_remap(mr_handle h, int nForcing, int nMap, const int *mapHruIndex, const int *numQhru, const int *qhruIndex, const double *weight, char *message);
 
 /* Replaces one main_route call (main_route.f90:29-268) for the time step [T0,T1] = TSEC(1:2). */
 int mr_step(mr_handle h, double T0, double T1, const double *basinRunoff /* [nHRU] */, char *message);

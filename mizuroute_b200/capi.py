@@ -25,12 +25,13 @@ KW_PITCH = 24            # particle-row pitch of an exchange record
 (INFO_NRCH, INFO_NHRU, INFO_NSTAGE, INFO_NTDH_BAS, INFO_MAXTDH, INFO_LAUNCHES_LAST, INFO_STEPS_DONE,
  INFO_MAX_BATCH, INFO_MAX_NUPS, INFO_KWT_PARTICLES, INFO_DEVICE_BYTES, INFO_KWT_TOUCHED, INFO_NHEAD, INFO_SUM_NTDH,
  INFO_SUM_NUPS) = range(15)
+INFO_NFORCING = 15
 
 EXPORTS = [
     "mr_create", "mr_set_network", "mr_step", "mr_step_batch", "mr_upload_runoff", "mr_route_resident",
     "mr_download_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
-    "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
+    "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_remap", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
 ]
 
 
@@ -100,6 +101,7 @@ def load(rebuild_if_stale: bool = True):
     L.mr_get_timing.argtypes = [vp, dp]
     L.mr_set_stream.argtypes = [vp, vp, cp]
     L.mr_set_counting.argtypes = [vp, C.c_int, cp]
+    L.mr_set_remap.argtypes = [vp, C.c_int, C.c_int, ip, ip, ip, dp, cp]
     L.mr_set_ghosts.argtypes = [vp, C.c_int, ip, ip, dp, dp, cp]
     L.mr_set_export.argtypes = [vp, C.c_int, ip, cp]
     L.mr_exchange_bytes.argtypes = [vp, C.c_int]

@@ -65,7 +65,7 @@ def _stamp(seconds: float, start: str) -> str:
 
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
-               fname_state_in: str = "coldstart", first_step: int = 0) -> str:
+               fname_state_in: str = "coldstart", first_step: int = 0, remap=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
     continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`."""
     t_first = _stamp(first_step * opts.dt, start)
@@ -77,7 +77,14 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         f.write("&HSLOPE\n  ! hillslope gamma UH\n  fshape = %r\n  tscale = %r\n/\n&IRF_UH\n  velo = %r\n  diff = %r\n/\n&KWT\n  mann_n = %r\n  wscale = %r\n/\n"
                 % (params.fshape, params.tscale, params.velo, params.diff, params.mann_n, params.wscale))
     ids, ro = net.hruId, runoff
-    if shuffle_hru_seed is not None:                       # forcing HRUs in a different order than the network's
+    if remap is not None:                                   # (map_ids, num_qhru, qhru_ids, weight, forcing_ids): runoff is on forcing polygons
+        map_ids, num_q, q_ids, wgt, ids = remap
+        f = netcdf_file(anc + "remap.nc", "w", version=2)
+        f.createDimension("hru", len(map_ids)); f.createDimension("data", len(q_ids))
+        for nm, dat, dim, typ in (("RN_hruId", map_ids, "hru", "i"), ("nOverlaps", num_q, "hru", "i"), ("overlapPolyId", q_ids, "data", "i"), ("weight", wgt, "data", "d")):
+            v = f.createVariable(nm, typ, (dim,)); v[:] = dat
+        f.close()
+    elif shuffle_hru_seed is not None:                       # forcing HRUs in a different order than the network's
         perm = np.random.default_rng(shuffle_hru_seed).permutation(net.nHRU)
         ids, ro = ids[perm], runoff[:, perm]
     K = runoff.shape[0]
@@ -121,7 +128,14 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("dname_hruid", "hru", "HRU dimension"),
         ("units_qsim", opts.units_qsim, "units of runoff"),
         ("dt_ro", int(opts.dt), "forcing interval [sec]"),
-        ("is_remap", "F", "runoff HRUs are the river-network HRUs"),
+        ("is_remap", "T" if remap is not None else "F", "runoff remapping"),
+        ("fname_remap", "remap.nc", "runoff mapping netCDF"),
+        ("vname_hruid_in_remap", "RN_hruId", "river-network HRU ids in the mapping"),
+        ("vname_weight", "weight", "areal weights"),
+        ("vname_qhruid", "overlapPolyId", "forcing polygon ids"),
+        ("vname_num_qhru", "nOverlaps", "overlapping polygons per river-network HRU"),
+        ("dname_hru_remap", "hru", "mapping HRU dimension"),
+        ("dname_data_remap", "data", "mapping data dimension"),
         ("param_nml", "param.nml", "spatially constant parameters"),
         ("restart_write", restart_write, "restart write option"),
         ("fname_state_in", fname_state_in, "input restart netCDF ('coldstart' = none)"),

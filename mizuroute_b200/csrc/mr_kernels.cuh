@@ -130,6 +130,32 @@ __global__ void __launch_bounds__(BASIN_TPB) k_basin(DevNet d, int K, long long 
     if (live) d.basinQI[p] = rr;
 }
 
+// remap_1D_runoff (process_remap.f90:164-262): runoff on the forcing polygons -> river-network HRUs.  One thread per
+// (mapping HRU, step): weighted sum over its overlapping polygons in file order, polygons without forcing skipped, values
+// <= -1e-6 skipped, renormalised when the weights used do not sum to one.  Network HRUs absent from the mapping keep 0
+// (get_basin_runoff.f90:73).
+__global__ void k_remap(const double *forcing, double *out, const int *mapNet, const int *mapPtr, const int *ovIdx, const double *ovW,
+                        int nMap, int nForcing, int nHRU, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nMap) return;
+    const int j = mapNet[i];
+    if (j < 0) return;
+    const int a = mapPtr[i], b = mapPtr[i + 1];
+    const double xTol = 1.e-6;
+    for (int t = blockIdx.y; t < K; t += gridDim.y) {
+        const double *f = forcing + (size_t)t * nForcing;
+        double sumW = 0.0, r = 0.0;
+        for (int m = a; m < b; ++m) {
+            const int q = ovIdx[m];
+            if (q < 0) continue;
+            const double v = f[q];
+            if (v > -xTol) { sumW = sumW + ovW[m]; r = r + ovW[m] * v; }
+        }
+        if (sumW > xTol) { if (fabs(1.0 - sumW) > xTol) r = r / sumW; }
+        out[(size_t)t * nHRU + j] = r;
+    }
+}
+
 // carry BASIN_QR(1) of the previous batch into row 0 of the series
 __global__ void k_carry_qr(double *qrSer, int N, int Kprev) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,6 +47,10 @@ struct mr_handle_s {
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
     int kwtGridMax = 148 * 8;                    // one resident wave of k_route_kwt blocks
+    // runoff remapping (mr_set_remap): forcing arrives on nForcing polygons, k_remap fills dRunoffNet [max_batch][nHRU]
+    int nForcing = 0, nMap = 0;
+    double *dRunoffNet = nullptr, *dOvW = nullptr;
+    int *dMapNet = nullptr, *dMapPtr = nullptr, *dOvIdx = nullptr;
     // software pipeline of mr_step_batch_async: copies on their own streams, forcing double-buffered
     cudaStream_t copyIn = nullptr, copyOut = nullptr;
     cudaEvent_t evIn[2] = {nullptr, nullptr}, evFree[2] = {nullptr, nullptr}, evOut = nullptr, evD2H = nullptr;
@@ -98,6 +102,20 @@ int dev_upload_const(mr_handle h, const T *&field, const std::vector<T> &v, cons
     int e = dev_upload(h, &tmp, v, where, message);
     field = tmp;
     return e;
+}
+
+// columns of the caller's runoff array: forcing polygons when a remapping is set, network HRUs otherwise
+size_t in_cols(mr_handle h) { return h->nForcing > 0 ? (size_t)h->nForcing : (size_t)h->d.nHRU; }
+
+// after the upload of nSteps rows into `src`: remap to network HRUs if asked, and point the kernels at the result
+void stage_runoff(mr_handle h, double *src, int nSteps, cudaStream_t st) {
+    if (h->nForcing > 0) {
+        dim3 grid((h->nMap + 127) / 128, nSteps < 64 ? nSteps : 64);
+        k_remap<<<grid, 128, 0, st>>>(src, h->dRunoffNet, h->dMapNet, h->dMapPtr, h->dOvIdx, h->dOvW, h->nMap, h->nForcing, h->d.nHRU, nSteps);
+        h->d.runoff = h->dRunoffNet;
+    } else {
+        h->d.runoff = src;
+    }
 }
 
 const char *site_text(int site) {
@@ -314,6 +332,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     if (ierr) return fail(message, ierr, "mr_set_network/" + terr);
     const int N = nRch;
     h->segIdCopy.assign(segId, segId + nRch);
+    h->nForcing = h->nMap = 0; h->dRunoffNet = nullptr; h->dOvW = nullptr; h->dMapNet = h->dMapPtr = h->dOvIdx = nullptr;
     h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
@@ -468,7 +487,8 @@ int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *messag
     const char *where = "mr_upload_runoff";
     int e = check_ready(h, nSteps, where, message); if (e) return e;
     if (!runoff) return fail(message, 1, "mr_upload_runoff/null runoff");
-    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->stream));
+    stage_runoff(h, h->dRunoff, nSteps, h->stream);
     CU(cudaStreamSynchronize(h->stream));
     put_msg(message, "");
     return 0;
@@ -542,7 +562,8 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     int e = check_ready(h, nSteps, where, message); if (e) return e;
     if (!runoff) return fail(message, 1, "mr_step_batch/null runoff");
     CU(cudaEventRecord(h->ev[0], h->stream));
-    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->stream));
+    stage_runoff(h, h->dRunoff, nSteps, h->stream);
     e = route_device(h, nSteps, T0, where, message); if (e) return e;
     CU(cudaEventRecord(h->ev[4], h->stream));
     if (q_out) { e = download_q(h, nSteps, q_out, where, message); if (e) return e; }
@@ -574,17 +595,16 @@ int mr_step_batch_async(mr_handle h, int nSteps, double T0, const double *runoff
     }
     if (!h->dRunoffSlot[1]) {
         h->dRunoffSlot[0] = h->dRunoff;
-        e = dev_alloc(h, &h->dRunoffSlot[1], (size_t)h->opt.max_batch * (h->d.nHRU > 0 ? h->d.nHRU : 1), where, message, false); if (e) return e;
+        e = dev_alloc(h, &h->dRunoffSlot[1], (size_t)h->opt.max_batch * (in_cols(h) > 0 ? in_cols(h) : 1), where, message, false); if (e) return e;
     }
     const int slot = h->asyncSlot; h->asyncSlot ^= 1;
     if (h->freeRec[slot]) CU(cudaStreamWaitEvent(h->copyIn, h->evFree[slot], 0));          // the batch that used this slot has been routed
-    CU(cudaMemcpyAsync(h->dRunoffSlot[slot], runoff, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->copyIn));
+    CU(cudaMemcpyAsync(h->dRunoffSlot[slot], runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->copyIn));
     CU(cudaEventRecord(h->evIn[slot], h->copyIn));
     CU(cudaStreamWaitEvent(h->stream, h->evIn[slot], 0));
     CU(cudaEventRecord(h->ev[0], h->stream));
-    h->d.runoff = h->dRunoffSlot[slot];
+    stage_runoff(h, h->dRunoffSlot[slot], nSteps, h->stream);
     e = route_device(h, nSteps, T0, where, message);
-    h->d.runoff = h->dRunoff;
     if (e) return e;
     CU(cudaEventRecord(h->evFree[slot], h->stream)); h->freeRec[slot] = true;
     if (q_out) {
@@ -859,6 +879,7 @@ long mr_get_info(mr_handle h, int key) {
     switch (key) {
         case MR_INFO_NRCH: return h->d.nRch;
         case MR_INFO_NHRU: return h->d.nHRU;
+        case MR_INFO_NFORCING: return (long)in_cols(h);
         case MR_INFO_NSTAGE: return h->topo.nStage;
         case MR_INFO_NTDH_BAS: return h->ntdhBas;
         case MR_INFO_MAXTDH: return h->maxtdh;
@@ -894,6 +915,40 @@ long mr_get_info(mr_handle h, int key) {
         }
         default: return -1;
     }
+}
+
+int mr_set_remap(mr_handle h, int nForcing, int nMap, const int *mapHruIndex, const int *numQhru, const int *qhruIndex, const double *weight, char *message) {
+    const char *where = "mr_set_remap";
+    if (!h || !h->hasNet) return fail(message, 1, "mr_set_remap/handle has no network");
+    if (h->nForcing) return fail(message, 1, "mr_set_remap/already set for this network");
+    if (nForcing < 1 || nMap < 1 || !mapHruIndex || !numQhru || !qhruIndex || !weight) return fail(message, 1, "mr_set_remap/missing argument");
+    CU(cudaSetDevice(h->opt.device));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<int> ptr(nMap + 1, 0), net(nMap);
+    for (int i = 0; i < nMap; ++i) {
+        if (numQhru[i] < 0) return fail(message, 1, "mr_set_remap/negative number of overlapping polygons");
+        ptr[i + 1] = ptr[i] + numQhru[i];
+        net[i] = (mapHruIndex[i] >= 0 && mapHruIndex[i] < h->d.nHRU) ? mapHruIndex[i] : -1;
+    }
+    const int nOv = ptr[nMap];
+    std::vector<int> ov(qhruIndex, qhruIndex + nOv);
+    for (int &q : ov) if (q < 0 || q >= nForcing) q = -1;
+    std::vector<double> w(weight, weight + nOv);
+    int e;
+    e = dev_upload(h, &h->dMapNet, net, where, message); if (e) return e;
+    e = dev_upload(h, &h->dMapPtr, ptr, where, message); if (e) return e;
+    e = dev_upload(h, &h->dOvIdx, ov, where, message); if (e) return e;
+    e = dev_upload(h, &h->dOvW, w, where, message); if (e) return e;
+    const size_t KB = (size_t)h->opt.max_batch;
+    e = dev_alloc(h, &h->dRunoffNet, KB * (h->d.nHRU > 0 ? h->d.nHRU : 1), where, message); if (e) return e;    // zero: HRUs outside the mapping
+    // the input staging buffers now hold forcing polygons
+    e = dev_alloc(h, &h->dRunoff, KB * nForcing, where, message, false); if (e) return e;
+    h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr;
+    h->nForcing = nForcing; h->nMap = nMap;
+    h->d.runoff = h->dRunoffNet;
+    CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
 }
 
 int mr_set_ghosts(mr_handle h, int nGhost, const int *ghostSegId, const int *kind, const double *totArea, const double *width, char *message) {

@@ -15,8 +15,8 @@
 // Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
-// <is_remap> must be F, <dt_qsim> must equal the forcing interval, one history file, output every step, standard /
-// proleptic_gregorian / noleap calendars.
+// <dt_qsim> must equal the forcing interval, one history file, output every step, standard /
+// proleptic_gregorian / noleap calendars.  <is_remap> T: 1-D polygon forcing only (remap_1D_runoff), remapped on the device.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -282,7 +282,7 @@ int main(int argc, char **argv) {
         o.min_length_route = c.num("min_length_route", 0.0);
         o.is_lake_sim = c.flag("is_lake_sim", false); o.lakeRegulate = c.flag("lakeRegulate", true); o.LakeInputOption = (int)c.num("LakeInputOption", 0);
         o.runoffMin = c.num("runoffMin", 0.0);
-        if (c.flag("is_remap", false)) die(20, "route_runoff/<is_remap> T (runoff remapping) is not supported by this host");
+        const bool isRemap = c.flag("is_remap", false);
         if (c.flag("is_flux_wm", false) || c.flag("is_vol_wm", false)) die(20, "route_runoff/water management is not on this path");
         {                                                        // units_qsim -> time_conv, length_conv (read_control.f90:443-474)
             const std::string u = c.need("units_qsim");
@@ -377,6 +377,25 @@ int main(int argc, char **argv) {
                               d03[2].empty() ? nullptr : d03[2].data(), d03[3].empty() ? nullptr : d03[3].data(), msg);
         if (ierr) die(ierr, msg);
 
+        // ---- runoff remapping (<is_remap> T): mapping netCDF -> device-side remap_1D (read_remap.f90:20-170, process_remap.f90:164-262)
+        const size_t nForcing = roHruId.size();
+        if (isRemap) {
+            nc3::Reader rm(join_path(ancil, c.need("fname_remap")));
+            std::vector<int> mapId, numQ, qId; std::vector<double> wgt;
+            rm.read_int(rm.var(c.need("vname_hruid_in_remap")), mapId);
+            rm.read_int(rm.var(c.need("vname_num_qhru")), numQ);
+            rm.read_int(rm.var(c.need("vname_qhruid")), qId);
+            rm.read_all(rm.var(c.need("vname_weight")), wgt);
+            if (mapId.size() != numQ.size() || qId.size() != wgt.size()) die(20, "read_remap/mapping variables have inconsistent sizes");
+            auto lookup = [](const std::vector<int> &keys, const std::vector<int> &ids) {
+                std::vector<std::pair<int, int>> tab(ids.size()); for (size_t i = 0; i < ids.size(); ++i) tab[i] = {ids[i], (int)i}; std::sort(tab.begin(), tab.end());
+                std::vector<int> out(keys.size(), -1);
+                for (size_t i = 0; i < keys.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(keys[i], -1)); if (it != tab.end() && it->first == keys[i]) out[i] = it->second; }
+                return out; };
+            const std::vector<int> hruIx = lookup(mapId, hruId), qIx = lookup(qId, roHruId);
+            ierr = mr_set_remap(h, (int)nForcing, (int)mapId.size(), hruIx.data(), numQ.data(), qIx.data(), wgt.data(), msg); if (ierr) die(ierr, msg);
+        }
+
         // ---- history file (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
         char stamp[64]; { int y, mo, d, hh = 0, mi = 0; double ss = 0; std::sscanf(c.need("sim_start").c_str(), "%d-%d-%d %d:%d:%lf", &y, &mo, &d, &hh, &mi, &ss);
                           std::snprintf(stamp, sizeof stamp, "%04d-%02d-%02d-%05d", y, mo, d, hh * 3600 + mi * 60 + (int)ss); }
@@ -395,7 +414,8 @@ int main(int argc, char **argv) {
         w.put_int(vId, segId.data());
 
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
-        std::vector<double> ro((size_t)batch * nHRU), q((size_t)o.n_routes * batch * nRch), rec;
+        const size_t inCols = isRemap ? nForcing : nHRU;
+        std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch), rec;
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
@@ -413,7 +433,8 @@ int main(int argc, char **argv) {
                 double fv; if (R.attr_value(qv, "_FillValue", fv)) fillv = fv;
                 R.read(qv, rec, wr.second, 1);
                 if (rec.size() != roHruId.size()) die(20, "read_runoff/runoff variable is not dimensioned [time, hru]");
-                double *dst = &ro[(size_t)k * nHRU];
+                double *dst = &ro[(size_t)k * inCols];
+                if (isRemap) { std::copy(rec.begin(), rec.end(), dst); continue; }  // remapped on the device (fill values are < -1e-6: skipped there)
                 std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
                 for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
             }

@@ -192,6 +192,15 @@ class Router:
         """Launch on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream."""
         self._check(self._L.mr_set_stream(self._h, C.c_void_p(cuda_stream or None), self._msg))
 
+    def set_remap(self, n_forcing: int, map_hru_index, num_qhru, qhru_index, weight):
+        """Runoff arrives on `n_forcing` polygons and is remapped to the network HRUs on the device (mr_set_remap,
+        remap_1D_runoff of the reference); afterwards every runoff array is [K, n_forcing]."""
+        a = np.ascontiguousarray(map_hru_index, dtype=np.int32); b = np.ascontiguousarray(num_qhru, dtype=np.int32)
+        c = np.ascontiguousarray(qhru_index, dtype=np.int32); w = np.ascontiguousarray(weight, dtype=np.float64)
+        self._check(self._L.mr_set_remap(self._h, int(n_forcing), len(a), _ptr(a, C.c_int), _ptr(b, C.c_int), _ptr(c, C.c_int),
+                                         _ptr(w, C.c_double), self._msg))
+        self.nHRU = int(n_forcing)                           # columns of the runoff arrays from now on
+
     # ---- multi-domain hand-off -------------------------------------------------------------------
     def set_export(self, seg_ids):
         ids = np.ascontiguousarray(seg_ids, dtype=np.int32)

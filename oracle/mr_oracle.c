@@ -1158,3 +1158,34 @@ int mro_remove_rch(double *Q, double *T, double *X, int n)
     n = b.n; free(b.Q); free(b.T); free(b.X);
     return n;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* remap_1D_runoff, process_remap.f90:164-262 (one time step).  hru_ix / qhru_ix are 0-based,  */
+/* -1 = integerMissing; basinRunoff is zeroed by the caller (get_basin_runoff.f90:73).         */
+/* ------------------------------------------------------------------------------------------ */
+void mro_remap_1d(int nMap, const int *hru_ix, const int *num_qhru, const int *qhru_ix, const double *weight,
+                  const double *sim, double *basinRunoff)
+{
+    const double xTol = 1.e-6;
+    int ixOverlap = 0, iHRU, ixPoly;
+    for (iHRU = 0; iHRU < nMap; iHRU++) {
+        int jHRU = hru_ix[iHRU];
+        double sumWeights;
+        if (jHRU < 0) { ixOverlap = ixOverlap + num_qhru[iHRU]; continue; }
+        sumWeights = 0.0;
+        basinRunoff[jHRU] = 0.0;
+        for (ixPoly = 0; ixPoly < num_qhru[iHRU]; ixPoly++) {
+            int ixRunoff;
+            if (qhru_ix[ixOverlap] < 0) { ixOverlap = ixOverlap + 1; continue; }
+            ixRunoff = qhru_ix[ixOverlap];
+            if (sim[ixRunoff] > -xTol) {
+                sumWeights = sumWeights + weight[ixOverlap];
+                basinRunoff[jHRU] = basinRunoff[jHRU] + weight[ixOverlap] * sim[ixRunoff];
+            }
+            ixOverlap = ixOverlap + 1;
+        }
+        if (sumWeights > xTol) {
+            if (fabs(1.0 - sumWeights) > xTol) basinRunoff[jHRU] = basinRunoff[jHRU] / sumWeights;
+        }
+    }
+}

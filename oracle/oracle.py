@@ -215,3 +215,13 @@ def remove_rch(Q, T, X):
     Q = np.array(Q, dtype=np.float64); T = np.array(T, dtype=np.float64); X = np.array(X, dtype=np.float64)
     n = lib().mro_remove_rch(_p(Q, C.c_double), _p(T, C.c_double), _p(X, C.c_double), C.c_int(Q.size))
     return Q[:n], T[:n], X[:n]
+
+
+def remap_1d(hru_ix, num_qhru, qhru_ix, weight, sim, n_hru):
+    """remap_1D_runoff for one time step (process_remap.f90:164-262): forcing vector `sim` -> basinRunoff[n_hru]."""
+    a = np.ascontiguousarray(hru_ix, dtype=np.int32); b = np.ascontiguousarray(num_qhru, dtype=np.int32)
+    c = np.ascontiguousarray(qhru_ix, dtype=np.int32); w = np.ascontiguousarray(weight, dtype=np.float64)
+    s = np.ascontiguousarray(sim, dtype=np.float64)
+    out = np.zeros(n_hru)
+    lib().mro_remap_1d(C.c_int(len(a)), _p(a, C.c_int), _p(b, C.c_int), _p(c, C.c_int), _p(w, C.c_double), _p(s, C.c_double), _p(out, C.c_double))
+    return out

@@ -38,9 +38,9 @@ def test_control_file_errors(tmp_path):
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode == 81 and "unknown control key" in r.stderr          # read_control.f90:374-377
     import re
-    bad.write_text(re.sub(r"(<is_remap>\s+)F", r"\1T", txt))
+    bad.write_text(txt + "<is_flux_wm>   T   ! water management is not on this path\n")
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
-    assert r.returncode != 0 and "is_remap" in r.stderr
+    assert r.returncode != 0 and "water management" in r.stderr
     bad.write_text(re.sub(r"(<dt_qsim>\s+)86400", r"\g<1>3600 ", txt))
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode != 0 and "forcing interval" in r.stderr

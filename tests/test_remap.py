@@ -1,0 +1,106 @@
+"""Runoff remapping (<is_remap> T, remap_1D_runoff, process_remap.f90:164-262): oracle restatement vs an independent
+numpy evaluation on the CPU; on the GPU the device-side remap (mr_set_remap / k_remap) feeding the routing must equal
+routing the oracle-remapped runoff, and the stand-alone host must read a reference-style mapping file."""
+import json
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.util import case
+
+
+def make_mapping(net, n_forcing, seed=0):
+    """Random ragged mapping: every network HRU but a few overlaps 1-4 forcing polygons; some mapping HRUs are not in
+    the network, some polygons have no forcing, some weight rows do not sum to one."""
+    rng = np.random.default_rng(seed)
+    map_ids = list(net.hruId) + [10**6 + k for k in range(5)]            # 5 mapping HRUs outside the network
+    rng.shuffle(map_ids)
+    drop = set(rng.choice(net.hruId, size=max(1, net.nHRU // 20), replace=False).tolist())
+    map_ids = [i for i in map_ids if i not in drop]                       # a few network HRUs are not in the mapping
+    forcing_ids = np.arange(1, n_forcing + 1) * 3
+    num, qid, w = [], [], []
+    for _ in map_ids:
+        k = int(rng.integers(1, 5))
+        ids = rng.choice(np.concatenate([forcing_ids, [999999]]), size=k, replace=False)      # 999999: polygon without forcing
+        ww = rng.random(k); ww /= ww.sum()
+        if rng.random() < 0.3:
+            ww *= rng.uniform(0.5, 0.9)                                   # weights that do not sum to one -> renormalised
+        num.append(k); qid += ids.tolist(); w += ww.tolist()
+    return np.array(map_ids), np.array(num), np.array(qid), np.array(w), forcing_ids
+
+
+def indices(net, map_ids, qid, forcing_ids):
+    pos = {int(h): i for i, h in enumerate(net.hruId)}
+    fpos = {int(h): i for i, h in enumerate(forcing_ids)}
+    return (np.array([pos.get(int(m), -1) for m in map_ids], dtype=np.int32), np.array([fpos.get(int(q), -1) for q in qid], dtype=np.int32))
+
+
+def numpy_remap(hru_ix, num, qix, w, sim, n_hru):
+    out = np.zeros(n_hru); o = 0
+    for i, j in enumerate(hru_ix):
+        sl = slice(o, o + num[i]); o += num[i]
+        if j < 0:
+            continue
+        ok = (qix[sl] >= 0)
+        ok[ok] &= sim[qix[sl][ok]] > -1e-6
+        ws, vs = w[sl][ok], sim[qix[sl][ok]]
+        acc, sw = 0.0, 0.0
+        for a, b in zip(ws, vs):
+            sw = sw + a; acc = acc + a * b
+        if sw > 1e-6 and abs(1.0 - sw) > 1e-6:
+            acc = acc / sw
+        out[j] = acc
+    return out
+
+
+def test_oracle_remap_matches_numpy():
+    from oracle import oracle as orc
+    net, params, opts, ro = case("random", n=120, seed=4, dt=86400.0, route_opt="1", steps=3)
+    map_ids, num, qid, w, fids = make_mapping(net, 90, seed=2)
+    hru_ix, qix = indices(net, map_ids, qid, fids)
+    rng = np.random.default_rng(5)
+    sim = rng.lognormal(np.log(2e-5), 1.0, 90); sim[::11] = -9999.0; sim[5] = -5e-7
+    got = orc.remap_1d(hru_ix, num, qix, w, sim, net.nHRU)
+    assert np.array_equal(got, numpy_remap(hru_ix, num, qix, w, sim, net.nHRU))
+    assert (got[np.isin(net.hruId, map_ids, invert=True)] == 0).all()
+
+
+@pytest.mark.gpu
+def test_device_remap_feeds_routing_like_the_oracle():
+    from mizuroute_b200.route import Router
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, _ = case("conus", n=800, seed=4, dt=3600.0, route_opt="012", steps=1)
+    nF, K = 500, 20
+    map_ids, num, qid, w, fids = make_mapping(net, nF, seed=7)
+    hru_ix, qix = indices(net, map_ids, qid, fids)
+    rng = np.random.default_rng(9)
+    forcing = rng.lognormal(np.log(2e-5), 1.0, size=(K, nF)); forcing[:, ::13] = -9999.0
+    ro_net = np.stack([orc.remap_1d(hru_ix, num, qix, w, forcing[t], net.nHRU) for t in range(K)])
+    qo = Oracle(net, params, opts).run(ro_net)
+    r = Router(net, params, opts, max_batch=8)
+    r.set_remap(nF, hru_ix, num, qix, w)
+    qg = np.concatenate([r.route_batch(np.ascontiguousarray(forcing[s:s + 8])) for s in range(0, K, 8)], axis=1)
+    assert np.array_equal(qg[0], qo[0]) and np.array_equal(qg[1], qo[1])       # remap + SUM / IRF: bit-identical
+    assert np.max(np.abs(qg[2] - qo[2]) / np.maximum(np.abs(qo[2]), 1e-300)) <= 1e-4
+
+
+@pytest.mark.gpu
+def test_host_reads_reference_style_mapping_file(tmp_path):
+    from mizuroute_b200 import build as mrbuild, casefiles
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, _ = case("conus", n=400, seed=5, dt=86400.0, route_opt="12", steps=1)
+    nF, K = 300, 12
+    map_ids, num, qid, w, fids = make_mapping(net, nF, seed=3)
+    hru_ix, qix = indices(net, map_ids, qid, fids)
+    forcing = np.random.default_rng(1).lognormal(np.log(2e-5), 1.0, size=(K, nF))
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, forcing, case_name="remap", remap=(map_ids, num, qid, w, fids))
+    r = subprocess.run([mrbuild.build_host(), ctl, "--batch", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    ro_net = np.stack([orc.remap_1d(hru_ix, num, qix, w, forcing[t], net.nHRU) for t in range(K)])
+    qo = Oracle(net, params, opts).run(ro_net)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
