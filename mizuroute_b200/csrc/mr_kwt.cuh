@@ -69,22 +69,33 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
     MR_NOUNROLL
     for (int IMID = IBEG + 1 + lane; IMID <= IEND; IMID += MR_NL)
         W[IMID] = (TOLD[IMID] - TOLD[IMID - 1]) * 0.5 * (QOLD[IMID - 1] + QOLD[IMID]);
+    // the slopes of the first and of the last segment (one division each) on two lanes
+    const int L1 = MR_NL > 1 ? 1 : 0;
+    double slB, slE;
+    {
+        const int I = (lane == L1 && MR_NL > 1) ? IEND : IBEG;
+        double sl = 0.0;
+        if (I >= 1) sl = (QOLD[I] - QOLD[I - 1]) / (TOLD[I] - TOLD[I - 1]);
+        slB = team_bcast(sl, 0);
+        if (MR_NL > 1) slE = team_bcast(sl, L1);
+        else slE = IEND >= 1 ? (QOLD[IEND] - QOLD[IEND - 1]) / (TOLD[IEND] - TOLD[IEND - 1]) : 0.0;
+    }
     MR_SYNC();
     if (lane == 0) {
         if (T1 < TOLD[IBEG]) {
-            const double SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+            const double SLOPE = slB;
             const double QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
             const double QEST1 = SLOPE * (T1 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
             QNEW = 0.5 * (QEST0 + QEST1);
         } else {
             double AREAB = 0.0, AREAE = 0.0, AREAM = 0.0;
             if (T0 < TOLD[IBEG]) {
-                const double SLOPE = (QOLD[IBEG] - QOLD[IBEG - 1]) / (TOLD[IBEG] - TOLD[IBEG - 1]);
+                const double SLOPE = slB;
                 const double QEST0 = SLOPE * (T0 - TOLD[IBEG - 1]) + QOLD[IBEG - 1];
                 AREAB = (TOLD[IBEG] - T0) * 0.5 * (QEST0 + QOLD[IBEG]);
             }
             if (T1 < TOLD[IEND]) {
-                const double SLOPE = (QOLD[IEND] - QOLD[IEND - 1]) / (TOLD[IEND] - TOLD[IEND - 1]);
+                const double SLOPE = slE;
                 const double QEST1 = SLOPE * (T1 - TOLD[IEND - 1]) + QOLD[IEND - 1];
                 AREAE = (T1 - TOLD[IEND - 1]) * 0.5 * (QOLD[IEND - 1] + QEST1);
             }
@@ -413,16 +424,19 @@ MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0
     if (NUPR == 0) {
         // only headwater basins upstream: the merge emits the single time T1 (series 0 supplies it, the other
         // basins are interpolated at their end point, :930-957)
+        MR_NOUNROLL
+        for (int s = lane; s < NUPB; s += MR_NL) {         // SFLOW of every basin series, one per lane (the upper half of scf is free here)
+            const double qb = S.u.m.sq[2 * s], qe = S.u.m.sq[2 * s + 1];
+            double SFLOW;
+            if (s == 0) SFLOW = qe * S.u.m.scf[0];
+            else { const double SLOPE = (qe - qb) / (T1 - T0); SFLOW = (qb + SLOPE * (T1 - T0)) * S.u.m.scf[s]; }
+            S.u.m.scf[MAXSER / 2 + s] = SFLOW;
+        }
+        MR_SYNC();
         if (lane == 0) {
             double Q_AGG = 0.0;
             MR_NOUNROLL
-            for (int s = 0; s < NUPB; ++s) {
-                const double qb = S.u.m.sq[2 * s], qe = S.u.m.sq[2 * s + 1];
-                double SFLOW;
-                if (s == 0) SFLOW = qe * S.u.m.scf[0];
-                else { const double SLOPE = (qe - qb) / (T1 - T0); SFLOW = (qb + SLOPE * (T1 - T0)) * S.u.m.scf[s]; }
-                Q_AGG = Q_AGG + SFLOW;
-            }
+            for (int s = 0; s < NUPB; ++s) Q_AGG = Q_AGG + S.u.m.scf[MAXSER / 2 + s];
             S.Q[nOwn] = Q_AGG; S.TE[nOwn] = T1;
         }
         ND = 1;
@@ -466,14 +480,25 @@ MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0
                     SFLOW = S.u.m.sq[o + k] * S.u.m.scf[s];
                 } else {
                     const int nc = S.u.m.ncand[s];
+                    // candidates of series s processed before this one: times < CT, or == CT in an earlier series
+                    // (times ascend within a series: linear scan for short series, bisection for long ones)
                     int cnt = 0;
-                    MR_NOUNROLL
-                    for (int kk = 1; kk <= nc; ++kk) {
-                        const double tt = S.u.m.st[o + kk];
-                        if (tt < CT) ++cnt;
-                        else if (tt == CT && s < J) { ++cnt; dup = true; }
-                        else break;
+                    if (nc <= 6) {
+                        MR_NOUNROLL
+                        for (int kk = 1; kk <= nc; ++kk) {
+                            const double tt = S.u.m.st[o + kk];
+                            if (tt < CT || (tt == CT && s < J)) ++cnt; else break;
+                        }
+                    } else {
+                        int hi = nc;
+                        MR_NOUNROLL
+                        while (cnt < hi) {
+                            const int mid = (cnt + hi + 1) >> 1;
+                            const double tt = S.u.m.st[o + mid];
+                            if (tt < CT || (tt == CT && s < J)) cnt = mid; else hi = mid - 1;
+                        }
                     }
+                    if (s < J && cnt >= 1 && S.u.m.st[o + cnt] == CT) dup = true;
                     ord += cnt;
                     int cur = 1 + cnt;
                     if (cur > S.u.m.cmax[s]) cur = S.u.m.cmax[s];
@@ -595,13 +620,17 @@ MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, d
 
     double QNEW = 0.0;
     if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return 0; }
-    double Q_END = 0.0, TIMEI = 0.0;
-    if (lane == 0) {
-        Qs[p] = QNEW * W + qr1;                        // kwt_route.f90:273
-        // end-of-step point, kwt_route.f90:288-292
-        Q_END = S.Q[NR] + ((S.Q[NR + 1] - S.Q[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
-        TIMEI = S.TE[NR] + ((S.TE[NR + 1] - S.TE[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+    // end-of-step point, kwt_route.f90:288-292: flow on lane 0, entry time on lane 1 (one division each)
+    double Q_END, TIMEI;
+    {
+        const int L1 = MR_NL > 1 ? 1 : 0;
+        const double *A = (lane == L1 && MR_NL > 1) ? S.TE : S.Q;
+        const double v = A[NR] + ((A[NR + 1] - A[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+        Q_END = team_bcast(v, 0);
+        if (MR_NL > 1) TIMEI = team_bcast(v, L1);
+        else TIMEI = S.TE[NR] + ((S.TE[NR + 1] - S.TE[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
     }
+    if (lane == 0) Qs[p] = QNEW * W + qr1;             // kwt_route.f90:273
 
     // KWAVE(0:NQ2+1) = routed(0:NR) | end-of-step point | non-routed(NR+1:NQ2), kwt_route.f90:299-311
     const size_t row = (size_t)p * KWP;

