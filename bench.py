@@ -353,23 +353,23 @@ def main():
             if dom is None:                                # software pipeline: H2D(b+1) | route(b) | D2H(b-1) overlap
                 r.route_batch_async(ro_pin, out_pin)
                 return
-            r.route_batch(ro_pin, out_pin)
-            dom.hand_off()
-            if rm is not None:
-                stream_main.wait_stream(stream)
-                rm.route_batch(rom_pin, outm_pin)
-                stream.wait_stream(stream_main)
+            dom.route_batch_pipelined(ro_pin, out_pin, rom_pin if rm is not None else None, outm_pin if rm is not None else None,
+                                      stream, stream_main)
 
         with torch.cuda.stream(stream):
             e2e_all()                                      # warm the pinned path once
             if dom is None:
                 r.wait()
+            else:
+                finish_all()
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 e2e_all()
             if dom is None:
                 r.wait()
+            else:
+                finish_all()
             torch.cuda.synchronize()
             e_s = time.perf_counter() - t0
         t_e = torch.tensor([e_s], dtype=torch.float64, device="cuda")
@@ -382,7 +382,7 @@ def main():
         e2e = {"value": full_n * T * args.steps / float(t_e.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
                "api": ("Router.route_batch_async (mr_step_batch_async): pinned host forcing in, REACH_Q series out, copies overlapped with routing"
-                       if dom is None else "Router.route_batch (mr_step_batch) per domain with pinned host buffers + NCCL hand-off")}
+                       if dom is None else "DomainSet.route_batch_pipelined: mr_step_batch_async per domain with pinned host buffers + NCCL hand-off")}
         del ro_pin, out_pin
 
     if rank != 0:

@@ -141,6 +141,14 @@ class DomainSet:
         if self.main is not None:
             self.main.route_resident(K)
 
+    def route_batch_pipelined(self, ro_trib, out_trib, ro_main, out_main, stream_trib, stream_main):
+        """End-to-end variant of `route_resident_pipelined`: pinned host forcing in, pinned REACH_Q out, for the
+        tributary domain of this rank and (rank 0) the mainstem; uploads, routing, hand-off and downloads of
+        consecutive calls overlap (mr_step_batch_async per domain).  Call `wait()` before reading the outputs."""
+        self._pipelined(stream_trib, stream_main,
+                        (lambda: self.trib.route_batch_async(ro_trib, out_trib)) if self.trib is not None else None,
+                        (lambda: self.main.route_batch_async(ro_main, out_main)) if self.main is not None else None)
+
     def route_resident_pipelined(self, K: int, stream_trib, stream_main):
         """The same, without host waits and with the mainstem on its own stream: the mainstem of this batch overlaps
         the tributaries of the next one (tributaries never depend on the mainstem).  `stream_*` are
@@ -149,12 +157,17 @@ class DomainSet:
         Rank 0 receives on the MAINSTEM stream, so its tributary stream never waits for the other ranks; its own
         outlets are copied export -> import first, and the next tributary batch (which overwrites the export buffer)
         waits for that copy only."""
+        self._pipelined(stream_trib, stream_main,
+                        (lambda: self.trib.route_resident_async(K)) if self.trib is not None else None,
+                        (lambda: self.main.route_resident_async(K)) if self.main is not None else None)
+
+    def _pipelined(self, stream_trib, stream_main, run_trib, run_main):
         torch = self.torch
         with torch.cuda.stream(stream_trib):
             if self._copy_done is not None:
                 stream_trib.wait_event(self._copy_done)
-            if self.trib is not None:
-                self.trib.route_resident_async(K)
+            if run_trib is not None:
+                run_trib()
             if self.main is None:
                 self.hand_off()                            # send: ordered after this rank's tributary kernels
                 return
@@ -168,7 +181,7 @@ class DomainSet:
             self._copy_done = torch.cuda.Event()
             self._copy_done.record(stream_main)
             self._recv_others()
-            self.main.route_resident_async(K)
+            run_main()
 
     def _recv_others(self):
         import torch.distributed as dist

@@ -30,14 +30,31 @@ ro = synth.runoff_series(net, K, seed=11, dt=opts.dt)
 single = Router(net, params, opts, device=local, max_batch=K).route_batch(ro)
 
 worst = 0.0
-for mode in ("blocking", "pipelined"):
+for mode in ("blocking", "pipelined", "pipelined end-to-end"):
     dom = DomainSet(net, params, opts, B, rank, world, device=local)
     sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
     if dom.trib is not None:
         dom.trib.set_stream(sa.cuda_stream)
     if dom.main is not None:
-        dom.main.set_stream(sb.cuda_stream if mode == "pipelined" else sa.cuda_stream)
-    for s in range(0, K, B):
+        dom.main.set_stream(sb.cuda_stream if mode != "blocking" else sa.cuda_stream)
+    if mode == "pipelined end-to-end":                     # pinned host buffers in and out, all batches in flight
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        nm = len(opts.route_opt)
+        ins_t = [pin(ro[s:s + B][:, dom.trib_net.meta["hru_index"]]) for s in range(0, K, B)]
+        outs_t = [torch.empty((nm, B, dom.trib_net.nRch), dtype=torch.float64).pin_memory() for _ in range(0, K, B)]
+        ins_m = [pin(ro[s:s + B][:, dom.main_net.meta["hru_index"]]) if dom.main is not None else None for s in range(0, K, B)]
+        outs_m = [torch.empty((nm, B, dom.main_net.nRch), dtype=torch.float64).pin_memory() if dom.main is not None else None for _ in range(0, K, B)]
+        for i in range(len(ins_t)):
+            dom.route_batch_pipelined(ins_t[i], outs_t[i], ins_m[i], outs_m[i], sa, sb)
+        sa.wait_stream(sb)
+        dom.wait()
+        torch.cuda.synchronize()
+        for i, s in enumerate(range(0, K, B)):
+            assert np.array_equal(outs_t[i].numpy(), single[:, s:s + B][:, :, dom.dec.trib[rank]]), f"rank {rank} tributaries differ ({mode})"
+            if dom.main is not None:
+                keep = ~dom.main_net.meta["ghost_mask"]
+                assert np.array_equal(outs_m[i].numpy()[:, :, keep], single[:, s:s + B][:, :, dom.main_net.meta["reach_index"][keep]]), f"mainstem differs ({mode})"
+    for s in (range(0, K, B) if mode != "pipelined end-to-end" else []):
         dom.upload_runoff(ro[s:s + B])
         with torch.cuda.stream(sa):
             if mode == "blocking":
