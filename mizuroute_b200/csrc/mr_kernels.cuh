@@ -311,32 +311,43 @@ __global__ void k_kwt_params(int N, const double *rslope, const double *rmann, d
 // KWT wavefront: one team of MR_TEAM lanes per (reach, step); the wave particles sit in the team's shared-memory
 // scratch.  The rare task that needs more room than the shared scratch offers borrows a full-capacity scratch
 // from a global arena (64 slots per SM, claimed with an atomic bit mask).
-constexpr int KWT_WARPS = 4;                             // warps per block
+#ifndef KWT_WARPS_N
+#define KWT_WARPS_N 4
+#endif
+constexpr int KWT_WARPS = KWT_WARPS_N;                   // warps per block
 constexpr int KWT_TEAMS = KWT_WARPS * (32 / MR_TEAM);    // teams (tasks in flight) per block
 constexpr int KWT_ARENA_SMS = 256, KWT_ARENA_SLOTS = 64;
-// one (reach, step) task of a KWT wavefront
-__device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, int p, int w, long long tau0) {
+// One (reach, step) task of a KWT wavefront, by one team.  EVERY lane of the warp enters (a team without a task has
+// active = false): the first attempt re-converges the teams of the warp at its phase boundaries (kwt_reach_team<.., true>).
+__device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, int p, bool active, int w, long long tau0) {
     const int lane = MR_LANE;
-    const int t = w - d.stageOf[p];
-    const int flags = d.flags[p];
-    if (flags & FLAG_GHOST) {                          // this step's wave of a tributary outlet routed in another domain
-        const int b = (int)((tau0 + t) & 1);
-        const double *rec = d.impBuf + ((size_t)d.impSlot[p] * d.kmax + t) * d.recLen + d.nRoutes + 1;
-        const size_t row = (size_t)p * KWP;
-        for (int k = lane; k < KWP; k += MR_NL) { d.kwQF[b][row + k] = rec[2 + k]; d.kwTR[b][row + k] = rec[2 + KWP + k]; }
-        if (lane == 0) { d.kwN[b][p] = (int)rec[0]; d.kwNR[b][p] = (int)rec[1]; }
-        return;
+    int t = 0;
+    if (active) {
+        t = w - d.stageOf[p];
+        const int flags = d.flags[p];
+        if (flags & FLAG_GHOST) {                      // this step's wave of a tributary outlet routed in another domain
+            const int b = (int)((tau0 + t) & 1);
+            const double *rec = d.impBuf + ((size_t)d.impSlot[p] * d.kmax + t) * d.recLen + d.nRoutes + 1;
+            const size_t row = (size_t)p * KWP;
+            for (int k = lane; k < KWP; k += MR_NL) { d.kwQF[b][row + k] = rec[2 + k]; d.kwTR[b][row + k] = rec[2 + KWP + k]; }
+            if (lane == 0) { d.kwN[b][p] = (int)rec[0]; d.kwNR[b][p] = (int)rec[1]; }
+            active = false;
+        } else if (flags & FLAG_LAKE) {
+            if (lane == 0) lake_reach<M_KWT>(d, p, t, tau0 + t);
+            active = false;
+        }
     }
-    if (flags & FLAG_LAKE) { if (lane == 0) lake_reach<M_KWT>(d, p, t, tau0 + t); return; }
     int nPre = 0;
     const long long c0 = d.kwProf ? clock64() : 0;
-    const int rc = kwt_reach_team(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t], &nPre);
+    const double T0 = active ? d.T0s[t] : 0.0, T1 = active ? d.T1s[t] : 0.0;
+    const int rc = kwt_reach_team<KwtScratchSmall, true>(d, S, p, t, tau0 + t, T0, T1, &nPre, active);
+    if (!active) return;
     if (d.kwProf && lane == 0) {                       // classes: particles before thinning 0 (no area), <=3, <=6, <=12, <=20, <=40, >40, retry
         const int cls = rc == KWT_RETRY ? 7 : (nPre == 0 ? 0 : nPre <= 3 ? 1 : nPre <= 6 ? 2 : nPre <= 12 ? 3 : nPre <= 20 ? 4 : nPre <= 40 ? 5 : 6);
         atomicAdd(&d.kwProf[2 * cls], (unsigned long long)(clock64() - c0)); atomicAdd(&d.kwProf[2 * cls + 1], 1ull);
     }
     if (rc != KWT_RETRY) return;
-    // wide confluence: claim a full-capacity scratch of this SM
+    // wide confluence: claim a full-capacity scratch of this SM (this team alone from here on)
     unsigned sm;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
     sm &= KWT_ARENA_SMS - 1;
@@ -351,23 +362,24 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
     }
     slot = team_bcast(slot, 0);
     KwtScratch &B = reinterpret_cast<KwtScratch *>(d.kwArena)[(size_t)sm * KWT_ARENA_SLOTS + slot];
-    kwt_reach_team(d, B, p, t, tau0 + t, d.T0s[t], d.T1s[t]);
+    kwt_reach_team<KwtScratch, false>(d, B, p, t, tau0 + t, T0, T1);
     MR_SYNC();
     if (lane == 0) { __threadfence(); atomicAnd(&d.kwArenaMask[sm], ~(1ull << slot)); }
 }
 
-// Tasks are dealt round-robin to the teams of a grid that is at most one resident wave (8 blocks per SM), so a
-// team works through several tasks and no block-scheduling cost is paid per task.
 #ifndef KWT_MIN_BLOCKS
 #define KWT_MIN_BLOCKS 8
 #endif
+// Tasks are dealt to teams block by block; the loop bounds are the same for all teams of a warp (required by the
+// full-warp syncs inside kwt_task).
 __global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
     __shared__ KwtScratchSmall S[KWT_TEAMS];
     const int team = threadIdx.x / MR_TEAM;
     const int stride = gridDim.x * KWT_TEAMS;
-    for (int p = lo + blockIdx.x * KWT_TEAMS + team; p < hi; p += stride) {
-        kwt_task(d, S[team], p, w, tau0);
-        MR_SYNC();
+    for (int base = lo + blockIdx.x * KWT_TEAMS; base < hi; base += stride) {
+        const int p = base + team;
+        kwt_task(d, S[team], p, p < hi, w, tau0);
+        MR_WSYNC();
     }
 }
 

@@ -545,120 +545,140 @@ MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0
 // KWAVE(NR-1:), so the owner simply starts reading at NR-1 next step, and the consumer (exactly one wavefront
 // behind, reading the same buffer) sees the unstripped array.
 // ------------------------------------------------------------------------------------------------
-template <class SC>
-MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1, int *nPre = nullptr) {
+// WS = true: every lane of the WARP calls this together (teams of MR_TEAM < 32 lanes, one task each; a team without a
+// task passes active = false) and the phases of the task -- gather + merge | thinning | routing | averaging + store --
+// end in a full-warp sync, so the teams of a warp, which diverge inside a phase whenever their tasks differ,
+// re-converge at every phase boundary and share the instruction stream wherever their paths agree.
+template <class SC, bool WS = false>
+MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1, int *nPre = nullptr, bool active = true) {
     const int lane = MR_LANE;
     const int N = d.nRch;
     const int b = (int)(tau & 1), bp = b ^ 1;
     double *Qs = d.qSer[M_KWT] + (size_t)t * N;
-    const double qr1 = d.qrSer[(size_t)(t + 1) * N + p];
-    const int nGood = d.nGood[p];
-    if (nGood == 0) {                                  // no contributing area upstream, kwt_route.f90:181-205
-        if (lane == 0) {
-            d.inflow[M_KWT][p] = 0.0;
-            Qs[p] = qr1;
-            d.kwN[b][p] = 1; d.kwNR[b][p] = 0;
-            const size_t row = (size_t)p * KWP;
-            d.kwQF[b][row] = -9999.0; d.kwTI[b][row] = -9999.0; d.kwTR[b][row] = -9999.0;
-        }
-        return 0;
-    }
-    const int u0 = d.upPtr[p];
-    const double W = d.rwidth[p];
-
-    // getusq_rch, kwt_route.f90:461-613
-    const int nPrev = d.kwN[bp][p], nrPrev = d.kwNR[bp][p];
-    const int first = nrPrev > 0 ? nrPrev - 1 : 0;
-    const int nOwn = nPrev > 0 ? nPrev - first : 1;
-    if (nPrev > 0) {
-        const size_t row = (size_t)p * KWP + first;
-        MR_NOUNROLL
-        for (int i = lane; i < nOwn; i += MR_NL) { S.Q[i] = d.kwQF[bp][row + i]; S.TE[i] = d.kwTI[bp][row + i]; }
-        if (lane == 0) S.TX[0] = d.kwTR[bp][row];
-    }
-    int ND = 0, ND_read = 0;
-    if (d.flags[p] & FLAG_LAKE_UP) {                   // lake outlet reach, kwt_route.f90:540-559
-        if (d.upPtr[p + 1] - u0 > 1) { if (lane == 0) raise(d.err, 10, p, E_LAKE_UPS); return 0; }
-        if (lane == 0) {
-            S.Q[nOwn] = Qs[d.upIdx[u0]] / W; S.TE[nOwn] = T1;
-            double qup = 0.0;                          // kwt_route.f90:168-174
-            MR_NOUNROLL
-            for (int m = 0; m < nGood; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
-            d.inflow[M_KWT][p] = qup;
-        }
-        ND = 1;
-    } else {
-        const int e = kwt_merge_team(d, S, p, t, b, T0, T1, nOwn, ND, ND_read);
-        if (e == -E_SCRATCH && SC::CAP < WCAP) return KWT_RETRY;       // nothing has been modified yet: re-run with the full scratch
-        if (e) {
-            const int site = -e;
-            if (lane == 0) raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site);
-            return 0;
-        }
-    }
-    MR_SYNC();
-    if (nPrev == 0 && lane == 0) {                     // cold start, kwt_route.f90:587-596
-        S.Q[0] = S.Q[nOwn]; S.TE[0] = T0 - (T1 - T0); S.TX[0] = T0;
-    }
-    MR_SYNC();
-    int n = nOwn + ND;
-    if (nPre) *nPre = n;
-    bool neg = false;
-    MR_NOUNROLL
-    for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;
-    if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return 0; }
-
-    if (n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); return 0; } }
-
-    const int NQ1 = n - 1;
+    int rc = 0, nOwn = 0, ND = 0, ND_read = 0, n = 0, NQ2 = 0, NR = 0;
+    double qr1 = 0.0, W = 1.0;
     unsigned routed = 0;
-    int NQ2;
-    const int ek = kwt_kinwav_team(d, S, p, T0, T1, NQ1, NQ2, routed);
-    if (ek) { if (lane == 0) raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); return 0; }
-    const int NR = mr_popc(routed);                    // count(FROUTE)-1 (FROUTE(0) is always true)
-    if (NR + 1 > NQ2) { if (lane == 0) raise(d.err, 21, p, E_NO_NONROUTED); return 0; }
+    bool live = active;
 
-    double QNEW = 0.0;
-    if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return 0; }
-    // end-of-step point, kwt_route.f90:288-292: flow on lane 0, entry time on lane 1 (one division each)
-    double Q_END, TIMEI;
-    {
-        const int L1 = MR_NL > 1 ? 1 : 0;
-        const double *A = (lane == L1 && MR_NL > 1) ? S.TE : S.Q;
-        const double v = A[NR] + ((A[NR + 1] - A[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
-        Q_END = team_bcast(v, 0);
-        if (MR_NL > 1) TIMEI = team_bcast(v, L1);
-        else TIMEI = S.TE[NR] + ((S.TE[NR + 1] - S.TE[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
-    }
-    if (lane == 0) Qs[p] = QNEW * W + qr1;             // kwt_route.f90:273
-
-    // KWAVE(0:NQ2+1) = routed(0:NR) | end-of-step point | non-routed(NR+1:NQ2), kwt_route.f90:299-311
-    const size_t row = (size_t)p * KWP;
-    double *oQ = d.kwQF[b] + row, *oI = d.kwTI[b] + row, *oR = d.kwTR[b] + row;
-    MR_NOUNROLL
-    for (int i = lane; i <= NQ2; i += MR_NL) {
-        const int j = i <= NR ? i : i + 1;
-        oQ[j] = S.Q[i]; oI[j] = S.TE[i]; oR[j] = S.TX[i];
-    }
-    if (d.expSlot) {                                   // tributary outlet: leave this step's wave for the mainstem domain
-        const int slot = d.expSlot[p];
-        if (slot >= 0) {
-            double *rec = d.expBuf + ((size_t)slot * d.kmax + t) * d.recLen + d.nRoutes + 1;
-            MR_NOUNROLL
-            for (int i = lane; i <= NQ2; i += MR_NL) {
-                const int j = i <= NR ? i : i + 1;
-                rec[2 + j] = S.Q[i]; rec[2 + KWP + j] = S.TX[i];
+    // ---- phase 1: getusq_rch (own wave + merged upstream waves), kwt_route.f90:461-613.  false = task finished or failed.
+    auto phase_in = [&]() -> bool {
+        qr1 = d.qrSer[(size_t)(t + 1) * N + p];
+        const int nGood = d.nGood[p];
+        if (nGood == 0) {                              // no contributing area upstream, kwt_route.f90:181-205
+            if (lane == 0) {
+                d.inflow[M_KWT][p] = 0.0;
+                Qs[p] = qr1;
+                d.kwN[b][p] = 1; d.kwNR[b][p] = 0;
+                const size_t row = (size_t)p * KWP;
+                d.kwQF[b][row] = -9999.0; d.kwTI[b][row] = -9999.0; d.kwTR[b][row] = -9999.0;
             }
-            if (lane == 0) { rec[0] = (double)(NQ2 + 2); rec[1] = (double)(NR + 2); rec[2 + NR + 1] = Q_END; rec[2 + KWP + NR + 1] = T1; }
+            return false;
+        }
+        const int u0 = d.upPtr[p];
+        W = d.rwidth[p];
+        const int nPrev = d.kwN[bp][p], nrPrev = d.kwNR[bp][p];
+        const int first = nrPrev > 0 ? nrPrev - 1 : 0;
+        nOwn = nPrev > 0 ? nPrev - first : 1;
+        if (nPrev > 0) {
+            const size_t row = (size_t)p * KWP + first;
+            MR_NOUNROLL
+            for (int i = lane; i < nOwn; i += MR_NL) { S.Q[i] = d.kwQF[bp][row + i]; S.TE[i] = d.kwTI[bp][row + i]; }
+            if (lane == 0) S.TX[0] = d.kwTR[bp][row];
+        }
+        if (d.flags[p] & FLAG_LAKE_UP) {               // lake outlet reach, kwt_route.f90:540-559
+            if (d.upPtr[p + 1] - u0 > 1) { if (lane == 0) raise(d.err, 10, p, E_LAKE_UPS); return false; }
+            if (lane == 0) {
+                S.Q[nOwn] = Qs[d.upIdx[u0]] / W; S.TE[nOwn] = T1;
+                double qup = 0.0;                      // kwt_route.f90:168-174
+                MR_NOUNROLL
+                for (int m = 0; m < nGood; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
+                d.inflow[M_KWT][p] = qup;
+            }
+            ND = 1;
+        } else {
+            const int e = kwt_merge_team(d, S, p, t, b, T0, T1, nOwn, ND, ND_read);
+            if (e == -E_SCRATCH && SC::CAP < WCAP) { rc = KWT_RETRY; return false; }   // nothing modified yet: re-run with the full scratch
+            if (e) {
+                const int site = -e;
+                if (lane == 0) raise(d.err, site == E_TIME_ORDER ? 30 : (site == E_BRACKET ? 40 : (site == E_STUCK ? 20 : 60)), p, site);
+                return false;
+            }
+        }
+        MR_SYNC();
+        if (nPrev == 0 && lane == 0) {                 // cold start, kwt_route.f90:587-596
+            S.Q[0] = S.Q[nOwn]; S.TE[0] = T0 - (T1 - T0); S.TX[0] = T0;
+        }
+        MR_SYNC();
+        n = nOwn + ND;
+        if (nPre) *nPre = n;
+        bool neg = false;
+        MR_NOUNROLL
+        for (int i = lane; i < n; i += MR_NL) if (S.Q[i] < 0.0) neg = true;
+        if (team_any(neg)) { if (lane == 0) raise(d.err, 20, p, E_NEG_FLOW); return false; }
+        return true;
+    };
+    if (live) live = phase_in();
+    if (WS) MR_WSYNC();
+
+    // ---- phase 2: remove_rch
+    if (live && n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); live = false; } }
+    if (WS) MR_WSYNC();
+
+    // ---- phase 3: kinwav_rch
+    if (live) {
+        const int ek = kwt_kinwav_team(d, S, p, T0, T1, n - 1, NQ2, routed);
+        if (ek) { if (lane == 0) raise(d.err, ek, p, ek == 20 ? E_ZERO_FLOW : (ek == 30 ? E_TEXIT2 : E_RUPDATE)); live = false; }
+        else {
+            NR = mr_popc(routed);                      // count(FROUTE)-1 (FROUTE(0) is always true)
+            if (NR + 1 > NQ2) { if (lane == 0) raise(d.err, 21, p, E_NO_NONROUTED); live = false; }
         }
     }
-    if (lane == 0) {
-        oQ[NR + 1] = Q_END; oI[NR + 1] = TIMEI; oR[NR + 1] = T1;
-        d.kwN[b][p] = NQ2 + 2;
-        d.kwNR[b][p] = NR + 2;
-        if (d.kwCount) d.kwCount[p] += (unsigned)(nOwn + ND_read + NQ2 + 2);
+    if (WS) MR_WSYNC();
+
+    // ---- phase 4: interp_rch, end-of-step point, new wave
+    if (live) {
+        double QNEW = 0.0;
+        if (kwt_time_average_team(S.TX, S.Q, NR + 2, T0, T1, S.u.k.XX, QNEW)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); return rc; }
+        // end-of-step point, kwt_route.f90:288-292: flow on lane 0, entry time on lane 1 (one division each)
+        double Q_END, TIMEI;
+        {
+            const int L1 = MR_NL > 1 ? 1 : 0;
+            const double *A = (lane == L1 && MR_NL > 1) ? S.TE : S.Q;
+            const double v = A[NR] + ((A[NR + 1] - A[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+            Q_END = team_bcast(v, 0);
+            if (MR_NL > 1) TIMEI = team_bcast(v, L1);
+            else TIMEI = S.TE[NR] + ((S.TE[NR + 1] - S.TE[NR]) / (S.TX[NR + 1] - S.TX[NR])) * (T1 - S.TX[NR]);
+        }
+        if (lane == 0) Qs[p] = QNEW * W + qr1;         // kwt_route.f90:273
+
+        // KWAVE(0:NQ2+1) = routed(0:NR) | end-of-step point | non-routed(NR+1:NQ2), kwt_route.f90:299-311
+        const size_t row = (size_t)p * KWP;
+        double *oQ = d.kwQF[b] + row, *oI = d.kwTI[b] + row, *oR = d.kwTR[b] + row;
+        MR_NOUNROLL
+        for (int i = lane; i <= NQ2; i += MR_NL) {
+            const int j = i <= NR ? i : i + 1;
+            oQ[j] = S.Q[i]; oI[j] = S.TE[i]; oR[j] = S.TX[i];
+        }
+        if (d.expSlot) {                               // tributary outlet: leave this step's wave for the mainstem domain
+            const int slot = d.expSlot[p];
+            if (slot >= 0) {
+                double *rec = d.expBuf + ((size_t)slot * d.kmax + t) * d.recLen + d.nRoutes + 1;
+                MR_NOUNROLL
+                for (int i = lane; i <= NQ2; i += MR_NL) {
+                    const int j = i <= NR ? i : i + 1;
+                    rec[2 + j] = S.Q[i]; rec[2 + KWP + j] = S.TX[i];
+                }
+                if (lane == 0) { rec[0] = (double)(NQ2 + 2); rec[1] = (double)(NR + 2); rec[2 + NR + 1] = Q_END; rec[2 + KWP + NR + 1] = T1; }
+            }
+        }
+        if (lane == 0) {
+            oQ[NR + 1] = Q_END; oI[NR + 1] = TIMEI; oR[NR + 1] = T1;
+            d.kwN[b][p] = NQ2 + 2;
+            d.kwNR[b][p] = NR + 2;
+            if (d.kwCount) d.kwCount[p] += (unsigned)(nOwn + ND_read + NQ2 + 2);
+        }
     }
-    return 0;
+    return rc;
 }
 
 }  // namespace mr

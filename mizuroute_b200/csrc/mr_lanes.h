@@ -12,8 +12,8 @@
 
 #if defined(__CUDACC__)
 #ifndef MR_TEAM
-#define MR_TEAM 32                       // lanes per team: 32 = a whole warp, 16 = two teams per warp (measured: the
-                                         // two teams of a warp rarely stay converged, so 16 is not faster)
+#define MR_TEAM 16                       // lanes per team: 32 = a whole warp, 16 = two teams per warp (they re-converge at the
+                                         // phase boundaries of a task, MR_WSYNC)
 #endif
 #define MR_DEV __device__ __forceinline__
 #define MR_DEV_NOINLINE __device__ __noinline__
@@ -22,6 +22,12 @@
 // lanes of this thread's team within its warp
 #define MR_TMASK (MR_TEAM == 32 ? 0xffffffffu : (((1u << (MR_TEAM & 31)) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(MR_TEAM - 1))))
 #define MR_SYNC() __syncwarp(MR_TMASK)
+// all 32 lanes of the warp (every team of it): reconvergence point between the phases of a task
+#if MR_TEAM < 32
+#define MR_WSYNC() __syncwarp()
+#else
+#define MR_WSYNC() ((void)0)
+#endif
 #define MR_NOUNROLL _Pragma("unroll 1")
 #else
 #define MR_DEV inline
@@ -29,6 +35,7 @@
 #define MR_LANE 0
 #define MR_NL 1
 #define MR_SYNC() ((void)0)
+#define MR_WSYNC() ((void)0)
 #define MR_NOUNROLL
 #endif
 
