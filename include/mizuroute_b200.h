@@ -134,6 +134,8 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
 int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message);
 int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
 int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
+/* BASIN_QR(1) ("dlayRunoff", the hillslope-routed lateral inflow) of the last batch as [nSteps][nRch] */
+int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message);
 /* mr_route_resident without the final wait: the kernels are enqueued on the handle's stream and the call returns,
  * so a caller can keep several domains (tributaries of the next batch, mainstem of this one) in flight on
  * different streams.  mr_wait blocks until the stream is idle and reports a device-side error (ierr, message). */

@@ -557,6 +557,20 @@ int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message) {
     return 0;
 }
 
+int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message) {
+    const char *where = "mr_download_basin_q";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!qr_out) return fail(message, 1, "mr_download_basin_q/null output");
+    if (nSteps > h->lastK) return fail(message, 1, "mr_download_basin_q/more steps requested than the last batch routed");
+    const int N = h->d.nRch;
+    dim3 grid((N + 255) / 256, nSteps < 64 ? nSteps : 64);
+    k_unpermute_rows<<<grid, 256, 0, h->stream>>>(h->d.qrSer + N, h->dOut, h->dRch2pos, N, nSteps);      // rows 1..nSteps = BASIN_QR(1) after each step
+    CU(cudaMemcpyAsync(qr_out, h->dOut, sizeof(double) * (size_t)nSteps * N, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
 int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message) {
     const char *where = "mr_step_batch";
     int e = check_ready(h, nSteps, where, message); if (e) return e;

@@ -15,7 +15,7 @@
 // Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
-// <dt_qsim> must equal the forcing interval, one history file, output every step, standard /
+// <dt_qsim> must equal the forcing interval, one history file, <outputFrequency> = n steps or daily, standard /
 // proleptic_gregorian / noleap calendars.  <is_remap> T: 1-D polygon forcing only (remap_1D_runoff), remapped on the device.
 #include <algorithm>
 #include <cmath>
@@ -406,9 +406,18 @@ int main(int argc, char **argv) {
         const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
         const char *vname[3] = {"sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"};
         const char *lname[3] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking"};
+        // <outputFrequency>: every step, a number of steps, or "daily"; fluxes are averaged over the period
+        // (histVars_data.f90:154-246) and stamped with the start of the period
+        int nAgg = 1;
+        { const std::string of = lower(c.str("outputFrequency", "1"));
+          if (of == "daily") { if (std::fmod(86400.0, o.dt) != 0.0) die(20, "route_runoff/<outputFrequency> daily needs dt_qsim to divide 86400 s"); nAgg = (int)std::lround(86400.0 / o.dt); }
+          else { char *e; const long v = std::strtol(of.c_str(), &e, 10); if (e == of.c_str() || v < 1) die(20, "route_runoff/<outputFrequency> " + of + ": only an integer number of steps or 'daily' is supported by this host"); nAgg = (int)v; } }
+        const bool wantDlay = c.flag("dlayRunoff", true);
+        int vDlay = -1;
         std::vector<int> vQ(o.n_routes, -1);
         for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
             vQ[r] = w.def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
+        if (wantDlay) vDlay = w.def_var("dlayRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "delayed runoff in each reach"}});
         w.global_attr("title", "mizuRoute routing (mizuroute-b200)");
         w.end_def();
         w.put_int(vId, segId.data());
@@ -416,12 +425,13 @@ int main(int argc, char **argv) {
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
         const size_t inCols = isRemap ? nForcing : nHRU;
         std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch), rec;
+        std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
+        int nAcc = 0; size_t recOut = 0; double tAcc = 0.0;
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
             T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
-        const double Tfirst = T0;
         double fillv = c.num("input_fillvalue", -9999.0);
         for (size_t s = 0; s < nSteps; s += batch) {
             const int nb = (int)std::min<size_t>(batch, nSteps - s);
@@ -439,10 +449,25 @@ int main(int argc, char **argv) {
                 for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
             }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
+            if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             for (int k = 0; k < nb; ++k) {
-                const double tsec = (Tfirst - std::floor(Tfirst / o.dt + 0.5) * o.dt) + (double)(s + k) * o.dt;      // seconds since <sim_start>
-                w.put_record(vTime, s + k, &tsec);
-                for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);
+                const double tsec = (double)(s + k) * o.dt;                                                          // seconds since <sim_start>
+                if (nAgg == 1) {
+                    w.put_record(vTime, s + k, &tsec);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);
+                    if (vDlay >= 0) w.put_record(vDlay, s + k, &qd[(size_t)k * nRch]);
+                    continue;
+                }
+                if (nAcc == 0) { tAcc = tsec; std::fill(acc.begin(), acc.end(), 0.0); }
+                for (int r = 0; r < o.n_routes; ++r) for (size_t i = 0; i < nRch; ++i) acc[(size_t)r * nRch + i] += q[((size_t)r * nb + k) * nRch + i];
+                if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
+                if (++nAcc == nAgg || s + k + 1 == nSteps) {
+                    for (auto &v : acc) v /= (double)nAcc;
+                    w.put_record(vTime, recOut, &tAcc);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], recOut, &acc[(size_t)r * nRch]);
+                    if (vDlay >= 0) w.put_record(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
+                    ++recOut; nAcc = 0;
+                }
             }
             T0 += nb * o.dt;
         }

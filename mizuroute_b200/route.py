@@ -152,6 +152,12 @@ class Router:
         self._check(self._L.mr_download_q(self._h, int(K), op, self._msg))
         return out
 
+    def download_basin_q(self, K: int) -> np.ndarray:
+        """BASIN_QR(1) (hillslope-routed lateral inflow, the reference's `dlayRunoff`) of the last batch, [K, nRch]."""
+        out = np.empty((int(K), self.nRch))
+        self._check(self._L.mr_download_basin_q(self._h, int(K), C.c_void_p(out.ctypes.data), self._msg))
+        return out
+
     @staticmethod
     def _host_ptr(a, ncol: int, rows: Optional[int] = None):
         if hasattr(a, "data_ptr"):                               # torch tensor (pinned host memory)

@@ -98,3 +98,26 @@ def test_exact_restart(tmp_path):
     h_second = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     for v in ("sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"):
         assert np.array_equal(np.concatenate([h_first[v], h_second[v]]), h_full[v]), v
+
+
+@pytest.mark.gpu
+def test_daily_mean_output_and_delayed_runoff(tmp_path):
+    """<outputFrequency> daily on an hourly run: every history record is the mean of 24 steps (histVars_data.f90:154-246);
+    dlayRunoff = BASIN_QR(1)."""
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("random", n=120, seed=2, dt=3600.0, route_opt="1", steps=60)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="agg", output_frequency="daily")
+    r = subprocess.run([_host(), ctl, "--batch", "25"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    o = Oracle(net, params, opts)
+    q, qr = [], []
+    for t in range(60):
+        o.step(ro[t]); q.append(o.get(orc.F_REACH_Q, orc.M_IRF)); qr.append(o.get(orc.F_BASIN_QR1))
+    q, qr = np.array(q), np.array(qr)
+    want_q = np.stack([q[0:24].mean(0), q[24:48].mean(0), q[48:60].mean(0)])
+    want_r = np.stack([qr[0:24].mean(0), qr[24:48].mean(0), qr[48:60].mean(0)])
+    assert np.array_equal(out["time"], np.array([0.0, 86400.0, 172800.0]))
+    np.testing.assert_allclose(out["IRFroutedRunoff"], want_q, rtol=3e-6, atol=1e-30)
+    np.testing.assert_allclose(out["dlayRunoff"], want_r, rtol=3e-6, atol=1e-30)
