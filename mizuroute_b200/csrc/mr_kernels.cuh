@@ -4,17 +4,21 @@
 //
 // Layout (all arrays in "stage order", see mr_topo.h; N = nRch):
 //   per-reach scalars      x[p]
-//   windows / particles    x[k*N + p]            (slot-major: thread-per-reach accesses are coalesced)
+//   UH windows             x[k*N + p]            (slot-major: thread-per-reach accesses are coalesced)
 //   per-step series        x[t*N + p]
+//   KWT wave particles     x[p*KWP + k]          (reach-major rows of 192 B, read by the team that routes the reach)
 //
 // Kernels
 //   k_basin       K1 basin2reach (process_remap.f90:372-420) fused with K2 hillslope UH
-//                 (basinUH.f90:94-176) for all steps of a batch; the UH window is a ring (no shift copy),
-//                 staged in shared memory when it fits so a batch reads/writes it once
-//   k_route<M>    one time-skewed wavefront of route_network (main_route.f90:356-403):
+//                 (basinUH.f90:94-176) for all steps of a batch; the UH window is a ring (no shift copy)
+//                 walked once per 64-step chunk
+//   k_remap       remap_1D_runoff (process_remap.f90:164-262), optional
+//   k_headwater<M>  reaches without upstream reaches, all steps of the batch in one launch
+//   k_route<M>    one time-skewed wavefront of route_network (main_route.f90:356-403), thread per (reach, step):
 //                 M=0 accum_inst_runoff (accum_runoff.f90:60-75), M=1 irf_rch+conv_upsbas_qr
-//                 (irf_route.f90:82-150,235-262), M=2 kwt_rch and callees (kwt_route.f90:36-1622);
-//                 lake reaches branch to lake_route (lake_route.f90:87-229)
+//                 (irf_route.f90:82-150,235-262); lake reaches branch to lake_route (lake_route.f90:87-229)
+//   k_route_kwt   the same for kwt_rch and callees (kwt_route.f90:36-1622), half-warp team per (reach, step)
+//   k_export_pack / k_import_unpack   tributary -> mainstem hand-off records (mpi_process.f90:1238-1329)
 #pragma once
 #include "mr_dev.h"
 #include "mr_kwt.cuh"

@@ -1,15 +1,17 @@
-// Warp-cooperative kinematic-wave-tracking reach step: kwt_rch and callees, kwt_route.f90:36-1622.
+// Team-cooperative kinematic-wave-tracking reach step: kwt_rch and callees, kwt_route.f90:36-1622.
 //
-// One team (MR_TEAM lanes of a warp on the device, see mr_lanes.h) routes one (reach, step).  The wave particles of
-// the reach live in the team's shared-memory scratch, one particle per lane:
+// One team (MR_TEAM = 16 lanes, half a warp, on the device; see mr_lanes.h) routes one (reach, step); the two teams of
+// a warp re-converge at the phase boundaries of their tasks (kwt_reach_team).  The wave particles of the reach live
+// in the team's shared-memory scratch, one particle per lane:
 //   getusq_rch/qexmul_rch  every candidate exit time of the upstream series is ranked and evaluated by its own
 //                          lane (the reference's sequential k-way MINLOC merge, :895-976, visits candidates in
 //                          (time, series) order; rank, duplicate flag and interpolation brackets of a candidate
 //                          are functions of that order alone, so they are computed independently);
 //   remove_rch             lane-parallel error evaluation, team argmin ("first minimum", :1081) per removal;
 //   kinwav_rch             lane-parallel celerity (pow), crossing points and exit times; team argmin per shock
-//                          merge; the short order-dependent tails (rUpdate's +1 s fix-up, interp_rch) run on
-//                          lane 0 exactly as the reference's serial loops.
+//                          merge; exit times are final in parallel unless rUpdate's +1 s fix-up applies, in which case
+//                          (and for merged particles) the order-dependent emission runs on lane 0 as the reference's
+//                          serial loop; interp_rch's trapezoids are evaluated by the lanes and added in order by lane 0.
 // Every floating-point value is produced by the same operations on the same operands as the serial
 // restatement, so results do not depend on the lane count.
 //
