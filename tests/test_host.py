@@ -55,6 +55,30 @@ def test_netcdf3_writer_roundtrip_through_scipy(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_reader_accepts_classic_cdf1_and_rejects_netcdf4(tmp_path):
+    """NetCDF-3 classic (CDF-1, 32-bit offsets) network file is read like the 64-bit-offset one; an HDF5 (netCDF-4)
+    file is refused with a clear message."""
+    from scipy.io import netcdf_file
+    net, params, opts, ro = case("random", n=30, seed=8, dt=86400.0, route_opt="1", steps=3)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="cdf1")
+    path = os.path.join(str(tmp_path), "ancillary", "ntopo.nc")
+    f = netcdf_file(path, "w", version=1)                   # rewrite the network as CDF-1
+    f.createDimension("seg", net.nRch); f.createDimension("hru", net.nHRU)
+    for nm, dat, dim, typ in (("segId", net.segId, "seg", "i"), ("downSegId", net.downSegId, "seg", "i"), ("length", net.length, "seg", "d"),
+                              ("slope", net.slope.astype(np.float32), "seg", "f"), ("HRUid", net.hruId, "hru", "i"),
+                              ("hruSegId", net.hruSegId, "hru", "i"), ("area", net.area, "hru", "d")):
+        v = f.createVariable(nm, typ, (dim,)); v[:] = dat
+    f.close()
+    assert open(path, "rb").read(4) == b"CDF\x01"
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[0])["nRch"] == net.nRch
+    with open(path, "wb") as fh:
+        fh.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "netCDF-4/HDF5 is not supported" in r.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("route,dt,lakes", [("012", 3600.0, 0), ("12", 86400.0, 5)])
 def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
