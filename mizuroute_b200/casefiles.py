@@ -65,9 +65,12 @@ def _stamp(seconds: float, start: str) -> str:
 
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
-               fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1") -> str:
+               fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1", forcing_dt=None, sim_steps=None,
+               ro_time_stamp=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
-    continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`."""
+    continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`.  `forcing_dt` != dt_qsim
+    writes the runoff records on their own interval (`sim_steps` simulation steps of opts.dt are then asked for);
+    `ro_time_stamp` = start|middle|end shifts the record time stamps within their interval."""
     t_first = _stamp(first_step * opts.dt, start)
     anc, inp, out = (os.path.join(case_dir, d) + "/" for d in ("ancillary", "input", "output"))
     for d in (anc, inp, out):
@@ -87,12 +90,18 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
     elif shuffle_hru_seed is not None:                       # forcing HRUs in a different order than the network's
         perm = np.random.default_rng(shuffle_hru_seed).permutation(net.nHRU)
         ids, ro = ids[perm], runoff[:, perm]
-    K = runoff.shape[0]
-    if split_forcing <= 1:
+    K = runoff.shape[0] if sim_steps is None else sim_steps
+    dt_ro = opts.dt if forcing_dt is None else float(forcing_dt)
+    if forcing_dt is not None or ro_time_stamp is not None:
+        assert split_forcing <= 1 and first_step == 0
+        shift = {None: 0.0, "start": 0.0, "middle": 0.5, "end": 1.0}[ro_time_stamp]
+        write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, dt_ro, start, t_offset_steps=shift)
+        fname_qsim = "runoff_%s.nc" % case_name
+    elif split_forcing <= 1:
         write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, opts.dt, start, t_offset_steps=first_step)
         fname_qsim = "runoff_%s.nc" % case_name
     else:
-        bounds = np.linspace(0, K, split_forcing + 1).astype(int)
+        bounds = np.linspace(0, runoff.shape[0], split_forcing + 1).astype(int)
         names = []
         for i in range(split_forcing):
             nm = "runoff_%02d.nc" % i
@@ -127,7 +136,8 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("dname_time", "time", "time dimension"),
         ("dname_hruid", "hru", "HRU dimension"),
         ("units_qsim", opts.units_qsim, "units of runoff"),
-        ("dt_ro", int(opts.dt), "forcing interval [sec]"),
+        ("dt_ro", int(dt_ro), "forcing interval [sec]"),
+        ("ro_time_stamp", ro_time_stamp or "start", "time stamp of a forcing record within its interval"),
         ("is_remap", "T" if remap is not None else "F", "runoff remapping"),
         ("fname_remap", "remap.nc", "runoff mapping netCDF"),
         ("vname_hruid_in_remap", "RN_hruId", "river-network HRU ids in the mapping"),

@@ -1,7 +1,7 @@
 // route_runoff -- stand-alone host of the B200 routing library, the counterpart of the reference's
 // PROGRAM route_runoff (route/build/src/standalone/route_runoff.f90:5-117):
 //
-//     route_runoff <control file> [--batch N] [--dry-run]
+//     route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE]]
 //
 //   init_model      read_control (read_control.f90:18: lines "<key> value ! comment", '!' comment lines, unknown key =
 //                   error) and the parameter namelist &HSLOPE/&IRF_UH/&KWT (read_param.f90:12)
@@ -15,7 +15,7 @@
 // Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
-// <dt_qsim> must equal the forcing interval, one history file, <outputFrequency> = n steps or daily, standard /
+// one history file, <outputFrequency> = n steps or daily, standard /
 // proleptic_gregorian / noleap calendars.  <is_remap> T: 1-D polygon forcing only (remap_1D_runoff), remapped on the device.
 #include <algorithm>
 #include <cmath>
@@ -253,12 +253,13 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE]]\n"); return 2; }
     const std::string cfile = argv[1];
-    int batch = 64; bool dry = false;
+    int batch = 64; bool dry = false; std::string dumpForcing;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--dry-run")) dry = true;
+        else if (!std::strcmp(argv[i], "--dump-forcing") && i + 1 < argc) dumpForcing = argv[++i];
         else die(2, std::string("unknown argument ") + argv[i]);
     }
     if (batch < 1) die(2, "--batch must be >= 1");
@@ -347,15 +348,49 @@ int main(int argc, char **argv) {
         }
         std::vector<double> tAll; std::vector<std::pair<int, size_t>> where;    // (file, record) of every forcing time
         for (size_t k = 0; k < files.size(); ++k) for (size_t i = 0; i < files[k].nTime; ++i) { tAll.push_back(files[k].tsec[i]); where.push_back({(int)k, i}); }
+        // ---- init_time (model_setup.f90:404-566): forcing interval and period, simulation period clipped to the forcing
+        double dtro = c.num("dt_ro", o.dt);                        // a single record: <dt_ro>, else <dt_qsim>
         if (tAll.size() >= 2) {
-            const double dtro = tAll[1] - tAll[0];                // dt_ro is taken from the file (model_setup.f90:502)
-            if (std::fabs(dtro - o.dt) > 1e-6 * o.dt) die(20, "route_runoff/forcing interval " + std::to_string(dtro) + " s differs from <dt_qsim>: temporal remapping is not supported by this host");
+            dtro = tAll[1] - tAll[0];                              // dt_ro is taken from the file (model_setup.f90:502)
+            if (!(dtro > 0.0)) die(20, "init_time/forcing times are not increasing");
+            for (size_t i = 2; i < tAll.size(); ++i)               // maxTimeDiff = 1 s, public_var.f90:28
+                if (std::fabs((tAll[i] - tAll[i - 1]) - dtro) > 1.0) die(20, "init_time/make sure the input netCDF files do not have time overlaps or gaps");
         }
-        const double tStart = parse_datetime(c.need("sim_start"), noleap), tEnd = parse_datetime(c.need("sim_end"), noleap);
-        size_t i0 = 0; while (i0 < tAll.size() && tAll[i0] < tStart - 1e-3) ++i0;
-        size_t i1 = i0; while (i1 < tAll.size() && tAll[i1] <= tEnd + 1e-3) ++i1;
-        if (i1 <= i0) die(20, "init_time/no forcing record between <sim_start> and <sim_end>");
-        const size_t nSteps = i1 - i0;
+        const std::string stampAt = lower(c.str("ro_time_stamp", "start"));
+        if (stampAt != "start" && stampAt != "end" && stampAt != "middle") die(20, "read_control/Input time stamp <ro_time_stamp> must be start, end, or middle");
+        const size_t nRo = tAll.size();
+        if (nRo == 0) die(20, "init_time/the forcing files hold no time record");
+        const double roBeg = tAll[0] - (stampAt == "end" ? dtro : stampAt == "middle" ? 0.5 * dtro : 0.0), roEnd = roBeg + (double)nRo * dtro;
+        const double tStartAsked = parse_datetime(c.need("sim_start"), noleap);
+        double tStart = tStartAsked, tEnd = parse_datetime(c.need("sim_end"), noleap);
+        if (tEnd < tStart) die(20, "init_time/simulation end is before simulation start");
+        if (tStart > roEnd) die(20, "init_time/check <sim_start> against runoff input time");
+        if (tStart < roBeg) { std::fprintf(stderr, "WARNING: <sim_start> is before the first time step in input runoff; reset to runoff_start\n"); tStart = roBeg; }
+        if (tEnd > roEnd) { std::fprintf(stderr, "WARNING: <sim_end> is after the last time step in input runoff; reset to runoff_end\n"); tEnd = roEnd; }
+        // update_time (init_model_data.f90:284-326): the step that starts at or after <sim_end> is the last one.  Steps
+        // the forcing does not cover completely are not run (the reference's map is undefined there).
+        const double tolT = 1e-6;
+        size_t nSteps = (size_t)std::ceil((tEnd - tStart) / o.dt - tolT) + 1;
+        { const size_t nCovered = (size_t)std::floor((roEnd - tStart) / o.dt + tolT); if (nSteps > nCovered) nSteps = nCovered; }
+        if (nSteps == 0) die(20, "init_time/no forcing record between <sim_start> and <sim_end>");
+        // timeMap_sim_forc (get_basin_runoff.f90:256-369): forcing records under simulation step k and their weights.
+        // One record (dt_qsim <= dt_ro, step inside a record): that record, no weight.
+        struct TimeMap { std::vector<size_t> rec; std::vector<double> frac; };
+        auto time_map = [&](size_t k) {
+            TimeMap m;
+            const double sim1 = (tStart - roBeg) + (double)k * o.dt, sim2 = sim1 + o.dt;
+            size_t front = (size_t)std::floor(sim1 / dtro + tolT);                       // first record whose end is after sim1
+            double e = std::ceil(sim2 / dtro - tolT) - 1.0; if (e < 0.0) e = 0.0;    // first record whose end is at or after sim2
+            size_t end = (size_t)e;
+            if (end > nRo - 1) end = nRo - 1;
+            if (front > end) die(30, "timeMap_sim_forc/index of idxFront lower than idxEnd");
+            for (size_t r = front; r <= end; ++r) {
+                m.rec.push_back(r);
+                if (front == end) break;
+                m.frac.push_back(r == front ? ((double)(r + 1) * dtro - sim1) / o.dt : r == end ? (sim2 - (double)r * dtro) / o.dt : dtro / o.dt);
+            }
+            return m; };
+        const size_t i0 = time_map(0).rec[0];
 
         // sort_flux index: forcing HRU -> network HRU (process_remap.f90:271-311)
         std::vector<int> ix(roHruId.size(), -1);
@@ -365,7 +400,53 @@ int main(int argc, char **argv) {
         std::printf("{\"case\": \"%s\", \"nRch\": %zu, \"nHRU\": %zu, \"nHRU_forcing\": %zu, \"nSteps\": %zu, \"dt\": %.1f, \"route_opt\": \"%s\", \"first_record\": %zu, "
                     "\"fshape\": %.6g, \"tscale\": %.6g, \"velo\": %.6g, \"diff\": %.6g, \"mann_n\": %.6g, \"wscale\": %.6g, \"time_conv\": %.9g, \"length_conv\": %.9g}\n",
                     c.str("case_name", "case").c_str(), nRch, nHRU, roHruId.size(), nSteps, o.dt, ropt.c_str(), i0, o.fshape, o.tscale, o.velo, o.diff, o.mann_n, o.wscale, o.time_conv, o.length_conv);
-        if (dry) return 0;
+        // get_hru_runoff for simulation step k (get_basin_runoff.f90:19-120): the step's forcing record(s) -> one row of
+        // the library's input (network HRU order, or forcing-polygon order when the device remaps)
+        const size_t nForcing = roHruId.size();
+        const size_t inCols = isRemap ? nForcing : nHRU;
+        std::vector<nc3::Reader *> rd(files.size(), nullptr);
+        std::vector<double> rec, wsum, wtot;
+        double fillv = c.num("input_fillvalue", -9999.0);
+        auto load_step = [&](size_t k, double *dst) {
+            const TimeMap tm = time_map(k);
+            for (size_t j = 0; j < tm.rec.size(); ++j) {
+                const auto wr = where[tm.rec[j]];
+                if (!rd[wr.first]) rd[wr.first] = new nc3::Reader(files[wr.first].path);
+                nc3::Reader &R = *rd[wr.first];
+                const nc3::Var &qv = R.var(vq);
+                double fv; if (R.attr_value(qv, "_FillValue", fv)) fillv = fv;
+                R.read(qv, rec, wr.second, 1);
+                if (rec.size() != nForcing) die(20, "read_runoff/runoff variable is not dimensioned [time, hru]");
+                if (tm.frac.empty()) break;
+                // several records under one step: time-weighted mean over the records that hold a value
+                // (read_1D_forcing, read_runoff.f90:298-325)
+                if (j == 0) { wsum.assign(rec.size(), 0.0); wtot.assign(rec.size(), 0.0); }
+                for (size_t i = 0; i < rec.size(); ++i) if (rec[i] != fillv) { wsum[i] += rec[i] * tm.frac[j]; wtot[i] += tm.frac[j]; }
+            }
+            if (!tm.frac.empty())
+                for (size_t i = 0; i < rec.size(); ++i) rec[i] = wtot[i] == 0.0 ? fillv : (wtot[i] < 1.0 ? wsum[i] / wtot[i] : wsum[i]);
+            if (isRemap) { for (size_t i = 0; i < rec.size(); ++i) dst[i] = rec[i] == fillv ? -9999.0 : rec[i]; return; }  // remapped on the device; realMissing (< 0) is skipped there
+            std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
+            for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
+        };
+
+        if (dry) {                                                       // the time map of the first steps, for inspection
+            std::printf("{\"dt_ro\": %.3f, \"ro_time_stamp\": \"%s\", \"time_map\": [", dtro, stampAt.c_str());
+            for (size_t k = 0; k < std::min<size_t>(nSteps, 6); ++k) {
+                const TimeMap m = time_map(k);
+                std::printf("%s[", k ? ", " : "");
+                for (size_t j = 0; j < m.rec.size(); ++j) std::printf("%s[%zu, %.9g]", j ? ", " : "", m.rec[j], m.frac.empty() ? 1.0 : m.frac[j]);
+                std::printf("]");
+            }
+            std::printf("]}\n");
+            if (!dumpForcing.empty()) {                                   // raw float64 [nSteps][columns]: what the time loop would feed the library
+                FILE *f = std::fopen(dumpForcing.c_str(), "wb"); if (!f) die(30, "route_runoff/cannot write " + dumpForcing);
+                std::vector<double> row(inCols);
+                for (size_t k = 0; k < nSteps; ++k) { load_step(k, row.data()); if (std::fwrite(row.data(), sizeof(double), inCols, f) != inCols) die(30, "route_runoff/short write to " + dumpForcing); }
+                std::fclose(f);
+            }
+            return 0;
+        }
 
         // ---- device side
         char msg[MR_STRLEN];
@@ -378,7 +459,6 @@ int main(int argc, char **argv) {
         if (ierr) die(ierr, msg);
 
         // ---- runoff remapping (<is_remap> T): mapping netCDF -> device-side remap_1D (read_remap.f90:20-170, process_remap.f90:164-262)
-        const size_t nForcing = roHruId.size();
         if (isRemap) {
             nc3::Reader rm(join_path(ancil, c.need("fname_remap")));
             std::vector<int> mapId, numQ, qId; std::vector<double> wgt;
@@ -423,35 +503,20 @@ int main(int argc, char **argv) {
         w.put_int(vId, segId.data());
 
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
-        const size_t inCols = isRemap ? nForcing : nHRU;
-        std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch), rec;
+        std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
         int nAcc = 0; size_t recOut = 0; double tAcc = 0.0;
-        std::vector<nc3::Reader *> rd(files.size(), nullptr);
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
             T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
-        double fillv = c.num("input_fillvalue", -9999.0);
         for (size_t s = 0; s < nSteps; s += batch) {
             const int nb = (int)std::min<size_t>(batch, nSteps - s);
-            for (int k = 0; k < nb; ++k) {
-                const auto wr = where[i0 + s + k];
-                if (!rd[wr.first]) rd[wr.first] = new nc3::Reader(files[wr.first].path);
-                nc3::Reader &R = *rd[wr.first];
-                const nc3::Var &qv = R.var(vq);
-                double fv; if (R.attr_value(qv, "_FillValue", fv)) fillv = fv;
-                R.read(qv, rec, wr.second, 1);
-                if (rec.size() != roHruId.size()) die(20, "read_runoff/runoff variable is not dimensioned [time, hru]");
-                double *dst = &ro[(size_t)k * inCols];
-                if (isRemap) { std::copy(rec.begin(), rec.end(), dst); continue; }  // remapped on the device (fill values are < -1e-6: skipped there)
-                std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
-                for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
-            }
+            for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             for (int k = 0; k < nb; ++k) {
-                const double tsec = (double)(s + k) * o.dt;                                                          // seconds since <sim_start>
+                const double tsec = (tStart - tStartAsked) + (double)(s + k) * o.dt;                                                       // seconds since <sim_start>
                 if (nAgg == 1) {
                     w.put_record(vTime, s + k, &tsec);
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);

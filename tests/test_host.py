@@ -41,9 +41,84 @@ def test_control_file_errors(tmp_path):
     bad.write_text(txt + "<is_flux_wm>   T   ! water management is not on this path\n")
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode != 0 and "water management" in r.stderr
-    bad.write_text(re.sub(r"(<dt_qsim>\s+)86400", r"\g<1>3600 ", txt))
+    bad.write_text(re.sub(r"(<ro_time_stamp>\s+)start", r"\g<1>front", txt))
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
-    assert r.returncode != 0 and "forcing interval" in r.stderr
+    assert r.returncode != 0 and "must be start, end, or middle" in r.stderr        # read_control.f90:514-518
+
+
+def _time_map(tmp_path, dt, forcing_dt, records, sim_steps, stamp=None, name="tm"):
+    net, params, opts, ro = case("random", n=20, seed=3, dt=dt, route_opt="1", steps=records)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name=name, forcing_dt=forcing_dt, sim_steps=sim_steps, ro_time_stamp=stamp)
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    a, b = (json.loads(x) for x in r.stdout.strip().splitlines()[:2])
+    return a, b
+
+
+def test_time_map_between_simulation_steps_and_forcing_records(tmp_path):
+    """timeMap_sim_forc (get_basin_runoff.f90:256-369): a simulation step inside one record uses that record; a step over
+    several records takes them with their time fractions."""
+    a, b = _time_map(tmp_path, 3600.0, 86400.0, records=3, sim_steps=72, name="fine")        # hourly steps, daily runoff
+    assert a["nSteps"] == 72 and b["dt_ro"] == 86400.0 and b["time_map"] == [[[0, 1.0]]] * 6
+    a, b = _time_map(tmp_path, 86400.0, 3600.0, records=72, sim_steps=3, name="coarse")      # daily steps, hourly runoff
+    assert a["nSteps"] == 3
+    assert [len(m) for m in b["time_map"]] == [24, 24, 24] and [m[0][0] for m in b["time_map"]] == [0, 24, 48]
+    assert all(abs(f - 1.0 / 24.0) < 1e-9 for m in b["time_map"] for _, f in m)
+    a, b = _time_map(tmp_path, 7200.0, 10800.0, records=4, sim_steps=6, name="ragged")       # 2-hourly steps, 3-hourly runoff
+    assert a["nSteps"] == 6
+    want = [[[0, 1.0]], [[0, 0.5], [1, 0.5]], [[1, 1.0]], [[2, 1.0]], [[2, 0.5], [3, 0.5]], [[3, 1.0]]]
+    assert b["time_map"] == want
+    # records stamped at the middle / end of the interval they cover (casefiles shifts the stamps, not the data): same map
+    for stamp in ("middle", "end"):
+        a, b = _time_map(tmp_path, 3600.0, 3600.0, records=5, sim_steps=4, stamp=stamp, name=stamp)
+        assert a["first_record"] == 0 and a["nSteps"] == 4 and b["time_map"] == [[[k, 1.0]] for k in range(4)]
+    # a simulation period longer than the forcing is cut to the steps the forcing covers completely
+    a, b = _time_map(tmp_path, 3600.0, 3600.0, records=5, sim_steps=9, name="clip")
+    assert a["nSteps"] == 5
+
+
+def _dump_forcing(ctl, tmp_path, cols):
+    path = os.path.join(str(tmp_path), "forcing.f64")
+    r = subprocess.run([_host(), ctl, "--dry-run", "--dump-forcing", path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return np.fromfile(path, dtype=np.float64).reshape(-1, cols)
+
+
+@pytest.mark.parametrize("dt,forcing_dt,records,sim_steps", [(3600.0, 3600.0, 12, 12), (3600.0, 10800.0, 10, 30), (10800.0, 3600.0, 36, 12),
+                                                             (7200.0, 10800.0, 8, 12)])
+def test_forcing_rows_fed_to_the_library(tmp_path, dt, forcing_dt, records, sim_steps):
+    """get_hru_runoff on the host side: the rows the time loop hands to mr_step_batch (--dump-forcing) are the forcing
+    records mapped onto the simulation steps (record the step lies in, or the time-weighted mean of the records it spans),
+    in network HRU order, negatives zeroed (sort_flux, process_remap.f90:271-311)."""
+    net, params, opts, ro = case("random", n=60, seed=4, dt=dt, route_opt="1", steps=records)
+    ro = ro.copy(); ro[1, 3] = -2.0                                        # a negative value: removed by sort_flux
+    same = forcing_dt == dt
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="rows", forcing_dt=None if same else forcing_dt,
+                               sim_steps=None if same else sim_steps, split_forcing=3 if same else 1, shuffle_hru_seed=7 if same else None)
+    got = _dump_forcing(ctl, tmp_path, net.nHRU)
+    fine = 1800.0
+    k = int(dt / fine)
+    ro_fine = np.repeat(ro, int(forcing_dt / fine), axis=0)[:sim_steps * k]
+    want = np.maximum(ro_fine.reshape(sim_steps, k, -1).mean(axis=1), 0.0) if not same else np.maximum(ro, 0.0)
+    assert got.shape == want.shape
+    if same or dt < forcing_dt and forcing_dt % dt == 0:
+        assert np.array_equal(got, want)                                     # one record per step: values pass through untouched
+    else:
+        mask = np.ones_like(want, dtype=bool)
+        if forcing_dt < dt: mask[0, 3] = False                              # the -2.0 enters a mean there (weighted like any value)
+        np.testing.assert_allclose(got[mask], want[mask], rtol=1e-14)
+
+
+def test_forcing_fill_values_are_skipped_in_the_time_mean(tmp_path):
+    """read_1D_forcing (read_runoff.f90:312-322): records holding the fill value drop out of a step's mean and the
+    remaining weights are renormalised; all records missing -> missing -> 0 after sort_flux."""
+    net, params, opts, ro = case("random", n=30, seed=5, dt=10800.0, route_opt="1", steps=12)
+    ro = ro.copy(); ro[0, 2] = -9999.0; ro[3:6, 4] = -9999.0
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="fill", forcing_dt=3600.0, sim_steps=4)
+    got = _dump_forcing(ctl, tmp_path, net.nHRU)
+    want = ro.reshape(4, 3, -1).mean(axis=1)
+    want[0, 2] = ro[1:3, 2].mean(); want[1, 4] = 0.0
+    np.testing.assert_allclose(got, want, rtol=1e-14)
 
 
 def test_netcdf3_writer_roundtrip_through_scipy(tmp_path):
@@ -97,6 +172,27 @@ def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
         got = out[names[c]]
         assert got.dtype == np.float32 and got.shape == (40, net.nRch)       # history is float32 [time, seg]
         np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c != "2" else 1e-4, atol=1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,forcing_dt,records,sim_steps", [(3600.0, 10800.0, 10, 30), (10800.0, 3600.0, 36, 12), (7200.0, 10800.0, 8, 12)])
+def test_host_maps_forcing_records_onto_simulation_steps(tmp_path, dt, forcing_dt, records, sim_steps):
+    """dt_qsim != dt_ro: the host feeds each step the record it lies in, or the time-weighted mean of the records it
+    spans (timeMap_sim_forc + read_1D_forcing); the oracle is run on the runoff averaged the same way here."""
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=300, seed=4, dt=dt, route_opt="12", steps=records)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="tmap", forcing_dt=forcing_dt, sim_steps=sim_steps)
+    r = subprocess.run([_host(), ctl, "--batch", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    fine = 1800.0                                                          # common divisor of every interval used here
+    ro_fine = np.repeat(ro, int(forcing_dt / fine), axis=0)
+    k = int(dt / fine)
+    ro_sim = ro_fine[:sim_steps * k].reshape(sim_steps, k, -1).mean(axis=1)
+    qo = Oracle(net, params, opts).run(ro_sim)
+    assert out["IRFroutedRunoff"].shape == (sim_steps, net.nRch)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=3e-6, atol=1e-30)
+    np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
 
 
 @pytest.mark.gpu

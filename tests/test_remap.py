@@ -104,3 +104,19 @@ def test_host_reads_reference_style_mapping_file(tmp_path):
     qo = Oracle(net, params, opts).run(ro_net)
     np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
     np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+def test_host_passes_polygon_forcing_through_for_the_device_remap(tmp_path):
+    """<is_remap> T: the rows the host hands to the library are the forcing polygons' records untouched (the device
+    remaps them), with the fill value turned into realMissing (read_runoff.f90:324) -- checked without a GPU."""
+    from mizuroute_b200 import build as mrbuild, casefiles
+    net, params, opts, _ = case("random", n=50, seed=5, dt=86400.0, route_opt="1", steps=1)
+    nF, K = 40, 5
+    map_ids, num, qid, w, fids = make_mapping(net, nF, seed=3)
+    forcing = np.random.default_rng(1).lognormal(np.log(2e-5), 1.0, size=(K, nF))
+    forcing[2, 7] = -9999.0
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, forcing, case_name="remap", remap=(map_ids, num, qid, w, fids))
+    path = str(tmp_path / "rows.f64")
+    r = subprocess.run([mrbuild.build_host(), ctl, "--dry-run", "--dump-forcing", path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(np.fromfile(path, dtype=np.float64).reshape(K, nF), forcing)
