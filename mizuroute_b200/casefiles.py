@@ -57,6 +57,25 @@ def write_runoff(path: str, hru_ids: np.ndarray, runoff: np.ndarray, dt: float, 
     f.close()
 
 
+def write_runoff_grid(path: str, runoff: np.ndarray, dt: float, start: str = "2000-01-01 00:00:00", fill=None):
+    """Gridded runoff[time, lat, lon] (the layout read_2D_forcing expects, read_runoff.f90:331-396)."""
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("lat", runoff.shape[1])
+    f.createDimension("lon", runoff.shape[2])
+    t = f.createVariable("time", "d", ("time",))
+    t.units = "seconds since " + start
+    t.calendar = "standard"
+    q = f.createVariable("runoff", "d", ("time", "lat", "lon"))
+    q.units = "mm/s"
+    if fill is not None:
+        q._FillValue = float(fill)
+    for k in range(runoff.shape[0]):
+        t[k] = k * dt
+        q[k] = runoff[k]
+    f.close()
+
+
 def _stamp(seconds: float, start: str) -> str:
     import datetime as _dt
     t0 = _dt.datetime.strptime(start, "%Y-%m-%d %H:%M:%S")
@@ -80,7 +99,16 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         f.write("&HSLOPE\n  ! hillslope gamma UH\n  fshape = %r\n  tscale = %r\n/\n&IRF_UH\n  velo = %r\n  diff = %r\n/\n&KWT\n  mann_n = %r\n  wscale = %r\n/\n"
                 % (params.fshape, params.tscale, params.velo, params.diff, params.mann_n, params.wscale))
     ids, ro = net.hruId, runoff
-    if remap is not None:                                   # (map_ids, num_qhru, qhru_ids, weight, forcing_ids): runoff is on forcing polygons
+    grid = remap is not None and isinstance(remap[0], str) and remap[0] == "grid"
+    if grid:                                                # ("grid", map_ids, num_qhru, i_index, j_index, weight): runoff[time, lat, lon]
+        _, map_ids, num_q, i_index, j_index, wgt = remap
+        f = netcdf_file(anc + "remap.nc", "w", version=2)
+        f.createDimension("hru", len(map_ids)); f.createDimension("data", len(wgt))
+        for nm, dat, dim, typ in (("RN_hruId", map_ids, "hru", "i"), ("nOverlaps", num_q, "hru", "i"), ("i_index", i_index, "data", "i"),
+                                  ("j_index", j_index, "data", "i"), ("weight", wgt, "data", "d")):
+            v = f.createVariable(nm, typ, (dim,)); v[:] = dat
+        f.close()
+    elif remap is not None:                                 # (map_ids, num_qhru, qhru_ids, weight, forcing_ids): runoff is on forcing polygons
         map_ids, num_q, q_ids, wgt, ids = remap
         f = netcdf_file(anc + "remap.nc", "w", version=2)
         f.createDimension("hru", len(map_ids)); f.createDimension("data", len(q_ids))
@@ -92,7 +120,11 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ids, ro = ids[perm], runoff[:, perm]
     K = runoff.shape[0] if sim_steps is None else sim_steps
     dt_ro = opts.dt if forcing_dt is None else float(forcing_dt)
-    if forcing_dt is not None or ro_time_stamp is not None:
+    if grid:
+        assert split_forcing <= 1 and first_step == 0
+        write_runoff_grid(inp + "runoff_%s.nc" % case_name, runoff, dt_ro, start)
+        fname_qsim = "runoff_%s.nc" % case_name
+    elif forcing_dt is not None or ro_time_stamp is not None:
         assert split_forcing <= 1 and first_step == 0
         shift = {None: 0.0, "start": 0.0, "middle": 0.5, "end": 1.0}[ro_time_stamp]
         write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, dt_ro, start, t_offset_steps=shift)
@@ -146,6 +178,10 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("vname_num_qhru", "nOverlaps", "overlapping polygons per river-network HRU"),
         ("dname_hru_remap", "hru", "mapping HRU dimension"),
         ("dname_data_remap", "data", "mapping data dimension"),
+        ("vname_i_index", "i_index", "x (lon) index of the overlapping grid cells, 1-based"),
+        ("vname_j_index", "j_index", "y (lat) index of the overlapping grid cells, 1-based"),
+        ("dname_xlon", "lon", "x dimension of gridded runoff"),
+        ("dname_ylat", "lat", "y dimension of gridded runoff"),
         ("param_nml", "param.nml", "spatially constant parameters"),
         ("restart_write", restart_write, "restart write option"),
         ("fname_state_in", fname_state_in, "input restart netCDF ('coldstart' = none)"),

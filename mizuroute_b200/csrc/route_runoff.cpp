@@ -1,7 +1,7 @@
 // route_runoff -- stand-alone host of the B200 routing library, the counterpart of the reference's
 // PROGRAM route_runoff (route/build/src/standalone/route_runoff.f90:5-117):
 //
-//     route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE]]
+//     route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]
 //
 //   init_model      read_control (read_control.f90:18: lines "<key> value ! comment", '!' comment lines, unknown key =
 //                   error) and the parameter namelist &HSLOPE/&IRF_UH/&KWT (read_param.f90:12)
@@ -16,7 +16,7 @@
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
 // one history file, <outputFrequency> = n steps or daily, standard /
-// proleptic_gregorian / noleap calendars.  <is_remap> T: 1-D polygon forcing only (remap_1D_runoff), remapped on the device.
+// proleptic_gregorian / noleap calendars.  <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -253,13 +253,14 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE]]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]\n"); return 2; }
     const std::string cfile = argv[1];
-    int batch = 64; bool dry = false; std::string dumpForcing;
+    int batch = 64; bool dry = false; std::string dumpForcing, dumpRemap;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--dry-run")) dry = true;
         else if (!std::strcmp(argv[i], "--dump-forcing") && i + 1 < argc) dumpForcing = argv[++i];
+        else if (!std::strcmp(argv[i], "--dump-remap") && i + 1 < argc) dumpRemap = argv[++i];
         else die(2, std::string("unknown argument ") + argv[i]);
     }
     if (batch < 1) die(2, "--batch must be >= 1");
@@ -332,8 +333,11 @@ int main(int argc, char **argv) {
             if (paths.empty()) die(20, "inFile_pop/no forcing file listed in " + q);
             for (auto &p : paths) { Forcing f; f.path = p; files.push_back(f); }
         }
-        const std::string vtime = c.need("vname_time"), vq = c.need("vname_qsim"), vhru = c.need("vname_hruid");
+        const std::string vtime = c.need("vname_time"), vq = c.need("vname_qsim");
         bool noleap = false; std::vector<int> roHruId;
+        // the runoff variable is [time, hru] (vector of polygons) or [time, lat, lon] (grid; needs <is_remap> T):
+        // read_forcing_metadata, model_setup.f90:741-775
+        bool grid = false; size_t nLat = 0, nLon = 0;
         for (auto &f : files) {
             nc3::Reader r(f.path);
             const nc3::Var &tv = r.var(vtime);
@@ -344,8 +348,16 @@ int main(int argc, char **argv) {
             std::vector<double> tt; r.read_all(tv, tt);
             f.nTime = tt.size(); f.tsec.resize(tt.size());
             for (size_t i = 0; i < tt.size(); ++i) f.tsec[i] = epoch + tt[i] * scale;
-            if (roHruId.empty()) r.read_int(r.var(vhru), roHruId);
+            const size_t rank = r.var(vq).dimids.size();
+            if (rank != 2 && rank != 3) die(20, "init_runoff_data/ndims of input data invalid");
+            if (rank == 3) {
+                const size_t la = r.dim_len(c.str("dname_ylat", "lat")), lo = r.dim_len(c.str("dname_xlon", "lon"));
+                if (grid && (la != nLat || lo != nLon)) die(20, "inFile_pop/forcing files have different grids");
+                grid = true; nLat = la; nLon = lo;
+            } else if (roHruId.empty()) r.read_int(r.var(c.need("vname_hruid")), roHruId);
         }
+        if (grid && !isRemap) die(20, "init_runoff_data/gridded runoff needs <is_remap> T and a mapping file with i_index/j_index");
+        const size_t nForcing = grid ? nLat * nLon : roHruId.size();
         std::vector<double> tAll; std::vector<std::pair<int, size_t>> where;    // (file, record) of every forcing time
         for (size_t k = 0; k < files.size(); ++k) for (size_t i = 0; i < files[k].nTime; ++i) { tAll.push_back(files[k].tsec[i]); where.push_back({(int)k, i}); }
         // ---- init_time (model_setup.f90:404-566): forcing interval and period, simulation period clipped to the forcing
@@ -393,16 +405,50 @@ int main(int argc, char **argv) {
         const size_t i0 = time_map(0).rec[0];
 
         // sort_flux index: forcing HRU -> network HRU (process_remap.f90:271-311)
-        std::vector<int> ix(roHruId.size(), -1);
+        std::vector<int> ix(nForcing, -1);
         { std::vector<std::pair<int, int>> tab(nHRU); for (size_t i = 0; i < nHRU; ++i) tab[i] = {hruId[i], (int)i}; std::sort(tab.begin(), tab.end());
           for (size_t i = 0; i < roHruId.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(roHruId[i], -1)); if (it != tab.end() && it->first == roHruId[i]) ix[i] = it->second; } }
 
         std::printf("{\"case\": \"%s\", \"nRch\": %zu, \"nHRU\": %zu, \"nHRU_forcing\": %zu, \"nSteps\": %zu, \"dt\": %.1f, \"route_opt\": \"%s\", \"first_record\": %zu, "
                     "\"fshape\": %.6g, \"tscale\": %.6g, \"velo\": %.6g, \"diff\": %.6g, \"mann_n\": %.6g, \"wscale\": %.6g, \"time_conv\": %.9g, \"length_conv\": %.9g}\n",
-                    c.str("case_name", "case").c_str(), nRch, nHRU, roHruId.size(), nSteps, o.dt, ropt.c_str(), i0, o.fshape, o.tscale, o.velo, o.diff, o.mann_n, o.wscale, o.time_conv, o.length_conv);
+                    c.str("case_name", "case").c_str(), nRch, nHRU, nForcing, nSteps, o.dt, ropt.c_str(), i0, o.fshape, o.tscale, o.velo, o.diff, o.mann_n, o.wscale, o.time_conv, o.length_conv);
+        // ---- runoff remapping (<is_remap> T): mapping netCDF -> index form for the device-side remap (read_remap.f90:20-170,
+        // process_remap.f90:59-262).  A gridded forcing is the same weighted sum over a flattened [lat][lon] record.
+        std::vector<int> mapHruIx, mapNumQ, mapQIx; std::vector<double> mapWgt;
+        if (isRemap) {
+            nc3::Reader rm(join_path(ancil, c.need("fname_remap")));
+            std::vector<int> mapId, numQ, qId; std::vector<double> wgt;
+            rm.read_int(rm.var(c.need("vname_hruid_in_remap")), mapId);
+            rm.read_int(rm.var(c.need("vname_num_qhru")), numQ);
+            rm.read_all(rm.var(c.need("vname_weight")), wgt);
+            std::vector<int> qIxGrid;
+            if (grid) {                                                     // remap_2D_runoff (process_remap.f90:59-162): sim2d(ii, jj), ii along lon, jj along lat, 1-based;
+                std::vector<int> ii, jj;                                    // a cell outside the grid is skipped like an unknown polygon id
+                rm.read_int(rm.var(c.str("vname_i_index", "i_index")), ii);
+                rm.read_int(rm.var(c.str("vname_j_index", "j_index")), jj);
+                if (ii.size() != wgt.size() || jj.size() != wgt.size()) die(20, "read_remap/mapping variables have inconsistent sizes");
+                qIxGrid.resize(ii.size());
+                for (size_t i = 0; i < ii.size(); ++i)
+                    qIxGrid[i] = (ii[i] < 1 || ii[i] > (int)nLon || jj[i] < 1 || jj[i] > (int)nLat) ? -1 : (jj[i] - 1) * (int)nLon + (ii[i] - 1);
+            } else rm.read_int(rm.var(c.need("vname_qhruid")), qId);
+            if (mapId.size() != numQ.size() || (!grid && qId.size() != wgt.size())) die(20, "read_remap/mapping variables have inconsistent sizes");
+            auto lookup = [](const std::vector<int> &keys, const std::vector<int> &ids) {
+                std::vector<std::pair<int, int>> tab(ids.size()); for (size_t i = 0; i < ids.size(); ++i) tab[i] = {ids[i], (int)i}; std::sort(tab.begin(), tab.end());
+                std::vector<int> out(keys.size(), -1);
+                for (size_t i = 0; i < keys.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(keys[i], -1)); if (it != tab.end() && it->first == keys[i]) out[i] = it->second; }
+                return out; };
+            mapHruIx = lookup(mapId, hruId); mapQIx = grid ? qIxGrid : lookup(qId, roHruId); mapNumQ = numQ; mapWgt = wgt;
+            if (!dumpRemap.empty()) {                                       // int32 n, m, hruIx[n], numQ[n], qIx[m]; float64 w[m] -- what mr_set_remap receives
+                FILE *f = std::fopen(dumpRemap.c_str(), "wb"); if (!f) die(30, "route_runoff/cannot write " + dumpRemap);
+                const int nm[2] = {(int)mapHruIx.size(), (int)mapQIx.size()};
+                std::fwrite(nm, sizeof(int), 2, f); std::fwrite(mapHruIx.data(), sizeof(int), mapHruIx.size(), f); std::fwrite(mapNumQ.data(), sizeof(int), mapNumQ.size(), f);
+                std::fwrite(mapQIx.data(), sizeof(int), mapQIx.size(), f); std::fwrite(mapWgt.data(), sizeof(double), mapWgt.size(), f); std::fclose(f);
+            }
+        }
+
+
         // get_hru_runoff for simulation step k (get_basin_runoff.f90:19-120): the step's forcing record(s) -> one row of
         // the library's input (network HRU order, or forcing-polygon order when the device remaps)
-        const size_t nForcing = roHruId.size();
         const size_t inCols = isRemap ? nForcing : nHRU;
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         std::vector<double> rec, wsum, wtot;
@@ -458,23 +504,7 @@ int main(int argc, char **argv) {
                               d03[2].empty() ? nullptr : d03[2].data(), d03[3].empty() ? nullptr : d03[3].data(), msg);
         if (ierr) die(ierr, msg);
 
-        // ---- runoff remapping (<is_remap> T): mapping netCDF -> device-side remap_1D (read_remap.f90:20-170, process_remap.f90:164-262)
-        if (isRemap) {
-            nc3::Reader rm(join_path(ancil, c.need("fname_remap")));
-            std::vector<int> mapId, numQ, qId; std::vector<double> wgt;
-            rm.read_int(rm.var(c.need("vname_hruid_in_remap")), mapId);
-            rm.read_int(rm.var(c.need("vname_num_qhru")), numQ);
-            rm.read_int(rm.var(c.need("vname_qhruid")), qId);
-            rm.read_all(rm.var(c.need("vname_weight")), wgt);
-            if (mapId.size() != numQ.size() || qId.size() != wgt.size()) die(20, "read_remap/mapping variables have inconsistent sizes");
-            auto lookup = [](const std::vector<int> &keys, const std::vector<int> &ids) {
-                std::vector<std::pair<int, int>> tab(ids.size()); for (size_t i = 0; i < ids.size(); ++i) tab[i] = {ids[i], (int)i}; std::sort(tab.begin(), tab.end());
-                std::vector<int> out(keys.size(), -1);
-                for (size_t i = 0; i < keys.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(keys[i], -1)); if (it != tab.end() && it->first == keys[i]) out[i] = it->second; }
-                return out; };
-            const std::vector<int> hruIx = lookup(mapId, hruId), qIx = lookup(qId, roHruId);
-            ierr = mr_set_remap(h, (int)nForcing, (int)mapId.size(), hruIx.data(), numQ.data(), qIx.data(), wgt.data(), msg); if (ierr) die(ierr, msg);
-        }
+        if (isRemap) { ierr = mr_set_remap(h, (int)nForcing, (int)mapHruIx.size(), mapHruIx.data(), mapNumQ.data(), mapQIx.data(), mapWgt.data(), msg); if (ierr) die(ierr, msg); }
 
         // ---- history file (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
         char stamp[64]; { int y, mo, d, hh = 0, mi = 0; double ss = 0; std::sscanf(c.need("sim_start").c_str(), "%d-%d-%d %d:%d:%lf", &y, &mo, &d, &hh, &mi, &ss);

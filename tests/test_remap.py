@@ -120,3 +120,87 @@ def test_host_passes_polygon_forcing_through_for_the_device_remap(tmp_path):
     r = subprocess.run([mrbuild.build_host(), ctl, "--dry-run", "--dump-forcing", path], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.fromfile(path, dtype=np.float64).reshape(K, nF), forcing)
+
+
+def make_grid_mapping(net, n_lat, n_lon, seed=0):
+    """River-network HRUs overlapping 1-4 cells of an [n_lat, n_lon] grid; a few cells lie outside the grid (skipped by
+    remap_2D_runoff, process_remap.f90:110-126), weights do not always sum to one."""
+    rng = np.random.default_rng(seed)
+    num = rng.integers(1, 5, size=net.nHRU).astype(np.int32)
+    m = int(num.sum())
+    ii = rng.integers(1, n_lon + 1, size=m).astype(np.int32)       # x / lon, 1-based
+    jj = rng.integers(1, n_lat + 1, size=m).astype(np.int32)       # y / lat, 1-based
+    out = rng.random(m) < 0.03
+    ii[out] = n_lon + 1 + rng.integers(0, 3, size=int(out.sum()))
+    w = rng.random(m) + 0.05
+    ptr = np.concatenate([[0], np.cumsum(num)])
+    for h in range(net.nHRU):
+        if h % 3:
+            w[ptr[h]:ptr[h + 1]] /= w[ptr[h]:ptr[h + 1]].sum()
+    order = rng.permutation(net.nHRU)
+    return net.hruId[order].astype(np.int32), num, ii, jj, w, order
+
+
+def numpy_remap_2d(order, num, ii, jj, w, grid, n_hru):
+    """Independent restatement of remap_2D_runoff (process_remap.f90:59-162) on grid[lat, lon]."""
+    out = np.zeros(n_hru); k = 0
+    for h, n in zip(order, num):
+        sw = acc = 0.0
+        for _ in range(n):
+            i, j = ii[k] - 1, jj[k] - 1
+            if 0 <= i < grid.shape[1] and 0 <= j < grid.shape[0] and grid[j, i] > -1e-6:
+                sw += w[k]; acc += w[k] * grid[j, i]
+            k += 1
+        if sw > 1e-6 and abs(1.0 - sw) > 1e-6:
+            acc /= sw
+        out[h] = acc
+    return out
+
+
+def _grid_case(tmp_path, n=60, n_lat=7, n_lon=9, K=5):
+    from mizuroute_b200 import casefiles
+    net, params, opts, _ = case("random", n=n, seed=6, dt=86400.0, route_opt="12", steps=1)
+    map_ids, num, ii, jj, w, order = make_grid_mapping(net, n_lat, n_lon, seed=2)
+    grid = np.random.default_rng(4).lognormal(np.log(2e-5), 1.0, size=(K, n_lat, n_lon))
+    grid[1, 2, 3] = -9999.0
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, grid, case_name="grid", remap=("grid", map_ids, num, ii, jj, w))
+    return net, params, opts, grid, (order, num, ii, jj, w), ctl
+
+
+def test_host_flattens_gridded_forcing_for_the_device_remap(tmp_path):
+    """[time, lat, lon] runoff + i_index/j_index mapping: the host hands the library flattened grid records and flat cell
+    indices; the 1-D weighted sum over them (oracle remap_1d) is remap_2D_runoff on the grid."""
+    from mizuroute_b200 import build as mrbuild
+    from oracle import oracle as orc
+    net, params, opts, grid, (order, num, ii, jj, w), ctl = _grid_case(tmp_path)
+    rows_path, map_path = str(tmp_path / "rows.f64"), str(tmp_path / "map.bin")
+    r = subprocess.run([mrbuild.build_host(), ctl, "--dry-run", "--dump-forcing", rows_path, "--dump-remap", map_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert json.loads(r.stdout.strip().splitlines()[0])["nHRU_forcing"] == grid.shape[1] * grid.shape[2]
+    rows = np.fromfile(rows_path, dtype=np.float64).reshape(grid.shape[0], -1)
+    assert np.array_equal(rows, grid.reshape(grid.shape[0], -1))
+    raw = open(map_path, "rb").read()
+    n, m = np.frombuffer(raw, dtype=np.int32, count=2)
+    hru_ix = np.frombuffer(raw, dtype=np.int32, count=n, offset=8)
+    num_q = np.frombuffer(raw, dtype=np.int32, count=n, offset=8 + 4 * n)
+    q_ix = np.frombuffer(raw, dtype=np.int32, count=m, offset=8 + 8 * n)
+    wgt = np.frombuffer(raw, dtype=np.float64, count=m, offset=8 + 8 * n + 4 * m)
+    assert np.array_equal(hru_ix, order) and np.array_equal(num_q, num) and np.array_equal(wgt, w) and (q_ix < 0).sum() == (ii > grid.shape[2]).sum()
+    for t in range(grid.shape[0]):
+        want = numpy_remap_2d(order, num, ii, jj, w, grid[t], net.nHRU)
+        got = orc.remap_1d(hru_ix, num_q, q_ix, wgt, rows[t], net.nHRU)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_host_routes_gridded_forcing_like_the_oracle(tmp_path):
+    from mizuroute_b200 import build as mrbuild, casefiles
+    from oracle.oracle import Oracle
+    net, params, opts, grid, (order, num, ii, jj, w), ctl = _grid_case(tmp_path, n=300, n_lat=12, n_lon=15, K=10)
+    r = subprocess.run([mrbuild.build_host(), ctl, "--batch", "4"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    ro_net = np.stack([numpy_remap_2d(order, num, ii, jj, w, grid[t], net.nHRU) for t in range(grid.shape[0])])
+    qo = Oracle(net, params, opts).run(ro_net)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
