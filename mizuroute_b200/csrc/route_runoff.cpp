@@ -15,8 +15,9 @@
 // Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
-// one history file, <outputFrequency> = n steps or daily, standard /
-// proleptic_gregorian / noleap calendars.  <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device.
+// <outputFrequency> = n steps or daily; standard / proleptic_gregorian / noleap calendars; <restart_write> never | last.
+// <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device; any ratio of <dt_qsim> to
+// the forcing interval; <newFileFrequency> single | daily | monthly | yearly.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -24,6 +25,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <memory>
 #include <set>
 #include <sstream>
 #include <string>
@@ -146,6 +148,33 @@ void parse_time_units(const std::string &units, bool noleap, double &scale, doub
     if (unit.rfind("sec", 0) == 0) scale = 1.0; else if (unit.rfind("min", 0) == 0) scale = 60.0; else if (unit.rfind("hour", 0) == 0 || unit == "h" || unit == "hr") scale = 3600.0;
     else if (unit.rfind("day", 0) == 0) scale = 86400.0; else die(20, "inFile_pop/<time_units>= " + unit + ": must be seconds, minutes, hours or days");
     epoch = parse_datetime(trim(units.substr(p + 5)), noleap);
+}
+
+// civil date of seconds since 1970-01-01 (proleptic Gregorian; noleap: 365-day years)
+struct Civil { int y, mo, d, sod; };
+Civil civil_from_sec(double t, bool noleap) {
+    const long long days = (long long)std::floor((t + 1e-6) / 86400.0);
+    Civil cv; cv.sod = (int)std::llround(t - (double)days * 86400.0);
+    if (noleap) { long long yy = days >= 0 ? days / 365 : -((-days + 364) / 365); cv.y = 1970 + (int)yy; int doy = (int)(days - yy * 365);
+                  static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31}; int m = 0; while (doy >= ml[m]) doy -= ml[m++]; cv.d = doy + 1; cv.mo = m + 1; }
+    else { const long long z = days + 719468, era = (z >= 0 ? z : z - 146096) / 146097; const unsigned doe = (unsigned)(z - era * 146097), yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+           const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153; cv.d = (int)(doy - (153 * mp + 2) / 5 + 1); cv.mo = (int)(mp < 10 ? mp + 3 : mp - 9); cv.y = (int)(yoe + era * 400 + (cv.mo <= 2)); }
+    return cv;
+}
+// history files: a new file when the year / month / day of the step's start changes (newFileAlarm, write_simoutput_pio.f90:110-135),
+// named <case>.h.<yyyy-mm-dd-sssss | yyyy-mm | yyyy>.nc after the first step it holds (get_hfilename, :329-392)
+bool new_file_alarm(const std::string &freq, const Civil &prev, const Civil &cur) {
+    if (freq == "yearly") return cur.y != prev.y;
+    if (freq == "monthly") return cur.mo != prev.mo;
+    if (freq == "daily") return cur.d != prev.d;
+    return false;                                                // single: only the first step opens a file
+}
+std::string hist_stamp(const std::string &freq, const Civil &cv) {
+    char b[64];
+    if (freq == "monthly") std::snprintf(b, sizeof b, "%04d-%02d", cv.y, cv.mo);
+    else if (freq == "yearly") std::snprintf(b, sizeof b, "%04d", cv.y);
+    else std::snprintf(b, sizeof b, "%04d-%02d-%02d-%05d", cv.y, cv.mo, cv.d, cv.sod);
+    return b;
 }
 
 std::string join_path(const std::string &dir, const std::string &f) { return (!f.empty() && f[0] == '/') ? f : dir + f; }
@@ -412,6 +441,25 @@ int main(int argc, char **argv) {
         std::printf("{\"case\": \"%s\", \"nRch\": %zu, \"nHRU\": %zu, \"nHRU_forcing\": %zu, \"nSteps\": %zu, \"dt\": %.1f, \"route_opt\": \"%s\", \"first_record\": %zu, "
                     "\"fshape\": %.6g, \"tscale\": %.6g, \"velo\": %.6g, \"diff\": %.6g, \"mann_n\": %.6g, \"wscale\": %.6g, \"time_conv\": %.9g, \"length_conv\": %.9g}\n",
                     c.str("case_name", "case").c_str(), nRch, nHRU, nForcing, nSteps, o.dt, ropt.c_str(), i0, o.fshape, o.tscale, o.velo, o.diff, o.mann_n, o.wscale, o.time_conv, o.length_conv);
+        // <outputFrequency>: every step, a number of steps, or "daily"; fluxes are averaged over the period
+        // (histVars_data.f90:154-246) and stamped with the start of the period
+        int nAgg = 1;
+        { const std::string of = lower(c.str("outputFrequency", "1"));
+          if (of == "daily") { if (std::fmod(86400.0, o.dt) != 0.0) die(20, "route_runoff/<outputFrequency> daily needs dt_qsim to divide 86400 s"); nAgg = (int)std::lround(86400.0 / o.dt); }
+          else { char *e; const long v = std::strtol(of.c_str(), &e, 10); if (e == of.c_str() || v < 1) die(20, "route_runoff/<outputFrequency> " + of + ": only an integer number of steps or 'daily' is supported by this host"); nAgg = (int)v; } }
+        // <newFileFrequency>: which history file every output record goes to
+        const std::string fileFreq = lower(c.str("newFileFrequency", "single"));
+        if (fileFreq != "single" && fileFreq != "daily" && fileFreq != "monthly" && fileFreq != "yearly") die(20, "new_file_alarm/unable to identify the option to define new output files");
+        struct HistFile { std::string path; size_t first, nrec; };          // first step held, records written
+        std::vector<HistFile> plan;
+        { int na = 0;
+          for (size_t k = 0; k < nSteps; ++k) {
+              const Civil cur = civil_from_sec(tStart + (double)k * o.dt, noleap);
+              if (k == 0 || new_file_alarm(fileFreq, civil_from_sec(tStart + (double)(k - 1) * o.dt, noleap), cur))
+                  plan.push_back({join_path(outdir, c.str("case_name", "case") + ".h." + hist_stamp(fileFreq, cur) + ".nc"), k, 0});
+              if (++na == nAgg || k + 1 == nSteps) { ++plan.back().nrec; na = 0; }
+          } }
+
         // ---- runoff remapping (<is_remap> T): mapping netCDF -> index form for the device-side remap (read_remap.f90:20-170,
         // process_remap.f90:59-262).  A gridded forcing is the same weighted sum over a flattened [lat][lon] record.
         std::vector<int> mapHruIx, mapNumQ, mapQIx; std::vector<double> mapWgt;
@@ -484,6 +532,8 @@ int main(int argc, char **argv) {
                 for (size_t j = 0; j < m.rec.size(); ++j) std::printf("%s[%zu, %.9g]", j ? ", " : "", m.rec[j], m.frac.empty() ? 1.0 : m.frac[j]);
                 std::printf("]");
             }
+            std::printf("], \"history_plan\": [");
+            for (size_t i = 0; i < plan.size(); ++i) std::printf("%s[\"%s\", %zu]", i ? ", " : "", plan[i].path.substr(plan[i].path.find_last_of('/') + 1).c_str(), plan[i].nrec);
             std::printf("]}\n");
             if (!dumpForcing.empty()) {                                   // raw float64 [nSteps][columns]: what the time loop would feed the library
                 FILE *f = std::fopen(dumpForcing.c_str(), "wb"); if (!f) die(30, "route_runoff/cannot write " + dumpForcing);
@@ -506,36 +556,31 @@ int main(int argc, char **argv) {
 
         if (isRemap) { ierr = mr_set_remap(h, (int)nForcing, (int)mapHruIx.size(), mapHruIx.data(), mapNumQ.data(), mapQIx.data(), mapWgt.data(), msg); if (ierr) die(ierr, msg); }
 
-        // ---- history file (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
-        char stamp[64]; { int y, mo, d, hh = 0, mi = 0; double ss = 0; std::sscanf(c.need("sim_start").c_str(), "%d-%d-%d %d:%d:%lf", &y, &mo, &d, &hh, &mi, &ss);
-                          std::snprintf(stamp, sizeof stamp, "%04d-%02d-%02d-%05d", y, mo, d, hh * 3600 + mi * 60 + (int)ss); }
-        const std::string opath = join_path(outdir, c.str("case_name", "case") + ".h." + stamp + ".nc");
-        nc3::Writer w(opath);
-        const int dTime = w.def_dim("time", 0), dSeg = w.def_dim("seg", nRch);
-        const int vTime = w.def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
-        const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
+        // ---- history files (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
         const char *vname[3] = {"sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"};
         const char *lname[3] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking"};
-        // <outputFrequency>: every step, a number of steps, or "daily"; fluxes are averaged over the period
-        // (histVars_data.f90:154-246) and stamped with the start of the period
-        int nAgg = 1;
-        { const std::string of = lower(c.str("outputFrequency", "1"));
-          if (of == "daily") { if (std::fmod(86400.0, o.dt) != 0.0) die(20, "route_runoff/<outputFrequency> daily needs dt_qsim to divide 86400 s"); nAgg = (int)std::lround(86400.0 / o.dt); }
-          else { char *e; const long v = std::strtol(of.c_str(), &e, 10); if (e == of.c_str() || v < 1) die(20, "route_runoff/<outputFrequency> " + of + ": only an integer number of steps or 'daily' is supported by this host"); nAgg = (int)v; } }
         const bool wantDlay = c.flag("dlayRunoff", true);
-        int vDlay = -1;
+        int vTime = -1, vDlay = -1;
         std::vector<int> vQ(o.n_routes, -1);
-        for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
-            vQ[r] = w.def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
-        if (wantDlay) vDlay = w.def_var("dlayRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "delayed runoff in each reach"}});
-        w.global_attr("title", "mizuRoute routing (mizuroute-b200)");
-        w.end_def();
-        w.put_int(vId, segId.data());
+        std::unique_ptr<nc3::Writer> w;
+        auto open_history = [&](const std::string &path) {
+            if (w) w->close();
+            w.reset(new nc3::Writer(path));
+            const int dTime = w->def_dim("time", 0), dSeg = w->def_dim("seg", nRch);
+            vTime = w->def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
+            const int vId = w->def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
+            for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
+                vQ[r] = w->def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
+            if (wantDlay) vDlay = w->def_var("dlayRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "delayed runoff in each reach"}});
+            w->global_attr("title", "mizuRoute routing (mizuroute-b200)");
+            w->end_def();
+            w->put_int(vId, segId.data());
+        };
 
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
         std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
-        int nAcc = 0; size_t recOut = 0; double tAcc = 0.0;
+        int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
@@ -546,11 +591,13 @@ int main(int argc, char **argv) {
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             for (int k = 0; k < nb; ++k) {
-                const double tsec = (tStart - tStartAsked) + (double)(s + k) * o.dt;                                                       // seconds since <sim_start>
+                const double tsec = (tStart - tStartAsked) + (double)(s + k) * o.dt;    // seconds since <sim_start>
+                if (fileNo < plan.size() && plan[fileNo].first == s + k) { open_history(plan[fileNo++].path); recOut = 0; }     // main_new_file
                 if (nAgg == 1) {
-                    w.put_record(vTime, s + k, &tsec);
-                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], s + k, &q[((size_t)r * nb + k) * nRch]);
-                    if (vDlay >= 0) w.put_record(vDlay, s + k, &qd[(size_t)k * nRch]);
+                    w->put_record(vTime, recOut, &tsec);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &q[((size_t)r * nb + k) * nRch]);
+                    if (vDlay >= 0) w->put_record(vDlay, recOut, &qd[(size_t)k * nRch]);
+                    ++recOut;
                     continue;
                 }
                 if (nAcc == 0) { tAcc = tsec; std::fill(acc.begin(), acc.end(), 0.0); }
@@ -558,32 +605,29 @@ int main(int argc, char **argv) {
                 if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
                     for (auto &v : acc) v /= (double)nAcc;
-                    w.put_record(vTime, recOut, &tAcc);
-                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w.put_record(vQ[r], recOut, &acc[(size_t)r * nRch]);
-                    if (vDlay >= 0) w.put_record(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
+                    w->put_record(vTime, recOut, &tAcc);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &acc[(size_t)r * nRch]);
+                    if (vDlay >= 0) w->put_record(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
                     ++recOut; nAcc = 0;
                 }
             }
             T0 += nb * o.dt;
         }
         for (auto *p : rd) delete p;
-        w.close();
+        if (w) w->close();
         const std::string rw = lower(c.str("restart_write", "never"));
         if (rw == "last") {                                                     // main_restart, route_runoff.f90:102
             const double tEndNext = tStart + (double)nSteps * o.dt;
-            long long days = (long long)std::floor(tEndNext / 86400.0); const int sod = (int)std::llround(tEndNext - (double)days * 86400.0);
-            // civil date of `days` since 1970-01-01 (proleptic Gregorian; noleap: 365-day years)
-            int y, mo, d;
-            if (noleap) { y = 1970 + (int)(days / 365); int doy = (int)(days % 365); static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31}; mo = 0; while (doy >= ml[mo]) doy -= ml[mo++]; d = doy + 1; mo += 1; }
-            else { long long z = days + 719468; const long long era = (z >= 0 ? z : z - 146096) / 146097; const unsigned doe = (unsigned)(z - era * 146097), yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-                   const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153; d = (int)(doy - (153 * mp + 2) / 5 + 1); mo = (int)(mp < 10 ? mp + 3 : mp - 9); y = (int)(yoe + era * 400 + (mo <= 2)); }
+            const Civil cv = civil_from_sec(tEndNext, noleap); const int y = cv.y, mo = cv.mo, d = cv.d, sod = cv.sod;
             char rs[64]; std::snprintf(rs, sizeof rs, "%04d-%02d-%02d-%05d", y, mo, d, sod);
             const std::string rpath = join_path(c.str("restart_dir", outdir), c.str("case_name", "case") + ".r." + rs + ".nc");
             write_restart(h, rpath, o, segId, T0, (long)std::lround(T0 / o.dt));
             std::printf("{\"restart\": \"%s\"}\n", rpath.c_str());
         } else if (rw != "never") die(20, "route_runoff/<restart_write> " + rw + ": only 'never' and 'last' are supported by this host");
         mr_destroy(h);
-        std::printf("{\"history\": \"%s\", \"steps\": %zu}\n", opath.c_str(), nSteps);
+        std::printf("{\"history\": \"%s\", \"steps\": %zu, \"history_files\": [", plan[0].path.c_str(), nSteps);
+        for (size_t i = 0; i < plan.size(); ++i) std::printf("%s\"%s\"", i ? ", " : "", plan[i].path.c_str());
+        std::printf("]}\n");
     } catch (const std::exception &e) {
         die(20, e.what());
     }

@@ -17,6 +17,17 @@ def _host():
     return mrbuild.build_host()
 
 
+# The host tests that route run twice: against the real library on a GPU ("cuda", the parity tests proper), and -- so that
+# the host's own I/O and bookkeeping are checked in the CPU suite too -- with a copy of the host linked against a test-only
+# stand-in for the library built on the oracle (tests/stub/mr_stub.c; says nothing about the CUDA path).
+BACKENDS = [pytest.param("oracle-stub", id="stub"), pytest.param("cuda", marks=pytest.mark.gpu, id="cuda")]
+
+
+def _routing_host(backend):
+    from tests import stub
+    return stub.build() if backend == "oracle-stub" else _host()
+
+
 def test_dry_run_parses_reference_style_case(tmp_path):
     net, params, opts, ro = case("random", n=90, seed=3, dt=3600.0, route_opt="012", steps=30)
     params = RouteParams(fshape=2.2, tscale=70000.0, velo=1.2, diff=4000.0, mann_n=0.02, wscale=0.0015)
@@ -75,6 +86,26 @@ def test_time_map_between_simulation_steps_and_forcing_records(tmp_path):
     # a simulation period longer than the forcing is cut to the steps the forcing covers completely
     a, b = _time_map(tmp_path, 3600.0, 3600.0, records=5, sim_steps=9, name="clip")
     assert a["nSteps"] == 5
+
+
+def test_history_file_plan(tmp_path):
+    """<newFileFrequency>: a new history file when the day / month / year of a step's start changes (newFileAlarm,
+    write_simoutput_pio.f90:110-135), stamped like get_hfilename (:329-392); records per file follow <outputFrequency>."""
+    net, params, opts, ro = case("random", n=20, seed=3, dt=21600.0, route_opt="1", steps=14)
+    def plan(freq, out_freq="1", start="2000-12-30 12:00:00"):
+        ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="hp", start=start, new_file_frequency=freq, output_frequency=out_freq)
+        r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout.strip().splitlines()[1])["history_plan"]
+    assert plan("single") == [["hp.h.2000-12-30-43200.nc", 14]]
+    assert plan("daily") == [["hp.h.2000-12-30-43200.nc", 2], ["hp.h.2000-12-31-00000.nc", 4], ["hp.h.2001-01-01-00000.nc", 4], ["hp.h.2001-01-02-00000.nc", 4]]
+    assert plan("monthly") == [["hp.h.2000-12.nc", 6], ["hp.h.2001-01.nc", 8]]
+    assert plan("yearly") == [["hp.h.2000.nc", 6], ["hp.h.2001.nc", 8]]
+    assert plan("monthly", "2") == [["hp.h.2000-12.nc", 3], ["hp.h.2001-01.nc", 4]]
+    assert plan("daily", start="2000-02-28 00:00:00")[1][0] == "hp.h.2000-02-29-00000.nc"          # leap day in the standard calendar
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="bad", new_file_frequency="weekly")
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "new output files" in r.stderr
 
 
 def _dump_forcing(ctl, tmp_path, cols):
@@ -154,13 +185,13 @@ def test_reader_accepts_classic_cdf1_and_rejects_netcdf4(tmp_path):
     assert r.returncode != 0 and "netCDF-4/HDF5 is not supported" in r.stderr
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("route,dt,lakes", [("012", 3600.0, 0), ("12", 86400.0, 5)])
-def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
+def test_host_run_matches_oracle(tmp_path, backend, route, dt, lakes):
     from oracle.oracle import Oracle
     net, params, opts, ro = case("conus", n=600, seed=8, dt=dt, route_opt=route, steps=40, lakes=lakes)
     ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="gpu", split_forcing=2, shuffle_hru_seed=5)
-    r = subprocess.run([_host(), ctl, "--batch", "16"], capture_output=True, text=True)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "16"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     hist = json.loads(r.stdout.strip().splitlines()[-1])["history"]
     out = casefiles.read_history(hist)
@@ -174,15 +205,15 @@ def test_host_run_matches_oracle(tmp_path, route, dt, lakes):
         np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c != "2" else 1e-4, atol=1e-30)
 
 
-@pytest.mark.gpu
+@pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("dt,forcing_dt,records,sim_steps", [(3600.0, 10800.0, 10, 30), (10800.0, 3600.0, 36, 12), (7200.0, 10800.0, 8, 12)])
-def test_host_maps_forcing_records_onto_simulation_steps(tmp_path, dt, forcing_dt, records, sim_steps):
+def test_host_maps_forcing_records_onto_simulation_steps(tmp_path, backend, dt, forcing_dt, records, sim_steps):
     """dt_qsim != dt_ro: the host feeds each step the record it lies in, or the time-weighted mean of the records it
     spans (timeMap_sim_forc + read_1D_forcing); the oracle is run on the runoff averaged the same way here."""
     from oracle.oracle import Oracle
     net, params, opts, ro = case("conus", n=300, seed=4, dt=dt, route_opt="12", steps=records)
     ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="tmap", forcing_dt=forcing_dt, sim_steps=sim_steps)
-    r = subprocess.run([_host(), ctl, "--batch", "5"], capture_output=True, text=True)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     fine = 1800.0                                                          # common divisor of every interval used here
@@ -195,15 +226,32 @@ def test_host_maps_forcing_records_onto_simulation_steps(tmp_path, dt, forcing_d
     np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
 
 
-@pytest.mark.gpu
-def test_exact_restart(tmp_path):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_daily_history_files_hold_the_single_file_run(tmp_path, backend):
+    net, params, opts, ro = case("random", n=150, seed=6, dt=10800.0, route_opt="12", steps=20)
+    d = str(tmp_path)
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "6"], capture_output=True, text=True)
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="one", start="2000-02-28 06:00:00")); assert r.returncode == 0, r.stderr
+    one = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="many", start="2000-02-28 06:00:00", new_file_frequency="daily")); assert r.returncode == 0, r.stderr
+    files = json.loads(r.stdout.strip().splitlines()[-1])["history_files"]
+    assert [os.path.basename(f) for f in files] == ["many.h.2000-02-28-21600.nc", "many.h.2000-02-29-00000.nc", "many.h.2000-03-01-00000.nc"]
+    parts = [casefiles.read_history(f) for f in files]
+    assert [len(p["time"]) for p in parts] == [6, 8, 6]
+    for v in ("time", "IRFroutedRunoff", "KWTroutedRunoff", "dlayRunoff"):
+        assert np.array_equal(np.concatenate([p[v] for p in parts]), one[v]), v
+    assert all(np.array_equal(p["reachID"], net.segId) for p in parts)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_exact_restart(tmp_path, backend):
     """ERS, the reference's main regression idea (cime_config/testdefs/testlist_mizuRoute.xml): 40 steps in one run ==
     20 steps + restart file (reference schema: qfuture, irf_qfuture, numWaves, tentry/texit/qwave/routed, ...) + 20 steps."""
     net, params, opts, ro = case("conus", n=500, seed=9, dt=3600.0, route_opt="012", steps=40, lakes=4)
     d = str(tmp_path)
     full = casefiles.write_case(d, net, params, opts, ro, case_name="full")
     first = casefiles.write_case(d, net, params, opts, ro[:20], case_name="first", restart_write="last")
-    run = lambda ctl: subprocess.run([_host(), ctl, "--batch", "7"], capture_output=True, text=True)
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "7"], capture_output=True, text=True)
     r = run(full); assert r.returncode == 0, r.stderr
     h_full = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     r = run(first); assert r.returncode == 0, r.stderr
@@ -220,15 +268,15 @@ def test_exact_restart(tmp_path):
         assert np.array_equal(np.concatenate([h_first[v], h_second[v]]), h_full[v]), v
 
 
-@pytest.mark.gpu
-def test_daily_mean_output_and_delayed_runoff(tmp_path):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_daily_mean_output_and_delayed_runoff(tmp_path, backend):
     """<outputFrequency> daily on an hourly run: every history record is the mean of 24 steps (histVars_data.f90:154-246);
     dlayRunoff = BASIN_QR(1)."""
     from oracle import oracle as orc
     from oracle.oracle import Oracle
     net, params, opts, ro = case("random", n=120, seed=2, dt=3600.0, route_opt="1", steps=60)
     ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="agg", output_frequency="daily")
-    r = subprocess.run([_host(), ctl, "--batch", "25"], capture_output=True, text=True)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "25"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     o = Oracle(net, params, opts)

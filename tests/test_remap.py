@@ -7,6 +7,7 @@ import subprocess
 import numpy as np
 import pytest
 
+from tests.test_host import BACKENDS, _routing_host
 from tests.util import case
 
 
@@ -86,8 +87,8 @@ def test_device_remap_feeds_routing_like_the_oracle():
     assert np.max(np.abs(qg[2] - qo[2]) / np.maximum(np.abs(qo[2]), 1e-300)) <= 1e-4
 
 
-@pytest.mark.gpu
-def test_host_reads_reference_style_mapping_file(tmp_path):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_host_reads_reference_style_mapping_file(tmp_path, backend):
     from mizuroute_b200 import build as mrbuild, casefiles
     from oracle import oracle as orc
     from oracle.oracle import Oracle
@@ -97,7 +98,7 @@ def test_host_reads_reference_style_mapping_file(tmp_path):
     hru_ix, qix = indices(net, map_ids, qid, fids)
     forcing = np.random.default_rng(1).lognormal(np.log(2e-5), 1.0, size=(K, nF))
     ctl = casefiles.write_case(str(tmp_path), net, params, opts, forcing, case_name="remap", remap=(map_ids, num, qid, w, fids))
-    r = subprocess.run([mrbuild.build_host(), ctl, "--batch", "5"], capture_output=True, text=True)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     ro_net = np.stack([orc.remap_1d(hru_ix, num, qix, w, forcing[t], net.nHRU) for t in range(K)])
@@ -192,12 +193,12 @@ def test_host_flattens_gridded_forcing_for_the_device_remap(tmp_path):
         assert np.array_equal(got, want)
 
 
-@pytest.mark.gpu
-def test_host_routes_gridded_forcing_like_the_oracle(tmp_path):
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_host_routes_gridded_forcing_like_the_oracle(tmp_path, backend):
     from mizuroute_b200 import build as mrbuild, casefiles
     from oracle.oracle import Oracle
     net, params, opts, grid, (order, num, ii, jj, w), ctl = _grid_case(tmp_path, n=300, n_lat=12, n_lon=15, K=10)
-    r = subprocess.run([mrbuild.build_host(), ctl, "--batch", "4"], capture_output=True, text=True)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "4"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     ro_net = np.stack([numpy_remap_2d(order, num, ii, jj, w, grid[t], net.nHRU) for t in range(grid.shape[0])])
