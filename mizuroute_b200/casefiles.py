@@ -85,7 +85,7 @@ def _stamp(seconds: float, start: str) -> str:
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
                fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1", forcing_dt=None, sim_steps=None,
-               ro_time_stamp=None, new_file_frequency="single") -> str:
+               ro_time_stamp=None, new_file_frequency="single", extra_keys=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
     continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`.  `forcing_dt` != dt_qsim
     writes the runoff records on their own interval (`sim_steps` simulation steps of opts.dt are then asked for);
@@ -188,6 +188,8 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("newFileFrequency", new_file_frequency, "history file frequency: single, daily, monthly or yearly"),
         ("outputFrequency", output_frequency, "output frequency: number of steps or daily"),
     ]
+    for k, v in (extra_keys or {}).items():
+        keys.append((k, v, "extra key"))
     ctl = os.path.join(case_dir, case_name + ".control")
     with open(ctl, "w") as f:
         f.write("! mizuRoute control file written by mizuroute_b200.casefiles\n! format: <key>  value  ! comment\n")

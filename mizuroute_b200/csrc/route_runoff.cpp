@@ -15,7 +15,8 @@
 // Everything numerical happens behind the C ABI (include/mizuroute_b200.h); this file is I/O and bookkeeping.
 // The reference's Fortran host cannot be built in this image (no Fortran compiler, no netCDF/PIO); NetCDF-3
 // classic / 64-bit-offset files are read and written with nc3.h.  Restrictions (each one is an explicit error):
-// <outputFrequency> = n steps or daily; standard / proleptic_gregorian / noleap calendars; <restart_write> never | last.
+// <outputFrequency> = n steps or daily; standard / proleptic_gregorian / noleap calendars.  <restart_write> never | last |
+// specified | yearly | monthly | daily.
 // <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device; any ratio of <dt_qsim> to
 // the forcing interval; <newFileFrequency> single | daily | monthly | yearly.
 #include <algorithm>
@@ -460,6 +461,30 @@ int main(int argc, char **argv) {
               if (++na == nAgg || k + 1 == nSteps) { ++plan.back().nrec; na = 0; }
           } }
 
+        // <restart_write>: the steps after which the state is written (restart_alarm, write_restart_pio.f90:110-163; init_time,
+        // model_setup.f90:646-686).  The file is stamped with the start of the NEXT step (restart_fname, :207-253), which is
+        // what the periodic options compare with <restart_month> / <restart_day> / <restart_hour>.
+        const std::string rw = lower(c.str("restart_write", "never"));
+        std::vector<std::pair<size_t, std::string>> restartPlan;             // (last step of the state, file)
+        {
+            if (rw != "never" && rw != "last" && rw != "specified" && rw != "yearly" && rw != "monthly" && rw != "daily")
+                die(20, "init_time/Accepted <restart_write> options: last, never, specified, yearly, monthly, or daily");
+            const int rMon = (int)c.num("restart_month", 1), rDay = (int)c.num("restart_day", 1), rHour = (int)c.num("restart_hour", 0);
+            double tSpec = 0.0;
+            if (rw == "specified") { if (!c.has("restart_date")) die(20, "init_time/<restart_date> must be provided when <restart_write> option is \"specified\""); tSpec = parse_datetime(c.need("restart_date"), noleap); }
+            auto ndays = [&](int y, int m) { static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+                                             return ml[m - 1] + ((m == 2 && !noleap && ((y % 4 == 0 && y % 100 != 0) || y % 400 == 0)) ? 1 : 0); };
+            for (size_t k = 0; rw != "never" && k < nSteps; ++k) {
+                const double tNext = tStart + (double)(k + 1) * o.dt;
+                const Civil cv = civil_from_sec(tNext, noleap);
+                const bool atHour = cv.sod == rHour * 3600, atDay = cv.d == std::min(rDay, ndays(cv.y, cv.mo));
+                const bool ring = rw == "last" ? k + 1 == nSteps : rw == "specified" ? std::fabs(tNext - tSpec) < 1e-3
+                                : rw == "daily" ? atHour : rw == "monthly" ? (atHour && atDay) : (atHour && atDay && cv.mo == rMon);
+                if (ring) { char rs[64]; std::snprintf(rs, sizeof rs, "%04d-%02d-%02d-%05d", cv.y, cv.mo, cv.d, cv.sod);
+                            restartPlan.push_back({k, join_path(c.str("restart_dir", outdir), c.str("case_name", "case") + ".r." + rs + ".nc")}); }
+            }
+        }
+
         // ---- runoff remapping (<is_remap> T): mapping netCDF -> index form for the device-side remap (read_remap.f90:20-170,
         // process_remap.f90:59-262).  A gridded forcing is the same weighted sum over a flattened [lat][lon] record.
         std::vector<int> mapHruIx, mapNumQ, mapQIx; std::vector<double> mapWgt;
@@ -534,6 +559,8 @@ int main(int argc, char **argv) {
             }
             std::printf("], \"history_plan\": [");
             for (size_t i = 0; i < plan.size(); ++i) std::printf("%s[\"%s\", %zu]", i ? ", " : "", plan[i].path.substr(plan[i].path.find_last_of('/') + 1).c_str(), plan[i].nrec);
+            std::printf("], \"restart_plan\": [");
+            for (size_t i = 0; i < restartPlan.size(); ++i) std::printf("%s[%zu, \"%s\"]", i ? ", " : "", restartPlan[i].first, restartPlan[i].second.substr(restartPlan[i].second.find_last_of('/') + 1).c_str());
             std::printf("]}\n");
             if (!dumpForcing.empty()) {                                   // raw float64 [nSteps][columns]: what the time loop would feed the library
                 FILE *f = std::fopen(dumpForcing.c_str(), "wb"); if (!f) die(30, "route_runoff/cannot write " + dumpForcing);
@@ -585,8 +612,10 @@ int main(int argc, char **argv) {
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
             T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
-        for (size_t s = 0; s < nSteps; s += batch) {
-            const int nb = (int)std::min<size_t>(batch, nSteps - s);
+        size_t nextRestart = 0;
+        for (size_t s = 0; s < nSteps;) {
+            int nb = (int)std::min<size_t>(batch, nSteps - s);
+            if (nextRestart < restartPlan.size()) nb = (int)std::min<size_t>(nb, restartPlan[nextRestart].first + 1 - s);      // a batch ends where a restart file is due
             for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
@@ -611,19 +640,15 @@ int main(int argc, char **argv) {
                     ++recOut; nAcc = 0;
                 }
             }
-            T0 += nb * o.dt;
+            T0 += nb * o.dt; s += nb;
+            if (nextRestart < restartPlan.size() && restartPlan[nextRestart].first + 1 == s) {                              // main_restart, route_runoff.f90:102
+                write_restart(h, restartPlan[nextRestart].second, o, segId, T0, (long)std::lround(T0 / o.dt));
+                std::printf("{\"restart\": \"%s\"}\n", restartPlan[nextRestart].second.c_str());
+                ++nextRestart;
+            }
         }
         for (auto *p : rd) delete p;
         if (w) w->close();
-        const std::string rw = lower(c.str("restart_write", "never"));
-        if (rw == "last") {                                                     // main_restart, route_runoff.f90:102
-            const double tEndNext = tStart + (double)nSteps * o.dt;
-            const Civil cv = civil_from_sec(tEndNext, noleap); const int y = cv.y, mo = cv.mo, d = cv.d, sod = cv.sod;
-            char rs[64]; std::snprintf(rs, sizeof rs, "%04d-%02d-%02d-%05d", y, mo, d, sod);
-            const std::string rpath = join_path(c.str("restart_dir", outdir), c.str("case_name", "case") + ".r." + rs + ".nc");
-            write_restart(h, rpath, o, segId, T0, (long)std::lround(T0 / o.dt));
-            std::printf("{\"restart\": \"%s\"}\n", rpath.c_str());
-        } else if (rw != "never") die(20, "route_runoff/<restart_write> " + rw + ": only 'never' and 'last' are supported by this host");
         mr_destroy(h);
         std::printf("{\"history\": \"%s\", \"steps\": %zu, \"history_files\": [", plan[0].path.c_str(), nSteps);
         for (size_t i = 0; i < plan.size(); ++i) std::printf("%s\"%s\"", i ? ", " : "", plan[i].path.c_str());

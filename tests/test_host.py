@@ -108,6 +108,29 @@ def test_history_file_plan(tmp_path):
     assert r.returncode != 0 and "new output files" in r.stderr
 
 
+def test_restart_write_plan(tmp_path):
+    """<restart_write> specified / daily / monthly / yearly / last: the state is written after the step whose END is the
+    restart time, and the file carries that time (restart_alarm + restart_fname, write_restart_pio.f90:110-253)."""
+    net, params, opts, ro = case("random", n=20, seed=3, dt=3600.0, route_opt="1", steps=80)
+    def plan(rw, **extra):
+        ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="rp", start="2000-01-30 22:00:00", restart_write=rw, extra_keys=extra)
+        r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        return json.loads(r.stdout.strip().splitlines()[1])["restart_plan"]
+    assert plan("never") == []
+    assert plan("last") == [[79, "rp.r.2000-02-03-21600.nc"]]
+    assert plan("specified", restart_date="2000-01-31 06:00:00") == [[7, "rp.r.2000-01-31-21600.nc"]]
+    assert plan("daily") == [[1, "rp.r.2000-01-31-00000.nc"], [25, "rp.r.2000-02-01-00000.nc"], [49, "rp.r.2000-02-02-00000.nc"], [73, "rp.r.2000-02-03-00000.nc"]]
+    assert plan("daily", restart_hour=12)[0] == [13, "rp.r.2000-01-31-43200.nc"]
+    assert plan("monthly") == [[25, "rp.r.2000-02-01-00000.nc"]]
+    assert plan("monthly", restart_day=31) == [[1, "rp.r.2000-01-31-00000.nc"]]
+    assert plan("yearly", restart_month=2, restart_day=2) == [[49, "rp.r.2000-02-02-00000.nc"]]
+    assert plan("yearly") == []
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="bad", restart_write="specified")
+    r = subprocess.run([_host(), ctl, "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "<restart_date> must be provided" in r.stderr
+
+
 def _dump_forcing(ctl, tmp_path, cols):
     path = os.path.join(str(tmp_path), "forcing.f64")
     r = subprocess.run([_host(), ctl, "--dry-run", "--dump-forcing", path], capture_output=True, text=True)
@@ -266,6 +289,27 @@ def test_exact_restart(tmp_path, backend):
     h_second = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     for v in ("sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"):
         assert np.array_equal(np.concatenate([h_first[v], h_second[v]]), h_full[v]), v
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_restart_files_written_during_the_run_continue_it_exactly(tmp_path, backend):
+    """<restart_write> daily on a 6-hourly run with --batch 5: batches are cut where a restart file is due, and a run
+    continued from the second file reproduces the rest of the uninterrupted run bit for bit."""
+    net, params, opts, ro = case("conus", n=300, seed=3, dt=21600.0, route_opt="12", steps=14, lakes=3)
+    d = str(tmp_path)
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="full", start="2000-03-01 12:00:00", restart_write="daily")); assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    rfiles = [x["restart"] for x in lines if "restart" in x]
+    assert [os.path.basename(f) for f in rfiles] == ["full.r.2000-03-02-00000.nc", "full.r.2000-03-03-00000.nc", "full.r.2000-03-04-00000.nc", "full.r.2000-03-05-00000.nc"]
+    h_full = casefiles.read_history(next(x["history"] for x in lines if "history" in x))
+    k0 = 6                                                                  # 2000-03-03 00:00 = 6 steps after the start
+    assert casefiles.read_history(rfiles[1])["time_bound"][0] == k0 * 21600.0
+    ctl = casefiles.write_case(d, net, params, opts, ro[k0:], case_name="cont", start="2000-03-01 12:00:00", first_step=k0, fname_state_in=os.path.basename(rfiles[1]))
+    r = run(ctl); assert r.returncode == 0, r.stderr
+    h_cont = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    for v in ("IRFroutedRunoff", "KWTroutedRunoff", "dlayRunoff"):
+        assert np.array_equal(h_cont[v], h_full[v][k0:]), v
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
