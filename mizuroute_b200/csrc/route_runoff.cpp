@@ -526,7 +526,13 @@ int main(int argc, char **argv) {
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         std::vector<double> rec, wsum, wtot;
         double fillv = c.num("input_fillvalue", -9999.0);
+        // <scale_factor_runoff> / <offset_value_runoff> (scale_forcing, get_basin_runoff.f90:375-423; both ~0 = no runoff at all, :71-73)
+        const double roScale = c.num("scale_factor_runoff", -9999.0), roOffset = c.num("offset_value_runoff", -9999.0);
+        const bool roRescale = roScale != -9999.0 || roOffset != -9999.0;
+        const bool roZero = std::fabs(roScale) < 2.3e-308 && (std::fabs(roOffset) < 2.3e-308 || roOffset == -9999.0);
+        const double roA = roScale == -9999.0 ? 1.0 : roScale, roB = roOffset == -9999.0 ? 0.0 : roOffset;
         auto load_step = [&](size_t k, double *dst) {
+            if (roZero) { std::fill(dst, dst + inCols, 0.0); return; }
             const TimeMap tm = time_map(k);
             for (size_t j = 0; j < tm.rec.size(); ++j) {
                 const auto wr = where[tm.rec[j]];
@@ -544,6 +550,7 @@ int main(int argc, char **argv) {
             }
             if (!tm.frac.empty())
                 for (size_t i = 0; i < rec.size(); ++i) rec[i] = wtot[i] == 0.0 ? fillv : (wtot[i] < 1.0 ? wsum[i] / wtot[i] : wsum[i]);
+            if (roRescale) for (size_t i = 0; i < rec.size(); ++i) if (rec[i] != fillv && rec[i] != -9999.0) rec[i] = roA * rec[i] + roB;
             if (isRemap) { for (size_t i = 0; i < rec.size(); ++i) dst[i] = rec[i] == fillv ? -9999.0 : rec[i]; return; }  // remapped on the device; realMissing (< 0) is skipped there
             std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
             for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }

@@ -175,6 +175,19 @@ def test_forcing_fill_values_are_skipped_in_the_time_mean(tmp_path):
     np.testing.assert_allclose(got, want, rtol=1e-14)
 
 
+def test_runoff_scale_and_offset(tmp_path):
+    """<scale_factor_runoff> / <offset_value_runoff> (scale_forcing, get_basin_runoff.f90:375-423): applied to every value that
+    is not missing, before negatives are removed; scale 0 without an offset switches the runoff off (:71-73)."""
+    net, params, opts, ro = case("random", n=30, seed=5, dt=86400.0, route_opt="1", steps=4)
+    ro = ro.copy(); ro[2, 5] = -9999.0
+    rows = lambda **extra: _dump_forcing(casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="sc", extra_keys=extra), tmp_path, net.nHRU)
+    want = 0.5 * ro + 1e-6; want[2, 5] = 0.0
+    assert np.array_equal(rows(scale_factor_runoff=0.5, offset_value_runoff=1e-6), want)
+    want = ro - 2e-5; want[2, 5] = 0.0
+    assert np.array_equal(rows(offset_value_runoff=-2e-5), np.maximum(want, 0.0))
+    assert not rows(scale_factor_runoff=0.0).any()
+
+
 def test_netcdf3_writer_roundtrip_through_scipy(tmp_path):
     """nc3.h writes what scipy reads: exercised by the host's history file in the GPU test; here the network and
     runoff files written by scipy are the reader's input (dry run) with float32 runoff and 64-bit offsets."""
