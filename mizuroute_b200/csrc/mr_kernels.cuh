@@ -267,7 +267,7 @@ __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long 
                 if (++s == nt) s = 0;
             }
             double q1 = qf[(size_t)head * N];
-            q1 = fmin((fmax(0.0, v1) / dt + qup) * 0.999, q1);
+            q1 = fmin((fmax(0.0, v1) / dt + qup) * (double)0.999f, q1);      // single-precision literal in irf_route.f90:245
             v1 = v1 - (q1 - qup) * dt;
             q = q1 + qlat;
             qf[(size_t)head * N] = 0.0;

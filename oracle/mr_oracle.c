@@ -556,7 +556,9 @@ static int irf_rch(mro_t *h, int j)
     ntdh = h->uh_ptr[j + 1] - h->uh_ptr[j];
     if (h->RLENGTH[j] > h->min_length_route) {
         for (k = 0; k < ntdh; k++) QF[k] = QF[k] + UH[k] * q_upstream;
-        QF[0] = fmin((fmax(0.0, h->REACH_VOL1[M][j]) / dt + q_upstream) * 0.999, QF[0]);
+        /* "*0.999" is a default-real (single precision) literal in irf_route.f90:245 and the reference is built without
+           -fdefault-real-8 (route/build/Makefile:101): the factor is float32(0.999) = 0.99900001287460327 */
+        QF[0] = fmin((fmax(0.0, h->REACH_VOL1[M][j]) / dt + q_upstream) * (double)0.999f, QF[0]);
         h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] - (QF[0] - q_upstream) * dt;
         h->REACH_Q[M][j] = QF[0] + Qlat;
         for (k = 1; k < ntdh; k++) QF[k - 1] = QF[k];

@@ -511,7 +511,7 @@ class Twin:
         if self.length[j] > self.o.min_length_route:
             for k in range(len(uh)):
                 qf[k] = qf[k] + uh[k] * qup
-            qf[0] = min((max(0.0, self.V1[m][j]) / dt + qup) * 0.999, qf[0])
+            qf[0] = min((max(0.0, self.V1[m][j]) / dt + qup) * _f32(0.999), qf[0])      # single-precision literal, irf_route.f90:245
             self.V1[m][j] = self.V1[m][j] - (qf[0] - qup) * dt
             self.Q[m][j] = qf[0] + qlat
             del qf[0]
