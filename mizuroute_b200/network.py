@@ -55,6 +55,7 @@ class RouteOptions:
     LakeInputOption: int = 0
     runoffMin: float = 0.0
     units_qsim: str = "mm/s"
+    floodplain: bool = False            # <floodplain>: finite bankfull depth for the Euler schemes (KW / MC / DW)
 
     def conv(self):
         """(time_conv, length_conv) exactly as read_control.f90:443-474 derives them."""

@@ -49,7 +49,12 @@
 #define PI_MR 3.14159265359        /* public_var.f90:15 */
 #define SECPRDAY 86400.0
 
-enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, N_METHOD = 3 };
+/* routing method ids = the digits of <route_opt> (public_var.f90:74-80) */
+enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, M_KW = 3, M_MC = 4, M_DW = 5, N_METHOD = 6 };
+/* computational molecules of the Euler schemes (init_model_data.f90:386-393) */
+static const int N_MOLECULE[N_METHOD] = {0, 0, 0, 20, 2, 20};
+#define MAX_MOLECULE 20
+#define HIGH_DEPTH 100000.0        /* globalData.f90:189 */
 
 /* path-coverage counters (tests assert that thinning / shock merging / disaggregation were exercised);
    0 remove_rch calls, 1 shock merges, 2 merged-and-exited, 3 disaggregated groups, 4 max merged series length,
@@ -84,6 +89,9 @@ typedef struct {
     int nLevel, *lev_ptr, *lev_idx; /* level sets for OpenMP sweep */
     /* reach parameters */
     double *RLENGTH, *R_SLOPE, *R_WIDTH, *R_MAN_N, *BASAREA, *UPSAREA, *TOTAREA;
+    /* channel geometry of the Euler schemes (process_ntopo.f90:174-203); <floodplain>, dscale, floodplainSlope (globalData.f90:187-188) */
+    double *R_DEPTH, *SIDE_SLOPE, *FLDP_SLOPE, *R_STORAGE;
+    int floodplain; double dscale, floodplainSlope;
     unsigned char *isLake, *lakeInlet; int *lakeModelType;
     double *D03_MaxStorage, *D03_Coefficient, *D03_Power, *D03_S0;
     /* unit hydrographs */
@@ -95,6 +103,8 @@ typedef struct {
     double *REACH_INFLOW[N_METHOD], *WB[N_METHOD];
     double *QFUTURE_IRF;
     kwave_t *KW;
+    double *MOL[N_METHOD];         /* molecule%Q of KW / MC / DW, [nRch][N_MOLECULE] */
+    double *FLOOD_VOL1[N_METHOD], *REACH_ELE[N_METHOD];
     double *reachRunoff;
     long iTime;                    /* globalData iTime, 1 on the first step */
     int nThreads;
@@ -295,6 +305,7 @@ static void down_index(int nUp, int nSeg, const int *segId, const int *downId, i
 #define ALLOC(p, n) do { (p) = calloc((size_t)((n) > 0 ? (n) : 1), sizeof(*(p))); } while (0)
 
 void mro_destroy(mro_t *h);
+void mro_set_channel(mro_t *h, int floodplain, double dscale, double floodplainSlope);
 
 /* ------------------------------------------------------------------------------------------ */
 /* create: read_streamSeg.f90 inputs -> augment_ntopo (process_ntopo.f90:39-266) -> put_data_struct */
@@ -331,7 +342,7 @@ mro_t *mro_create(int nRch, int nHRU,
     h->nRoutes = 0;
     for (c = route_opt; *c; c++) {
         int id = *c - '0', mm = -1;
-        if (id == 0) mm = M_SUM; else if (id == 1) mm = M_IRF; else if (id == 2) mm = M_KWT;
+        if (id >= 0 && id < N_METHOD) mm = id;
         if (mm < 0 || h->onRoute[mm]) { free(h); return NULL; }
         h->onRoute[mm] = 1; h->routeOrder[h->nRoutes++] = mm;
     }
@@ -399,6 +410,8 @@ mro_t *mro_create(int nRch, int nHRU,
         h->R_WIDTH[i] = width_in ? width_in[i] : wscale * sqrt(h->TOTAREA[i]);
         h->R_MAN_N[i] = man_n_in ? man_n_in[i] : mann_n;
     }
+    ALLOC(h->R_DEPTH, nRch); ALLOC(h->SIDE_SLOPE, nRch); ALLOC(h->FLDP_SLOPE, nRch); ALLOC(h->R_STORAGE, nRch);
+    mro_set_channel(h, 0, 0.000045, 1000.0);
     /* lakes (process_ntopo.f90:476-485; network_topo.f90:958-985) */
     ALLOC(h->isLake, nRch); ALLOC(h->lakeInlet, nRch); ALLOC(h->lakeModelType, nRch);
     ALLOC(h->D03_MaxStorage, nRch); ALLOC(h->D03_Coefficient, nRch); ALLOC(h->D03_Power, nRch); ALLOC(h->D03_S0, nRch);
@@ -443,6 +456,8 @@ mro_t *mro_create(int nRch, int nHRU,
     for (m = 0; m < N_METHOD; m++) {
         ALLOC(h->REACH_Q[m], nRch); ALLOC(h->REACH_VOL0[m], nRch); ALLOC(h->REACH_VOL1[m], nRch);
         ALLOC(h->REACH_INFLOW[m], nRch); ALLOC(h->WB[m], nRch);
+        ALLOC(h->FLOOD_VOL1[m], nRch); ALLOC(h->REACH_ELE[m], nRch);
+        if (N_MOLECULE[m] > 0 && h->onRoute[m]) ALLOC(h->MOL[m], (size_t)nRch * N_MOLECULE[m]);   /* molecule%Q(:) = 0, init_model_data.f90:463-497 */
     }
     ALLOC(h->KW, nRch);
     if (h->onRoute[M_KWT] && is_lake_sim)
@@ -463,7 +478,9 @@ void mro_destroy(mro_t *h)
     free(h->D03_MaxStorage); free(h->D03_Coefficient); free(h->D03_Power); free(h->D03_S0);
     free(h->FRAC_FUTURE); free(h->uh_ptr); free(h->uh_val);
     free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff);
-    for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]); }
+    for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
+                                     free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); }
+    free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
     free(h->QFUTURE_IRF); free(h->KW);
     free(h);
 }
@@ -569,6 +586,298 @@ static int irf_rch(mro_t *h, int j)
         h->REACH_Q[M][j] = QF[0] + Qlat;
         h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0;
     }
+    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* hydraulic.f90: trapezoidal main channel (b, zc) + floodplain (zf) above bankDepth.          */
+/* Integer powers are the multiplication chains a compiler expands x**n to.                    */
+/* ------------------------------------------------------------------------------------------ */
+static double hy_Btop(double y, double b, double zc, double zf, double bd)      /* hydraulic.f90:46-77 */
+{
+    double B;
+    if (y <= bd) return b + 2 * y * zc;
+    B = b + 2 * bd * zc;
+    B = B + zf * (y - bd) * 2;
+    return B;
+}
+static double hy_Pwet(double y, double b, double zc, double zf, double bd)      /* hydraulic.f90:82-113 */
+{
+    double P;
+    if (y <= bd) return b + 2 * y * sqrt(1 + zc * zc);
+    P = b + 2 * bd * sqrt(1 + zc * zc);
+    P = P + 2 * (y - bd) * sqrt(1 + zf * zf);
+    return P;
+}
+static double hy_area(double y, double b, double zc, double zf, double bd)      /* flow_area, hydraulic.f90:118-152 */
+{
+    double A, Bt, Bb;
+    if (y <= bd) return y * (b + zc * y);
+    A = bd * (b + zc * bd);
+    Bt = hy_Btop(y, b, zc, zf, bd); Bb = hy_Btop(bd, b, zc, zf, bd);
+    return A + (y - bd) * (Bt + Bb) / 2.0;
+}
+static double hy_water_height(double area, double b, double zc, double zf, double bd)   /* hydraulic.f90:157-202 */
+{
+    double A_bank = hy_area(bd, b, zc, zf, bd);
+    if (area > A_bank) {
+        double Bb = hy_Btop(bd, b, zc, zf, bd);
+        double disc = Bb * Bb - 4.0 * zf * (A_bank - area);
+        return bd + (-Bb + sqrt(disc)) / (2.0 * zf);
+    }
+    if (zc == 0) return area / b;
+    return (-b + sqrt(b * b + 4.0 * area * zc)) / (2.0 * zc);
+}
+static double hy_flow_depth(double Q, double b, double zc, double S, double n, double zf, double bd)   /* hydraulic.f90:299-420 */
+{
+    const double c13 = 1.0 / 3.0, c23 = 2.0 / 3.0, c53 = 5.0 / 3.0, c103 = 10.0 / 3.0, err_thresh = 0.005, Qmin = 1.e-50;
+    double error = 100.0, depth = 0.0, y0, Coef1, Coef2, A, P, Bt, hh, dhdy, t;
+    if (!(Q > Qmin)) return 0.0;
+    {   /* bankDepth is always passed by the routing schemes: floodplain = .true. */
+        double Abf = hy_area(bd, b, zc, zf, bd), Pbf = hy_Pwet(bd, b, zc, zf, bd), Bbf = hy_Btop(bd, b, zc, zf, bd);
+        double Qbf = Abf * pow(Abf / Pbf, c23) * sqrt(S) / n;
+        if (Q < Qbf) {
+            t = sqrt(S) / n / Q; Coef1 = t * t * t;
+            Coef2 = 2 * sqrt(zc * zc + 1.0);
+            y0 = pow(1.0 / Coef1 / (b * b * b), 1.0 / 5.0);
+            while (error > err_thresh) {
+                double A2, A4, A5;
+                A = hy_area(y0, b, zc, zf, bd); Bt = hy_Btop(y0, b, zc, zf, bd); P = hy_Pwet(y0, b, zc, zf, bd);
+                A2 = A * A; A4 = A2 * A2; A5 = A4 * A;
+                hh = Coef1 * A5 / (P * P) - 1.0;
+                dhdy = Coef1 * (5 * A4 * Bt * P - 2 * Coef2 * A5) / (P * P * P);
+                depth = y0 - hh / dhdy;
+                error = fabs((depth - y0) / depth);
+                y0 = depth;
+            }
+        } else {
+            y0 = bd + 2.0;
+            Coef1 = sqrt(S) / n / pow(Pbf, c23);
+            Coef2 = 2 * pow(zf / 2, c53) * sqrt(S) / n / pow(zf * zf + 1.0, c13);
+            while (error > err_thresh) {
+                double ye = y0 - bd;
+                hh = Coef1 * pow(Abf + Bbf * ye, c53) + Coef2 * pow(ye, c103) / pow(ye, c23) - Q;
+                dhdy = Coef1 * c53 * Bbf * pow(Abf + Bbf * ye, c23) + Coef2 * (c103 - c23) * pow(ye, c53);
+                depth = y0 - hh / dhdy;
+                error = fabs((depth - y0) / depth);
+                y0 = depth;
+            }
+        }
+    }
+    return depth;
+}
+static double hy_friction_slope(double Q, double y, double b, double zc, double n, double zf, double bd)
+{
+    double A = hy_area(y, b, zc, zf, bd), P = hy_Pwet(y, b, zc, zf, bd);
+    double t = Q * n / A / pow(A / P, 2.0 / 3.0);
+    return t * t;
+}
+static double hy_celerity(double Q, double y, double b, double zc, double S, double n, double zf, double bd)   /* hydraulic.f90:425-471 */
+{
+    double Bt, Sf;
+    (void)S;
+    if (!(y > 0.0)) return 0.0;
+    Bt = hy_Btop(y, b, zc, zf, bd);
+    Sf = hy_friction_slope(Q, y, b, zc, n, zf, bd);          /* useFrictionSlope = .true. */
+    return 5.0 / 3.0 * pow(Sf, 0.3) * pow(Q, 0.4) / pow(Bt, 0.4) / pow(n, 0.6);
+}
+static double hy_diffusivity(double Q, double y, double b, double zc, double S, double n, double zf, double bd) /* hydraulic.f90:476-522 */
+{
+    double Bt, Sf;
+    (void)S;
+    if (!(y > 0.0)) return 0.0;
+    Bt = hy_Btop(y, b, zc, zf, bd);
+    Sf = hy_friction_slope(Q, y, b, zc, n, zf, bd);
+    return fabs(Q) / Sf / Bt / 2.0;
+}
+
+/* process_ntopo.f90:174-203: bankfull depth, side / floodplain slopes, bankfull storage */
+void mro_set_channel(mro_t *h, int floodplain, double dscale, double floodplainSlope)
+{
+    int i;
+    h->floodplain = floodplain; h->dscale = dscale; h->floodplainSlope = floodplainSlope;
+    for (i = 0; i < h->nRch; i++) {
+        h->R_DEPTH[i] = floodplain ? dscale * sqrt(h->TOTAREA[i]) : HIGH_DEPTH;
+        h->SIDE_SLOPE[i] = 0.0;
+        h->FLDP_SLOPE[i] = floodplainSlope;
+        h->R_STORAGE[i] = hy_area(h->R_DEPTH[i], h->R_WIDTH[i], h->SIDE_SLOPE[i], h->FLDP_SLOPE[i], h->R_DEPTH[i]) * h->RLENGTH[i];
+    }
+}
+
+/* upstream discharge and lateral flow of a reach, shared by irf_rch / kw_rch / mc_rch / dfw_rch
+   (kwe_route.f90:82-113, mc_route.f90:80-110, dfw_route.f90:86-117) */
+static int euler_inflow(mro_t *h, int M, int j, double *q_upstream, double *Qlat)
+{
+    int nUps = h->nGood[j], m, k, isHW = 1; double qup = 0.0;
+    h->REACH_VOL0[M][j] = h->REACH_VOL1[M][j];
+    *Qlat = 0.0;
+    if (nUps > 0) {
+        isHW = 0;
+        for (k = 0; k < nUps; k++) {
+            m = h->up_ptr[j] + k;
+            if (!h->goodBas[m]) continue;
+            qup = qup + h->REACH_Q[M][h->up_idx[m]];
+        }
+        *Qlat = h->BASIN_QR1[j];
+    } else {
+        if (h->hw_drain_point == 1) { qup = qup + h->BASIN_QR1[j]; *Qlat = 0.0; }
+        else if (h->hw_drain_point == 2) { *Qlat = h->BASIN_QR1[j]; }
+    }
+    h->REACH_INFLOW[M][j] = qup;
+    *q_upstream = qup;
+    return isHW;
+}
+
+/* flood volume and water surface height after the volume update (kwe_route.f90:319-326 and siblings) */
+static void euler_stage(mro_t *h, int M, int j)
+{
+    if (h->REACH_VOL1[M][j] > h->R_STORAGE[j]) h->FLOOD_VOL1[M][j] = h->REACH_VOL1[M][j] - h->R_STORAGE[j];
+    else h->FLOOD_VOL1[M][j] = 0.0;
+    h->REACH_ELE[M][j] = hy_water_height(h->REACH_VOL1[M][j] / h->RLENGTH[j], h->R_WIDTH[j], h->SIDE_SLOPE[j], h->FLDP_SLOPE[j], h->R_DEPTH[j]);
+}
+
+/* advection_diffusion.f90:19-262: solve_ade with its defaults (central difference, Neumann downstream B.C.,
+   wck = wdk = 1) + TDMA.  prev/cur hold nMol nodes; node nMol-1 (1-based) is the reach outlet. */
+static void solve_ade(double L, int nMol, double dtl, double FluxUp, double ck, double dk, const double *prev, double *cur)
+{
+    const double wck = 1.0, wdk = 1.0;
+    double up[MAX_MOLECULE], di[MAX_MOLECULE], lo[MAX_MOLECULE], b[MAX_MOLECULE], D[MAX_MOLECULE], b1[MAX_MOLECULE];
+    const int Nx = nMol - 1;
+    const double dx = L / (Nx - 1);
+    const double Cd = dk * dtl / (dx * dx), Ca = ck * dtl / dx;
+    int i;
+    for (i = 0; i < nMol; i++) { up[i] = 0.0; lo[i] = 0.0; }
+    di[0] = 1.0;
+    for (i = 1; i < nMol - 1; i++) di[i] = 2.0 + 4 * wdk * Cd;
+    di[nMol - 1] = 1.0;
+    for (i = 2; i < nMol; i++) up[i] = wck * Ca - 2.0 * wdk * Cd;
+    for (i = 0; i < nMol - 2; i++) lo[i] = -wck * Ca - 2.0 * wdk * Cd;
+    lo[nMol - 2] = -1.0;
+    b[0] = FluxUp;
+    b[nMol - 1] = prev[nMol - 1] - prev[nMol - 2];
+    for (i = 1; i < nMol - 1; i++)
+        b[i] = ((1.0 - wck) * Ca + 2.0 * (1.0 - wdk) * Cd) * prev[i - 1] + (2.0 - 4.0 * (1.0 - wdk) * Cd) * prev[i]
+             - ((1.0 - wck) * Ca - 2.0 * (1.0 - wdk) * Cd) * prev[i + 1];
+    /* TDMA: up[i] = A(i-1,i), lo[i] = A(i+1,i) */
+    for (i = 0; i < nMol; i++) { D[i] = di[i]; b1[i] = b[i]; }
+    for (i = 1; i < nMol; i++) {
+        double coef = lo[i - 1] / D[i - 1];
+        D[i] = D[i] - coef * up[i];
+        b1[i] = b1[i] - coef * b1[i - 1];
+    }
+    cur[nMol - 1] = b1[nMol - 1] / D[nMol - 1];
+    for (i = nMol - 2; i >= 0; i--) cur[i] = (b1[i] - up[i + 1] * cur[i + 1]) / D[i];
+}
+
+/* kwe_route.f90:40-365 (M_KW, dk = 0) and dfw_route.f90:43-372 (M_DW): one implicit Euler step of the linearised
+   advection(-diffusion) equation on the reach's molecule */
+static int kw_dw_rch(mro_t *h, int M, int j)
+{
+    const int nMol = N_MOLECULE[M];
+    double q_upstream, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * nMol, cur[MAX_MOLECULE];
+    const int isHW = euler_inflow(h, M, j, &q_upstream, &Qlat);
+    const double S = h->R_SLOPE[j], n = h->R_MAN_N[j], bt = h->R_WIDTH[j], bd = h->R_DEPTH[j], zc = h->SIDE_SLOPE[j], zf = h->FLDP_SLOPE[j], L = h->RLENGTH[j];
+    int i;
+    if (!isHW || h->hw_drain_point == 1) {
+        if (L > h->min_length_route) {
+            double Qbar = (q_upstream + mol[0] + mol[nMol - 2]) / 3.0;
+            double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
+            double ck = hy_celerity(fabs(Qbar), depth, bt, zc, S, n, zf, bd);
+            double dk = M == M_DW ? hy_diffusivity(fabs(Qbar), depth, bt, zc, S, n, zf, bd) : 0.0;
+            solve_ade(L, nMol, dt, q_upstream, ck, dk, mol, cur);
+            if (fabs(cur[nMol - 2]) > 0.0) {
+                double volTmp = fmax(0.0, h->REACH_VOL1[M][j]);
+                double qoutTmp = cur[nMol - 2] * dt;
+                double pcntReduc = fmin((volTmp + dt * q_upstream) * 0.999 / qoutTmp, 1.0);
+                for (i = 1; i < nMol; i++) cur[i] = cur[i] * pcntReduc;
+            }
+            h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] + (q_upstream - cur[nMol - 2]) * dt;
+            euler_stage(h, M, j);
+            h->REACH_Q[M][j] = cur[nMol - 2] + Qlat;
+            for (i = 0; i < nMol; i++) mol[i] = cur[i];
+        } else {
+            h->REACH_Q[M][j] = q_upstream + Qlat;
+            for (i = 0; i < nMol; i++) mol[i] = 0.0;
+            mol[nMol - 1] = h->REACH_Q[M][j];
+            h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
+        }
+    } else {
+        h->REACH_Q[M][j] = Qlat;
+        h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
+        for (i = 0; i < nMol; i++) mol[i] = 0.0;
+        mol[nMol - 1] = h->REACH_Q[M][j];
+    }
+    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    return 0;
+}
+
+/* mc_route.f90:45-418: Muskingum-Cunge with sub-stepping when the Courant number exceeds one */
+static int mc_rch(mro_t *h, int j)
+{
+    const int M = M_MC;
+    const double Y = 0.5, Qmin = 1.e-50;
+    double q_upstream, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * 2;
+    const int isHW = euler_inflow(h, M, j, &q_upstream, &Qlat);
+    const double S = h->R_SLOPE[j], n = h->R_MAN_N[j], bt = h->R_WIDTH[j], bd = h->R_DEPTH[j], zc = h->SIDE_SLOPE[j], zf = h->FLDP_SLOPE[j], L = h->RLENGTH[j];
+    double Q00 = mol[0], Q01 = mol[1], Q10, Q11;
+    if (!isHW || h->hw_drain_point == 1) {
+        if (L > h->min_length_route) {
+            double theta = dt / L, Qbar;
+            Q10 = q_upstream;
+            Qbar = (Q00 + Q10 + Q01) / 3.0;
+            if (Qbar > Qmin) {
+                double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
+                double ck = hy_celerity(fabs(Qbar), depth, bt, zc, S, n, zf, bd);
+                double Cn = ck * theta, dTsub = dt, QinPrev, QoutPrev, sum = 0.0;
+                int ntSub = 1, ix;
+                if (Cn > 1.0) { ntSub = (int)ceil(dt / L * ck); dTsub = dt / ntSub; }
+                QinPrev = Q00; QoutPrev = Q01;
+                for (ix = 1; ix <= ntSub; ix++) {
+                    double Qin = Q10, Qout;
+                    Qbar = (Qin + QinPrev + QoutPrev) / 3.0;
+                    if (Qbar > Qmin) {
+                        double topWidth, X, C0, C1, C2;
+                        depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
+                        topWidth = hy_Btop(depth, bt, zc, zf, bd);
+                        ck = hy_celerity(fabs(Qbar), depth, bt, zc, S, n, zf, bd);
+                        X = 0.5 * (1.0 - Qbar / (topWidth * S * ck * L));
+                        Cn = ck * dTsub / L;
+                        C0 = (-X + Cn * (1 - Y)) / (1 - X + Cn * (1 - Y));
+                        C1 = (X + Cn * Y) / (1 - X + Cn * (1 - Y));
+                        C2 = (1 - X - Cn * Y) / (1 - X + Cn * (1 - Y));
+                        Qout = C0 * Qin + C1 * QinPrev + C2 * QoutPrev;
+                        Qout = fmax(0.0, Qout);
+                    } else Qout = 0.0;
+                    sum = sum + Qout;
+                    QinPrev = Qin; QoutPrev = Qout;
+                }
+                Q11 = sum / (double)ntSub;
+                if (fabs(Q11) > 0.0) {
+                    /* "*0.999" is a single-precision literal here (mc_route.f90:352), unlike kwe/dfw_route */
+                    double pcntReduc = fmin((h->REACH_VOL1[M][j] / dt + Q10) * (double)0.999f / Q11, 1.0);
+                    Q11 = Q11 * pcntReduc;
+                }
+                h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] + (Q10 - Q11) * dt;
+                euler_stage(h, M, j);
+                h->REACH_Q[M][j] = Q11 + Qlat;
+            } else {
+                Q11 = 0.0;
+                h->REACH_Q[M][j] = Q11 + Qlat;
+                h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] + (Q10 - Q11) * dt;
+                euler_stage(h, M, j);
+            }
+        } else {
+            Q10 = q_upstream; Q11 = q_upstream;
+            h->REACH_Q[M][j] = q_upstream + Qlat;
+            h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
+        }
+    } else {
+        Q10 = 0.0; Q11 = 0.0;
+        h->REACH_Q[M][j] = Qlat;
+        h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
+    }
+    mol[0] = Q10; mol[1] = Q11;
     comp_reach_wb(h, M, j, q_upstream, Qlat);
     return 0;
 }
@@ -1005,6 +1314,8 @@ static int route_one(mro_t *h, int M, int j, double T0, double T1, wave_buf_t *b
     if (h->isLake[j] && h->is_lake_sim && M != M_SUM) return lake_route(h, j, M);
     if (M == M_SUM) return accum_inst_runoff(h, j);
     if (M == M_IRF) return irf_rch(h, j);
+    if (M == M_KW || M == M_DW) return kw_dw_rch(h, M, j);
+    if (M == M_MC) return mc_rch(h, j);
     return kwt_rch(h, j, T0, T1, b);
 }
 
@@ -1119,6 +1430,9 @@ int mro_set(mro_t *h, int method, int field, const double *in)
     memcpy(dst, in, sizeof(double) * h->nRch);
     return 0;
 }
+int mro_n_molecule(int method) { return method >= 0 && method < N_METHOD ? N_MOLECULE[method] : 0; }
+void mro_get_molecule(mro_t *h, int method, double *out) { if (h->MOL[method]) memcpy(out, h->MOL[method], sizeof(double) * (size_t)h->nRch * N_MOLECULE[method]); }
+void mro_set_molecule(mro_t *h, int method, const double *in) { if (h->MOL[method]) memcpy(h->MOL[method], in, sizeof(double) * (size_t)h->nRch * N_MOLECULE[method]); }
 void mro_set_itime(mro_t *h, long it) { h->iTime = it; }
 void mro_set_threads(mro_t *h, int n) { h->nThreads = n > 0 ? n : 1; }
 /* KWT state in the restart layout [seg][wave] (write_restart_pio.f90:1039-1134), wave dimension = cap */

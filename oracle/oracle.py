@@ -15,8 +15,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-M_SUM, M_IRF, M_KWT = 0, 1, 2
-METHOD_OF_DIGIT = {"0": M_SUM, "1": M_IRF, "2": M_KWT}
+M_SUM, M_IRF, M_KWT, M_KW, M_MC, M_DW = range(6)        # = the digits of <route_opt> (public_var.f90:74-80)
+METHOD_OF_DIGIT = {str(m): m for m in range(6)}
+N_MOLECULE = {M_KW: 20, M_MC: 2, M_DW: 20}               # init_model_data.f90:386-393
 F_REACH_Q, F_REACH_VOL1, F_REACH_INFLOW, F_WB, F_BASIN_QI, F_BASIN_QR1, F_BASIN_QR0, F_REACH_VOL0 = range(8)
 F_WIDTH, F_TOTAREA, F_BASAREA, F_SLOPE = 10, 11, 12, 13
 KW_CAP = 24
@@ -75,6 +76,8 @@ class Oracle:
             C.c_int(n_threads)))
         if not self.h:
             raise OracleError(-1, "mro_create failed (bad route_opt or UH construction)")
+        if getattr(opts, "floodplain", False):          # <floodplain> T: bankfull depth dscale*sqrt(totalArea) (process_ntopo.f90:174-203)
+            L.mro_set_channel(self.h, C.c_int(1), dbl(0.000045), dbl(1000.0))
         self.T0, self.T1 = 0.0, float(opts.dt)      # init_model_data.f90:600
 
     def __del__(self):
@@ -117,6 +120,17 @@ class Oracle:
     def set(self, field: int, values, method: int = M_IRF):
         v = np.ascontiguousarray(values, dtype=np.float64)
         assert lib().mro_set(self.h, C.c_int(method), C.c_int(field), _p(v, C.c_double)) == 0
+
+    def molecule(self, method: int) -> np.ndarray:
+        """molecule%Q of an Euler scheme, [nRch, N_MOLECULE[method]]."""
+        out = np.empty((self.net.nRch, N_MOLECULE[method]))
+        lib().mro_get_molecule(self.h, C.c_int(method), _p(out, C.c_double))
+        return out
+
+    def set_molecule(self, method: int, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape == (self.net.nRch, N_MOLECULE[method])
+        lib().mro_set_molecule(self.h, C.c_int(method), _p(v, C.c_double))
 
     # --- unit hydrographs -------------------------------------------------------------------
     def frac_future(self) -> np.ndarray:

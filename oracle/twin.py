@@ -176,6 +176,118 @@ def make_uh(length, dt, velo, diff):
 
 
 # ---------------------------------------------------------------- KWT helpers
+# -- hydraulic.f90 (trapezoid + floodplain above bankDepth); written independently of the C oracle ----------------
+def hy_btop(y, b, zc, zf, bd):
+    if y <= bd:
+        return b + 2 * y * zc
+    return (b + 2 * bd * zc) + zf * (y - bd) * 2
+
+
+def hy_pwet(y, b, zc, zf, bd):
+    if y <= bd:
+        return b + 2 * y * math.sqrt(1 + zc * zc)
+    return (b + 2 * bd * math.sqrt(1 + zc * zc)) + 2 * (y - bd) * math.sqrt(1 + zf * zf)
+
+
+def hy_area(y, b, zc, zf, bd):
+    if y <= bd:
+        return y * (b + zc * y)
+    return bd * (b + zc * bd) + (y - bd) * (hy_btop(y, b, zc, zf, bd) + hy_btop(bd, b, zc, zf, bd)) / 2.0
+
+
+def hy_water_height(area, b, zc, zf, bd):
+    a_bank = hy_area(bd, b, zc, zf, bd)
+    if area > a_bank:
+        bb = hy_btop(bd, b, zc, zf, bd)
+        return bd + (-bb + math.sqrt(bb * bb - 4.0 * zf * (a_bank - area))) / (2.0 * zf)
+    if zc == 0:
+        return area / b
+    return (-b + math.sqrt(b * b + 4.0 * area * zc)) / (2.0 * zc)
+
+
+def hy_flow_depth(q, b, zc, s, n, zf, bd):
+    """Normal depth by Newton-Raphson to 0.5 % (hydraulic.f90:299-420)."""
+    if not q > 1.0e-50:
+        return 0.0
+    err, depth = 100.0, 0.0
+    abf, pbf, bbf = hy_area(bd, b, zc, zf, bd), hy_pwet(bd, b, zc, zf, bd), hy_btop(bd, b, zc, zf, bd)
+    qbf = abf * (abf / pbf) ** (2.0 / 3.0) * math.sqrt(s) / n
+    if q < qbf:
+        t = math.sqrt(s) / n / q
+        c1 = t * t * t
+        c2 = 2 * math.sqrt(zc * zc + 1.0)
+        y0 = (1.0 / c1 / (b * b * b)) ** (1.0 / 5.0)
+        while err > 0.005:
+            a, bt, p = hy_area(y0, b, zc, zf, bd), hy_btop(y0, b, zc, zf, bd), hy_pwet(y0, b, zc, zf, bd)
+            a2 = a * a
+            a4 = a2 * a2
+            a5 = a4 * a
+            hh = c1 * a5 / (p * p) - 1.0
+            dh = c1 * (5 * a4 * bt * p - 2 * c2 * a5) / (p * p * p)
+            depth = y0 - hh / dh
+            err = abs((depth - y0) / depth)
+            y0 = depth
+    else:
+        y0 = bd + 2.0
+        c1 = math.sqrt(s) / n / pbf ** (2.0 / 3.0)
+        c2 = 2 * (zf / 2) ** (5.0 / 3.0) * math.sqrt(s) / n / (zf * zf + 1.0) ** (1.0 / 3.0)
+        while err > 0.005:
+            ye = y0 - bd
+            hh = c1 * (abf + bbf * ye) ** (5.0 / 3.0) + c2 * ye ** (10.0 / 3.0) / ye ** (2.0 / 3.0) - q
+            dh = c1 * (5.0 / 3.0) * bbf * (abf + bbf * ye) ** (2.0 / 3.0) + c2 * (10.0 / 3.0 - 2.0 / 3.0) * ye ** (5.0 / 3.0)
+            depth = y0 - hh / dh
+            err = abs((depth - y0) / depth)
+            y0 = depth
+    return depth
+
+
+def _hy_sf(q, y, b, zc, n, zf, bd):
+    a, p = hy_area(y, b, zc, zf, bd), hy_pwet(y, b, zc, zf, bd)
+    t = q * n / a / (a / p) ** (2.0 / 3.0)
+    return t * t
+
+
+def hy_celerity(q, y, b, zc, s, n, zf, bd):
+    if not y > 0.0:
+        return 0.0
+    return 5.0 / 3.0 * _hy_sf(q, y, b, zc, n, zf, bd) ** 0.3 * q ** 0.4 / hy_btop(y, b, zc, zf, bd) ** 0.4 / n ** 0.6
+
+
+def hy_diffusivity(q, y, b, zc, s, n, zf, bd):
+    if not y > 0.0:
+        return 0.0
+    return abs(q) / _hy_sf(q, y, b, zc, n, zf, bd) / hy_btop(y, b, zc, zf, bd) / 2.0
+
+
+def solve_ade(length, prev, dt, q_up, ck, dk):
+    """advection_diffusion.f90: implicit central-difference step with a Neumann outlet, Thomas algorithm.  Written on the
+    matrix rows (sub / diag / super per row) rather than the reference's column-stored diagonals."""
+    nm = len(prev)
+    dx = length / (nm - 2)
+    cd = dk * dt / (dx * dx)
+    ca = ck * dt / dx
+    sub = [0.0] * nm      # A[i][i-1]
+    dia = [0.0] * nm
+    sup = [0.0] * nm      # A[i][i+1]
+    rhs = [0.0] * nm
+    dia[0], rhs[0] = 1.0, q_up
+    for i in range(1, nm - 1):
+        sub[i] = -1.0 * ca - 2.0 * 1.0 * cd
+        dia[i] = 2.0 + 4 * 1.0 * cd
+        sup[i] = 1.0 * ca - 2.0 * 1.0 * cd
+        rhs[i] = (0.0 * ca + 2.0 * 0.0 * cd) * prev[i - 1] + (2.0 - 4.0 * 0.0 * cd) * prev[i] - (0.0 * ca - 2.0 * 0.0 * cd) * prev[i + 1]
+    sub[nm - 1], dia[nm - 1], rhs[nm - 1] = -1.0, 1.0, prev[nm - 1] - prev[nm - 2]
+    for i in range(1, nm):
+        c = sub[i] / dia[i - 1]
+        dia[i] = dia[i] - c * sup[i - 1]
+        rhs[i] = rhs[i] - c * rhs[i - 1]
+    out = [0.0] * nm
+    out[nm - 1] = rhs[nm - 1] / dia[nm - 1]
+    for i in range(nm - 2, -1, -1):
+        out[i] = (rhs[i] - sup[i] * out[i + 1]) / dia[i]
+    return out
+
+
 class Wave:
     __slots__ = ("QF", "TI", "TR", "RF")
 
@@ -348,7 +460,7 @@ class Twin:
         n = net.nRch
         self.n = n
         self.tc, self.lc = opts.conv()
-        self.methods = [int(c) for c in opts.route_opt]      # 0 SUM, 1 IRF, 2 KWT
+        self.methods = [int(c) for c in opts.route_opt]      # 0 SUM, 1 IRF, 2 KWT, 3 KW, 4 MC, 5 DW
         seg = [int(v) for v in net.segId]
         id2ix = {}
         for i, s in enumerate(seg):
@@ -414,11 +526,20 @@ class Twin:
         self.QR0 = [0.0] * n
         self.QR1 = [0.0] * n
         self.qfut = [[0.0] * len(self.ff) for _ in range(n)]
-        self.Q = {m: [0.0] * n for m in (0, 1, 2)}
-        self.V0 = {m: [0.0] * n for m in (0, 1, 2)}
-        self.V1 = {m: [0.0] * n for m in (0, 1, 2)}
-        self.INF = {m: [0.0] * n for m in (0, 1, 2)}
-        self.WB = {m: [0.0] * n for m in (0, 1, 2)}
+        self.Q = {m: [0.0] * n for m in range(6)}
+        self.V0 = {m: [0.0] * n for m in range(6)}
+        self.V1 = {m: [0.0] * n for m in range(6)}
+        self.INF = {m: [0.0] * n for m in range(6)}
+        self.WB = {m: [0.0] * n for m in range(6)}
+        # Euler schemes: channel geometry (process_ntopo.f90:174-203) and molecules (init_model_data.f90:386-393,463-497)
+        fp = bool(getattr(opts, "floodplain", False))
+        self.depth = [0.000045 * math.sqrt(self.tot[i]) if fp else 100000.0 for i in range(n)]
+        self.zc = [0.0] * n
+        self.zf = [1000.0] * n
+        self.storage = [hy_area(self.depth[i], self.width[i], self.zc[i], self.zf[i], self.depth[i]) * self.length[i] for i in range(n)]
+        self.mol = {m: [[0.0] * k for _ in range(n)] for m, k in ((3, 20), (4, 2), (5, 20)) if m in self.methods}
+        self.FLOOD = {m: [0.0] * n for m in (3, 4, 5)}
+        self.ELE = {m: [0.0] * n for m in (3, 4, 5)}
         self.KW = [None] * n
         if 2 in self.methods and opts.is_lake_sim:
             for i in range(n):
@@ -473,8 +594,12 @@ class Twin:
                     self._sum(j)
                 elif m == 1:
                     self._irf(j)
-                else:
+                elif m == 2:
                     self._kwt(j, self.T0, self.T1)
+                elif m == 4:
+                    self._mc(j)
+                else:
+                    self._kw_dw(j, m)
         self.T0 = self.T1
         self.T1 = self.T0 + float(o.dt)
         self.itime += 1
@@ -523,6 +648,123 @@ class Twin:
             self.Q[m][j] = qf[0] + qlat
             self.V0[m][j] = 0.0
             self.V1[m][j] = 0.0
+        self._wb(m, j, qup, qlat)
+
+    # -- Euler schemes: kwe_route.f90, dfw_route.f90, mc_route.f90 ---------------------------------
+    def _inflow(self, j, m):
+        self.V0[m][j] = self.V1[m][j]
+        qup, head = 0.0, True
+        if self.ngood[j] > 0:
+            head = False
+            for u in self.ups[j][: self.ngood[j]]:
+                qup = qup + self.Q[m][u]
+            qlat = self.QR1[j]
+        elif self.o.hw_drain_point == 1:
+            qup = qup + self.QR1[j]
+            qlat = 0.0
+        else:
+            qlat = self.QR1[j]
+        self.INF[m][j] = qup
+        return qup, qlat, head
+
+    def _geom(self, j):
+        return self.width[j], self.zc[j], self.slope[j], self.man_n[j], self.zf[j], self.depth[j]
+
+    def _stage(self, j, m):
+        v = self.V1[m][j]
+        self.FLOOD[m][j] = v - self.storage[j] if v > self.storage[j] else 0.0
+        b, zc, _, _, zf, bd = self._geom(j)
+        self.ELE[m][j] = hy_water_height(v / self.length[j], b, zc, zf, bd)
+
+    def _dry(self, j, m):
+        self.V0[m][j] = self.V1[m][j] = 0.0
+        self.FLOOD[m][j] = self.ELE[m][j] = 0.0
+
+    def _kw_dw(self, j, m):
+        dt, L = self.o.dt, self.length[j]
+        qup, qlat, head = self._inflow(j, m)
+        mol = self.mol[m][j]
+        nm = len(mol)
+        if (not head) or self.o.hw_drain_point == 1:
+            if L > self.o.min_length_route:
+                b, zc, s, n, zf, bd = self._geom(j)
+                qbar = abs((qup + mol[0] + mol[nm - 2]) / 3.0)
+                y = hy_flow_depth(qbar, b, zc, s, n, zf, bd)
+                ck = hy_celerity(qbar, y, b, zc, s, n, zf, bd)
+                dk = hy_diffusivity(qbar, y, b, zc, s, n, zf, bd) if m == 5 else 0.0
+                cur = solve_ade(L, mol, dt, qup, ck, dk)
+                if abs(cur[nm - 2]) > 0.0:
+                    red = min((max(0.0, self.V1[m][j]) + dt * qup) * 0.999 / (cur[nm - 2] * dt), 1.0)
+                    for i in range(1, nm):
+                        cur[i] = cur[i] * red
+                self.V1[m][j] = self.V1[m][j] + (qup - cur[nm - 2]) * dt
+                self._stage(j, m)
+                self.Q[m][j] = cur[nm - 2] + qlat
+                self.mol[m][j] = cur
+            else:
+                self.Q[m][j] = qup + qlat
+                self.mol[m][j] = [0.0] * (nm - 1) + [self.Q[m][j]]
+                self._dry(j, m)
+        else:
+            self.Q[m][j] = qlat
+            self.mol[m][j] = [0.0] * (nm - 1) + [qlat]
+            self._dry(j, m)
+        self._wb(m, j, qup, qlat)
+
+    def _mc(self, j):
+        m, dt, L = 4, self.o.dt, self.length[j]
+        qup, qlat, head = self._inflow(j, m)
+        q00, q01 = self.mol[m][j]
+        q10 = q11 = 0.0
+        if (not head) or self.o.hw_drain_point == 1:
+            q10 = qup
+            if L > self.o.min_length_route:
+                b, zc, s, n, zf, bd = self._geom(j)
+                qbar = (q00 + q10 + q01) / 3.0
+                if qbar > 1.0e-50:
+                    y = hy_flow_depth(abs(qbar), b, zc, s, n, zf, bd)
+                    ck = hy_celerity(abs(qbar), y, b, zc, s, n, zf, bd)
+                    nsub, dtsub = 1, dt
+                    if ck * (dt / L) > 1.0:
+                        nsub = int(math.ceil(dt / L * ck))
+                        dtsub = dt / nsub
+                    qin = [q00] + [q10] * nsub
+                    qout = [q01] + [0.0] * nsub
+                    for ix in range(1, nsub + 1):
+                        qbar = (qin[ix] + qin[ix - 1] + qout[ix - 1]) / 3.0
+                        if qbar > 1.0e-50:
+                            y = hy_flow_depth(abs(qbar), b, zc, s, n, zf, bd)
+                            tw = hy_btop(y, b, zc, zf, bd)
+                            ck = hy_celerity(abs(qbar), y, b, zc, s, n, zf, bd)
+                            x = 0.5 * (1.0 - qbar / (tw * s * ck * L))
+                            cn = ck * dtsub / L
+                            den = 1 - x + cn * (1 - 0.5)
+                            c0 = (-x + cn * (1 - 0.5)) / den
+                            c1 = (x + cn * 0.5) / den
+                            c2 = (1 - x - cn * 0.5) / den
+                            qout[ix] = max(0.0, c0 * qin[ix] + c1 * qin[ix - 1] + c2 * qout[ix - 1])
+                    tot = 0.0
+                    for v in qout[1:]:
+                        tot = tot + v
+                    q11 = tot / float(nsub)
+                    if abs(q11) > 0.0:
+                        q11 = q11 * min((self.V1[m][j] / dt + q10) * _f32(0.999) / q11, 1.0)     # single-precision literal, mc_route.f90:352
+                    self.V1[m][j] = self.V1[m][j] + (q10 - q11) * dt
+                    self._stage(j, m)
+                    self.Q[m][j] = q11 + qlat
+                else:
+                    q11 = 0.0
+                    self.Q[m][j] = q11 + qlat
+                    self.V1[m][j] = self.V1[m][j] + (q10 - q11) * dt
+                    self._stage(j, m)
+            else:
+                q11 = qup
+                self.Q[m][j] = qup + qlat
+                self._dry(j, m)
+        else:
+            self.Q[m][j] = qlat
+            self._dry(j, m)
+        self.mol[m][j] = [q10, q11]
         self._wb(m, j, qup, qlat)
 
     def _lake(self, j, m):

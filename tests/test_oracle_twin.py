@@ -62,3 +62,40 @@ def test_openmp_level_sweep_equals_serial_sweep():
     a = orc.Oracle(net, params, opts, n_threads=1).run(ro)
     b = orc.Oracle(net, params, opts, n_threads=4).run(ro)
     assert np.array_equal(a, b)
+
+
+EULER_CASES = [
+    dict(kind="random", n=60, seed=5, dt=3600.0, steps=40, zero_area_frac=0.08),
+    dict(kind="random", n=60, seed=6, dt=86400.0, steps=20),                      # Courant > 1: Muskingum-Cunge sub-steps
+    dict(kind="conus", n=300, seed=4, dt=86400.0, steps=10, lakes=5),
+    dict(kind="random", n=50, seed=7, dt=900.0, steps=30, hw_drain_point=1),
+    dict(kind="binary", n=63, seed=2, dt=10800.0, steps=20, floodplain=True),     # finite bankfull depth: over-bank branch
+]
+
+
+@pytest.mark.parametrize("kw", EULER_CASES, ids=lambda k: "%s-%g%s" % (k["kind"], k["dt"], "-fp" if k.get("floodplain") else ""))
+def test_euler_schemes_kw_mc_dw(kw):
+    """<route_opt> 3 / 4 / 5 (kwe_route.f90, mc_route.f90, dfw_route.f90 over hydraulic.f90 + advection_diffusion.f90):
+    the C restatement and the separately written twin agree to round-off, and the reach water balance closes."""
+    kw = dict(kw)
+    fp = kw.pop("floodplain", False)
+    net, params, opts, ro = case(route_opt="345", **kw)
+    opts.floodplain = fp
+    o, t, q, qt = _both(net, params, opts, ro)
+    for i, m in enumerate(t.methods):
+        assert rel_err(q[i], np.array(qt[m])) <= 1e-12
+        assert np.array_equal(o.molecule(m), np.array(t.mol[m]))
+        lake = net.islake == 1 if (opts.is_lake_sim and net.islake is not None) else np.zeros(net.nRch, bool)
+        scale = np.maximum(np.abs(o.get(orc.F_REACH_VOL1, m)), 1.0)
+        assert np.max(np.abs(o.get(orc.F_WB, m))[~lake] / scale[~lake]) < 1e-9
+    if fp:
+        assert max(max(t.FLOOD[m]) for m in t.methods) > 0.0
+
+
+def test_euler_schemes_reach_the_steady_state_of_constant_runoff():
+    """Constant runoff long enough: every scheme's discharge tends to the accumulated runoff (method 0)."""
+    net, params, opts, ro = case("random", n=40, seed=3, dt=3600.0, route_opt="0345", steps=1)
+    ro = np.repeat(ro, 600, axis=0)
+    q = orc.Oracle(net, params, opts).run(ro)
+    for i in (1, 2, 3):
+        assert rel_err(q[i, -1], q[0, -1]) < 2e-3
