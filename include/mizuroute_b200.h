@@ -35,7 +35,8 @@ extern "C" {
 #define MR_KW_SLOTS 22           /* KWAVE(0:NQ2+1) can momentarily hold 21 entries (kwt_route.f90:299) */
 
 /* routing-method ids, public_var.f90:74-80 */
-enum { MR_ACCUM_RUNOFF = 0, MR_IMPULSE_RESPONSE_FUNC = 1, MR_KINEMATIC_WAVE_TRACKING = 2 };
+enum { MR_ACCUM_RUNOFF = 0, MR_IMPULSE_RESPONSE_FUNC = 1, MR_KINEMATIC_WAVE_TRACKING = 2,
+       MR_KINEMATIC_WAVE = 3, MR_MUSKINGUM_CUNGE = 4, MR_DIFFUSIVE_WAVE = 5 };
 
 /* flux fields of STRFLX (dataTypes.f90:346-377) readable with mr_get_flux */
 enum {
@@ -60,7 +61,10 @@ enum {
     MR_ST_KWT_TENTRY    = 6,   /* double [nRch][MR_KW_SLOTS]   "tentry"       */
     MR_ST_KWT_TEXIT     = 7,   /* double [nRch][MR_KW_SLOTS]   "texit"        */
     MR_ST_KWT_ROUTED    = 8,   /* int    [nRch][MR_KW_SLOTS]   "routed"       */
-    MR_ST_LAKE_VOL      = 9    /* double [nRoutes][nRch]       REACH_VOL(1) of every active method */
+    MR_ST_LAKE_VOL      = 9,   /* double [nRoutes][nRch]       REACH_VOL(1) of every active method ("volume_irf|kwt|kw|mc|dw") */
+    MR_ST_MOLECULE_KW   = 10,  /* double [nRch][20]            "q_sub_kw": molecule%Q of the kinematic wave (init_model_data.f90:388) */
+    MR_ST_MOLECULE_MC   = 11,  /* double [nRch][2]             "q_sub_mc": inflow / outflow of the previous step */
+    MR_ST_MOLECULE_DW   = 12   /* double [nRch][20]            "q_sub_dw" */
 };
 
 /* integer facts about a handle, mr_get_info */
@@ -93,6 +97,10 @@ typedef struct {
     double mann_n, wscale;       /* &KWT    */
     int    device;               /* CUDA device ordinal */
     int    max_batch;            /* largest nSteps a batch call may pass (sizes the resident series) */
+    /* Euler schemes (route methods 3/4/5) only; zero = the reference's defaults */
+    int    floodplain;           /* <floodplain>: 1 = finite bankfull depth dscale*sqrt(totalArea), 0 = high_depth (process_ntopo.f90:174-196) */
+    double dscale;               /* bankfull depth scaling, 0 -> 0.000045 (globalData.f90:187) */
+    double floodplainSlope;      /* floodplain slope h:v, 0 -> 1000 (globalData.f90:188) */
 } mr_options;
 
 /* Replaces init_route_method + the option globals (init_model_data.f90:753-805, public_var.f90). */

@@ -20,7 +20,8 @@ R_WIDTH, TOTAREA, BASAREA, R_SLOPE, NGOOD = 10, 11, 12, 13, 14
 KW_PITCH = 24            # particle-row pitch of an exchange record
 # state variables
 (ST_BASIN_QFUTURE, ST_BASIN_QR, ST_IRF_QFUTURE, ST_IRF_VOL, ST_KWT_NWAVE, ST_KWT_QWAVE, ST_KWT_TENTRY,
- ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL) = range(10)
+ ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL, ST_MOLECULE_KW, ST_MOLECULE_MC, ST_MOLECULE_DW) = range(13)
+N_MOLECULE = {3: 20, 4: 2, 5: 20}     # nodes of the Euler schemes' molecules (route methods 3 KW, 4 MC, 5 DW)
 # info keys
 (INFO_NRCH, INFO_NHRU, INFO_NSTAGE, INFO_NTDH_BAS, INFO_MAXTDH, INFO_LAUNCHES_LAST, INFO_STEPS_DONE,
  INFO_MAX_BATCH, INFO_MAX_NUPS, INFO_KWT_PARTICLES, INFO_DEVICE_BYTES, INFO_KWT_TOUCHED, INFO_NHEAD, INFO_SUM_NTDH,
@@ -57,6 +58,9 @@ class mr_options(C.Structure):
         ("wscale", C.c_double),
         ("device", C.c_int),
         ("max_batch", C.c_int),
+        ("floodplain", C.c_int),
+        ("dscale", C.c_double),
+        ("floodplainSlope", C.c_double),
     ]
 
 

@@ -2,7 +2,9 @@
 // (mr_kernels.cuh), the warp-cooperative KWT code (mr_kwt.cuh) and its single-lane host build (tests/emul).
 #pragma once
 #include <cfloat>
+#include <cmath>
 #include <cstdint>
+#include <cstring>
 #include "../../include/mizuroute_b200.h"
 #include "mr_lanes.h"
 
@@ -18,7 +20,10 @@ constexpr int POOL_S = 88;            // with the full-capacity scratch in the g
 constexpr int NKIN = MR_MAXQPAR + 2;  // kinwav work arrays (1-based, <= 19 particles routed)
 
 enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
-enum { M_SUM = 0, M_IRF = 1, M_KWT = 2 };
+enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, M_KW = 3, M_MC = 4, M_DW = 5, N_METHODS = 6 };   // = digits of <route_opt>, public_var.f90:74-80
+// computational molecules of the Euler schemes (init_model_data.f90:386-393): KW 20, MC 2, DW 20 nodes per reach
+constexpr int n_molecule(int m) { return m == M_KW || m == M_DW ? 20 : (m == M_MC ? 2 : 0); }
+template <int M> constexpr int NMOL = (M == M_KW || M == M_DW) ? 20 : (M == M_MC ? 2 : 0);      // the same, usable in device code
 
 struct DevNet {
     int nRch, nHRU, nStage, ntdhBas, maxtdh;
@@ -32,18 +37,21 @@ struct DevNet {
     const double *uh, *fracFuture;
     const double *kwK, *kwAK;       // KWT: sqrt(R_SLOPE)/R_MAN_N and ALFA*K**(1/ALFA) per reach (kwt_route.f90:1283-1296)
     const double *d03MaxS, *d03Coef, *d03Pow, *d03S0;
+    const double *rdepth, *sideSlope, *fldpSlope, *rstorage;   // Euler schemes: bankfull depth, side / floodplain slopes, bankfull storage
     // forcing and per-step times
     const double *runoff, *T0s, *T1s;
     // state and fluxes
     double *qfutBas, *qrSer, *basinQI;
-    double *qSer[3], *vol0[3], *vol1[3], *inflow[3], *wb[3];
+    double *qSer[N_METHODS], *vol0[N_METHODS], *vol1[N_METHODS], *inflow[N_METHODS], *wb[N_METHODS];
+    double *mol[N_METHODS];         // molecule%Q of KW / MC / DW, node-major [n_molecule][nRch]
+    double *floodVol[N_METHODS], *reachEle[N_METHODS];
     double *qfutIrf;
     int *kwN[2], *kwNR[2];
     double *kwQF[2], *kwTI[2], *kwTR[2];
     // multi-domain hand-off: per-step records of exported outlets / imported ghosts, [slot][kmax][recLen]
     const int *expSlot, *impSlot;   // by position, -1 = none (nullptr = feature off)
     double *expBuf; const double *impBuf;
-    int recLen, kmax, nRoutes, routeSlot[3];
+    int recLen, kmax, nRoutes, routeSlot[N_METHODS];
     void *kwArena; unsigned long long *kwArenaMask;   // full-capacity KWT scratch: 64 slots per SM + their busy bits
     int *err;                       // [0] code (0 = ok) [1] position [2] site
     unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
@@ -65,5 +73,18 @@ MR_DEV_NOINLINE void raise(int *err, int code, int p, int site) {
 #endif
 }
 
+// one out-of-line copy of pow(): its inlined body is ~250 instructions per call site
+#if defined(MR_TEST_POW_NOISE) && !defined(__CUDACC__)
+// Host test builds only (tests/test_kwt_conditioning.py, tests/test_euler_emul.py): pow() perturbed by -1/0/+1 ulp, pseudo-randomly, to measure how
+// a case reacts to the last-ulp differences between two correct pow() implementations (libm vs the device).
+inline double mr_pow(double x, double y) {
+    const double r = pow(x, y);
+    unsigned long long u; memcpy(&u, &x, 8);
+    u = (u * 0x9E3779B97F4A7C15ull + (unsigned long long)(MR_TEST_POW_NOISE)) >> 61;
+    return u < 3 ? nextafter(r, 1e300) : (u < 6 ? nextafter(r, -1e300) : r);
+}
+#else
+MR_DEV_NOINLINE double mr_pow(double x, double y) { return pow(x, y); }
+#endif
 
 }  // namespace mr

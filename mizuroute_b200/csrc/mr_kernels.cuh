@@ -16,12 +16,14 @@
 //   k_headwater<M>  reaches without upstream reaches, all steps of the batch in one launch
 //   k_route<M>    one time-skewed wavefront of route_network (main_route.f90:356-403), thread per (reach, step):
 //                 M=0 accum_inst_runoff (accum_runoff.f90:60-75), M=1 irf_rch+conv_upsbas_qr
-//                 (irf_route.f90:82-150,235-262); lake reaches branch to lake_route (lake_route.f90:87-229)
+//                 (irf_route.f90:82-150,235-262), M=3/4/5 the Euler schemes kw_rch / mc_rch / dfw_rch (mr_euler.cuh);
+//                 lake reaches branch to lake_route (lake_route.f90:87-229)
 //   k_route_kwt   the same for kwt_rch and callees (kwt_route.f90:36-1622), half-warp team per (reach, step)
 //   k_export_pack / k_import_unpack   tributary -> mainstem hand-off records (mpi_process.f90:1238-1329)
 #pragma once
 #include "mr_dev.h"
 #include "mr_kwt.cuh"
+#include "mr_euler.cuh"
 
 namespace mr {
 
@@ -281,6 +283,10 @@ __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long 
         Qs[p] = q;
         d.vol0[M_IRF][p] = v0; d.vol1[M_IRF][p] = v1;
         d.wb[M_IRF][p] = reach_wb(v1, v0, qup, qlat, q, dt);
+    } else if constexpr (M == M_KW || M == M_DW) {     // kwe_route.f90 / dfw_route.f90 (mr_euler.cuh)
+        kw_dw_reach<M>(d, p, t);
+    } else if constexpr (M == M_MC) {                  // mc_route.f90
+        mc_reach(d, p, t);
     }
 }
 
@@ -396,7 +402,7 @@ __global__ void k_export_pack(DevNet d, const int *expPos, int nExp, int K) {
     if (i >= nExp * K) return;
     const int slot = i / K, t = i - slot * K, p = expPos[slot], N = d.nRch;
     double *rec = d.expBuf + ((size_t)slot * d.kmax + t) * d.recLen;
-    for (int m = 0; m < 3; ++m) if (d.routeSlot[m] >= 0) rec[d.routeSlot[m]] = d.qSer[m][(size_t)t * N + p];
+    for (int m = 0; m < N_METHODS; ++m) if (d.routeSlot[m] >= 0) rec[d.routeSlot[m]] = d.qSer[m][(size_t)t * N + p];
     rec[d.nRoutes] = d.qrSer[(size_t)(t + 1) * N + p];
     if (d.nGood[p] == 0 || d.routeSlot[M_KWT] < 0) { rec[d.nRoutes + 1] = 1.0; rec[d.nRoutes + 2] = 0.0; }
 }
@@ -407,7 +413,7 @@ __global__ void k_import_unpack(DevNet d, const int *impPos, int nImp, int K) {
     if (i >= nImp * K) return;
     const int slot = i / K, t = i - slot * K, p = impPos[slot], N = d.nRch;
     const double *rec = d.impBuf + ((size_t)slot * d.kmax + t) * d.recLen;
-    for (int m = 0; m < 3; ++m) if (d.routeSlot[m] >= 0) d.qSer[m][(size_t)t * N + p] = rec[d.routeSlot[m]];
+    for (int m = 0; m < N_METHODS; ++m) if (d.routeSlot[m] >= 0) d.qSer[m][(size_t)t * N + p] = rec[d.routeSlot[m]];
     d.qrSer[(size_t)(t + 1) * N + p] = rec[d.nRoutes];
 }
 

@@ -112,19 +112,6 @@ MR_DEV int kwt_time_average_team(const double *TOLD, const double *QOLD, int NOL
     return 0;
 }
 
-// one out-of-line copy of pow(): its inlined body is ~250 instructions per call site
-#if defined(MR_TEST_POW_NOISE) && !defined(__CUDACC__)
-// Host test builds only (tests/test_kwt_conditioning.py): pow() perturbed by -1/0/+1 ulp, pseudo-randomly, to measure how
-// a case reacts to the last-ulp differences between two correct pow() implementations (libm vs the device).
-inline double mr_pow(double x, double y) {
-    const double r = pow(x, y);
-    unsigned long long u; memcpy(&u, &x, 8);
-    u = (u * 0x9E3779B97F4A7C15ull + (unsigned long long)(MR_TEST_POW_NOISE)) >> 61;
-    return u < 3 ? nextafter(r, 1e300) : (u < 6 ? nextafter(r, -1e300) : r);
-}
-#else
-MR_DEV_NOINLINE double mr_pow(double x, double y) { return pow(x, y); }
-#endif
 
 MR_DEV_NOINLINE double thin_err(const double *Q, const double *T, int a, int m, int b) {
     // |INTERP(T(m), Q(a), Q(b), T(a), T(b)) - Q(m)|, kwt_route.f90:1054,1062,1114-1121

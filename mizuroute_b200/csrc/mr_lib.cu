@@ -25,7 +25,7 @@ using namespace mr;
 
 struct mr_handle_s {
     mr_options opt{};
-    bool on[3] = {false, false, false};
+    bool on[N_METHODS] = {false, false, false, false, false, false};
     bool hasNet = false;
     Topology topo;
     std::vector<double> fracFuture, uhHost;      // uhHost slot-major [maxtdh][N], stage order
@@ -41,8 +41,8 @@ struct mr_handle_s {
     double timing[8] = {0};
     cudaStream_t stream = nullptr, ownStream = nullptr;
     cudaEvent_t ev[10] = {nullptr};
-    cudaStream_t aux[2] = {nullptr, nullptr};    // the routing methods of route_opt are independent: all but the last run on these
-    cudaEvent_t mev[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};   // start / end of each method
+    cudaStream_t aux[N_METHODS - 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // the routing methods of route_opt are independent: all but the last run on these
+    cudaEvent_t mev[N_METHODS][2] = {};          // start / end of each method
     unsigned *dKwCount = nullptr;
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
@@ -203,7 +203,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     // The methods of route_opt share only BASIN_QR (read-only here), so they run concurrently: the last one on the
     // handle's stream, the others on auxiliary streams forked after k_basin and joined before the export.
     const int hb = (d.nHead + 255) / 256, nr = h->opt.n_routes;
-    cudaStream_t st[3];
+    cudaStream_t st[N_METHODS];
     for (int r = 0; r < nr; ++r) {
         st[r] = r == nr - 1 ? h->stream : h->aux[r];
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
@@ -213,6 +213,9 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
                 case M_SUM: k_headwater<M_SUM><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_IRF: k_headwater<M_IRF><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_KWT: k_headwater<M_KWT><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_KW: k_headwater<M_KW><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_MC: k_headwater<M_MC><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_DW: k_headwater<M_DW><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
             }
             h->launchesLast++;
         }
@@ -223,6 +226,9 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
                 case M_SUM: launch_wavefront<M_SUM>(h, st[r], w, K, h->stepsDone); break;
                 case M_IRF: launch_wavefront<M_IRF>(h, st[r], w, K, h->stepsDone); break;
                 case M_KWT: launch_wavefront<M_KWT>(h, st[r], w, K, h->stepsDone); break;
+                case M_KW: launch_wavefront<M_KW>(h, st[r], w, K, h->stepsDone); break;
+                case M_MC: launch_wavefront<M_MC>(h, st[r], w, K, h->stepsDone); break;
+                case M_DW: launch_wavefront<M_DW>(h, st[r], w, K, h->stepsDone); break;
             }
     for (int r = 0; r < nr; ++r) {
         CU(cudaEventRecord(h->mev[r][1], st[r]));
@@ -258,7 +264,7 @@ void collect_timing(mr_handle h) {
     h->timing[2] = span(2, 3);
     const int nr = h->opt.n_routes;
     for (int r = 0; r < 3; ++r) h->timing[5 + r] = 0.0;
-    for (int r = 0; r < nr; ++r) { ms = 0.f; cudaEventElapsedTime(&ms, h->mev[r][0], h->mev[r][1]); h->timing[5 + r] = ms; }
+    for (int r = 0; r < nr && r < 3; ++r) { ms = 0.f; cudaEventElapsedTime(&ms, h->mev[r][0], h->mev[r][1]); h->timing[5 + r] = ms; }   // the first three methods of route_opt
 }
 
 }  // namespace
@@ -270,16 +276,16 @@ int mr_create(const mr_options *opts, mr_handle *out, char *message) {
     const char *where = "mr_create";
     if (!opts || !out) return fail(message, 1, "mr_create/null argument");
     *out = nullptr;
-    if (opts->n_routes < 1 || opts->n_routes > 3) return fail(message, 1, "mr_create/route_opt must name 1-3 methods");
+    if (opts->n_routes < 1 || opts->n_routes > N_METHODS) return fail(message, 1, "mr_create/route_opt must name 1-6 methods");
     if (!(opts->dt > 0.0)) return fail(message, 1, "mr_create/dt_qsim must be positive");
     if (opts->max_batch < 1) return fail(message, 1, "mr_create/max_batch must be >= 1");
     mr_handle h = new mr_handle_s();
     h->opt = *opts;
     for (int r = 0; r < opts->n_routes; ++r) {
         const int m = opts->route_methods[r];
-        if (m < 0 || m > 2 || h->on[m]) {        // read_control.f90:583-597; methods 3/4/5 are not on this path
+        if (m < 0 || m >= N_METHODS || h->on[m]) {   // read_control.f90:583-597
             delete h;
-            return fail(message, 81, "mr_create/route_opt: only 0 (SUM), 1 (IRF), 2 (KWT), each at most once");
+            return fail(message, 81, "mr_create/route_opt: routing method id expect digits 0-5, each at most once");
         }
         h->on[m] = true;
     }
@@ -293,8 +299,8 @@ int mr_create(const mr_options *opts, mr_handle *out, char *message) {
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->ownStream, cudaStreamNonBlocking);
     h->stream = h->ownStream;
     for (int i = 0; i < 10 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
-    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->mev[i / 2][i % 2]);
+    for (int i = 0; i < N_METHODS - 1 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
+    for (int i = 0; i < 2 * N_METHODS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->mev[i / 2][i % 2]);
     if (ce != cudaSuccess) { delete h; CU(ce); }
     put_msg(message, "");
     *out = h;
@@ -341,6 +347,11 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     // reach parameters in stage order (process_ntopo.f90:176-187,359-366)
     std::vector<double> rlen(N), rslp(N), rwid(N), rman(N), maxS(N, 0.0), coef(N, 0.0), pw(N, 0.0), s0(N, 0.0);
     std::vector<int> ltype(N, MR_LAKE_DOLL03);
+    // channel geometry of the Euler schemes (process_ntopo.f90:174-203): bankfull depth dscale*sqrt(totalArea) with
+    // <floodplain> T, else high_depth (globalData.f90:187-189); rectangular main channel; bankfull storage (hydraulic.f90:207-237)
+    const bool euler = h->on[M_KW] || h->on[M_MC] || h->on[M_DW];
+    std::vector<double> rdep, zside, zfld, rstor;
+    if (euler) { rdep.assign(N, 100000.0); zside.assign(N, 0.0); zfld.assign(N, o.floodplainSlope > 0.0 ? o.floodplainSlope : 1000.0); rstor.assign(N, 0.0); }
     h->flags.assign(N, 0);
     for (int p = 0; p < N; ++p) {
         const int r = T.pos2rch[p];
@@ -349,6 +360,10 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         rwid[p] = width ? width[r] : o.wscale * std::sqrt(T.totArea[p]);
         rman[p] = man_n ? man_n[r] : o.mann_n;
         if (h->nGhost && gKind[r]) { h->flags[p] |= FLAG_GHOST; rwid[p] = gWidth[r]; }
+        if (euler) {
+            if (o.floodplain) rdep[p] = (o.dscale > 0.0 ? o.dscale : 0.000045) * std::sqrt(T.totArea[p]);
+            rstor[p] = rdep[p] * (rwid[p] + zside[p] * rdep[p]) * rlen[p];       // flow_area(y = bankDepth) * length
+        }
         if (o.is_lake_sim) {
             if (islake && islake[r] == 1) h->flags[p] |= FLAG_LAKE;
             ltype[p] = (!o.lakeRegulate || !lakeModelType) ? MR_LAKE_DOLL03 : lakeModelType[r];
@@ -404,13 +419,15 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     UP(fracFuture, h->fracFuture);
     if (h->on[M_IRF]) UP(uh, h->uhHost);
     UP(d03MaxS, maxS); UP(d03Coef, coef); UP(d03Pow, pw); UP(d03S0, s0);
+    if (euler) { UP(rdepth, rdep); UP(sideSlope, zside); UP(fldpSlope, zfld); UP(rstorage, rstor); }
     AL(d.qfutBas, (size_t)h->ntdhBas * N);
     AL(d.qrSer, (size_t)(KB + 1) * N);
     AL(d.basinQI, N);
-    for (int m = 0; m < 3; ++m) {
+    for (int m = 0; m < N_METHODS; ++m) {
         if (!h->on[m]) continue;
         AL(d.qSer[m], (size_t)KB * N);
         AL(d.vol0[m], N); AL(d.vol1[m], N); AL(d.inflow[m], N); AL(d.wb[m], N);
+        if (n_molecule(m)) { AL(d.mol[m], (size_t)n_molecule(m) * N); AL(d.floodVol[m], N); AL(d.reachEle[m], N); }   // molecule%Q = 0, init_model_data.f90:463-497
     }
     if (h->on[M_IRF]) AL(d.qfutIrf, (size_t)h->maxtdh * N);
     if (h->on[M_KWT]) {
@@ -447,7 +464,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     AL(d.err, 4);
     d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
     d.nRoutes = o.n_routes; d.kmax = KB; d.recLen = o.n_routes + 3 + 2 * KWP;
-    for (int m = 0; m < 3; ++m) d.routeSlot[m] = -1;
+    for (int m = 0; m < N_METHODS; ++m) d.routeSlot[m] = -1;
     for (int r = 0; r < o.n_routes; ++r) d.routeSlot[o.route_methods[r]] = r;
     if (h->nGhost) {
         std::vector<int> slot(N, -1), pos(h->nGhost);
@@ -657,7 +674,7 @@ int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) 
     const double *src = nullptr;
     std::vector<double> tmp(N);
     const bool perMethod = (field == MR_REACH_Q || field == MR_REACH_VOL1 || field == MR_REACH_VOL0 || field == MR_REACH_INFLOW || field == MR_WB);
-    if (perMethod && (method < 0 || method > 2 || !h->on[method])) return fail(message, 1, "mr_get_flux/routing method is not active");
+    if (perMethod && (method < 0 || method >= N_METHODS || !h->on[method])) return fail(message, 1, "mr_get_flux/routing method is not active");
     switch (field) {
         case MR_REACH_Q: src = h->lastK > 0 ? h->d.qSer[method] + (size_t)(h->lastK - 1) * N : nullptr; break;
         case MR_REACH_VOL1: src = h->d.vol1[method]; break;
@@ -694,6 +711,9 @@ static long state_bytes(mr_handle h, int var) {
         case MR_ST_KWT_QWAVE: case MR_ST_KWT_TENTRY: case MR_ST_KWT_TEXIT: return 8L * N * KWS;
         case MR_ST_KWT_ROUTED: return 4L * N * KWS;
         case MR_ST_LAKE_VOL: return 8L * N * h->opt.n_routes;
+        case MR_ST_MOLECULE_KW: return 8L * N * n_molecule(M_KW);
+        case MR_ST_MOLECULE_MC: return 8L * N * n_molecule(M_MC);
+        case MR_ST_MOLECULE_DW: return 8L * N * n_molecule(M_DW);
         default: return -1;
     }
 }
@@ -736,6 +756,13 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
             std::vector<double> tmp(N);
             CU(pull(h->d.vol1[M_IRF], tmp.data(), 8L * N));
             for (int r = 0; r < N; ++r) out[r] = tmp[T.rch2pos[r]];
+            break; }
+        case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: {
+            const int m = var == MR_ST_MOLECULE_KW ? M_KW : var == MR_ST_MOLECULE_MC ? M_MC : M_DW, nm = n_molecule(m);
+            if (!h->on[m]) return fail(message, 1, "mr_get_state/routing method is not active");
+            std::vector<double> tmp((size_t)nm * N);
+            CU(pull(h->d.mol[m], tmp.data(), tmp.size() * 8));
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r]; for (int k = 0; k < nm; ++k) out[(size_t)r * nm + k] = tmp[(size_t)k * N + p]; }
             break; }
         case MR_ST_LAKE_VOL: {
             std::vector<double> tmp(N);
@@ -811,6 +838,13 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
             std::vector<double> tmp(N);
             for (int r = 0; r < N; ++r) tmp[T.rch2pos[r]] = in[r];
             CU(push(h->d.vol1[M_IRF], tmp.data(), 8L * N));
+            break; }
+        case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: {
+            const int m = var == MR_ST_MOLECULE_KW ? M_KW : var == MR_ST_MOLECULE_MC ? M_MC : M_DW, nm = n_molecule(m);
+            if (!h->on[m]) return fail(message, 1, "mr_set_state/routing method is not active");
+            std::vector<double> tmp((size_t)nm * N);
+            for (int r = 0; r < N; ++r) { const int p = T.rch2pos[r]; for (int k = 0; k < nm; ++k) tmp[(size_t)k * N + p] = in[(size_t)r * nm + k]; }
+            CU(push(h->d.mol[m], tmp.data(), tmp.size() * 8));
             break; }
         case MR_ST_LAKE_VOL: {
             std::vector<double> tmp(N);

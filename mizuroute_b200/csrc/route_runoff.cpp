@@ -202,6 +202,16 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
     if (kwt) { vNw = w.def_var("numWaves", nc3::NC_INT, {dSeg}); vTe = w.def_var("tentry", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "s"}}); vTx = w.def_var("texit", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "s"}});
                vQw = w.def_var("qwave", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "m2/s"}}); vQm = w.def_var("qwave_mod", nc3::NC_DOUBLE, {dWave, dSeg}, {{"units", "m2/s"}});
                vRt = w.def_var("routed", nc3::NC_INT, {dWave, dSeg}); vKv = w.def_var("volume_kwt", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}}); }
+    static const char *eul[3] = {"kw", "mc", "dw"}; static const int molN[3] = {20, 2, 20};      // popMetadat.f90:283-295
+    int vMol[3] = {-1, -1, -1}, vMolVol[3] = {-1, -1, -1};
+    for (int q = 0; q < o.n_routes; ++q) {
+        const int m = o.route_methods[q];
+        if (m < MR_KINEMATIC_WAVE) continue;
+        const std::string e = eul[m - 3];
+        const int dMol = w.def_dim("mol_" + e, molN[m - 3]);
+        vMol[m - 3] = w.def_var("q_sub_" + e, nc3::NC_DOUBLE, {dMol, dSeg}, {{"units", "m3/s"}});
+        vMolVol[m - 3] = w.def_var("volume_" + e, nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}});
+    }
     w.end_def();
     w.put_int(vId, segId.data());
     const double tb[2] = {T0, T0 + o.dt}; w.put_double(vTb, tb); (void)steps;
@@ -233,6 +243,14 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
         check(mr_get_state(h, MR_ST_KWT_QWAVE, a.data(), (long)a.size() * 8, msg), msg); w.put_double(vQw, transposed(a, W).data());
         std::fill(a.begin(), a.end(), -9999.0); w.put_double(vQm, a.data());                                  // QM is a dead field (always realMissing)
         for (int q = 0; q < o.n_routes; ++q) if (o.route_methods[q] == MR_KINEMATIC_WAVE_TRACKING) w.put_double(vKv, &lv[(size_t)q * N]);
+    }
+    for (int q = 0; q < o.n_routes; ++q) {                                 // Euler schemes: q_sub_<m> [mol, seg], volume_<m>
+        const int m = o.route_methods[q];
+        if (m < MR_KINEMATIC_WAVE) continue;
+        const int nm = molN[m - 3];
+        a.resize((size_t)N * nm); check(mr_get_state(h, MR_ST_MOLECULE_KW + (m - 3), a.data(), (long)a.size() * 8, msg), msg);
+        w.put_double(vMol[m - 3], transposed(a, nm).data());
+        w.put_double(vMolVol[m - 3], &lv[(size_t)q * N]);
     }
     w.close();
 }
@@ -274,6 +292,13 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
             r.read_all(r.var("texit"), t); a = rowmajor(t, W); check(mr_set_state(h, MR_ST_KWT_TEXIT, a.data(), (long)a.size() * 8, msg), msg);
             r.read_all(r.var("qwave"), t); a = rowmajor(t, W); check(mr_set_state(h, MR_ST_KWT_QWAVE, a.data(), (long)a.size() * 8, msg), msg);
             r.read_all(r.var("volume_kwt"), t); std::copy(t.begin(), t.end(), lv.begin() + (size_t)q * N);
+        } else if (o.route_methods[q] >= MR_KINEMATIC_WAVE) {
+            static const char *eul[3] = {"kw", "mc", "dw"}; static const int molN[3] = {20, 2, 20};
+            const int m = o.route_methods[q]; const std::string e = eul[m - 3];
+            if ((int)r.dim_len("mol_" + e) != molN[m - 3]) die(20, "read_state_nc/molecule dimension of the restart file differs");
+            r.read_all(r.var("q_sub_" + e), t); a = rowmajor(t, molN[m - 3]);
+            check(mr_set_state(h, MR_ST_MOLECULE_KW + (m - 3), a.data(), (long)a.size() * 8, msg), msg);
+            r.read_all(r.var("volume_" + e), t); std::copy(t.begin(), t.end(), lv.begin() + (size_t)q * N);
         }
     }
     check(mr_set_state(h, MR_ST_LAKE_VOL, lv.data(), (long)lv.size() * 8, msg), msg);
@@ -329,6 +354,7 @@ int main(int argc, char **argv) {
         read_param_nml(join_path(ancil, c.need("param_nml")), o);
         o.device = std::getenv("MR_DEVICE") ? std::atoi(std::getenv("MR_DEVICE")) : 0;
         o.max_batch = batch;
+        o.floodplain = c.flag("floodplain", false);              // Euler schemes: finite bankfull depth (process_ntopo.f90:190-196)
 
         // ---- init_ntopo: river network (read_streamSeg.f90:44-276)
         nc3::Reader nt(join_path(ancil, c.need("fname_ntopOld")));
@@ -591,8 +617,9 @@ int main(int argc, char **argv) {
         if (isRemap) { ierr = mr_set_remap(h, (int)nForcing, (int)mapHruIx.size(), mapHruIx.data(), mapNumQ.data(), mapQIx.data(), mapWgt.data(), msg); if (ierr) die(ierr, msg); }
 
         // ---- history files (write_simoutput_pio.f90: one float32 variable per active routing method, [time, seg])
-        const char *vname[3] = {"sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff"};
-        const char *lname[3] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking"};
+        const char *vname[6] = {"sumUpstreamRunoff", "IRFroutedRunoff", "KWTroutedRunoff", "KWroutedRunoff", "MCroutedRunoff", "DWroutedRunoff"};
+        const char *lname[6] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking",
+                                "routed runoff in each reach-kinematic wave", "routed runoff in each reach-muskingum-cunge", "routed runoff in each reach-diffusive wave"};
         const bool wantDlay = c.flag("dlayRunoff", true);
         int vTime = -1, vDlay = -1;
         std::vector<int> vQ(o.n_routes, -1);

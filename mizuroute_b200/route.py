@@ -57,6 +57,7 @@ class Router:
         o.mann_n, o.wscale = params.mann_n, params.wscale
         o.device = int(device)
         o.max_batch = int(max_batch)
+        o.floodplain = int(bool(getattr(opts, "floodplain", False)))     # dscale / floodplainSlope stay 0 = the reference's constants
         self.max_batch = int(max_batch)
         self._check(self._L.mr_create(C.byref(o), C.byref(self._h), self._msg))
         n = net
@@ -249,6 +250,9 @@ class Router:
             capi.ST_KWT_TEXIT: ((n, w), np.float64),
             capi.ST_KWT_ROUTED: ((n, w), np.int32),
             capi.ST_LAKE_VOL: ((len(self.methods), n), np.float64),
+            capi.ST_MOLECULE_KW: ((n, capi.N_MOLECULE[3]), np.float64),
+            capi.ST_MOLECULE_MC: ((n, capi.N_MOLECULE[4]), np.float64),
+            capi.ST_MOLECULE_DW: ((n, capi.N_MOLECULE[5]), np.float64),
         }[var]
 
     def get_state(self, var: int) -> np.ndarray:

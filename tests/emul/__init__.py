@@ -24,3 +24,19 @@ def load():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC",
                                "-o", _SO, _SRC])
     return C.CDLL(_SO)
+
+
+_EULER_SO = os.path.join(_HERE, "libeuler_emul.so")
+_EULER_SRC = os.path.join(_HERE, "euler_emul.cpp")
+_EULER_DEPS = [_EULER_SRC] + [os.path.join(_CSRC, f) for f in ("mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
+
+
+def load_euler(noise_seed: int = 0):
+    """Host build of the Euler routing schemes (mr_euler.cuh), see euler_emul.cpp; noise_seed > 0: pow() perturbed by at
+    most one ulp (MR_TEST_POW_NOISE, mr_dev.h)."""
+    so = _EULER_SO if not noise_seed else os.path.join(_HERE, "libeuler_emul_noise%d.so" % noise_seed)
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in _EULER_DEPS):
+        extra = ["-DMR_TEST_POW_NOISE=%d" % (7919 * noise_seed + 1)] if noise_seed else []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", *extra, "-x", "c++", "-shared",
+                               "-fPIC", "-o", so, _EULER_SRC])
+    return C.CDLL(so)

@@ -48,6 +48,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
                       h->o.is_lake_sim, h->o.lakeRegulate, h->o.LakeInputOption, h->o.runoffMin, h->o.time_conv, h->o.length_conv,
                       h->o.fshape, h->o.tscale, h->o.velo, h->o.diff, h->o.mann_n, h->o.wscale, 1);
     if (!h->m) { say(message, "mr_set_network/oracle refused the network"); return 20; }
+    if (h->o.floodplain) mro_set_channel(h->m, 1, h->o.dscale > 0.0 ? h->o.dscale : 0.000045, h->o.floodplainSlope > 0.0 ? h->o.floodplainSlope : 1000.0);
     say(message, "");
     return 0;
 }
@@ -159,6 +160,7 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message)
             else for (i = 0; i < N * W; i++) ip[i] = s.rf[i];
             kw_free(s);
             return 0; }
+        case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: mro_get_molecule(h->m, M_KW + (var - MR_ST_MOLECULE_KW), d); return 0;
         default: say(message, "mr_get_state/unknown state variable"); return 1;
     }
 }
@@ -190,6 +192,7 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
             mro_set_kwt_state(h->m, MR_KW_SLOTS, s.n, s.qf, s.ti, s.tr, s.rf);
             kw_free(s);
             return 0; }
+        case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: mro_set_molecule(h->m, M_KW + (var - MR_ST_MOLECULE_KW), d); return 0;
         default: say(message, "mr_set_state/unknown state variable"); return 1;
     }
 }

@@ -46,7 +46,10 @@ def test_create_fails_loudly_without_a_gpu_or_with_bad_options():
     msg = C.create_string_buffer(256)
     if not torch.cuda.is_available():
         assert L.mr_create(C.byref(o), C.byref(h), msg) == 90 and b"no CPU path" in msg.value
-    o.route_methods[0] = 4                      # Muskingum-Cunge is not on this path
+    o.route_methods[0] = 6                      # routing method ids are the digits 0-5 (main_route.f90:331)
     assert L.mr_create(C.byref(o), C.byref(h), msg) == 81
+    o.n_routes = 2; o.route_methods[0] = 4; o.route_methods[1] = 4      # each method at most once
+    assert L.mr_create(C.byref(o), C.byref(h), msg) == 81
+    o.n_routes = 1
     o.route_methods[0] = 1; o.dt = 0.0
     assert L.mr_create(C.byref(o), C.byref(h), msg) == 1

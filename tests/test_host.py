@@ -222,7 +222,7 @@ def test_reader_accepts_classic_cdf1_and_rejects_netcdf4(tmp_path):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
-@pytest.mark.parametrize("route,dt,lakes", [("012", 3600.0, 0), ("12", 86400.0, 5)])
+@pytest.mark.parametrize("route,dt,lakes", [("012", 3600.0, 0), ("12", 86400.0, 5), ("345", 3600.0, 4)])
 def test_host_run_matches_oracle(tmp_path, backend, route, dt, lakes):
     from oracle.oracle import Oracle
     net, params, opts, ro = case("conus", n=600, seed=8, dt=dt, route_opt=route, steps=40, lakes=lakes)
@@ -234,11 +234,11 @@ def test_host_run_matches_oracle(tmp_path, backend, route, dt, lakes):
     qo = Oracle(net, params, opts).run(ro)
     assert np.array_equal(out["reachID"], net.segId)
     assert np.array_equal(out["time"], np.arange(40) * dt)
-    names = {"0": "sumUpstreamRunoff", "1": "IRFroutedRunoff", "2": "KWTroutedRunoff"}
+    names = {"0": "sumUpstreamRunoff", "1": "IRFroutedRunoff", "2": "KWTroutedRunoff", "3": "KWroutedRunoff", "4": "MCroutedRunoff", "5": "DWroutedRunoff"}
     for i, c in enumerate(route):
         got = out[names[c]]
         assert got.dtype == np.float32 and got.shape == (40, net.nRch)       # history is float32 [time, seg]
-        np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c != "2" else 1e-4, atol=1e-30)
+        np.testing.assert_allclose(got, qo[i].astype(np.float32), rtol=2e-6 if c in "01" else 1e-4, atol=1e-30)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
@@ -323,6 +323,33 @@ def test_restart_files_written_during_the_run_continue_it_exactly(tmp_path, back
     h_cont = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
     for v in ("IRFroutedRunoff", "KWTroutedRunoff", "dlayRunoff"):
         assert np.array_equal(h_cont[v], h_full[v][k0:]), v
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_exact_restart_of_the_euler_schemes(tmp_path, backend):
+    """q_sub_kw / q_sub_mc / q_sub_dw [mol, seg] and volume_* in the restart file (popMetadat.f90:283-295): 24 steps in one
+    run == 12 steps + restart + 12 steps, bit for bit, with <floodplain> T."""
+    net, params, opts, ro = case("conus", n=400, seed=6, dt=3600.0, route_opt="345", steps=24, floodplain=True)
+    d = str(tmp_path)
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+    fp = {"floodplain": "T"}
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="full", extra_keys=fp)); assert r.returncode == 0, r.stderr
+    h_full = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    r = run(casefiles.write_case(d, net, params, opts, ro[:12], case_name="first", restart_write="last", extra_keys=fp)); assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    rfile = next(x["restart"] for x in lines if "restart" in x)
+    rst = casefiles.read_history(rfile)
+    assert rst["q_sub_kw"].shape == (20, net.nRch) and rst["q_sub_mc"].shape == (2, net.nRch) and rst["q_sub_dw"].shape == (20, net.nRch)
+    assert {"volume_kw", "volume_mc", "volume_dw"} <= set(rst)
+    r = run(casefiles.write_case(d, net, params, opts, ro[12:], case_name="second", fname_state_in=os.path.basename(rfile), first_step=12, extra_keys=fp))
+    assert r.returncode == 0, r.stderr
+    h_second = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    for v in ("KWroutedRunoff", "MCroutedRunoff", "DWroutedRunoff"):
+        assert np.array_equal(h_second[v], h_full[v][12:]), v
+    if backend == "oracle-stub":                      # <floodplain> T reached the routing: differs from the default geometry
+        from oracle.oracle import Oracle
+        q_fp = Oracle(net, params, opts).run(ro)
+        np.testing.assert_allclose(h_full["MCroutedRunoff"], q_fp[1].astype(np.float32), rtol=2e-6, atol=1e-30)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)

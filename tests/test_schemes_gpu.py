@@ -1,0 +1,68 @@
+"""GPU parity of the Euler routing schemes -- <route_opt> 3 kinematic wave, 4 Muskingum-Cunge, 5 diffusive wave
+(kwe_route.f90, mc_route.f90, dfw_route.f90) -- through the C ABI against the CPU oracle.
+
+Tolerance: 1e-4 relative, as for KWT.  The arithmetic is the oracle's (tests/test_euler_emul.py holds the same source,
+compiled for the host, to bit equality), but flow_depth / celerity call pow(), whose device implementation differs from
+libm in the last ulp, and flow_depth's Newton iteration stops at a 0.5 % change: a last-ulp flip of that test moves the
+depth by ~1e-5.  Typical agreement is ~1e-14 (tests/test_euler_emul.py measures the conditioning)."""
+import numpy as np
+import pytest
+
+from tests.util import case, rel_err
+
+pytestmark = pytest.mark.gpu
+EULER_RTOL = 1e-4
+
+
+def _both(net, params, opts, ro, batch):
+    from tests.test_gpu_parity import _run_both
+    return _run_both(net, params, opts, ro, batch)
+
+
+@pytest.mark.parametrize("kw,batch", [
+    (dict(kind="random", n=80, seed=5, dt=3600.0, steps=40, zero_area_frac=0.08), 1),
+    (dict(kind="random", n=60, seed=6, dt=86400.0, steps=20), 7),                      # Muskingum-Cunge sub-steps
+    (dict(kind="conus", n=3000, seed=4, dt=3600.0, steps=24), 24),
+    (dict(kind="random", n=50, seed=7, dt=900.0, steps=30, hw_drain_point=1), 8),
+    (dict(kind="binary", n=1023, seed=2, dt=10800.0, steps=20, floodplain=True), 5),    # finite bankfull depth
+    (dict(kind="random", n=40, seed=8, dt=3600.0, steps=12, min_length_route=1500.0), 4),
+    (dict(kind="conus", n=1500, seed=4, dt=86400.0, steps=12, lakes=12), 6),           # lake_route under the Euler schemes
+], ids=["hourly", "daily-substeps", "conus3000", "hw-top", "floodplain", "pass-through", "lakes"])
+def test_kw_mc_dw_match_oracle(kw, batch):
+    from mizuroute_b200 import capi
+    from oracle import oracle as orc
+    net, params, opts, ro = case(route_opt="345", **kw)
+    o, r, qo, qg = _both(net, params, opts, ro, batch)
+    for i, m in enumerate((3, 4, 5)):
+        assert rel_err(qg[i], qo[i]) <= EULER_RTOL, m
+        assert rel_err(r.flux(capi.REACH_VOL1, m), o.get(orc.F_REACH_VOL1, m), floor=1e-6) <= EULER_RTOL
+        assert rel_err(r.flux(capi.REACH_INFLOW, m), o.get(orc.F_REACH_INFLOW, m), floor=1e-30) <= EULER_RTOL
+        mol = r.get_state(capi.ST_MOLECULE_KW + (m - 3))
+        assert mol.shape == (net.nRch, capi.N_MOLECULE[m])
+        assert rel_err(mol, o.molecule(m), floor=1e-12) <= EULER_RTOL
+
+
+def test_all_six_methods_in_one_run():
+    net, params, opts, ro = case("conus", n=6000, seed=7, dt=3600.0, route_opt="012345", steps=20)   # KWT well-conditioned here (test_kwt_conditioning)
+    o, r, qo, qg = _both(net, params, opts, ro, 10)
+    assert np.array_equal(qg[:2], qo[:2])                                   # SUM / IRF stay bit-identical
+    for i in range(2, 6):
+        assert rel_err(qg[i], qo[i]) <= EULER_RTOL, i
+
+
+def test_molecule_state_round_trip_continues_exactly():
+    """mr_get_state / mr_set_state of q_sub_kw|mc|dw + volumes: a second handle seeded with the state of the first one
+    reproduces the rest of the run bit for bit (the restart path of the stand-alone host)."""
+    from mizuroute_b200 import capi
+    from mizuroute_b200.route import Router
+    net, params, opts, ro = case("conus", n=800, seed=3, dt=3600.0, route_opt="345", steps=24)
+    a = Router(net, params, opts, max_batch=12)
+    a.route_batch(np.ascontiguousarray(ro[:12]))
+    b = Router(net, params, opts, max_batch=12)
+    b.set_steps_done(12)
+    for v in (capi.ST_BASIN_QFUTURE, capi.ST_BASIN_QR, capi.ST_MOLECULE_KW, capi.ST_MOLECULE_MC, capi.ST_MOLECULE_DW, capi.ST_LAKE_VOL):
+        b.set_state(v, a.get_state(v))
+    b.TSEC = list(a.TSEC)
+    qa = a.route_batch(np.ascontiguousarray(ro[12:]))
+    qb = b.route_batch(np.ascontiguousarray(ro[12:]))
+    assert np.array_equal(qa, qb)
