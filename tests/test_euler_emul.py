@@ -69,3 +69,43 @@ def test_last_ulp_of_pow_moves_discharge_by_less_than_the_gpu_tolerance(method):
         o, qo, qe, ve, me = _run(kw, method, noise_seed=1)
         worst = max(worst, float(np.max(np.abs(qe - qo) / np.maximum(np.abs(qo), 1e-300))))
     assert worst < 1e-5, worst
+
+
+@pytest.mark.parametrize("method", [orc.M_KW, orc.M_MC, orc.M_DW], ids=["kw", "mc", "dw"])
+def test_dry_channels_then_a_flood_pulse(method):
+    """runoffMin = 0 and no runoff at first: discharge is exactly zero (flow_depth returns 0 below Qmin = 1e-50, celerity 0,
+    Muskingum-Cunge takes its Qbar <= Qmin branch), then a pulse 1e6 times the usual runoff arrives; no NaN/Inf, the
+    device source still equals the oracle bit for bit and the twin agrees."""
+    from oracle.twin import Twin
+    net, params, opts, ro = case("random", n=40, seed=9, dt=3600.0, route_opt=str(method), steps=30)
+    opts.runoffMin = 0.0
+    ro = ro.copy(); ro[:6] = 0.0; ro[12:14] *= 1.0e6; ro[20:] = 0.0
+    kw = dict(kind="random", n=40, seed=9, dt=3600.0, steps=30)
+
+    def run_with(ro_):
+        o = Oracle(net, params, opts)
+        K = ro_.shape[0]
+        qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+        qr[0] = o.get(orc.F_BASIN_QR1)
+        for t in range(K):
+            o.step(ro_[t]); qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, method)
+        return o, qr, qo
+    o, qr, qo = run_with(ro)
+    assert np.isfinite(qo).all() and (qo >= 0.0).all()
+    assert not qo[:1].any() and qo[12:16].max() > 1.0                     # dry start, then the pulse
+    L = emul.load_euler()
+    K = ro.shape[0]
+    qe = np.empty((K, net.nRch)); ve = np.empty(net.nRch); me = np.empty((net.nRch, orc.N_MOLECULE[method]))
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
+    ierr = L.euler_emul_run(C.c_int(method), C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int),
+                            p(net.hruSegId, C.c_int), p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
+                            C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(opts.hw_drain_point),
+                            C.c_double(opts.min_length_route), C.c_int(0), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double),
+                            p(ve, C.c_double), p(me, C.c_double), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qe, qo) and np.array_equal(me, o.molecule(method))
+    t = Twin(net, params, opts)
+    for k in range(K):
+        t.step(ro[k])
+    assert np.array_equal(np.array(t.Q[method]), qo[-1])
