@@ -106,6 +106,9 @@ typedef struct {
     double *MOL[N_METHOD];         /* molecule%Q of KW / MC / DW, [nRch][N_MOLECULE] */
     double *FLOOD_VOL1[N_METHOD], *REACH_ELE[N_METHOD];
     double *reachRunoff;
+    /* lake forcing: reach-level evaporation / precipitation [m3/s] of the current step (RCHFLX%basinevapo / basinprecip,
+       main_route.f90:174-199,243-249); hasEP = 0: no such forcing given, both are exactly zero */
+    double *reachEvapo, *reachPrecip; int hasEP;
     long iTime;                    /* globalData iTime, 1 on the first step */
     int nThreads;
     char message[256];
@@ -452,7 +455,7 @@ mro_t *mro_create(int nRch, int nHRU,
     /* cold start (init_model_data.f90:399-463,600) */
     ALLOC(h->BASIN_QI, nRch); ALLOC(h->BASIN_QR0, nRch); ALLOC(h->BASIN_QR1, nRch);
     ALLOC(h->QFUTURE, (size_t)nRch * h->ntdh_bas); ALLOC(h->qfuture_alloc, nRch);
-    ALLOC(h->reachRunoff, nRch);
+    ALLOC(h->reachRunoff, nRch); ALLOC(h->reachEvapo, nRch); ALLOC(h->reachPrecip, nRch);
     for (m = 0; m < N_METHOD; m++) {
         ALLOC(h->REACH_Q[m], nRch); ALLOC(h->REACH_VOL0[m], nRch); ALLOC(h->REACH_VOL1[m], nRch);
         ALLOC(h->REACH_INFLOW[m], nRch); ALLOC(h->WB[m], nRch);
@@ -477,7 +480,7 @@ void mro_destroy(mro_t *h)
     free(h->isLake); free(h->lakeInlet); free(h->lakeModelType);
     free(h->D03_MaxStorage); free(h->D03_Coefficient); free(h->D03_Power); free(h->D03_S0);
     free(h->FRAC_FUTURE); free(h->uh_ptr); free(h->uh_val);
-    free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff);
+    free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff); free(h->reachEvapo); free(h->reachPrecip);
     for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
                                      free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); }
     free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
@@ -529,15 +532,19 @@ static void hru_irf(mro_t *h, int j)
 }
 
 /* water_balance.f90:61-87 (REACH_WM_FLUX = 0; precip/evap = 0 unless LakeInputOption uses them) */
-static void comp_reach_wb(mro_t *h, int m, int j, double Qupstream, double Qlat)
+static void comp_reach_wb_lake(mro_t *h, int m, int j, double Qupstream, double Qlat, int lakeFlag)
 {
     double dt = h->dt;
     double dVol = h->REACH_VOL1[m][j] - h->REACH_VOL0[m][j];
-    double Qin = Qupstream * dt, Qlateral = Qlat * dt, precip = 0.0, evapo = 0.0;
+    double Qin = Qupstream * dt, Qlateral = Qlat * dt;
+    double precip = (lakeFlag && h->hasEP) ? h->reachPrecip[j] * dt : 0.0;
+    double evapo = (lakeFlag && h->hasEP) ? -1.0 * h->reachEvapo[j] * dt : 0.0;
     double Qout = -1.0 * h->REACH_Q[m][j] * dt;
     double Qtake_actual = -1.0 * 0.0 * dt;
     h->WB[m][j] = dVol - (Qin + Qlateral + precip + Qtake_actual + Qout + evapo);
 }
+
+static void comp_reach_wb(mro_t *h, int m, int j, double Qupstream, double Qlat) { comp_reach_wb_lake(h, m, j, Qupstream, Qlat, 0); }
 
 /* accum_runoff.f90:60-75 */
 static int accum_inst_runoff(mro_t *h, int j)
@@ -897,10 +904,11 @@ static int lake_route(mro_t *h, int j, int M)
     h->REACH_VOL0[M][j] = *V1;
     *V1 = *V1 + q_upstream * dt;
     if (h->LakeInputOption == 1 || h->LakeInputOption == 2) *V1 = *V1 + h->BASIN_QR1[j] * dt;
-    if (h->LakeInputOption == 0 || h->LakeInputOption == 2) {
-        /* basinprecip = basinevapo = 0 in this restatement (no evap/precip forcing) */
-        *V1 = *V1 + 0.0 * dt;
-        if (*V1 > 0.0 * dt) *V1 = *V1 - 0.0 * dt; else *V1 = 0.0;
+    if (h->LakeInputOption == 0 || h->LakeInputOption == 2) {   /* lake_route.f90:166-174 */
+        const double pr = h->hasEP ? h->reachPrecip[j] : 0.0, ev = h->hasEP ? h->reachEvapo[j] : 0.0;
+        *V1 = *V1 + pr * dt;
+        if (*V1 > ev * dt) *V1 = *V1 - ev * dt;
+        else { if (h->hasEP) h->reachEvapo[j] = *V1 / dt; *V1 = 0.0; }   /* basinevapo is shared by the routing methods of a step */
     }
     switch (h->lakeModelType[j]) {
         case LAKE_ENDORHEIC: *Q = 0.0; break;
@@ -916,7 +924,7 @@ static int lake_route(mro_t *h, int j, int M)
         default: snprintf(h->message, 256, "lake_route/lake model type not restated in oracle"); return 20;
     }
     /* lake_route does not touch REACH_INFLOW */
-    comp_reach_wb(h, M, j, q_upstream, h->BASIN_QR1[j]);
+    comp_reach_wb_lake(h, M, j, q_upstream, h->BASIN_QR1[j], 1);
     return 0;
 }
 
@@ -1319,11 +1327,22 @@ static int route_one(mro_t *h, int M, int j, double T0, double T1, wave_buf_t *b
     return kwt_rch(h, j, T0, T1, b);
 }
 
-int mro_step(mro_t *h, double T0, double T1, const double *basinRunoff)
+int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const double *basinEvapo, const double *basinPrecip);
+int mro_step(mro_t *h, double T0, double T1, const double *basinRunoff) { return mro_step_ep(h, T0, T1, basinRunoff, NULL, NULL); }
+
+/* basinEvapo / basinPrecip [nHRU] in the units of the runoff (NULL = no lake forcing: exactly zero in lake_route) */
+int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const double *basinEvapo, const double *basinPrecip)
 {
     int j, r, ierr;
     ierr = basin2reach(h, basinRunoff, h->reachRunoff, 1);
     if (ierr) return ierr;
+    h->hasEP = (h->is_lake_sim && basinEvapo && basinPrecip);
+    if (h->hasEP) {                       /* main_route.f90:174-199: the same basin2reach, limitRunoff absent = .true. */
+        ierr = basin2reach(h, basinEvapo, h->reachEvapo, 1);
+        if (ierr) return ierr;
+        ierr = basin2reach(h, basinPrecip, h->reachPrecip, 1);
+        if (ierr) return ierr;
+    }
     if (h->doesBasinRoute == 1) {
 #pragma omp parallel for schedule(static) num_threads(h->nThreads)
         for (j = 0; j < h->nRch; j++) { h->BASIN_QI[j] = h->reachRunoff[j]; hru_irf(h, j); }
@@ -1376,6 +1395,20 @@ int mro_run(mro_t *h, int nSteps, double T0, const double *runoff /* [nSteps][nH
     }
     return 0;
 }
+
+int mro_run_ep(mro_t *h, int nSteps, double T0, const double *runoff, const double *evapo, const double *precip, double *q_out)
+{
+    int t, r, ierr; double t0 = T0, t1 = T0 + h->dt;
+    for (t = 0; t < nSteps; t++) {
+        ierr = mro_step_ep(h, t0, t1, runoff + (size_t)t * h->nHRU, evapo ? evapo + (size_t)t * h->nHRU : NULL, precip ? precip + (size_t)t * h->nHRU : NULL);
+        if (ierr) return ierr;
+        if (q_out) for (r = 0; r < h->nRoutes; r++)
+            memcpy(q_out + ((size_t)r * nSteps + t) * h->nRch, h->REACH_Q[h->routeOrder[r]], sizeof(double) * h->nRch);
+        t0 = t1; t1 = t0 + h->dt;
+    }
+    return 0;
+}
+void mro_get_lake_forcing(mro_t *h, double *evapo, double *precip) { memcpy(evapo, h->reachEvapo, sizeof(double) * h->nRch); memcpy(precip, h->reachPrecip, sizeof(double) * h->nRch); }
 
 /* ------------------------------------------------------------------------------------------ */
 /* accessors                                                                                   */

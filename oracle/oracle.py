@@ -92,18 +92,23 @@ class Oracle:
         if ierr != 0:
             raise OracleError(ierr, lib().mro_message(self.h).decode())
 
-    def step(self, runoff: np.ndarray):
+    def step(self, runoff: np.ndarray, evapo=None, precip=None):
+        """evapo / precip [nHRU] (runoff units): lake evaporation / precipitation forcing (main_route.f90:174-199)."""
         r = np.ascontiguousarray(runoff, dtype=np.float64)
         assert r.shape == (self.net.nHRU,)
-        self._check(lib().mro_step(self.h, C.c_double(self.T0), C.c_double(self.T1), _p(r, C.c_double)))
+        e = None if evapo is None else np.ascontiguousarray(evapo, dtype=np.float64)
+        p = None if precip is None else np.ascontiguousarray(precip, dtype=np.float64)
+        self._check(lib().mro_step_ep(self.h, C.c_double(self.T0), C.c_double(self.T1), _p(r, C.c_double), _p(e, C.c_double), _p(p, C.c_double)))
         self.T0 = self.T1
         self.T1 = self.T0 + float(self.opts.dt)     # init_model_data.f90:311-312
 
-    def run(self, runoff: np.ndarray, want_q: bool = True):
+    def run(self, runoff: np.ndarray, want_q: bool = True, evapo=None, precip=None):
         r = np.ascontiguousarray(runoff, dtype=np.float64)
         n = r.shape[0]
         q = np.empty((len(self.methods), n, self.net.nRch)) if want_q else None
-        self._check(lib().mro_run(self.h, C.c_int(n), C.c_double(self.T0), _p(r, C.c_double), _p(q, C.c_double)))
+        e = None if evapo is None else np.ascontiguousarray(evapo, dtype=np.float64)
+        p = None if precip is None else np.ascontiguousarray(precip, dtype=np.float64)
+        self._check(lib().mro_run_ep(self.h, C.c_int(n), C.c_double(self.T0), _p(r, C.c_double), _p(e, C.c_double), _p(p, C.c_double), _p(q, C.c_double)))
         for _ in range(n):
             self.T0 = self.T1
             self.T1 = self.T0 + float(self.opts.dt)
@@ -120,6 +125,13 @@ class Oracle:
     def set(self, field: int, values, method: int = M_IRF):
         v = np.ascontiguousarray(values, dtype=np.float64)
         assert lib().mro_set(self.h, C.c_int(method), C.c_int(field), _p(v, C.c_double)) == 0
+
+    def lake_forcing(self):
+        """(reach evaporation, reach precipitation) [m3/s] of the last step; the evaporation is what lake_route left
+        (cut to the lake volume where the lake ran dry)."""
+        e, p = np.empty(self.net.nRch), np.empty(self.net.nRch)
+        lib().mro_get_lake_forcing(self.h, _p(e, C.c_double), _p(p, C.c_double))
+        return e, p
 
     def molecule(self, method: int) -> np.ndarray:
         """molecule%Q of an Euler scheme, [nRch, N_MOLECULE[method]]."""

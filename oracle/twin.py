@@ -547,17 +547,17 @@ class Twin:
                     self.KW[i] = [Wave(-9999.0, -9999.0, -9999.0, False)]
         self.T0, self.T1 = 0.0, float(opts.dt)
         self.itime = 1
+        self.has_ep = False
 
     # -- step ---------------------------------------------------------------------------------
-    def step(self, runoff):
-        o = self.o
-        n = self.n
+    def _basin2reach(self, flux):
+        o, n = self.o, self.n
         rr = [0.0] * n
         for j in range(n):
             if self.hrus[j]:
                 r = 0.0
                 for w, hh in zip(self.wgt[j], self.hrus[j]):
-                    ro = float(runoff[hh])
+                    ro = float(flux[hh])
                     if ro < -1.0e-3:
                         raise RouteError(20, "basin2reach/exceeded negative runoff tolerance")
                     r = r + w * ro * self.tc * self.lc
@@ -566,6 +566,17 @@ class Twin:
                 rr[j] = r * self.bas[j]
             else:
                 rr[j] = o.runoffMin
+        return rr
+
+    def step(self, runoff, evapo=None, precip=None):
+        o = self.o
+        n = self.n
+        rr = self._basin2reach(runoff)
+        # lake evaporation / precipitation go through the same basin2reach (main_route.f90:174-199); None = exactly zero
+        self.has_ep = bool(o.is_lake_sim and evapo is not None and precip is not None)
+        if self.has_ep:
+            self.evap = self._basin2reach(evapo)
+            self.prec = self._basin2reach(precip)
         if o.doesBasinRoute == 1:
             nb = len(self.ff)
             for j in range(n):
@@ -604,10 +615,10 @@ class Twin:
         self.T1 = self.T0 + float(o.dt)
         self.itime += 1
 
-    def _wb(self, m, j, qup, qlat):
+    def _wb(self, m, j, qup, qlat, precip=0.0, evapo=0.0):
         dt = self.o.dt
         dvol = self.V1[m][j] - self.V0[m][j]
-        self.WB[m][j] = dvol - (qup * dt + qlat * dt + 0.0 + (-1.0 * 0.0 * dt) + (-1.0 * self.Q[m][j] * dt) + 0.0)
+        self.WB[m][j] = dvol - (qup * dt + qlat * dt + precip + (-1.0 * 0.0 * dt) + (-1.0 * self.Q[m][j] * dt) + evapo)
 
     def _sum(self, j):
         q = self.QR1[j]
@@ -785,8 +796,15 @@ class Twin:
         if self.o.LakeInputOption in (1, 2):
             v = v + self.QR1[j] * dt
         if self.o.LakeInputOption in (0, 2):
-            v = v + 0.0 * dt
-            v = v - 0.0 * dt if v > 0.0 * dt else 0.0
+            pr = self.prec[j] if self.has_ep else 0.0
+            ev = self.evap[j] if self.has_ep else 0.0
+            v = v + pr * dt
+            if v > ev * dt:
+                v = v - ev * dt
+            else:                       # the lake dries out: evaporation is cut to what was there, for every later method too
+                if self.has_ep:
+                    self.evap[j] = v / dt
+                v = 0.0
         if lt == 0:
             q = 0.0
         elif lt == 1:
@@ -802,7 +820,8 @@ class Twin:
             raise RouteError(20, "lake type not restated")
         self.V1[m][j] = v
         self.Q[m][j] = q
-        self._wb(m, j, qup, self.QR1[j])
+        pe = (self.prec[j] * dt, -1.0 * self.evap[j] * dt) if self.has_ep else (0.0, 0.0)
+        self._wb(m, j, qup, self.QR1[j], pe[0], pe[1])
 
     # -- KWT ------------------------------------------------------------------------------------
     def _qexmul(self, j, t0, t1):

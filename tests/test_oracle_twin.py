@@ -99,3 +99,37 @@ def test_euler_schemes_reach_the_steady_state_of_constant_runoff():
     q = orc.Oracle(net, params, opts).run(ro)
     for i in (1, 2, 3):
         assert rel_err(q[i, -1], q[0, -1]) < 2e-3
+
+
+@pytest.mark.parametrize("option", [0, 1, 2])
+def test_lake_evaporation_and_precipitation_forcing(option):
+    """LakeInputOption 0 / 2 add precipitation and subtract evaporation (both through basin2reach, main_route.f90:174-199;
+    lake_route.f90:166-174); a lake that cannot supply the evaporation dries out and the evaporation is cut back for the
+    methods routed after it.  Oracle and twin agree; with option 1 the forcing only enters the water balance."""
+    # (KWT cannot route the zero outflow of a dried lake -- kinwav_rch stops with "zero flow", kwt_route.f90:1365 -- so IRF + MC)
+    net, params, opts, ro = case("conus", n=600, seed=4, dt=86400.0, route_opt="14", steps=12, lakes=8)
+    opts.LakeInputOption = option
+    rng = np.random.default_rng(3)
+    ev = np.abs(rng.lognormal(np.log(3e-5), 0.5, size=ro.shape))
+    pr = np.abs(rng.lognormal(np.log(2e-5), 0.8, size=ro.shape))
+    lakes = np.flatnonzero(net.islake == 1)
+    dry = np.isin(net.hruSegId, net.segId[lakes[:2]])
+    ev[:, dry] *= 3.0e4                                                      # two lakes evaporate far more than they hold
+    o = orc.Oracle(net, params, opts)
+    t = Twin(net, params, opts)
+    q_plain = orc.Oracle(net, params, opts).run(ro)
+    cut = False
+    for k in range(ro.shape[0]):
+        o.step(ro[k], ev[k], pr[k]); t.step(ro[k], ev[k], pr[k])
+        for i, m in enumerate(t.methods):
+            assert rel_err(o.get(orc.F_REACH_Q, m), np.array(t.Q[m])) <= 1e-12
+            assert rel_err(o.get(orc.F_REACH_VOL1, m), np.array(t.V1[m]), floor=1e-9) <= 1e-12
+            assert rel_err(o.get(orc.F_WB, m)[lakes], np.array(t.WB[m])[lakes], floor=1e-3) <= 1e-9
+        e_left, _ = o.lake_forcing()
+        assert np.array_equal(e_left, np.array(t.evap))
+        cut = cut or bool((o.get(orc.F_REACH_VOL1, orc.M_IRF)[lakes[:2]] == 0.0).any())
+    q_forced = np.stack([o.get(orc.F_REACH_Q, m) for m in o.methods])
+    if option == 1:
+        assert np.array_equal(q_forced, q_plain[:, -1])                      # runoff-only lakes ignore the forcing
+    else:
+        assert cut and not np.array_equal(q_forced, q_plain[:, -1])
