@@ -141,6 +141,12 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
  * upload -> route (device only, no host<->device traffic) -> download. */
 int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message);
 int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
+/* Lake evaporation / precipitation of the NEXT routing call (mr_step, mr_step_batch*, mr_route_resident*), which must
+ * route exactly nSteps steps: basinEvapo / basinPrecip [nSteps][nHRU] in the units of the runoff, river-network HRU
+ * order (the optional arguments basinEvapo_in / basinPrecip_in of main_route, main_route.f90:33-34,174-199).  They pass
+ * through the same basin2reach as the runoff and enter lake_route when LakeInputOption is 0 or 2 (lake_route.f90:166-174)
+ * and the lake water balance.  A routing call without a preceding upload uses exactly zero for both. */
+int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message);
 int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
 /* BASIN_QR(1) ("dlayRunoff", the hillslope-routed lateral inflow) of the last batch as [nSteps][nRch] */
 int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message);

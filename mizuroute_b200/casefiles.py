@@ -39,8 +39,9 @@ def write_network(path: str, net: RiverNetwork):
 
 
 def write_runoff(path: str, hru_ids: np.ndarray, runoff: np.ndarray, dt: float, start: str = "2000-01-01 00:00:00",
-                 t_offset_steps: int = 0, dtype: str = "d"):
-    """runoff[time, hru]; time in seconds since `start` (stamped at the start of each step)."""
+                 t_offset_steps: int = 0, dtype: str = "d", extra=None):
+    """runoff[time, hru]; time in seconds since `start` (stamped at the start of each step).  `extra` = {name: array[time, hru]}
+    adds further forcing variables (lake evaporation / precipitation)."""
     f = netcdf_file(path, "w", version=2)
     f.createDimension("time", None)
     f.createDimension("hru", len(hru_ids))
@@ -51,9 +52,15 @@ def write_runoff(path: str, hru_ids: np.ndarray, runoff: np.ndarray, dt: float, 
     h[:] = hru_ids
     q = f.createVariable("runoff", dtype, ("time", "hru"))
     q.units = "mm/s"
+    more = {}
+    for nm in (extra or {}):
+        more[nm] = f.createVariable(nm, dtype, ("time", "hru"))
+        more[nm].units = "mm/s"
     for k in range(runoff.shape[0]):
         t[k] = (t_offset_steps + k) * dt
         q[k, :] = runoff[k]
+        for nm, v in more.items():
+            v[k, :] = extra[nm][k]
     f.close()
 
 
@@ -85,7 +92,7 @@ def _stamp(seconds: float, start: str) -> str:
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
                fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1", forcing_dt=None, sim_steps=None,
-               ro_time_stamp=None, new_file_frequency="single", extra_keys=None) -> str:
+               ro_time_stamp=None, new_file_frequency="single", extra_keys=None, lake_forcing=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
     continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`.  `forcing_dt` != dt_qsim
     writes the runoff records on their own interval (`sim_steps` simulation steps of opts.dt are then asked for);
@@ -130,7 +137,11 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, dt_ro, start, t_offset_steps=shift)
         fname_qsim = "runoff_%s.nc" % case_name
     elif split_forcing <= 1:
-        write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, opts.dt, start, t_offset_steps=first_step)
+        extra = None
+        if lake_forcing is not None:                         # (evapo[time, hru], precip[time, hru]) in river-network HRU order
+            assert remap is None and shuffle_hru_seed is None
+            extra = {"evapo": lake_forcing[0], "precip": lake_forcing[1]}
+        write_runoff(inp + "runoff_%s.nc" % case_name, ids, ro, opts.dt, start, t_offset_steps=first_step, extra=extra)
         fname_qsim = "runoff_%s.nc" % case_name
     else:
         bounds = np.linspace(0, runoff.shape[0], split_forcing + 1).astype(int)
@@ -164,6 +175,8 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("fname_qsim", fname_qsim, "runoff netCDF or list of netCDFs"),
         ("vname_qsim", "runoff", "runoff variable"),
         ("vname_time", "time", "time variable"),
+        ("vname_evapo", "evapo", "lake evaporation variable (<is_lake_sim> T, <LakeInputOption> 0 or 2)"),
+        ("vname_precip", "precip", "lake precipitation variable"),
         ("vname_hruid", "hruid", "forcing HRU id variable"),
         ("dname_time", "time", "time dimension"),
         ("dname_hruid", "hru", "HRU dimension"),

@@ -37,6 +37,11 @@ struct DevNet {
     const double *uh, *fracFuture;
     const double *kwK, *kwAK;       // KWT: sqrt(R_SLOPE)/R_MAN_N and ALFA*K**(1/ALFA) per reach (kwt_route.f90:1283-1296)
     const double *d03MaxS, *d03Coef, *d03Pow, *d03S0;
+    // lake forcing (optional): HRU-level evaporation / precipitation of the batch [K][nHRU] and their reach-level values for
+    // the lake reaches [kmax][nLake]; lakeEvap == nullptr = no lake forcing (exact zeros in lake_route)
+    const int *lakeSlot; int nLake;
+    const double *evapo, *precip;
+    double *lakeEvap, *lakePrecip;
     const double *rdepth, *sideSlope, *fldpSlope, *rstorage;   // Euler schemes: bankfull depth, side / floodplain slopes, bankfull storage
     // forcing and per-step times
     const double *runoff, *T0s, *T1s;

@@ -24,6 +24,7 @@
 #include "mr_dev.h"
 #include "mr_kwt.cuh"
 #include "mr_euler.cuh"
+#include "mr_lake.cuh"
 
 namespace mr {
 
@@ -162,6 +163,15 @@ __global__ void k_remap(const double *forcing, double *out, const int *mapNet, c
     }
 }
 
+// reach-level evaporation / precipitation of the lake reaches for the K steps of a batch (main_route.f90:174-199)
+__global__ void k_lake_forcing(DevNet d, const int *lakePos, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d.nLake * K) return;
+    const int slot = i % d.nLake, t = i / d.nLake, p = lakePos[slot];
+    d.lakeEvap[(size_t)t * d.nLake + slot] = lake_basin2reach(d, p, d.evapo + (size_t)t * d.nHRU);
+    d.lakePrecip[(size_t)t * d.nLake + slot] = lake_basin2reach(d, p, d.precip + (size_t)t * d.nHRU);
+}
+
 // carry BASIN_QR(1) of the previous batch into row 0 of the series
 __global__ void k_carry_qr(double *qrSer, int N, int Kprev) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,46 +187,6 @@ __device__ __forceinline__ double reach_wb(double v1, double v0, double qup, dou
     const double Qout = -1.0 * q * dt;
     const double Qtake = -1.0 * 0.0 * dt;
     return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
-}
-
-// lake_route.f90:87-229,466-470 for the endorheic and Doll-2003 types
-template <int M>
-__device__ void lake_reach(const DevNet &d, int p, int t, long long tau) {
-    const int N = d.nRch;
-    double *Qs = d.qSer[M] + (size_t)t * N;
-    const int u0 = d.upPtr[p], u1 = d.upPtr[p + 1];
-    const double dt = d.dt;
-    double qup = 0.0;
-    for (int m = u0; m < u1; ++m) qup = qup + Qs[d.upIdx[m]];
-    const int type = d.lakeType[p];
-    double v1 = d.vol1[M][p];
-    if (tau == 0) {                                    // iTime==1 cold start, lake_route.f90:139-157
-        if (type == MR_LAKE_ENDORHEIC) v1 = d.d03S0[p];
-        else if (type == MR_LAKE_DOLL03) v1 = d.d03MaxS[p];
-        else { raise(d.err, 20, p, E_LAKE_TYPE); return; }
-    }
-    const double v0 = v1;
-    const double qr1 = d.qrSer[(size_t)(t + 1) * N + p];
-    v1 = v1 + qup * dt;
-    if (d.lakeInputOption == 1 || d.lakeInputOption == 2) v1 = v1 + qr1 * dt;
-    if (d.lakeInputOption == 0 || d.lakeInputOption == 2) {
-        v1 = v1 + 0.0 * dt;                            // basinprecip = basinevapo = 0 (no such forcing on this path)
-        if (v1 > 0.0 * dt) v1 = v1 - 0.0 * dt; else v1 = 0.0;
-    }
-    double q;
-    if (type == MR_LAKE_ENDORHEIC) {
-        q = 0.0;
-    } else if (type == MR_LAKE_DOLL03) {
-        const double s0 = d.d03S0[p];
-        if ((v1 - s0) > 0) q = d.d03Coef[p] * (v1 - s0) * pow((v1 - s0) / (d.d03MaxS[p] - s0), d.d03Pow[p]);
-        else q = 0;
-        q = q / 86400.0;
-        q = fmin(q, v1 / dt);
-        v1 = v1 - q * dt;
-    } else { raise(d.err, 20, p, E_LAKE_TYPE); return; }
-    Qs[p] = q;
-    d.vol0[M][p] = v0; d.vol1[M][p] = v1;
-    d.wb[M][p] = reach_wb(v1, v0, qup, qr1, q, dt);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,6 +58,10 @@ struct mr_handle_s {
     double *dRunoffSlot[2] = {nullptr, nullptr};
     bool freeRec[2] = {false, false}, d2hRec = false;
     int asyncSlot = 0;
+    // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
+    int nLake = 0, lakeForcingSteps = 0;
+    int *dLakePos = nullptr;
+    double *dEvapo = nullptr, *dPrecip = nullptr, *dLakeEvap = nullptr, *dLakePrecip = nullptr;
     // multi-domain hand-off
     std::vector<int> ghostSegId, ghostKind; std::vector<double> ghostTotArea, ghostWidth;   // consumed by mr_set_network
     int nGhost = 0, nExport = 0;
@@ -187,12 +191,28 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     DevNet &d = h->d;
     const int N = d.nRch;
     h->launchesLast = 0;
+    if (h->lakeForcingSteps && h->lakeForcingSteps != K) {      // refused before anything is launched
+        h->lakeForcingSteps = 0;
+        return fail(message, 1, std::string(where) + "/lake forcing was uploaded for a different number of steps");
+    }
     CU(cudaEventRecord(h->ev[1], h->stream));
     k_times<<<1, 1, 0, h->stream>>>(T0, h->opt.dt, K, h->dT0s, h->dT1s);
     if (h->lastK > 0 && h->lastK != 0) k_carry_qr<<<(N + 255) / 256, 256, 0, h->stream>>>(d.qrSer, N, h->lastK);
     h->launchesLast += 2;
     k_basin<<<(N + BASIN_TPB - 1) / BASIN_TPB, BASIN_TPB, h->basinSmem, h->stream>>>(d, K, h->stepsDone);
     h->launchesLast++;
+    // lake forcing uploaded for this batch: reach-level evaporation / precipitation of the lake reaches (main_route.f90:174-199)
+    bool lakeForcing = false;
+    d.lakeEvap = d.lakePrecip = nullptr; d.evapo = d.precip = nullptr;
+    if (h->lakeForcingSteps) {
+        h->lakeForcingSteps = 0;
+        if (h->nLake) {
+            d.evapo = h->dEvapo; d.precip = h->dPrecip; d.lakeEvap = h->dLakeEvap; d.lakePrecip = h->dLakePrecip;
+            k_lake_forcing<<<(h->nLake * K + 255) / 256, 256, 0, h->stream>>>(d, h->dLakePos, K);
+            h->launchesLast++;
+            lakeForcing = true;
+        }
+    }
     if (h->nGhost) {
         if (!d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
         k_import_unpack<<<(h->nGhost * K + 255) / 256, 256, 0, h->stream>>>(d, h->dImpPos, h->nGhost, K);
@@ -202,10 +222,14 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     CU(cudaEventRecord(h->ev[2], h->stream));
     // The methods of route_opt share only BASIN_QR (read-only here), so they run concurrently: the last one on the
     // handle's stream, the others on auxiliary streams forked after k_basin and joined before the export.
+    // Exception: lake_route may cut the evaporation of a lake that runs dry, and the methods routed after it in the same
+    // step see the cut value (RCHFLX%basinevapo is shared, lake_route.f90:169-172) -- with lake forcing and LakeInputOption
+    // 0 / 2 the methods therefore run one after the other, in route_opt order.
     const int hb = (d.nHead + 255) / 256, nr = h->opt.n_routes;
+    const bool serialMethods = lakeForcing && nr > 1 && (h->opt.LakeInputOption == 0 || h->opt.LakeInputOption == 2);
     cudaStream_t st[N_METHODS];
     for (int r = 0; r < nr; ++r) {
-        st[r] = r == nr - 1 ? h->stream : h->aux[r];
+        st[r] = (serialMethods || r == nr - 1) ? h->stream : h->aux[r];
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
@@ -220,8 +244,9 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
             h->launchesLast++;
         }
     }
+    for (int pass = 0; pass < (serialMethods ? nr : 1); ++pass)
     for (int w = 0; w < h->topo.nStage + K - 1; ++w)
-        for (int r = 0; r < nr; ++r)
+        for (int r = serialMethods ? pass : 0; r < (serialMethods ? pass + 1 : nr); ++r)
             switch (h->opt.route_methods[r]) {
                 case M_SUM: launch_wavefront<M_SUM>(h, st[r], w, K, h->stepsDone); break;
                 case M_IRF: launch_wavefront<M_IRF>(h, st[r], w, K, h->stepsDone); break;
@@ -342,6 +367,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->nForcing = h->nMap = 0; h->dRunoffNet = nullptr; h->dOvW = nullptr; h->dMapNet = h->dMapPtr = h->dOvIdx = nullptr;
     h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
+    h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
     // reach parameters in stage order (process_ntopo.f90:176-187,359-366)
@@ -461,6 +487,13 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
             }
         }
     }
+    if (o.is_lake_sim) {                              // lake reaches by position, for the optional lake forcing
+        std::vector<int> slot(N, -1), pos;
+        for (int p = 0; p < N; ++p) if (h->flags[p] & FLAG_LAKE) { slot[p] = (int)pos.size(); pos.push_back(p); }
+        h->nLake = (int)pos.size();
+        if (h->nLake) { UP(lakeSlot, slot); e = dev_upload(h, &h->dLakePos, pos, where, message); if (e) return e; }
+        d.nLake = h->nLake;
+    }
     AL(d.err, 4);
     d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
     d.nRoutes = o.n_routes; d.kmax = KB; d.recLen = o.n_routes + 3 + 2 * KWP;
@@ -508,6 +541,26 @@ int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *messag
     CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->stream));
     stage_runoff(h, h->dRunoff, nSteps, h->stream);
     CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message) {
+    const char *where = "mr_upload_lake_forcing";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!basinEvapo || !basinPrecip) return fail(message, 1, "mr_upload_lake_forcing/null evaporation or precipitation");
+    if (!h->opt.is_lake_sim) return fail(message, 1, "mr_upload_lake_forcing/is_lake_sim is off");
+    const size_t nH = (size_t)(h->d.nHRU > 0 ? h->d.nHRU : 1), KB = (size_t)h->opt.max_batch, nL = (size_t)(h->nLake > 0 ? h->nLake : 1);
+    if (!h->dEvapo) {                                  // first use: rows of one batch, HRU level and lake-reach level
+        e = dev_alloc(h, &h->dEvapo, KB * nH, where, message); if (e) return e;
+        e = dev_alloc(h, &h->dPrecip, KB * nH, where, message); if (e) return e;
+        e = dev_alloc(h, &h->dLakeEvap, KB * nL, where, message); if (e) return e;
+        e = dev_alloc(h, &h->dLakePrecip, KB * nL, where, message); if (e) return e;
+    }
+    CU(cudaMemcpyAsync(h->dEvapo, basinEvapo, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dPrecip, basinPrecip, sizeof(double) * (size_t)nSteps * h->d.nHRU, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->lakeForcingSteps = nSteps;
     put_msg(message, "");
     return 0;
 }

@@ -552,22 +552,23 @@ int main(int argc, char **argv) {
         std::vector<nc3::Reader *> rd(files.size(), nullptr);
         std::vector<double> rec, wsum, wtot;
         double fillv = c.num("input_fillvalue", -9999.0);
-        // <scale_factor_runoff> / <offset_value_runoff> (scale_forcing, get_basin_runoff.f90:375-423; both ~0 = no runoff at all, :71-73)
-        const double roScale = c.num("scale_factor_runoff", -9999.0), roOffset = c.num("offset_value_runoff", -9999.0);
-        const bool roRescale = roScale != -9999.0 || roOffset != -9999.0;
-        const bool roZero = std::fabs(roScale) < 2.3e-308 && (std::fabs(roOffset) < 2.3e-308 || roOffset == -9999.0);
-        const double roA = roScale == -9999.0 ? 1.0 : roScale, roB = roOffset == -9999.0 ? 0.0 : roOffset;
-        auto load_step = [&](size_t k, double *dst) {
-            if (roZero) { std::fill(dst, dst + inCols, 0.0); return; }
+        // One forcing variable of simulation step k -> one row.  <scale_factor_*> / <offset_value_*>: scale_forcing
+        // (get_basin_runoff.f90:375-423); both ~0 = the variable is not read at all and is zero (:71-73,138-141,168-171).
+        struct VarSpec { std::string name; double scale, offset; bool flip; };
+        auto load_var = [&](const VarSpec &vs, size_t k, double *dst, size_t cols, bool forDeviceRemap) {
+            const bool rescale = vs.scale != -9999.0 || vs.offset != -9999.0;
+            const bool zero = std::fabs(vs.scale) < 2.3e-308 && (std::fabs(vs.offset) < 2.3e-308 || vs.offset == -9999.0);
+            const double A = vs.scale == -9999.0 ? 1.0 : vs.scale, B = vs.offset == -9999.0 ? 0.0 : vs.offset;
+            if (zero) { std::fill(dst, dst + cols, 0.0); return; }
             const TimeMap tm = time_map(k);
             for (size_t j = 0; j < tm.rec.size(); ++j) {
                 const auto wr = where[tm.rec[j]];
                 if (!rd[wr.first]) rd[wr.first] = new nc3::Reader(files[wr.first].path);
                 nc3::Reader &R = *rd[wr.first];
-                const nc3::Var &qv = R.var(vq);
+                const nc3::Var &qv = R.var(vs.name);
                 double fv; if (R.attr_value(qv, "_FillValue", fv)) fillv = fv;
                 R.read(qv, rec, wr.second, 1);
-                if (rec.size() != nForcing) die(20, "read_runoff/runoff variable is not dimensioned [time, hru]");
+                if (rec.size() != nForcing) die(20, "read_runoff/forcing variable " + vs.name + " is not dimensioned like the runoff");
                 if (tm.frac.empty()) break;
                 // several records under one step: time-weighted mean over the records that hold a value
                 // (read_1D_forcing, read_runoff.f90:298-325)
@@ -576,11 +577,19 @@ int main(int argc, char **argv) {
             }
             if (!tm.frac.empty())
                 for (size_t i = 0; i < rec.size(); ++i) rec[i] = wtot[i] == 0.0 ? fillv : (wtot[i] < 1.0 ? wsum[i] / wtot[i] : wsum[i]);
-            if (roRescale) for (size_t i = 0; i < rec.size(); ++i) if (rec[i] != fillv && rec[i] != -9999.0) rec[i] = roA * rec[i] + roB;
-            if (isRemap) { for (size_t i = 0; i < rec.size(); ++i) dst[i] = rec[i] == fillv ? -9999.0 : rec[i]; return; }  // remapped on the device; realMissing (< 0) is skipped there
+            if (vs.flip) for (size_t i = 0; i < rec.size(); ++i) if (rec[i] != fillv && rec[i] != -9999.0) rec[i] = -1.0 * rec[i] + 0.0;   // <is_Ep_upward_negative>
+            if (rescale) for (size_t i = 0; i < rec.size(); ++i) if (rec[i] != fillv && rec[i] != -9999.0) rec[i] = A * rec[i] + B;
+            if (forDeviceRemap) { for (size_t i = 0; i < rec.size(); ++i) dst[i] = rec[i] == fillv ? -9999.0 : rec[i]; return; }  // remapped on the device; realMissing (< 0) is skipped there
             std::fill(dst, dst + nHRU, 0.0);                                 // HRUs without forcing: realMissing -> 0 (sort_flux)
             for (size_t i = 0; i < rec.size(); ++i) if (ix[i] >= 0) { double v = rec[i]; if (v == fillv || v < 0.0) v = 0.0; dst[ix[i]] = v; }
         };
+        const VarSpec vsRunoff{vq, c.num("scale_factor_runoff", -9999.0), c.num("offset_value_runoff", -9999.0), false};
+        auto load_step = [&](size_t k, double *dst) { load_var(vsRunoff, k, dst, inCols, isRemap); };
+        // lake evaporation / precipitation (get_basin_runoff.f90:136-197): read with <is_lake_sim> T and <LakeInputOption> 0 or 2
+        const bool lakeForcing = o.is_lake_sim && (o.LakeInputOption == 0 || o.LakeInputOption == 2);
+        if (lakeForcing && isRemap) die(20, "route_runoff/lake evaporation and precipitation with <is_remap> T are not supported by this host");
+        const VarSpec vsEvapo{c.str("vname_evapo", "evapo"), c.num("scale_factor_Ep", -9999.0), c.num("offset_value_Ep", -9999.0), c.flag("is_Ep_upward_negative", false)};
+        const VarSpec vsPrecip{c.str("vname_precip", "precip"), c.num("scale_factor_prec", -9999.0), c.num("offset_value_prec", -9999.0), false};
 
         if (dry) {                                                       // the time map of the first steps, for inspection
             std::printf("{\"dt_ro\": %.3f, \"ro_time_stamp\": \"%s\", \"time_map\": [", dtro, stampAt.c_str());
@@ -640,6 +649,7 @@ int main(int argc, char **argv) {
 
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
         std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch);
+        std::vector<double> evRows(lakeForcing ? (size_t)batch * nHRU : 0), prRows(evRows.size());
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
@@ -651,6 +661,10 @@ int main(int argc, char **argv) {
             int nb = (int)std::min<size_t>(batch, nSteps - s);
             if (nextRestart < restartPlan.size()) nb = (int)std::min<size_t>(nb, restartPlan[nextRestart].first + 1 - s);      // a batch ends where a restart file is due
             for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
+            if (lakeForcing) {
+                for (int k = 0; k < nb; ++k) { load_var(vsEvapo, s + k, &evRows[(size_t)k * nHRU], nHRU, false); load_var(vsPrecip, s + k, &prRows[(size_t)k * nHRU], nHRU, false); }
+                ierr = mr_upload_lake_forcing(h, nb, evRows.data(), prRows.data(), msg); if (ierr) die(ierr, msg);
+            }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             for (int k = 0; k < nb; ++k) {

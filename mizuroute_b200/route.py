@@ -129,6 +129,15 @@ class Router:
         self._check(self._L.mr_step_batch_async(self._h, K, self.TSEC[0], rp, op, self._msg))
         self._advance(K)
 
+    def upload_lake_forcing(self, evapo, precip):
+        """Lake evaporation / precipitation [K, nHRU] (runoff units, river-network HRU order) of the NEXT routing call, which
+        must route K steps (mr_upload_lake_forcing; basinEvapo_in / basinPrecip_in of main_route)."""
+        e = np.ascontiguousarray(evapo, dtype=np.float64); p = np.ascontiguousarray(precip, dtype=np.float64)
+        if e.ndim == 1:
+            e, p = e[None, :], p[None, :]
+        assert e.shape == p.shape and e.shape[1] == self.net.nHRU
+        self._check(self._L.mr_upload_lake_forcing(self._h, int(e.shape[0]), _ptr(e, C.c_double), _ptr(p, C.c_double), self._msg))
+
     def upload_runoff(self, runoff):
         K, rp = self._host_ptr(runoff, self.nHRU)
         self._check(self._L.mr_upload_runoff(self._h, K, rp, self._msg))

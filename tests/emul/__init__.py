@@ -40,3 +40,16 @@ def load_euler(noise_seed: int = 0):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", *extra, "-x", "c++", "-shared",
                                "-fPIC", "-o", so, _EULER_SRC])
     return C.CDLL(so)
+
+
+_LAKE_SO = os.path.join(_HERE, "liblake_emul.so")
+_LAKE_SRC = os.path.join(_HERE, "lake_emul.cpp")
+_LAKE_DEPS = [_LAKE_SRC] + [os.path.join(_CSRC, f) for f in ("mr_lake.cuh", "mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
+
+
+def load_lake():
+    """Host build of the lake reach step (mr_lake.cuh) inside a kinematic-wave network, see lake_emul.cpp."""
+    if not os.path.exists(_LAKE_SO) or any(os.path.getmtime(f) > os.path.getmtime(_LAKE_SO) for f in _LAKE_DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-x", "c++", "-shared", "-fPIC",
+                               "-o", _LAKE_SO, _LAKE_SRC])
+    return C.CDLL(_LAKE_SO)

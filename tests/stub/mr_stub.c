@@ -16,6 +16,8 @@ struct mr_handle_s {
     int nRch, nHRU;
     /* remap (mr_set_remap) */
     int nForcing, nMap, *mapHru, *numQ, *qIx; double *wgt;
+    /* lake forcing of the next batch (mr_upload_lake_forcing) */
+    double *ev, *pr; int epSteps;
     /* BASIN_QR(1) of the steps of the last batch */
     double *qr; int qrSteps;
 };
@@ -69,12 +71,13 @@ int mr_set_remap(mr_handle h, int nForcing, int nMap, const int *mapHruIndex, co
 int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, double *q_out, char *message)
 {
     int t, r, ierr; double t0 = T0, t1 = T0 + h->o.dt;
+    if (h->epSteps && h->epSteps != nSteps) { say(message, "mr_step_batch/lake forcing was uploaded for a different number of steps"); return 1; }
     double *row = (double *)calloc((size_t)h->nHRU + 1, sizeof(double));
     free(h->qr); h->qr = (double *)malloc(sizeof(double) * (size_t)nSteps * (size_t)h->nRch); h->qrSteps = nSteps;
     for (t = 0; t < nSteps; t++) {
         const double *in = runoff + (size_t)t * (size_t)(h->nMap ? h->nForcing : h->nHRU);
         if (h->nMap) { mro_remap_1d(h->nMap, h->mapHru, h->numQ, h->qIx, h->wgt, in, row); in = row; }
-        ierr = mro_step(h->m, t0, t1, in);
+        ierr = h->epSteps ? mro_step_ep(h->m, t0, t1, in, h->ev + (size_t)t * h->nHRU, h->pr + (size_t)t * h->nHRU) : mro_step(h->m, t0, t1, in);
         if (ierr) { char b[MR_STRLEN]; snprintf(b, sizeof b, "mr_step_batch/main_route/%s", mro_message(h->m)); say(message, b); free(row); return ierr; }
         for (r = 0; r < h->m->nRoutes; r++)
             memcpy(q_out + ((size_t)r * nSteps + t) * h->nRch, h->m->REACH_Q[h->m->routeOrder[r]], sizeof(double) * (size_t)h->nRch);
@@ -82,6 +85,18 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
         t0 = t1; t1 = t0 + h->o.dt;
     }
     free(row);
+    h->epSteps = 0;
+    say(message, "");
+    return 0;
+}
+
+int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message)
+{
+    const size_t n = (size_t)nSteps * (size_t)h->nHRU;
+    free(h->ev); free(h->pr);
+    h->ev = (double *)malloc(sizeof(double) * (n + 1)); h->pr = (double *)malloc(sizeof(double) * (n + 1));
+    memcpy(h->ev, basinEvapo, sizeof(double) * n); memcpy(h->pr, basinPrecip, sizeof(double) * n);
+    h->epSteps = nSteps;
     say(message, "");
     return 0;
 }
@@ -208,6 +223,6 @@ void mr_destroy(mr_handle h)
 {
     if (!h) return;
     if (h->m) mro_destroy(h->m);
-    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr);
+    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr); free(h->ev); free(h->pr);
     free(h);
 }

@@ -326,6 +326,30 @@ def test_restart_files_written_during_the_run_continue_it_exactly(tmp_path, back
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("option", [0, 2])
+def test_host_feeds_lake_evaporation_and_precipitation(tmp_path, backend, option):
+    """<is_lake_sim> T with <LakeInputOption> 0 / 2: evaporation and precipitation are read from the forcing file beside the
+    runoff (get_basin_runoff.f90:136-197), with <scale_factor_Ep> applied, and reach lake_route through
+    mr_upload_lake_forcing; two methods, so the evaporation cut of a dried lake is shared (methods run in route_opt order)."""
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=500, seed=4, dt=86400.0, route_opt="14", steps=12, lakes=7)
+    opts.LakeInputOption = option
+    rng = np.random.default_rng(3)
+    ev = np.abs(rng.lognormal(np.log(3e-5), 0.5, size=ro.shape)); pr = np.abs(rng.lognormal(np.log(2e-5), 0.8, size=ro.shape))
+    lakes = np.flatnonzero(net.islake == 1)
+    ev[:, np.isin(net.hruSegId, net.segId[lakes[:2]])] *= 3.0e4                 # two lakes run dry
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="lakeep", lake_forcing=(ev, pr), extra_keys={"scale_factor_Ep": 0.5})
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    qo = Oracle(net, params, opts).run(ro, evapo=0.5 * ev, precip=pr)
+    q_plain = Oracle(net, params, opts).run(ro)
+    assert not np.array_equal(qo, q_plain)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["MCroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_exact_restart_of_the_euler_schemes(tmp_path, backend):
     """q_sub_kw / q_sub_mc / q_sub_dw [mol, seg] and volume_* in the restart file (popMetadat.f90:283-295): 24 steps in one
     run == 12 steps + restart + 12 steps, bit for bit, with <floodplain> T."""

@@ -1,0 +1,53 @@
+"""The lake reach step as the GPU runs it (mizuroute_b200/csrc/mr_lake.cuh), compiled for the host and stepped in stage
+order inside a kinematic-wave network, against the CPU oracle -- bit for bit: REACH_Q, REACH_VOL(1), the lake water
+balance and the evaporation left after a lake ran dry; without lake forcing (exact zeros, the path every earlier GPU lake
+test takes) and with evaporation / precipitation for LakeInputOption 0, 1, 2."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle.oracle import Oracle
+from tests import emul
+from tests.util import case
+
+
+@pytest.mark.parametrize("option,forcing", [(1, False), (0, False), (2, False), (0, True), (1, True), (2, True)])
+def test_lake_reach_device_source_matches_oracle(option, forcing):
+    net, params, opts, ro = case("conus", n=700, seed=4, dt=86400.0, route_opt="3", steps=14, lakes=9)
+    opts.LakeInputOption = option
+    K = ro.shape[0]
+    ev = pr = None
+    if forcing:
+        rng = np.random.default_rng(3)
+        ev = np.abs(rng.lognormal(np.log(3e-5), 0.5, size=ro.shape)); pr = np.abs(rng.lognormal(np.log(2e-5), 0.8, size=ro.shape))
+        lakes = np.flatnonzero(net.islake == 1)
+        ev[:, np.isin(net.hruSegId, net.segId[lakes[:2]])] *= 3.0e4          # two lakes run dry
+    o = Oracle(net, params, opts)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.step(ro[t], None if ev is None else ev[t], None if pr is None else pr[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, orc.M_KW)
+    tc, lc = opts.conv()
+    L = emul.load_lake()
+    qe = np.empty((K, net.nRch)); ve = np.empty(net.nRch); we = np.empty(net.nRch); ee = np.empty(net.nRch)
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.POINTER(ct))
+    arrs = [np.ascontiguousarray(a) for a in (net.islake, net.lakeModelType, net.D03_MaxStorage, net.D03_Coefficient, net.D03_Power, net.D03_S0)]
+    ierr = L.lake_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
+                           p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), p(arrs[0], C.c_int), p(arrs[1], C.c_int),
+                           p(arrs[2], C.c_double), p(arrs[3], C.c_double), p(arrs[4], C.c_double), p(arrs[5], C.c_double),
+                           C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(option), C.c_double(opts.runoffMin),
+                           C.c_double(tc), C.c_double(lc), C.c_int(K), p(qr, C.c_double), p(ev, C.c_double), p(pr, C.c_double),
+                           p(qe, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(ee, C.c_double), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qe, qo)
+    assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, orc.M_KW))
+    assert np.array_equal(we, o.get(orc.F_WB, orc.M_KW))
+    if forcing:
+        lk = net.islake == 1
+        assert np.array_equal(ee[lk], o.lake_forcing()[0][lk])
+        if option != 1:
+            assert (ve[lk] == 0.0).any()                                     # a lake did run dry

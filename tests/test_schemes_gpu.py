@@ -66,3 +66,40 @@ def test_molecule_state_round_trip_continues_exactly():
     qa = a.route_batch(np.ascontiguousarray(ro[12:]))
     qb = b.route_batch(np.ascontiguousarray(ro[12:]))
     assert np.array_equal(qa, qb)
+
+
+@pytest.mark.parametrize("option,route", [(0, "14"), (2, "14"), (1, "14"), (2, "1")])
+def test_lake_evaporation_and_precipitation_forcing(option, route):
+    """mr_upload_lake_forcing: evaporation / precipitation through basin2reach into lake_route (LakeInputOption 0 / 2) and the
+    lake water balance; two lakes run dry and their cut evaporation is seen by the method routed second (methods then run
+    one after the other).  IRF stays within 1e-6 (Doll's outflow calls pow), MC / KWT within 1e-4."""
+    from mizuroute_b200 import capi
+    from mizuroute_b200.route import Router
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0, route_opt=route, steps=12, lakes=9)
+    opts.LakeInputOption = option
+    rng = np.random.default_rng(3)
+    ev = np.abs(rng.lognormal(np.log(3e-5), 0.5, size=ro.shape)); pr = np.abs(rng.lognormal(np.log(2e-5), 0.8, size=ro.shape))
+    lakes = np.flatnonzero(net.islake == 1)
+    if option != 1:
+        ev[:, np.isin(net.hruSegId, net.segId[lakes[:2]])] *= 3.0e4
+    o = Oracle(net, params, opts)
+    qo = o.run(ro, evapo=ev, precip=pr)
+    r = Router(net, params, opts, max_batch=8)
+    parts = []
+    for s in range(0, ro.shape[0], 5):
+        r.upload_lake_forcing(ev[s:s + 5], pr[s:s + 5])
+        parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + 5])))
+    qg = np.concatenate(parts, axis=1)
+    for i, c in enumerate(route):
+        tol = 1e-6 if c == "1" else EULER_RTOL
+        assert rel_err(qg[i], qo[i], floor=1e-12) <= tol, c
+        assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1e-3) <= tol
+        assert rel_err(r.flux(capi.WB, int(c))[lakes], o.get(orc.F_WB, int(c))[lakes], floor=1.0) <= 1e-6
+    if option != 1:
+        assert (o.get(orc.F_REACH_VOL1, int(route[0]))[lakes] == 0.0).any()
+    # a batch without a preceding upload uses exact zeros again, and a wrong step count is refused
+    r.upload_lake_forcing(ev[:3], pr[:3])
+    with pytest.raises(Exception):
+        r.route_batch(np.ascontiguousarray(ro[:5]))
