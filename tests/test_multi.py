@@ -94,3 +94,16 @@ def test_decomposed_equals_single_domain(kind, n, nparts, dt, route):
     assert dec.mainstem.size > 0 and dec.outlets.size > 0
     assert not np.isnan(q).any()
     assert np.array_equal(q, single), "decomposed routing must reproduce the single-domain run bit for bit"
+
+
+@pytest.mark.gpu
+def test_decomposed_euler_schemes_equal_single_domain():
+    """The tributary -> mainstem hand-off carries REACH_Q of every active method, so the Euler schemes (route_opt 3/4/5)
+    decompose like SUM / IRF: bit-identical to the single-domain run."""
+    from mizuroute_b200.multi import route_decomposed_local
+    from mizuroute_b200.route import Router
+    net, params, opts, ro = case("conus", n=3000, seed=7, dt=3600.0, route_opt="345", steps=20)
+    single = Router(net, params, opts, max_batch=20).route_batch(ro)
+    q, dec = route_decomposed_local(net, params, opts, ro, 4, batch=7)
+    assert dec.mainstem.size > 0 and dec.outlets.size > 0
+    assert np.array_equal(q, single)
