@@ -56,6 +56,8 @@ class RouteOptions:
     runoffMin: float = 0.0
     units_qsim: str = "mm/s"
     floodplain: bool = False            # <floodplain>: finite bankfull depth for the Euler schemes (KW / MC / DW)
+    sim_start: Optional[tuple] = None   # (year, month, day, seconds of day) of <sim_start>: calendar of the HYPE lake model
+    calendar: str = "standard"          # "standard" (= gregorian, proleptic_gregorian) or "noleap"
 
     def conv(self):
         """(time_conv, length_conv) exactly as read_control.f90:443-474 derives them."""
@@ -92,6 +94,7 @@ class RiverNetwork:
     D03_Coefficient: Optional[np.ndarray] = None
     D03_Power: Optional[np.ndarray] = None
     D03_S0: Optional[np.ndarray] = None
+    lake_params: dict = field(default_factory=dict)      # further per-reach lake parameters by reference name, e.g. "HYP_E_emr" (dataTypes.f90:202-254)
     meta: dict = field(default_factory=dict)
 
     def __post_init__(self):

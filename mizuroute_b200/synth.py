@@ -221,6 +221,29 @@ def add_lakes(net: RiverNetwork, n_lakes: int, rng: np.random.Generator, frac_en
     net.meta["n_lakes"] = int(islake.sum())
 
 
+def make_hype_lakes(net: RiverNetwork, rng: np.random.Generator, frac: float = 0.5) -> int:
+    """Turn a share of the Doll-2003 lakes into HYPE reservoirs (lakeModelType 3, lake_route.f90:398-438) with plausible
+    parameters: ~10 m deep at the emergency spillway, a seasonal primary spillway, both outflow-combination modes."""
+    doll = np.flatnonzero((net.islake == 1) & (net.lakeModelType == 1))
+    pick = doll[rng.random(doll.size) < frac]
+    if pick.size == 0 and doll.size:
+        pick = doll[:1]
+    n = net.nRch
+    net.lakeModelType = net.lakeModelType.copy()
+    net.lakeModelType[pick] = 3
+    area = np.exp(rng.normal(np.log(2.0e7), 0.7, n))                 # m2
+    e_zero = rng.uniform(100.0, 900.0, n)
+    net.lake_params = {
+        "HYP_A_avg": area, "HYP_E_zero": e_zero, "HYP_E_min": e_zero + rng.uniform(0.5, 2.0, n),
+        "HYP_E_lim": e_zero + rng.uniform(4.0, 6.0, n), "HYP_E_emr": e_zero + rng.uniform(8.0, 12.0, n),
+        "HYP_Qrate_emr": rng.uniform(20.0, 80.0, n), "HYP_Erate_emr": rng.uniform(1.0, 2.0, n),
+        "HYP_Qrate_prim": rng.uniform(2.0, 30.0, n), "HYP_Qrate_amp": rng.uniform(0.0, 1.2, n),
+        "HYP_Qrate_phs": rng.integers(0, 365, n).astype(np.float64), "HYP_prim_F": (rng.random(n) < 0.8).astype(np.float64),
+        "HYP_Qsim_mode": (rng.random(n) < 0.5).astype(np.float64),
+    }
+    return int(pick.size)
+
+
 def runoff_series(net: RiverNetwork, n_steps: int, seed: int = 11, dt: float = 86400.0,
                   mean_mm_s: float = 2.0e-5, sigma: float = 1.0) -> np.ndarray:
     """Strictly positive runoff depth [n_steps, nHRU] in mm/s: per-HRU lognormal level x

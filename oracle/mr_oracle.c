@@ -109,6 +109,10 @@ typedef struct {
     /* lake forcing: reach-level evaporation / precipitation [m3/s] of the current step (RCHFLX%basinevapo / basinprecip,
        main_route.f90:174-199,243-249); hasEP = 0: no such forcing given, both are exactly zero */
     double *reachEvapo, *reachPrecip; int hasEP;
+    /* parametric lake models beyond Doll-2003: per-reach parameters by name (dataTypes.f90:202-254) and the simulation
+       start datetime (simDatetime(1) of step 1) the HYPE / Hanasaki formulations read the calendar from */
+    double *LP[64];
+    int hasStart, startYear, startMonth, startDay, noleap; double startSec;
     long iTime;                    /* globalData iTime, 1 on the first step */
     int nThreads;
     char message[256];
@@ -309,6 +313,10 @@ static void down_index(int nUp, int nSeg, const int *segId, const int *downId, i
 
 void mro_destroy(mro_t *h);
 void mro_set_channel(mro_t *h, int floodplain, double dscale, double floodplainSlope);
+static const char *LP_NAMES[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
+                                 "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode", NULL};
+enum { LP_HYP_E_emr, LP_HYP_E_lim, LP_HYP_E_min, LP_HYP_E_zero, LP_HYP_Qrate_emr, LP_HYP_Erate_emr, LP_HYP_Qrate_prim,
+       LP_HYP_Qrate_amp, LP_HYP_Qrate_phs, LP_HYP_prim_F, LP_HYP_A_avg, LP_HYP_Qsim_mode, LP_COUNT };
 
 /* ------------------------------------------------------------------------------------------ */
 /* create: read_streamSeg.f90 inputs -> augment_ntopo (process_ntopo.f90:39-266) -> put_data_struct */
@@ -483,6 +491,7 @@ void mro_destroy(mro_t *h)
     free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff); free(h->reachEvapo); free(h->reachPrecip);
     for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
                                      free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); }
+    { int k; for (k = 0; k < 64; k++) free(h->LP[k]); }
     free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
     free(h->QFUTURE_IRF); free(h->KW);
     free(h);
@@ -889,6 +898,59 @@ static int mc_rch(mro_t *h, int j)
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* datetime_data.f90: month, day and day-of-year of simDatetime(1) = start + (iTime-1)*dt      */
+/* ------------------------------------------------------------------------------------------ */
+static long long cal_days_from_civil(long long y, int m, int d, int noleap)
+{
+    static const int cum[12] = {0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334};
+    long long era; unsigned yoe, doy, doe;
+    if (noleap) return (y - 1970) * 365 + cum[m - 1] + (d - 1);
+    y -= m <= 2;
+    era = (y >= 0 ? y : y - 399) / 400;
+    yoe = (unsigned)(y - era * 400); doy = (153u * (unsigned)(m + (m > 2 ? -3 : 9)) + 2) / 5 + (unsigned)d - 1; doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (long long)doe - 719468;
+}
+static void cal_civil_from_days(long long days, int noleap, int *y, int *m, int *d)
+{
+    if (noleap) {
+        static const int ml[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+        long long yy = days >= 0 ? days / 365 : -((-days + 364) / 365); int doy = (int)(days - yy * 365), k = 0;
+        while (doy >= ml[k]) doy -= ml[k++];
+        *y = 1970 + (int)yy; *m = k + 1; *d = doy + 1;
+    } else {
+        long long z = days + 719468, era = (z >= 0 ? z : z - 146096) / 146097;
+        unsigned doe = (unsigned)(z - era * 146097), yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+        unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153;
+        *d = (int)(doy - (153 * mp + 2) / 5 + 1); *m = (int)(mp < 10 ? mp + 3 : mp - 9); *y = (int)(yoe + era * 400 + (*m <= 2));
+    }
+}
+/* calendar of the step being routed; returns 0 when no start datetime was given */
+static int step_calendar(const mro_t *h, int *month, int *day, int *doy)
+{
+    double t; long long days; int y;
+    if (!h->hasStart) return 0;
+    t = (double)cal_days_from_civil(h->startYear, h->startMonth, h->startDay, h->noleap) * SECPRDAY + h->startSec + (double)(h->iTime - 1) * h->dt;
+    days = (long long)floor((t + 1.e-6) / SECPRDAY);
+    cal_civil_from_days(days, h->noleap, &y, month, day);
+    *doy = (int)(days - cal_days_from_civil(y, 1, 1, h->noleap)) + 1;        /* fn_dayofyear, datetime_data.f90:209-218 */
+    return 1;
+}
+void mro_set_sim_start(mro_t *h, int year, int month, int day, double sec, int noleap)
+{
+    h->hasStart = 1; h->startYear = year; h->startMonth = month; h->startDay = day; h->startSec = sec; h->noleap = noleap;
+}
+int mro_set_lake_param(mro_t *h, const char *name, const double *values)
+{
+    int k;
+    for (k = 0; LP_NAMES[k]; k++) if (!strcmp(LP_NAMES[k], name)) {
+        free(h->LP[k]); h->LP[k] = (double *)malloc(sizeof(double) * (size_t)(h->nRch > 0 ? h->nRch : 1));
+        memcpy(h->LP[k], values, sizeof(double) * (size_t)h->nRch);
+        return 0;
+    }
+    return 1;
+}
+
 /* lake_route.f90:28-229,466-470 (endorheic and Doll03; LakeTargVol / WM / H06 / HYPE not restated) */
 static int lake_route(mro_t *h, int j, int M)
 {
@@ -898,6 +960,9 @@ static int lake_route(mro_t *h, int j, int M)
         switch (h->lakeModelType[j]) {
             case LAKE_ENDORHEIC: *V1 = h->D03_S0[j]; break;
             case LAKE_DOLL03:    *V1 = h->D03_MaxStorage[j]; break;
+            case LAKE_HYPE:
+                if (!h->LP[LP_HYP_E_emr] || !h->LP[LP_HYP_E_zero] || !h->LP[LP_HYP_A_avg]) { snprintf(h->message, 256, "lake_route/HYPE parameters are not set"); return 20; }
+                *V1 = (h->LP[LP_HYP_E_emr][j] - h->LP[LP_HYP_E_zero][j]) * h->LP[LP_HYP_A_avg][j]; break;
             default: snprintf(h->message, 256, "lake_route/lake model type not restated in oracle"); return 20;
         }
     }
@@ -921,6 +986,22 @@ static int lake_route(mro_t *h, int j, int M)
             *Q = fmin(*Q, *V1 / dt);
             *V1 = *V1 - *Q * dt;
             break;
+        case LAKE_HYPE: {          /* lake_route.f90:398-438 */
+            int k, month, day, doy;
+            double ELE, F_sin, F_lin, Q_prim, Q_spill, Q_sim; int F_prim;
+            for (k = 0; k < LP_COUNT; k++) if (!h->LP[k]) { snprintf(h->message, 256, "lake_route/HYPE parameter %s is not set", LP_NAMES[k]); return 20; }
+            if (!step_calendar(h, &month, &day, &doy)) { snprintf(h->message, 256, "lake_route/HYPE needs the simulation start datetime"); return 20; }
+            ELE = *V1 / h->LP[LP_HYP_A_avg][j] + h->LP[LP_HYP_E_zero][j];
+            F_sin = fmax(0.0, (1 + h->LP[LP_HYP_Qrate_amp][j] * sin(2 * PI_MR * (doy + (int)h->LP[LP_HYP_Qrate_phs][j]) / 365)));
+            F_lin = fmin(fmax((ELE - h->LP[LP_HYP_E_min][j]) / (h->LP[LP_HYP_E_lim][j] - h->LP[LP_HYP_E_min][j]), 0.0), 1.0);
+            F_prim = h->LP[LP_HYP_prim_F][j] != 0.0 ? 1 : 0;
+            Q_prim = F_sin * F_lin * F_prim * h->LP[LP_HYP_Qrate_prim][j];
+            Q_spill = 0.0;
+            if (ELE > h->LP[LP_HYP_E_emr][j]) Q_spill = h->LP[LP_HYP_Qrate_emr][j] * pow(ELE - h->LP[LP_HYP_E_emr][j], h->LP[LP_HYP_Erate_emr][j]);
+            if (h->LP[LP_HYP_Qsim_mode][j] != 0.0) Q_sim = Q_prim + Q_spill; else Q_sim = fmax(Q_prim, Q_spill);
+            *Q = fmin(Q_sim, fmax(0.0, (ELE - h->LP[LP_HYP_E_min][j]) * h->LP[LP_HYP_A_avg][j]) / dt);
+            *V1 = *V1 - *Q * dt;
+            break; }
         default: snprintf(h->message, 256, "lake_route/lake model type not restated in oracle"); return 20;
     }
     /* lake_route does not touch REACH_INFLOW */

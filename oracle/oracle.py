@@ -76,6 +76,14 @@ class Oracle:
             C.c_int(n_threads)))
         if not self.h:
             raise OracleError(-1, "mro_create failed (bad route_opt or UH construction)")
+        for name, vals in (getattr(net, "lake_params", None) or {}).items():
+            v = np.ascontiguousarray(vals, dtype=np.float64)
+            assert v.shape == (net.nRch,)
+            if L.mro_set_lake_param(self.h, C.c_char_p(name.encode()), _p(v, C.c_double)) != 0:
+                raise OracleError(20, "unknown lake parameter " + name)
+        if getattr(opts, "sim_start", None):
+            y, mo, d, sec = opts.sim_start
+            L.mro_set_sim_start(self.h, C.c_int(y), C.c_int(mo), C.c_int(d), dbl(sec), C.c_int(int(opts.calendar == "noleap")))
         if getattr(opts, "floodplain", False):          # <floodplain> T: bankfull depth dscale*sqrt(totalArea) (process_ntopo.f90:174-203)
             L.mro_set_channel(self.h, C.c_int(1), dbl(0.000045), dbl(1000.0))
         self.T0, self.T1 = 0.0, float(opts.dt)      # init_model_data.f90:600

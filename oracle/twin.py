@@ -615,6 +615,19 @@ class Twin:
         self.T1 = self.T0 + float(o.dt)
         self.itime += 1
 
+    def _day_of_year(self):
+        """dayofyear of simDatetime(1) (datetime_data.f90:209-218), via Python's calendar for the standard calendar."""
+        import datetime as _dt
+        if not getattr(self.o, "sim_start", None):
+            raise RouteError(20, "HYPE needs the simulation start datetime")
+        y, mo, d, sec = self.o.sim_start
+        elapsed = sec + (self.itime - 1) * float(self.o.dt)
+        if self.o.calendar == "noleap":
+            cum = [0, 31, 59, 90, 120, 151, 181, 212, 243, 273, 304, 334]
+            return (cum[mo - 1] + (d - 1) + int(math.floor((elapsed + 1e-6) / 86400.0))) % 365 + 1
+        now = _dt.datetime(y, mo, d) + _dt.timedelta(days=int(math.floor((elapsed + 1e-6) / 86400.0)))
+        return now.timetuple().tm_yday
+
     def _wb(self, m, j, qup, qlat, precip=0.0, evapo=0.0):
         dt = self.o.dt
         dvol = self.V1[m][j] - self.V0[m][j]
@@ -784,11 +797,14 @@ class Twin:
         for u in self.ups[j]:
             qup = qup + self.Q[m][u]
         lt = self.ltype[j]
+        lp = lambda name: float(net.lake_params[name][j])
         if self.itime == 1:
             if lt == 0:
                 self.V1[m][j] = float(net.D03_S0[j])
             elif lt == 1:
                 self.V1[m][j] = float(net.D03_MaxStorage[j])
+            elif lt == 3:
+                self.V1[m][j] = (lp("HYP_E_emr") - lp("HYP_E_zero")) * lp("HYP_A_avg")
             else:
                 raise RouteError(20, "lake type not restated")
         self.V0[m][j] = self.V1[m][j]
@@ -815,6 +831,19 @@ class Twin:
                 q = 0.0
             q = q / 86400.0
             q = min(q, v / dt)
+            v = v - q * dt
+        elif lt == 3:                   # HYPE, lake_route.f90:398-438
+            ele = v / lp("HYP_A_avg") + lp("HYP_E_zero")
+            doy = self._day_of_year()
+            f_sin = max(0.0, 1 + lp("HYP_Qrate_amp") * math.sin(2 * 3.14159265359 * (doy + int(lp("HYP_Qrate_phs"))) / 365))
+            f_lin = min(max((ele - lp("HYP_E_min")) / (lp("HYP_E_lim") - lp("HYP_E_min")), 0.0), 1.0)
+            f_prim = 1 if lp("HYP_prim_F") != 0.0 else 0
+            q_prim = f_sin * f_lin * f_prim * lp("HYP_Qrate_prim")
+            q_spill = 0.0
+            if ele > lp("HYP_E_emr"):
+                q_spill = lp("HYP_Qrate_emr") * (ele - lp("HYP_E_emr")) ** lp("HYP_Erate_emr")
+            q_sim = q_prim + q_spill if lp("HYP_Qsim_mode") != 0.0 else max(q_prim, q_spill)
+            q = min(q_sim, max(0.0, (ele - lp("HYP_E_min")) * lp("HYP_A_avg")) / dt)
             v = v - q * dt
         else:
             raise RouteError(20, "lake type not restated")

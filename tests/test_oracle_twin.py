@@ -133,3 +133,25 @@ def test_lake_evaporation_and_precipitation_forcing(option):
         assert np.array_equal(q_forced, q_plain[:, -1])                      # runoff-only lakes ignore the forcing
     else:
         assert cut and not np.array_equal(q_forced, q_plain[:, -1])
+
+
+@pytest.mark.parametrize("calendar,start", [("standard", (2000, 2, 25, 0.0)), ("noleap", (2001, 12, 28, 43200.0))])
+def test_hype_reservoirs(calendar, start):
+    """lakeModelType 3 (HYPE, lake_route.f90:398-438): seasonal primary spillway by day of year, emergency spillway above
+    HYP_E_emr, both ways of combining them; the run crosses a leap day / a year end so the calendars matter."""
+    from mizuroute_b200 import synth
+    net, params, opts, ro = case("conus", n=500, seed=4, dt=86400.0, route_opt="13", steps=14, lakes=10)
+    n_hype = synth.make_hype_lakes(net, np.random.default_rng(5))
+    assert n_hype >= 2
+    opts.sim_start, opts.calendar = start, calendar
+    ro = ro * 30.0                                                            # enough water to reach the spillways
+    o, t, q, qt = _both(net, params, opts, ro)
+    for i, m in enumerate(t.methods):
+        assert rel_err(q[i], np.array(qt[m])) <= 1e-12
+        assert rel_err(o.get(orc.F_REACH_VOL1, m), np.array(t.V1[m]), floor=1e-6) <= 1e-12
+    hype = np.flatnonzero((net.islake == 1) & (net.lakeModelType == 3))
+    assert (q[0][:, hype] > 0.0).any()
+    # without the start datetime the model cannot place the step in the year
+    opts.sim_start = None
+    with pytest.raises(orc.OracleError):
+        orc.Oracle(net, params, opts).run(ro[:1])
