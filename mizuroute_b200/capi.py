@@ -33,7 +33,7 @@ EXPORTS = [
     "mr_download_q", "mr_download_basin_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
     "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_remap", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
-    "mr_upload_lake_forcing",
+    "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start",
 ]
 
 

@@ -35,6 +35,8 @@ def write_network(path: str, net: RiverNetwork):
         for k in ("D03_MaxStorage", "D03_Coefficient", "D03_Power", "D03_S0"):
             if getattr(net, k) is not None:
                 put(k, getattr(net, k), "seg", "d")
+        for k, v in (getattr(net, "lake_params", None) or {}).items():      # HYP_* etc. by their reference names
+            put(k, v, "seg", "d")
     f.close()
 
 

@@ -20,6 +20,9 @@ constexpr int POOL_S = 88;            // with the full-capacity scratch in the g
 constexpr int NKIN = MR_MAXQPAR + 2;  // kinwav work arrays (1-based, <= 19 particles routed)
 
 enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
+// HYPE reservoir parameters of one lake (dataTypes.f90:202-213; integers / logicals as 0/1 doubles), in this order
+struct HypeParams { double E_emr, E_lim, E_min, E_zero, Qrate_emr, Erate_emr, Qrate_prim, Qrate_amp, Qrate_phs, prim_F, A_avg, Qsim_mode; };
+constexpr int HYP_COUNT = 12;
 enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, M_KW = 3, M_MC = 4, M_DW = 5, N_METHODS = 6 };   // = digits of <route_opt>, public_var.f90:74-80
 // computational molecules of the Euler schemes (init_model_data.f90:386-393): KW 20, MC 2, DW 20 nodes per reach
 constexpr int n_molecule(int m) { return m == M_KW || m == M_DW ? 20 : (m == M_MC ? 2 : 0); }
@@ -40,6 +43,10 @@ struct DevNet {
     // lake forcing (optional): HRU-level evaporation / precipitation of the batch [K][nHRU] and their reach-level values for
     // the lake reaches [kmax][nLake]; lakeEvap == nullptr = no lake forcing (exact zeros in lake_route)
     const int *lakeSlot; int nLake;
+    // HYPE reservoirs (lakeModelType 3): parameters by lake slot [nLake] and the day of year of every step of the batch [kmax]
+    // (nullptr = no simulation start datetime was given)
+    const struct HypeParams *hyp;
+    const int *stepDoy;
     const double *evapo, *precip;
     double *lakeEvap, *lakePrecip;
     const double *rdepth, *sideSlope, *fldpSlope, *rstorage;   // Euler schemes: bankfull depth, side / floodplain slopes, bankfull storage
@@ -67,7 +74,7 @@ struct DevNet {
 enum {
     E_NEG_RUNOFF = 1, E_LAKE_UPS = 2, E_NEG_FLOW = 3, E_SCRATCH = 4, E_STUCK = 5, E_TIME_ORDER = 6, E_BRACKET = 7,
     E_QD_BOUNDS = 8, E_ZERO_FLOW = 9, E_TEXIT2 = 10, E_RUPDATE = 11, E_NO_NONROUTED = 12, E_INTERP = 13,
-    E_LAKE_TYPE = 14, E_TOO_MANY_UPS = 15, E_THIN = 16, E_NO_ROUTED_UP = 17
+    E_LAKE_TYPE = 14, E_TOO_MANY_UPS = 15, E_THIN = 16, E_NO_ROUTED_UP = 17, E_LAKE_PARAM = 18, E_NO_CALENDAR = 19
 };
 
 MR_DEV_NOINLINE void raise(int *err, int code, int p, int site) {

@@ -192,12 +192,12 @@ __device__ __forceinline__ double reach_wb(double v1, double v0, double qup, dou
 // ------------------------------------------------------------------------------------------------
 // per-reach bodies of the three methods (route_network loop body, main_route.f90:372-390)
 // ------------------------------------------------------------------------------------------------
-template <int M, bool HEAD>
+template <int M, bool HEAD, bool HY = false>
 __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
     const int flags = d.flags[p];
     if (flags & FLAG_GHOST) return;
-    if (M != M_SUM && (flags & FLAG_LAKE)) { lake_reach<M>(d, p, t, tau); return; }
+    if (M != M_SUM && (flags & FLAG_LAKE)) { lake_reach<M, HY>(d, p, t, tau); return; }
     if (M == M_KWT && HEAD) {                          // no upstream reach => count(goodBas)=0, kwt_route.f90:181-205
         const int b = (int)(tau & 1);
         d.inflow[M_KWT][p] = 0.0;
@@ -261,21 +261,21 @@ __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long 
 }
 
 // headwater reaches (positions [0, nHead)): no upstream dependency, so one thread routes all K steps
-template <int M>
+template <int M, bool HY = false>
 __global__ void __launch_bounds__(256) k_headwater(DevNet d, int K, long long tau0) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= d.nHead) return;
-    for (int t = 0; t < K; ++t) route_reach<M, true>(d, p, t, tau0 + t);
+    for (int t = 0; t < K; ++t) route_reach<M, true, HY>(d, p, t, tau0 + t);
 }
 
 // one wavefront of interior reaches: positions [lo,hi) hold stages w-K+1..w; the reach at stage s does step t = w - s
-template <int M>
+template <int M, bool HY = false>
 __global__ void __launch_bounds__(256) k_route(DevNet d, int lo, int hi, int w, long long tau0) {
     static_assert(M != M_KWT, "KWT wavefronts run in k_route_kwt");
     const int p = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hi) return;
     const int t = w - d.stageOf[p];
-    route_reach<M, false>(d, p, t, tau0 + t);
+    route_reach<M, false, HY>(d, p, t, tau0 + t);
 }
 
 // per-reach constants of kinwav_rch (kwt_route.f90:1283-1296), evaluated once with the device's sqrt/pow
@@ -299,6 +299,7 @@ constexpr int KWT_TEAMS = KWT_WARPS * (32 / MR_TEAM);    // teams (tasks in flig
 constexpr int KWT_ARENA_SMS = 256, KWT_ARENA_SLOTS = 64;
 // One (reach, step) task of a KWT wavefront, by one team.  EVERY lane of the warp enters (a team without a task has
 // active = false): the first attempt re-converges the teams of the warp at its phase boundaries (kwt_reach_team<.., true>).
+template <bool HY>
 __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, int p, bool active, int w, long long tau0) {
     const int lane = MR_LANE;
     int t = 0;
@@ -313,7 +314,7 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
             if (lane == 0) { d.kwN[b][p] = (int)rec[0]; d.kwNR[b][p] = (int)rec[1]; }
             active = false;
         } else if (flags & FLAG_LAKE) {
-            if (lane == 0) lake_reach<M_KWT>(d, p, t, tau0 + t);
+            if (lane == 0) lake_reach<M_KWT, HY>(d, p, t, tau0 + t);
             active = false;
         }
     }
@@ -352,13 +353,14 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
 #endif
 // Tasks are dealt to teams block by block; the loop bounds are the same for all teams of a warp (required by the
 // full-warp syncs inside kwt_task).
+template <bool HY = false>
 __global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
     __shared__ KwtScratchSmall S[KWT_TEAMS];
     const int team = threadIdx.x / MR_TEAM;
     const int stride = gridDim.x * KWT_TEAMS;
     for (int base = lo + blockIdx.x * KWT_TEAMS; base < hi; base += stride) {
         const int p = base + team;
-        kwt_task(d, S[team], p, p < hi, w, tau0);
+        kwt_task<HY>(d, S[team], p, p < hi, w, tau0);
         MR_WSYNC();
     }
 }

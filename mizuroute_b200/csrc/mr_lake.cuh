@@ -1,4 +1,4 @@
-// Lake reaches: lake_route (lake_route.f90:87-229,466-470) for the endorheic and Doll-2003 types, with the lake forcing
+// Lake reaches: lake_route (lake_route.f90:87-229,398-438,466-470) for the endorheic, Doll-2003 and HYPE types, with the lake forcing
 // of main_route.f90:174-199,243-249 -- reach-level evaporation and precipitation, produced by the same basin2reach as the
 // runoff -- when the caller supplies it (mr_upload_lake_forcing); without it both are exactly zero.
 // Compiles for the device (called from route_reach / kwt_task) and for the host (tests/emul), where it must match the
@@ -40,7 +40,26 @@ MR_LAKE_FN double lake_wb(double v1, double v0, double qup, double qlat, double 
     return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
 }
 
-template <int M>
+// HYPE reservoir outflow (lake_route.f90:398-438) of a lake holding volume v1 on day-of-year doy.  Out of line and fed
+// through a pointer into HBM (a DevNet reference would force the kernel's parameter block into local memory, a dozen scalar
+// arguments would raise the register pressure at the call site), so that sin() / pow() do not weigh on the wavefront
+// kernels that merely may meet such a lake.
+MR_DEV_NOINLINE double hype_outflow(const HypeParams *hp, int doy, double v1, double dt) {
+    const HypeParams h = *hp;
+    const double ELE = v1 / h.A_avg + h.E_zero;
+    const double F_sin = fmax(0.0, (1 + h.Qrate_amp * sin(2 * 3.14159265359 * (doy + (int)h.Qrate_phs) / 365)));   // pi, public_var.f90:16
+    const double F_lin = fmin(fmax((ELE - h.E_min) / (h.E_lim - h.E_min), 0.0), 1.0);
+    const int F_prim = h.prim_F != 0.0 ? 1 : 0;
+    const double Q_prim = F_sin * F_lin * F_prim * h.Qrate_prim;
+    double Q_spill = 0.0;
+    if (ELE > h.E_emr) Q_spill = h.Qrate_emr * pow(ELE - h.E_emr, h.Erate_emr);
+    const double Q_sim = h.Qsim_mode != 0.0 ? Q_prim + Q_spill : fmax(Q_prim, Q_spill);
+    return fmin(Q_sim, fmax(0.0, (ELE - h.E_min) * h.A_avg) / dt);
+}
+
+// HY: the domain holds HYPE reservoirs.  The kernels are instantiated for both values and the launch picks one, so that a
+// domain without them runs exactly the code it ran before HYPE existed (no extra registers, stack or spills).
+template <int M, bool HY = false>
 MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
     double *Qs = d.qSer[M] + (size_t)t * N;
@@ -53,6 +72,11 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     if (tau == 0) {                                    // iTime==1 cold start, lake_route.f90:139-157
         if (type == MR_LAKE_ENDORHEIC) v1 = d.d03S0[p];
         else if (type == MR_LAKE_DOLL03) v1 = d.d03MaxS[p];
+        else if (HY && type == MR_LAKE_HYPE) {
+            if (!d.hyp) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
+            const HypeParams &hp = d.hyp[d.lakeSlot[p]];
+            v1 = (hp.E_emr - hp.E_zero) * hp.A_avg;
+        }
         else { raise(d.err, 20, p, E_LAKE_TYPE); return; }
     }
     const double v0 = v1;
@@ -82,6 +106,13 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
         q = q / 86400.0;
         q = fmin(q, v1 / dt);
         v1 = v1 - q * dt;
+    } else if (HY && type == MR_LAKE_HYPE) {
+        if constexpr (HY) {
+            if (!d.hyp) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
+            if (!d.stepDoy) { raise(d.err, 20, p, E_NO_CALENDAR); return; }
+            q = hype_outflow(d.hyp + d.lakeSlot[p], d.stepDoy[t], v1, dt);
+            v1 = v1 - q * dt;
+        } else q = 0.0;
     } else { raise(d.err, 20, p, E_LAKE_TYPE); return; }
     Qs[p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1;

@@ -14,12 +14,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "mr_kernels.cuh"
 #include "mr_topo.h"
 #include "mr_uh.h"
+#include "mr_calendar.h"
 
 using namespace mr;
 
@@ -58,6 +60,11 @@ struct mr_handle_s {
     double *dRunoffSlot[2] = {nullptr, nullptr};
     bool freeRec[2] = {false, false}, d2hRec = false;
     int asyncSlot = 0;
+    // parametric lake models beyond Doll-2003: named per-reach parameters (caller order, consumed by mr_set_network) and the
+    // simulation start datetime (mr_set_sim_start) from which the day of year of every step follows
+    std::map<std::string, std::vector<double>> lakeParams;
+    bool hasStart = false, hasHype = false; int startY = 0, startM = 1, startD = 1, noleap = 0; double startSec = 0.0;
+    int *dStepDoy = nullptr; std::vector<int> stepDoyHost;
     // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
     int nLake = 0, lakeForcingSteps = 0;
     int *dLakePos = nullptr;
@@ -139,6 +146,8 @@ const char *site_text(int site) {
         case E_NO_NONROUTED: return "kwt_rch/no non-routed particle left";
         case E_INTERP: return "kwt_rch/interp_rch/bad bounds";
         case E_LAKE_TYPE: return "lake_route/unable to identify the parametric lake model type";
+        case E_LAKE_PARAM: return "lake_route/parameters of the lake model are not set (mr_set_lake_param)";
+        case E_NO_CALENDAR: return "lake_route/the lake model needs the simulation start datetime (mr_set_sim_start)";
         case E_TOO_MANY_UPS: return "kwt_rch/qexmul_rch/more upstream series than the kernel merges";
         case E_THIN: return "kwt_rch/remove_rch/no interior particle to remove";
         case E_NO_ROUTED_UP: return "kwt_rch/qexmul_rch/upstream wave has no routed element";
@@ -164,9 +173,11 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     if constexpr (M == M_KWT) {
         int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        k_route_kwt<<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
     } else {
-        k_route<M><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
     h->launchesLast++;
 }
@@ -194,6 +205,13 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     if (h->lakeForcingSteps && h->lakeForcingSteps != K) {      // refused before anything is launched
         h->lakeForcingSteps = 0;
         return fail(message, 1, std::string(where) + "/lake forcing was uploaded for a different number of steps");
+    }
+    d.stepDoy = nullptr;
+    if (h->hasHype && h->hasStart) {                    // day of year of simDatetime(1) of every step of the batch
+        h->stepDoyHost.resize(K);
+        for (int t = 0; t < K; ++t) { int mo, dy; step_calendar(h->startY, h->startM, h->startD, h->startSec, h->noleap != 0, h->opt.dt, h->stepsDone + t, mo, dy, h->stepDoyHost[t]); }
+        CU(cudaMemcpyAsync(h->dStepDoy, h->stepDoyHost.data(), sizeof(int) * K, cudaMemcpyHostToDevice, h->stream));
+        d.stepDoy = h->dStepDoy;
     }
     CU(cudaEventRecord(h->ev[1], h->stream));
     k_times<<<1, 1, 0, h->stream>>>(T0, h->opt.dt, K, h->dT0s, h->dT1s);
@@ -233,13 +251,14 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
+            const bool hy = h->hasHype;             // HYPE reservoirs in this domain: the instantiation that knows them
             switch (h->opt.route_methods[r]) {
-                case M_SUM: k_headwater<M_SUM><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
-                case M_IRF: k_headwater<M_IRF><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
-                case M_KWT: k_headwater<M_KWT><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
-                case M_KW: k_headwater<M_KW><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
-                case M_MC: k_headwater<M_MC><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
-                case M_DW: k_headwater<M_DW><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_SUM: if (hy) k_headwater<M_SUM, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_SUM, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_IRF: if (hy) k_headwater<M_IRF, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_IRF, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_KWT: if (hy) k_headwater<M_KWT, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_KWT, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_KW: if (hy) k_headwater<M_KW, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_KW, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_MC: if (hy) k_headwater<M_MC, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_MC, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
+                case M_DW: if (hy) k_headwater<M_DW, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_DW, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
             }
             h->launchesLast++;
         }
@@ -367,6 +386,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->nForcing = h->nMap = 0; h->dRunoffNet = nullptr; h->dOvW = nullptr; h->dMapNet = h->dMapPtr = h->dOvIdx = nullptr;
     h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
+    h->dStepDoy = nullptr; h->hasHype = false;
     h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -493,6 +513,21 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         h->nLake = (int)pos.size();
         if (h->nLake) { UP(lakeSlot, slot); e = dev_upload(h, &h->dLakePos, pos, where, message); if (e) return e; }
         d.nLake = h->nLake;
+        h->hasHype = false;
+        for (int p : pos) if (ltype[p] == MR_LAKE_HYPE) h->hasHype = true;
+        if (h->hasHype) {                             // HYP_* by lake slot (dataTypes.f90:202-213)
+            static const char *names[HYP_COUNT] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr",
+                                                   "HYP_Qrate_prim", "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
+            std::vector<HypeParams> bySlot(h->nLake);
+            for (int k = 0; k < HYP_COUNT; ++k) {
+                auto it = h->lakeParams.find(names[k]);
+                if (it == h->lakeParams.end() || (int)it->second.size() != nRch)
+                    return fail(message, 20, std::string("mr_set_network/HYPE lakes need the parameter ") + names[k] + " for every reach (mr_set_lake_param)");
+                for (int sIdx = 0; sIdx < h->nLake; ++sIdx) reinterpret_cast<double *>(&bySlot[sIdx])[k] = it->second[T.pos2rch[pos[sIdx]]];
+            }
+            UP(hyp, bySlot);
+            AL(h->dStepDoy, KB);
+        }
     }
     AL(d.err, 4);
     d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
@@ -517,7 +552,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     {
         int nSM = 148, perSM = 8;
         cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, o.device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt<false>, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
         h->kwtGridMax = 0x7fffffff;                // measured on C4: one block per KWT_TEAMS tasks beats a persistent grid by 3 %
         (void)nSM; (void)perSM;
         // tuning knob (development): MR_KWT_WAVES = resident waves the KWT grid may span; 0 = one block per KWT_TEAMS tasks
@@ -541,6 +576,26 @@ int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *messag
     CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->stream));
     stage_runoff(h, h->dRunoff, nSteps, h->stream);
     CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message) {
+    if (!h || !name || !values || n < 1) return fail(message, 1, "mr_set_lake_param/null argument");
+    static const char *known[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
+                                  "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
+    bool ok = false;
+    for (const char *k : known) ok = ok || !std::strcmp(k, name);
+    if (!ok) return fail(message, 20, std::string("mr_set_lake_param/unknown or unsupported lake parameter ") + name);
+    h->lakeParams[name].assign(values, values + n);
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay, int noleap, char *message) {
+    if (!h) return fail(message, 1, "mr_set_sim_start/null handle");
+    if (month < 1 || month > 12 || day < 1 || day > 31 || secOfDay < 0.0 || secOfDay >= 86400.0) return fail(message, 1, "mr_set_sim_start/invalid date");
+    h->hasStart = true; h->startY = year; h->startM = month; h->startD = day; h->startSec = secOfDay; h->noleap = noleap ? 1 : 0;
     put_msg(message, "");
     return 0;
 }

@@ -617,6 +617,16 @@ int main(int argc, char **argv) {
         char msg[MR_STRLEN];
         mr_handle h = nullptr;
         int ierr = mr_create(&o, &h, msg); if (ierr) die(ierr, msg);
+        if (o.is_lake_sim) {                                  // HYPE reservoirs: HYP_* of the river-network file, and the calendar of the steps
+            static const char *hypNames[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
+                                             "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
+            for (const char *nm : hypNames)
+                if (const nc3::Var *v = nt.find(c.str(std::string("varname_") + nm, nm))) {
+                    std::vector<double> vals; nt.read_all(*v, vals);
+                    if (vals.size() != nRch) die(20, std::string("read_streamSeg/") + nm + " is not dimensioned by segment");
+                    ierr = mr_set_lake_param(h, nm, (int)nRch, vals.data(), msg); if (ierr) die(ierr, msg);
+                }
+        }
         ierr = mr_set_network(h, (int)nRch, (int)nHRU, segId.data(), downSegId.data(), hruSegId.data(), area.data(), length.data(), slope.data(),
                               geomFromFile ? width.data() : nullptr, geomFromFile ? man_n.data() : nullptr, islake.empty() ? nullptr : islake.data(),
                               lakeType.empty() ? nullptr : lakeType.data(), d03[0].empty() ? nullptr : d03[0].data(), d03[1].empty() ? nullptr : d03[1].data(),
@@ -656,6 +666,10 @@ int main(int argc, char **argv) {
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
             T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
+        if (o.is_lake_sim) {                                  // the library counts steps from the cold start: step 0 was T0 seconds before <sim_start>
+            const Civil cv = civil_from_sec(tStart - T0, noleap);
+            ierr = mr_set_sim_start(h, cv.y, cv.mo, cv.d, (double)cv.sod, noleap ? 1 : 0, msg); if (ierr) die(ierr, msg);
+        }
         size_t nextRestart = 0;
         for (size_t s = 0; s < nSteps;) {
             int nb = (int)std::min<size_t>(batch, nSteps - s);

@@ -61,6 +61,12 @@ class Router:
         self.max_batch = int(max_batch)
         self._check(self._L.mr_create(C.byref(o), C.byref(self._h), self._msg))
         n = net
+        for name, vals in (getattr(net, "lake_params", None) or {}).items():     # HYPE reservoirs etc., before mr_set_network
+            v = np.ascontiguousarray(vals, dtype=np.float64)
+            self._check(self._L.mr_set_lake_param(self._h, name.encode(), int(v.size), _ptr(v, C.c_double), self._msg))
+        if getattr(opts, "sim_start", None):
+            y, mo, d, sec = opts.sim_start
+            self._check(self._L.mr_set_sim_start(self._h, int(y), int(mo), int(d), C.c_double(float(sec)), int(opts.calendar == "noleap"), self._msg))
         if ghosts is not None:
             gid, gkind, garea, gwidth = (np.ascontiguousarray(ghosts[0], dtype=np.int32), np.ascontiguousarray(ghosts[1], dtype=np.int32),
                                          np.ascontiguousarray(ghosts[2], dtype=np.float64), np.ascontiguousarray(ghosts[3], dtype=np.float64))

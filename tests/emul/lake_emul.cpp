@@ -11,6 +11,7 @@
 #include "../../mizuroute_b200/csrc/mr_euler.cuh"
 #include "../../mizuroute_b200/csrc/mr_lake.cuh"
 #include "../../mizuroute_b200/csrc/mr_topo.h"
+#include "../../mizuroute_b200/csrc/mr_calendar.h"
 
 using namespace mr;
 
@@ -20,6 +21,8 @@ extern "C" int lake_emul_run(int nRch, int nHRU, const int *segId, const int *do
                              int lakeInputOption, double runoffMin, double tconv, double lconv, int nSteps,
                              const double *qr /* [nSteps+1][nRch] BASIN_QR(1), caller order */,
                              const double *evapo, const double *precip /* [nSteps][nHRU] or NULL */,
+                             const double *hyp /* [12][nRch] HYP_* in HypeParams order, caller order, or NULL */,
+                             int startY, int startM, int startD, double startSec, int noleap /* startY = 0: no calendar */,
                              double *q_out /* [nSteps][nRch] */, double *vol_out, double *wb_out, double *evap_left /* [nRch], last step */, char *msg) {
     Topology T;
     std::string terr;
@@ -52,6 +55,16 @@ extern "C" int lake_emul_run(int nRch, int nHRU, const int *segId, const int *do
     d.qrSer = qrSer.data(); d.qSer[M] = qSer.data(); d.inflow[M] = inflow.data(); d.vol0[M] = vol0.data(); d.vol1[M] = vol1.data();
     d.wb[M] = wb.data(); d.mol[M] = mol.data(); d.floodVol[M] = flood.data(); d.reachEle[M] = ele.data();
     d.err = err; d.lakeSlot = slot.data(); d.nLake = nLake;
+    std::vector<HypeParams> hypBySlot(nLake ? nLake : 1);
+    std::vector<int> doy(nSteps, 0);
+    if (hyp && nLake) {                                      // as mr_set_network / route_device do
+        for (int k = 0; k < HYP_COUNT; ++k) for (int sl = 0; sl < nLake; ++sl) reinterpret_cast<double *>(&hypBySlot[sl])[k] = hyp[(size_t)k * N + T.pos2rch[pos[sl]]];
+        d.hyp = hypBySlot.data();
+    }
+    if (startY) {
+        for (int t = 0; t < nSteps; ++t) { int mo, dy; step_calendar(startY, startM, startD, startSec, noleap != 0, dt, t, mo, dy, doy[t]); }
+        d.stepDoy = doy.data();
+    }
     if (evapo && precip && nLake) {                          // k_lake_forcing
         d.evapo = evapo; d.precip = precip; d.lakeEvap = lakeE.data(); d.lakePrecip = lakeP.data();
         for (int t = 0; t < nSteps; ++t) for (int s = 0; s < nLake; ++s) {
@@ -61,7 +74,7 @@ extern "C" int lake_emul_run(int nRch, int nHRU, const int *segId, const int *do
     }
     for (int t = 0; t < nSteps; ++t)
         for (int p = 0; p < N; ++p) {                        // route_reach<M_KW, *>: stage order
-            if (flags[p] & FLAG_LAKE) lake_reach<M>(d, p, t, (long long)t); else kw_dw_reach<M>(d, p, t);
+            if (flags[p] & FLAG_LAKE) lake_reach<M, true>(d, p, t, (long long)t); else kw_dw_reach<M>(d, p, t);
             if (err[0]) { std::snprintf(msg, 256, "ierr %d at position %d site %d step %d", err[0], err[1], err[2], t); return err[0]; }
         }
     for (int t = 0; t < nSteps; ++t) for (int r = 0; r < N; ++r) q_out[(size_t)t * N + r] = qSer[(size_t)t * N + T.rch2pos[r]];

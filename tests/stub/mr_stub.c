@@ -16,6 +16,9 @@ struct mr_handle_s {
     int nRch, nHRU;
     /* remap (mr_set_remap) */
     int nForcing, nMap, *mapHru, *numQ, *qIx; double *wgt;
+    /* named lake parameters and the simulation start, applied to the oracle in mr_set_network */
+    char lpName[16][32]; double *lpVal[16]; int nLp;
+    int hasStart, sy, sm, sd, noleap; double ssec;
     /* lake forcing of the next batch (mr_upload_lake_forcing) */
     double *ev, *pr; int epSteps;
     /* BASIN_QR(1) of the steps of the last batch */
@@ -50,6 +53,8 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
                       h->o.is_lake_sim, h->o.lakeRegulate, h->o.LakeInputOption, h->o.runoffMin, h->o.time_conv, h->o.length_conv,
                       h->o.fshape, h->o.tscale, h->o.velo, h->o.diff, h->o.mann_n, h->o.wscale, 1);
     if (!h->m) { say(message, "mr_set_network/oracle refused the network"); return 20; }
+    { int k; for (k = 0; k < h->nLp; k++) if (mro_set_lake_param(h->m, h->lpName[k], h->lpVal[k])) { say(message, "mr_set_network/unknown lake parameter"); return 20; } }
+    if (h->hasStart) mro_set_sim_start(h->m, h->sy, h->sm, h->sd, h->ssec, h->noleap);
     if (h->o.floodplain) mro_set_channel(h->m, 1, h->o.dscale > 0.0 ? h->o.dscale : 0.000045, h->o.floodplainSlope > 0.0 ? h->o.floodplainSlope : 1000.0);
     say(message, "");
     return 0;
@@ -86,6 +91,24 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     }
     free(row);
     h->epSteps = 0;
+    say(message, "");
+    return 0;
+}
+
+int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message)
+{
+    if (h->nLp >= 16) { say(message, "mr_set_lake_param/too many parameters for the stub"); return 1; }
+    strncpy(h->lpName[h->nLp], name, 31); h->lpName[h->nLp][31] = 0;
+    h->lpVal[h->nLp] = (double *)malloc(sizeof(double) * (size_t)n); memcpy(h->lpVal[h->nLp], values, sizeof(double) * (size_t)n);
+    h->nLp++;
+    say(message, "");
+    return 0;
+}
+
+int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay, int noleap, char *message)
+{
+    h->hasStart = 1; h->sy = year; h->sm = month; h->sd = day; h->ssec = secOfDay; h->noleap = noleap;
+    if (h->m) mro_set_sim_start(h->m, year, month, day, secOfDay, noleap);
     say(message, "");
     return 0;
 }

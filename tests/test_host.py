@@ -350,6 +350,34 @@ def test_host_feeds_lake_evaporation_and_precipitation(tmp_path, backend, option
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_hype_reservoirs_and_their_calendar_survive_a_restart(tmp_path, backend):
+    """lakeModelType 3: HYP_* are read from the river-network file and the day of year follows <sim_start>; a run continued
+    from a restart file -- whose library handle counts steps from the cold start -- keeps the calendar (2000-02-25 + 14 days
+    crosses the leap day) and reproduces the uninterrupted run bit for bit."""
+    from mizuroute_b200 import synth
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=400, seed=4, dt=86400.0, route_opt="13", steps=14, lakes=8)
+    assert synth.make_hype_lakes(net, np.random.default_rng(5), frac=0.7) >= 2
+    ro = ro * 30.0
+    d = str(tmp_path)
+    start = "2000-02-25 00:00:00"
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "4"], capture_output=True, text=True)
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="full", start=start)); assert r.returncode == 0, r.stderr
+    h_full = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    opts.sim_start = (2000, 2, 25, 0.0)
+    qo = Oracle(net, params, opts).run(ro)
+    np.testing.assert_allclose(h_full["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(h_full["KWroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+    r = run(casefiles.write_case(d, net, params, opts, ro[:6], case_name="first", start=start, restart_write="last")); assert r.returncode == 0, r.stderr
+    rfile = next(json.loads(x)["restart"] for x in r.stdout.strip().splitlines() if "restart" in x)
+    r = run(casefiles.write_case(d, net, params, opts, ro[6:], case_name="second", start=start, first_step=6, fname_state_in=os.path.basename(rfile)))
+    assert r.returncode == 0, r.stderr
+    h_second = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    for v in ("IRFroutedRunoff", "KWroutedRunoff"):
+        assert np.array_equal(h_second[v], h_full[v][6:]), v
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_exact_restart_of_the_euler_schemes(tmp_path, backend):
     """q_sub_kw / q_sub_mc / q_sub_dw [mol, seg] and volume_* in the restart file (popMetadat.f90:283-295): 24 steps in one
     run == 12 steps + restart + 12 steps, bit for bit, with <floodplain> T."""

@@ -13,10 +13,24 @@ from tests import emul
 from tests.util import case
 
 
-@pytest.mark.parametrize("option,forcing", [(1, False), (0, False), (2, False), (0, True), (1, True), (2, True)])
-def test_lake_reach_device_source_matches_oracle(option, forcing):
+HYP_ORDER = ["HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim", "HYP_Qrate_amp",
+             "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"]
+
+
+@pytest.mark.parametrize("option,forcing,hype", [(1, False, None), (0, False, None), (2, False, None), (0, True, None), (1, True, None), (2, True, None),
+                                                 (1, False, ("standard", (2000, 2, 25, 0.0))), (2, True, ("noleap", (2001, 12, 28, 43200.0)))])
+def test_lake_reach_device_source_matches_oracle(option, forcing, hype):
     net, params, opts, ro = case("conus", n=700, seed=4, dt=86400.0, route_opt="3", steps=14, lakes=9)
     opts.LakeInputOption = option
+    hyp = None
+    start = (0, 1, 1, 0.0)
+    if hype:                                          # HYPE reservoirs + the simulation calendar (run crosses a leap day / a year end)
+        from mizuroute_b200 import synth
+        assert synth.make_hype_lakes(net, np.random.default_rng(5)) >= 2
+        opts.calendar, opts.sim_start = hype
+        start = opts.sim_start
+        ro = ro * 30.0
+        hyp = np.stack([net.lake_params[k] for k in HYP_ORDER])
     K = ro.shape[0]
     ev = pr = None
     if forcing:
@@ -41,13 +55,17 @@ def test_lake_reach_device_source_matches_oracle(option, forcing):
                            p(arrs[2], C.c_double), p(arrs[3], C.c_double), p(arrs[4], C.c_double), p(arrs[5], C.c_double),
                            C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(option), C.c_double(opts.runoffMin),
                            C.c_double(tc), C.c_double(lc), C.c_int(K), p(qr, C.c_double), p(ev, C.c_double), p(pr, C.c_double),
+                           p(hyp, C.c_double), C.c_int(start[0]), C.c_int(start[1]), C.c_int(start[2]), C.c_double(start[3]), C.c_int(int(opts.calendar == "noleap")),
                            p(qe, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(ee, C.c_double), msg)
     assert ierr == 0, msg.value.decode()
     assert np.array_equal(qe, qo)
     assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, orc.M_KW))
     assert np.array_equal(we, o.get(orc.F_WB, orc.M_KW))
+    if hype:
+        hy = (net.islake == 1) & (net.lakeModelType == 3)
+        assert (qo[:, hy] > 0.0).any()
     if forcing:
         lk = net.islake == 1
         assert np.array_equal(ee[lk], o.lake_forcing()[0][lk])
-        if option != 1:
+        if option != 1 and not hype:
             assert (ve[lk] == 0.0).any()                                     # a lake did run dry

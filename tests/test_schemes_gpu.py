@@ -103,3 +103,36 @@ def test_lake_evaporation_and_precipitation_forcing(option, route):
     r.upload_lake_forcing(ev[:3], pr[:3])
     with pytest.raises(Exception):
         r.route_batch(np.ascontiguousarray(ro[:5]))
+
+
+@pytest.mark.parametrize("calendar,start,route", [("standard", (2000, 2, 25, 0.0), "13"), ("noleap", (2001, 12, 28, 43200.0), "1")])
+def test_hype_reservoirs(calendar, start, route):
+    """lakeModelType 3 (HYPE): mr_set_lake_param + mr_set_sim_start; seasonal primary spillway by day of year (the runs cross
+    a leap day / a year end), emergency spillway, both combination modes.  sin() and pow() on the device differ from libm in
+    the last ulp: IRF is held to 1e-6 here, the kinematic wave to 1e-4."""
+    from mizuroute_b200 import capi, synth
+    from oracle import oracle as orc
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0, route_opt=route, steps=14, lakes=10)
+    assert synth.make_hype_lakes(net, np.random.default_rng(5), frac=0.7) >= 2
+    opts.sim_start, opts.calendar = start, calendar
+    ro = ro * 30.0
+    o, r, qo, qg = _both(net, params, opts, ro, 5)
+    for i, c in enumerate(route):
+        tol = 1e-6 if c == "1" else EULER_RTOL
+        assert rel_err(qg[i], qo[i], floor=1e-6) <= tol, c
+        assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1.0) <= tol
+    hy = (net.islake == 1) & (net.lakeModelType == 3)
+    assert (qo[0][:, hy] > 0.0).any()
+
+
+def test_hype_without_calendar_or_parameters_is_an_error():
+    from mizuroute_b200 import synth
+    from mizuroute_b200.route import Router, RoutingError
+    net, params, opts, ro = case("conus", n=300, seed=4, dt=86400.0, route_opt="1", steps=2, lakes=6)
+    synth.make_hype_lakes(net, np.random.default_rng(5), frac=0.7)
+    r = Router(net, params, opts, max_batch=2)                  # no sim_start
+    with pytest.raises(RoutingError, match="simulation start"):
+        r.route_batch(ro)
+    net.lake_params.pop("HYP_A_avg")
+    with pytest.raises(RoutingError, match="HYP_A_avg"):
+        Router(net, params, opts, max_batch=2)
