@@ -244,6 +244,34 @@ def make_hype_lakes(net: RiverNetwork, rng: np.random.Generator, frac: float = 0
     return int(pick.size)
 
 
+def make_h06_lakes(net: RiverNetwork, rng: np.random.Generator, frac: float = 0.5, memory: bool = True, mem_years: int = 1) -> int:
+    """Turn a share of the Doll-2003 lakes into Hanasaki-2006 reservoirs (lakeModelType 2, lake_route.f90:231-396):
+    irrigation and non-irrigation purposes, within-a-year and multi-year storage ratios, optional inflow memory."""
+    doll = np.flatnonzero((net.islake == 1) & (net.lakeModelType == 1))
+    pick = doll[rng.random(doll.size) < frac]
+    if pick.size == 0 and doll.size:
+        pick = doll[:1]
+    n = net.nRch
+    net.lakeModelType = net.lakeModelType.copy()
+    net.lakeModelType[pick] = 2
+    base = np.exp(rng.normal(np.log(8.0), 0.8, n))                   # mean inflow m3/s
+    season = 1.0 + 0.5 * np.sin(2.0 * np.pi * (np.arange(12)[:, None] + rng.uniform(0, 12, n)[None, :]) / 12.0)
+    p = dict(net.lake_params)
+    months = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"]
+    for k, mo in enumerate(months):
+        p["H06_I_" + mo] = base * season[k]
+        p["H06_D_" + mo] = base * rng.uniform(0.1, 0.9, n) * season[(k + 5) % 12]
+    ratio = np.where(rng.random(n) < 0.5, rng.uniform(0.05, 0.4, n), rng.uniform(0.6, 2.0, n))      # c below / above c_compare = 0.5
+    p["H06_Smax"] = ratio * base * 365.0 * 86400.0
+    p.update({"H06_alpha": np.full(n, 0.85), "H06_envfact": rng.uniform(0.2, 0.9, n), "H06_S_ini": p["H06_Smax"] * 0.8,
+              "H06_c1": np.full(n, 0.1), "H06_c2": np.full(n, 0.9), "H06_exponent": np.full(n, 2.0), "H06_denominator": np.full(n, 0.5),
+              "H06_c_compare": np.full(n, 0.5), "H06_frac_Sdead": np.full(n, 0.1), "H06_E_rel_ini": rng.uniform(0.6, 1.1, n),
+              "H06_purpose": (rng.random(n) < 0.5).astype(np.float64), "H06_I_mem_F": np.full(n, 1.0 if memory else 0.0),
+              "H06_D_mem_F": np.zeros(n), "H06_I_mem_L": np.full(n, float(mem_years)), "H06_D_mem_L": np.full(n, float(mem_years))})
+    net.lake_params = p
+    return int(pick.size)
+
+
 def runoff_series(net: RiverNetwork, n_steps: int, seed: int = 11, dt: float = 86400.0,
                   mean_mm_s: float = 2.0e-5, sigma: float = 1.0) -> np.ndarray:
     """Strictly positive runoff depth [n_steps, nHRU] in mm/s: per-HRU lognormal level x

@@ -112,6 +112,9 @@ typedef struct {
     /* parametric lake models beyond Doll-2003: per-reach parameters by name (dataTypes.f90:202-254) and the simulation
        start datetime (simDatetime(1) of step 1) the HYPE / Hanasaki formulations read the calendar from */
     double *LP[64];
+    /* Hanasaki-2006 inflow memory QPASTUP_IRF(12, past_length) of every lake reach (shared by the routing methods, as the
+       monthly means H06_I_* and H06_E_rel_ini it feeds are: they live in RPARAM / RCHFLX, not in ROUTE(:)) */
+    double **h06Mem; int *h06Len;
     int hasStart, startYear, startMonth, startDay, noleap; double startSec;
     long iTime;                    /* globalData iTime, 1 on the first step */
     int nThreads;
@@ -314,9 +317,19 @@ static void down_index(int nUp, int nSeg, const int *segId, const int *downId, i
 void mro_destroy(mro_t *h);
 void mro_set_channel(mro_t *h, int floodplain, double dscale, double floodplainSlope);
 static const char *LP_NAMES[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
-                                 "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode", NULL};
+                                 "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode",
+                                 "H06_Smax", "H06_alpha", "H06_envfact", "H06_S_ini", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
+                                 "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini",
+                                 "H06_I_Jan", "H06_I_Feb", "H06_I_Mar", "H06_I_Apr", "H06_I_May", "H06_I_Jun", "H06_I_Jul", "H06_I_Aug", "H06_I_Sep",
+                                 "H06_I_Oct", "H06_I_Nov", "H06_I_Dec",
+                                 "H06_D_Jan", "H06_D_Feb", "H06_D_Mar", "H06_D_Apr", "H06_D_May", "H06_D_Jun", "H06_D_Jul", "H06_D_Aug", "H06_D_Sep",
+                                 "H06_D_Oct", "H06_D_Nov", "H06_D_Dec",
+                                 "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L", NULL};
 enum { LP_HYP_E_emr, LP_HYP_E_lim, LP_HYP_E_min, LP_HYP_E_zero, LP_HYP_Qrate_emr, LP_HYP_Erate_emr, LP_HYP_Qrate_prim,
-       LP_HYP_Qrate_amp, LP_HYP_Qrate_phs, LP_HYP_prim_F, LP_HYP_A_avg, LP_HYP_Qsim_mode, LP_COUNT };
+       LP_HYP_Qrate_amp, LP_HYP_Qrate_phs, LP_HYP_prim_F, LP_HYP_A_avg, LP_HYP_Qsim_mode, LP_COUNT,
+       LP_H06_Smax = LP_COUNT, LP_H06_alpha, LP_H06_envfact, LP_H06_S_ini, LP_H06_c1, LP_H06_c2, LP_H06_exponent, LP_H06_denominator,
+       LP_H06_c_compare, LP_H06_frac_Sdead, LP_H06_E_rel_ini, LP_H06_I_Jan, LP_H06_D_Jan = LP_H06_I_Jan + 12,
+       LP_H06_purpose = LP_H06_D_Jan + 12, LP_H06_I_mem_F, LP_H06_D_mem_F, LP_H06_I_mem_L, LP_H06_D_mem_L, LP_END };
 
 /* ------------------------------------------------------------------------------------------ */
 /* create: read_streamSeg.f90 inputs -> augment_ntopo (process_ntopo.f90:39-266) -> put_data_struct */
@@ -492,6 +505,7 @@ void mro_destroy(mro_t *h)
     for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
                                      free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); }
     { int k; for (k = 0; k < 64; k++) free(h->LP[k]); }
+    if (h->h06Mem) { int k; for (k = 0; k < h->nRch; k++) free(h->h06Mem[k]); free(h->h06Mem); free(h->h06Len); }
     free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
     free(h->QFUTURE_IRF); free(h->KW);
     free(h);
@@ -960,6 +974,9 @@ static int lake_route(mro_t *h, int j, int M)
         switch (h->lakeModelType[j]) {
             case LAKE_ENDORHEIC: *V1 = h->D03_S0[j]; break;
             case LAKE_DOLL03:    *V1 = h->D03_MaxStorage[j]; break;
+            case LAKE_H06:
+                if (!h->LP[LP_H06_Smax]) { snprintf(h->message, 256, "lake_route/Hanasaki parameters are not set"); return 20; }
+                *V1 = h->LP[LP_H06_Smax][j]; break;
             case LAKE_HYPE:
                 if (!h->LP[LP_HYP_E_emr] || !h->LP[LP_HYP_E_zero] || !h->LP[LP_HYP_A_avg]) { snprintf(h->message, 256, "lake_route/HYPE parameters are not set"); return 20; }
                 *V1 = (h->LP[LP_HYP_E_emr][j] - h->LP[LP_HYP_E_zero][j]) * h->LP[LP_HYP_A_avg][j]; break;
@@ -986,6 +1003,58 @@ static int lake_route(mro_t *h, int j, int M)
             *Q = fmin(*Q, *V1 / dt);
             *V1 = *V1 - *Q * dt;
             break;
+        case LAKE_H06: {           /* lake_route.f90:231-396 (no water-management demand: is_flux_wm = F) */
+            int k, i, month, day, doy, start_month = 0;
+            double I_months[12], D_months[12], I_yearly, D_yearly, c, target_r, sI = 0.0, sD = 0.0, ratio;
+            double **P = h->LP;
+            for (k = LP_H06_Smax; k < LP_END; k++) if (!P[k]) { snprintf(h->message, 256, "lake_route/Hanasaki parameter %s is not set", LP_NAMES[k]); return 20; }
+            if (!step_calendar(h, &month, &day, &doy)) { snprintf(h->message, 256, "lake_route/Hanasaki needs the simulation start datetime"); return 20; }
+            if (P[LP_H06_I_mem_F][j] != 0.0) {      /* memory of the upstream inflow, one row per month */
+                static const int ndays31[7] = {0, 2, 4, 6, 7, 9, 11}, ndays30[3] = {3, 5, 8};
+                const double memL = (double)(int)P[LP_H06_I_mem_L][j];
+                int L31 = (int)floor(memL * 31 * SECPRDAY / dt), L30 = (int)floor(memL * 30 * SECPRDAY / dt), LF, L, m2;
+                double *mem;
+                if (!h->h06Mem) { h->h06Mem = (double **)calloc((size_t)h->nRch, sizeof(double *)); h->h06Len = (int *)calloc((size_t)h->nRch, sizeof(int)); }
+                if (!h->h06Mem[j]) {                /* first call: filled with the monthly parameters, nothing inserted */
+                    h->h06Len[j] = L31;
+                    h->h06Mem[j] = (double *)malloc(sizeof(double) * 12 * (size_t)(L31 > 0 ? L31 : 1));
+                    for (k = 0; k < 12; k++) for (i = 0; i < L31; i++) h->h06Mem[j][(size_t)k * L31 + i] = P[LP_H06_I_Jan + k][j];
+                } else {                            /* shift the current month's row and insert the inflow of this call */
+                    L = h->h06Len[j]; mem = h->h06Mem[j] + (size_t)(month - 1) * L;
+                    for (i = L - 1; i >= 1; i--) mem[i] = mem[i - 1];
+                    mem[0] = q_upstream;
+                }
+                L = h->h06Len[j];
+                for (k = 0; k < 7; k++) { m2 = ndays31[k]; mem = h->h06Mem[j] + (size_t)m2 * L; sI = 0.0; for (i = 0; i < L31; i++) sI += mem[i]; P[LP_H06_I_Jan + m2][j] = sI / L31; }
+                for (k = 0; k < 3; k++) { m2 = ndays30[k]; mem = h->h06Mem[j] + (size_t)m2 * L; sI = 0.0; for (i = 0; i < L30; i++) sI += mem[i]; P[LP_H06_I_Jan + m2][j] = sI / L30; }
+                /* November is not updated by the reference (lake_route.f90:258-272) */
+                LF = h->noleap ? (int)floor(memL * 28 * SECPRDAY / dt) : (int)floor(memL * 28.25 * SECPRDAY / dt);
+                mem = h->h06Mem[j] + (size_t)1 * L; sI = 0.0; for (i = 0; i < LF; i++) sI += mem[i]; P[LP_H06_I_Jan + 1][j] = sI / LF;
+            }
+            sI = 0.0; sD = 0.0;
+            for (k = 0; k < 12; k++) { I_months[k] = P[LP_H06_I_Jan + k][j]; D_months[k] = P[LP_H06_D_Jan + k][j]; sI += I_months[k]; sD += D_months[k]; }
+            I_yearly = sI / 12; D_yearly = sD / 12;
+            c = P[LP_H06_Smax][j] / (I_yearly * 365 * SECPRDAY);
+            for (i = 1; i <= 12; i++) if (I_yearly <= I_months[i - 1]) start_month = i + 1;
+            if (month == start_month && day == 1) P[LP_H06_E_rel_ini][j] = *V1 / (P[LP_H06_alpha][j] * P[LP_H06_Smax][j]);
+            if ((int)P[LP_H06_purpose][j] == 1) {
+                if (P[LP_H06_envfact][j] * I_yearly <= D_yearly)
+                    target_r = I_months[month - 1] * P[LP_H06_c1][j] + I_yearly * P[LP_H06_c2][j] * (D_months[month - 1] / D_yearly);
+                else target_r = I_yearly + D_months[month - 1] - D_yearly;
+            } else target_r = I_yearly;
+            if (c >= P[LP_H06_c_compare][j]) *Q = target_r * P[LP_H06_E_rel_ini][j];
+            else if (0 <= c && c < P[LP_H06_c_compare][j]) {
+                ratio = pow(c / P[LP_H06_denominator][j], P[LP_H06_exponent][j]);
+                *Q = P[LP_H06_E_rel_ini][j] * target_r * ratio + q_upstream * (1 - pow(c / P[LP_H06_denominator][j], P[LP_H06_exponent][j]));
+            }                                       /* else (c < 0 or NaN): REACH_Q keeps its previous value */
+            if (*V1 < (P[LP_H06_Smax][j] * P[LP_H06_frac_Sdead][j])) {
+                *Q = *Q - (P[LP_H06_Smax][j] * P[LP_H06_frac_Sdead][j] - *V1) / dt;
+                if (*Q < 0) *Q = 0;
+            } else if (*V1 > P[LP_H06_Smax][j]) {
+                *Q = *Q + (*V1 - P[LP_H06_Smax][j]) / dt;
+            }
+            *V1 = *V1 - *Q * dt;
+            break; }
         case LAKE_HYPE: {          /* lake_route.f90:398-438 */
             int k, month, day, doy;
             double ELE, F_sin, F_lin, Q_prim, Q_spill, Q_sim; int F_prim;

@@ -615,6 +615,86 @@ class Twin:
         self.T1 = self.T0 + float(o.dt)
         self.itime += 1
 
+    MONTHS = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"]
+
+    def _h06(self, j, m, v, qup):
+        """Release of a Hanasaki-2006 reservoir holding volume v.  The monthly mean inflows H06_I_*, the release coefficient
+        H06_E_rel_ini and the inflow memory are per REACH (RPARAM / RCHFLX), i.e. shared by the routing methods."""
+        P, dt = self.net.lake_params, self.o.dt
+        g = lambda name: float(P[name][j])
+        month, day = self._month_day()
+        if g("H06_I_mem_F") != 0.0:
+            years = int(g("H06_I_mem_L"))
+            n31, n30 = int(math.floor(years * 31 * 86400.0 / dt)), int(math.floor(years * 30 * 86400.0 / dt))
+            nfeb = int(math.floor(years * (28 if self.o.calendar == "noleap" else 28.25) * 86400.0 / dt))
+            if not hasattr(self, "h06_mem"):
+                self.h06_mem = {}
+            if j not in self.h06_mem:
+                self.h06_mem[j] = [[g("H06_I_" + mo)] * n31 for mo in self.MONTHS]
+            else:
+                row = self.h06_mem[j][month - 1]
+                row.insert(0, qup)
+                row.pop()
+            for k, mo in enumerate(self.MONTHS):
+                if mo == "Nov":
+                    continue                      # not updated by the reference
+                n = nfeb if mo == "Feb" else (n30 if mo in ("Apr", "Jun", "Sep") else n31)
+                tot = 0.0
+                for x in self.h06_mem[j][k][:n]:
+                    tot += x
+                P["H06_I_" + mo][j] = tot / n
+        inflow = [g("H06_I_" + mo) for mo in self.MONTHS]
+        demand = [g("H06_D_" + mo) for mo in self.MONTHS]
+        tot_i = tot_d = 0.0
+        for x in inflow:
+            tot_i += x
+        for x in demand:
+            tot_d += x
+        i_year, d_year = tot_i / 12, tot_d / 12
+        c = g("H06_Smax") / (i_year * 365 * 86400.0)
+        start_month = 0
+        for i in range(12):
+            if i_year <= inflow[i]:
+                start_month = i + 2
+        if month == start_month and day == 1:
+            P["H06_E_rel_ini"][j] = v / (g("H06_alpha") * g("H06_Smax"))
+        if int(g("H06_purpose")) == 1:
+            if g("H06_envfact") * i_year <= d_year:
+                target = inflow[month - 1] * g("H06_c1") + i_year * g("H06_c2") * (demand[month - 1] / d_year)
+            else:
+                target = i_year + demand[month - 1] - d_year
+        else:
+            target = i_year
+        q = self.Q[m][j]
+        if c >= g("H06_c_compare"):
+            q = target * g("H06_E_rel_ini")
+        elif 0 <= c < g("H06_c_compare"):
+            r = (c / g("H06_denominator")) ** g("H06_exponent")
+            q = g("H06_E_rel_ini") * target * r + qup * (1 - r)
+        dead = g("H06_Smax") * g("H06_frac_Sdead")
+        if v < dead:
+            q = max(q - (dead - v) / dt, 0.0)
+        elif v > g("H06_Smax"):
+            q = q + (v - g("H06_Smax")) / dt
+        return q
+
+    def _month_day(self):
+        import datetime as _dt
+        if not getattr(self.o, "sim_start", None):
+            raise RouteError(20, "the lake model needs the simulation start datetime")
+        y, mo, d, sec = self.o.sim_start
+        days = int(math.floor((sec + (self.itime - 1) * float(self.o.dt) + 1e-6) / 86400.0))
+        if self.o.calendar == "noleap":
+            ml = [31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+            doy = (sum(ml[:mo - 1]) + (d - 1) + days) % 365
+            k = 0
+            while doy >= ml[k]:
+                doy -= ml[k]
+                k += 1
+            return k + 1, doy + 1
+        now = _dt.datetime(y, mo, d) + _dt.timedelta(days=days)
+        return now.month, now.day
+
     def _day_of_year(self):
         """dayofyear of simDatetime(1) (datetime_data.f90:209-218), via Python's calendar for the standard calendar."""
         import datetime as _dt
@@ -803,6 +883,8 @@ class Twin:
                 self.V1[m][j] = float(net.D03_S0[j])
             elif lt == 1:
                 self.V1[m][j] = float(net.D03_MaxStorage[j])
+            elif lt == 2:
+                self.V1[m][j] = lp("H06_Smax")
             elif lt == 3:
                 self.V1[m][j] = (lp("HYP_E_emr") - lp("HYP_E_zero")) * lp("HYP_A_avg")
             else:
@@ -831,6 +913,9 @@ class Twin:
                 q = 0.0
             q = q / 86400.0
             q = min(q, v / dt)
+            v = v - q * dt
+        elif lt == 2:                   # Hanasaki 2006, lake_route.f90:231-396 (without water-management demand)
+            q = self._h06(j, m, v, qup)
             v = v - q * dt
         elif lt == 3:                   # HYPE, lake_route.f90:398-438
             ele = v / lp("HYP_A_avg") + lp("HYP_E_zero")

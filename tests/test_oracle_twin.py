@@ -155,3 +155,35 @@ def test_hype_reservoirs(calendar, start):
     opts.sim_start = None
     with pytest.raises(orc.OracleError):
         orc.Oracle(net, params, opts).run(ro[:1])
+
+
+@pytest.mark.parametrize("memory,calendar,start,dt,steps", [(False, "standard", (2000, 5, 20, 0.0), 86400.0, 30),
+                                                            (True, "standard", (2000, 2, 20, 0.0), 86400.0, 24),
+                                                            (True, "noleap", (2001, 12, 25, 0.0), 43200.0, 30)])
+def test_hanasaki_reservoirs(memory, calendar, start, dt, steps):
+    """lakeModelType 2 (Hanasaki 2006, lake_route.f90:231-396): irrigation / non-irrigation target release, within-a-year and
+    multi-year reservoirs, the release coefficient reset on the first day of the operational year, dead storage and spill;
+    with the inflow memory (one row per month, shifted by EVERY routing method's call because it is per reach) the monthly
+    means -- and so the parameters -- change as the run goes.  Two methods, so that sharing is exercised."""
+    from mizuroute_b200 import synth
+    net, params, opts, ro = case("conus", n=500, seed=4, dt=dt, route_opt="13", steps=steps, lakes=10)
+    n_h06 = synth.make_h06_lakes(net, np.random.default_rng(6), frac=0.7, memory=memory)
+    assert n_h06 >= 2
+    opts.sim_start, opts.calendar = start, calendar
+    ro = ro * 20.0
+    import copy
+    net_t = copy.deepcopy(net)                               # both restatements update the monthly inflow parameters in place
+    o = orc.Oracle(net, params, opts)
+    t = Twin(net_t, params, opts)
+    h06 = np.flatnonzero((net.islake == 1) & (net.lakeModelType == 2))
+    q_seen = []
+    for k in range(steps):
+        o.step(ro[k]); t.step(ro[k])
+        for m in t.methods:
+            assert rel_err(o.get(orc.F_REACH_Q, m), np.array(t.Q[m])) <= 1e-12, (k, m)
+            assert rel_err(o.get(orc.F_REACH_VOL1, m), np.array(t.V1[m]), floor=1e-6) <= 1e-12
+        q_seen.append(o.get(orc.F_REACH_Q, orc.M_IRF)[h06])
+    assert np.isfinite(np.array(q_seen)).all() and (np.array(q_seen) > 0.0).any()
+    month0 = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"][start[1] - 1]
+    moved = not np.array_equal(net_t.lake_params["H06_I_" + month0][h06], net.lake_params["H06_I_" + month0][h06])
+    assert moved == memory                                   # the memory feeds back into the monthly inflow parameters
