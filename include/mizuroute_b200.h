@@ -48,7 +48,7 @@ enum {
 };
 
 /* lake model types, public_var.f90 / lake_route.f90:196-438 */
-enum { MR_LAKE_ENDORHEIC = 0, MR_LAKE_DOLL03 = 1, MR_LAKE_HANASAKI06 = 2 /* not implemented */, MR_LAKE_HYPE = 3 };
+enum { MR_LAKE_ENDORHEIC = 0, MR_LAKE_DOLL03 = 1, MR_LAKE_HANASAKI06 = 2, MR_LAKE_HYPE = 3 };
 
 /* state variables in the reference's restart schema (write_restart_pio.f90:544,1039-1134; read_restart.f90:402-470) */
 enum {
@@ -149,8 +149,11 @@ int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
 int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message);
 /* Per-reach parameters of the parametric lake models beyond Doll-2003, by their name in RCHPRP (dataTypes.f90:202-213):
  * HYP_E_emr, HYP_E_lim, HYP_E_min, HYP_E_zero, HYP_Qrate_emr, HYP_Erate_emr, HYP_Qrate_prim, HYP_Qrate_amp, HYP_Qrate_phs,
- * HYP_prim_F, HYP_A_avg, HYP_Qsim_mode (integers and logicals as 0/1 doubles); values[n = nRch] in the caller's reach order.
- * Call BEFORE mr_set_network (like mr_set_ghosts).  lakeModelType 3 (HYPE) needs all twelve. */
+ * HYP_prim_F, HYP_A_avg, HYP_Qsim_mode, and (dataTypes.f90:215-254) H06_Smax, H06_alpha, H06_envfact, H06_S_ini, H06_c1, H06_c2,
+ * H06_exponent, H06_denominator, H06_c_compare, H06_frac_Sdead, H06_E_rel_ini, H06_I_Jan..H06_I_Dec, H06_D_Jan..H06_D_Dec,
+ * H06_purpose, H06_I_mem_F, H06_D_mem_F, H06_I_mem_L, H06_D_mem_L (integers and logicals as doubles); values[n = nRch] in the
+ * caller's reach order.  Call BEFORE mr_set_network (like mr_set_ghosts).  lakeModelType 3 (HYPE) needs all HYP_*, lakeModelType
+ * 2 (Hanasaki 2006) all H06_* (the demand memory H06_D_mem_* belongs to water management and is not used). */
 int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message);
 /* Datetime of the first simulation step (simDatetime(1) at iTime = 1, init_model_data.f90) and the calendar (0 standard /
  * gregorian / proleptic_gregorian, 1 noleap): HYPE's seasonal spillway reads the day of year (lake_route.f90:404). */

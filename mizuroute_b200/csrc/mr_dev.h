@@ -23,6 +23,16 @@ enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
 // HYPE reservoir parameters of one lake (dataTypes.f90:202-213; integers / logicals as 0/1 doubles), in this order
 struct HypeParams { double E_emr, E_lim, E_min, E_zero, Qrate_emr, Erate_emr, Qrate_prim, Qrate_amp, Qrate_phs, prim_F, A_avg, Qsim_mode; };
 constexpr int HYP_COUNT = 12;
+// Hanasaki-2006 reservoir of one lake (dataTypes.f90:215-254): parameters, the monthly mean inflows / release coefficient the
+// model itself rewrites, and its inflow memory QPASTUP_IRF(12, L31) kept as one ring per month (newest value at `head`).
+// All of it is per REACH in the reference (RPARAM / RCHFLX), i.e. shared by the routing methods of a step.
+struct H06Lake {
+    double Smax, alpha, envfact, c1, c2, exponent, denominator, c_compare, frac_Sdead, E_rel_ini;
+    double I[12], D[12];
+    int purpose, memF, L31, L30, LF, LFnoleap, filled;      // LF / LFnoleap: February row length in the standard / noleap calendar
+    int head[12];
+    long long memOff;              // offset of this lake's [12][L31] block in DevNet::h06Mem
+};
 enum { M_SUM = 0, M_IRF = 1, M_KWT = 2, M_KW = 3, M_MC = 4, M_DW = 5, N_METHODS = 6 };   // = digits of <route_opt>, public_var.f90:74-80
 // computational molecules of the Euler schemes (init_model_data.f90:386-393): KW 20, MC 2, DW 20 nodes per reach
 constexpr int n_molecule(int m) { return m == M_KW || m == M_DW ? 20 : (m == M_MC ? 2 : 0); }
@@ -46,6 +56,11 @@ struct DevNet {
     // HYPE reservoirs (lakeModelType 3): parameters by lake slot [nLake] and the day of year of every step of the batch [kmax]
     // (nullptr = no simulation start datetime was given)
     const struct HypeParams *hyp;
+    struct H06Lake *h06;            // Hanasaki-2006 reservoirs by lake slot (nullptr = none in this domain)
+    double *h06Mem;
+    const int *stepMonth, *stepDay; // month / day of month of every step of the batch [kmax], with stepDoy
+    int noleap;                     // calendar given with mr_set_sim_start
+    int lastK;                      // steps of the previous batch (its last REACH_Q row is still in qSer)
     const int *stepDoy;
     const double *evapo, *precip;
     double *lakeEvap, *lakePrecip;

@@ -57,8 +57,63 @@ MR_DEV_NOINLINE double hype_outflow(const HypeParams *hp, int doy, double v1, do
     return fmin(Q_sim, fmax(0.0, (ELE - h.E_min) * h.A_avg) / dt);
 }
 
-// HY: the domain holds HYPE reservoirs.  The kernels are instantiated for both values and the launch picks one, so that a
-// domain without them runs exactly the code it ran before HYPE existed (no extra registers, stack or spills).
+// Hanasaki-2006 release (lake_route.f90:231-396, no water-management demand) of the lake L holding volume v1; updates the
+// lake's inflow memory, monthly mean inflows and release coefficient as the reference updates RCHFLX / RPARAM.  `prevQ` is
+// REACH_Q of the previous step (kept when the storage ratio c is negative).  Out of line, pointer arguments only.
+MR_DEV_NOINLINE double h06_release(H06Lake *Lk, double *memAll, int month, int day, int noleap, double v1, double qup, double prevQ, double dt) {
+    H06Lake &L = *Lk;
+    if (L.memF) {
+        double *mem = memAll + L.memOff;
+        if (!L.filled) {                              // first call: every row holds the monthly parameter, nothing is inserted
+            for (int k = 0; k < 12; ++k) { for (int i = 0; i < L.L31; ++i) mem[(size_t)k * L.L31 + i] = L.I[k]; L.head[k] = 0; }
+        } else {                                      // shift the month's row by one and insert the inflow: the ring steps back
+            const int k = month - 1;
+            int hd = L.head[k] - 1; if (hd < 0) hd += L.L31;
+            mem[(size_t)k * L.L31 + hd] = qup;
+            L.head[k] = hd;
+        }
+        // means, newest value first (sum(QPASTUP(m, 1:n))/n).  Rows other than the month's did not change since their mean
+        // was last taken, so only that one is recomputed -- all of them on the first call.  November is never updated.
+        for (int k = 0; k < 12; ++k) {
+            if (k == 10 || (L.filled && k != month - 1)) continue;
+            const int n = k == 1 ? (noleap ? L.LFnoleap : L.LF) : ((k == 3 || k == 5 || k == 8) ? L.L30 : L.L31);
+            const double *row = mem + (size_t)k * L.L31;
+            double sum = 0.0;
+            int idx = L.head[k];
+            for (int i = 0; i < n; ++i) { sum += row[idx]; if (++idx == L.L31) idx = 0; }
+            L.I[k] = sum / n;
+        }
+        L.filled = 1;
+    }
+    double sI = 0.0, sD = 0.0;
+    for (int k = 0; k < 12; ++k) { sI += L.I[k]; sD += L.D[k]; }
+    const double I_yearly = sI / 12, D_yearly = sD / 12;
+    const double c = L.Smax / (I_yearly * 365 * 86400.0);
+    int start_month = 0;
+    for (int i = 1; i <= 12; ++i) if (I_yearly <= L.I[i - 1]) start_month = i + 1;
+    if (month == start_month && day == 1) L.E_rel_ini = v1 / (L.alpha * L.Smax);
+    double target_r;
+    if (L.purpose == 1) {
+        if (L.envfact * I_yearly <= D_yearly) target_r = L.I[month - 1] * L.c1 + I_yearly * L.c2 * (L.D[month - 1] / D_yearly);
+        else target_r = I_yearly + L.D[month - 1] - D_yearly;
+    } else target_r = I_yearly;
+    double q = prevQ;
+    if (c >= L.c_compare) q = target_r * L.E_rel_ini;
+    else if (0 <= c && c < L.c_compare) {
+        const double ratio = pow(c / L.denominator, L.exponent);
+        q = L.E_rel_ini * target_r * ratio + qup * (1 - ratio);
+    }
+    if (v1 < (L.Smax * L.frac_Sdead)) {
+        q = q - (L.Smax * L.frac_Sdead - v1) / dt;
+        if (q < 0) q = 0;
+    } else if (v1 > L.Smax) {
+        q = q + (v1 - L.Smax) / dt;
+    }
+    return q;
+}
+
+// HY: the domain holds HYPE or Hanasaki reservoirs.  The kernels are instantiated for both values and the launch picks one,
+// so that a domain without them runs exactly the code it ran before those models existed (no extra registers, stack or spills).
 template <int M, bool HY = false>
 MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
@@ -72,6 +127,10 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     if (tau == 0) {                                    // iTime==1 cold start, lake_route.f90:139-157
         if (type == MR_LAKE_ENDORHEIC) v1 = d.d03S0[p];
         else if (type == MR_LAKE_DOLL03) v1 = d.d03MaxS[p];
+        else if (HY && type == MR_LAKE_HANASAKI06) {
+            if (!d.h06) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
+            v1 = d.h06[d.lakeSlot[p]].Smax;
+        }
         else if (HY && type == MR_LAKE_HYPE) {
             if (!d.hyp) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
             const HypeParams &hp = d.hyp[d.lakeSlot[p]];
@@ -106,6 +165,14 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
         q = q / 86400.0;
         q = fmin(q, v1 / dt);
         v1 = v1 - q * dt;
+    } else if (HY && type == MR_LAKE_HANASAKI06) {
+        if constexpr (HY) {
+            if (!d.h06) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
+            if (!d.stepMonth) { raise(d.err, 20, p, E_NO_CALENDAR); return; }
+            const double prevQ = t > 0 ? Qs[p - (size_t)N] : (d.lastK > 0 ? d.qSer[M][(size_t)(d.lastK - 1) * N + p] : 0.0);   // REACH_Q of the previous step
+            q = h06_release(d.h06 + d.lakeSlot[p], d.h06Mem, d.stepMonth[t], d.stepDay[t], d.noleap, v1, qup, prevQ, dt);
+            v1 = v1 - q * dt;
+        } else q = 0.0;
     } else if (HY && type == MR_LAKE_HYPE) {
         if constexpr (HY) {
             if (!d.hyp) { raise(d.err, 20, p, E_LAKE_PARAM); return; }

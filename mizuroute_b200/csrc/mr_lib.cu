@@ -63,8 +63,8 @@ struct mr_handle_s {
     // parametric lake models beyond Doll-2003: named per-reach parameters (caller order, consumed by mr_set_network) and the
     // simulation start datetime (mr_set_sim_start) from which the day of year of every step follows
     std::map<std::string, std::vector<double>> lakeParams;
-    bool hasStart = false, hasHype = false; int startY = 0, startM = 1, startD = 1, noleap = 0; double startSec = 0.0;
-    int *dStepDoy = nullptr; std::vector<int> stepDoyHost;
+    bool hasStart = false, hasHype = false, hasH06 = false; int startY = 0, startM = 1, startD = 1, noleap = 0; double startSec = 0.0;
+    int *dStepDoy = nullptr; std::vector<int> stepDoyHost;      // [3][max_batch]: day of year, month, day of month
     // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
     int nLake = 0, lakeForcingSteps = 0;
     int *dLakePos = nullptr;
@@ -173,10 +173,10 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     if constexpr (M == M_KWT) {
         int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        if (h->hasHype) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
     } else {
-        if (h->hasHype) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
     h->launchesLast++;
@@ -206,12 +206,16 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         h->lakeForcingSteps = 0;
         return fail(message, 1, std::string(where) + "/lake forcing was uploaded for a different number of steps");
     }
-    d.stepDoy = nullptr;
-    if (h->hasHype && h->hasStart) {                    // day of year of simDatetime(1) of every step of the batch
-        h->stepDoyHost.resize(K);
-        for (int t = 0; t < K; ++t) { int mo, dy; step_calendar(h->startY, h->startM, h->startD, h->startSec, h->noleap != 0, h->opt.dt, h->stepsDone + t, mo, dy, h->stepDoyHost[t]); }
-        CU(cudaMemcpyAsync(h->dStepDoy, h->stepDoyHost.data(), sizeof(int) * K, cudaMemcpyHostToDevice, h->stream));
-        d.stepDoy = h->dStepDoy;
+    d.stepDoy = d.stepMonth = d.stepDay = nullptr;
+    d.lastK = h->lastK; d.noleap = h->noleap;
+    if ((h->hasHype || h->hasH06) && h->hasStart) {     // calendar of simDatetime(1) of every step of the batch
+        const int KB = h->opt.max_batch;
+        h->stepDoyHost.assign((size_t)3 * KB, 0);
+        for (int t = 0; t < K; ++t)
+            step_calendar(h->startY, h->startM, h->startD, h->startSec, h->noleap != 0, h->opt.dt, h->stepsDone + t,
+                          h->stepDoyHost[(size_t)KB + t], h->stepDoyHost[(size_t)2 * KB + t], h->stepDoyHost[t]);
+        CU(cudaMemcpyAsync(h->dStepDoy, h->stepDoyHost.data(), sizeof(int) * 3 * KB, cudaMemcpyHostToDevice, h->stream));
+        d.stepDoy = h->dStepDoy; d.stepMonth = h->dStepDoy + KB; d.stepDay = h->dStepDoy + 2 * KB;
     }
     CU(cudaEventRecord(h->ev[1], h->stream));
     k_times<<<1, 1, 0, h->stream>>>(T0, h->opt.dt, K, h->dT0s, h->dT1s);
@@ -242,16 +246,19 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     // handle's stream, the others on auxiliary streams forked after k_basin and joined before the export.
     // Exception: lake_route may cut the evaporation of a lake that runs dry, and the methods routed after it in the same
     // step see the cut value (RCHFLX%basinevapo is shared, lake_route.f90:169-172) -- with lake forcing and LakeInputOption
-    // 0 / 2 the methods therefore run one after the other, in route_opt order.
+    // 0 / 2 the methods therefore share one stream, in route_opt order within every wavefront.
     const int hb = (d.nHead + 255) / 256, nr = h->opt.n_routes;
-    const bool serialMethods = lakeForcing && nr > 1 && (h->opt.LakeInputOption == 0 || h->opt.LakeInputOption == 2);
+    // The same holds for Hanasaki reservoirs, whose inflow memory, monthly means and release coefficient are per reach.  On
+    // one stream, wavefront by wavefront and method by method, every lake sees (step t, method 1), (step t, method 2),
+    // (step t+1, method 1), ... -- the reference's order.
+    const bool serialMethods = nr > 1 && (h->hasH06 || (lakeForcing && (h->opt.LakeInputOption == 0 || h->opt.LakeInputOption == 2)));
     cudaStream_t st[N_METHODS];
     for (int r = 0; r < nr; ++r) {
         st[r] = (serialMethods || r == nr - 1) ? h->stream : h->aux[r];
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
-            const bool hy = h->hasHype;             // HYPE reservoirs in this domain: the instantiation that knows them
+            const bool hy = h->hasHype || h->hasH06;  // HYPE / Hanasaki reservoirs in this domain: the instantiation that knows them
             switch (h->opt.route_methods[r]) {
                 case M_SUM: if (hy) k_headwater<M_SUM, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_SUM, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_IRF: if (hy) k_headwater<M_IRF, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_IRF, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
@@ -263,9 +270,8 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
             h->launchesLast++;
         }
     }
-    for (int pass = 0; pass < (serialMethods ? nr : 1); ++pass)
     for (int w = 0; w < h->topo.nStage + K - 1; ++w)
-        for (int r = serialMethods ? pass : 0; r < (serialMethods ? pass + 1 : nr); ++r)
+        for (int r = 0; r < nr; ++r)
             switch (h->opt.route_methods[r]) {
                 case M_SUM: launch_wavefront<M_SUM>(h, st[r], w, K, h->stepsDone); break;
                 case M_IRF: launch_wavefront<M_IRF>(h, st[r], w, K, h->stepsDone); break;
@@ -386,7 +392,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->nForcing = h->nMap = 0; h->dRunoffNet = nullptr; h->dOvW = nullptr; h->dMapNet = h->dMapPtr = h->dOvIdx = nullptr;
     h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
-    h->dStepDoy = nullptr; h->hasHype = false;
+    h->dStepDoy = nullptr; h->hasHype = false; h->hasH06 = false;
     h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -526,8 +532,47 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
                 for (int sIdx = 0; sIdx < h->nLake; ++sIdx) reinterpret_cast<double *>(&bySlot[sIdx])[k] = it->second[T.pos2rch[pos[sIdx]]];
             }
             UP(hyp, bySlot);
-            AL(h->dStepDoy, KB);
         }
+        h->hasH06 = false;
+        for (int p : pos) if (ltype[p] == MR_LAKE_HANASAKI06) h->hasH06 = true;
+        if (h->hasH06) {                              // H06_* by lake slot (dataTypes.f90:215-254) + the inflow memory
+            auto par = [&](const std::string &nm) -> const std::vector<double> * {
+                auto it = h->lakeParams.find(nm);
+                return (it == h->lakeParams.end() || (int)it->second.size() != nRch) ? nullptr : &it->second; };
+            static const char *mon[12] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
+            static const char *scal[10] = {"H06_Smax", "H06_alpha", "H06_envfact", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
+                                           "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini"};
+            std::vector<H06Lake> lk(h->nLake);
+            long long off = 0;
+            std::string missing;
+            auto val = [&](const std::string &nm, int r, double &out) { const auto *v = par(nm); if (!v) { missing = nm; return; } out = (*v)[r]; };
+            for (int sIdx = 0; sIdx < h->nLake; ++sIdx) {
+                H06Lake &L = lk[sIdx];
+                std::memset(&L, 0, sizeof L);
+                if (ltype[pos[sIdx]] != MR_LAKE_HANASAKI06) continue;
+                if (pos[sIdx] < T.nHead && o.n_routes > 1)
+                    return fail(message, 20, "mr_set_network/a Hanasaki reservoir without upstream reaches cannot be routed with several methods (its state is shared by them)");
+                const int r = T.pos2rch[pos[sIdx]];
+                double *sc = &L.Smax;
+                for (int k = 0; k < 10; ++k) val(scal[k], r, sc[k]);
+                for (int k = 0; k < 12; ++k) { val(std::string("H06_I_") + mon[k], r, L.I[k]); val(std::string("H06_D_") + mon[k], r, L.D[k]); }
+                double purpose = 0, memF = 0, memL = 0;
+                val("H06_purpose", r, purpose); val("H06_I_mem_F", r, memF); val("H06_I_mem_L", r, memL);
+                if (!missing.empty()) return fail(message, 20, "mr_set_network/Hanasaki lakes need the parameter " + missing + " for every reach (mr_set_lake_param)");
+                L.purpose = (int)purpose; L.memF = memF != 0.0 ? 1 : 0;
+                const double yrs = (double)(int)memL;
+                L.L31 = (int)std::floor(yrs * 31 * 86400.0 / o.dt); L.L30 = (int)std::floor(yrs * 30 * 86400.0 / o.dt);
+                L.LF = (int)std::floor(yrs * 28.25 * 86400.0 / o.dt); L.LFnoleap = (int)std::floor(yrs * 28 * 86400.0 / o.dt);
+                if (L.memF && L.LFnoleap < 1) return fail(message, 20, "mr_set_network/H06_I_mem_L must cover at least one step");
+                L.memOff = off;
+                if (L.memF) off += 12LL * L.L31;
+            }
+            H06Lake *dl = nullptr;
+            e = dev_upload(h, &dl, lk, where, message); if (e) return e;
+            d.h06 = dl;
+            AL(d.h06Mem, (size_t)(off > 0 ? off : 1));
+        }
+        if (h->hasHype || h->hasH06) AL(h->dStepDoy, (size_t)3 * KB);
     }
     AL(d.err, 4);
     d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
@@ -583,8 +628,10 @@ int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *messag
 int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message) {
     if (!h || !name || !values || n < 1) return fail(message, 1, "mr_set_lake_param/null argument");
     static const char *known[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
-                                  "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
-    bool ok = false;
+                                  "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode",
+                                  "H06_Smax", "H06_alpha", "H06_envfact", "H06_S_ini", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
+                                  "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini", "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L"};
+    bool ok = !std::strncmp(name, "H06_I_", 6) || !std::strncmp(name, "H06_D_", 6);      // H06_I_Jan .. H06_D_Dec (and the mem_* above)
     for (const char *k : known) ok = ok || !std::strcmp(k, name);
     if (!ok) return fail(message, 20, std::string("mr_set_lake_param/unknown or unsupported lake parameter ") + name);
     h->lakeParams[name].assign(values, values + n);

@@ -617,15 +617,22 @@ int main(int argc, char **argv) {
         char msg[MR_STRLEN];
         mr_handle h = nullptr;
         int ierr = mr_create(&o, &h, msg); if (ierr) die(ierr, msg);
-        if (o.is_lake_sim) {                                  // HYPE reservoirs: HYP_* of the river-network file, and the calendar of the steps
-            static const char *hypNames[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
-                                             "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
-            for (const char *nm : hypNames)
+        if (o.is_lake_sim) {                                  // HYPE / Hanasaki reservoirs: HYP_* and H06_* of the river-network file
+            std::vector<std::string> hypNames = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
+                                                 "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode",
+                                                 "H06_Smax", "H06_alpha", "H06_envfact", "H06_S_ini", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
+                                                 "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini", "H06_purpose", "H06_I_mem_F", "H06_D_mem_F",
+                                                 "H06_I_mem_L", "H06_D_mem_L"};
+            for (const char *mo : {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"}) {
+                hypNames.push_back(std::string("H06_I_") + mo); hypNames.push_back(std::string("H06_D_") + mo); }
+            for (const std::string &nmS : hypNames) {
+                const char *nm = nmS.c_str();
                 if (const nc3::Var *v = nt.find(c.str(std::string("varname_") + nm, nm))) {
                     std::vector<double> vals; nt.read_all(*v, vals);
                     if (vals.size() != nRch) die(20, std::string("read_streamSeg/") + nm + " is not dimensioned by segment");
                     ierr = mr_set_lake_param(h, nm, (int)nRch, vals.data(), msg); if (ierr) die(ierr, msg);
                 }
+            }
         }
         ierr = mr_set_network(h, (int)nRch, (int)nHRU, segId.data(), downSegId.data(), hruSegId.data(), area.data(), length.data(), slope.data(),
                               geomFromFile ? width.data() : nullptr, geomFromFile ? man_n.data() : nullptr, islake.empty() ? nullptr : islake.data(),

@@ -86,3 +86,102 @@ extern "C" int lake_emul_run(int nRch, int nHRU, const int *segId, const int *do
     std::snprintf(msg, 256, "ok");
     return 0;
 }
+
+// Two Euler methods (kinematic wave + diffusive wave) routed the way route_device orders them when lake state is shared by
+// the methods (one stream): per batch of K steps the headwater reaches first (k_headwater, method by method), then wavefront
+// by wavefront and, inside a wavefront, method by method.  With Hanasaki-2006 reservoirs (H06Lake built as mr_set_network
+// builds it) this must reproduce the oracle, which -- like the reference -- steps method by method inside every time step.
+template <int M>
+static void emul_reach(DevNet &d, const std::vector<int> &flags, int p, int t, long long tau) {
+    if (flags[p] & FLAG_LAKE) lake_reach<M, true>(d, p, t, tau); else kw_dw_reach<M>(d, p, t);
+}
+
+extern "C" int lake_emul_run_h06(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId, const double *hruArea,
+                                 const double *length, const double *slope, const int *islake, const int *lakeType, const double *maxS,
+                                 const double *coef, const double *pw, const double *s0, double mann_n, double wscale, double dt,
+                                 int lakeInputOption, int nSteps, int K,
+                                 const double *qr /* [nSteps+1][nRch] BASIN_QR(1), caller order */,
+                                 const double *h06 /* [38][nRch]: 10 scalars (H06Lake order), I_Jan..Dec, D_Jan..Dec, purpose, I_mem_F, I_mem_L, 0 */,
+                                 int startY, int startM, int startD, double startSec, int noleap,
+                                 double *q_out /* [2][nSteps][nRch] */, double *vol_out /* [2][nRch] */, char *msg) {
+    Topology T;
+    std::string terr;
+    if (build_topology(nRch, nHRU, segId, downSegId, hruSegId, hruArea, T, terr)) { std::snprintf(msg, 256, "%s", terr.c_str()); return 1; }
+    const int N = nRch, MM[2] = {M_KW, M_DW};
+    std::vector<double> rlen(N), rslp(N), rwid(N), rman(N, mann_n), rdep(N, 100000.0), zc(N, 0.0), zf(N, 1000.0), rstor(N);
+    std::vector<double> dMaxS(N), dCoef(N), dPw(N), dS0(N);
+    std::vector<int> flags(N, 0), ltype(N, MR_LAKE_DOLL03), slot(N, -1), pos;
+    for (int p = 0; p < N; ++p) {
+        const int r = T.pos2rch[p];
+        rlen[p] = length[r]; rslp[p] = std::fmax(slope[r], 1.e-6); rwid[p] = wscale * std::sqrt(T.totArea[p]);
+        rstor[p] = rdep[p] * (rwid[p] + zc[p] * rdep[p]) * rlen[p];
+        if (islake[r] == 1) { flags[p] |= FLAG_LAKE; slot[p] = (int)pos.size(); pos.push_back(p); }
+        ltype[p] = lakeType[r]; dMaxS[p] = maxS[r]; dCoef[p] = coef[r]; dPw[p] = pw[r]; dS0[p] = s0[r];
+    }
+    const int nLake = (int)pos.size();
+    std::vector<H06Lake> lk(nLake ? nLake : 1);
+    long long off = 0;
+    for (int s = 0; s < nLake; ++s) {                        // as mr_set_network
+        H06Lake &L = lk[s];
+        std::memset(&L, 0, sizeof L);
+        if (ltype[pos[s]] != MR_LAKE_HANASAKI06) continue;
+        const int r = T.pos2rch[pos[s]];
+        double *sc = &L.Smax;
+        for (int k = 0; k < 10; ++k) sc[k] = h06[(size_t)k * N + r];
+        for (int k = 0; k < 12; ++k) { L.I[k] = h06[(size_t)(10 + k) * N + r]; L.D[k] = h06[(size_t)(22 + k) * N + r]; }
+        L.purpose = (int)h06[(size_t)34 * N + r]; L.memF = h06[(size_t)35 * N + r] != 0.0 ? 1 : 0;
+        const double yrs = (double)(int)h06[(size_t)36 * N + r];
+        L.L31 = (int)std::floor(yrs * 31 * 86400.0 / dt); L.L30 = (int)std::floor(yrs * 30 * 86400.0 / dt);
+        L.LF = (int)std::floor(yrs * 28.25 * 86400.0 / dt); L.LFnoleap = (int)std::floor(yrs * 28 * 86400.0 / dt);
+        L.memOff = off;
+        if (L.memF) off += 12LL * L.L31;
+    }
+    std::vector<double> mem((size_t)(off > 0 ? off : 1), 0.0);
+    std::vector<double> qrAll((size_t)(nSteps + 1) * N);
+    for (int t = 0; t <= nSteps; ++t) for (int r = 0; r < N; ++r) qrAll[(size_t)t * N + T.rch2pos[r]] = qr[(size_t)t * N + r];
+    std::vector<double> qrSer((size_t)(K + 1) * N), qSer[2], inflow[2], vol0[2], vol1[2], wb[2], mol[2], flood[2], ele[2];
+    int err[4] = {0, 0, 0, 0};
+    DevNet d{};
+    d.nRch = N; d.nHRU = nHRU; d.nStage = T.nStage; d.nHead = T.nHead; d.dt = dt; d.hwDrain = 2; d.minLengthRoute = 0.0;
+    d.lakeInputOption = lakeInputOption; d.isLakeSim = 1; d.noleap = noleap;
+    d.stageOf = T.stageOf.data(); d.upPtr = T.upPtr.data(); d.upIdx = T.upIdx.data(); d.nGood = T.nGood.data(); d.flags = flags.data();
+    d.hruPtr = T.hruPtr.data(); d.hruIdx = T.hruIdx.data(); d.hruWgt = T.hruWgt.data(); d.basArea = T.basArea.data();
+    d.rlength = rlen.data(); d.rslope = rslp.data(); d.rwidth = rwid.data(); d.rmann = rman.data();
+    d.rdepth = rdep.data(); d.sideSlope = zc.data(); d.fldpSlope = zf.data(); d.rstorage = rstor.data();
+    d.lakeType = ltype.data(); d.d03MaxS = dMaxS.data(); d.d03Coef = dCoef.data(); d.d03Pow = dPw.data(); d.d03S0 = dS0.data();
+    d.qrSer = qrSer.data(); d.err = err; d.lakeSlot = slot.data(); d.nLake = nLake; d.h06 = lk.data(); d.h06Mem = mem.data();
+    for (int i = 0; i < 2; ++i) {
+        const int m = MM[i], nm = n_molecule(m);
+        qSer[i].assign((size_t)K * N, 0.0); inflow[i].assign(N, 0.0); vol0[i].assign(N, 0.0); vol1[i].assign(N, 0.0); wb[i].assign(N, 0.0);
+        mol[i].assign((size_t)nm * N, 0.0); flood[i].assign(N, 0.0); ele[i].assign(N, 0.0);
+        d.qSer[m] = qSer[i].data(); d.inflow[m] = inflow[i].data(); d.vol0[m] = vol0[i].data(); d.vol1[m] = vol1[i].data(); d.wb[m] = wb[i].data();
+        d.mol[m] = mol[i].data(); d.floodVol[m] = flood[i].data(); d.reachEle[m] = ele[i].data();
+    }
+    std::vector<int> doy(K), mon(K), dom(K);
+    d.stepDoy = doy.data(); d.stepMonth = mon.data(); d.stepDay = dom.data();
+    int lastK = 0;
+    for (int s0 = 0; s0 < nSteps; s0 += K) {
+        const int kb = nSteps - s0 < K ? nSteps - s0 : K;
+        d.lastK = lastK;
+        for (int t = 0; t <= kb; ++t) std::memcpy(&qrSer[(size_t)t * N], &qrAll[(size_t)(s0 + t) * N], sizeof(double) * N);
+        for (int t = 0; t < kb; ++t) step_calendar(startY, startM, startD, startSec, noleap != 0, dt, s0 + t, mon[t], dom[t], doy[t]);
+        for (int i = 0; i < 2; ++i)                          // k_headwater<M>
+            for (int p = 0; p < T.nHead; ++p)
+                for (int t = 0; t < kb; ++t) { if (MM[i] == M_KW) emul_reach<M_KW>(d, flags, p, t, s0 + t); else emul_reach<M_DW>(d, flags, p, t, s0 + t); }
+        for (int w = 0; w < T.nStage + kb; ++w)              // wavefronts: (reach, step) with stage + step == w
+            for (int i = 0; i < 2; ++i)
+                for (int p = T.nHead; p < N; ++p) {
+                    const int t = w - T.stageOf[p];
+                    if (t < 0 || t >= kb) continue;
+                    if (MM[i] == M_KW) emul_reach<M_KW>(d, flags, p, t, s0 + t); else emul_reach<M_DW>(d, flags, p, t, s0 + t);
+                    if (err[0]) { std::snprintf(msg, 256, "ierr %d at position %d site %d", err[0], err[1], err[2]); return err[0]; }
+                }
+        for (int i = 0; i < 2; ++i)
+            for (int t = 0; t < kb; ++t) for (int r = 0; r < N; ++r)
+                q_out[((size_t)i * nSteps + s0 + t) * N + r] = qSer[i][(size_t)t * N + T.rch2pos[r]];
+        lastK = kb;
+    }
+    for (int i = 0; i < 2; ++i) for (int r = 0; r < N; ++r) vol_out[(size_t)i * N + r] = vol1[i][T.rch2pos[r]];
+    std::snprintf(msg, 256, "ok");
+    return 0;
+}

@@ -17,7 +17,7 @@ struct mr_handle_s {
     /* remap (mr_set_remap) */
     int nForcing, nMap, *mapHru, *numQ, *qIx; double *wgt;
     /* named lake parameters and the simulation start, applied to the oracle in mr_set_network */
-    char lpName[16][32]; double *lpVal[16]; int nLp;
+    char lpName[64][32]; double *lpVal[64]; int nLp;
     int hasStart, sy, sm, sd, noleap; double ssec;
     /* lake forcing of the next batch (mr_upload_lake_forcing) */
     double *ev, *pr; int epSteps;
@@ -97,7 +97,7 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
 
 int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message)
 {
-    if (h->nLp >= 16) { say(message, "mr_set_lake_param/too many parameters for the stub"); return 1; }
+    if (h->nLp >= 64) { say(message, "mr_set_lake_param/too many parameters for the stub"); return 1; }
     strncpy(h->lpName[h->nLp], name, 31); h->lpName[h->nLp][31] = 0;
     h->lpVal[h->nLp] = (double *)malloc(sizeof(double) * (size_t)n); memcpy(h->lpVal[h->nLp], values, sizeof(double) * (size_t)n);
     h->nLp++;

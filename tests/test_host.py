@@ -378,6 +378,25 @@ def test_hype_reservoirs_and_their_calendar_survive_a_restart(tmp_path, backend)
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+def test_hanasaki_reservoirs_from_the_network_file(tmp_path, backend):
+    """lakeModelType 2: the H06_* variables of the river-network file reach the routing, two methods share the reservoirs'
+    state, and the inflow memory makes the release depend on the run's own history."""
+    from mizuroute_b200 import synth
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=400, seed=4, dt=86400.0, route_opt="13", steps=20, lakes=8)
+    assert synth.make_h06_lakes(net, np.random.default_rng(6), frac=0.7, memory=True) >= 2
+    ro = ro * 20.0
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="h06", start="2000-02-20 00:00:00")
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "6"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    opts.sim_start = (2000, 2, 20, 0.0)
+    qo = Oracle(net, params, opts).run(ro)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["KWroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_exact_restart_of_the_euler_schemes(tmp_path, backend):
     """q_sub_kw / q_sub_mc / q_sub_dw [mol, seg] and volume_* in the restart file (popMetadat.f90:283-295): 24 steps in one
     run == 12 steps + restart + 12 steps, bit for bit, with <floodplain> T."""

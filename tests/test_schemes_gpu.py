@@ -136,3 +136,23 @@ def test_hype_without_calendar_or_parameters_is_an_error():
     net.lake_params.pop("HYP_A_avg")
     with pytest.raises(RoutingError, match="HYP_A_avg"):
         Router(net, params, opts, max_batch=2)
+
+
+@pytest.mark.parametrize("memory,calendar,start,dt,steps,route", [(False, "standard", (2000, 5, 20, 0.0), 86400.0, 30, "1"),
+                                                                  (True, "standard", (2000, 2, 20, 0.0), 86400.0, 24, "13"),
+                                                                  (True, "noleap", (2001, 12, 25, 0.0), 43200.0, 30, "35")])
+def test_hanasaki_reservoirs(memory, calendar, start, dt, steps, route):
+    """lakeModelType 2 (Hanasaki 2006): per-lake parameters, ring-buffer inflow memory, release coefficient reset at the start
+    of the operational year; with two methods the reservoirs' state is shared, so the methods run on one stream, wavefront
+    by wavefront (tests/test_lake_emul.py holds that order to bit equality on the host)."""
+    from mizuroute_b200 import capi, synth
+    from oracle import oracle as orc
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=dt, route_opt=route, steps=steps, lakes=10)
+    assert synth.make_h06_lakes(net, np.random.default_rng(6), frac=0.7, memory=memory) >= 2
+    opts.sim_start, opts.calendar = start, calendar
+    ro = ro * 20.0
+    o, r, qo, qg = _both(net, params, opts, ro, 7)
+    for i, c in enumerate(route):
+        tol = 1e-6 if c == "1" else EULER_RTOL
+        assert rel_err(qg[i], qo[i], floor=1e-6) <= tol, c
+        assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1.0) <= tol
