@@ -22,6 +22,7 @@
 #include "mr_topo.h"
 #include "mr_uh.h"
 #include "mr_calendar.h"
+#include "mr_lakeparams.h"
 
 using namespace mr;
 
@@ -521,56 +522,32 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         d.nLake = h->nLake;
         h->hasHype = false;
         for (int p : pos) if (ltype[p] == MR_LAKE_HYPE) h->hasHype = true;
+        const LakeParamLookup par = [&](const std::string &nm) -> const std::vector<double> * {
+            auto it = h->lakeParams.find(nm);
+            return (it == h->lakeParams.end() || (int)it->second.size() != nRch) ? nullptr : &it->second; };
         if (h->hasHype) {                             // HYP_* by lake slot (dataTypes.f90:202-213)
-            static const char *names[HYP_COUNT] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr",
-                                                   "HYP_Qrate_prim", "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
-            std::vector<HypeParams> bySlot(h->nLake);
-            for (int k = 0; k < HYP_COUNT; ++k) {
-                auto it = h->lakeParams.find(names[k]);
-                if (it == h->lakeParams.end() || (int)it->second.size() != nRch)
-                    return fail(message, 20, std::string("mr_set_network/HYPE lakes need the parameter ") + names[k] + " for every reach (mr_set_lake_param)");
-                for (int sIdx = 0; sIdx < h->nLake; ++sIdx) reinterpret_cast<double *>(&bySlot[sIdx])[k] = it->second[T.pos2rch[pos[sIdx]]];
-            }
+            std::vector<HypeParams> bySlot;
+            const std::string missing = build_hype_params(h->nLake, pos.data(), T.pos2rch.data(), par, bySlot);
+            if (!missing.empty()) return fail(message, 20, "mr_set_network/HYPE lakes need the parameter " + missing + " for every reach (mr_set_lake_param)");
             UP(hyp, bySlot);
         }
         h->hasH06 = false;
         for (int p : pos) if (ltype[p] == MR_LAKE_HANASAKI06) h->hasH06 = true;
         if (h->hasH06) {                              // H06_* by lake slot (dataTypes.f90:215-254) + the inflow memory
-            auto par = [&](const std::string &nm) -> const std::vector<double> * {
-                auto it = h->lakeParams.find(nm);
-                return (it == h->lakeParams.end() || (int)it->second.size() != nRch) ? nullptr : &it->second; };
-            static const char *mon[12] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
-            static const char *scal[10] = {"H06_Smax", "H06_alpha", "H06_envfact", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
-                                           "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini"};
-            std::vector<H06Lake> lk(h->nLake);
-            long long off = 0;
-            std::string missing;
-            auto val = [&](const std::string &nm, int r, double &out) { const auto *v = par(nm); if (!v) { missing = nm; return; } out = (*v)[r]; };
+            std::vector<H06Lake> lk;
+            long long memDoubles = 0;
+            const std::string missing = build_h06_lakes(h->nLake, pos.data(), T.pos2rch.data(), ltype.data(), o.dt, par, lk, memDoubles);
+            if (!missing.empty()) return fail(message, 20, "mr_set_network/Hanasaki lakes need the parameter " + missing + " for every reach (mr_set_lake_param)");
             for (int sIdx = 0; sIdx < h->nLake; ++sIdx) {
-                H06Lake &L = lk[sIdx];
-                std::memset(&L, 0, sizeof L);
                 if (ltype[pos[sIdx]] != MR_LAKE_HANASAKI06) continue;
                 if (pos[sIdx] < T.nHead && o.n_routes > 1)
                     return fail(message, 20, "mr_set_network/a Hanasaki reservoir without upstream reaches cannot be routed with several methods (its state is shared by them)");
-                const int r = T.pos2rch[pos[sIdx]];
-                double *sc = &L.Smax;
-                for (int k = 0; k < 10; ++k) val(scal[k], r, sc[k]);
-                for (int k = 0; k < 12; ++k) { val(std::string("H06_I_") + mon[k], r, L.I[k]); val(std::string("H06_D_") + mon[k], r, L.D[k]); }
-                double purpose = 0, memF = 0, memL = 0;
-                val("H06_purpose", r, purpose); val("H06_I_mem_F", r, memF); val("H06_I_mem_L", r, memL);
-                if (!missing.empty()) return fail(message, 20, "mr_set_network/Hanasaki lakes need the parameter " + missing + " for every reach (mr_set_lake_param)");
-                L.purpose = (int)purpose; L.memF = memF != 0.0 ? 1 : 0;
-                const double yrs = (double)(int)memL;
-                L.L31 = (int)std::floor(yrs * 31 * 86400.0 / o.dt); L.L30 = (int)std::floor(yrs * 30 * 86400.0 / o.dt);
-                L.LF = (int)std::floor(yrs * 28.25 * 86400.0 / o.dt); L.LFnoleap = (int)std::floor(yrs * 28 * 86400.0 / o.dt);
-                if (L.memF && L.LFnoleap < 1) return fail(message, 20, "mr_set_network/H06_I_mem_L must cover at least one step");
-                L.memOff = off;
-                if (L.memF) off += 12LL * L.L31;
+                if (lk[sIdx].memF && lk[sIdx].LFnoleap < 1) return fail(message, 20, "mr_set_network/H06_I_mem_L must cover at least one step");
             }
             H06Lake *dl = nullptr;
             e = dev_upload(h, &dl, lk, where, message); if (e) return e;
             d.h06 = dl;
-            AL(d.h06Mem, (size_t)(off > 0 ? off : 1));
+            AL(d.h06Mem, (size_t)(memDoubles > 0 ? memDoubles : 1));
         }
         if (h->hasHype || h->hasH06) AL(h->dStepDoy, (size_t)3 * KB);
     }

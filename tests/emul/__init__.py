@@ -44,7 +44,7 @@ def load_euler(noise_seed: int = 0):
 
 _LAKE_SO = os.path.join(_HERE, "liblake_emul.so")
 _LAKE_SRC = os.path.join(_HERE, "lake_emul.cpp")
-_LAKE_DEPS = [_LAKE_SRC] + [os.path.join(_CSRC, f) for f in ("mr_lake.cuh", "mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_calendar.h")]
+_LAKE_DEPS = [_LAKE_SRC] + [os.path.join(_CSRC, f) for f in ("mr_lake.cuh", "mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_calendar.h", "mr_lakeparams.h")]
 
 
 def load_lake():

@@ -12,6 +12,8 @@
 #include "../../mizuroute_b200/csrc/mr_lake.cuh"
 #include "../../mizuroute_b200/csrc/mr_topo.h"
 #include "../../mizuroute_b200/csrc/mr_calendar.h"
+#include "../../mizuroute_b200/csrc/mr_lakeparams.h"
+#include <map>
 
 using namespace mr;
 
@@ -55,10 +57,16 @@ extern "C" int lake_emul_run(int nRch, int nHRU, const int *segId, const int *do
     d.qrSer = qrSer.data(); d.qSer[M] = qSer.data(); d.inflow[M] = inflow.data(); d.vol0[M] = vol0.data(); d.vol1[M] = vol1.data();
     d.wb[M] = wb.data(); d.mol[M] = mol.data(); d.floodVol[M] = flood.data(); d.reachEle[M] = ele.data();
     d.err = err; d.lakeSlot = slot.data(); d.nLake = nLake;
-    std::vector<HypeParams> hypBySlot(nLake ? nLake : 1);
+    std::vector<HypeParams> hypBySlot;
     std::vector<int> doy(nSteps, 0);
-    if (hyp && nLake) {                                      // as mr_set_network / route_device do
-        for (int k = 0; k < HYP_COUNT; ++k) for (int sl = 0; sl < nLake; ++sl) reinterpret_cast<double *>(&hypBySlot[sl])[k] = hyp[(size_t)k * N + T.pos2rch[pos[sl]]];
+    if (hyp && nLake) {                                      // mr_set_network: the same builder
+        static const char *names[HYP_COUNT] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr",
+                                               "HYP_Qrate_prim", "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode"};
+        std::map<std::string, std::vector<double>> given;
+        for (int k = 0; k < HYP_COUNT; ++k) given[names[k]].assign(hyp + (size_t)k * N, hyp + (size_t)(k + 1) * N);
+        const LakeParamLookup par = [&](const std::string &nm) -> const std::vector<double> * { auto it = given.find(nm); return it == given.end() ? nullptr : &it->second; };
+        const std::string missing = build_hype_params(nLake, pos.data(), T.pos2rch.data(), par, hypBySlot);
+        if (!missing.empty()) { std::snprintf(msg, 256, "missing %s", missing.c_str()); return 20; }
         d.hyp = hypBySlot.data();
     }
     if (startY) {
@@ -119,22 +127,20 @@ extern "C" int lake_emul_run_h06(int nRch, int nHRU, const int *segId, const int
         ltype[p] = lakeType[r]; dMaxS[p] = maxS[r]; dCoef[p] = coef[r]; dPw[p] = pw[r]; dS0[p] = s0[r];
     }
     const int nLake = (int)pos.size();
-    std::vector<H06Lake> lk(nLake ? nLake : 1);
+    std::vector<H06Lake> lk;
     long long off = 0;
-    for (int s = 0; s < nLake; ++s) {                        // as mr_set_network
-        H06Lake &L = lk[s];
-        std::memset(&L, 0, sizeof L);
-        if (ltype[pos[s]] != MR_LAKE_HANASAKI06) continue;
-        const int r = T.pos2rch[pos[s]];
-        double *sc = &L.Smax;
-        for (int k = 0; k < 10; ++k) sc[k] = h06[(size_t)k * N + r];
-        for (int k = 0; k < 12; ++k) { L.I[k] = h06[(size_t)(10 + k) * N + r]; L.D[k] = h06[(size_t)(22 + k) * N + r]; }
-        L.purpose = (int)h06[(size_t)34 * N + r]; L.memF = h06[(size_t)35 * N + r] != 0.0 ? 1 : 0;
-        const double yrs = (double)(int)h06[(size_t)36 * N + r];
-        L.L31 = (int)std::floor(yrs * 31 * 86400.0 / dt); L.L30 = (int)std::floor(yrs * 30 * 86400.0 / dt);
-        L.LF = (int)std::floor(yrs * 28.25 * 86400.0 / dt); L.LFnoleap = (int)std::floor(yrs * 28 * 86400.0 / dt);
-        L.memOff = off;
-        if (L.memF) off += 12LL * L.L31;
+    {                                                        // mr_set_network: the same builder, fed by name
+        static const char *mon[12] = {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"};
+        std::vector<std::string> names = {"H06_Smax", "H06_alpha", "H06_envfact", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
+                                          "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini"};
+        for (int k = 0; k < 12; ++k) names.push_back(std::string("H06_I_") + mon[k]);
+        for (int k = 0; k < 12; ++k) names.push_back(std::string("H06_D_") + mon[k]);
+        names.push_back("H06_purpose"); names.push_back("H06_I_mem_F"); names.push_back("H06_I_mem_L");
+        std::map<std::string, std::vector<double>> given;
+        for (size_t k = 0; k < names.size(); ++k) given[names[k]].assign(h06 + k * N, h06 + (k + 1) * N);
+        const LakeParamLookup par = [&](const std::string &nm) -> const std::vector<double> * { auto it = given.find(nm); return it == given.end() ? nullptr : &it->second; };
+        const std::string missing = build_h06_lakes(nLake, pos.data(), T.pos2rch.data(), ltype.data(), dt, par, lk, off);
+        if (!missing.empty()) { std::snprintf(msg, 256, "missing %s", missing.c_str()); return 20; }
     }
     std::vector<double> mem((size_t)(off > 0 ? off : 1), 0.0);
     std::vector<double> qrAll((size_t)(nSteps + 1) * N);
