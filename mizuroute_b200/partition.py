@@ -55,6 +55,7 @@ def subnetwork(net: RiverNetwork, reaches: np.ndarray) -> RiverNetwork:
                        area=net.area[hru_keep], width=pick(net.width), man_n=pick(net.man_n), islake=pick(net.islake),
                        lakeModelType=pick(net.lakeModelType), D03_MaxStorage=pick(net.D03_MaxStorage),
                        D03_Coefficient=pick(net.D03_Coefficient), D03_Power=pick(net.D03_Power), D03_S0=pick(net.D03_S0),
+                       lake_params={k: np.asarray(v)[reaches] for k, v in (net.lake_params or {}).items()},
                        meta=dict(net.meta))
     sub.meta["hru_index"] = np.flatnonzero(hru_keep)      # columns of the global runoff array this domain reads
     sub.meta["reach_index"] = np.asarray(reaches)

@@ -107,3 +107,18 @@ def test_decomposed_euler_schemes_equal_single_domain():
     q, dec = route_decomposed_local(net, params, opts, ro, 4, batch=7)
     assert dec.mainstem.size > 0 and dec.outlets.size > 0
     assert np.array_equal(q, single)
+
+
+def test_subnetworks_carry_the_named_lake_parameters():
+    from mizuroute_b200 import synth
+    from mizuroute_b200.partition import decompose, mainstem_network, subnetwork
+    net, params, opts, ro = case("conus", n=600, seed=4, dt=86400.0, route_opt="1", steps=1, lakes=8)
+    synth.make_hype_lakes(net, np.random.default_rng(5), frac=0.7)
+    dec = decompose(net, 3)
+    subs = [subnetwork(net, r) for r in dec.trib if len(r)] + [mainstem_network(net, dec)]
+    for sub in subs:
+        pos = {int(s): i for i, s in enumerate(net.segId)}
+        glob = np.array([pos[int(s)] for s in sub.segId])
+        assert set(sub.lake_params) == set(net.lake_params)
+        for k, v in sub.lake_params.items():
+            assert v.shape == (sub.nRch,) and np.array_equal(v, net.lake_params[k][glob])
