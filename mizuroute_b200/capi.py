@@ -115,6 +115,9 @@ def load(rebuild_if_stale: bool = True):
     L.mr_set_exchange_buffer.argtypes = [vp, C.c_int, vp, C.c_long, cp]
     L.mr_get_exchange_buffer.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_long), cp]
     L.mr_copy_exchange.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, cp]
+    L.mr_upload_lake_forcing.argtypes = [vp, C.c_int, dp, dp, cp]
+    L.mr_set_lake_param.argtypes = [vp, cp, C.c_int, dp, cp]
+    L.mr_set_sim_start.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, cp]
     L.mr_destroy.argtypes = [vp]
     L.mr_destroy.restype = None
     for name in EXPORTS:

@@ -66,7 +66,7 @@ class Router:
             self._check(self._L.mr_set_lake_param(self._h, name.encode(), int(v.size), _ptr(v, C.c_double), self._msg))
         if getattr(opts, "sim_start", None):
             y, mo, d, sec = opts.sim_start
-            self._check(self._L.mr_set_sim_start(self._h, int(y), int(mo), int(d), C.c_double(float(sec)), int(opts.calendar == "noleap"), self._msg))
+            self._check(self._L.mr_set_sim_start(self._h, int(y), int(mo), int(d), float(sec), int(opts.calendar == "noleap"), self._msg))
         if ghosts is not None:
             gid, gkind, garea, gwidth = (np.ascontiguousarray(ghosts[0], dtype=np.int32), np.ascontiguousarray(ghosts[1], dtype=np.int32),
                                          np.ascontiguousarray(ghosts[2], dtype=np.float64), np.ascontiguousarray(ghosts[3], dtype=np.float64))
