@@ -169,7 +169,7 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
         if constexpr (HY) {
             if (!d.h06) { raise(d.err, 20, p, E_LAKE_PARAM); return; }
             if (!d.stepMonth) { raise(d.err, 20, p, E_NO_CALENDAR); return; }
-            const double prevQ = t > 0 ? Qs[p - (size_t)N] : (d.lastK > 0 ? d.qSer[M][(size_t)(d.lastK - 1) * N + p] : 0.0);   // REACH_Q of the previous step
+            const double prevQ = t > 0 ? d.qSer[M][(size_t)(t - 1) * N + p] : (d.lastK > 0 ? d.qSer[M][(size_t)(d.lastK - 1) * N + p] : 0.0);   // REACH_Q of the previous step
             q = h06_release(d.h06 + d.lakeSlot[p], d.h06Mem, d.stepMonth[t], d.stepDay[t], d.noleap, v1, qup, prevQ, dt);
             v1 = v1 - q * dt;
         } else q = 0.0;
