@@ -109,6 +109,9 @@ typedef struct {
     /* lake forcing: reach-level evaporation / precipitation [m3/s] of the current step (RCHFLX%basinevapo / basinprecip,
        main_route.f90:174-199,243-249); hasEP = 0: no such forcing given, both are exactly zero */
     double *reachEvapo, *reachPrecip; int hasEP;
+    /* water management (is_flux_wm / is_vol_wm, main_route.f90:110-123): abstraction (+) / injection (-) per reach, target
+       lake volumes, the volume jump start, and REACH_WM_FLUX_actual per method; wmFlux = NULL: is_flux_wm off (flux 0) */
+    const double *wmFlux, *wmVol; int volJumpStart; double *WM_ACTUAL[N_METHOD];
     /* parametric lake models beyond Doll-2003: per-reach parameters by name (dataTypes.f90:202-254) and the simulation
        start datetime (simDatetime(1) of step 1) the HYPE / Hanasaki formulations read the calendar from */
     double *LP[64];
@@ -324,12 +327,13 @@ static const char *LP_NAMES[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_z
                                  "H06_I_Oct", "H06_I_Nov", "H06_I_Dec",
                                  "H06_D_Jan", "H06_D_Feb", "H06_D_Mar", "H06_D_Apr", "H06_D_May", "H06_D_Jun", "H06_D_Jul", "H06_D_Aug", "H06_D_Sep",
                                  "H06_D_Oct", "H06_D_Nov", "H06_D_Dec",
-                                 "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L", NULL};
+                                 "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L", "LakeTargVol", NULL};
 enum { LP_HYP_E_emr, LP_HYP_E_lim, LP_HYP_E_min, LP_HYP_E_zero, LP_HYP_Qrate_emr, LP_HYP_Erate_emr, LP_HYP_Qrate_prim,
        LP_HYP_Qrate_amp, LP_HYP_Qrate_phs, LP_HYP_prim_F, LP_HYP_A_avg, LP_HYP_Qsim_mode, LP_COUNT,
        LP_H06_Smax = LP_COUNT, LP_H06_alpha, LP_H06_envfact, LP_H06_S_ini, LP_H06_c1, LP_H06_c2, LP_H06_exponent, LP_H06_denominator,
        LP_H06_c_compare, LP_H06_frac_Sdead, LP_H06_E_rel_ini, LP_H06_I_Jan, LP_H06_D_Jan = LP_H06_I_Jan + 12,
-       LP_H06_purpose = LP_H06_D_Jan + 12, LP_H06_I_mem_F, LP_H06_D_mem_F, LP_H06_I_mem_L, LP_H06_D_mem_L, LP_END };
+       LP_H06_purpose = LP_H06_D_Jan + 12, LP_H06_I_mem_F, LP_H06_D_mem_F, LP_H06_I_mem_L, LP_H06_D_mem_L, LP_END,
+       LP_LakeTargVol = LP_END /* NETOPO%LakeTargVol: the lake follows the target volume REACH_WM_VOL (lake_route.f90:196-203) */ };
 
 /* ------------------------------------------------------------------------------------------ */
 /* create: read_streamSeg.f90 inputs -> augment_ntopo (process_ntopo.f90:39-266) -> put_data_struct */
@@ -480,7 +484,7 @@ mro_t *mro_create(int nRch, int nHRU,
     for (m = 0; m < N_METHOD; m++) {
         ALLOC(h->REACH_Q[m], nRch); ALLOC(h->REACH_VOL0[m], nRch); ALLOC(h->REACH_VOL1[m], nRch);
         ALLOC(h->REACH_INFLOW[m], nRch); ALLOC(h->WB[m], nRch);
-        ALLOC(h->FLOOD_VOL1[m], nRch); ALLOC(h->REACH_ELE[m], nRch);
+        ALLOC(h->FLOOD_VOL1[m], nRch); ALLOC(h->REACH_ELE[m], nRch); ALLOC(h->WM_ACTUAL[m], nRch);
         if (N_MOLECULE[m] > 0 && h->onRoute[m]) ALLOC(h->MOL[m], (size_t)nRch * N_MOLECULE[m]);   /* molecule%Q(:) = 0, init_model_data.f90:463-497 */
     }
     ALLOC(h->KW, nRch);
@@ -503,7 +507,7 @@ void mro_destroy(mro_t *h)
     free(h->FRAC_FUTURE); free(h->uh_ptr); free(h->uh_val);
     free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff); free(h->reachEvapo); free(h->reachPrecip);
     for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
-                                     free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); }
+                                     free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); free(h->WM_ACTUAL[m]); }
     { int k; for (k = 0; k < 64; k++) free(h->LP[k]); }
     if (h->h06Mem) { int k; for (k = 0; k < h->nRch; k++) free(h->h06Mem[k]); free(h->h06Mem); free(h->h06Len); }
     free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
@@ -563,8 +567,44 @@ static void comp_reach_wb_lake(mro_t *h, int m, int j, double Qupstream, double 
     double precip = (lakeFlag && h->hasEP) ? h->reachPrecip[j] * dt : 0.0;
     double evapo = (lakeFlag && h->hasEP) ? -1.0 * h->reachEvapo[j] * dt : 0.0;
     double Qout = -1.0 * h->REACH_Q[m][j] * dt;
-    double Qtake_actual = -1.0 * 0.0 * dt;
+    double Qtake_actual = -1.0 * (h->wmFlux ? h->WM_ACTUAL[m][j] : 0.0) * dt;
     h->WB[m][j] = dVol - (Qin + Qlateral + precip + Qtake_actual + Qout + evapo);
+}
+
+/* Water abstraction (+) / injection (-) of a reach, shared by irf_rch, kw_rch, mc_rch and dfw_rch (irf_route.f90:114-142 =
+   kwe_route.f90:118-146 = mc_route.f90:118-146 = dfw_route.f90:122-150): taken from the storage first, then from the upstream
+   inflow, then from the lateral flow.  REACH_WM_FLUX_actual starts as the demand, missing value included. */
+static void wm_cascade(mro_t *h, int M, int j, double q_upstream, double *q_upstream_mod, double *Qlat)
+{
+    double dt = h->dt, Qabs;
+    *q_upstream_mod = q_upstream;
+    if (!h->wmFlux) { h->WM_ACTUAL[M][j] = 0.0; return; }
+    Qabs = h->wmFlux[j];
+    h->WM_ACTUAL[M][j] = h->wmFlux[j];
+    if (h->wmFlux[j] == -9999.0) return;                   /* realMissing: no water management at this reach */
+    if (Qabs > 0) {
+        if (h->REACH_VOL1[M][j] / dt > Qabs) {
+            h->REACH_VOL1[M][j] = h->REACH_VOL1[M][j] - Qabs * dt;
+        } else {
+            Qabs = Qabs - h->REACH_VOL1[M][j] / dt;
+            h->REACH_VOL1[M][j] = 0.0;
+            if (q_upstream > Qabs) {
+                *q_upstream_mod = q_upstream - Qabs;
+            } else {
+                Qabs = Qabs - q_upstream;
+                *q_upstream_mod = 0.0;
+                if (*Qlat > Qabs) {
+                    *Qlat = *Qlat - Qabs;
+                } else {
+                    Qabs = Qabs - *Qlat;
+                    *Qlat = 0.0;
+                    h->WM_ACTUAL[M][j] = h->wmFlux[j] - Qabs;
+                }
+            }
+        }
+    } else {
+        *Qlat = *Qlat - Qabs;
+    }
 }
 
 static void comp_reach_wb(mro_t *h, int m, int j, double Qupstream, double Qlat) { comp_reach_wb_lake(h, m, j, Qupstream, Qlat, 0); }
@@ -585,7 +625,7 @@ static int accum_inst_runoff(mro_t *h, int j)
 static int irf_rch(mro_t *h, int j)
 {
     const int M = M_IRF;
-    int nUps = h->nGood[j], m, k, ntdh; double q_upstream = 0.0, Qlat = 0.0, dt = h->dt;
+    int nUps = h->nGood[j], m, k, ntdh; double q_upstream = 0.0, Qlat = 0.0, dt = h->dt, q_mod, q_in;
     double *QF = h->QFUTURE_IRF + h->uh_ptr[j]; const double *UH = h->uh_val + h->uh_ptr[j];
     h->REACH_VOL0[M][j] = h->REACH_VOL1[M][j];
     if (nUps > 0) {
@@ -600,6 +640,8 @@ static int irf_rch(mro_t *h, int j)
         else if (h->hw_drain_point == 2) { Qlat = h->BASIN_QR1[j]; }
     }
     h->REACH_INFLOW[M][j] = q_upstream;
+    wm_cascade(h, M, j, q_upstream, &q_mod, &Qlat);
+    q_in = q_upstream; q_upstream = q_mod;          /* conv_upsbas_qr sees the inflow left after the abstraction */
     ntdh = h->uh_ptr[j + 1] - h->uh_ptr[j];
     if (h->RLENGTH[j] > h->min_length_route) {
         for (k = 0; k < ntdh; k++) QF[k] = QF[k] + UH[k] * q_upstream;
@@ -616,7 +658,7 @@ static int irf_rch(mro_t *h, int j)
         h->REACH_Q[M][j] = QF[0] + Qlat;
         h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0;
     }
-    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    comp_reach_wb(h, M, j, q_in, Qlat);
     return 0;
 }
 
@@ -805,10 +847,11 @@ static void solve_ade(double L, int nMol, double dtl, double FluxUp, double ck, 
 static int kw_dw_rch(mro_t *h, int M, int j)
 {
     const int nMol = N_MOLECULE[M];
-    double q_upstream, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * nMol, cur[MAX_MOLECULE];
-    const int isHW = euler_inflow(h, M, j, &q_upstream, &Qlat);
+    double q_upstream, q_in, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * nMol, cur[MAX_MOLECULE];
+    const int isHW = euler_inflow(h, M, j, &q_in, &Qlat);
     const double S = h->R_SLOPE[j], n = h->R_MAN_N[j], bt = h->R_WIDTH[j], bd = h->R_DEPTH[j], zc = h->SIDE_SLOPE[j], zf = h->FLDP_SLOPE[j], L = h->RLENGTH[j];
     int i;
+    wm_cascade(h, M, j, q_in, &q_upstream, &Qlat);      /* the solver sees Qupstream_mod, the water balance Qupstream */
     if (!isHW || h->hw_drain_point == 1) {
         if (L > h->min_length_route) {
             double Qbar = (q_upstream + mol[0] + mol[nMol - 2]) / 3.0;
@@ -838,7 +881,7 @@ static int kw_dw_rch(mro_t *h, int M, int j)
         for (i = 0; i < nMol; i++) mol[i] = 0.0;
         mol[nMol - 1] = h->REACH_Q[M][j];
     }
-    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    comp_reach_wb(h, M, j, q_in, Qlat);
     return 0;
 }
 
@@ -847,10 +890,11 @@ static int mc_rch(mro_t *h, int j)
 {
     const int M = M_MC;
     const double Y = 0.5, Qmin = 1.e-50;
-    double q_upstream, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * 2;
-    const int isHW = euler_inflow(h, M, j, &q_upstream, &Qlat);
+    double q_upstream, q_in, Qlat, dt = h->dt, *mol = h->MOL[M] + (size_t)j * 2;
+    const int isHW = euler_inflow(h, M, j, &q_in, &Qlat);
     const double S = h->R_SLOPE[j], n = h->R_MAN_N[j], bt = h->R_WIDTH[j], bd = h->R_DEPTH[j], zc = h->SIDE_SLOPE[j], zf = h->FLDP_SLOPE[j], L = h->RLENGTH[j];
     double Q00 = mol[0], Q01 = mol[1], Q10, Q11;
+    wm_cascade(h, M, j, q_in, &q_upstream, &Qlat);
     if (!isHW || h->hw_drain_point == 1) {
         if (L > h->min_length_route) {
             double theta = dt / L, Qbar;
@@ -908,7 +952,7 @@ static int mc_rch(mro_t *h, int j)
         h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
     }
     mol[0] = Q10; mol[1] = Q11;
-    comp_reach_wb(h, M, j, q_upstream, Qlat);
+    comp_reach_wb(h, M, j, q_in, Qlat);
     return 0;
 }
 
@@ -970,7 +1014,11 @@ static int lake_route(mro_t *h, int j, int M)
 {
     int m; double q_upstream = 0.0, dt = h->dt, *V1 = &h->REACH_VOL1[M][j], *Q = &h->REACH_Q[M][j];
     for (m = h->up_ptr[j]; m < h->up_ptr[j + 1]; m++) q_upstream = q_upstream + h->REACH_Q[M][h->up_idx[m]];
-    if (h->iTime == 1) {   /* cold start (isColdStart = T) */
+    const int targVol = h->LP[LP_LakeTargVol] && h->LP[LP_LakeTargVol][j] != 0.0;
+    const double wmVolJ = h->wmVol ? h->wmVol[j] : 0.0;        /* REACH_WM_VOL (0 when is_vol_wm is off, main_route.f90:117-123) */
+    if (h->iTime == 1 && h->volJumpStart && targVol) {          /* lake_route.f90:137-139 */
+        *V1 = wmVolJ;
+    } else if (h->iTime == 1) {   /* cold start (isColdStart = T) */
         switch (h->lakeModelType[j]) {
             case LAKE_ENDORHEIC: *V1 = h->D03_S0[j]; break;
             case LAKE_DOLL03:    *V1 = h->D03_MaxStorage[j]; break;
@@ -992,6 +1040,18 @@ static int lake_route(mro_t *h, int j, int M)
         if (*V1 > ev * dt) *V1 = *V1 - ev * dt;
         else { if (h->hasEP) h->reachEvapo[j] = *V1 / dt; *V1 = 0.0; }   /* basinevapo is shared by the routing methods of a step */
     }
+    /* water abstraction / injection from the lake (lake_route.f90:176-193) */
+    h->WM_ACTUAL[M][j] = h->wmFlux ? h->wmFlux[j] : 0.0;
+    if (h->wmFlux && h->wmFlux[j] != -9999.0) {
+        const double f = h->wmFlux[j];
+        if (f <= 0) { *V1 = *V1 - f * dt; h->WM_ACTUAL[M][j] = f; }
+        else if (f * dt <= *V1) { *V1 = *V1 - f * dt; h->WM_ACTUAL[M][j] = f; }
+        else { h->WM_ACTUAL[M][j] = *V1 / dt; *V1 = 0.0; }
+    }
+    if (targVol) {                                             /* lake_route.f90:196-203 */
+        if (*V1 < wmVolJ) *Q = 0;
+        else { *Q = (*V1 - wmVolJ) / dt; *V1 = wmVolJ; }
+    } else
     switch (h->lakeModelType[j]) {
         case LAKE_ENDORHEIC: *Q = 0.0; break;
         case LAKE_DOLL03:
@@ -1441,6 +1501,21 @@ static int kwt_rch(mro_t *h, int j, double T0, double T1, wave_buf_t *b)
     if (b->n > MAXQPAR) { ierr = remove_rch(b); if (ierr) return ierr; }
     NQ1 = b->n - 1;
     T_START = T0; T_END = T1;     /* RSTEP = 0 */
+    if (h->wmFlux && h->wmFlux[j] != -9999.0) {   /* extract_from_rch, kwt_route.f90:351-455 (note its sign: > 0 adds water) */
+        const double Qtake = h->wmFlux[j], alfa = 5.0 / 3.0, K = sqrt(h->R_SLOPE[j]) / h->R_MAN_N[j];
+        const int NRw = b->n;
+        double Qavg, totQ, Qfrac;
+        ierr = interp_rch(b->T, b->Q, NRw, T_START, T_END, &Qavg);
+        if (ierr) { snprintf(h->message, 256, "extract_from_rch/interp_rch"); return ierr; }
+        totQ = Qavg * h->R_WIDTH[j];
+        if (Qtake > 0.0) { Qfrac = Qtake / totQ; for (i = 1; i < NRw; i++) b->Q[i] = b->Q[i] * (1.0 + Qfrac); }
+        else if (Qtake < 0.0 && fabs(Qtake) < totQ) { Qfrac = fabs(Qtake) / totQ; for (i = 1; i < NRw; i++) b->Q[i] = b->Q[i] * (1.0 - Qfrac); }
+        else { for (i = 0; i < NRw; i++) b->Q[i] = 0.0; }           /* RPARAM%MINFLOW: minFlow of the network file, 0 here */
+        for (i = 1; i < NRw; i++) {
+            double wc = alfa * pow(K, 1.0 / alfa) * pow(b->Q[i], (alfa - 1.0) / alfa);
+            b->X[i] = fmin(h->RLENGTH[j] / wc + b->T[i], HUGE_DP);
+        }
+    }
     FROUTE[0] = 1; for (i = 1; i <= NQ1; i++) FROUTE[i] = 0;
     ierr = kinwav_rch(h, j, T_START, T_END, b->Q + 1, b->T + 1, b->X + 1, FROUTE + 1, NQ1, &NQ2);
     if (ierr) return ierr;
@@ -1481,6 +1556,12 @@ int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const
 int mro_step(mro_t *h, double T0, double T1, const double *basinRunoff) { return mro_step_ep(h, T0, T1, basinRunoff, NULL, NULL); }
 
 /* basinEvapo / basinPrecip [nHRU] in the units of the runoff (NULL = no lake forcing: exactly zero in lake_route) */
+/* water management forcing of the NEXT steps (until changed): flux_wm / vol_wm [nRch] in the caller's reach order, NULL = off */
+void mro_set_wm(mro_t *h, const double *flux_wm, const double *vol_wm, int volJumpStart)
+{
+    h->wmFlux = flux_wm; h->wmVol = (vol_wm && h->is_lake_sim) ? vol_wm : NULL; h->volJumpStart = volJumpStart;
+}
+
 int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const double *basinEvapo, const double *basinPrecip)
 {
     int j, r, ierr;

@@ -134,6 +134,13 @@ class Oracle:
         v = np.ascontiguousarray(values, dtype=np.float64)
         assert lib().mro_set(self.h, C.c_int(method), C.c_int(field), _p(v, C.c_double)) == 0
 
+    def set_wm(self, flux_wm=None, vol_wm=None, vol_jumpstart: bool = False):
+        """Water management of the following steps (is_flux_wm / is_vol_wm): flux_wm [nRch] abstraction (+) / injection (-),
+        -9999 = none at that reach; vol_wm [nRch] target volume of the lakes flagged by the lake parameter LakeTargVol."""
+        self._wm = (None if flux_wm is None else np.ascontiguousarray(flux_wm, dtype=np.float64),
+                    None if vol_wm is None else np.ascontiguousarray(vol_wm, dtype=np.float64))     # kept alive: the C side holds the pointers
+        lib().mro_set_wm(self.h, _p(self._wm[0], C.c_double), _p(self._wm[1], C.c_double), C.c_int(int(vol_jumpstart)))
+
     def lake_forcing(self):
         """(reach evaporation, reach precipitation) [m3/s] of the last step; the evaporation is what lake_route left
         (cut to the lake volume where the lake ran dry)."""

@@ -548,6 +548,41 @@ class Twin:
         self.T0, self.T1 = 0.0, float(opts.dt)
         self.itime = 1
         self.has_ep = False
+        self.wm_flux = self.wm_vol = None
+        self.wm_jump = False
+        self.WMA = {m: [0.0] * n for m in range(6)}      # REACH_WM_FLUX_actual per method
+
+    def set_wm(self, flux_wm=None, vol_wm=None, vol_jumpstart=False):
+        self.wm_flux = None if flux_wm is None else [float(x) for x in flux_wm]
+        self.wm_vol = None if (vol_wm is None or not self.o.is_lake_sim) else [float(x) for x in vol_wm]
+        self.wm_jump = bool(vol_jumpstart)
+
+    def _take(self, m, j, qup, qlat):
+        """Abstraction (+) / injection (-): storage first, then upstream inflow, then lateral flow (irf_route.f90:114-142 and
+        the identical blocks of the Euler schemes).  Returns (inflow left, lateral flow left)."""
+        if self.wm_flux is None:
+            self.WMA[m][j] = 0.0
+            return qup, qlat
+        want = self.wm_flux[j]
+        self.WMA[m][j] = want
+        if want == -9999.0:
+            return qup, qlat
+        dt = self.o.dt
+        if want <= 0:
+            return qup, qlat - want
+        if self.V1[m][j] / dt > want:
+            self.V1[m][j] = self.V1[m][j] - want * dt
+            return qup, qlat
+        rest = want - self.V1[m][j] / dt
+        self.V1[m][j] = 0.0
+        if qup > rest:
+            return qup - rest, qlat
+        rest = rest - qup
+        if qlat > rest:
+            return 0.0, qlat - rest
+        rest = rest - qlat
+        self.WMA[m][j] = want - rest
+        return 0.0, 0.0
 
     # -- step ---------------------------------------------------------------------------------
     def _basin2reach(self, flux):
@@ -711,7 +746,8 @@ class Twin:
     def _wb(self, m, j, qup, qlat, precip=0.0, evapo=0.0):
         dt = self.o.dt
         dvol = self.V1[m][j] - self.V0[m][j]
-        self.WB[m][j] = dvol - (qup * dt + qlat * dt + precip + (-1.0 * 0.0 * dt) + (-1.0 * self.Q[m][j] * dt) + evapo)
+        took = self.WMA[m][j] if self.wm_flux is not None else 0.0
+        self.WB[m][j] = dvol - (qup * dt + qlat * dt + precip + (-1.0 * took * dt) + (-1.0 * self.Q[m][j] * dt) + evapo)
 
     def _sum(self, j):
         q = self.QR1[j]
@@ -736,6 +772,8 @@ class Twin:
         else:
             qlat = self.QR1[j]
         self.INF[m][j] = qup
+        q_in = qup
+        qup, qlat = self._take(m, j, qup, qlat)
         qf, uh = self.qf_irf[j], self.uh[j]
         if self.length[j] > self.o.min_length_route:
             for k in range(len(uh)):
@@ -752,7 +790,7 @@ class Twin:
             self.Q[m][j] = qf[0] + qlat
             self.V0[m][j] = 0.0
             self.V1[m][j] = 0.0
-        self._wb(m, j, qup, qlat)
+        self._wb(m, j, q_in, qlat)
 
     # -- Euler schemes: kwe_route.f90, dfw_route.f90, mc_route.f90 ---------------------------------
     def _inflow(self, j, m):
@@ -786,7 +824,8 @@ class Twin:
 
     def _kw_dw(self, j, m):
         dt, L = self.o.dt, self.length[j]
-        qup, qlat, head = self._inflow(j, m)
+        q_in, qlat, head = self._inflow(j, m)
+        qup, qlat = self._take(m, j, q_in, qlat)
         mol = self.mol[m][j]
         nm = len(mol)
         if (not head) or self.o.hw_drain_point == 1:
@@ -813,11 +852,12 @@ class Twin:
             self.Q[m][j] = qlat
             self.mol[m][j] = [0.0] * (nm - 1) + [qlat]
             self._dry(j, m)
-        self._wb(m, j, qup, qlat)
+        self._wb(m, j, q_in, qlat)
 
     def _mc(self, j):
         m, dt, L = 4, self.o.dt, self.length[j]
-        qup, qlat, head = self._inflow(j, m)
+        q_in, qlat, head = self._inflow(j, m)
+        qup, qlat = self._take(m, j, q_in, qlat)
         q00, q01 = self.mol[m][j]
         q10 = q11 = 0.0
         if (not head) or self.o.hw_drain_point == 1:
@@ -869,7 +909,7 @@ class Twin:
             self.Q[m][j] = qlat
             self._dry(j, m)
         self.mol[m][j] = [q10, q11]
-        self._wb(m, j, qup, qlat)
+        self._wb(m, j, q_in, qlat)
 
     def _lake(self, j, m):
         dt, net = self.o.dt, self.net
@@ -878,7 +918,11 @@ class Twin:
             qup = qup + self.Q[m][u]
         lt = self.ltype[j]
         lp = lambda name: float(net.lake_params[name][j])
-        if self.itime == 1:
+        follows = "LakeTargVol" in net.lake_params and float(net.lake_params["LakeTargVol"][j]) != 0.0
+        target = self.wm_vol[j] if self.wm_vol is not None else 0.0
+        if self.itime == 1 and self.wm_jump and follows:
+            self.V1[m][j] = target
+        elif self.itime == 1:
             if lt == 0:
                 self.V1[m][j] = float(net.D03_S0[j])
             elif lt == 1:
@@ -903,7 +947,21 @@ class Twin:
                 if self.has_ep:
                     self.evap[j] = v / dt
                 v = 0.0
-        if lt == 0:
+        self.WMA[m][j] = self.wm_flux[j] if self.wm_flux is not None else 0.0
+        if self.wm_flux is not None and self.wm_flux[j] != -9999.0:      # lake_route.f90:176-193
+            f = self.wm_flux[j]
+            if f <= 0 or f * dt <= v:
+                v = v - f * dt
+            else:
+                self.WMA[m][j] = v / dt
+                v = 0.0
+        if follows:                                                       # lake_route.f90:196-203
+            if v < target:
+                q = 0.0
+            else:
+                q = (v - target) / dt
+                v = target
+        elif lt == 0:
             q = 0.0
         elif lt == 1:
             s0, smax = float(net.D03_S0[j]), float(net.D03_MaxStorage[j])
@@ -1049,6 +1107,17 @@ class Twin:
         if len(Q) > MAXQPAR:
             Q, T, X = remove_rch(Q, T, X)
         K = math.sqrt(self.slope[j]) / self.man_n[j]
+        if self.wm_flux is not None and self.wm_flux[j] != -9999.0:
+            # extract_from_rch (kwt_route.f90:351-455): the waves are scaled by the share of the time-step mean flow that is
+            # added (take > 0, its own sign convention) or removed (take < 0); the exit times it sets are redone by kinwav_rch
+            take = self.wm_flux[j]
+            tot = interp_rch(T, Q, t0, t1) * self.width[j]
+            if take > 0.0:
+                Q = [Q[0]] + [q * (1.0 + take / tot) for q in Q[1:]]
+            elif take < 0.0 and abs(take) < tot:
+                Q = [Q[0]] + [q * (1.0 - abs(take) / tot) for q in Q[1:]]
+            else:
+                Q = [0.0] * len(Q)
         rq, rt, rx, rf = kinwav_rch(K, self.length[j], t0, t1, Q[1:], T[1:])
         nq2 = len(rq)
         Q = [Q[0]] + rq
