@@ -40,13 +40,22 @@ MR_DEV double hy_water_height(double area, double b, double zc, double zf, doubl
     if (zc == 0) return area / b;
     return (-b + sqrt(b * b + 4.0 * area * zc)) / (2.0 * zc);
 }
+// What flow_depth / celerity evaluate from the channel alone, i.e. the same for every discharge: computed once per
+// (reach, step) with the reference's expressions and reused by the sub-steps of Muskingum-Cunge (same values, fewer pow calls)
+struct HyChannel { double Abf, Pbf, Bbf, Qbf, nPow06; };
+MR_DEV HyChannel hy_channel(double b, double zc, double S, double n, double zf, double bd) {
+    HyChannel c;
+    c.Abf = hy_area(bd, b, zc, zf, bd); c.Pbf = hy_pwet(bd, b, zc, zf, bd); c.Bbf = hy_btop(bd, b, zc, zf, bd);
+    c.Qbf = c.Abf * mr_pow(c.Abf / c.Pbf, 2.0 / 3.0) * sqrt(S) / n;          // bankfull uniform flow, hydraulic.f90:351
+    c.nPow06 = mr_pow(n, 0.6);                                              // n**0.6 of celerity, hydraulic.f90:466
+    return c;
+}
+
 // normal depth by Newton-Raphson to 0.5 % (flow_depth, :299-420; the schemes always pass bankDepth: floodplain = .true.)
-MR_DEV_NOINLINE double hy_flow_depth(double Q, double b, double zc, double S, double n, double zf, double bd) {
+MR_DEV_NOINLINE double hy_flow_depth(double Q, double b, double zc, double S, double n, double zf, double bd, double Abf, double Pbf, double Bbf, double Qbf) {
     const double c13 = 1.0 / 3.0, c23 = 2.0 / 3.0, c53 = 5.0 / 3.0, c103 = 10.0 / 3.0, err_thresh = 0.005, Qmin = 1.e-50;
     double error = 100.0, depth = 0.0, y0;
     if (!(Q > Qmin)) return 0.0;
-    const double Abf = hy_area(bd, b, zc, zf, bd), Pbf = hy_pwet(bd, b, zc, zf, bd), Bbf = hy_btop(bd, b, zc, zf, bd);
-    const double Qbf = Abf * mr_pow(Abf / Pbf, c23) * sqrt(S) / n;
     if (Q < Qbf) {
         const double t = sqrt(S) / n / Q, Coef1 = t * t * t;
         const double Coef2 = 2 * sqrt(zc * zc + 1.0);
@@ -82,11 +91,11 @@ MR_DEV double hy_friction_slope(double Q, double y, double b, double zc, double 
     const double t = Q * n / A / mr_pow(A / P, 2.0 / 3.0);
     return t * t;
 }
-MR_DEV_NOINLINE double hy_celerity(double Q, double y, double b, double zc, double n, double zf, double bd) {   // celerity, :425-471
+MR_DEV_NOINLINE double hy_celerity(double Q, double y, double b, double zc, double n, double zf, double bd, double nPow06) {   // celerity, :425-471
     if (!(y > 0.0)) return 0.0;
     const double Bt = hy_btop(y, b, zc, zf, bd);
     const double Sf = hy_friction_slope(Q, y, b, zc, n, zf, bd);       // useFrictionSlope = .true.
-    return 5.0 / 3.0 * mr_pow(Sf, 0.3) * mr_pow(Q, 0.4) / mr_pow(Bt, 0.4) / mr_pow(n, 0.6);
+    return 5.0 / 3.0 * mr_pow(Sf, 0.3) * mr_pow(Q, 0.4) / mr_pow(Bt, 0.4) / nPow06;
 }
 MR_DEV_NOINLINE double hy_diffusivity(double Q, double y, double b, double zc, double n, double zf, double bd) { // diffusivity, :476-522
     if (!(y > 0.0)) return 0.0;
@@ -141,8 +150,9 @@ MR_DEV void kw_dw_reach(const DevNet &d, int p, int t) {
         if (L > d.minLengthRoute) {
             const double S = d.rslope[p], n = d.rmann[p], bt = d.rwidth[p], bd = d.rdepth[p], zc = d.sideSlope[p], zf = d.fldpSlope[p];
             const double Qbar = (qup + mol[0] + mol[(size_t)(NM - 2) * N]) / 3.0;
-            const double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
-            const double ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd);
+            const HyChannel hc = hy_channel(bt, zc, S, n, zf, bd);
+            const double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd, hc.Abf, hc.Pbf, hc.Bbf, hc.Qbf);
+            const double ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd, hc.nPow06);
             const double dk = M == M_DW ? hy_diffusivity(fabs(Qbar), depth, bt, zc, n, zf, bd) : 0.0;
             const double wck = 1.0, wdk = 1.0;
             const double dx = L / ((NM - 1) - 1);
@@ -235,8 +245,9 @@ MR_DEV void mc_reach(const DevNet &d, int p, int t) {
             Q10 = qup;
             double Qbar = (Q00 + Q10 + Q01) / 3.0;
             if (Qbar > Qmin) {
-                double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
-                double ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd);
+                const HyChannel hc = hy_channel(bt, zc, S, n, zf, bd);
+                double depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd, hc.Abf, hc.Pbf, hc.Bbf, hc.Qbf);
+                double ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd, hc.nPow06);
                 double Cn = ck * theta, dTsub = dt;
                 int ntSub = 1;
                 if (Cn > 1.0) { ntSub = (int)ceil(dt / L * ck); dTsub = dt / ntSub; }
@@ -247,9 +258,9 @@ MR_DEV void mc_reach(const DevNet &d, int p, int t) {
                     double Qout;
                     Qbar = (Qin + QinPrev + QoutPrev) / 3.0;
                     if (Qbar > Qmin) {
-                        depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd);
+                        depth = hy_flow_depth(fabs(Qbar), bt, zc, S, n, zf, bd, hc.Abf, hc.Pbf, hc.Bbf, hc.Qbf);
                         const double topWidth = hy_btop(depth, bt, zc, zf, bd);
-                        ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd);
+                        ck = hy_celerity(fabs(Qbar), depth, bt, zc, n, zf, bd, hc.nPow06);
                         const double X = 0.5 * (1.0 - Qbar / (topWidth * S * ck * L));
                         Cn = ck * dTsub / L;
                         const double C0 = (-X + Cn * (1 - Y)) / (1 - X + Cn * (1 - Y));
