@@ -23,6 +23,7 @@
 #pragma once
 #include "mr_dev.h"
 #include "mr_kwt.cuh"
+#include "mr_irf.cuh"
 #include "mr_euler.cuh"
 #include "mr_lake.cuh"
 
@@ -179,17 +180,6 @@ __global__ void k_carry_qr(double *qrSer, int N, int Kprev) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// water balance, water_balance.f90:67-87 (no water management, no precipitation/evaporation forcing)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double reach_wb(double v1, double v0, double qup, double qlat, double q, double dt) {
-    const double dVol = v1 - v0;
-    const double Qin = qup * dt, Qlateral = qlat * dt, precip = 0.0, evapo = 0.0;
-    const double Qout = -1.0 * q * dt;
-    const double Qtake = -1.0 * 0.0 * dt;
-    return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
-}
-
-// ------------------------------------------------------------------------------------------------
 // per-reach bodies of the three methods (route_network loop body, main_route.f90:372-390)
 // ------------------------------------------------------------------------------------------------
 template <int M, bool HEAD, bool HY = false>
@@ -205,54 +195,10 @@ __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long 
         d.kwN[b][p] = 1; d.kwNR[b][p] = 0;         // the sentinel particle (-9999) is written once by mr_set_network
         return;
     }
-    if (M == M_SUM) {                                  // accum_runoff.f90:60-75
-        double *Qs = d.qSer[M_SUM] + (size_t)t * N;
-        const int u0 = d.upPtr[p], u1 = d.upPtr[p + 1];
-        double q = d.qrSer[(size_t)(t + 1) * N + p];
-        if (u1 > u0) {
-            double qup = 0.0;
-            for (int m = u0; m < u1; ++m) qup = qup + Qs[d.upIdx[m]];
-            q = q + qup;
-        }
-        Qs[p] = q;
-    } else if (M == M_IRF) {                           // irf_route.f90:82-150,235-262
-        double *Qs = d.qSer[M_IRF] + (size_t)t * N;
-        const int nUps = d.nGood[p], u0 = d.upPtr[p];
-        const double qr1 = d.qrSer[(size_t)(t + 1) * N + p], dt = d.dt;
-        double v1 = d.vol1[M_IRF][p], v0 = v1;
-        double qup = 0.0, qlat = 0.0;
-        if (nUps > 0) {
-            for (int m = 0; m < nUps; ++m) qup = qup + Qs[d.upIdx[u0 + m]];
-            qlat = qr1;
-        } else if (d.hwDrain == 1) { qup = qup + qr1; qlat = 0.0; }
-        else if (d.hwDrain == 2) { qlat = qr1; }
-        d.inflow[M_IRF][p] = qup;
-        const int nt = d.ntdh[p];
-        double *qf = d.qfutIrf + p;
-        const double *uh = d.uh + p;
-        double q;
-        if (d.rlength[p] > d.minLengthRoute) {
-            const int head = (int)(tau % nt);
-            int s = head;
-            for (int k = 0; k < nt; ++k) {
-                qf[(size_t)s * N] = qf[(size_t)s * N] + uh[(size_t)k * N] * qup;
-                if (++s == nt) s = 0;
-            }
-            double q1 = qf[(size_t)head * N];
-            q1 = fmin((fmax(0.0, v1) / dt + qup) * (double)0.999f, q1);      // single-precision literal in irf_route.f90:245
-            v1 = v1 - (q1 - qup) * dt;
-            q = q1 + qlat;
-            qf[(size_t)head * N] = 0.0;
-        } else {                                       // pass-through, irf_route.f90:255-262
-            const int nxt = (int)((tau + 1) % nt);
-            for (int k = 0; k < nt; ++k) qf[(size_t)k * N] = 0.0;
-            qf[(size_t)nxt * N] = qup;                 // logical slot 0 as seen by the next step / by mr_get_state
-            q = qup + qlat;
-            v0 = 0.0; v1 = 0.0;
-        }
-        Qs[p] = q;
-        d.vol0[M_IRF][p] = v0; d.vol1[M_IRF][p] = v1;
-        d.wb[M_IRF][p] = reach_wb(v1, v0, qup, qlat, q, dt);
+    if constexpr (M == M_SUM) {                        // accum_runoff.f90:60-75 (mr_irf.cuh)
+        sum_reach(d, p, t);
+    } else if constexpr (M == M_IRF) {                 // irf_route.f90:82-150,235-262 (mr_irf.cuh)
+        irf_reach(d, p, t, tau);
     } else if constexpr (M == M_KW || M == M_DW) {     // kwe_route.f90 / dfw_route.f90 (mr_euler.cuh)
         kw_dw_reach<M>(d, p, t);
     } else if constexpr (M == M_MC) {                  // mc_route.f90

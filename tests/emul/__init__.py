@@ -53,3 +53,16 @@ def load_lake():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-x", "c++", "-shared", "-fPIC",
                                "-o", _LAKE_SO, _LAKE_SRC])
     return C.CDLL(_LAKE_SO)
+
+
+_IRF_SO = os.path.join(_HERE, "libirf_emul.so")
+_IRF_SRC = os.path.join(_HERE, "irf_emul.cpp")
+_IRF_DEPS = [_IRF_SRC] + [os.path.join(_CSRC, f) for f in ("mr_irf.cuh", "mr_lake.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_uh.h")]
+
+
+def load_irf():
+    """Host build of the accumulation / IRF reach steps (mr_irf.cuh), see irf_emul.cpp."""
+    if not os.path.exists(_IRF_SO) or any(os.path.getmtime(f) > os.path.getmtime(_IRF_SO) for f in _IRF_DEPS):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-x", "c++", "-shared", "-fPIC",
+                               "-o", _IRF_SO, _IRF_SRC])
+    return C.CDLL(_IRF_SO)
