@@ -147,12 +147,21 @@ int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
  * through the same basin2reach as the runoff and enter lake_route when LakeInputOption is 0 or 2 (lake_route.f90:166-174)
  * and the lake water balance.  A routing call without a preceding upload uses exactly zero for both. */
 int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message);
+/* Water management of the NEXT routing call (which must route exactly nSteps steps): flux_wm [nSteps][nRch] = REACH_WM_FLUX,
+ * abstraction (+) / injection (-) in m3/s, -9999 = none at that reach (<is_flux_wm>, the reachflux_in argument of main_route,
+ * main_route.f90:110-116); vol_wm [nSteps][nRch] = REACH_WM_VOL, the target volume of the lakes flagged with the lake parameter
+ * "LakeTargVol" (<is_vol_wm>, :117-123); volJumpStart = <is_vol_wm_jumpstart>.  Either array may be NULL (= that option off).
+ * Caller's reach order.  The abstraction cascade of irf_rch and of the Euler schemes (irf_route.f90:114-142) and the lake
+ * fluxes / target volumes (lake_route.f90:137-139,176-203) run on the device; extract_from_rch of KWT does not: fluxes with
+ * route method 2 are refused. */
+int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *vol_wm, int volJumpStart, char *message);
 /* Per-reach parameters of the parametric lake models beyond Doll-2003, by their name in RCHPRP (dataTypes.f90:202-213):
  * HYP_E_emr, HYP_E_lim, HYP_E_min, HYP_E_zero, HYP_Qrate_emr, HYP_Erate_emr, HYP_Qrate_prim, HYP_Qrate_amp, HYP_Qrate_phs,
  * HYP_prim_F, HYP_A_avg, HYP_Qsim_mode, and (dataTypes.f90:215-254) H06_Smax, H06_alpha, H06_envfact, H06_S_ini, H06_c1, H06_c2,
  * H06_exponent, H06_denominator, H06_c_compare, H06_frac_Sdead, H06_E_rel_ini, H06_I_Jan..H06_I_Dec, H06_D_Jan..H06_D_Dec,
  * H06_purpose, H06_I_mem_F, H06_D_mem_F, H06_I_mem_L, H06_D_mem_L (integers and logicals as doubles); values[n = nRch] in the
- * caller's reach order.  Call BEFORE mr_set_network (like mr_set_ghosts).  lakeModelType 3 (HYPE) needs all HYP_*, lakeModelType
+ * caller's reach order; "LakeTargVol" (NETOPO%LakeTargVol, 0/1) flags the lakes that follow the target volume of mr_upload_wm.
+ * Call BEFORE mr_set_network (like mr_set_ghosts).  lakeModelType 3 (HYPE) needs all HYP_*, lakeModelType
  * 2 (Hanasaki 2006) all H06_* (the demand memory H06_D_mem_* belongs to water management and is not used). */
 int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values, char *message);
 /* Datetime of the first simulation step (simDatetime(1) at iTime = 1, init_model_data.f90) and the calendar (0 standard /

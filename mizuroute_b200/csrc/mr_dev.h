@@ -59,6 +59,9 @@ struct DevNet {
     struct H06Lake *h06;            // Hanasaki-2006 reservoirs by lake slot (nullptr = none in this domain)
     double *h06Mem;
     const int *stepMonth, *stepDay; // month / day of month of every step of the batch [kmax], with stepDoy
+    // water management of the batch (mr_upload_wm; nullptr = off): abstraction (+) / injection (-) and target lake volume per
+    // reach and step [kmax][nRch] in stage order, -9999 = none; lakes that follow the target volume; volume jump start
+    const double *wmFlux, *wmVol; const unsigned char *lakeTargVol; int volJumpStart;
     int noleap;                     // calendar given with mr_set_sim_start
     int lastK;                      // steps of the previous batch (its last REACH_Q row is still in qSer)
     const int *stepDoy;
@@ -98,6 +101,39 @@ MR_DEV_NOINLINE void raise(int *err, int code, int p, int site) {
 #else
     if (err[0] == 0) { err[0] = code; err[1] = p; err[2] = site; }
 #endif
+}
+
+// Water abstraction (+) / injection (-) of a river reach (irf_route.f90:114-142 = kwe_route.f90:118-146 = mc_route.f90:118-146 =
+// dfw_route.f90:122-150): taken from the storage first, then from the upstream inflow, then from the lateral flow.  Returns
+// REACH_WM_FLUX_actual (it starts as the demand -- the missing value included, as in the reference).
+MR_DEV double wm_cascade(double want, double dt, double &v1, double &qup, double &qlat) {
+    double actual = want;
+    if (want == -9999.0) return actual;                // realMissing: no water management at this reach
+    double Qabs = want;
+    if (Qabs > 0) {
+        if (v1 / dt > Qabs) {
+            v1 = v1 - Qabs * dt;
+        } else {
+            Qabs = Qabs - v1 / dt;
+            v1 = 0.0;
+            if (qup > Qabs) {
+                qup = qup - Qabs;
+            } else {
+                Qabs = Qabs - qup;
+                qup = 0.0;
+                if (qlat > Qabs) {
+                    qlat = qlat - Qabs;
+                } else {
+                    Qabs = Qabs - qlat;
+                    qlat = 0.0;
+                    actual = want - Qabs;
+                }
+            }
+        }
+    } else {
+        qlat = qlat - Qabs;
+    }
+    return actual;
 }
 
 // one out-of-line copy of pow(): its inlined body is ~250 instructions per call site

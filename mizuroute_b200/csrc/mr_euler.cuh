@@ -122,11 +122,11 @@ MR_DEV bool euler_inflow(const DevNet &d, int p, int t, double &qup, double &qla
 }
 
 // reach_wb of mr_kernels.cuh (water_balance.f90:67-87), repeated here so that this header stands alone for the host build
-MR_DEV double euler_wb(double v1, double v0, double qup, double qlat, double q, double dt) {
+MR_DEV double euler_wb(double v1, double v0, double qup, double qlat, double q, double dt, double took = 0.0) {
     const double dVol = v1 - v0;
     const double Qin = qup * dt, Qlateral = qlat * dt, precip = 0.0, evapo = 0.0;
     const double Qout = -1.0 * q * dt;
-    const double Qtake = -1.0 * 0.0 * dt;
+    const double Qtake = -1.0 * took * dt;
     return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
 }
 
@@ -134,7 +134,7 @@ MR_DEV double euler_wb(double v1, double v0, double qup, double qlat, double q, 
 // solve_ade (advection_diffusion.f90:19-262, central differences, Neumann outlet, wck = wdk = 1) by the Thomas algorithm.
 // The tridiagonal coefficients are constants by row range, so only the forward-sweep pivots D and right-hand sides b1
 // are kept; every element is computed with the reference's expression.
-template <int M>
+template <int M, bool EXT = false>
 MR_DEV void kw_dw_reach(const DevNet &d, int p, int t) {
     static_assert(M == M_KW || M == M_DW, "kinematic / diffusive wave");
     constexpr int NM = NMOL<M>;
@@ -145,6 +145,9 @@ MR_DEV void kw_dw_reach(const DevNet &d, int p, int t) {
     double *mol = d.mol[M] + p;                                    // node k at mol[k * N]
     double v1 = d.vol1[M][p], v0 = v1, q, flood = 0.0, ele = 0.0;
     d.inflow[M][p] = qup;
+    const double qin = qup;                                        // the solver sees Qupstream_mod, the water balance Qupstream
+    double took = 0.0;
+    if (EXT && d.wmFlux) took = wm_cascade(d.wmFlux[(size_t)t * N + p], dt, v1, qup, qlat);
     const double L = d.rlength[p];
     if (!isHW || d.hwDrain == 1) {
         if (L > d.minLengthRoute) {
@@ -223,10 +226,11 @@ MR_DEV void kw_dw_reach(const DevNet &d, int p, int t) {
     }
     d.qSer[M][(size_t)t * N + p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
-    d.wb[M][p] = euler_wb(v1, v0, qup, qlat, q, dt);
+    d.wb[M][p] = euler_wb(v1, v0, qin, qlat, q, dt, took);
 }
 
 // mc_rch + muskingum_cunge (mc_route.f90:45-418), sub-stepping when the Courant number exceeds one
+template <bool EXT = false>
 MR_DEV void mc_reach(const DevNet &d, int p, int t) {
     constexpr int M = M_MC;
     const int N = d.nRch;
@@ -237,6 +241,9 @@ MR_DEV void mc_reach(const DevNet &d, int p, int t) {
     const double Q00 = mol[0], Q01 = mol[N];
     double Q10, Q11, q, v1 = d.vol1[M][p], v0 = v1, flood = 0.0, ele = 0.0;
     d.inflow[M][p] = qup;
+    const double qin = qup;
+    double took = 0.0;
+    if (EXT && d.wmFlux) took = wm_cascade(d.wmFlux[(size_t)t * N + p], dt, v1, qup, qlat);
     const double L = d.rlength[p];
     if (!isHW || d.hwDrain == 1) {
         if (L > d.minLengthRoute) {
@@ -300,7 +307,7 @@ MR_DEV void mc_reach(const DevNet &d, int p, int t) {
     mol[0] = Q10; mol[N] = Q11;
     d.qSer[M][(size_t)t * N + p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
-    d.wb[M][p] = euler_wb(v1, v0, qup, qlat, q, dt);
+    d.wb[M][p] = euler_wb(v1, v0, qin, qlat, q, dt, took);
 }
 
 }  // namespace mr

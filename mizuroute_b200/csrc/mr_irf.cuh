@@ -8,12 +8,12 @@
 
 namespace mr {
 
-// water balance, water_balance.f90:67-87 (no water management, no precipitation / evaporation: river reaches)
-MR_DEV double reach_wb(double v1, double v0, double qup, double qlat, double q, double dt) {
+// water balance, water_balance.f90:67-87 (river reaches: no precipitation / evaporation); took = REACH_WM_FLUX_actual
+MR_DEV double reach_wb(double v1, double v0, double qup, double qlat, double q, double dt, double took = 0.0) {
     const double dVol = v1 - v0;
     const double Qin = qup * dt, Qlateral = qlat * dt, precip = 0.0, evapo = 0.0;
     const double Qout = -1.0 * q * dt;
-    const double Qtake = -1.0 * 0.0 * dt;
+    const double Qtake = -1.0 * took * dt;
     return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
 }
 
@@ -32,6 +32,8 @@ MR_DEV void sum_reach(const DevNet &d, int p, int t) {
 
 // The future-flow series QFUTURE_IRF of a reach is a ring of ntdh slots, slot-major in HBM; logical slot k of step tau
 // lives at physical slot (tau + k) mod ntdh, so the eoshift of the reference is the head moving on.
+// EXT: the instantiation for domains with water management (see lake_reach in mr_lake.cuh for why it is a template flag)
+template <bool EXT = false>
 MR_DEV void irf_reach(const DevNet &d, int p, int t, long long tau) {
     const int N = d.nRch;
     double *Qs = d.qSer[M_IRF] + (size_t)t * N;
@@ -45,6 +47,9 @@ MR_DEV void irf_reach(const DevNet &d, int p, int t, long long tau) {
     } else if (d.hwDrain == 1) { qup = qup + qr1; qlat = 0.0; }
     else if (d.hwDrain == 2) { qlat = qr1; }
     d.inflow[M_IRF][p] = qup;
+    const double qin = qup;                            // the water balance sees the inflow before the abstraction
+    double took = 0.0;
+    if (EXT && d.wmFlux) took = wm_cascade(d.wmFlux[(size_t)t * N + p], dt, v1, qup, qlat);
     const int nt = d.ntdh[p];
     double *qf = d.qfutIrf + p;
     const double *uh = d.uh + p;
@@ -70,7 +75,7 @@ MR_DEV void irf_reach(const DevNet &d, int p, int t, long long tau) {
     }
     Qs[p] = q;
     d.vol0[M_IRF][p] = v0; d.vol1[M_IRF][p] = v1;
-    d.wb[M_IRF][p] = reach_wb(v1, v0, qup, qlat, q, dt);
+    d.wb[M_IRF][p] = reach_wb(v1, v0, qin, qlat, q, dt, took);
 }
 
 }  // namespace mr

@@ -198,11 +198,11 @@ __device__ __forceinline__ void route_reach(const DevNet &d, int p, int t, long 
     if constexpr (M == M_SUM) {                        // accum_runoff.f90:60-75 (mr_irf.cuh)
         sum_reach(d, p, t);
     } else if constexpr (M == M_IRF) {                 // irf_route.f90:82-150,235-262 (mr_irf.cuh)
-        irf_reach(d, p, t, tau);
+        irf_reach<HY>(d, p, t, tau);
     } else if constexpr (M == M_KW || M == M_DW) {     // kwe_route.f90 / dfw_route.f90 (mr_euler.cuh)
-        kw_dw_reach<M>(d, p, t);
+        kw_dw_reach<M, HY>(d, p, t);
     } else if constexpr (M == M_MC) {                  // mc_route.f90
-        mc_reach(d, p, t);
+        mc_reach<HY>(d, p, t);
     }
 }
 

@@ -30,12 +30,12 @@ MR_LAKE_FN double lake_basin2reach(const DevNet &d, int p, const double *flux) {
 }
 
 // comp_reach_wb with lakeFlag (water_balance.f90:61-87): precipitation and evaporation enter the balance
-MR_LAKE_FN double lake_wb(double v1, double v0, double qup, double qlat, double q, double dt, double pr, double ev, bool ep) {
+MR_LAKE_FN double lake_wb(double v1, double v0, double qup, double qlat, double q, double dt, double pr, double ev, bool ep, double took = 0.0) {
     const double dVol = v1 - v0;
     const double Qin = qup * dt, Qlateral = qlat * dt;
     const double precip = ep ? pr * dt : 0.0;
     const double Qout = -1.0 * q * dt;
-    const double Qtake = -1.0 * 0.0 * dt;
+    const double Qtake = -1.0 * took * dt;
     const double evapo = ep ? -1.0 * ev * dt : 0.0;
     return dVol - (Qin + Qlateral + precip + Qtake + Qout + evapo);
 }
@@ -124,6 +124,12 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     for (int m = u0; m < u1; ++m) qup = qup + Qs[d.upIdx[m]];
     const int type = d.lakeType[p];
     double v1 = d.vol1[M][p];
+    // water management (HY instantiation only): the lake follows a target volume / loses or gains a flux
+    const bool follows = HY && d.lakeTargVol && d.lakeTargVol[p];
+    const double target = (HY && d.wmVol) ? d.wmVol[(size_t)t * N + p] : 0.0;      // REACH_WM_VOL, 0 when is_vol_wm is off
+    if (tau == 0 && follows && d.volJumpStart) {       // lake_route.f90:137-139
+        v1 = target;
+    } else
     if (tau == 0) {                                    // iTime==1 cold start, lake_route.f90:139-157
         if (type == MR_LAKE_ENDORHEIC) v1 = d.d03S0[p];
         else if (type == MR_LAKE_DOLL03) v1 = d.d03MaxS[p];
@@ -155,7 +161,21 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
             v1 = 0.0;
         }
     }
+    double took = 0.0;                                 // REACH_WM_FLUX_actual
+    if (HY && d.wmFlux) {                              // lake_route.f90:176-193
+        const double f = d.wmFlux[(size_t)t * N + p];
+        took = f;
+        if (f != -9999.0) {
+            if (f <= 0) v1 = v1 - f * dt;
+            else if (f * dt <= v1) v1 = v1 - f * dt;
+            else { took = v1 / dt; v1 = 0.0; }
+        }
+    }
     double q;
+    if (follows) {                                     // lake_route.f90:196-203
+        if (v1 < target) q = 0;
+        else { q = (v1 - target) / dt; v1 = target; }
+    } else
     if (type == MR_LAKE_ENDORHEIC) {
         q = 0.0;
     } else if (type == MR_LAKE_DOLL03) {
@@ -183,7 +203,7 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     } else { raise(d.err, 20, p, E_LAKE_TYPE); return; }
     Qs[p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1;
-    d.wb[M][p] = lake_wb(v1, v0, qup, qr1, q, dt, pr, ev, ep);
+    d.wb[M][p] = lake_wb(v1, v0, qup, qr1, q, dt, pr, ev, ep, took);
 }
 
 }  // namespace mr

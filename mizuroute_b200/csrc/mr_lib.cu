@@ -66,6 +66,11 @@ struct mr_handle_s {
     std::map<std::string, std::vector<double>> lakeParams;
     bool hasStart = false, hasHype = false, hasH06 = false; int startY = 0, startM = 1, startD = 1, noleap = 0; double startSec = 0.0;
     int *dStepDoy = nullptr; std::vector<int> stepDoyHost;      // [3][max_batch]: day of year, month, day of month
+    // water management (mr_upload_wm): per-reach flux / target volume rows of the next batch, stage order; lakes that follow
+    // the target volume (lake parameter LakeTargVol)
+    int wmSteps = 0, wmJumpStart = 0; bool wmHasFlux = false, wmHasVol = false, wmActive = false;
+    double *dWmFlux = nullptr, *dWmVol = nullptr; unsigned char *dLakeTargVol = nullptr;
+    std::vector<double> wmStage;
     // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
     int nLake = 0, lakeForcingSteps = 0;
     int *dLakePos = nullptr;
@@ -174,10 +179,10 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     if constexpr (M == M_KWT) {
         int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        if (h->hasHype || h->hasH06) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
     } else {
-        if (h->hasHype || h->hasH06) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
     h->launchesLast++;
@@ -206,6 +211,18 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     if (h->lakeForcingSteps && h->lakeForcingSteps != K) {      // refused before anything is launched
         h->lakeForcingSteps = 0;
         return fail(message, 1, std::string(where) + "/lake forcing was uploaded for a different number of steps");
+    }
+    if (h->wmSteps && h->wmSteps != K) {
+        h->wmSteps = 0;
+        return fail(message, 1, std::string(where) + "/water management was uploaded for a different number of steps");
+    }
+    d.wmFlux = d.wmVol = nullptr; d.volJumpStart = 0; d.lakeTargVol = h->dLakeTargVol;
+    h->wmActive = false;
+    if (h->wmSteps) {                                   // water management rows uploaded for this batch
+        h->wmSteps = 0;
+        if (h->wmHasFlux && h->on[M_KWT]) return fail(message, 20, std::string(where) + "/water-management fluxes with KWT (extract_from_rch) are not on the device");
+        d.wmFlux = h->wmHasFlux ? h->dWmFlux : nullptr; d.wmVol = h->wmHasVol ? h->dWmVol : nullptr; d.volJumpStart = h->wmJumpStart;
+        h->wmActive = true;
     }
     d.stepDoy = d.stepMonth = d.stepDay = nullptr;
     d.lastK = h->lastK; d.noleap = h->noleap;
@@ -259,7 +276,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
-            const bool hy = h->hasHype || h->hasH06;  // HYPE / Hanasaki reservoirs in this domain: the instantiation that knows them
+            const bool hy = h->hasHype || h->hasH06 || h->wmActive;  // parametric reservoirs or water management: the instantiation that knows them
             switch (h->opt.route_methods[r]) {
                 case M_SUM: if (hy) k_headwater<M_SUM, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_SUM, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_IRF: if (hy) k_headwater<M_IRF, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_IRF, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
@@ -394,6 +411,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->dRunoffSlot[0] = h->dRunoffSlot[1] = nullptr; h->freeRec[0] = h->freeRec[1] = false; h->d2hRec = false; h->asyncSlot = 0;
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
     h->dStepDoy = nullptr; h->hasHype = false; h->hasH06 = false;
+    h->wmSteps = 0; h->wmActive = false; h->dWmFlux = h->dWmVol = nullptr; h->dLakeTargVol = nullptr;
     h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -550,6 +568,11 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
             AL(d.h06Mem, (size_t)(memDoubles > 0 ? memDoubles : 1));
         }
         if (h->hasHype || h->hasH06) AL(h->dStepDoy, (size_t)3 * KB);
+        if (const std::vector<double> *tv = par("LakeTargVol")) {          // NETOPO%LakeTargVol: the lake follows REACH_WM_VOL
+            std::vector<unsigned char> f(N, 0);
+            for (int p = 0; p < N; ++p) f[p] = (*tv)[T.pos2rch[p]] != 0.0 ? 1 : 0;
+            e = dev_upload(h, &h->dLakeTargVol, f, where, message); if (e) return e;
+        }
     }
     AL(d.err, 4);
     d.expSlot = d.impSlot = nullptr; d.expBuf = nullptr; d.impBuf = nullptr;
@@ -607,7 +630,8 @@ int mr_set_lake_param(mr_handle h, const char *name, int n, const double *values
     static const char *known[] = {"HYP_E_emr", "HYP_E_lim", "HYP_E_min", "HYP_E_zero", "HYP_Qrate_emr", "HYP_Erate_emr", "HYP_Qrate_prim",
                                   "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode",
                                   "H06_Smax", "H06_alpha", "H06_envfact", "H06_S_ini", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
-                                  "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini", "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L"};
+                                  "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini", "H06_purpose", "H06_I_mem_F", "H06_D_mem_F", "H06_I_mem_L", "H06_D_mem_L",
+                                  "LakeTargVol"};
     bool ok = !std::strncmp(name, "H06_I_", 6) || !std::strncmp(name, "H06_D_", 6);      // H06_I_Jan .. H06_D_Dec (and the mem_* above)
     for (const char *k : known) ok = ok || !std::strcmp(k, name);
     if (!ok) return fail(message, 20, std::string("mr_set_lake_param/unknown or unsupported lake parameter ") + name);
@@ -620,6 +644,29 @@ int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay,
     if (!h) return fail(message, 1, "mr_set_sim_start/null handle");
     if (month < 1 || month > 12 || day < 1 || day > 31 || secOfDay < 0.0 || secOfDay >= 86400.0) return fail(message, 1, "mr_set_sim_start/invalid date");
     h->hasStart = true; h->startY = year; h->startM = month; h->startD = day; h->startSec = secOfDay; h->noleap = noleap ? 1 : 0;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *vol_wm, int volJumpStart, char *message) {
+    const char *where = "mr_upload_wm";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!flux_wm && !vol_wm) return fail(message, 1, "mr_upload_wm/neither fluxes nor target volumes given");
+    const size_t N = (size_t)h->d.nRch, KB = (size_t)h->opt.max_batch;
+    const Topology &T = h->topo;
+    h->wmStage.resize((size_t)nSteps * N);
+    for (int w = 0; w < 2; ++w) {
+        const double *src = w == 0 ? flux_wm : vol_wm;
+        double **dst = w == 0 ? &h->dWmFlux : &h->dWmVol;
+        if (!src) continue;
+        if (!*dst) { e = dev_alloc(h, dst, KB * N, where, message); if (e) return e; }
+        for (int t = 0; t < nSteps; ++t)                  // caller's reach order -> stage order
+            for (size_t p = 0; p < N; ++p) h->wmStage[(size_t)t * N + p] = src[(size_t)t * N + T.pos2rch[p]];
+        CU(cudaMemcpy(*dst, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
+    }
+    h->wmHasFlux = flux_wm != nullptr; h->wmHasVol = vol_wm != nullptr && h->opt.is_lake_sim;      // REACH_WM_VOL is 0 without is_lake_sim
+    h->wmJumpStart = volJumpStart ? 1 : 0;
+    h->wmSteps = nSteps;
     put_msg(message, "");
     return 0;
 }

@@ -135,6 +135,15 @@ class Router:
         self._check(self._L.mr_step_batch_async(self._h, K, self.TSEC[0], rp, op, self._msg))
         self._advance(K)
 
+    def upload_wm(self, flux_wm=None, vol_wm=None, vol_jumpstart: bool = False):
+        """Water management [K, nRch] of the NEXT routing call (mr_upload_wm): abstraction (+) / injection (-) fluxes, -9999 =
+        none, and / or target volumes of the lakes flagged by the lake parameter "LakeTargVol"."""
+        f = None if flux_wm is None else np.ascontiguousarray(np.atleast_2d(flux_wm), dtype=np.float64)
+        v = None if vol_wm is None else np.ascontiguousarray(np.atleast_2d(vol_wm), dtype=np.float64)
+        k = (f if f is not None else v).shape[0]
+        assert all(a is None or a.shape == (k, self.nRch) for a in (f, v))
+        self._check(self._L.mr_upload_wm(self._h, int(k), _ptr(f, C.c_double), _ptr(v, C.c_double), int(bool(vol_jumpstart)), self._msg))
+
     def upload_lake_forcing(self, evapo, precip):
         """Lake evaporation / precipitation [K, nHRU] (runoff units, river-network HRU order) of the NEXT routing call, which
         must route K steps (mr_upload_lake_forcing; basinEvapo_in / basinPrecip_in of main_route)."""

@@ -17,9 +17,11 @@ using namespace mr;
 
 template <int M>
 static void run_method(DevNet &d, const Topology &T, int nSteps) {
+    const bool ext = d.wmFlux != nullptr;                   // water management: the EXT instantiations, as route_device picks them
     for (int t = 0; t < nSteps; ++t)
         for (int p = 0; p < d.nRch; ++p) {                  // stage order: upstream before downstream
-            if constexpr (M == M_MC) mc_reach(d, p, t); else kw_dw_reach<M>(d, p, t);
+            if (ext) { if constexpr (M == M_MC) mc_reach<true>(d, p, t); else kw_dw_reach<M, true>(d, p, t); }
+            else { if constexpr (M == M_MC) mc_reach<false>(d, p, t); else kw_dw_reach<M, false>(d, p, t); }
         }
 }
 
@@ -27,6 +29,7 @@ extern "C" int euler_emul_run(int method, int nRch, int nHRU, const int *segId, 
                               const double *length, const double *slope, double mann_n, double wscale, double dt, int hw_drain_point,
                               double min_length_route, int floodplain, int nSteps,
                               const double *qr /* [nSteps+1][nRch] BASIN_QR(1) before step 0 and after every step, caller order */,
+                              const double *wm_flux /* [nSteps][nRch] caller order, or NULL */,
                               double *q_out /* [nSteps][nRch] REACH_Q */, double *vol_out /* [nRch] REACH_VOL(1) */,
                               double *mol_out /* [nRch][n_molecule] */, char *msg) {
     Topology T;
@@ -51,6 +54,12 @@ extern "C" int euler_emul_run(int method, int nRch, int nHRU, const int *segId, 
     d.rdepth = rdep.data(); d.sideSlope = zc.data(); d.fldpSlope = zf.data(); d.rstorage = rstor.data();
     d.qrSer = qrSer.data(); d.qSer[method] = qSer.data(); d.inflow[method] = inflow.data(); d.vol0[method] = vol0.data(); d.vol1[method] = vol1.data();
     d.wb[method] = wb.data(); d.mol[method] = mol.data(); d.floodVol[method] = flood.data(); d.reachEle[method] = ele.data();
+    std::vector<double> fS;
+    if (wm_flux) {                                          // stage order, as mr_upload_wm
+        fS.resize((size_t)nSteps * N);
+        for (int t = 0; t < nSteps; ++t) for (int p = 0; p < N; ++p) fS[(size_t)t * N + p] = wm_flux[(size_t)t * N + T.pos2rch[p]];
+        d.wmFlux = fS.data();
+    }
     if (method == M_KW) run_method<M_KW>(d, T, nSteps); else if (method == M_MC) run_method<M_MC>(d, T, nSteps); else run_method<M_DW>(d, T, nSteps);
     for (int t = 0; t < nSteps; ++t) for (int r = 0; r < N; ++r) q_out[(size_t)t * N + r] = qSer[(size_t)t * N + T.rch2pos[r]];
     for (int r = 0; r < N; ++r) {

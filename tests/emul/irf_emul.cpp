@@ -21,6 +21,8 @@ extern "C" int irf_emul_run(int nRch, int nHRU, const int *segId, const int *dow
                             const double *coef, const double *pw, const double *s0, double wscale, double dt, double velo, double diff,
                             int hw_drain_point, double min_length_route, int lakeInputOption, int nSteps,
                             const double *qr /* [nSteps+1][nRch] BASIN_QR(1), caller order */,
+                            const double *wm_flux, const double *wm_vol /* [nSteps][nRch] caller order, or NULL */, const double *targ /* [nRch] 0/1 or NULL */,
+                            int jumpStart,
                             double *q_sum /* [nSteps][nRch] */, double *q_irf /* [nSteps][nRch] */, double *vol_out, double *wb_out,
                             double *qfut_out /* [nRch][maxtdh] logical order */, int *maxtdh_out, char *msg) {
     Topology T;
@@ -54,10 +56,21 @@ extern "C" int irf_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     d.lakeSlot = slot.data(); d.nLake = nLake;
     d.qrSer = qrSer.data(); d.qSer[M_SUM] = qS.data(); d.qSer[M_IRF] = qI.data(); d.inflow[M_IRF] = inflow.data();
     d.vol0[M_IRF] = vol0.data(); d.vol1[M_IRF] = vol1.data(); d.wb[M_IRF] = wb.data(); d.err = err;
+    // water management: rows permuted to stage order as mr_upload_wm does; the EXT instantiations are used then
+    const bool ext = wm_flux || wm_vol;
+    std::vector<double> fS, vS; std::vector<unsigned char> tg(N, 0);
+    auto stage = [&](const double *src, std::vector<double> &dst) {
+        dst.resize((size_t)nSteps * N);
+        for (int t = 0; t < nSteps; ++t) for (int p = 0; p < N; ++p) dst[(size_t)t * N + p] = src[(size_t)t * N + T.pos2rch[p]]; };
+    if (wm_flux) { stage(wm_flux, fS); d.wmFlux = fS.data(); }
+    if (wm_vol && islake) { stage(wm_vol, vS); d.wmVol = vS.data(); }
+    if (targ) { for (int p = 0; p < N; ++p) tg[p] = targ[T.pos2rch[p]] != 0.0; d.lakeTargVol = tg.data(); }
+    d.volJumpStart = jumpStart;
     for (int t = 0; t < nSteps; ++t)
         for (int p = 0; p < N; ++p) {                        // route_reach<M_SUM>, route_reach<M_IRF>: stage order
             sum_reach(d, p, t);
-            if (flags[p] & FLAG_LAKE) lake_reach<M_IRF, false>(d, p, t, (long long)t); else irf_reach(d, p, t, (long long)t);
+            if (ext) { if (flags[p] & FLAG_LAKE) lake_reach<M_IRF, true>(d, p, t, (long long)t); else irf_reach<true>(d, p, t, (long long)t); }
+            else if (flags[p] & FLAG_LAKE) lake_reach<M_IRF, false>(d, p, t, (long long)t); else irf_reach<false>(d, p, t, (long long)t);
             if (err[0]) { std::snprintf(msg, 256, "ierr %d at position %d site %d step %d", err[0], err[1], err[2], t); return err[0]; }
         }
     for (int t = 0; t < nSteps; ++t) for (int r = 0; r < N; ++r) {

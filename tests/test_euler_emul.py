@@ -43,7 +43,7 @@ def _run(kw, method, noise_seed=0):
     ierr = L.euler_emul_run(C.c_int(method), C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int),
                             p(net.hruSegId, C.c_int), p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
                             C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(opts.hw_drain_point),
-                            C.c_double(opts.min_length_route), C.c_int(int(fp)), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double),
+                            C.c_double(opts.min_length_route), C.c_int(int(fp)), C.c_int(K), p(qr, C.c_double), None, p(qe, C.c_double),
                             p(ve, C.c_double), p(me, C.c_double), msg)
     assert ierr == 0, msg.value.decode()
     return o, qo, qe, ve, me
@@ -101,7 +101,7 @@ def test_dry_channels_then_a_flood_pulse(method):
     ierr = L.euler_emul_run(C.c_int(method), C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int),
                             p(net.hruSegId, C.c_int), p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
                             C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(opts.hw_drain_point),
-                            C.c_double(opts.min_length_route), C.c_int(0), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double),
+                            C.c_double(opts.min_length_route), C.c_int(0), C.c_int(K), p(qr, C.c_double), None, p(qe, C.c_double),
                             p(ve, C.c_double), p(me, C.c_double), msg)
     assert ierr == 0, msg.value.decode()
     assert np.array_equal(qe, qo) and np.array_equal(me, o.molecule(method))
@@ -109,3 +109,37 @@ def test_dry_channels_then_a_flood_pulse(method):
     for k in range(K):
         t.step(ro[k])
     assert np.array_equal(np.array(t.Q[method]), qo[-1])
+
+
+@pytest.mark.parametrize("method", [orc.M_KW, orc.M_MC, orc.M_DW], ids=["kw", "mc", "dw"])
+def test_water_management_cascade_in_the_euler_schemes(method):
+    """The abstraction / injection cascade of kw_dw_reach<M, EXT> / mc_reach<EXT> (kwe_route.f90:118-146 and siblings) against
+    Oracle.set_wm, bit for bit -- REACH_Q, REACH_VOL(1) and the molecules."""
+    net, params, opts, ro = case("conus", n=700, seed=3, dt=3600.0, route_opt=str(method), steps=24)
+    K = ro.shape[0]
+    rng = np.random.default_rng(5)
+    flux = np.full((K, net.nRch), -9999.0)
+    pick = rng.random((K, net.nRch)) < 0.4
+    flux[pick] = rng.choice([-1.0, 1.0], pick.sum()) * rng.lognormal(np.log(0.02), 1.5, pick.sum())
+    o = Oracle(net, params, opts)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.set_wm(flux[t])
+        o.step(ro[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, method)
+    L = emul.load_euler()
+    nm = orc.N_MOLECULE[method]
+    qe = np.empty((K, net.nRch)); ve = np.empty(net.nRch); me = np.empty((net.nRch, nm))
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(ct))
+    ierr = L.euler_emul_run(C.c_int(method), C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int),
+                            p(net.hruSegId, C.c_int), p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
+                            C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(opts.hw_drain_point),
+                            C.c_double(opts.min_length_route), C.c_int(0), C.c_int(K), p(qr, C.c_double), p(flux, C.c_double),
+                            p(qe, C.c_double), p(ve, C.c_double), p(me, C.c_double), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qe, qo)
+    assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, method))
+    assert np.array_equal(me, o.molecule(method))
+    assert not np.array_equal(qo, Oracle(net, params, opts).run(ro)[0])

@@ -47,7 +47,7 @@ def test_sum_and_irf_device_source_match_oracle_bit_for_bit(kw):
                           p(net.D03_Power if lake else zeros, C.c_double), p(net.D03_S0 if lake else zeros, C.c_double),
                           C.c_double(params.wscale), C.c_double(opts.dt), C.c_double(params.velo), C.c_double(params.diff),
                           C.c_int(opts.hw_drain_point), C.c_double(opts.min_length_route), C.c_int(opts.LakeInputOption), C.c_int(K),
-                          p(qr, C.c_double), p(qs, C.c_double), p(qi, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(qf, C.c_double),
+                          p(qr, C.c_double), None, None, None, C.c_int(0), p(qs, C.c_double), p(qi, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(qf, C.c_double),
                           C.byref(mx), msg)
     assert ierr == 0, msg.value.decode()
     assert np.array_equal(qs, qo[0])
@@ -59,3 +59,49 @@ def test_sum_and_irf_device_source_match_oracle_bit_for_bit(kw):
     assert mx.value == int(np.diff(ptr).max())
     for r in range(net.nRch):
         assert np.array_equal(qf[r, :ptr[r + 1] - ptr[r]], flat[ptr[r]:ptr[r + 1]]), r
+
+
+@pytest.mark.parametrize("lakes", [0, 9])
+def test_water_management_device_source_matches_oracle(lakes):
+    """mr_upload_wm path: the abstraction cascade of irf_reach<EXT> and, with lakes, the lake fluxes, the target volumes of
+    the lakes flagged LakeTargVol and the volume jump start in lake_reach<M, EXT> -- against Oracle.set_wm, bit for bit."""
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0, route_opt="01", steps=12, lakes=lakes)
+    K = ro.shape[0]
+    rng = np.random.default_rng(11)
+    lake = bool(lakes)
+    targ = None
+    if lake:
+        lk = np.flatnonzero(net.islake == 1)
+        net.lake_params = {"LakeTargVol": np.isin(np.arange(net.nRch), lk[:3]).astype(np.float64)}
+        targ = net.lake_params["LakeTargVol"]
+    flux = np.full((K, net.nRch), -9999.0)
+    pick = rng.random((K, net.nRch)) < 0.4
+    flux[pick] = rng.choice([-1.0, 1.0], pick.sum()) * rng.lognormal(np.log(0.05), 1.5, pick.sum())
+    vol = np.where(net.islake == 1, rng.uniform(1e6, 5e7, (K, net.nRch)), 0.0) if lake else None
+    o = Oracle(net, params, opts)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.set_wm(flux[t], None if vol is None else vol[t], vol_jumpstart=True)
+        o.step(ro[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, orc.M_IRF)
+    L = emul.load_irf()
+    qs = np.empty((K, net.nRch)); qi = np.empty((K, net.nRch)); ve = np.empty(net.nRch); we = np.empty(net.nRch)
+    qf = np.empty((net.nRch, 240)); mx = C.c_int(0)
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.POINTER(ct))
+    zeros = np.zeros(net.nRch)
+    ierr = L.irf_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
+                          p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
+                          p(net.islake if lake else None, C.c_int), p(net.lakeModelType if lake else None, C.c_int),
+                          p(net.D03_MaxStorage if lake else zeros, C.c_double), p(net.D03_Coefficient if lake else zeros, C.c_double),
+                          p(net.D03_Power if lake else zeros, C.c_double), p(net.D03_S0 if lake else zeros, C.c_double),
+                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_double(params.velo), C.c_double(params.diff),
+                          C.c_int(opts.hw_drain_point), C.c_double(opts.min_length_route), C.c_int(opts.LakeInputOption), C.c_int(K),
+                          p(qr, C.c_double), p(flux, C.c_double), p(vol, C.c_double), p(targ, C.c_double), C.c_int(1),
+                          p(qs, C.c_double), p(qi, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(qf, C.c_double), C.byref(mx), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qi, qo)
+    assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, orc.M_IRF))
+    assert np.array_equal(we, o.get(orc.F_WB, orc.M_IRF))
+    assert (qo[:, (net.islake != 1) if lake else slice(None)] == 0.0).any()          # somewhere more was asked for than there was

@@ -156,3 +156,47 @@ def test_hanasaki_reservoirs(memory, calendar, start, dt, steps, route):
         tol = 1e-6 if c == "1" else EULER_RTOL
         assert rel_err(qg[i], qo[i], floor=1e-6) <= tol, c
         assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1.0) <= tol
+
+
+@pytest.mark.parametrize("route,lakes", [("1", 0), ("134", 9), ("5", 0)])
+def test_water_management(route, lakes):
+    """mr_upload_wm: abstraction / injection fluxes through the storage -> inflow -> lateral-flow cascade of IRF and the Euler
+    schemes, lakes losing / gaining the flux, lakes flagged LakeTargVol following their target volume (jump-started)."""
+    from mizuroute_b200 import capi
+    from mizuroute_b200.route import Router, RoutingError
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0 if lakes else 3600.0, route_opt=route, steps=12, lakes=lakes)
+    K = ro.shape[0]
+    rng = np.random.default_rng(11)
+    vol = None
+    if lakes:
+        lk = np.flatnonzero(net.islake == 1)
+        net.lake_params = {"LakeTargVol": np.isin(np.arange(net.nRch), lk[:3]).astype(np.float64)}
+        vol = np.where(net.islake == 1, rng.uniform(1e6, 5e7, (K, net.nRch)), 0.0)
+    flux = np.full((K, net.nRch), -9999.0)
+    pick = rng.random((K, net.nRch)) < 0.4
+    flux[pick] = rng.choice([-1.0, 1.0], pick.sum()) * rng.lognormal(np.log(0.05), 1.5, pick.sum())
+    o = Oracle(net, params, opts)
+    qo = np.empty((len(route), K, net.nRch))
+    for t in range(K):
+        o.set_wm(flux[t], None if vol is None else vol[t], vol_jumpstart=True)
+        o.step(ro[t])
+        for i, c in enumerate(route):
+            qo[i, t] = o.get(orc.F_REACH_Q, int(c))
+    r = Router(net, params, opts, max_batch=8)
+    parts = []
+    for s in range(0, K, 5):
+        r.upload_wm(flux[s:s + 5], None if vol is None else vol[s:s + 5], vol_jumpstart=True)
+        parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + 5])))
+    qg = np.concatenate(parts, axis=1)
+    for i, c in enumerate(route):
+        tol = 1e-6 if c == "1" else EULER_RTOL
+        assert rel_err(qg[i], qo[i], floor=1e-9) <= tol, c
+        assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1e-3) <= tol
+        assert rel_err(r.flux(capi.WB, int(c)), o.get(orc.F_WB, int(c)), floor=1.0) <= 1e-5
+    if route == "1":                                      # fluxes with KWT are refused (extract_from_rch is not on the device)
+        r2 = Router(net, params, type(opts)(**{**opts.__dict__, "route_opt": "2"}), max_batch=8)
+        r2.upload_wm(flux[:5])
+        with pytest.raises(RoutingError, match="extract_from_rch"):
+            r2.route_batch(np.ascontiguousarray(ro[:5]))
