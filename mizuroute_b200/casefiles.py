@@ -66,6 +66,28 @@ def write_runoff(path: str, hru_ids: np.ndarray, runoff: np.ndarray, dt: float, 
     f.close()
 
 
+def write_wm(path: str, seg_ids: np.ndarray, flux, vol, dt: float, start: str = "2000-01-01 00:00:00"):
+    """Water-management file: flux_wm / vol_wm [time, seg] (either may be None), reach ids, time in seconds since `start`."""
+    f = netcdf_file(path, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("seg", len(seg_ids))
+    t = f.createVariable("time", "d", ("time",))
+    t.units = "seconds since " + start
+    t.calendar = "standard"
+    sid = f.createVariable("seg_id", "i", ("seg",))
+    sid[:] = seg_ids
+    vf = f.createVariable("flux_wm", "d", ("time", "seg")) if flux is not None else None
+    vv = f.createVariable("vol_wm", "d", ("time", "seg")) if vol is not None else None
+    n = (flux if flux is not None else vol).shape[0]
+    for k in range(n):
+        t[k] = k * dt
+        if vf is not None:
+            vf[k, :] = flux[k]
+        if vv is not None:
+            vv[k, :] = vol[k]
+    f.close()
+
+
 def write_runoff_grid(path: str, runoff: np.ndarray, dt: float, start: str = "2000-01-01 00:00:00", fill=None):
     """Gridded runoff[time, lat, lon] (the layout read_2D_forcing expects, read_runoff.f90:331-396)."""
     f = netcdf_file(path, "w", version=2)
@@ -94,7 +116,7 @@ def _stamp(seconds: float, start: str) -> str:
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
                fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1", forcing_dt=None, sim_steps=None,
-               ro_time_stamp=None, new_file_frequency="single", extra_keys=None, lake_forcing=None) -> str:
+               ro_time_stamp=None, new_file_frequency="single", extra_keys=None, lake_forcing=None, wm=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
     continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`.  `forcing_dt` != dt_qsim
     writes the runoff records on their own interval (`sim_steps` simulation steps of opts.dt are then asked for);
@@ -203,6 +225,13 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
         ("newFileFrequency", new_file_frequency, "history file frequency: single, daily, monthly or yearly"),
         ("outputFrequency", output_frequency, "output frequency: number of steps or daily"),
     ]
+    if wm is not None:                                      # (seg_ids, flux_wm[time, seg] or None, vol_wm[time, seg] or None)
+        wm_ids, wm_flux, wm_vol = wm
+        write_wm(inp + "wm_%s.nc" % case_name, wm_ids, wm_flux, wm_vol, opts.dt, t_first)
+        keys += [("is_flux_wm", "T" if wm_flux is not None else "F", "abstraction / injection fluxes"),
+                 ("is_vol_wm", "T" if wm_vol is not None else "F", "target lake volumes"), ("is_vol_wm_jumpstart", "T", "start the target-volume lakes at their target"),
+                 ("fname_wm", "wm_%s.nc" % case_name, "water-management netCDF"), ("vname_flux_wm", "flux_wm", ""), ("vname_vol_wm", "vol_wm", ""),
+                 ("vname_time_wm", "time", ""), ("vname_segid_wm", "seg_id", ""), ("dname_time_wm", "time", ""), ("dname_segid_wm", "seg", "")]
     for k, v in (extra_keys or {}).items():
         keys.append((k, v, "extra key"))
     ctl = os.path.join(case_dir, case_name + ".control")

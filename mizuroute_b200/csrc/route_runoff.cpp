@@ -18,7 +18,8 @@
 // <outputFrequency> = n steps or daily; standard / proleptic_gregorian / noleap calendars.  <restart_write> never | last |
 // specified | yearly | monthly | daily.
 // <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device; any ratio of <dt_qsim> to
-// the forcing interval; <newFileFrequency> single | daily | monthly | yearly.
+// the forcing interval; <newFileFrequency> single | daily | monthly | yearly.  <is_flux_wm> / <is_vol_wm> T: one water-management
+// netCDF <fname_wm> with [time, seg] variables (not with route method 2).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -340,7 +341,9 @@ int main(int argc, char **argv) {
         o.is_lake_sim = c.flag("is_lake_sim", false); o.lakeRegulate = c.flag("lakeRegulate", true); o.LakeInputOption = (int)c.num("LakeInputOption", 0);
         o.runoffMin = c.num("runoffMin", 0.0);
         const bool isRemap = c.flag("is_remap", false);
-        if (c.flag("is_flux_wm", false) || c.flag("is_vol_wm", false)) die(20, "route_runoff/water management is not on this path");
+        const bool fluxWm = c.flag("is_flux_wm", false), volWm = c.flag("is_vol_wm", false) && o.is_lake_sim;    // main_route.f90:110-123
+        for (int r = 0; r < o.n_routes; ++r)
+            if (fluxWm && o.route_methods[r] == MR_KINEMATIC_WAVE_TRACKING) die(20, "route_runoff/<is_flux_wm> T with route method 2: extract_from_rch of KWT is not on the device");
         {                                                        // units_qsim -> time_conv, length_conv (read_control.f90:443-474)
             const std::string u = c.need("units_qsim");
             const size_t sl = u.find('/');
@@ -444,20 +447,22 @@ int main(int argc, char **argv) {
         // timeMap_sim_forc (get_basin_runoff.f90:256-369): forcing records under simulation step k and their weights.
         // One record (dt_qsim <= dt_ro, step inside a record): that record, no weight.
         struct TimeMap { std::vector<size_t> rec; std::vector<double> frac; };
-        auto time_map = [&](size_t k) {
+        auto time_map_of = [&](double beg, double dtIn, size_t nRec, size_t k) {      // the same for the runoff and the water-management files
             TimeMap m;
-            const double sim1 = (tStart - roBeg) + (double)k * o.dt, sim2 = sim1 + o.dt;
-            size_t front = (size_t)std::floor(sim1 / dtro + tolT);                       // first record whose end is after sim1
-            double e = std::ceil(sim2 / dtro - tolT) - 1.0; if (e < 0.0) e = 0.0;    // first record whose end is at or after sim2
+            const double sim1 = (tStart - beg) + (double)k * o.dt, sim2 = sim1 + o.dt;
+            double f0 = std::floor(sim1 / dtIn + tolT); if (f0 < 0.0) f0 = 0.0;
+            size_t front = (size_t)f0;                                                   // first record whose end is after sim1
+            double e = std::ceil(sim2 / dtIn - tolT) - 1.0; if (e < 0.0) e = 0.0;    // first record whose end is at or after sim2
             size_t end = (size_t)e;
-            if (end > nRo - 1) end = nRo - 1;
+            if (end > nRec - 1) end = nRec - 1;
             if (front > end) die(30, "timeMap_sim_forc/index of idxFront lower than idxEnd");
             for (size_t r = front; r <= end; ++r) {
                 m.rec.push_back(r);
                 if (front == end) break;
-                m.frac.push_back(r == front ? ((double)(r + 1) * dtro - sim1) / o.dt : r == end ? (sim2 - (double)r * dtro) / o.dt : dtro / o.dt);
+                m.frac.push_back(r == front ? ((double)(r + 1) * dtIn - sim1) / o.dt : r == end ? (sim2 - (double)r * dtIn) / o.dt : dtIn / o.dt);
             }
             return m; };
+        auto time_map = [&](size_t k) { return time_map_of(roBeg, dtro, nRo, k); };
         const size_t i0 = time_map(0).rec[0];
 
         // sort_flux index: forcing HRU -> network HRU (process_remap.f90:271-311)
@@ -591,6 +596,40 @@ int main(int argc, char **argv) {
         const VarSpec vsEvapo{c.str("vname_evapo", "evapo"), c.num("scale_factor_Ep", -9999.0), c.num("offset_value_Ep", -9999.0), c.flag("is_Ep_upward_negative", false)};
         const VarSpec vsPrecip{c.str("vname_precip", "precip"), c.num("scale_factor_prec", -9999.0), c.num("offset_value_prec", -9999.0), false};
 
+        // water management (<is_flux_wm>, <is_vol_wm>): one netCDF with [time, seg] variables (get_basin_runoff.f90:199-250);
+        // sort_flux by reach id: reaches the file does not hold get realMissing (= no flux) / 0 (target volume)
+        std::unique_ptr<nc3::Reader> wmFile;
+        std::vector<int> wmIx; size_t nWm = 0; double wmBeg = 0.0, dtWm = o.dt; std::vector<double> wmRec, wmSum, wmTot;
+        if (fluxWm || volWm) {
+            wmFile.reset(new nc3::Reader(join_path(indir, c.need("fname_wm"))));
+            const nc3::Var &tv = wmFile->var(c.need("vname_time_wm"));
+            double scale, epoch; parse_time_units(wmFile->attr_text(tv, "units"), noleap, scale, epoch);
+            std::vector<double> tt; wmFile->read_all(tv, tt);
+            if (tt.empty()) die(20, "init_time/the water-management file holds no time record");
+            nWm = tt.size(); wmBeg = epoch + tt[0] * scale; dtWm = nWm >= 2 ? (tt[1] - tt[0]) * scale : c.num("dt_wm", o.dt);
+            if (tStart < wmBeg - 1e-3 || tStart + (double)nSteps * o.dt > wmBeg + (double)nWm * dtWm + 1e-3) die(20, "init_time/the water-management file does not cover the simulation period");
+            std::vector<int> wmSeg; wmFile->read_int(wmFile->var(c.need("vname_segid_wm")), wmSeg);
+            std::vector<std::pair<int, int>> tab(nRch); for (size_t i = 0; i < nRch; ++i) tab[i] = {segId[i], (int)i}; std::sort(tab.begin(), tab.end());
+            wmIx.assign(wmSeg.size(), -1);
+            for (size_t i = 0; i < wmSeg.size(); ++i) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(wmSeg[i], -1)); if (it != tab.end() && it->first == wmSeg[i]) wmIx[i] = it->second; }
+        }
+        auto load_wm = [&](const std::string &vname, bool removeNegatives, size_t k, double *dst) {
+            const TimeMap tm = time_map_of(wmBeg, dtWm, nWm, k);
+            const nc3::Var &qv = wmFile->var(vname);
+            double fv = -9999.0; wmFile->attr_value(qv, "_FillValue", fv);
+            for (size_t j = 0; j < tm.rec.size(); ++j) {
+                wmFile->read(qv, wmRec, tm.rec[j], 1);
+                if (wmRec.size() != wmIx.size()) die(20, "read_runoff/water-management variable " + vname + " is not dimensioned [time, seg]");
+                if (tm.frac.empty()) break;
+                if (j == 0) { wmSum.assign(wmRec.size(), 0.0); wmTot.assign(wmRec.size(), 0.0); }
+                for (size_t i = 0; i < wmRec.size(); ++i) if (wmRec[i] != fv) { wmSum[i] += wmRec[i] * tm.frac[j]; wmTot[i] += tm.frac[j]; }
+            }
+            if (!tm.frac.empty())
+                for (size_t i = 0; i < wmRec.size(); ++i) wmRec[i] = wmTot[i] == 0.0 ? fv : (wmTot[i] < 1.0 ? wmSum[i] / wmTot[i] : wmSum[i]);
+            std::fill(dst, dst + nRch, removeNegatives ? 0.0 : -9999.0);
+            for (size_t i = 0; i < wmRec.size(); ++i) if (wmIx[i] >= 0) { double v = wmRec[i] == fv ? -9999.0 : wmRec[i]; if (removeNegatives && v < 0.0) v = 0.0; dst[wmIx[i]] = v; }
+        };
+
         if (dry) {                                                       // the time map of the first steps, for inspection
             std::printf("{\"dt_ro\": %.3f, \"ro_time_stamp\": \"%s\", \"time_map\": [", dtro, stampAt.c_str());
             for (size_t k = 0; k < std::min<size_t>(nSteps, 6); ++k) {
@@ -622,7 +661,7 @@ int main(int argc, char **argv) {
                                                  "HYP_Qrate_amp", "HYP_Qrate_phs", "HYP_prim_F", "HYP_A_avg", "HYP_Qsim_mode",
                                                  "H06_Smax", "H06_alpha", "H06_envfact", "H06_S_ini", "H06_c1", "H06_c2", "H06_exponent", "H06_denominator",
                                                  "H06_c_compare", "H06_frac_Sdead", "H06_E_rel_ini", "H06_purpose", "H06_I_mem_F", "H06_D_mem_F",
-                                                 "H06_I_mem_L", "H06_D_mem_L"};
+                                                 "H06_I_mem_L", "H06_D_mem_L", "LakeTargVol"};
             for (const char *mo : {"Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"}) {
                 hypNames.push_back(std::string("H06_I_") + mo); hypNames.push_back(std::string("H06_D_") + mo); }
             for (const std::string &nmS : hypNames) {
@@ -667,6 +706,7 @@ int main(int argc, char **argv) {
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
         std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch);
         std::vector<double> evRows(lakeForcing ? (size_t)batch * nHRU : 0), prRows(evRows.size());
+        std::vector<double> wmFluxRows(fluxWm ? (size_t)batch * nRch : 0), wmVolRows(volWm ? (size_t)batch * nRch : 0);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
@@ -685,6 +725,14 @@ int main(int argc, char **argv) {
             if (lakeForcing) {
                 for (int k = 0; k < nb; ++k) { load_var(vsEvapo, s + k, &evRows[(size_t)k * nHRU], nHRU, false); load_var(vsPrecip, s + k, &prRows[(size_t)k * nHRU], nHRU, false); }
                 ierr = mr_upload_lake_forcing(h, nb, evRows.data(), prRows.data(), msg); if (ierr) die(ierr, msg);
+            }
+            if (fluxWm || volWm) {
+                for (int k = 0; k < nb; ++k) {
+                    if (fluxWm) load_wm(c.need("vname_flux_wm"), false, s + k, &wmFluxRows[(size_t)k * nRch]);
+                    if (volWm) load_wm(c.need("vname_vol_wm"), true, s + k, &wmVolRows[(size_t)k * nRch]);
+                }
+                ierr = mr_upload_wm(h, nb, fluxWm ? wmFluxRows.data() : nullptr, volWm ? wmVolRows.data() : nullptr, c.flag("is_vol_wm_jumpstart", false) ? 1 : 0, msg);
+                if (ierr) die(ierr, msg);
             }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }

@@ -19,6 +19,8 @@ struct mr_handle_s {
     /* named lake parameters and the simulation start, applied to the oracle in mr_set_network */
     char lpName[64][32]; double *lpVal[64]; int nLp;
     int hasStart, sy, sm, sd, noleap; double ssec;
+    /* water management of the next batch (mr_upload_wm) */
+    double *wmF, *wmV; int wmSteps, wmJump;
     /* lake forcing of the next batch (mr_upload_lake_forcing) */
     double *ev, *pr; int epSteps;
     /* BASIN_QR(1) of the steps of the last batch */
@@ -82,6 +84,8 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     for (t = 0; t < nSteps; t++) {
         const double *in = runoff + (size_t)t * (size_t)(h->nMap ? h->nForcing : h->nHRU);
         if (h->nMap) { mro_remap_1d(h->nMap, h->mapHru, h->numQ, h->qIx, h->wgt, in, row); in = row; }
+        if (h->wmSteps) mro_set_wm(h->m, h->wmF ? h->wmF + (size_t)t * h->nRch : NULL, h->wmV ? h->wmV + (size_t)t * h->nRch : NULL, h->wmJump);
+        else mro_set_wm(h->m, NULL, NULL, 0);
         ierr = h->epSteps ? mro_step_ep(h->m, t0, t1, in, h->ev + (size_t)t * h->nHRU, h->pr + (size_t)t * h->nHRU) : mro_step(h->m, t0, t1, in);
         if (ierr) { char b[MR_STRLEN]; snprintf(b, sizeof b, "mr_step_batch/main_route/%s", mro_message(h->m)); say(message, b); free(row); return ierr; }
         for (r = 0; r < h->m->nRoutes; r++)
@@ -90,7 +94,7 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
         t0 = t1; t1 = t0 + h->o.dt;
     }
     free(row);
-    h->epSteps = 0;
+    h->epSteps = 0; h->wmSteps = 0;
     say(message, "");
     return 0;
 }
@@ -109,6 +113,17 @@ int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay,
 {
     h->hasStart = 1; h->sy = year; h->sm = month; h->sd = day; h->ssec = secOfDay; h->noleap = noleap;
     if (h->m) mro_set_sim_start(h->m, year, month, day, secOfDay, noleap);
+    say(message, "");
+    return 0;
+}
+
+int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *vol_wm, int volJumpStart, char *message)
+{
+    const size_t n = (size_t)nSteps * (size_t)h->nRch;
+    free(h->wmF); free(h->wmV); h->wmF = h->wmV = NULL;
+    if (flux_wm) { h->wmF = (double *)malloc(sizeof(double) * (n + 1)); memcpy(h->wmF, flux_wm, sizeof(double) * n); }
+    if (vol_wm) { h->wmV = (double *)malloc(sizeof(double) * (n + 1)); memcpy(h->wmV, vol_wm, sizeof(double) * n); }
+    h->wmSteps = nSteps; h->wmJump = volJumpStart;
     say(message, "");
     return 0;
 }
@@ -246,6 +261,6 @@ void mr_destroy(mr_handle h)
 {
     if (!h) return;
     if (h->m) mro_destroy(h->m);
-    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr); free(h->ev); free(h->pr);
+    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr); free(h->ev); free(h->pr); free(h->wmF); free(h->wmV);
     free(h);
 }

@@ -49,9 +49,12 @@ def test_control_file_errors(tmp_path):
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode == 81 and "unknown control key" in r.stderr          # read_control.f90:374-377
     import re
-    bad.write_text(txt + "<is_flux_wm>   T   ! water management is not on this path\n")
+    bad.write_text(txt + "<is_flux_wm>   T   ! water management needs its file\n")
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
-    assert r.returncode != 0 and "water management" in r.stderr
+    assert r.returncode != 0 and "<fname_wm> must be given" in r.stderr
+    bad.write_text(re.sub(r"(<route_opt>\s+)1 ", r"\g<1>12", txt) + "<is_flux_wm>   T   ! KWT's extract_from_rch is not on the device\n")
+    r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
+    assert r.returncode != 0 and "extract_from_rch" in r.stderr
     bad.write_text(re.sub(r"(<ro_time_stamp>\s+)start", r"\g<1>front", txt))
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode != 0 and "must be start, end, or middle" in r.stderr        # read_control.f90:514-518
@@ -394,6 +397,37 @@ def test_hanasaki_reservoirs_from_the_network_file(tmp_path, backend):
     qo = Oracle(net, params, opts).run(ro)
     np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
     np.testing.assert_allclose(out["KWroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_host_reads_the_water_management_file(tmp_path, backend):
+    """<is_flux_wm> / <is_vol_wm> T: fluxes and target volumes [time, seg] of <fname_wm>, given for a shuffled subset of the
+    reaches (the others get "none"), reach the routing through mr_upload_wm; LakeTargVol comes with the river network."""
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=500, seed=4, dt=86400.0, route_opt="14", steps=12, lakes=7)
+    K = ro.shape[0]
+    rng = np.random.default_rng(11)
+    lk = np.flatnonzero(net.islake == 1)
+    net.lake_params = {"LakeTargVol": np.isin(np.arange(net.nRch), lk[:3]).astype(np.float64)}
+    sub = rng.permutation(net.nRch)[: int(0.6 * net.nRch)]                     # reaches the file knows, in file order
+    sub = np.union1d(sub, lk)[rng.permutation(np.union1d(sub, lk).size)]
+    flux_f = rng.choice([-1.0, 1.0], (K, sub.size)) * rng.lognormal(np.log(0.05), 1.5, (K, sub.size))
+    vol_f = np.where(net.islake[sub] == 1, rng.uniform(1e6, 5e7, (K, sub.size)), 0.0)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="wm", wm=(net.segId[sub], flux_f, vol_f))
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    o = Oracle(net, params, opts)
+    qo = np.empty((2, K, net.nRch))
+    for t in range(K):
+        flux = np.full(net.nRch, -9999.0); flux[sub] = flux_f[t]
+        vol = np.zeros(net.nRch); vol[sub] = vol_f[t]
+        o.set_wm(flux, vol, vol_jumpstart=True)
+        o.step(ro[t])
+        qo[0, t] = o.get(0, 1); qo[1, t] = o.get(0, 4)          # F_REACH_Q of IRF and MC
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["MCroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+    assert not np.array_equal(qo, Oracle(net, params, opts).run(ro))
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
