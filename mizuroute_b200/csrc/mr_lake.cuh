@@ -147,7 +147,7 @@ MR_LAKE_FN void lake_reach(const DevNet &d, int p, int t, long long tau) {
     const double v0 = v1;
     const double qr1 = d.qrSer[(size_t)(t + 1) * N + p];
     // lake forcing of this step; the evaporation may have been cut back by a method routed earlier in the step
-    const bool ep = d.lakeEvap != nullptr;
+    const bool ep = HY && d.lakeEvap != nullptr;      // (forcing, like the parametric models, only in the HY instantiation)
     size_t ix = 0;
     double pr = 0.0, ev = 0.0;
     if (ep) { ix = (size_t)t * d.nLake + d.lakeSlot[p]; pr = d.lakePrecip[ix]; ev = d.lakeEvap[ix]; }

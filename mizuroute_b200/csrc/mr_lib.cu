@@ -68,7 +68,7 @@ struct mr_handle_s {
     int *dStepDoy = nullptr; std::vector<int> stepDoyHost;      // [3][max_batch]: day of year, month, day of month
     // water management (mr_upload_wm): per-reach flux / target volume rows of the next batch, stage order; lakes that follow
     // the target volume (lake parameter LakeTargVol)
-    int wmSteps = 0, wmJumpStart = 0; bool wmHasFlux = false, wmHasVol = false, wmActive = false;
+    int wmSteps = 0, wmJumpStart = 0; bool wmHasFlux = false, wmHasVol = false, wmActive = false, lakeForcingActive = false;
     double *dWmFlux = nullptr, *dWmVol = nullptr; unsigned char *dLakeTargVol = nullptr;
     std::vector<double> wmStage;
     // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
@@ -179,10 +179,10 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     if constexpr (M == M_KWT) {
         int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        if (h->hasHype || h->hasH06 || h->wmActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
     } else {
-        if (h->hasHype || h->hasH06 || h->wmActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
     h->launchesLast++;
@@ -253,6 +253,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
             lakeForcing = true;
         }
     }
+    h->lakeForcingActive = lakeForcing;
     if (h->nGhost) {
         if (!d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
         k_import_unpack<<<(h->nGhost * K + 255) / 256, 256, 0, h->stream>>>(d, h->dImpPos, h->nGhost, K);
@@ -276,7 +277,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
-            const bool hy = h->hasHype || h->hasH06 || h->wmActive;  // parametric reservoirs or water management: the instantiation that knows them
+            const bool hy = h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive;  // parametric reservoirs, lake forcing or water management: the instantiation that knows them
             switch (h->opt.route_methods[r]) {
                 case M_SUM: if (hy) k_headwater<M_SUM, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_SUM, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_IRF: if (hy) k_headwater<M_IRF, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_IRF, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
