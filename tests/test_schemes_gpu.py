@@ -72,7 +72,7 @@ def test_molecule_state_round_trip_continues_exactly():
 def test_lake_evaporation_and_precipitation_forcing(option, route):
     """mr_upload_lake_forcing: evaporation / precipitation through basin2reach into lake_route (LakeInputOption 0 / 2) and the
     lake water balance; two lakes run dry and their cut evaporation is seen by the method routed second (methods then run
-    one after the other).  IRF stays within 1e-6 (Doll's outflow calls pow), MC / KWT within 1e-4."""
+    on one stream, in route_opt order inside every wavefront).  IRF stays within 1e-6 (Doll's outflow calls pow), MC / KWT within 1e-4."""
     from mizuroute_b200 import capi
     from mizuroute_b200.route import Router
     from oracle import oracle as orc
