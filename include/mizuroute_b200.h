@@ -151,9 +151,9 @@ int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, co
  * abstraction (+) / injection (-) in m3/s, -9999 = none at that reach (<is_flux_wm>, the reachflux_in argument of main_route,
  * main_route.f90:110-116); vol_wm [nSteps][nRch] = REACH_WM_VOL, the target volume of the lakes flagged with the lake parameter
  * "LakeTargVol" (<is_vol_wm>, :117-123); volJumpStart = <is_vol_wm_jumpstart>.  Either array may be NULL (= that option off).
- * Caller's reach order.  The abstraction cascade of irf_rch and of the Euler schemes (irf_route.f90:114-142) and the lake
- * fluxes / target volumes (lake_route.f90:137-139,176-203) run on the device; extract_from_rch of KWT does not: fluxes with
- * route method 2 are refused. */
+ * Caller's reach order.  On the device: the abstraction cascade of irf_rch and of the Euler schemes (irf_route.f90:114-142),
+ * extract_from_rch of KWT (kwt_route.f90:351-455; note that it reads the sign the other way round) and the lake fluxes /
+ * target volumes (lake_route.f90:137-139,176-203). */
 int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *vol_wm, int volJumpStart, char *message);
 /* Per-reach parameters of the parametric lake models beyond Doll-2003, by their name in RCHPRP (dataTypes.f90:202-213):
  * HYP_E_emr, HYP_E_lim, HYP_E_min, HYP_E_zero, HYP_Qrate_emr, HYP_Erate_emr, HYP_Qrate_prim, HYP_Qrate_amp, HYP_Qrate_phs,

@@ -267,7 +267,7 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
     int nPre = 0;
     const long long c0 = d.kwProf ? clock64() : 0;
     const double T0 = active ? d.T0s[t] : 0.0, T1 = active ? d.T1s[t] : 0.0;
-    const int rc = kwt_reach_team<KwtScratchSmall, true>(d, S, p, t, tau0 + t, T0, T1, &nPre, active);
+    const int rc = kwt_reach_team<KwtScratchSmall, true, HY>(d, S, p, t, tau0 + t, T0, T1, &nPre, active);
     if (!active) return;
     if (d.kwProf && lane == 0) {                       // classes: particles before thinning 0 (no area), <=3, <=6, <=12, <=20, <=40, >40, retry
         const int cls = rc == KWT_RETRY ? 7 : (nPre == 0 ? 0 : nPre <= 3 ? 1 : nPre <= 6 ? 2 : nPre <= 12 ? 3 : nPre <= 20 ? 4 : nPre <= 40 ? 5 : 6);
@@ -289,7 +289,7 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
     }
     slot = team_bcast(slot, 0);
     KwtScratch &B = reinterpret_cast<KwtScratch *>(d.kwArena)[(size_t)sm * KWT_ARENA_SLOTS + slot];
-    kwt_reach_team<KwtScratch, false>(d, B, p, t, tau0 + t, T0, T1);
+    kwt_reach_team<KwtScratch, false, HY>(d, B, p, t, tau0 + t, T0, T1);
     MR_SYNC();
     if (lane == 0) { __threadfence(); atomicAnd(&d.kwArenaMask[sm], ~(1ull << slot)); }
 }

@@ -538,7 +538,8 @@ MR_DEV int kwt_merge_team(const DevNet &d, SC &S, int p, int t, int b, double T0
 // task passes active = false) and the phases of the task -- gather + merge | thinning | routing | averaging + store --
 // end in a full-warp sync, so the teams of a warp, which diverge inside a phase whenever their tasks differ,
 // re-converge at every phase boundary and share the instruction stream wherever their paths agree.
-template <class SC, bool WS = false>
+// EXT = true: the instantiation for batches with water management (extract_from_rch between thinning and routing).
+template <class SC, bool WS = false, bool EXT = false>
 MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, double T0, double T1, int *nPre = nullptr, bool active = true) {
     const int lane = MR_LANE;
     const int N = d.nRch;
@@ -612,6 +613,29 @@ MR_DEV int kwt_reach_team(const DevNet &d, SC &S, int p, int t, long long tau, d
     // ---- phase 2: remove_rch
     if (live && n > MR_MAXQPAR) { if (kwt_thin_team(S, n)) { if (lane == 0) raise(d.err, 60, p, E_THIN); live = false; } }
     if (WS) MR_WSYNC();
+
+    // ---- phase 2b: extract_from_rch (kwt_route.f90:351-455), water management only.  The waves (all but particle 0) are
+    // scaled by the share of the step's mean flow -- time average of the (TENTRY, Q) series, the same interp_rch -- that is
+    // added (Qtake > 0: this routine reads the sign the other way round than the other schemes) or removed (Qtake < 0,
+    // smaller than what is there); otherwise everything becomes MINFLOW (0).  The exit times it sets are redone by kinwav_rch.
+    if (EXT) {
+        if (live && d.wmFlux) {
+            const double Qtake = d.wmFlux[(size_t)t * N + p];
+            if (Qtake != -9999.0) {
+                double Qavg = 0.0;
+                if (kwt_time_average_team(S.TE, S.Q, n, T0, T1, S.u.k.XX, Qavg)) { if (lane == 0) raise(d.err, 40, p, E_INTERP); live = false; }
+                else {
+                    const double totQ = team_bcast(Qavg, 0) * W;      // the average is valid on lane 0
+                    MR_SYNC();
+                    if (Qtake > 0.0) { const double Qfrac = Qtake / totQ; MR_NOUNROLL for (int i = 1 + lane; i < n; i += MR_NL) S.Q[i] = S.Q[i] * (1.0 + Qfrac); }
+                    else if (Qtake < 0.0 && fabs(Qtake) < totQ) { const double Qfrac = fabs(Qtake) / totQ; MR_NOUNROLL for (int i = 1 + lane; i < n; i += MR_NL) S.Q[i] = S.Q[i] * (1.0 - Qfrac); }
+                    else { MR_NOUNROLL for (int i = lane; i < n; i += MR_NL) S.Q[i] = 0.0; }
+                    MR_SYNC();
+                }
+            }
+        }
+        if (WS) MR_WSYNC();
+    }
 
     // ---- phase 3: kinwav_rch
     if (live) {

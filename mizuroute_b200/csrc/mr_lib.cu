@@ -220,7 +220,6 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     h->wmActive = false;
     if (h->wmSteps) {                                   // water management rows uploaded for this batch
         h->wmSteps = 0;
-        if (h->wmHasFlux && h->on[M_KWT]) return fail(message, 20, std::string(where) + "/water-management fluxes with KWT (extract_from_rch) are not on the device");
         d.wmFlux = h->wmHasFlux ? h->dWmFlux : nullptr; d.wmVol = h->wmHasVol ? h->dWmVol : nullptr; d.volJumpStart = h->wmJumpStart;
         h->wmActive = true;
     }

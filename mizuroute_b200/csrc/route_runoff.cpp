@@ -19,7 +19,7 @@
 // specified | yearly | monthly | daily.
 // <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device; any ratio of <dt_qsim> to
 // the forcing interval; <newFileFrequency> single | daily | monthly | yearly.  <is_flux_wm> / <is_vol_wm> T: one water-management
-// netCDF <fname_wm> with [time, seg] variables (not with route method 2).
+// netCDF <fname_wm> with [time, seg] variables.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -342,8 +342,6 @@ int main(int argc, char **argv) {
         o.runoffMin = c.num("runoffMin", 0.0);
         const bool isRemap = c.flag("is_remap", false);
         const bool fluxWm = c.flag("is_flux_wm", false), volWm = c.flag("is_vol_wm", false) && o.is_lake_sim;    // main_route.f90:110-123
-        for (int r = 0; r < o.n_routes; ++r)
-            if (fluxWm && o.route_methods[r] == MR_KINEMATIC_WAVE_TRACKING) die(20, "route_runoff/<is_flux_wm> T with route method 2: extract_from_rch of KWT is not on the device");
         {                                                        // units_qsim -> time_conv, length_conv (read_control.f90:443-474)
             const std::string u = c.need("units_qsim");
             const size_t sl = u.find('/');

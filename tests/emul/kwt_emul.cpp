@@ -18,6 +18,7 @@ using namespace mr;
 extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId, const double *hruArea,
                             const double *length, const double *slope, double mann_n, double wscale, double dt, int nSteps,
                             const double *qr /* [nSteps+1][nRch] BASIN_QR(1) before step 0 and after every step, caller order */,
+                            const double *wm_flux /* [nSteps][nRch] REACH_WM_FLUX, caller order, or NULL: the EXT instantiation is used then */,
                             double *q_out /* [nSteps][nRch] REACH_Q, caller order */, int *n_out /* [nRch] live particles */, char *msg) {
     Topology T;
     std::string terr;
@@ -49,6 +50,12 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     d.err = err; d.kwCount = nullptr;
     double t0 = 0.0, t1 = dt;
     for (int t = 0; t < nSteps; ++t) { T0s[t] = t0; T1s[t] = t1; t0 = t1; t1 = t0 + dt; }
+    std::vector<double> fS;
+    if (wm_flux) {                                          // stage order, as mr_upload_wm
+        fS.resize((size_t)nSteps * N);
+        for (int t = 0; t < nSteps; ++t) for (int p = 0; p < N; ++p) fS[(size_t)t * N + p] = wm_flux[(size_t)t * N + T.pos2rch[p]];
+        d.wmFlux = fS.data();
+    }
     static KwtScratch S;
     static KwtScratchSmall Ssmall;
     long retries = 0;
@@ -60,7 +67,12 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
         }
         for (int p = T.nHead; p < N; ++p) {                 // stage order: upstream before downstream
             // the shared-memory-sized scratch first, the full-capacity one on KWT_RETRY -- as k_route_kwt does
-            if (kwt_reach_team(d, Ssmall, p, t, (long long)t, T0s[t], T1s[t]) == KWT_RETRY) {
+            if (wm_flux) {
+                if (kwt_reach_team<KwtScratchSmall, false, true>(d, Ssmall, p, t, (long long)t, T0s[t], T1s[t]) == KWT_RETRY) {
+                    ++retries;
+                    kwt_reach_team<KwtScratch, false, true>(d, S, p, t, (long long)t, T0s[t], T1s[t]);
+                }
+            } else if (kwt_reach_team(d, Ssmall, p, t, (long long)t, T0s[t], T1s[t]) == KWT_RETRY) {
                 ++retries;
                 kwt_reach_team(d, S, p, t, (long long)t, T0s[t], T1s[t]);
             }

@@ -52,9 +52,6 @@ def test_control_file_errors(tmp_path):
     bad.write_text(txt + "<is_flux_wm>   T   ! water management needs its file\n")
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode != 0 and "<fname_wm> must be given" in r.stderr
-    bad.write_text(re.sub(r"(<route_opt>\s+)1 ", r"\g<1>12", txt) + "<is_flux_wm>   T   ! KWT's extract_from_rch is not on the device\n")
-    r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
-    assert r.returncode != 0 and "extract_from_rch" in r.stderr
     bad.write_text(re.sub(r"(<ro_time_stamp>\s+)start", r"\g<1>front", txt))
     r = subprocess.run([_host(), str(bad), "--dry-run"], capture_output=True, text=True)
     assert r.returncode != 0 and "must be start, end, or middle" in r.stderr        # read_control.f90:514-518

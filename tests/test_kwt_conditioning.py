@@ -35,7 +35,7 @@ def _noise_error(net, params, opts, ro, seed=1):
     p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
     ierr = L.kwt_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
                           p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
-                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double), p(ne, C.c_int), msg)
+                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), None, p(qe, C.c_double), p(ne, C.c_int), msg)
     assert ierr == 0, msg.value.decode()
     return float(np.max(np.abs(qe - qo) / np.maximum(np.abs(qo), 1e-300)))
 

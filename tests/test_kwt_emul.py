@@ -27,7 +27,7 @@ def _emul_vs_oracle(net, params, opts, ro):
     p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
     ierr = L.kwt_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
                           p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
-                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), p(qe, C.c_double), p(ne, C.c_int), msg)
+                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), None, p(qe, C.c_double), p(ne, C.c_int), msg)
     assert ierr == 0, msg.value.decode()
     _emul_vs_oracle.retries = int(msg.value.decode().split("=")[1])
     return o, qo, qe, ne
@@ -59,3 +59,54 @@ def test_team_kwt_zero_area_parents():
     net, params, opts, ro = case("random", n=150, seed=5, dt=3600.0, route_opt="2", steps=30, zero_area_frac=0.15)
     o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro)
     assert np.array_equal(qe, qo)
+
+
+def test_water_management_extract_from_rch():
+    """extract_from_rch in the team code (kwt_reach_team<.., EXT>, between thinning and routing) against Oracle.set_wm, bit for
+    bit.  Reaches whose wave series has no point strictly inside the step make the reference's interp_rch return 0, hence
+    "no water", hence zero flow and kinwav_rch's stop (kwt_route.f90:1603-1606, 421) -- they are found by trial and left out."""
+    net, params, opts, ro = case("random", n=200, seed=21, dt=3600.0, route_opt="2", steps=30)
+    K = ro.shape[0]
+    ob = Oracle(net, params, opts)
+    inflow = []
+    for k in range(K):
+        ob.step(ro[k]); inflow.append(ob.get(orc.F_REACH_INFLOW, orc.M_KWT))
+    low = np.min(np.array(inflow)[4:], axis=0)
+    rng = np.random.default_rng(2)
+    want = np.where(low > 0.0, rng.uniform(-0.2, 0.2, net.nRch) * low, -9999.0)
+    ok = []
+    for j in np.flatnonzero(want != -9999.0)[:60]:
+        one = np.full(net.nRch, -9999.0); one[j] = want[j]
+        oj = Oracle(net, params, opts)
+        try:
+            finite = True
+            for k in range(K):
+                if k == 4:
+                    oj.set_wm(one)
+                oj.step(ro[k])
+                finite = finite and bool(np.isfinite(oj.get(orc.F_REACH_Q, orc.M_KWT)).all())
+            if finite:                                       # (an injection into "no water" divides by zero: inf / NaN waves)
+                ok.append(j)
+        except orc.OracleError:
+            pass
+    assert len(ok) >= 5
+    L = emul.load()
+    p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
+    for j in ok[:5]:
+        flux = np.full((K, net.nRch), -9999.0); flux[4:, j] = want[j]
+        o = Oracle(net, params, opts)
+        qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+        qr[0] = o.get(orc.F_BASIN_QR1)
+        for t in range(K):
+            o.set_wm(flux[t])
+            o.step(ro[t])
+            qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, orc.M_KWT)
+        qe = np.empty((K, net.nRch)); ne = np.empty(net.nRch, dtype=np.int32)
+        msg = C.create_string_buffer(256)
+        ierr = L.kwt_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
+                              p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
+                              C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), p(flux, C.c_double), p(qe, C.c_double),
+                              p(ne, C.c_int), msg)
+        assert ierr == 0, msg.value.decode()
+        assert np.isfinite(qo).all() and np.array_equal(qe, qo), j
+        assert not np.array_equal(qo[-1], ob.get(orc.F_REACH_Q, orc.M_KWT))

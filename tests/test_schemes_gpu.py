@@ -163,7 +163,7 @@ def test_water_management(route, lakes):
     """mr_upload_wm: abstraction / injection fluxes through the storage -> inflow -> lateral-flow cascade of IRF and the Euler
     schemes, lakes losing / gaining the flux, lakes flagged LakeTargVol following their target volume (jump-started)."""
     from mizuroute_b200 import capi
-    from mizuroute_b200.route import Router, RoutingError
+    from mizuroute_b200.route import Router
     from oracle import oracle as orc
     from oracle.oracle import Oracle
     net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0 if lakes else 3600.0, route_opt=route, steps=12, lakes=lakes)
@@ -195,8 +195,41 @@ def test_water_management(route, lakes):
         assert rel_err(qg[i], qo[i], floor=1e-9) <= tol, c
         assert rel_err(r.flux(capi.REACH_VOL1, int(c)), o.get(orc.F_REACH_VOL1, int(c)), floor=1e-3) <= tol
         assert rel_err(r.flux(capi.WB, int(c)), o.get(orc.F_WB, int(c)), floor=1.0) <= 1e-5
-    if route == "1":                                      # fluxes with KWT are refused (extract_from_rch is not on the device)
-        r2 = Router(net, params, type(opts)(**{**opts.__dict__, "route_opt": "2"}), max_batch=8)
-        r2.upload_wm(flux[:5])
-        with pytest.raises(RoutingError, match="extract_from_rch"):
-            r2.route_batch(np.ascontiguousarray(ro[:5]))
+
+
+def test_water_management_in_kwt():
+    """extract_from_rch inside the team KWT kernel (k_route_kwt<true>): one reach at a time, as in tests/test_kwt_emul.py --
+    reaches on which the reference's routine sees "no water" (and then stops in kinwav_rch) are found by trial on the oracle."""
+    from mizuroute_b200.route import Router
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("random", n=200, seed=21, dt=3600.0, route_opt="2", steps=30)
+    K = ro.shape[0]
+    ob = Oracle(net, params, opts)
+    inflow = []
+    for k in range(K):
+        ob.step(ro[k]); inflow.append(ob.get(orc.F_REACH_INFLOW, orc.M_KWT))
+    low = np.min(np.array(inflow)[4:], axis=0)
+    want = np.where(low > 0.0, np.random.default_rng(2).uniform(-0.2, 0.2, net.nRch) * low, -9999.0)
+    done = 0
+    for j in np.flatnonzero(want != -9999.0)[:60]:
+        flux = np.full((K, net.nRch), -9999.0); flux[4:, j] = want[j]
+        o = Oracle(net, params, opts)
+        qo = np.empty((K, net.nRch))
+        try:
+            for t in range(K):
+                o.set_wm(flux[t]); o.step(ro[t]); qo[t] = o.get(orc.F_REACH_Q, orc.M_KWT)
+        except orc.OracleError:
+            continue
+        if not np.isfinite(qo).all():
+            continue
+        r = Router(net, params, opts, max_batch=10)
+        parts = []
+        for s in range(0, K, 10):
+            r.upload_wm(flux[s:s + 10])
+            parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + 10])))
+        assert rel_err(np.concatenate(parts, axis=1)[0], qo) <= 1e-4, j
+        done += 1
+        if done == 3:
+            break
+    assert done == 3
