@@ -66,3 +66,12 @@ def load_irf():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-x", "c++", "-shared", "-fPIC",
                                "-o", _IRF_SO, _IRF_SRC])
     return C.CDLL(_IRF_SO)
+
+
+def load_calendar():
+    """Host build of mr_calendar.h, see calendar_emul.cpp."""
+    so, src = os.path.join(_HERE, "libcalendar_emul.so"), os.path.join(_HERE, "calendar_emul.cpp")
+    deps = [src, os.path.join(_CSRC, "mr_calendar.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    return C.CDLL(so)
