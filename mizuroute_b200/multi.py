@@ -125,6 +125,22 @@ class DomainSet:
             self.main.upload_runoff(np.ascontiguousarray(runoff_global[:, self.main_net.meta["hru_index"]]))
         return K
 
+    def upload_lake_forcing(self, evapo_global: np.ndarray, precip_global: np.ndarray):
+        """Lake evaporation / precipitation [K, nHRU_global] of the next routing call, this rank's HRU columns to its domains."""
+        for dom, sub in ((self.trib, getattr(self, "trib_net", None)), (self.main, getattr(self, "main_net", None))):
+            if dom is not None:
+                cols = sub.meta["hru_index"]
+                dom.upload_lake_forcing(np.ascontiguousarray(evapo_global[:, cols]), np.ascontiguousarray(precip_global[:, cols]))
+
+    def upload_wm(self, flux_global=None, vol_global=None, vol_jumpstart: bool = False):
+        """Water management [K, nRch_global] of the next routing call, this rank's reach columns to its domains (the ghost
+        reaches of the mainstem domain receive their reach's values too; they are not routed there)."""
+        pick = lambda a, cols: None if a is None else np.ascontiguousarray(a[:, cols])
+        for dom, sub in ((self.trib, getattr(self, "trib_net", None)), (self.main, getattr(self, "main_net", None))):
+            if dom is not None:
+                cols = sub.meta["reach_index"]
+                dom.upload_wm(pick(flux_global, cols), pick(vol_global, cols), vol_jumpstart)
+
     def hand_off(self):
         if self.dec.mainstem.size == 0:
             return
