@@ -112,6 +112,10 @@ typedef struct {
     /* water management (is_flux_wm / is_vol_wm, main_route.f90:110-123): abstraction (+) / injection (-) per reach, target
        lake volumes, the volume jump start, and REACH_WM_FLUX_actual per method; wmFlux = NULL: is_flux_wm off (flux 0) */
     const double *wmFlux, *wmVol; int volJumpStart; double *WM_ACTUAL[N_METHOD];
+    /* data assimilation by direct insertion (qmodOption = 1; main_route.f90:124-148, data_assimilation.f90): last observed
+       discharge and steps since then per reach, discharge error per reach and method */
+    int qmodOption, qBlendPeriod, QerrTrend; double *Qobs, *Qerror[N_METHOD]; int *Qelapsed;
+    int obsNow; const double *obsRow;
     /* parametric lake models beyond Doll-2003: per-reach parameters by name (dataTypes.f90:202-254) and the simulation
        start datetime (simDatetime(1) of step 1) the HYPE / Hanasaki formulations read the calendar from */
     double *LP[64];
@@ -481,10 +485,11 @@ mro_t *mro_create(int nRch, int nHRU,
     ALLOC(h->BASIN_QI, nRch); ALLOC(h->BASIN_QR0, nRch); ALLOC(h->BASIN_QR1, nRch);
     ALLOC(h->QFUTURE, (size_t)nRch * h->ntdh_bas); ALLOC(h->qfuture_alloc, nRch);
     ALLOC(h->reachRunoff, nRch); ALLOC(h->reachEvapo, nRch); ALLOC(h->reachPrecip, nRch);
+    ALLOC(h->Qobs, nRch); ALLOC(h->Qelapsed, nRch);
     for (m = 0; m < N_METHOD; m++) {
         ALLOC(h->REACH_Q[m], nRch); ALLOC(h->REACH_VOL0[m], nRch); ALLOC(h->REACH_VOL1[m], nRch);
         ALLOC(h->REACH_INFLOW[m], nRch); ALLOC(h->WB[m], nRch);
-        ALLOC(h->FLOOD_VOL1[m], nRch); ALLOC(h->REACH_ELE[m], nRch); ALLOC(h->WM_ACTUAL[m], nRch);
+        ALLOC(h->FLOOD_VOL1[m], nRch); ALLOC(h->REACH_ELE[m], nRch); ALLOC(h->WM_ACTUAL[m], nRch); ALLOC(h->Qerror[m], nRch);
         if (N_MOLECULE[m] > 0 && h->onRoute[m]) ALLOC(h->MOL[m], (size_t)nRch * N_MOLECULE[m]);   /* molecule%Q(:) = 0, init_model_data.f90:463-497 */
     }
     ALLOC(h->KW, nRch);
@@ -507,7 +512,8 @@ void mro_destroy(mro_t *h)
     free(h->FRAC_FUTURE); free(h->uh_ptr); free(h->uh_val);
     free(h->BASIN_QI); free(h->BASIN_QR0); free(h->BASIN_QR1); free(h->QFUTURE); free(h->qfuture_alloc); free(h->reachRunoff); free(h->reachEvapo); free(h->reachPrecip);
     for (m = 0; m < N_METHOD; m++) { free(h->REACH_Q[m]); free(h->REACH_VOL0[m]); free(h->REACH_VOL1[m]); free(h->REACH_INFLOW[m]); free(h->WB[m]);
-                                     free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); free(h->WM_ACTUAL[m]); }
+                                     free(h->FLOOD_VOL1[m]); free(h->REACH_ELE[m]); free(h->MOL[m]); free(h->WM_ACTUAL[m]); free(h->Qerror[m]); }
+    free(h->Qobs); free(h->Qelapsed);
     { int k; for (k = 0; k < 64; k++) free(h->LP[k]); }
     if (h->h06Mem) { int k; for (k = 0; k < h->nRch; k++) free(h->h06Mem[k]); free(h->h06Mem); free(h->h06Len); }
     free(h->R_DEPTH); free(h->SIDE_SLOPE); free(h->FLDP_SLOPE); free(h->R_STORAGE);
@@ -607,6 +613,40 @@ static void wm_cascade(mro_t *h, int M, int j, double q_upstream, double *q_upst
     }
 }
 
+/* data_assimilation.f90:23-97: pull REACH_Q towards the last observation, the correction fading over qBlendPeriod steps */
+static int direct_insertion(mro_t *h, int M, int j)
+{
+    double *Qerror = &h->Qerror[M][j], Qcorrect, k, x0, y0;
+    const int Qelapsed = h->Qelapsed[j], blend = h->qBlendPeriod;
+    if (h->Qobs[j] > 0.0) *Qerror = h->REACH_Q[M][j] - h->Qobs[j];
+    if (Qelapsed > blend) *Qerror = 0.0;
+    if (Qelapsed <= blend) {
+        switch (h->QerrTrend) {
+            case 1: Qcorrect = *Qerror; break;
+            case 2: Qcorrect = *Qerror * (1.0 - (double)Qelapsed / (double)blend); break;
+            case 3:
+                x0 = 0.25; y0 = (double)0.90f;       /* single-precision literals, data_assimilation.f90:76 */
+                k = log(1.0 / y0 - 1.0) / (blend / 2.0 - blend * x0);
+                Qcorrect = *Qerror / (1.0 + exp(-k * (1.0 * Qelapsed - blend / 2.0)));
+                break;
+            case 4:
+                if (*Qerror != 0.0) { k = log(0.1 / fabs(*Qerror)) / (1.0 * blend); Qcorrect = *Qerror * exp(k * Qelapsed); }
+                else Qcorrect = 0.0;
+                break;
+            default: snprintf(h->message, 256, "direct_insertion/discharge error trend model must be 1(const),2(liear), or 3(logistic)"); return 81;
+        }
+    } else Qcorrect = 0.0;
+    h->REACH_Q[M][j] = fmax(h->REACH_Q[M][j] - Qcorrect, 0.0);
+    return 0;
+}
+
+/* river reaches: direct insertion when qmodOption = 1, else the water balance (irf_route.f90:188-202 and the Euler schemes) */
+static int finish_reach(mro_t *h, int m, int j, double Qupstream, double Qlat)
+{
+    if (h->qmodOption == 1) return direct_insertion(h, m, j);
+    comp_reach_wb_lake(h, m, j, Qupstream, Qlat, 0);
+    return 0;
+}
 static void comp_reach_wb(mro_t *h, int m, int j, double Qupstream, double Qlat) { comp_reach_wb_lake(h, m, j, Qupstream, Qlat, 0); }
 
 /* accum_runoff.f90:60-75 */
@@ -658,8 +698,7 @@ static int irf_rch(mro_t *h, int j)
         h->REACH_Q[M][j] = QF[0] + Qlat;
         h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0;
     }
-    comp_reach_wb(h, M, j, q_in, Qlat);
-    return 0;
+    return finish_reach(h, M, j, q_in, Qlat);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -881,8 +920,7 @@ static int kw_dw_rch(mro_t *h, int M, int j)
         for (i = 0; i < nMol; i++) mol[i] = 0.0;
         mol[nMol - 1] = h->REACH_Q[M][j];
     }
-    comp_reach_wb(h, M, j, q_in, Qlat);
-    return 0;
+    return finish_reach(h, M, j, q_in, Qlat);
 }
 
 /* mc_route.f90:45-418: Muskingum-Cunge with sub-stepping when the Courant number exceeds one */
@@ -952,8 +990,7 @@ static int mc_rch(mro_t *h, int j)
         h->REACH_VOL0[M][j] = 0.0; h->REACH_VOL1[M][j] = 0.0; h->FLOOD_VOL1[M][j] = 0.0; h->REACH_ELE[M][j] = 0.0;
     }
     mol[0] = Q10; mol[1] = Q11;
-    comp_reach_wb(h, M, j, q_in, Qlat);
-    return 0;
+    return finish_reach(h, M, j, q_in, Qlat);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -1555,16 +1592,34 @@ static int route_one(mro_t *h, int M, int j, double T0, double T1, wave_buf_t *b
 int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const double *basinEvapo, const double *basinPrecip);
 int mro_step(mro_t *h, double T0, double T1, const double *basinRunoff) { return mro_step_ep(h, T0, T1, basinRunoff, NULL, NULL); }
 
-/* basinEvapo / basinPrecip [nHRU] in the units of the runoff (NULL = no lake forcing: exactly zero in lake_route) */
+/* data assimilation (public_var.f90:189-191 qmodOption, qBlendPeriod, QerrTrend), and the gauge observations of the NEXT step
+   only: obs [nRch] in the caller's reach order, NaN or < 0 = no gauge value there; NULL = the gauge file has no record at that
+   time (gage_obs_data%time_ix = integerMissing) */
+void mro_set_da(mro_t *h, int qmodOption, int qBlendPeriod, int QerrTrend) { h->qmodOption = qmodOption; h->qBlendPeriod = qBlendPeriod; h->QerrTrend = QerrTrend; }
+void mro_set_obs(mro_t *h, const double *obs) { h->obsNow = obs != NULL; h->obsRow = obs; }
+
 /* water management forcing of the NEXT steps (until changed): flux_wm / vol_wm [nRch] in the caller's reach order, NULL = off */
 void mro_set_wm(mro_t *h, const double *flux_wm, const double *vol_wm, int volJumpStart)
 {
     h->wmFlux = flux_wm; h->wmVol = (vol_wm && h->is_lake_sim) ? vol_wm : NULL; h->volJumpStart = volJumpStart;
 }
 
+/* basinEvapo / basinPrecip [nHRU] in the units of the runoff (NULL = no lake forcing: exactly zero in lake_route) */
 int mro_step_ep(mro_t *h, double T0, double T1, const double *basinRunoff, const double *basinEvapo, const double *basinPrecip)
 {
     int j, r, ierr;
+    if (h->qmodOption == 1) {             /* main_route.f90:125-148: before the runoff is mapped */
+        if (h->obsNow) {
+            for (j = 0; j < h->nRch; j++) {
+                const double qobs = h->obsRow[j];
+                if ((qobs != qobs) || (qobs < 0)) continue;
+                h->Qobs[j] = qobs; h->Qelapsed[j] = 0;
+            }
+        } else {
+            for (j = 0; j < h->nRch; j++) h->Qelapsed[j] = h->Qelapsed[j] + 1;
+        }
+        h->obsNow = 0; h->obsRow = NULL;
+    } else if (h->qmodOption != 0) { snprintf(h->message, 256, "main_route/Error: qmodOption invalid"); return 1; }
     ierr = basin2reach(h, basinRunoff, h->reachRunoff, 1);
     if (ierr) return ierr;
     h->hasEP = (h->is_lake_sim && basinEvapo && basinPrecip);
@@ -1645,6 +1700,7 @@ void mro_get_lake_forcing(mro_t *h, double *evapo, double *precip) { memcpy(evap
 /* accessors                                                                                   */
 /* ------------------------------------------------------------------------------------------ */
 enum { F_REACH_Q = 0, F_REACH_VOL1 = 1, F_REACH_INFLOW = 2, F_WB = 3, F_BASIN_QI = 4, F_BASIN_QR1 = 5, F_BASIN_QR0 = 6, F_REACH_VOL0 = 7,
+       F_QERROR = 8, F_QOBS = 9,
        F_WIDTH = 10, F_TOTAREA = 11, F_BASAREA = 12, F_SLOPE = 13 };
 
 int mro_get(mro_t *h, int method, int field, double *out)
@@ -1659,6 +1715,8 @@ int mro_get(mro_t *h, int method, int field, double *out)
         case F_BASIN_QI: src = h->BASIN_QI; break;
         case F_BASIN_QR1: src = h->BASIN_QR1; break;
         case F_BASIN_QR0: src = h->BASIN_QR0; break;
+        case F_QERROR: src = h->Qerror[method]; break;
+        case F_QOBS: src = h->Qobs; break;
         case F_WIDTH: src = h->R_WIDTH; break;
         case F_TOTAREA: src = h->TOTAREA; break;
         case F_BASAREA: src = h->BASAREA; break;
@@ -1689,6 +1747,8 @@ int mro_set(mro_t *h, int method, int field, const double *in)
         case F_REACH_VOL0: dst = h->REACH_VOL0[method]; break;
         case F_BASIN_QR1: dst = h->BASIN_QR1; break;
         case F_BASIN_QR0: dst = h->BASIN_QR0; break;
+        case F_QERROR: dst = h->Qerror[method]; break;
+        case F_QOBS: dst = h->Qobs; break;
         default: return 1;
     }
     memcpy(dst, in, sizeof(double) * h->nRch);
@@ -1698,6 +1758,8 @@ int mro_n_molecule(int method) { return method >= 0 && method < N_METHOD ? N_MOL
 void mro_get_molecule(mro_t *h, int method, double *out) { if (h->MOL[method]) memcpy(out, h->MOL[method], sizeof(double) * (size_t)h->nRch * N_MOLECULE[method]); }
 void mro_set_molecule(mro_t *h, int method, const double *in) { if (h->MOL[method]) memcpy(h->MOL[method], in, sizeof(double) * (size_t)h->nRch * N_MOLECULE[method]); }
 void mro_set_itime(mro_t *h, long it) { h->iTime = it; }
+void mro_get_qelapsed(mro_t *h, int *out) { memcpy(out, h->Qelapsed, sizeof(int) * h->nRch); }
+void mro_set_qelapsed(mro_t *h, const int *in) { memcpy(h->Qelapsed, in, sizeof(int) * h->nRch); }
 void mro_set_threads(mro_t *h, int n) { h->nThreads = n > 0 ? n : 1; }
 /* KWT state in the restart layout [seg][wave] (write_restart_pio.f90:1039-1134), wave dimension = cap */
 void mro_get_kwt_state(mro_t *h, int cap, int *numWaves, double *qf, double *ti, double *tr, unsigned char *rf)

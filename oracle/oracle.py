@@ -19,6 +19,7 @@ M_SUM, M_IRF, M_KWT, M_KW, M_MC, M_DW = range(6)        # = the digits of <route
 METHOD_OF_DIGIT = {str(m): m for m in range(6)}
 N_MOLECULE = {M_KW: 20, M_MC: 2, M_DW: 20}               # init_model_data.f90:386-393
 F_REACH_Q, F_REACH_VOL1, F_REACH_INFLOW, F_WB, F_BASIN_QI, F_BASIN_QR1, F_BASIN_QR0, F_REACH_VOL0 = range(8)
+F_QERROR, F_QOBS = 8, 9
 F_WIDTH, F_TOTAREA, F_BASAREA, F_SLOPE = 10, 11, 12, 13
 KW_CAP = 24
 
@@ -140,6 +141,22 @@ class Oracle:
         self._wm = (None if flux_wm is None else np.ascontiguousarray(flux_wm, dtype=np.float64),
                     None if vol_wm is None else np.ascontiguousarray(vol_wm, dtype=np.float64))     # kept alive: the C side holds the pointers
         lib().mro_set_wm(self.h, _p(self._wm[0], C.c_double), _p(self._wm[1], C.c_double), C.c_int(int(vol_jumpstart)))
+
+    def set_da(self, qmod_option: int = 1, q_blend_period: int = 10, q_err_trend: int = 1):
+        """Data assimilation by direct insertion (<qmodOption> 1, <qBlendPeriod>, <QerrTrend> 1 constant / 2 linear /
+        3 logistic / 4 exponential; public_var.f90:189-191)."""
+        lib().mro_set_da(self.h, C.c_int(int(qmod_option)), C.c_int(int(q_blend_period)), C.c_int(int(q_err_trend)))
+
+    def set_obs(self, obs=None):
+        """Gauge observations [m3/s] of the NEXT step only: obs [nRch], NaN or negative = no value at that reach; None = the
+        gauge file has no record at that time (every reach's Qelapsed goes up by one)."""
+        self._obs = None if obs is None else np.ascontiguousarray(obs, dtype=np.float64)   # kept alive until the step
+        lib().mro_set_obs(self.h, _p(self._obs, C.c_double))
+
+    def qelapsed(self) -> np.ndarray:
+        out = np.empty(self.net.nRch, dtype=np.int32)
+        lib().mro_get_qelapsed(self.h, _p(out, C.c_int))
+        return out
 
     def lake_forcing(self):
         """(reach evaporation, reach precipitation) [m3/s] of the last step; the evaporation is what lake_route left

@@ -551,6 +551,55 @@ class Twin:
         self.wm_flux = self.wm_vol = None
         self.wm_jump = False
         self.WMA = {m: [0.0] * n for m in range(6)}      # REACH_WM_FLUX_actual per method
+        self.qmod, self.blend, self.trend, self.obs = 0, 10, 1, None
+        self.Qobs, self.Qelapsed = [0.0] * n, [0] * n             # init_model_data.f90:404-405
+        self.Qerr = {m: [0.0] * n for m in range(6)}
+
+    # -- data assimilation by direct insertion: main_route.f90:125-148, data_assimilation.f90:23-97 --------------
+    def set_da(self, qmod_option=1, q_blend_period=10, q_err_trend=1):
+        self.qmod, self.blend, self.trend = int(qmod_option), int(q_blend_period), int(q_err_trend)
+
+    def set_obs(self, obs=None):
+        self.obs = None if obs is None else [float(x) for x in obs]
+
+    def _read_obs(self):
+        if self.obs is not None:
+            for j, q in enumerate(self.obs):
+                if math.isnan(q) or q < 0:
+                    continue
+                self.Qobs[j] = q
+                self.Qelapsed[j] = 0
+        else:
+            self.Qelapsed = [e + 1 for e in self.Qelapsed]
+        self.obs = None
+
+    def _finish(self, m, j, qup, qlat):
+        """End of a river reach: direct insertion instead of the water balance when qmodOption = 1."""
+        if self.qmod != 1:
+            return self._wb(m, j, qup, qlat)
+        el, blend = self.Qelapsed[j], self.blend
+        if self.Qobs[j] > 0.0:
+            self.Qerr[m][j] = self.Q[m][j] - self.Qobs[j]
+        if el > blend:
+            self.Qerr[m][j] = 0.0
+        err = self.Qerr[m][j]
+        corr = 0.0
+        if el <= blend:
+            if self.trend == 1:
+                corr = err
+            elif self.trend == 2:
+                corr = err * (1.0 - float(el) / float(blend))
+            elif self.trend == 3:
+                x0, y0 = 0.25, _f32(0.90)
+                k = math.log(1.0 / y0 - 1.0) / (blend / 2.0 - blend * x0)
+                corr = err / (1.0 + math.exp(-k * (1.0 * el - blend / 2.0)))
+            elif self.trend == 4:
+                if err != 0.0:
+                    k = math.log(0.1 / abs(err)) / (1.0 * blend)
+                    corr = err * math.exp(k * el)
+            else:
+                raise RouteError(81, "direct_insertion/discharge error trend model must be 1(const),2(liear), or 3(logistic)")
+        self.Q[m][j] = max(self.Q[m][j] - corr, 0.0)
 
     def set_wm(self, flux_wm=None, vol_wm=None, vol_jumpstart=False):
         self.wm_flux = None if flux_wm is None else [float(x) for x in flux_wm]
@@ -606,6 +655,10 @@ class Twin:
     def step(self, runoff, evapo=None, precip=None):
         o = self.o
         n = self.n
+        if self.qmod == 1:
+            self._read_obs()
+        elif self.qmod != 0:
+            raise RouteError(1, "main_route/Error: qmodOption invalid")
         rr = self._basin2reach(runoff)
         # lake evaporation / precipitation go through the same basin2reach (main_route.f90:174-199); None = exactly zero
         self.has_ep = bool(o.is_lake_sim and evapo is not None and precip is not None)
@@ -790,7 +843,7 @@ class Twin:
             self.Q[m][j] = qf[0] + qlat
             self.V0[m][j] = 0.0
             self.V1[m][j] = 0.0
-        self._wb(m, j, q_in, qlat)
+        self._finish(m, j, q_in, qlat)
 
     # -- Euler schemes: kwe_route.f90, dfw_route.f90, mc_route.f90 ---------------------------------
     def _inflow(self, j, m):
@@ -852,7 +905,7 @@ class Twin:
             self.Q[m][j] = qlat
             self.mol[m][j] = [0.0] * (nm - 1) + [qlat]
             self._dry(j, m)
-        self._wb(m, j, q_in, qlat)
+        self._finish(m, j, q_in, qlat)
 
     def _mc(self, j):
         m, dt, L = 4, self.o.dt, self.length[j]
@@ -909,7 +962,7 @@ class Twin:
             self.Q[m][j] = qlat
             self._dry(j, m)
         self.mol[m][j] = [q10, q11]
-        self._wb(m, j, q_in, qlat)
+        self._finish(m, j, q_in, qlat)
 
     def _lake(self, j, m):
         dt, net = self.o.dt, self.net

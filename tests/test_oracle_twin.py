@@ -261,3 +261,59 @@ def test_water_management_in_kwt_scales_the_waves():
             o.step(ro[k]); t.step(ro[k])
             assert rel_err(o.get(orc.F_REACH_Q, orc.M_KWT), np.array(t.Q[2])) <= 1e-12, (j, k)
     assert not np.array_equal(o.get(orc.F_REACH_Q, orc.M_KWT), base_last)
+
+
+@pytest.mark.parametrize("trend", [1, 2, 3, 4])
+def test_direct_insertion(trend):
+    """qmodOption = 1 (main_route.f90:125-148, data_assimilation.f90:23-97): at a gauge reach REACH_Q of IRF / KW / MC / DW is
+    pulled to the last observation, the correction fading over qBlendPeriod steps by QerrTrend; KWT and SUM are left alone;
+    the water balance of the corrected methods is not evaluated.  Oracle = twin; and the documented behaviour itself."""
+    net, params, opts, ro = case("random", n=120, seed=21, dt=86400.0, route_opt="012345", steps=16)
+    blend = 5
+    o = orc.Oracle(net, params, opts); t = Twin(net, params, opts)
+    base = orc.Oracle(net, params, opts)
+    o.set_da(1, blend, trend); t.set_da(1, blend, trend)
+    rng = np.random.default_rng(3)
+    gauges = rng.choice(net.nRch, 15, replace=False)
+    obs_steps = {2, 3, 9}                       # records of the gauge file; in between the reaches drift back
+    last_obs = np.zeros(net.nRch)
+    for k in range(ro.shape[0]):
+        base.step(ro[k])
+        if k in obs_steps:
+            obs = np.full(net.nRch, np.nan)
+            obs[gauges] = base.get(orc.F_REACH_Q, orc.M_IRF)[gauges] * rng.uniform(0.3, 2.5, gauges.size)
+            obs[gauges[0]] = -1.0               # negative and missing values are skipped (main_route.f90:139)
+            o.set_obs(obs); t.set_obs(obs)
+            good = gauges[1:]
+            last_obs[good] = obs[good]
+        else:
+            o.set_obs(None); t.set_obs(None)
+        o.step(ro[k]); t.step(ro[k])
+        for m in t.methods:
+            assert rel_err(o.get(orc.F_REACH_Q, m), np.array(t.Q[m])) <= 1e-12, (k, m)
+            assert rel_err(o.get(orc.F_QERROR, m), np.array(t.Qerr[m]), floor=1e-9) <= 1e-10, (k, m)
+        assert (o.qelapsed() == np.array(t.Qelapsed)).all()
+        for m in (orc.M_SUM, orc.M_KWT):        # no direct_insertion call in accum_runoff / kwt_route
+            if m == orc.M_SUM:
+                assert (o.get(orc.F_REACH_Q, m) == base.get(orc.F_REACH_Q, m)).all()
+        if k in obs_steps and trend in (1, 2):  # elapsed 0: the full error is removed -> the observation itself
+            for m in (1, 3, 4, 5):
+                assert rel_err(o.get(orc.F_REACH_Q, m)[gauges[1:]], last_obs[gauges[1:]]) <= 1e-12
+    # after the blend period the error is forgotten ...
+    el = o.qelapsed()                           # gauges: steps since their last value; the others: every step without a record
+    assert (el[gauges[1:]] == 16 - 1 - 9).all() and 16 - 1 - 9 > blend and (el[never_seen := np.setdiff1d(np.arange(net.nRch), gauges[1:])] == 16 - 3).all()
+    for m in (1, 3, 4, 5):
+        assert (o.get(orc.F_QERROR, m) == 0.0).all()
+    # ... and a reach that never saw an observation keeps Qerror = 0 throughout
+    never = np.setdiff1d(np.arange(net.nRch), gauges)
+    assert (np.array(t.Qerr[1])[never] == 0.0).all()
+
+
+def test_direct_insertion_rejects_unknown_options():
+    net, params, opts, ro = case("random", n=20, seed=2, dt=86400.0, route_opt="1", steps=2)
+    o = orc.Oracle(net, params, opts); o.set_da(1, 5, 7)
+    with pytest.raises(orc.OracleError, match="discharge error trend"):
+        o.step(ro[0])
+    o = orc.Oracle(net, params, opts); o.set_da(2, 5, 1)
+    with pytest.raises(orc.OracleError, match="qmodOption invalid"):
+        o.step(ro[0])
