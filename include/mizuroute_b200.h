@@ -42,6 +42,7 @@ enum { MR_ACCUM_RUNOFF = 0, MR_IMPULSE_RESPONSE_FUNC = 1, MR_KINEMATIC_WAVE_TRAC
 enum {
     MR_REACH_Q = 0, MR_REACH_VOL1 = 1, MR_REACH_INFLOW = 2, MR_WB = 3,
     MR_BASIN_QI = 4, MR_BASIN_QR1 = 5, MR_BASIN_QR0 = 6, MR_REACH_VOL0 = 7,
+    MR_QERROR = 8,               /* ROUTE(:)%Qerror of IRF / KW / MC / DW under data assimilation (dataTypes.f90:354) */
     /* derived reach parameters (RCHPRP, dataTypes.f90:183-255) */
     MR_R_WIDTH = 10, MR_TOTAREA = 11, MR_BASAREA = 12, MR_R_SLOPE = 13,
     MR_NGOOD = 14                /* count(goodBas), network_topo.f90:769-775 (as a double) */
@@ -64,7 +65,12 @@ enum {
     MR_ST_LAKE_VOL      = 9,   /* double [nRoutes][nRch]       REACH_VOL(1) of every active method ("volume_irf|kwt|kw|mc|dw") */
     MR_ST_MOLECULE_KW   = 10,  /* double [nRch][20]            "q_sub_kw": molecule%Q of the kinematic wave (init_model_data.f90:388) */
     MR_ST_MOLECULE_MC   = 11,  /* double [nRch][2]             "q_sub_mc": inflow / outflow of the previous step */
-    MR_ST_MOLECULE_DW   = 12   /* double [nRch][20]            "q_sub_dw" */
+    MR_ST_MOLECULE_DW   = 12,  /* double [nRch][20]            "q_sub_dw" */
+    MR_ST_QERROR        = 13,  /* double [nRoutes][nRch]       Qerror of every active method (restart variables of ixIRF%qerror .. ixDW%qerror,
+                                  read_restart.f90:381,538,611,684; zero for SUM and KWT, which are not corrected) */
+    MR_ST_DA_QOBS       = 14,  /* double [nRch]                RCHFLX%Qobs, the last gauge value seen (not in the reference's restart file, which
+                                  starts again from 0: init_model_data.f90:511-512) */
+    MR_ST_DA_QELAPSED   = 15   /* int    [nRch]                RCHFLX%Qelapsed, steps since then (likewise) */
 };
 
 /* integer facts about a handle, mr_get_info */
@@ -155,6 +161,17 @@ int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, co
  * extract_from_rch of KWT (kwt_route.f90:351-455; note that it reads the sign the other way round) and the lake fluxes /
  * target volumes (lake_route.f90:137-139,176-203). */
 int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *vol_wm, int volJumpStart, char *message);
+/* Data assimilation by direct insertion (<qmodOption> 1, <qBlendPeriod>, <QerrTrend> 1 constant / 2 linear / 3 logistic /
+ * 4 exponential; public_var.f90:189-191): where a gauge value is known, REACH_Q of IRF, KW, MC and DW is pulled to it, the
+ * correction fading over qBlendPeriod steps (data_assimilation.f90:23-97; irf_route.f90:188-199 and the Euler schemes); the
+ * water balance of those methods is then not evaluated (:200-202).  SUM and KWT are not corrected.  qmodOption 0 = off.
+ * Errors as the reference: ierr 1 "qmodOption invalid" (main_route.f90:146-147), ierr 81 for an unknown trend model. */
+int mr_set_da(mr_handle h, int qmodOption, int qBlendPeriod, int QerrTrend, char *message);
+/* Gauge observations of the NEXT routing call (which must route exactly nSteps steps): obs [nSteps][nRch] in m3/s, caller's
+ * reach order, NaN or negative = no value at that reach (main_route.f90:136-142: gage_obs_data%read_obs + link_ix);
+ * hasRecord [nSteps], 0 = the gauge file has no record at that step (time_ix = integerMissing: every reach's Qelapsed goes up
+ * by one, :143-145), NULL = every step has one.  A routing call without a preceding upload is a stretch without records. */
+int mr_upload_obs(mr_handle h, int nSteps, const int *hasRecord, const double *obs, char *message);
 /* Per-reach parameters of the parametric lake models beyond Doll-2003, by their name in RCHPRP (dataTypes.f90:202-213):
  * HYP_E_emr, HYP_E_lim, HYP_E_min, HYP_E_zero, HYP_Qrate_emr, HYP_Erate_emr, HYP_Qrate_prim, HYP_Qrate_amp, HYP_Qrate_phs,
  * HYP_prim_F, HYP_A_avg, HYP_Qsim_mode, and (dataTypes.f90:215-254) H06_Smax, H06_alpha, H06_envfact, H06_S_ini, H06_c1, H06_c2,

@@ -15,12 +15,13 @@ MR_STRLEN = 256
 MR_KW_SLOTS = 22
 
 # flux fields
-REACH_Q, REACH_VOL1, REACH_INFLOW, WB, BASIN_QI, BASIN_QR1, BASIN_QR0, REACH_VOL0 = range(8)
+REACH_Q, REACH_VOL1, REACH_INFLOW, WB, BASIN_QI, BASIN_QR1, BASIN_QR0, REACH_VOL0, QERROR = range(9)
 R_WIDTH, TOTAREA, BASAREA, R_SLOPE, NGOOD = 10, 11, 12, 13, 14
 KW_PITCH = 24            # particle-row pitch of an exchange record
 # state variables
 (ST_BASIN_QFUTURE, ST_BASIN_QR, ST_IRF_QFUTURE, ST_IRF_VOL, ST_KWT_NWAVE, ST_KWT_QWAVE, ST_KWT_TENTRY,
- ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL, ST_MOLECULE_KW, ST_MOLECULE_MC, ST_MOLECULE_DW) = range(13)
+ ST_KWT_TEXIT, ST_KWT_ROUTED, ST_LAKE_VOL, ST_MOLECULE_KW, ST_MOLECULE_MC, ST_MOLECULE_DW,
+ ST_QERROR, ST_DA_QOBS, ST_DA_QELAPSED) = range(16)
 N_MOLECULE = {3: 20, 4: 2, 5: 20}     # nodes of the Euler schemes' molecules (route methods 3 KW, 4 MC, 5 DW)
 # info keys
 (INFO_NRCH, INFO_NHRU, INFO_NSTAGE, INFO_NTDH_BAS, INFO_MAXTDH, INFO_LAUNCHES_LAST, INFO_STEPS_DONE,
@@ -33,7 +34,7 @@ EXPORTS = [
     "mr_download_q", "mr_download_basin_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
     "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_remap", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
-    "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start", "mr_upload_wm",
+    "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start", "mr_upload_wm", "mr_set_da", "mr_upload_obs",
 ]
 
 
@@ -117,6 +118,8 @@ def load(rebuild_if_stale: bool = True):
     L.mr_copy_exchange.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, cp]
     L.mr_upload_lake_forcing.argtypes = [vp, C.c_int, dp, dp, cp]
     L.mr_upload_wm.argtypes = [vp, C.c_int, dp, dp, C.c_int, cp]
+    L.mr_set_da.argtypes = [vp, C.c_int, C.c_int, C.c_int, cp]
+    L.mr_upload_obs.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, cp]
     L.mr_set_lake_param.argtypes = [vp, cp, C.c_int, dp, cp]
     L.mr_set_sim_start.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, cp]
     L.mr_destroy.argtypes = [vp]

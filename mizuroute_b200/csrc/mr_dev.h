@@ -86,6 +86,10 @@ struct DevNet {
     int *err;                       // [0] code (0 = ok) [1] position [2] site
     unsigned *kwCount;              // optional per-reach count of particles read+written (nullptr = off)
     unsigned long long *kwProf;     // optional [8][2] cycles / tasks per task class (development profile, nullptr = off)
+    // (last, so that the parameter offsets the other kernels read stay where they were)
+    // data assimilation by direct insertion (mr_set_da / mr_upload_obs; daQobs == nullptr = off): RCHFLX%Qobs and %Qelapsed as
+    // every step of the batch sees them [kmax][nRch] in stage order (written by k_da_rows), and ROUTE(:)%Qerror per method
+    const double *daQobs; const int *daElapsed; double *qerr[N_METHODS]; int qBlendPeriod, qErrTrend;
 };
 
 // site ids for error messages (decoded in mr_lib.cu)
@@ -134,6 +138,48 @@ MR_DEV double wm_cascade(double want, double dt, double &v1, double &qup, double
         qlat = qlat - Qabs;
     }
     return actual;
+}
+
+// Gauge observations of a batch -> what direct_insertion sees at every step (main_route.f90:125-148).  obs [K][N] holds the
+// gauge values of the steps (NaN / negative = none at that reach) and is overwritten by RCHFLX%Qobs; el [K][N] receives
+// RCHFLX%Qelapsed; hasRecord[t] = 0: the gauge file has no record at step t (every reach's Qelapsed goes up by one).  The
+// running Qobs / Qelapsed of the reach (qobsState, elState) carry over to the next batch.  One thread per reach.
+MR_DEV void da_rows(double *obs, int *el, double *qobsState, int *elState, const unsigned char *hasRecord, int N, int p, int K) {
+    double qobs = qobsState[p];
+    int e = elState[p];
+    for (int t = 0; t < K; ++t) {
+        if (hasRecord[t]) {
+            const double v = obs[(size_t)t * N + p];
+            if (!((v != v) || (v < 0))) { qobs = v; e = 0; }
+        } else e = e + 1;
+        obs[(size_t)t * N + p] = qobs; el[(size_t)t * N + p] = e;
+    }
+    qobsState[p] = qobs; elState[p] = e;
+}
+
+// direct_insertion (data_assimilation.f90:23-97) of method M at (reach p, step t): returns the corrected REACH_Q.  The trend
+// model (1 constant, 2 linear, 3 logistic, 4 exponential) is validated by mr_set_da.
+MR_DEV_NOINLINE double direct_insertion(const DevNet &d, int M, int p, int t, double q) {
+    const size_t i = (size_t)t * d.nRch + p;
+    const double qobs = d.daQobs[i];
+    const int el = d.daElapsed[i], blend = d.qBlendPeriod;
+    double qerror = d.qerr[M][p], qcorrect = 0.0;
+    if (qobs > 0.0) qerror = q - qobs;
+    if (el > blend) qerror = 0.0;
+    if (el <= blend) {
+        if (d.qErrTrend == 1) qcorrect = qerror;
+        else if (d.qErrTrend == 2) qcorrect = qerror * (1.0 - (double)el / (double)blend);
+        else if (d.qErrTrend == 3) {
+            const double x0 = 0.25, y0 = (double)0.90f;            // single-precision literals, data_assimilation.f90:76
+            const double k = log(1.0 / y0 - 1.0) / (blend / 2.0 - blend * x0);
+            qcorrect = qerror / (1.0 + exp(-k * (1.0 * el - blend / 2.0)));
+        } else if (qerror != 0.0) {
+            const double k = log(0.1 / fabs(qerror)) / (1.0 * blend);
+            qcorrect = qerror * exp(k * el);
+        }
+    }
+    d.qerr[M][p] = qerror;
+    return fmax(q - qcorrect, 0.0);
 }
 
 // one out-of-line copy of pow(): its inlined body is ~250 instructions per call site

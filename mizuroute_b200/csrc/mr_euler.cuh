@@ -224,6 +224,11 @@ MR_DEV void kw_dw_reach(const DevNet &d, int p, int t) {
         for (int i = 0; i < NM - 1; ++i) mol[(size_t)i * N] = 0.0;
         mol[(size_t)(NM - 1) * N] = q;
     }
+    if (EXT && d.daQobs) {                                         // qmodOption 1: direct insertion, no water balance
+        d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
+        d.qSer[M][(size_t)t * N + p] = direct_insertion(d, M, p, t, q);
+        return;
+    }
     d.qSer[M][(size_t)t * N + p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
     d.wb[M][p] = euler_wb(v1, v0, qin, qlat, q, dt, took);
@@ -305,6 +310,11 @@ MR_DEV void mc_reach(const DevNet &d, int p, int t) {
         v0 = 0.0; v1 = 0.0;
     }
     mol[0] = Q10; mol[N] = Q11;
+    if (EXT && d.daQobs) {                                         // qmodOption 1: direct insertion, no water balance
+        d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
+        d.qSer[M][(size_t)t * N + p] = direct_insertion(d, M, p, t, q);
+        return;
+    }
     d.qSer[M][(size_t)t * N + p] = q;
     d.vol0[M][p] = v0; d.vol1[M][p] = v1; d.floodVol[M][p] = flood; d.reachEle[M][p] = ele;
     d.wb[M][p] = euler_wb(v1, v0, qin, qlat, q, dt, took);

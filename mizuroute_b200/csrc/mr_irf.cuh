@@ -73,6 +73,11 @@ MR_DEV void irf_reach(const DevNet &d, int p, int t, long long tau) {
         q = qup + qlat;
         v0 = 0.0; v1 = 0.0;
     }
+    if (EXT && d.daQobs) {                                                  // qmodOption 1: no water balance, irf_route.f90:188-202
+        d.vol0[M_IRF][p] = v0; d.vol1[M_IRF][p] = v1;
+        Qs[p] = direct_insertion(d, M_IRF, p, t, q);
+        return;
+    }
     Qs[p] = q;
     d.vol0[M_IRF][p] = v0; d.vol1[M_IRF][p] = v1;
     d.wb[M_IRF][p] = reach_wb(v1, v0, qin, qlat, q, dt, took);

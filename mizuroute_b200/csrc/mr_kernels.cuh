@@ -173,6 +173,12 @@ __global__ void k_lake_forcing(DevNet d, const int *lakePos, int K) {
     d.lakePrecip[(size_t)t * d.nLake + slot] = lake_basin2reach(d, p, d.precip + (size_t)t * d.nHRU);
 }
 
+// gauge observations of the batch -> RCHFLX%Qobs / %Qelapsed rows (da_rows, mr_dev.h); coalesced over the reaches
+__global__ void k_da_rows(double *obs, int *el, double *qobsState, int *elState, const unsigned char *hasRecord, int N, int K) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < N) da_rows(obs, el, qobsState, elState, hasRecord, N, p, K);
+}
+
 // carry BASIN_QR(1) of the previous batch into row 0 of the series
 __global__ void k_carry_qr(double *qrSer, int N, int Kprev) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -71,6 +71,12 @@ struct mr_handle_s {
     int wmSteps = 0, wmJumpStart = 0; bool wmHasFlux = false, wmHasVol = false, wmActive = false, lakeForcingActive = false;
     double *dWmFlux = nullptr, *dWmVol = nullptr; unsigned char *dLakeTargVol = nullptr;
     std::vector<double> wmStage;
+    // data assimilation by direct insertion (mr_set_da, mr_upload_obs): options, the rows of the next batch and the running
+    // Qobs / Qelapsed of every reach (device, stage order)
+    int qmodOption = 0, qBlendPeriod = 10, qErrTrend = 1, obsSteps = 0; bool daActive = false;
+    double *dDaQobs = nullptr, *dQobsState = nullptr, *dQerr[N_METHODS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int *dDaEl = nullptr, *dElState = nullptr; unsigned char *dHasRecord = nullptr;
+    std::vector<unsigned char> hasRecordHost;
     // lake forcing (mr_upload_lake_forcing): HRU-level rows of the next batch and their reach-level values at the lake reaches
     int nLake = 0, lakeForcingSteps = 0;
     int *dLakePos = nullptr;
@@ -179,10 +185,10 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     if constexpr (M == M_KWT) {
         int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
     } else {
-        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
+        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
     }
     h->launchesLast++;
@@ -203,6 +209,22 @@ int check_ready(mr_handle h, int nSteps, const char *where, char *message) {
     return 0;
 }
 
+// first use of data assimilation on this network: rows of one batch, the running Qobs / Qelapsed (0, init_model_data.f90:404-405)
+// and Qerror of the methods that call direct_insertion (IRF, KW, MC, DW)
+int ensure_da(mr_handle h, const char *where, char *message) {
+    if (h->dDaQobs) return 0;
+    const size_t N = (size_t)h->d.nRch, KB = (size_t)h->opt.max_batch;
+    int e;
+    if ((e = dev_alloc(h, &h->dDaQobs, KB * N, where, message))) return e;
+    if ((e = dev_alloc(h, &h->dDaEl, KB * N, where, message))) return e;
+    if ((e = dev_alloc(h, &h->dQobsState, N, where, message))) return e;
+    if ((e = dev_alloc(h, &h->dElState, N, where, message))) return e;
+    if ((e = dev_alloc(h, &h->dHasRecord, KB, where, message))) return e;
+    for (int m : {M_IRF, M_KW, M_MC, M_DW})
+        if (h->on[m] && (e = dev_alloc(h, &h->dQerr[m], N, where, message))) return e;
+    return 0;
+}
+
 // device part of a batch: everything between "forcing is in HBM" and "REACH_Q series is in HBM"
 int route_device(mr_handle h, int K, double T0, const char *where, char *message) {
     DevNet &d = h->d;
@@ -215,6 +237,10 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     if (h->wmSteps && h->wmSteps != K) {
         h->wmSteps = 0;
         return fail(message, 1, std::string(where) + "/water management was uploaded for a different number of steps");
+    }
+    if (h->obsSteps && h->obsSteps != K) {
+        h->obsSteps = 0;
+        return fail(message, 1, std::string(where) + "/gauge observations were uploaded for a different number of steps");
     }
     d.wmFlux = d.wmVol = nullptr; d.volJumpStart = 0; d.lakeTargVol = h->dLakeTargVol;
     h->wmActive = false;
@@ -253,6 +279,19 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         }
     }
     h->lakeForcingActive = lakeForcing;
+    // data assimilation (main_route.f90:125-148): Qobs / Qelapsed of every (reach, step) of the batch; a batch without an
+    // upload is a stretch of the gauge file without records
+    d.daQobs = nullptr; d.daElapsed = nullptr; h->daActive = false;
+    if (h->qmodOption == 1) {
+        int e = ensure_da(h, where, message); if (e) return e;
+        if (!h->obsSteps) CU(cudaMemsetAsync(h->dHasRecord, 0, (size_t)K, h->stream));
+        h->obsSteps = 0;
+        k_da_rows<<<(N + 255) / 256, 256, 0, h->stream>>>(h->dDaQobs, h->dDaEl, h->dQobsState, h->dElState, h->dHasRecord, N, K);
+        h->launchesLast++;
+        d.daQobs = h->dDaQobs; d.daElapsed = h->dDaEl; d.qBlendPeriod = h->qBlendPeriod; d.qErrTrend = h->qErrTrend;
+        for (int m = 0; m < N_METHODS; ++m) d.qerr[m] = h->dQerr[m];
+        h->daActive = true;
+    }
     if (h->nGhost) {
         if (!d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
         k_import_unpack<<<(h->nGhost * K + 255) / 256, 256, 0, h->stream>>>(d, h->dImpPos, h->nGhost, K);
@@ -276,7 +315,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         if (st[r] != h->stream) CU(cudaStreamWaitEvent(st[r], h->ev[2], 0));
         CU(cudaEventRecord(h->mev[r][0], st[r]));
         if (hb) {
-            const bool hy = h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive;  // parametric reservoirs, lake forcing or water management: the instantiation that knows them
+            const bool hy = h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive;  // parametric reservoirs, lake forcing or water management: the instantiation that knows them
             switch (h->opt.route_methods[r]) {
                 case M_SUM: if (hy) k_headwater<M_SUM, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_SUM, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
                 case M_IRF: if (hy) k_headwater<M_IRF, true><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); else k_headwater<M_IRF, false><<<hb, 256, 0, st[r]>>>(d, K, h->stepsDone); break;
@@ -412,6 +451,8 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->nExport = 0; h->dExpPos = h->dImpPos = h->dExpSlot = h->dImpSlot = nullptr;
     h->dStepDoy = nullptr; h->hasHype = false; h->hasH06 = false;
     h->wmSteps = 0; h->wmActive = false; h->dWmFlux = h->dWmVol = nullptr; h->dLakeTargVol = nullptr;
+    h->obsSteps = 0; h->daActive = false; h->dDaQobs = h->dQobsState = nullptr; h->dDaEl = h->dElState = nullptr; h->dHasRecord = nullptr;
+    for (int m = 0; m < N_METHODS; ++m) h->dQerr[m] = nullptr;
     h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -671,6 +712,37 @@ int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *v
     return 0;
 }
 
+int mr_set_da(mr_handle h, int qmodOption, int qBlendPeriod, int QerrTrend, char *message) {
+    if (!h) return fail(message, 1, "mr_set_da/null handle");
+    if (qmodOption != 0 && qmodOption != 1) return fail(message, 1, "main_route/Error: qmodOption invalid");                  // main_route.f90:146-147
+    if (qmodOption == 1 && (QerrTrend < 1 || QerrTrend > 4))                                                              // data_assimilation.f90:87
+        return fail(message, 81, "direct_insertion/discharge error trend model must be 1(const),2(liear), or 3(logistic)");
+    h->qmodOption = qmodOption; h->qBlendPeriod = qBlendPeriod; h->qErrTrend = QerrTrend;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_upload_obs(mr_handle h, int nSteps, const int *hasRecord, const double *obs, char *message) {
+    const char *where = "mr_upload_obs";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (h->qmodOption != 1) return fail(message, 1, "mr_upload_obs/qmodOption is not 1 (mr_set_da)");
+    if (!obs) return fail(message, 1, "mr_upload_obs/null observations");
+    if ((e = ensure_da(h, where, message))) return e;
+    const size_t N = (size_t)h->d.nRch;
+    const Topology &T = h->topo;
+    h->wmStage.resize((size_t)nSteps * N);
+    for (int t = 0; t < nSteps; ++t)                      // caller's reach order -> stage order
+        for (size_t p = 0; p < N; ++p) h->wmStage[(size_t)t * N + p] = obs[(size_t)t * N + T.pos2rch[p]];
+    h->hasRecordHost.assign((size_t)nSteps, 1);
+    if (hasRecord) for (int t = 0; t < nSteps; ++t) h->hasRecordHost[t] = hasRecord[t] ? 1 : 0;
+    CU(cudaStreamSynchronize(h->stream));                 // the rows of the previous batch may still be read
+    CU(cudaMemcpy(h->dDaQobs, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->dHasRecord, h->hasRecordHost.data(), (size_t)nSteps, cudaMemcpyHostToDevice));
+    h->obsSteps = nSteps;
+    put_msg(message, "");
+    return 0;
+}
+
 int mr_upload_lake_forcing(mr_handle h, int nSteps, const double *basinEvapo, const double *basinPrecip, char *message) {
     const char *where = "mr_upload_lake_forcing";
     int e = check_ready(h, nSteps, where, message); if (e) return e;
@@ -852,7 +924,7 @@ int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) 
     const Topology &T = h->topo;
     const double *src = nullptr;
     std::vector<double> tmp(N);
-    const bool perMethod = (field == MR_REACH_Q || field == MR_REACH_VOL1 || field == MR_REACH_VOL0 || field == MR_REACH_INFLOW || field == MR_WB);
+    const bool perMethod = (field == MR_REACH_Q || field == MR_REACH_VOL1 || field == MR_REACH_VOL0 || field == MR_REACH_INFLOW || field == MR_WB || field == MR_QERROR);
     if (perMethod && (method < 0 || method >= N_METHODS || !h->on[method])) return fail(message, 1, "mr_get_flux/routing method is not active");
     switch (field) {
         case MR_REACH_Q: src = h->lastK > 0 ? h->d.qSer[method] + (size_t)(h->lastK - 1) * N : nullptr; break;
@@ -860,6 +932,7 @@ int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) 
         case MR_REACH_VOL0: src = h->d.vol0[method]; break;
         case MR_REACH_INFLOW: src = h->d.inflow[method]; break;
         case MR_WB: src = h->d.wb[method]; break;
+        case MR_QERROR: src = h->dQerr[method]; break;            // nullptr (zeros) before the first step with qmodOption 1
         case MR_BASIN_QI: src = h->d.basinQI; break;
         case MR_BASIN_QR1: src = h->d.qrSer + (size_t)h->lastK * N; break;
         case MR_BASIN_QR0: src = h->lastK > 0 ? h->d.qrSer + (size_t)(h->lastK - 1) * N : nullptr; break;
@@ -893,6 +966,9 @@ static long state_bytes(mr_handle h, int var) {
         case MR_ST_MOLECULE_KW: return 8L * N * n_molecule(M_KW);
         case MR_ST_MOLECULE_MC: return 8L * N * n_molecule(M_MC);
         case MR_ST_MOLECULE_DW: return 8L * N * n_molecule(M_DW);
+        case MR_ST_QERROR: return 8L * N * h->opt.n_routes;
+        case MR_ST_DA_QOBS: return 8L * N;
+        case MR_ST_DA_QELAPSED: return 4L * N;
         default: return -1;
     }
 }
@@ -970,6 +1046,23 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
                     if (var == MR_ST_KWT_ROUTED) iout[(size_t)r * KWS + k] = (k < cnt && first + k < nr[p]) ? 1 : 0;
                     else out[(size_t)r * KWS + k] = k < cnt ? tmp[(size_t)p * KWP + first + k] : -9999.0;
                 }
+            }
+            break; }
+        case MR_ST_QERROR: case MR_ST_DA_QOBS: case MR_ST_DA_QELAPSED: {
+            if (!h->dDaQobs) { std::memset(buf, 0, (size_t)nbytes); break; }          // as initialised, init_model_data.f90:404-405
+            if (var == MR_ST_DA_QELAPSED) {
+                std::vector<int> tmp(N);
+                CU(pull(h->dElState, tmp.data(), 4L * N));
+                for (int r = 0; r < N; ++r) iout[r] = tmp[T.rch2pos[r]];
+                break;
+            }
+            std::vector<double> tmp(N);
+            const int nq = var == MR_ST_QERROR ? h->opt.n_routes : 1;
+            for (int q = 0; q < nq; ++q) {
+                const double *src = var == MR_ST_QERROR ? h->dQerr[h->opt.route_methods[q]] : h->dQobsState;
+                if (!src) { for (int r = 0; r < N; ++r) out[(size_t)q * N + r] = 0.0; continue; }   // SUM, KWT: no direct_insertion
+                CU(pull(src, tmp.data(), 8L * N));
+                for (int r = 0; r < N; ++r) out[(size_t)q * N + r] = tmp[T.rch2pos[r]];
             }
             break; }
         default: return fail(message, 1, "mr_get_state/unknown state variable");
@@ -1056,6 +1149,24 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
                 for (int k = 0; k < KWS; ++k) tmp[(size_t)p * KWP + k] = in[(size_t)r * KWS + k]; }
             double *dst = var == MR_ST_KWT_QWAVE ? h->d.kwQF[b] : (var == MR_ST_KWT_TENTRY ? h->d.kwTI[b] : h->d.kwTR[b]);
             CU(push(dst, tmp.data(), tmp.size() * 8));
+            break; }
+        case MR_ST_QERROR: case MR_ST_DA_QOBS: case MR_ST_DA_QELAPSED: {
+            int e = ensure_da(h, where, message); if (e) return e;
+            CU(cudaStreamSynchronize(h->stream));
+            if (var == MR_ST_DA_QELAPSED) {
+                std::vector<int> tmp(N);
+                for (int r = 0; r < N; ++r) tmp[T.rch2pos[r]] = iin[r];
+                CU(push(h->dElState, tmp.data(), 4L * N));
+                break;
+            }
+            std::vector<double> tmp(N);
+            const int nq = var == MR_ST_QERROR ? h->opt.n_routes : 1;
+            for (int q = 0; q < nq; ++q) {
+                double *dst = var == MR_ST_QERROR ? h->dQerr[h->opt.route_methods[q]] : h->dQobsState;
+                if (!dst) continue;
+                for (int r = 0; r < N; ++r) tmp[T.rch2pos[r]] = in[(size_t)q * N + r];
+                CU(push(dst, tmp.data(), 8L * N));
+            }
             break; }
         default: return fail(message, 1, "mr_set_state/unknown state variable");
     }

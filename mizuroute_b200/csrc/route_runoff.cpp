@@ -57,7 +57,8 @@ const char *KNOWN_KEYS[] = {
     "scale_factor_prec", "offset_value_prec", "min_length_route", "ntopAugmentMode", "units_qsim", "units_cc", "dt_ro", "input_fillvalue",
     "ro_calendar", "ro_time_units", "ro_time_stamp", "runoffMin", "dt_wm", "is_remap", "restart_write", "restart_date", "restart_month",
     "restart_day", "restart_hour", "param_nml", "qmodOption", "qBlendPeriod", "QerrTrend", "hydGeometryOption", "topoNetworkOption",
-    "computeReachList", "gageMetaFile", "outputAtGage", "strlen_gageSite", "pio_netcdf_format", "pio_netcdf_type", "debug", "seg_outlet",
+    "computeReachList", "gageMetaFile", "outputAtGage", "strlen_gageSite", "fname_gageObs", "vname_gageFlow", "vname_gageSite", "vname_gageTime",
+    "dname_gageSite", "dname_gageTime", "pio_netcdf_format", "pio_netcdf_type", "debug", "seg_outlet",
     "desireId", "checkMassBalance", "maxPfafLen", "pfafMissing", "time_units", "newFileFrequency", "outputFrequency", "outputNameOption",
     "histTimeStamp_offset", "basRunoff", "instRunoff", "dlayRunoff", "sumUpstreamRunoff", "KWTroutedRunoff", "IRFroutedRunoff",
     "KWroutedRunoff", "DWroutedRunoff", "MCroutedRunoff", "IRFvolume", "KWTvolume", "KWvolume", "MCvolume", "DWvolume", "KWfloodVolume",
@@ -628,6 +629,64 @@ int main(int argc, char **argv) {
             for (size_t i = 0; i < wmRec.size(); ++i) if (wmIx[i] >= 0) { double v = wmRec[i] == fv ? -9999.0 : wmRec[i]; if (removeNegatives && v < 0.0) v = 0.0; dst[wmIx[i]] = v; }
         };
 
+        // data assimilation (<qmodOption> 1, init_model_data.f90:841-871): gauge metadata csv <gageMetaFile> (header row; columns
+        // gage_id, reach_id: gageMeta_data.f90:58-68) and the gauge netCDF <fname_gageObs> ([time, site] flow, site names as a
+        // character variable: obs_data.f90:272-516), both in <ancil_dir>; a step sees the record whose time equals the start of
+        // the step (gage_obs_data%time_ix(simDatetime(1)), main_route.f90:128); without the file the option is switched off
+        int qmodOption = (int)c.num("qmodOption", 0);
+        std::unique_ptr<nc3::Reader> obsFile;
+        std::vector<int> obsIx; std::vector<double> obsTime, obsRec; double obsFill = -9999.0; const nc3::Var *obsVar = nullptr;
+        if (qmodOption != 0 && qmodOption != 1) die(1, "init_qmod/Error: qmodOption invalid");
+        if (qmodOption == 1) {
+            const std::string obsPath = join_path(ancil, c.str("fname_gageObs", ""));
+            FILE *probe = c.str("fname_gageObs", "").empty() ? nullptr : std::fopen(obsPath.c_str(), "rb");
+            if (!probe) qmodOption = 0;
+            else {
+                std::fclose(probe);
+                std::map<std::string, int> reachOfGage;                      // gage_id -> reach_id
+                {
+                    std::ifstream csv(join_path(ancil, c.need("gageMetaFile")));
+                    if (!csv) die(20, "read_gage_meta/cannot open " + join_path(ancil, c.need("gageMetaFile")));
+                    std::string line; int cg = -1, cr = -1;
+                    auto cells = [](const std::string &ln) { std::vector<std::string> v; std::stringstream ss(ln); std::string x; while (std::getline(ss, x, ',')) v.push_back(trim(x)); return v; };
+                    if (std::getline(csv, line)) { const auto hd = cells(line); for (size_t i = 0; i < hd.size(); ++i) { if (hd[i] == "gage_id") cg = (int)i; if (hd[i] == "reach_id") cr = (int)i; } }
+                    if (cg < 0 || cr < 0) die(20, "read_gage_meta/the csv needs the columns gage_id and reach_id");
+                    while (std::getline(csv, line)) { const auto v = cells(line); if ((int)v.size() > std::max(cg, cr) && !v[cg].empty()) reachOfGage[v[cg]] = std::atoi(v[cr].c_str()); }
+                }
+                obsFile.reset(new nc3::Reader(obsPath));
+                const nc3::Var &tv = obsFile->var(c.need("vname_gageTime"));
+                double scale, epoch; parse_time_units(obsFile->attr_text(tv, "units"), noleap, scale, epoch);
+                obsFile->read_all(tv, obsTime);
+                for (auto &t : obsTime) t = epoch + t * scale;
+                std::vector<double> chars; const nc3::Var &sv = obsFile->var(c.need("vname_gageSite"));
+                obsFile->read_all(sv, chars);
+                const int dSite = obsFile->dim_index(c.need("dname_gageSite"));
+                if (dSite < 0) die(20, "gageObs/dimension " + c.need("dname_gageSite") + " not found");
+                const size_t nSite = obsFile->dims[dSite].len, len = nSite ? chars.size() / nSite : 0;
+                std::vector<std::pair<int, int>> tab(nRch); for (size_t i = 0; i < nRch; ++i) tab[i] = {segId[i], (int)i}; std::sort(tab.begin(), tab.end());
+                obsIx.assign(nSite, -1);                                   // comp_link: site -> gage_id -> reach_id -> reach index
+                for (size_t i = 0; i < nSite; ++i) {
+                    std::string nm; for (size_t k = 0; k < len; ++k) { const char ch = (char)chars[i * len + k]; if (ch == '\0') break; nm.push_back(ch); }
+                    auto g = reachOfGage.find(trim(nm)); if (g == reachOfGage.end()) continue;
+                    auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(g->second, -1));
+                    if (it != tab.end() && it->first == g->second) obsIx[i] = it->second;
+                }
+                obsVar = &obsFile->var(c.need("vname_gageFlow"));
+                obsFile->attr_value(*obsVar, "_FillValue", obsFill);
+            }
+        }
+        // gauge row of the step that starts at absolute time t: false = no record at that time
+        auto load_obs = [&](double t, double *dst) {
+            for (size_t i = 0; i < nRch; ++i) dst[i] = std::nan("");
+            size_t j = 0; while (j < obsTime.size() && std::fabs(obsTime[j] - t) > 0.5) ++j;     // first match, obs_data.f90:755-760
+            if (j == obsTime.size()) return false;
+            if (obsVar->record) obsFile->read(*obsVar, obsRec, j, 1);
+            else { std::vector<double> all; obsFile->read(*obsVar, all); obsRec.assign(all.begin() + j * obsIx.size(), all.begin() + (j + 1) * obsIx.size()); }
+            if (obsRec.size() != obsIx.size()) die(20, "gageObs/read_obs: the flow variable is not dimensioned [time, site]");
+            for (size_t i = 0; i < obsRec.size(); ++i) if (obsIx[i] >= 0) dst[obsIx[i]] = obsRec[i] == obsFill ? std::nan("") : obsRec[i];
+            return true;
+        };
+
         if (dry) {                                                       // the time map of the first steps, for inspection
             std::printf("{\"dt_ro\": %.3f, \"ro_time_stamp\": \"%s\", \"time_map\": [", dtro, stampAt.c_str());
             for (size_t k = 0; k < std::min<size_t>(nSteps, 6); ++k) {
@@ -671,6 +730,7 @@ int main(int argc, char **argv) {
                 }
             }
         }
+        if (qmodOption == 1) { ierr = mr_set_da(h, 1, (int)c.num("qBlendPeriod", 10), (int)c.num("QerrTrend", 1), msg); if (ierr) die(ierr, msg); }
         ierr = mr_set_network(h, (int)nRch, (int)nHRU, segId.data(), downSegId.data(), hruSegId.data(), area.data(), length.data(), slope.data(),
                               geomFromFile ? width.data() : nullptr, geomFromFile ? man_n.data() : nullptr, islake.empty() ? nullptr : islake.data(),
                               lakeType.empty() ? nullptr : lakeType.data(), d03[0].empty() ? nullptr : d03[0].data(), d03[1].empty() ? nullptr : d03[1].data(),
@@ -705,6 +765,7 @@ int main(int argc, char **argv) {
         std::vector<double> ro((size_t)batch * inCols), q((size_t)o.n_routes * batch * nRch);
         std::vector<double> evRows(lakeForcing ? (size_t)batch * nHRU : 0), prRows(evRows.size());
         std::vector<double> wmFluxRows(fluxWm ? (size_t)batch * nRch : 0), wmVolRows(volWm ? (size_t)batch * nRch : 0);
+        std::vector<double> obsRows(qmodOption == 1 ? (size_t)batch * nRch : 0); std::vector<int> obsHas(batch, 0);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
@@ -731,6 +792,10 @@ int main(int argc, char **argv) {
                 }
                 ierr = mr_upload_wm(h, nb, fluxWm ? wmFluxRows.data() : nullptr, volWm ? wmVolRows.data() : nullptr, c.flag("is_vol_wm_jumpstart", false) ? 1 : 0, msg);
                 if (ierr) die(ierr, msg);
+            }
+            if (qmodOption == 1) {
+                for (int k = 0; k < nb; ++k) obsHas[k] = load_obs(tStart + (double)(s + k) * o.dt, &obsRows[(size_t)k * nRch]) ? 1 : 0;
+                ierr = mr_upload_obs(h, nb, obsHas.data(), obsRows.data(), msg); if (ierr) die(ierr, msg);
             }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }

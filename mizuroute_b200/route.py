@@ -144,6 +144,19 @@ class Router:
         assert all(a is None or a.shape == (k, self.nRch) for a in (f, v))
         self._check(self._L.mr_upload_wm(self._h, int(k), _ptr(f, C.c_double), _ptr(v, C.c_double), int(bool(vol_jumpstart)), self._msg))
 
+    def set_da(self, qmod_option: int = 1, q_blend_period: int = 10, q_err_trend: int = 1):
+        """Data assimilation by direct insertion (<qmodOption>, <qBlendPeriod>, <QerrTrend>; mr_set_da)."""
+        self._check(self._L.mr_set_da(self._h, int(qmod_option), int(q_blend_period), int(q_err_trend), self._msg))
+
+    def upload_obs(self, obs, has_record=None):
+        """Gauge observations [K, nRch] (m3/s; NaN or negative = none at that reach) of the NEXT routing call, which must
+        route K steps (mr_upload_obs); has_record [K], 0 = the gauge file has no record at that step."""
+        o = np.ascontiguousarray(np.atleast_2d(obs), dtype=np.float64)
+        assert o.shape[1] == self.nRch
+        r = None if has_record is None else np.ascontiguousarray(has_record, dtype=np.int32)
+        assert r is None or r.shape == (o.shape[0],)
+        self._check(self._L.mr_upload_obs(self._h, int(o.shape[0]), _ptr(r, C.c_int), _ptr(o, C.c_double), self._msg))
+
     def upload_lake_forcing(self, evapo, precip):
         """Lake evaporation / precipitation [K, nHRU] (runoff units, river-network HRU order) of the NEXT routing call, which
         must route K steps (mr_upload_lake_forcing; basinEvapo_in / basinPrecip_in of main_route)."""
@@ -277,6 +290,9 @@ class Router:
             capi.ST_MOLECULE_KW: ((n, capi.N_MOLECULE[3]), np.float64),
             capi.ST_MOLECULE_MC: ((n, capi.N_MOLECULE[4]), np.float64),
             capi.ST_MOLECULE_DW: ((n, capi.N_MOLECULE[5]), np.float64),
+            capi.ST_QERROR: ((len(self.methods), n), np.float64),
+            capi.ST_DA_QOBS: ((n,), np.float64),
+            capi.ST_DA_QELAPSED: ((n,), np.int32),
         }[var]
 
     def get_state(self, var: int) -> np.ndarray:

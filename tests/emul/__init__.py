@@ -28,7 +28,7 @@ def load():
 
 _EULER_SO = os.path.join(_HERE, "libeuler_emul.so")
 _EULER_SRC = os.path.join(_HERE, "euler_emul.cpp")
-_EULER_DEPS = [_EULER_SRC] + [os.path.join(_CSRC, f) for f in ("mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
+_EULER_DEPS = [_EULER_SRC, os.path.join(_HERE, "da_emul.h")] + [os.path.join(_CSRC, f) for f in ("mr_euler.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
 
 
 def load_euler(noise_seed: int = 0):
@@ -57,7 +57,7 @@ def load_lake():
 
 _IRF_SO = os.path.join(_HERE, "libirf_emul.so")
 _IRF_SRC = os.path.join(_HERE, "irf_emul.cpp")
-_IRF_DEPS = [_IRF_SRC] + [os.path.join(_CSRC, f) for f in ("mr_irf.cuh", "mr_lake.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_uh.h")]
+_IRF_DEPS = [_IRF_SRC, os.path.join(_HERE, "da_emul.h")] + [os.path.join(_CSRC, f) for f in ("mr_irf.cuh", "mr_lake.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_uh.h")]
 
 
 def load_irf():

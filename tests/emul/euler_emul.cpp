@@ -12,12 +12,19 @@
 
 #include "../../mizuroute_b200/csrc/mr_euler.cuh"
 #include "../../mizuroute_b200/csrc/mr_topo.h"
+#include "da_emul.h"
 
 using namespace mr;
 
+static DaEmul g_da;
+// gauge observations of the NEXT euler_emul_run: obs [nSteps][nRch] caller order, hasRecord [nSteps] or NULL; qerr_out [nRch]
+extern "C" void euler_emul_set_da(int blend, int trend, const int *hasRecord, const double *obs, double *qerr_out) {
+    g_da.blend = blend; g_da.trend = trend; g_da.hasRecord = hasRecord; g_da.obs = obs; g_da.qerrOut = qerr_out;
+}
+
 template <int M>
 static void run_method(DevNet &d, const Topology &T, int nSteps) {
-    const bool ext = d.wmFlux != nullptr;                   // water management: the EXT instantiations, as route_device picks them
+    const bool ext = d.wmFlux != nullptr || d.daQobs != nullptr;   // water management / data assimilation: the EXT instantiations, as route_device picks them
     for (int t = 0; t < nSteps; ++t)
         for (int p = 0; p < d.nRch; ++p) {                  // stage order: upstream before downstream
             if (ext) { if constexpr (M == M_MC) mc_reach<true>(d, p, t); else kw_dw_reach<M, true>(d, p, t); }
@@ -60,6 +67,7 @@ extern "C" int euler_emul_run(int method, int nRch, int nHRU, const int *segId, 
         for (int t = 0; t < nSteps; ++t) for (int p = 0; p < N; ++p) fS[(size_t)t * N + p] = wm_flux[(size_t)t * N + T.pos2rch[p]];
         d.wmFlux = fS.data();
     }
+    g_da.attach(d, T, method, nSteps);
     if (method == M_KW) run_method<M_KW>(d, T, nSteps); else if (method == M_MC) run_method<M_MC>(d, T, nSteps); else run_method<M_DW>(d, T, nSteps);
     for (int t = 0; t < nSteps; ++t) for (int r = 0; r < N; ++r) q_out[(size_t)t * N + r] = qSer[(size_t)t * N + T.rch2pos[r]];
     for (int r = 0; r < N; ++r) {
@@ -67,6 +75,7 @@ extern "C" int euler_emul_run(int method, int nRch, int nHRU, const int *segId, 
         vol_out[r] = vol1[p];
         for (int k = 0; k < nm; ++k) mol_out[(size_t)r * nm + k] = mol[(size_t)k * N + p];
     }
+    g_da.finish(T);
     std::snprintf(msg, 256, "ok");
     return 0;
 }

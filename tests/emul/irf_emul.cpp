@@ -13,8 +13,15 @@
 #include "../../mizuroute_b200/csrc/mr_lake.cuh"
 #include "../../mizuroute_b200/csrc/mr_topo.h"
 #include "../../mizuroute_b200/csrc/mr_uh.h"
+#include "da_emul.h"
 
 using namespace mr;
+
+static DaEmul g_da;
+// gauge observations of the NEXT irf_emul_run: obs [nSteps][nRch] caller order, hasRecord [nSteps] or NULL; qerr_out [nRch]
+extern "C" void irf_emul_set_da(int blend, int trend, const int *hasRecord, const double *obs, double *qerr_out) {
+    g_da.blend = blend; g_da.trend = trend; g_da.hasRecord = hasRecord; g_da.obs = obs; g_da.qerrOut = qerr_out;
+}
 
 extern "C" int irf_emul_run(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId, const double *hruArea,
                             const double *length, const double *slope, const int *islake /* or NULL */, const int *lakeType, const double *maxS,
@@ -57,7 +64,7 @@ extern "C" int irf_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     d.qrSer = qrSer.data(); d.qSer[M_SUM] = qS.data(); d.qSer[M_IRF] = qI.data(); d.inflow[M_IRF] = inflow.data();
     d.vol0[M_IRF] = vol0.data(); d.vol1[M_IRF] = vol1.data(); d.wb[M_IRF] = wb.data(); d.err = err;
     // water management: rows permuted to stage order as mr_upload_wm does; the EXT instantiations are used then
-    const bool ext = wm_flux || wm_vol;
+    const bool ext = g_da.attach(d, T, M_IRF, nSteps) || wm_flux || wm_vol;
     std::vector<double> fS, vS; std::vector<unsigned char> tg(N, 0);
     auto stage = [&](const double *src, std::vector<double> &dst) {
         dst.resize((size_t)nSteps * N);
@@ -81,6 +88,7 @@ extern "C" int irf_emul_run(int nRch, int nHRU, const int *segId, const int *dow
         vol_out[r] = vol1[p]; wb_out[r] = wb[p];
         for (int k = 0; k < 240; ++k) qfut_out[(size_t)r * 240 + k] = k < ntdh[p] ? qfut[(size_t)(((long long)nSteps + k) % ntdh[p]) * N + p] : 0.0;   // as mr_get_state
     }
+    g_da.finish(T);
     std::snprintf(msg, 256, "ok");
     return 0;
 }

@@ -10,7 +10,7 @@ import pytest
 from oracle import oracle as orc
 from oracle.oracle import Oracle
 from tests import emul
-from tests.util import case
+from tests.util import case, gauge_series
 
 CASES = [
     dict(kind="random", n=80, seed=5, dt=3600.0, steps=40, zero_area_frac=0.08),
@@ -143,3 +143,39 @@ def test_water_management_cascade_in_the_euler_schemes(method):
     assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, method))
     assert np.array_equal(me, o.molecule(method))
     assert not np.array_equal(qo, Oracle(net, params, opts).run(ro)[0])
+
+
+@pytest.mark.parametrize("trend", [1, 2, 3, 4])
+@pytest.mark.parametrize("method", [orc.M_KW, orc.M_MC, orc.M_DW], ids=["kw", "mc", "dw"])
+def test_direct_insertion_in_the_euler_schemes(method, trend):
+    """kw_dw_reach<M, EXT> / mc_reach<EXT> ending in direct_insertion (kwe_route.f90:183-197 and siblings) on the rows da_rows
+    builds from the gauge records -- against Oracle.set_da / set_obs, bit for bit: REACH_Q, REACH_VOL(1), molecules, Qerror."""
+    net, params, opts, ro = case("conus", n=500, seed=3, dt=3600.0, route_opt=str(method), steps=24)
+    K = ro.shape[0]
+    base = Oracle(net, params, opts).run(ro)[0]
+    obs, has, gauges = gauge_series(net, K, seed=10 + trend, base=base)
+    blend = 5
+    o = Oracle(net, params, opts); o.set_da(1, blend, trend)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.set_obs(obs[t] if has[t] else None)
+        o.step(ro[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, method)
+    L = emul.load_euler()
+    nm = orc.N_MOLECULE[method]
+    qe = np.empty((K, net.nRch)); ve = np.empty(net.nRch); me = np.empty((net.nRch, nm)); qerr = np.empty(net.nRch)
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.POINTER(ct))
+    L.euler_emul_set_da(C.c_int(blend), C.c_int(trend), p(has, C.c_int), p(obs, C.c_double), p(qerr, C.c_double))
+    ierr = L.euler_emul_run(C.c_int(method), C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int),
+                            p(net.hruSegId, C.c_int), p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double),
+                            C.c_double(params.mann_n), C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(opts.hw_drain_point),
+                            C.c_double(opts.min_length_route), C.c_int(0), C.c_int(K), p(qr, C.c_double), None,
+                            p(qe, C.c_double), p(ve, C.c_double), p(me, C.c_double), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qe, qo)
+    assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, method))
+    assert np.array_equal(me, o.molecule(method))
+    assert np.array_equal(qerr, o.get(orc.F_QERROR, method))
+    assert not np.array_equal(qo, base)

@@ -10,7 +10,7 @@ import pytest
 from oracle import oracle as orc
 from oracle.oracle import Oracle
 from tests import emul
-from tests.util import case
+from tests.util import case, gauge_series
 
 CASES = [
     dict(kind="random", n=120, seed=5, dt=3600.0, steps=40, zero_area_frac=0.1),
@@ -105,3 +105,43 @@ def test_water_management_device_source_matches_oracle(lakes):
     assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, orc.M_IRF))
     assert np.array_equal(we, o.get(orc.F_WB, orc.M_IRF))
     assert (qo[:, (net.islake != 1) if lake else slice(None)] == 0.0).any()          # somewhere more was asked for than there was
+
+
+@pytest.mark.parametrize("trend", [1, 2, 3, 4])
+def test_direct_insertion_device_source_matches_oracle(trend):
+    """mr_set_da / mr_upload_obs path: da_rows (the body of k_da_rows) turns the gauge records of a batch into the Qobs /
+    Qelapsed every (reach, step) sees, irf_reach<EXT> ends in direct_insertion (mr_dev.h) instead of the water balance --
+    against Oracle.set_da / set_obs, bit for bit: REACH_Q, REACH_VOL(1), Qerror, the future-flow series."""
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=86400.0, route_opt="01", steps=24)
+    K = ro.shape[0]
+    base = Oracle(net, params, opts).run(ro)[1]
+    obs, has, gauges = gauge_series(net, K, seed=trend, base=base)
+    blend = 4
+    o = Oracle(net, params, opts); o.set_da(1, blend, trend)
+    qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
+    qr[0] = o.get(orc.F_BASIN_QR1)
+    for t in range(K):
+        o.set_obs(obs[t] if has[t] else None)
+        o.step(ro[t])
+        qr[t + 1] = o.get(orc.F_BASIN_QR1); qo[t] = o.get(orc.F_REACH_Q, orc.M_IRF)
+    L = emul.load_irf()
+    qs = np.empty((K, net.nRch)); qi = np.empty((K, net.nRch)); ve = np.empty(net.nRch); we = np.empty(net.nRch); qerr = np.empty(net.nRch)
+    qf = np.empty((net.nRch, 240)); mx = C.c_int(0)
+    msg = C.create_string_buffer(256)
+    p = lambda a, ct: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.POINTER(ct))
+    zeros = np.zeros(net.nRch)
+    L.irf_emul_set_da(C.c_int(blend), C.c_int(trend), p(has, C.c_int), p(obs, C.c_double), p(qerr, C.c_double))
+    ierr = L.irf_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
+                          p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), None, None,
+                          p(zeros, C.c_double), p(zeros, C.c_double), p(zeros, C.c_double), p(zeros, C.c_double),
+                          C.c_double(params.wscale), C.c_double(opts.dt), C.c_double(params.velo), C.c_double(params.diff),
+                          C.c_int(opts.hw_drain_point), C.c_double(opts.min_length_route), C.c_int(opts.LakeInputOption), C.c_int(K),
+                          p(qr, C.c_double), None, None, None, C.c_int(0),
+                          p(qs, C.c_double), p(qi, C.c_double), p(ve, C.c_double), p(we, C.c_double), p(qf, C.c_double), C.byref(mx), msg)
+    assert ierr == 0, msg.value.decode()
+    assert np.array_equal(qi, qo)
+    assert np.array_equal(ve, o.get(orc.F_REACH_VOL1, orc.M_IRF))
+    assert np.array_equal(qerr, o.get(orc.F_QERROR, orc.M_IRF))
+    assert (we == 0.0).all()                                   # the water balance is not evaluated under qmodOption 1
+    assert not np.array_equal(qo, base)                        # and the observations did change the flow
+    assert np.array_equal(qs, Oracle(net, params, opts).run(ro)[0])      # runoff accumulation is not corrected

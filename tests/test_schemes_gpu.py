@@ -233,3 +233,53 @@ def test_water_management_in_kwt():
         if done == 3:
             break
     assert done == 3
+
+
+@pytest.mark.parametrize("trend", [1, 3])
+def test_direct_insertion(trend):
+    """mr_set_da / mr_upload_obs: k_da_rows + direct_insertion in the EXT instantiations of IRF and the Euler schemes over
+    several batches (one of them without an upload = a stretch without gauge records), SUM and KWT untouched; Qerror and the
+    running Qobs / Qelapsed survive a state round trip into a second handle."""
+    from mizuroute_b200 import capi
+    from mizuroute_b200.route import Router
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    from tests.util import gauge_series
+    route = "012345"
+    net, params, opts, ro = case("conus", n=900, seed=4, dt=3600.0, route_opt=route, steps=20)
+    K = ro.shape[0]
+    base = Oracle(net, params, opts).run(ro)[1]
+    obs, has, gauges = gauge_series(net, K, seed=trend, base=base)
+    has[10:15] = 0                                           # the batch that gets no upload at all
+    blend = 4
+    o = Oracle(net, params, opts); o.set_da(1, blend, trend)
+    qo = np.empty((len(route), K, net.nRch))
+    for t in range(K):
+        o.set_obs(obs[t] if has[t] else None)
+        o.step(ro[t])
+        for i, c in enumerate(route):
+            qo[i, t] = o.get(orc.F_REACH_Q, int(c))
+    r = Router(net, params, opts, max_batch=8)
+    r.set_da(1, blend, trend)
+    parts = []
+    for s in range(0, K, 5):
+        if s == 15:                                          # continue in a fresh handle from the saved state
+            r2 = Router(net, params, opts, max_batch=8); r2.set_da(1, blend, trend)
+            for var in range(16):
+                try:
+                    r2.set_state(var, r.get_state(var))
+                except RuntimeError:
+                    pass
+            r2.set_steps_done(s); r = r2
+        if s != 10:
+            r.upload_obs(obs[s:s + 5], has[s:s + 5])
+        parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + 5])))
+    qg = np.concatenate(parts, axis=1)
+    assert np.array_equal(qg[0], qo[0])                      # SUM: bit-identical and uncorrected
+    for i, c in enumerate(route):
+        tol = 1e-4 if c == "2" else (1e-6 if c == "1" else EULER_RTOL)
+        assert rel_err(qg[i], qo[i], floor=1e-9) <= tol, c
+        if c in "1345":
+            assert rel_err(r.flux(capi.QERROR, int(c)), o.get(orc.F_QERROR, int(c)), floor=1e-6) <= 1e-5, c
+    assert np.array_equal(r.get_state(capi.ST_DA_QELAPSED), o.qelapsed())
+    assert np.array_equal(r.get_state(capi.ST_DA_QOBS), o.get(orc.F_QOBS))

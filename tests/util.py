@@ -51,3 +51,20 @@ def star_network(arms=12, depth=3, seed=3, steps=40, dt=3600.0, route_opt="2"):
     opts = RouteOptions(dt=dt, route_opt=route_opt, runoffMin=1e-15)
     ro = np.abs(rng.lognormal(np.log(2e-5), 1.0, size=(steps, n))) + 1e-9
     return net, RouteParams(), opts, ro
+
+
+def gauge_series(net, K, seed=3, n_gauge=40, record_frac=0.5, scale=(0.3, 2.5), base=None):
+    """Synthetic gauge file for the data-assimilation tests: obs [K][nRch] (NaN = no gauge / missing, a few negative),
+    has_record [K] int32 (0 = no record at that step).  base [K][nRch]: flows the values are scattered around."""
+    rng = np.random.default_rng(seed)
+    gauges = rng.choice(net.nRch, min(n_gauge, net.nRch), replace=False)
+    has = (rng.random(K) < record_frac).astype(np.int32)
+    has[0] = 0; has[min(2, K - 1)] = 1
+    obs = np.full((K, net.nRch), np.nan)
+    for t in range(K):
+        b = base[t, gauges] if base is not None else rng.lognormal(0.0, 1.0, gauges.size)
+        v = b * rng.uniform(scale[0], scale[1], gauges.size)
+        v[rng.random(gauges.size) < 0.15] = np.nan          # gauge silent at that record
+        v[rng.random(gauges.size) < 0.05] = -1.0            # flagged bad
+        obs[t, gauges] = v
+    return obs, has, gauges
