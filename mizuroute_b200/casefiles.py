@@ -113,10 +113,38 @@ def _stamp(seconds: float, start: str) -> str:
     return (t0 + _dt.timedelta(seconds=seconds)).strftime("%Y-%m-%d %H:%M:%S")
 
 
+def write_gauges(csv_path: str, nc_path: str, site_ids, gage_ids, reach_ids, times_sec, flow, start: str = "2000-01-01 00:00:00", strlen: int = 30,
+                 fill: float = -9999.0):
+    """Gauge metadata csv (<gageMetaFile>: header row, columns gage_id, reach_id, as gageMeta_data.f90:58-68 reads them) and the
+    gauge netCDF (<fname_gageObs>: flow [time, site], site names as a character variable [site, strlen], time in seconds since
+    `start` -- records only at `times_sec`; NaN in `flow` is written as the fill value).  `site_ids` are the gauges of the netCDF,
+    `gage_ids` / `reach_ids` the rows of the csv (they need not hold the same gauges)."""
+    with open(csv_path, "w") as f:
+        f.write("gage_id,reach_id,lat,lon\n")
+        for g, r in zip(gage_ids, reach_ids):
+            f.write("%s,%d,0.0,0.0\n" % (g, int(r)))
+    f = netcdf_file(nc_path, "w", version=2)
+    f.createDimension("time", None)
+    f.createDimension("site", len(site_ids))
+    f.createDimension("strlen", strlen)
+    t = f.createVariable("time", "d", ("time",))
+    t.units = "seconds since " + start
+    t.calendar = "standard"
+    sv = f.createVariable("site", "c", ("site", "strlen"))
+    for i, g in enumerate(site_ids):
+        sv[i, :] = np.frombuffer(str(g).ljust(strlen)[:strlen].encode(), dtype="S1")
+    q = f.createVariable("flow", "d", ("time", "site"))
+    q._FillValue = fill
+    for k, ts in enumerate(times_sec):
+        t[k] = float(ts)
+        q[k, :] = np.where(np.isnan(flow[k]), fill, flow[k])
+    f.close()
+
+
 def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: RouteOptions, runoff: np.ndarray, case_name: str = "case",
                start: str = "2000-01-01 00:00:00", split_forcing: int = 1, shuffle_hru_seed=None, restart_write: str = "never",
                fname_state_in: str = "coldstart", first_step: int = 0, remap=None, output_frequency="1", forcing_dt=None, sim_steps=None,
-               ro_time_stamp=None, new_file_frequency="single", extra_keys=None, lake_forcing=None, wm=None) -> str:
+               ro_time_stamp=None, new_file_frequency="single", extra_keys=None, lake_forcing=None, wm=None, gauges=None) -> str:
     """Creates <case_dir>/{ancillary,input,output} and returns the control-file path.  `first_step` > 0 writes a
     continuation run: the forcing records and <sim_start> begin `first_step` steps after `start`.  `forcing_dt` != dt_qsim
     writes the runoff records on their own interval (`sim_steps` simulation steps of opts.dt are then asked for);
@@ -232,6 +260,14 @@ def write_case(case_dir: str, net: RiverNetwork, params: RouteParams, opts: Rout
                  ("is_vol_wm", "T" if wm_vol is not None else "F", "target lake volumes"), ("is_vol_wm_jumpstart", "T", "start the target-volume lakes at their target"),
                  ("fname_wm", "wm_%s.nc" % case_name, "water-management netCDF"), ("vname_flux_wm", "flux_wm", ""), ("vname_vol_wm", "vol_wm", ""),
                  ("vname_time_wm", "time", ""), ("vname_segid_wm", "seg_id", ""), ("dname_time_wm", "time", ""), ("dname_segid_wm", "seg", "")]
+    if gauges is not None:                                  # (site_ids, csv gage_ids, csv reach_ids, times_sec, flow[time, site], qBlendPeriod, QerrTrend)
+        g_sites, g_ids, g_rch, g_t, g_flow, blend, trend = gauges
+        write_gauges(anc + "gauges_%s.csv" % case_name, anc + "gauge_obs_%s.nc" % case_name, g_sites, g_ids, g_rch, g_t, g_flow, t_first)
+        keys += [("qmodOption", 1, "direct insertion"), ("qBlendPeriod", int(blend), "steps over which the correction fades"),
+                 ("QerrTrend", int(trend), "1 constant, 2 linear, 3 logistic, 4 exponential"),
+                 ("gageMetaFile", "gauges_%s.csv" % case_name, "gauge metadata csv"), ("fname_gageObs", "gauge_obs_%s.nc" % case_name, "gauge netCDF"),
+                 ("vname_gageFlow", "flow", ""), ("vname_gageSite", "site", ""), ("vname_gageTime", "time", ""), ("dname_gageSite", "site", ""),
+                 ("dname_gageTime", "time", ""), ("strlen_gageSite", 30, "")]
     for k, v in (extra_keys or {}).items():
         keys.append((k, v, "extra key"))
     ctl = os.path.join(case_dir, case_name + ".control")

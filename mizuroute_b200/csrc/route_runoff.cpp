@@ -20,6 +20,7 @@
 // <is_remap> T: polygon [time, hru] or gridded [time, lat, lon] forcing, remapped on the device; any ratio of <dt_qsim> to
 // the forcing interval; <newFileFrequency> single | daily | monthly | yearly.  <is_flux_wm> / <is_vol_wm> T: one water-management
 // netCDF <fname_wm> with [time, seg] variables.
+// <qmodOption> 1: gauge metadata csv <gageMetaFile> + gauge netCDF <fname_gageObs> (in <ancil_dir>) -> mr_set_da / mr_upload_obs.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -730,12 +731,12 @@ int main(int argc, char **argv) {
                 }
             }
         }
-        if (qmodOption == 1) { ierr = mr_set_da(h, 1, (int)c.num("qBlendPeriod", 10), (int)c.num("QerrTrend", 1), msg); if (ierr) die(ierr, msg); }
         ierr = mr_set_network(h, (int)nRch, (int)nHRU, segId.data(), downSegId.data(), hruSegId.data(), area.data(), length.data(), slope.data(),
                               geomFromFile ? width.data() : nullptr, geomFromFile ? man_n.data() : nullptr, islake.empty() ? nullptr : islake.data(),
                               lakeType.empty() ? nullptr : lakeType.data(), d03[0].empty() ? nullptr : d03[0].data(), d03[1].empty() ? nullptr : d03[1].data(),
                               d03[2].empty() ? nullptr : d03[2].data(), d03[3].empty() ? nullptr : d03[3].data(), msg);
         if (ierr) die(ierr, msg);
+        if (qmodOption == 1) { ierr = mr_set_da(h, 1, (int)c.num("qBlendPeriod", 10), (int)c.num("QerrTrend", 1), msg); if (ierr) die(ierr, msg); }
 
         if (isRemap) { ierr = mr_set_remap(h, (int)nForcing, (int)mapHruIx.size(), mapHruIx.data(), mapNumQ.data(), mapQIx.data(), mapWgt.data(), msg); if (ierr) die(ierr, msg); }
 

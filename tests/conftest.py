@@ -30,7 +30,7 @@ NOT_YET_RUN_ON_HARDWARE = (
     "test_hype_reservoirs_and_their_calendar_survive_a_restart", "test_exact_restart_of_the_euler_schemes",
     "test_host_run_matches_oracle[345", "test_host_routes_gridded_forcing_like_the_oracle",
     "test_decomposed_euler_schemes_equal_single_domain", "test_hanasaki", "test_schemes_gpu.py::test_hanasaki", "test_schemes_gpu.py::test_water_management", "test_host_reads_the_water_management_file",
-    "test_schemes_gpu.py::test_direct_insertion",
+    "test_schemes_gpu.py::test_direct_insertion", "test_host_reads_the_gauge_files_for_direct_insertion",
 )
 
 

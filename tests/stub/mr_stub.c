@@ -21,6 +21,8 @@ struct mr_handle_s {
     int hasStart, sy, sm, sd, noleap; double ssec;
     /* water management of the next batch (mr_upload_wm) */
     double *wmF, *wmV; int wmSteps, wmJump;
+    /* gauge observations of the next batch (mr_upload_obs) */
+    double *obs; int *obsHas; int obsSteps, qmod;
     /* lake forcing of the next batch (mr_upload_lake_forcing) */
     double *ev, *pr; int epSteps;
     /* BASIN_QR(1) of the steps of the last batch */
@@ -86,6 +88,7 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
         if (h->nMap) { mro_remap_1d(h->nMap, h->mapHru, h->numQ, h->qIx, h->wgt, in, row); in = row; }
         if (h->wmSteps) mro_set_wm(h->m, h->wmF ? h->wmF + (size_t)t * h->nRch : NULL, h->wmV ? h->wmV + (size_t)t * h->nRch : NULL, h->wmJump);
         else mro_set_wm(h->m, NULL, NULL, 0);
+        if (h->qmod == 1) mro_set_obs(h->m, (h->obsSteps && h->obsHas[t]) ? h->obs + (size_t)t * h->nRch : NULL);
         ierr = h->epSteps ? mro_step_ep(h->m, t0, t1, in, h->ev + (size_t)t * h->nHRU, h->pr + (size_t)t * h->nHRU) : mro_step(h->m, t0, t1, in);
         if (ierr) { char b[MR_STRLEN]; snprintf(b, sizeof b, "mr_step_batch/main_route/%s", mro_message(h->m)); say(message, b); free(row); return ierr; }
         for (r = 0; r < h->m->nRoutes; r++)
@@ -94,7 +97,7 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
         t0 = t1; t1 = t0 + h->o.dt;
     }
     free(row);
-    h->epSteps = 0; h->wmSteps = 0;
+    h->epSteps = 0; h->wmSteps = 0; h->obsSteps = 0;
     say(message, "");
     return 0;
 }
@@ -113,6 +116,25 @@ int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay,
 {
     h->hasStart = 1; h->sy = year; h->sm = month; h->sd = day; h->ssec = secOfDay; h->noleap = noleap;
     if (h->m) mro_set_sim_start(h->m, year, month, day, secOfDay, noleap);
+    say(message, "");
+    return 0;
+}
+
+int mr_set_da(mr_handle h, int qmodOption, int qBlendPeriod, int QerrTrend, char *message)
+{
+    h->qmod = qmodOption; mro_set_da(h->m, qmodOption, qBlendPeriod, QerrTrend);
+    say(message, "");
+    return 0;
+}
+
+int mr_upload_obs(mr_handle h, int nSteps, const int *hasRecord, const double *obs, char *message)
+{
+    const size_t n = (size_t)nSteps * (size_t)h->nRch; int t;
+    free(h->obs); free(h->obsHas);
+    h->obs = (double *)malloc(sizeof(double) * (n + 1)); memcpy(h->obs, obs, sizeof(double) * n);
+    h->obsHas = (int *)malloc(sizeof(int) * (size_t)(nSteps + 1));
+    for (t = 0; t < nSteps; t++) h->obsHas[t] = hasRecord ? hasRecord[t] : 1;
+    h->obsSteps = nSteps;
     say(message, "");
     return 0;
 }

@@ -475,3 +475,44 @@ def test_daily_mean_output_and_delayed_runoff(tmp_path, backend):
     assert np.array_equal(out["time"], np.array([0.0, 86400.0, 172800.0]))
     np.testing.assert_allclose(out["IRFroutedRunoff"], want_q, rtol=3e-6, atol=1e-30)
     np.testing.assert_allclose(out["dlayRunoff"], want_r, rtol=3e-6, atol=1e-30)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_host_reads_the_gauge_files_for_direct_insertion(tmp_path, backend):
+    """<qmodOption> 1: gauge ids of <fname_gageObs> are linked to reaches through the csv <gageMetaFile> (one site is not in
+    the csv, one points at a reach outside the network), records exist only at some of the steps (the others count up
+    Qelapsed), fill values and negative flows are skipped -- the observations reach the routing through mr_upload_obs."""
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=400, seed=4, dt=3600.0, route_opt="14", steps=20)
+    K = ro.shape[0]
+    rng = np.random.default_rng(5)
+    base = Oracle(net, params, opts).run(ro)[0]
+    rch = rng.choice(net.nRch, 12, replace=False)
+    gage_ids = ["G%05d" % i for i in range(14)]
+    csv_ids, csv_rch = gage_ids[:13], list(net.segId[rch]) + [int(net.segId.max()) + 77]     # G00012 -> unknown reach; G00013 not in the csv
+    rec_steps = [2, 3, 4, 9, 15]
+    flow = np.full((len(rec_steps), 14), np.nan)
+    for i, k in enumerate(rec_steps):
+        flow[i, :12] = base[k, rch] * rng.uniform(0.4, 2.0, 12)
+        flow[i, 12:] = 5.0
+    flow[1, 3] = np.nan; flow[2, 5] = -3.0
+    blend, trend = 3, 2
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="da",
+                               gauges=(gage_ids, csv_ids, csv_rch, [k * opts.dt for k in rec_steps], flow, blend, trend))
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "6"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    o = Oracle(net, params, opts); o.set_da(1, blend, trend)
+    qo = np.empty((2, K, net.nRch))
+    for t in range(K):
+        if t in rec_steps:
+            obs = np.full(net.nRch, np.nan); obs[rch] = flow[rec_steps.index(t), :12]
+            o.set_obs(obs)
+        else:
+            o.set_obs(None)
+        o.step(ro[t])
+        qo[0, t] = o.get(orc.F_REACH_Q, 1); qo[1, t] = o.get(orc.F_REACH_Q, 4)
+    np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(out["MCroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+    assert not np.array_equal(qo[0], base)
