@@ -141,6 +141,19 @@ class DomainSet:
                 cols = sub.meta["reach_index"]
                 dom.upload_wm(pick(flux_global, cols), pick(vol_global, cols), vol_jumpstart)
 
+    def set_da(self, qmod_option: int = 1, q_blend_period: int = 10, q_err_trend: int = 1):
+        """Data assimilation options to every domain of this rank (mr_set_da)."""
+        for dom in (self.trib, self.main):
+            if dom is not None:
+                dom.set_da(qmod_option, q_blend_period, q_err_trend)
+
+    def upload_obs(self, obs_global: np.ndarray, has_record=None):
+        """Gauge observations [K, nRch_global] of the next routing call, this rank's reach columns to its domains.  A
+        tributary outlet is corrected where it is routed; its ghost in the mainstem domain only hands the corrected flow on."""
+        for dom, sub in ((self.trib, getattr(self, "trib_net", None)), (self.main, getattr(self, "main_net", None))):
+            if dom is not None:
+                dom.upload_obs(np.ascontiguousarray(np.atleast_2d(obs_global)[:, sub.meta["reach_index"]]), has_record)
+
     def hand_off(self):
         if self.dec.mainstem.size == 0:
             return
