@@ -190,7 +190,7 @@ struct Forcing { std::string path; size_t nTime = 0; std::vector<double> tsec; }
 // MAXQPAR+1 waves between steps.
 void check(int ierr, const char *msg) { if (ierr) die(ierr, msg); }
 
-void write_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, double T0, long steps) {
+void write_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, double T0, long steps, bool da = false) {
     char msg[MR_STRLEN];
     const size_t N = segId.size();
     const int nb = (int)mr_get_info(h, MR_INFO_NTDH_BAS), mx = (int)mr_get_info(h, MR_INFO_MAXTDH), W = MR_KW_SLOTS;
@@ -215,6 +215,10 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
         vMol[m - 3] = w.def_var("q_sub_" + e, nc3::NC_DOUBLE, {dMol, dSeg}, {{"units", "m3/s"}});
         vMolVol[m - 3] = w.def_var("volume_" + e, nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}});
     }
+    // discharge error of the corrected methods: written only under data assimilation (write_restart_pio.f90:1021-1030 and siblings)
+    static const char *qerrName[6] = {nullptr, "qerror_irf", nullptr, "qerror_kw", "qerror_mc", "qerror_dw"};      // popMetadat.f90:285-300
+    int vQerr[6] = {-1, -1, -1, -1, -1, -1};
+    if (da) for (int q = 0; q < o.n_routes; ++q) { const int m = o.route_methods[q]; if (qerrName[m]) vQerr[m] = w.def_var(qerrName[m], nc3::NC_DOUBLE, {dSeg}, {{"units", "m3/s"}}); }
     w.end_def();
     w.put_int(vId, segId.data());
     const double tb[2] = {T0, T0 + o.dt}; w.put_double(vTb, tb); (void)steps;
@@ -255,11 +259,15 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
         w.put_double(vMol[m - 3], transposed(a, nm).data());
         w.put_double(vMolVol[m - 3], &lv[(size_t)q * N]);
     }
+    if (da) {
+        std::vector<double> qe((size_t)o.n_routes * N); check(mr_get_state(h, MR_ST_QERROR, qe.data(), (long)qe.size() * 8, msg), msg);
+        for (int q = 0; q < o.n_routes; ++q) if (vQerr[o.route_methods[q]] >= 0) w.put_double(vQerr[o.route_methods[q]], &qe[(size_t)q * N]);
+    }
     w.close();
 }
 
 // returns TSEC(1) of the next step
-double read_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId) {
+double read_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, bool da = false) {
     char msg[MR_STRLEN];
     const size_t N = segId.size();
     nc3::Reader r(path);
@@ -305,6 +313,15 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
         }
     }
     check(mr_set_state(h, MR_ST_LAKE_VOL, lv.data(), (long)lv.size() * 8, msg), msg);
+    if (da) {                                   // qerror_<method> if the file has it, else 0 (read_restart.f90:358-366); Qobs / Qelapsed start from 0
+        static const char *qerrName[6] = {nullptr, "qerror_irf", nullptr, "qerror_kw", "qerror_mc", "qerror_dw"};
+        std::vector<double> qe((size_t)o.n_routes * N, 0.0);
+        for (int q = 0; q < o.n_routes; ++q) {
+            const char *nm = qerrName[o.route_methods[q]];
+            if (nm && r.find(nm)) { r.read_all(r.var(nm), t); std::copy(t.begin(), t.end(), qe.begin() + (size_t)q * N); }
+        }
+        check(mr_set_state(h, MR_ST_QERROR, qe.data(), (long)qe.size() * 8, msg), msg);
+    }
     return tb[0];
 }
 
@@ -772,7 +789,7 @@ int main(int argc, char **argv) {
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
-            T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId);   // init_state_data, init_model_data.f90:332-623
+            T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId, qmodOption == 1);   // init_state_data, init_model_data.f90:332-623
         if (o.is_lake_sim) {                                  // the library counts steps from the cold start: step 0 was T0 seconds before <sim_start>
             const Civil cv = civil_from_sec(tStart - T0, noleap);
             ierr = mr_set_sim_start(h, cv.y, cv.mo, cv.d, (double)cv.sod, noleap ? 1 : 0, msg); if (ierr) die(ierr, msg);
@@ -823,7 +840,7 @@ int main(int argc, char **argv) {
             }
             T0 += nb * o.dt; s += nb;
             if (nextRestart < restartPlan.size() && restartPlan[nextRestart].first + 1 == s) {                              // main_restart, route_runoff.f90:102
-                write_restart(h, restartPlan[nextRestart].second, o, segId, T0, (long)std::lround(T0 / o.dt));
+                write_restart(h, restartPlan[nextRestart].second, o, segId, T0, (long)std::lround(T0 / o.dt), qmodOption == 1);
                 std::printf("{\"restart\": \"%s\"}\n", restartPlan[nextRestart].second.c_str());
                 ++nextRestart;
             }

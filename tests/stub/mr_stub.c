@@ -236,6 +236,9 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message)
             kw_free(s);
             return 0; }
         case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: mro_get_molecule(h->m, M_KW + (var - MR_ST_MOLECULE_KW), d); return 0;
+        case MR_ST_QERROR: for (r = 0; r < h->o.n_routes; r++) memcpy(d + (size_t)r * N, h->m->Qerror[h->o.route_methods[r]], 8 * N); return 0;
+        case MR_ST_DA_QOBS: memcpy(d, h->m->Qobs, 8 * N); return 0;
+        case MR_ST_DA_QELAPSED: memcpy(ip, h->m->Qelapsed, 4 * N); return 0;
         default: say(message, "mr_get_state/unknown state variable"); return 1;
     }
 }
@@ -268,6 +271,9 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
             kw_free(s);
             return 0; }
         case MR_ST_MOLECULE_KW: case MR_ST_MOLECULE_MC: case MR_ST_MOLECULE_DW: mro_set_molecule(h->m, M_KW + (var - MR_ST_MOLECULE_KW), d); return 0;
+        case MR_ST_QERROR: for (r = 0; r < h->o.n_routes; r++) memcpy(h->m->Qerror[h->o.route_methods[r]], d + (size_t)r * N, 8 * N); return 0;
+        case MR_ST_DA_QOBS: memcpy(h->m->Qobs, d, 8 * N); return 0;
+        case MR_ST_DA_QELAPSED: memcpy(h->m->Qelapsed, ip, 4 * N); return 0;
         default: say(message, "mr_set_state/unknown state variable"); return 1;
     }
 }

@@ -516,3 +516,56 @@ def test_host_reads_the_gauge_files_for_direct_insertion(tmp_path, backend):
     np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
     np.testing.assert_allclose(out["MCroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
     assert not np.array_equal(qo[0], base)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_restart_under_data_assimilation_carries_the_discharge_error(tmp_path, backend):
+    """qerror_irf / qerror_mc are written to the restart file only under <qmodOption> 1 (write_restart_pio.f90:1021-1030) and read
+    back when present (read_restart.f90:358-366); Qobs / Qelapsed are not part of the reference's restart file and start from
+    zero again (init_model_data.f90:511-512) -- so a restarted run equals the oracle told the same: Qerror kept, Qobs = 0,
+    Qelapsed = 0."""
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("conus", n=300, seed=6, dt=3600.0, route_opt="14", steps=16)
+    rng = np.random.default_rng(8)
+    base = Oracle(net, params, opts).run(ro)[0]
+    rch = rng.choice(net.nRch, 10, replace=False)
+    gage_ids = ["S%03d" % i for i in range(10)]
+    rec_steps = [1, 5, 6, 11]
+    flow = np.stack([base[k, rch] * rng.uniform(0.5, 1.8, 10) for k in rec_steps])
+    blend, trend = 6, 1
+    d = str(tmp_path)
+    g = lambda steps: (gage_ids, gage_ids, list(net.segId[rch]), [k * opts.dt for k in steps], flow[[rec_steps.index(k) for k in steps]], blend, trend)
+    run = lambda ctl: subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+    r = run(casefiles.write_case(d, net, params, opts, ro[:8], case_name="first", restart_write="last", gauges=g(rec_steps)))
+    assert r.returncode == 0, r.stderr
+    rfile = next(x["restart"] for x in (json.loads(l) for l in r.stdout.strip().splitlines()) if "restart" in x)
+    rst = casefiles.read_history(rfile)
+    assert {"qerror_irf", "qerror_mc"} <= set(rst) and np.abs(rst["qerror_irf"]).max() > 0.0
+    # second leg: the gauge file's time axis counts from the start of the whole run
+    ctl = casefiles.write_case(d, net, params, opts, ro[8:], case_name="second", fname_state_in=os.path.basename(rfile), first_step=8,
+                               gauges=(gage_ids, gage_ids, list(net.segId[rch]), [(k - 8) * opts.dt for k in rec_steps if k >= 8],
+                                       flow[[i for i, k in enumerate(rec_steps) if k >= 8]], blend, trend))
+    r = run(ctl); assert r.returncode == 0, r.stderr
+    h2 = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    o = Oracle(net, params, opts); o.set_da(1, blend, trend)
+    qo = np.empty((2, 16, net.nRch))
+    for t in range(16):
+        if t == 8:                                              # what the restart file does not carry
+            o.set(orc.F_QOBS, np.zeros(net.nRch)); lib_reset_elapsed(o)
+        if t in rec_steps:
+            obs = np.full(net.nRch, np.nan); obs[rch] = flow[rec_steps.index(t)]
+            o.set_obs(obs)
+        else:
+            o.set_obs(None)
+        o.step(ro[t])
+        qo[0, t] = o.get(orc.F_REACH_Q, 1); qo[1, t] = o.get(orc.F_REACH_Q, 4)
+    np.testing.assert_allclose(h2["IRFroutedRunoff"], qo[0, 8:].astype(np.float32), rtol=2e-6, atol=1e-30)
+    np.testing.assert_allclose(h2["MCroutedRunoff"], qo[1, 8:].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+def lib_reset_elapsed(o):
+    import ctypes as C
+    from oracle import oracle as orc
+    z = np.zeros(o.net.nRch, dtype=np.int32)
+    orc.lib().mro_set_qelapsed(o.h, z.ctypes.data_as(C.POINTER(C.c_int)))
