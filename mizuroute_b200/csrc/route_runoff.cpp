@@ -762,6 +762,21 @@ int main(int argc, char **argv) {
         const char *lname[6] = {"accumulated runoff from all upstream reaches", "routed runoff in each reach-impulse response function", "routed runoff in each reach-kinematic wave tracking",
                                 "routed runoff in each reach-kinematic wave", "routed runoff in each reach-muskingum-cunge", "routed runoff in each reach-diffusive wave"};
         const bool wantDlay = c.flag("dlayRunoff", true);
+        // Per-method reach volume (value at the end of the output period), mean inflow from upstream and the mean instantaneous
+        // runoff (histVars_data.f90:200-246).  The library keeps these for the last step of a call only, so a batch ends where an
+        // output period ends when a volume is asked for, and is one step long when an inflow or instRunoff is.  All default to F
+        // here (the reference writes IRFvolume by default, popMetadat.f90:246).
+        const char *volName[6] = {nullptr, "IRFvolume", "KWTvolume", "KWvolume", "MCvolume", "DWvolume"};
+        const char *infName[6] = {nullptr, "IRFinflow", "KWTinflow", "KWinflow", "MCinflow", "DWinflow"};
+        std::vector<char> wantVol(o.n_routes, 0), wantInf(o.n_routes, 0);
+        bool anyVol = false, anyStep = c.flag("instRunoff", false);
+        const bool wantInst = anyStep;
+        for (int r = 0; r < o.n_routes; ++r) {
+            const int m = o.route_methods[r];
+            if (volName[m] && c.flag(volName[m], false)) { wantVol[r] = 1; anyVol = true; }
+            if (infName[m] && c.flag(infName[m], false)) { wantInf[r] = 1; anyStep = true; }
+        }
+        std::vector<int> vVol(o.n_routes, -1), vInf(o.n_routes, -1); int vInst = -1;
         int vTime = -1, vDlay = -1;
         std::vector<int> vQ(o.n_routes, -1);
         std::unique_ptr<nc3::Writer> w;
@@ -774,6 +789,12 @@ int main(int argc, char **argv) {
             for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
                 vQ[r] = w->def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
             if (wantDlay) vDlay = w->def_var("dlayRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "delayed runoff in each reach"}});
+            if (wantInst) vInst = w->def_var("instRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "instantaneous runoff into stream or lake"}});
+            for (int r = 0; r < o.n_routes; ++r) {
+                const int m = o.route_methods[r];
+                if (wantVol[r]) vVol[r] = w->def_var(volName[m], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3"}, {"long_name", "Volume in lake or stream"}});
+                if (wantInf[r]) vInf[r] = w->def_var(infName[m], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "Inflow from upstream lake or streams"}});
+            }
             w->global_attr("title", "mizuRoute routing (mizuroute-b200)");
             w->end_def();
             w->put_int(vId, segId.data());
@@ -785,6 +806,13 @@ int main(int argc, char **argv) {
         std::vector<double> wmFluxRows(fluxWm ? (size_t)batch * nRch : 0), wmVolRows(volWm ? (size_t)batch * nRch : 0);
         std::vector<double> obsRows(qmodOption == 1 ? (size_t)batch * nRch : 0); std::vector<int> obsHas(batch, 0);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
+        std::vector<double> stepX(anyStep ? (size_t)(o.n_routes + 1) * nRch : 0), accX(stepX.size(), 0.0), volNow(anyVol ? nRch : 0);
+        auto put_volumes = [&](size_t rec) {                       // REACH_VOL(1) as the last step of the call left it
+            for (int r = 0; r < o.n_routes; ++r) if (vVol[r] >= 0) {
+                int e = mr_get_flux(h, o.route_methods[r], MR_REACH_VOL1, volNow.data(), msg); if (e) die(e, msg);
+                w->put_record(vVol[r], rec, volNow.data());
+            }
+        };
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
@@ -798,6 +826,8 @@ int main(int argc, char **argv) {
         for (size_t s = 0; s < nSteps;) {
             int nb = (int)std::min<size_t>(batch, nSteps - s);
             if (nextRestart < restartPlan.size()) nb = (int)std::min<size_t>(nb, restartPlan[nextRestart].first + 1 - s);      // a batch ends where a restart file is due
+            if (anyStep) nb = 1;
+            else if (anyVol) nb = std::min(nb, nAgg - nAcc);                   // the batch ends where the output period ends
             for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
             if (lakeForcing) {
                 for (int k = 0; k < nb; ++k) { load_var(vsEvapo, s + k, &evRows[(size_t)k * nHRU], nHRU, false); load_var(vsPrecip, s + k, &prRows[(size_t)k * nHRU], nHRU, false); }
@@ -817,6 +847,10 @@ int main(int argc, char **argv) {
             }
             ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
+            if (anyStep) {                                                     // nb == 1: REACH_INFLOW / BASIN_QI of this step
+                for (int r = 0; r < o.n_routes; ++r) if (wantInf[r]) { ierr = mr_get_flux(h, o.route_methods[r], MR_REACH_INFLOW, &stepX[(size_t)r * nRch], msg); if (ierr) die(ierr, msg); }
+                if (wantInst) { ierr = mr_get_flux(h, o.route_methods[0], MR_BASIN_QI, &stepX[(size_t)o.n_routes * nRch], msg); if (ierr) die(ierr, msg); }
+            }
             for (int k = 0; k < nb; ++k) {
                 const double tsec = (tStart - tStartAsked) + (double)(s + k) * o.dt;    // seconds since <sim_start>
                 if (fileNo < plan.size() && plan[fileNo].first == s + k) { open_history(plan[fileNo++].path); recOut = 0; }     // main_new_file
@@ -824,10 +858,14 @@ int main(int argc, char **argv) {
                     w->put_record(vTime, recOut, &tsec);
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &q[((size_t)r * nb + k) * nRch]);
                     if (vDlay >= 0) w->put_record(vDlay, recOut, &qd[(size_t)k * nRch]);
+                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &stepX[(size_t)r * nRch]);
+                    if (vInst >= 0) w->put_record(vInst, recOut, &stepX[(size_t)o.n_routes * nRch]);
+                    if (anyVol) put_volumes(recOut);
                     ++recOut;
                     continue;
                 }
-                if (nAcc == 0) { tAcc = tsec; std::fill(acc.begin(), acc.end(), 0.0); }
+                if (nAcc == 0) { tAcc = tsec; std::fill(acc.begin(), acc.end(), 0.0); std::fill(accX.begin(), accX.end(), 0.0); }
+                for (size_t i = 0; i < accX.size(); ++i) accX[i] += stepX[i];
                 for (int r = 0; r < o.n_routes; ++r) for (size_t i = 0; i < nRch; ++i) acc[(size_t)r * nRch + i] += q[((size_t)r * nb + k) * nRch + i];
                 if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
@@ -835,6 +873,10 @@ int main(int argc, char **argv) {
                     w->put_record(vTime, recOut, &tAcc);
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &acc[(size_t)r * nRch]);
                     if (vDlay >= 0) w->put_record(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
+                    for (auto &v : accX) v /= (double)nAcc;
+                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &accX[(size_t)r * nRch]);
+                    if (vInst >= 0) w->put_record(vInst, recOut, &accX[(size_t)o.n_routes * nRch]);
+                    if (anyVol) put_volumes(recOut);
                     ++recOut; nAcc = 0;
                 }
             }

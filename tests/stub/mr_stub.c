@@ -208,6 +208,13 @@ static kw_t kw_get(mr_handle h)
 }
 static void kw_free(kw_t s) { free(s.n); free(s.qf); free(s.ti); free(s.tr); free(s.rf); }
 
+int mr_get_flux(mr_handle h, int method, int field, double *out, char *message)
+{
+    say(message, "");
+    if (mro_get(h->m, method, field, out)) { say(message, "mr_get_flux/unknown field"); return 1; }     /* the field ids are the oracle's */
+    return 0;
+}
+
 int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message)
 {
     const size_t N = (size_t)h->nRch, W = MR_KW_SLOTS; size_t i, k; int r;

@@ -569,3 +569,32 @@ def lib_reset_elapsed(o):
     from oracle import oracle as orc
     z = np.zeros(o.net.nRch, dtype=np.int32)
     orc.lib().mro_set_qelapsed(o.h, z.ctypes.data_as(C.POINTER(C.c_int)))
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("freq,keys", [("daily", {"IRFvolume": "T", "KWvolume": "T"}), ("5", {"IRFinflow": "T", "instRunoff": "T", "KWvolume": "T"}),
+                                       ("1", {"IRFvolume": "T", "KWinflow": "T"})], ids=["daily-volumes", "5-inflow-inst", "1-mixed"])
+def test_history_volume_inflow_and_instantaneous_runoff(tmp_path, backend, freq, keys):
+    """<IRFvolume> ... = REACH_VOL(1) at the END of the output period, <IRFinflow> ... = mean REACH_INFLOW, <instRunoff> = mean
+    BASIN_QI over it (histVars_data.f90:200-246) -- the host cuts its batches where the library's last-step values are needed."""
+    from oracle import oracle as orc
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("random", n=90, seed=3, dt=3600.0, route_opt="13", steps=52)
+    ctl = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="vars", output_frequency=freq, extra_keys=keys)
+    r = subprocess.run([_routing_host(backend), ctl, "--batch", "7"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    o = Oracle(net, params, opts)
+    ser = {k: [] for k in ("IRFvolume", "KWvolume", "IRFinflow", "KWinflow", "instRunoff", "IRFroutedRunoff")}
+    for t in range(52):
+        o.step(ro[t])
+        ser["IRFvolume"].append(o.get(orc.F_REACH_VOL1, 1)); ser["KWvolume"].append(o.get(orc.F_REACH_VOL1, 3))
+        ser["IRFinflow"].append(o.get(orc.F_REACH_INFLOW, 1)); ser["KWinflow"].append(o.get(orc.F_REACH_INFLOW, 3))
+        ser["instRunoff"].append(o.get(orc.F_BASIN_QI)); ser["IRFroutedRunoff"].append(o.get(orc.F_REACH_Q, 1))
+    n = 24 if freq == "daily" else int(freq)
+    bounds = [(a, min(a + n, 52)) for a in range(0, 52, n)]
+    for name in list(keys) + ["IRFroutedRunoff"]:
+        a = np.array(ser[name])
+        want = np.stack([a[hi - 1] if name.endswith("volume") else a[lo:hi].mean(0) for lo, hi in bounds])
+        np.testing.assert_allclose(out[name], want, rtol=1e-4 if name.startswith("KW") else 3e-6, atol=1e-12, err_msg=name)
+    assert set(out) >= set(keys) and "KWTvolume" not in out
