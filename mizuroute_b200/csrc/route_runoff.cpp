@@ -776,6 +776,10 @@ int main(int argc, char **argv) {
             if (volName[m] && c.flag(volName[m], false)) { wantVol[r] = 1; anyVol = true; }
             if (infName[m] && c.flag(infName[m], false)) { wantInf[r] = 1; anyStep = true; }
         }
+        // <basRunoff>: HRU runoff as it enters basin2reach, period mean, [time, hru] with basinID (historyFile.f90:156-165, default T as
+        // in the reference); with <is_remap> T the remapped values exist on the device only and the variable is left out
+        const bool wantBas = c.flag("basRunoff", true) && !isRemap;
+        int vBas = -1;
         std::vector<int> vVol(o.n_routes, -1), vInf(o.n_routes, -1); int vInst = -1;
         int vTime = -1, vDlay = -1;
         std::vector<int> vQ(o.n_routes, -1);
@@ -786,6 +790,9 @@ int main(int argc, char **argv) {
             const int dTime = w->def_dim("time", 0), dSeg = w->def_dim("seg", nRch);
             vTime = w->def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
             const int vId = w->def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
+            int dHru = -1, vHid = -1;
+            if (wantBas) { dHru = w->def_dim("hru", nHRU); vHid = w->def_var("basinID", nc3::NC_INT, {dHru}, {{"long_name", "basin ID"}});
+                           vBas = w->def_var("basRunoff", nc3::NC_FLOAT, {dTime, dHru}, {{"units", c.need("units_qsim")}, {"long_name", "basin runoff"}}); }
             for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true))
                 vQ[r] = w->def_var(vname[o.route_methods[r]], nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", lname[o.route_methods[r]]}});
             if (wantDlay) vDlay = w->def_var("dlayRunoff", nc3::NC_FLOAT, {dTime, dSeg}, {{"units", "m3/s"}, {"long_name", "delayed runoff in each reach"}});
@@ -798,6 +805,7 @@ int main(int argc, char **argv) {
             w->global_attr("title", "mizuRoute routing (mizuroute-b200)");
             w->end_def();
             w->put_int(vId, segId.data());
+            if (vHid >= 0) w->put_int(vHid, hruId.data());
         };
 
         // ---- time loop (route_runoff.f90:80-106), `batch` steps per library call
@@ -806,6 +814,7 @@ int main(int argc, char **argv) {
         std::vector<double> wmFluxRows(fluxWm ? (size_t)batch * nRch : 0), wmVolRows(volWm ? (size_t)batch * nRch : 0);
         std::vector<double> obsRows(qmodOption == 1 ? (size_t)batch * nRch : 0); std::vector<int> obsHas(batch, 0);
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
+        std::vector<double> accB(wantBas ? nHRU : 0, 0.0);
         std::vector<double> stepX(anyStep ? (size_t)(o.n_routes + 1) * nRch : 0), accX(stepX.size(), 0.0), volNow(anyVol ? nRch : 0);
         auto put_volumes = [&](size_t rec) {                       // REACH_VOL(1) as the last step of the call left it
             for (int r = 0; r < o.n_routes; ++r) if (vVol[r] >= 0) {
@@ -861,11 +870,14 @@ int main(int argc, char **argv) {
                     for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &stepX[(size_t)r * nRch]);
                     if (vInst >= 0) w->put_record(vInst, recOut, &stepX[(size_t)o.n_routes * nRch]);
                     if (anyVol) put_volumes(recOut);
+                    if (vBas >= 0) w->put_record(vBas, recOut, &ro[(size_t)k * inCols]);
                     ++recOut;
                     continue;
                 }
                 if (nAcc == 0) { tAcc = tsec; std::fill(acc.begin(), acc.end(), 0.0); std::fill(accX.begin(), accX.end(), 0.0); }
+                if (nAcc == 0) std::fill(accB.begin(), accB.end(), 0.0);
                 for (size_t i = 0; i < accX.size(); ++i) accX[i] += stepX[i];
+                for (size_t i = 0; i < accB.size(); ++i) accB[i] += ro[(size_t)k * inCols + i];
                 for (int r = 0; r < o.n_routes; ++r) for (size_t i = 0; i < nRch; ++i) acc[(size_t)r * nRch + i] += q[((size_t)r * nb + k) * nRch + i];
                 if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
@@ -877,6 +889,7 @@ int main(int argc, char **argv) {
                     for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &accX[(size_t)r * nRch]);
                     if (vInst >= 0) w->put_record(vInst, recOut, &accX[(size_t)o.n_routes * nRch]);
                     if (anyVol) put_volumes(recOut);
+                    if (vBas >= 0) { for (auto &v : accB) v /= (double)nAcc; w->put_record(vBas, recOut, accB.data()); }
                     ++recOut; nAcc = 0;
                 }
             }

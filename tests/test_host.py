@@ -598,3 +598,6 @@ def test_history_volume_inflow_and_instantaneous_runoff(tmp_path, backend, freq,
         want = np.stack([a[hi - 1] if name.endswith("volume") else a[lo:hi].mean(0) for lo, hi in bounds])
         np.testing.assert_allclose(out[name], want, rtol=1e-4 if name.startswith("KW") else 3e-6, atol=1e-12, err_msg=name)
     assert set(out) >= set(keys) and "KWTvolume" not in out
+    want_b = np.stack([ro[lo:hi].mean(0) for lo, hi in bounds])                  # <basRunoff>: the HRU runoff as read, period mean
+    np.testing.assert_allclose(out["basRunoff"], want_b, rtol=3e-6, atol=1e-30)
+    assert np.array_equal(out["basinID"], net.hruId)
