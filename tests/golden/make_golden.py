@@ -27,6 +27,14 @@ CASES = {
     "binary127_hourly_1_hwtop": dict(kind="binary", n=127, seed=2, dt=3600.0, route_opt="1", steps=30, hw_drain_point=1),
 }
 
+# Fixtures of the options that hang off the per-reach loop: the Euler schemes, water management (is_flux_wm: flux rows stored with
+# the fixture) and data assimilation (qmodOption 1: gauge rows + record flags stored with the fixture)
+OPTION_CASES = {
+    "tree60_hourly_345": dict(case=dict(kind="random", n=60, seed=5, dt=3600.0, route_opt="345", steps=30)),
+    "conus300_hourly_135_wm": dict(case=dict(kind="conus", n=300, seed=4, dt=3600.0, route_opt="135", steps=16), wm=True),
+    "conus300_hourly_0145_da": dict(case=dict(kind="conus", n=300, seed=4, dt=3600.0, route_opt="0145", steps=20), da=(4, 2)),   # qBlendPeriod, QerrTrend
+}
+
 NET_FIELDS = ["segId", "downSegId", "length", "slope", "hruId", "hruSegId", "area", "islake", "lakeModelType",
               "D03_MaxStorage", "D03_Coefficient", "D03_Power", "D03_S0"]
 
@@ -47,8 +55,62 @@ def build(name):
     return out
 
 
+def option_inputs(name):
+    """(net, params, opts, runoff, flux_wm or None, (obs, has_record) or None) of an OPTION_CASES fixture, seeded."""
+    from tests.util import gauge_series
+    spec = OPTION_CASES[name]
+    net, params, opts, ro = case(**spec["case"])
+    K = ro.shape[0]
+    flux = obs = None
+    if spec.get("wm"):
+        rng = np.random.default_rng(17)
+        flux = np.full((K, net.nRch), -9999.0)
+        pick = rng.random((K, net.nRch)) < 0.3
+        flux[pick] = rng.choice([-1.0, 1.0], pick.sum()) * rng.lognormal(np.log(0.02), 1.5, pick.sum())
+    if spec.get("da"):
+        base = Oracle(net, params, opts).run(ro)[1]
+        o, has, _ = gauge_series(net, K, seed=23, base=base)
+        obs = (o, has)
+    return net, params, opts, ro, flux, obs
+
+
+def run_option_case(name, net, params, opts, ro, flux, obs):
+    o = Oracle(net, params, opts)
+    if obs is not None:
+        o.set_da(1, *OPTION_CASES[name]["da"])
+    q = np.empty((len(opts.route_opt), ro.shape[0], net.nRch))
+    for t in range(ro.shape[0]):
+        if flux is not None:
+            o.set_wm(flux[t])
+        if obs is not None:
+            o.set_obs(obs[0][t] if obs[1][t] else None)
+        o.step(ro[t])
+        for i, c in enumerate(opts.route_opt):
+            q[i, t] = o.get(0, int(c))
+    return q
+
+
+def build_option(name):
+    net, params, opts, ro, flux, obs = option_inputs(name)
+    out = {"runoff": ro, "q": run_option_case(name, net, params, opts, ro, flux, obs)}
+    if flux is not None:
+        out["flux_wm"] = flux
+    if obs is not None:
+        out["obs"], out["has_record"] = obs
+    for f in NET_FIELDS:
+        v = getattr(net, f)
+        if v is not None:
+            out["net_" + f] = v
+    return out
+
+
 if __name__ == "__main__":
-    for name in CASES:
+    only_options = "--options-only" in sys.argv          # leave the fixtures of CASES as they are
+    for name in ([] if only_options else CASES):
         d = build(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
         print(name, {k: v.shape for k, v in d.items() if k in ("runoff", "q")})
+    for name in OPTION_CASES:
+        d = build_option(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+        print(name, d["q"].shape)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from mizuroute_b200.network import RiverNetwork, RouteOptions, RouteParams
-from tests.golden.make_golden import CASES, NET_FIELDS
+from tests.golden.make_golden import CASES, NET_FIELDS, OPTION_CASES, run_option_case
 from tests.util import IRF_RTOL, KWT_RTOL, rel_err
 
 HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -61,3 +61,44 @@ def test_cuda_reproduces_golden(name, batch):
     if "2" in opts.route_opt:
         assert np.array_equal(r.get_state(capi.ST_KWT_NWAVE), z["state_kwt_n"])
     assert rel_err(r.get_state(capi.ST_BASIN_QFUTURE), z["state_qfuture"], 1e-30) <= IRF_RTOL
+
+
+def load_option(name):
+    z = np.load(os.path.join(HERE, name + ".npz"))
+    kw = OPTION_CASES[name]["case"]
+    net = RiverNetwork(**{f: (z["net_" + f] if "net_" + f in z.files else None) for f in NET_FIELDS})
+    opts = RouteOptions(dt=kw["dt"], route_opt=kw["route_opt"], runoffMin=1e-15)
+    flux = z["flux_wm"] if "flux_wm" in z.files else None
+    obs = (z["obs"], z["has_record"]) if "obs" in z.files else None
+    return z, net, RouteParams(), opts, flux, obs
+
+
+@pytest.mark.parametrize("name", sorted(OPTION_CASES))
+def test_oracle_reproduces_option_golden(name):
+    """Euler schemes, water management, data assimilation: the oracle reproduces the committed discharge bit for bit."""
+    z, net, params, opts, flux, obs = load_option(name)
+    assert np.array_equal(run_option_case(name, net, params, opts, z["runoff"], flux, obs), z["q"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(OPTION_CASES))
+def test_cuda_reproduces_option_golden(name):
+    from mizuroute_b200.route import Router
+    z, net, params, opts, flux, obs = load_option(name)
+    ro, batch = z["runoff"], 6
+    r = Router(net, params, opts, max_batch=batch)
+    if obs is not None:
+        r.set_da(1, *OPTION_CASES[name]["da"])
+    parts = []
+    for s in range(0, ro.shape[0], batch):
+        if flux is not None:
+            r.upload_wm(flux[s:s + batch])
+        if obs is not None:
+            r.upload_obs(obs[0][s:s + batch], obs[1][s:s + batch])
+        parts.append(r.route_batch(np.ascontiguousarray(ro[s:s + batch])))
+    q = np.concatenate(parts, axis=1)
+    for i, c in enumerate(opts.route_opt):
+        if c == "0":
+            assert np.array_equal(q[i], z["q"][i])
+        else:                                      # IRF 1e-6 (bit-identical without options), Euler schemes 1e-4 (pow / Newton stop, test_schemes_gpu.py)
+            assert rel_err(q[i], z["q"][i], floor=1e-9) <= (IRF_RTOL if c == "1" else 1e-4), c
