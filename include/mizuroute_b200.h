@@ -147,6 +147,18 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
  * upload -> route (device only, no host<->device traffic) -> download. */
 int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *message);
 int mr_route_resident(mr_handle h, int nSteps, double T0, char *message);
+/* Forcing ingest on the device, for callers that hold raw forcing records instead of per-step rows (replaces what
+ * get_basin_runoff does to the runoff, get_basin_runoff.f90:19-251, when no areal remapping is needed):
+ *   mr_set_ingest      forcingOfHru [nHRU]: column of every river-network HRU in the forcing records, -1 = none (the IX_in of
+ *                      sort_flux inverted, process_remap.f90:271-314); scale / offset = <scale_factor_runoff> / <offset_value_runoff>
+ *                      (-9999 = not given, scale_forcing :375-423); fill = the records' fill value.  After mr_set_network.
+ *   mr_ingest_records  records [nRec][nForcing]; step t takes records recIdx[recPtr[t] .. recPtr[t+1]) with the shares recFrac of
+ *                      the step (timeMap_sim_forc, :256-369; recFrac NULL = exactly one record per step, taken as it is); the
+ *                      time-weighted mean skips fill values (read_1D_forcing, read_runoff.f90:298-325); HRUs without forcing and
+ *                      negative values become 0.  Leaves nSteps runoff rows resident, as mr_upload_runoff does: follow with
+ *                      mr_route_resident(h, nSteps, T0). */
+int mr_set_ingest(mr_handle h, int nForcing, const int *forcingOfHru, double scale, double offset, double fill, char *message);
+int mr_ingest_records(mr_handle h, int nSteps, int nRec, const double *records, const int *recPtr, const int *recIdx, const double *recFrac, char *message);
 /* Lake evaporation / precipitation of the NEXT routing call (mr_step, mr_step_batch*, mr_route_resident*), which must
  * route exactly nSteps steps: basinEvapo / basinPrecip [nSteps][nHRU] in the units of the runoff, river-network HRU
  * order (the optional arguments basinEvapo_in / basinPrecip_in of main_route, main_route.f90:33-34,174-199).  They pass

@@ -34,7 +34,7 @@ EXPORTS = [
     "mr_download_q", "mr_download_basin_q", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
     "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_remap", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
-    "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start", "mr_upload_wm", "mr_set_da", "mr_upload_obs",
+    "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start", "mr_upload_wm", "mr_set_da", "mr_upload_obs", "mr_set_ingest", "mr_ingest_records",
 ]
 
 
@@ -120,6 +120,8 @@ def load(rebuild_if_stale: bool = True):
     L.mr_upload_wm.argtypes = [vp, C.c_int, dp, dp, C.c_int, cp]
     L.mr_set_da.argtypes = [vp, C.c_int, C.c_int, C.c_int, cp]
     L.mr_upload_obs.argtypes = [vp, C.c_int, C.POINTER(C.c_int), dp, cp]
+    L.mr_set_ingest.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double, cp]
+    L.mr_ingest_records.argtypes = [vp, C.c_int, C.c_int, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp, cp]
     L.mr_set_lake_param.argtypes = [vp, cp, C.c_int, dp, cp]
     L.mr_set_sim_start.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, cp]
     L.mr_destroy.argtypes = [vp]

@@ -26,6 +26,7 @@
 #include "mr_irf.cuh"
 #include "mr_euler.cuh"
 #include "mr_lake.cuh"
+#include "mr_ingest.h"
 
 namespace mr {
 
@@ -162,6 +163,16 @@ __global__ void k_remap(const double *forcing, double *out, const int *mapNet, c
         if (sumW > xTol) { if (fabs(1.0 - sumW) > xTol) r = r / sumW; }
         out[(size_t)t * nHRU + j] = r;
     }
+}
+
+// forcing records -> runoff rows of the batch in river-network HRU order (ingest_value, mr_ingest.h); thread per HRU, steps in y
+__global__ void k_ingest(const double *rec, double *out, const int *srcOfHru, const int *recPtr, const int *recIdx, const double *recFrac,
+                         int nIn, int nHRU, int K, int rescale, double A, double B, double fill) {
+    const int hru = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hru >= nHRU) return;
+    const int src = srcOfHru[hru];
+    for (int t = blockIdx.y; t < K; t += gridDim.y)
+        out[(size_t)t * nHRU + hru] = ingest_value(rec, nIn, src, recIdx, recFrac, recPtr[t], recPtr[t + 1], rescale, A, B, fill);
 }
 
 // reach-level evaporation / precipitation of the lake reaches for the K steps of a batch (main_route.f90:174-199)

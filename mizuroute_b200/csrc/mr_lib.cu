@@ -81,6 +81,10 @@ struct mr_handle_s {
     int nLake = 0, lakeForcingSteps = 0;
     int *dLakePos = nullptr;
     double *dEvapo = nullptr, *dPrecip = nullptr, *dLakeEvap = nullptr, *dLakePrecip = nullptr;
+    // forcing ingest on the device (mr_set_ingest, mr_ingest_records)
+    int ingestCols = 0, ingestRescale = 0; double ingestA = 1.0, ingestB = 0.0, ingestFill = -9999.0;
+    int *dIngestSrc = nullptr, *dIngestPtr = nullptr, *dIngestIdx = nullptr; double *dIngestRec = nullptr, *dIngestFrac = nullptr;
+    size_t ingestRecCap = 0, ingestIdxCap = 0;
     // multi-domain hand-off
     std::vector<int> ghostSegId, ghostKind; std::vector<double> ghostTotArea, ghostWidth;   // consumed by mr_set_network
     int nGhost = 0, nExport = 0;
@@ -453,6 +457,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     h->wmSteps = 0; h->wmActive = false; h->dWmFlux = h->dWmVol = nullptr; h->dLakeTargVol = nullptr;
     h->obsSteps = 0; h->daActive = false; h->dDaQobs = h->dQobsState = nullptr; h->dDaEl = h->dElState = nullptr; h->dHasRecord = nullptr;
     for (int m = 0; m < N_METHODS; ++m) h->dQerr[m] = nullptr;
+    h->ingestCols = 0; h->dIngestSrc = h->dIngestPtr = h->dIngestIdx = nullptr; h->dIngestRec = h->dIngestFrac = nullptr; h->ingestRecCap = h->ingestIdxCap = 0;
     h->nLake = 0; h->lakeForcingSteps = 0; h->dLakePos = nullptr; h->dEvapo = h->dPrecip = h->dLakeEvap = h->dLakePrecip = nullptr;
     for (int w = 0; w < 2; ++w) { h->xbuf[w] = nullptr; h->xowned[w] = false; }          // set again after mr_set_network
 
@@ -662,6 +667,52 @@ int mr_upload_runoff(mr_handle h, int nSteps, const double *runoff, char *messag
     CU(cudaMemcpyAsync(h->dRunoff, runoff, sizeof(double) * (size_t)nSteps * in_cols(h), cudaMemcpyHostToDevice, h->stream));
     stage_runoff(h, h->dRunoff, nSteps, h->stream);
     CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_set_ingest(mr_handle h, int nForcing, const int *forcingOfHru, double scale, double offset, double fill, char *message) {
+    const char *where = "mr_set_ingest";
+    int e = check_ready(h, 1, where, message); if (e) return e;
+    if (h->nForcing > 0) return fail(message, 1, "mr_set_ingest/the handle remaps its forcing (mr_set_remap); ingest maps forcing HRUs one to one");
+    if (nForcing < 1 || !forcingOfHru) return fail(message, 1, "mr_set_ingest/invalid arguments");
+    const int nH = h->d.nHRU;
+    std::vector<int> src(forcingOfHru, forcingOfHru + nH);
+    for (int i = 0; i < nH; ++i) if (src[i] >= nForcing) return fail(message, 1, "mr_set_ingest/forcing column outside the records");
+    if (!h->dIngestSrc) { e = dev_alloc(h, &h->dIngestSrc, (size_t)nH, where, message, false); if (e) return e;
+                          e = dev_alloc(h, &h->dIngestPtr, (size_t)h->opt.max_batch + 1, where, message, false); if (e) return e; }
+    CU(cudaMemcpy(h->dIngestSrc, src.data(), sizeof(int) * (size_t)nH, cudaMemcpyHostToDevice));
+    // scale_forcing (get_basin_runoff.f90:375-423): -9999 = not given
+    h->ingestRescale = (scale != -9999.0 || offset != -9999.0) ? 1 : 0;
+    h->ingestA = scale == -9999.0 ? 1.0 : scale; h->ingestB = offset == -9999.0 ? 0.0 : offset; h->ingestFill = fill;
+    h->ingestCols = nForcing;
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_ingest_records(mr_handle h, int nSteps, int nRec, const double *records, const int *recPtr, const int *recIdx, const double *recFrac, char *message) {
+    const char *where = "mr_ingest_records";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!h->ingestCols) return fail(message, 1, "mr_ingest_records/mr_set_ingest has not been called");
+    if (nRec < 1 || !records || !recPtr || !recIdx) return fail(message, 1, "mr_ingest_records/invalid arguments");
+    const size_t nIdx = (size_t)recPtr[nSteps];
+    for (int t = 0; t < nSteps; ++t) if (recPtr[t + 1] <= recPtr[t]) return fail(message, 30, "timeMap_sim_forc/a simulation step without forcing record");
+    for (size_t j = 0; j < nIdx; ++j) if (recIdx[j] < 0 || recIdx[j] >= nRec) return fail(message, 30, "timeMap_sim_forc/record index outside the uploaded records");
+    CU(cudaStreamSynchronize(h->stream));
+    const size_t need = (size_t)nRec * h->ingestCols;
+    if (need > h->ingestRecCap) { e = dev_alloc(h, &h->dIngestRec, need, where, message, false); if (e) return e; h->ingestRecCap = need; }   // (the smaller one stays until mr_destroy)
+    if (nIdx > h->ingestIdxCap) { e = dev_alloc(h, &h->dIngestIdx, nIdx, where, message, false); if (e) return e;
+                                  e = dev_alloc(h, &h->dIngestFrac, nIdx, where, message, false); if (e) return e; h->ingestIdxCap = nIdx; }
+    CU(cudaMemcpyAsync(h->dIngestRec, records, sizeof(double) * need, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dIngestPtr, recPtr, sizeof(int) * ((size_t)nSteps + 1), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->dIngestIdx, recIdx, sizeof(int) * nIdx, cudaMemcpyHostToDevice, h->stream));
+    if (recFrac) CU(cudaMemcpyAsync(h->dIngestFrac, recFrac, sizeof(double) * nIdx, cudaMemcpyHostToDevice, h->stream));
+    dim3 grid((h->d.nHRU + 255) / 256, nSteps < 64 ? nSteps : 64);
+    k_ingest<<<grid, 256, 0, h->stream>>>(h->dIngestRec, h->dRunoff, h->dIngestSrc, h->dIngestPtr, h->dIngestIdx, recFrac ? h->dIngestFrac : nullptr,
+                                          h->ingestCols, h->d.nHRU, nSteps, h->ingestRescale, h->ingestA, h->ingestB, h->ingestFill);
+    h->d.runoff = h->dRunoff;
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
     put_msg(message, "");
     return 0;
 }

@@ -144,6 +144,26 @@ class Router:
         assert all(a is None or a.shape == (k, self.nRch) for a in (f, v))
         self._check(self._L.mr_upload_wm(self._h, int(k), _ptr(f, C.c_double), _ptr(v, C.c_double), int(bool(vol_jumpstart)), self._msg))
 
+    def set_ingest(self, n_forcing: int, forcing_of_hru, scale: float = -9999.0, offset: float = -9999.0, fill: float = -9999.0):
+        """Forcing ingest on the device (mr_set_ingest): forcing_of_hru [nHRU] = column of every river-network HRU in the raw
+        forcing records (-1 = none); scale / offset = <scale_factor_runoff> / <offset_value_runoff> (-9999 = not given)."""
+        f = np.ascontiguousarray(forcing_of_hru, dtype=np.int32)
+        assert f.shape == (self.nHRU,)
+        self._check(self._L.mr_set_ingest(self._h, int(n_forcing), _ptr(f, C.c_int), float(scale), float(offset), float(fill), self._msg))
+        self._n_forcing = int(n_forcing)
+
+    def ingest_records(self, records, rec_ptr, rec_idx, rec_frac=None) -> int:
+        """Raw forcing records [nRec, nForcing] -> the runoff rows of K = len(rec_ptr) - 1 steps, resident on the device
+        (mr_ingest_records; time-weighted mean over the records under a step, scale / offset, sort_flux).  Follow with
+        route_resident(K)."""
+        r = np.ascontiguousarray(records, dtype=np.float64)
+        p = np.ascontiguousarray(rec_ptr, dtype=np.int32); i = np.ascontiguousarray(rec_idx, dtype=np.int32)
+        f = None if rec_frac is None else np.ascontiguousarray(rec_frac, dtype=np.float64)
+        assert r.ndim == 2 and r.shape[1] == self._n_forcing and i.size == p[-1] and (f is None or f.size == i.size)
+        self._check(self._L.mr_ingest_records(self._h, int(p.size - 1), int(r.shape[0]), _ptr(r, C.c_double), _ptr(p, C.c_int), _ptr(i, C.c_int),
+                                              _ptr(f, C.c_double), self._msg))
+        return int(p.size - 1)
+
     def set_da(self, qmod_option: int = 1, q_blend_period: int = 10, q_err_trend: int = 1):
         """Data assimilation by direct insertion (<qmodOption>, <qBlendPeriod>, <QerrTrend>; mr_set_da)."""
         self._check(self._L.mr_set_da(self._h, int(qmod_option), int(q_blend_period), int(q_err_trend), self._msg))

@@ -75,3 +75,12 @@ def load_calendar():
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
     return C.CDLL(so)
+
+
+def load_ingest():
+    """Host build of the forcing ingest (mr_ingest.h), see ingest_emul.cpp."""
+    so, src = os.path.join(_HERE, "libingest_emul.so"), os.path.join(_HERE, "ingest_emul.cpp")
+    deps = [src, os.path.join(_CSRC, "mr_ingest.h"), os.path.join(_CSRC, "mr_dev.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    return C.CDLL(so)

@@ -205,3 +205,39 @@ def test_host_routes_gridded_forcing_like_the_oracle(tmp_path, backend):
     qo = Oracle(net, params, opts).run(ro_net)
     np.testing.assert_allclose(out["IRFroutedRunoff"], qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
     np.testing.assert_allclose(out["KWTroutedRunoff"], qo[1].astype(np.float32), rtol=1e-4, atol=1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt,forcing_dt,records,sim_steps", [(3600.0, 3600.0, 12, 12), (10800.0, 3600.0, 36, 12), (7200.0, 10800.0, 8, 12)])
+def test_device_ingest_feeds_routing_like_host_built_rows(dt, forcing_dt, records, sim_steps):
+    """mr_set_ingest / mr_ingest_records (k_ingest): raw forcing records in shuffled forcing-HRU order, with fill values, a
+    negative value, scale and offset -> resident runoff rows -> routing, against the oracle fed the rows the host build of
+    the same source makes (tests/test_ingest_emul.py pins those to the stand-alone host's rows bit for bit)."""
+    from mizuroute_b200.route import Router
+    from oracle.oracle import Oracle
+    from tests.test_ingest_emul import _emul_rows
+    from tests.util import case, rel_err
+    from tests.util_ingest import time_map
+    net, params, opts, ro = case("conus", n=400, seed=4, dt=dt, route_opt="01", steps=records)
+    rng = np.random.default_rng(9)
+    nIn = net.nHRU + 7
+    col = rng.permutation(nIn)[:net.nHRU].astype(np.int32)          # forcing column of every river-network HRU
+    col[5] = -1                                                      # an HRU the forcing does not know
+    rec = rng.lognormal(-11.0, 1.0, (records, nIn))
+    rec[:, col[col >= 0]] = ro[:, col >= 0]
+    rec[1, col[3]] = -2.0; rec[2, col[8]] = -9999.0
+    ptr, idx, frac = time_map(sim_steps, dt, records, forcing_dt)
+    rows = _emul_rows(rec, col, ptr, idx, frac, scale=1.25, offset=1e-10)
+    qo = Oracle(net, params, opts).run(rows)
+    r = Router(net, params, opts, max_batch=8)
+    r.set_ingest(nIn, col, scale=1.25, offset=1e-10)
+    parts = []
+    for s in range(0, sim_steps, 5):
+        e = min(s + 5, sim_steps)
+        j0, j1 = ptr[s], ptr[e]
+        lo, hi = idx[j0:j1].min(), idx[j0:j1].max() + 1             # only the records this batch needs travel
+        K = r.ingest_records(rec[lo:hi], ptr[s:e + 1] - j0, idx[j0:j1] - lo, frac[j0:j1])
+        r.route_resident(K)
+        parts.append(r.download_q(K))
+    qg = np.concatenate(parts, axis=1)
+    assert np.array_equal(qg[0], qo[0]) and np.array_equal(qg[1], qo[1])          # SUM / IRF: bit-identical rows -> bit-identical flow
