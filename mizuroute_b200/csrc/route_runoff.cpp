@@ -1,7 +1,7 @@
 // route_runoff -- stand-alone host of the B200 routing library, the counterpart of the reference's
 // PROGRAM route_runoff (route/build/src/standalone/route_runoff.f90:5-117):
 //
-//     route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]
+//     route_runoff <control file> [--batch N] [--device-ingest] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]
 //
 //   init_model      read_control (read_control.f90:18: lines "<key> value ! comment", '!' comment lines, unknown key =
 //                   error) and the parameter namelist &HSLOPE/&IRF_UH/&KWT (read_param.f90:12)
@@ -328,12 +328,13 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--device-ingest] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]\n"); return 2; }
     const std::string cfile = argv[1];
-    int batch = 64; bool dry = false; std::string dumpForcing, dumpRemap;
+    int batch = 64; bool dry = false, deviceIngest = false; std::string dumpForcing, dumpRemap;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--dry-run")) dry = true;
+        else if (!std::strcmp(argv[i], "--device-ingest")) deviceIngest = true;       // forcing records -> runoff rows on the device (mr_ingest_records)
         else if (!std::strcmp(argv[i], "--dump-forcing") && i + 1 < argc) dumpForcing = argv[++i];
         else if (!std::strcmp(argv[i], "--dump-remap") && i + 1 < argc) dumpRemap = argv[++i];
         else die(2, std::string("unknown argument ") + argv[i]);
@@ -754,6 +755,44 @@ int main(int argc, char **argv) {
                               d03[2].empty() ? nullptr : d03[2].data(), d03[3].empty() ? nullptr : d03[3].data(), msg);
         if (ierr) die(ierr, msg);
         if (qmodOption == 1) { ierr = mr_set_da(h, 1, (int)c.num("qBlendPeriod", 10), (int)c.num("QerrTrend", 1), msg); if (ierr) die(ierr, msg); }
+        // --device-ingest: the runoff records of a batch travel as they are in the file; the time-weighted mean over the records
+        // under a step, <scale_factor_runoff> / <offset_value_runoff> and sort_flux run on the device (mr_ingest_records)
+        std::vector<double> ingRec, ingFrac; std::vector<int> ingPtr, ingIdx;
+        if (deviceIngest) {
+            if (isRemap) die(20, "route_runoff/--device-ingest maps forcing HRUs one to one; not with <is_remap> T");
+            const bool zero = std::fabs(vsRunoff.scale) < 2.3e-308 && (std::fabs(vsRunoff.offset) < 2.3e-308 || vsRunoff.offset == -9999.0);
+            if (zero) deviceIngest = false;                              // the runoff is switched off: rows of zeros, nothing to ingest
+        }
+        if (deviceIngest) {
+            std::vector<int> colOfHru(nHRU, -1);
+            for (size_t i = 0; i < nForcing; ++i) if (ix[i] >= 0) colOfHru[ix[i]] = (int)i;              // sort_flux inverted (the last one wins, as there)
+            const auto w0 = where[time_map(0).rec[0]];
+            if (!rd[w0.first]) rd[w0.first] = new nc3::Reader(files[w0.first].path);
+            double fv; if (rd[w0.first]->attr_value(rd[w0.first]->var(vsRunoff.name), "_FillValue", fv)) fillv = fv;
+            ierr = mr_set_ingest(h, (int)nForcing, colOfHru.data(), vsRunoff.scale, vsRunoff.offset, fillv, msg); if (ierr) die(ierr, msg);
+        }
+        auto ingest_batch = [&](size_t s, int nb) {
+            ingPtr.assign(1, 0); ingIdx.clear(); ingFrac.clear();
+            size_t lo = (size_t)-1, hi = 0;
+            for (int k = 0; k < nb; ++k) {
+                const TimeMap tm = time_map(s + k);
+                for (size_t j = 0; j < tm.rec.size(); ++j) {
+                    ingIdx.push_back((int)tm.rec[j]); ingFrac.push_back(tm.frac.empty() ? 1.0 : tm.frac[j]);
+                    lo = std::min(lo, tm.rec[j]); hi = std::max(hi, tm.rec[j]);
+                }
+                ingPtr.push_back((int)ingIdx.size());
+            }
+            for (auto &v : ingIdx) v -= (int)lo;
+            ingRec.resize((hi - lo + 1) * nForcing);
+            for (size_t r = lo; r <= hi; ++r) {
+                const auto wr = where[r];
+                if (!rd[wr.first]) rd[wr.first] = new nc3::Reader(files[wr.first].path);
+                rd[wr.first]->read(rd[wr.first]->var(vsRunoff.name), rec, wr.second, 1);
+                if (rec.size() != nForcing) die(20, "read_runoff/forcing variable " + vsRunoff.name + " is not dimensioned like the runoff");
+                std::copy(rec.begin(), rec.end(), ingRec.begin() + (r - lo) * nForcing);
+            }
+            int e = mr_ingest_records(h, nb, (int)(hi - lo + 1), ingRec.data(), ingPtr.data(), ingIdx.data(), ingFrac.data(), msg); if (e) die(e, msg);
+        };
 
         if (isRemap) { ierr = mr_set_remap(h, (int)nForcing, (int)mapHruIx.size(), mapHruIx.data(), mapNumQ.data(), mapQIx.data(), mapWgt.data(), msg); if (ierr) die(ierr, msg); }
 
@@ -837,7 +876,8 @@ int main(int argc, char **argv) {
             if (nextRestart < restartPlan.size()) nb = (int)std::min<size_t>(nb, restartPlan[nextRestart].first + 1 - s);      // a batch ends where a restart file is due
             if (anyStep) nb = 1;
             else if (anyVol) nb = std::min(nb, nAgg - nAcc);                   // the batch ends where the output period ends
-            for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
+            if (deviceIngest && !wantBas) ingest_batch(s, nb);
+            else for (int k = 0; k < nb; ++k) load_step(s + k, &ro[(size_t)k * inCols]);
             if (lakeForcing) {
                 for (int k = 0; k < nb; ++k) { load_var(vsEvapo, s + k, &evRows[(size_t)k * nHRU], nHRU, false); load_var(vsPrecip, s + k, &prRows[(size_t)k * nHRU], nHRU, false); }
                 ierr = mr_upload_lake_forcing(h, nb, evRows.data(), prRows.data(), msg); if (ierr) die(ierr, msg);
@@ -854,7 +894,13 @@ int main(int argc, char **argv) {
                 for (int k = 0; k < nb; ++k) obsHas[k] = load_obs(tStart + (double)(s + k) * o.dt, &obsRows[(size_t)k * nRch]) ? 1 : 0;
                 ierr = mr_upload_obs(h, nb, obsHas.data(), obsRows.data(), msg); if (ierr) die(ierr, msg);
             }
-            ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
+            if (deviceIngest) {
+                if (wantBas) ingest_batch(s, nb);                              // <basRunoff> wants the rows on the host as well
+                ierr = mr_route_resident(h, nb, T0, msg); if (ierr) die(ierr, msg);
+                ierr = mr_download_q(h, nb, q.data(), msg); if (ierr) die(ierr, msg);
+            } else {
+                ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
+            }
             if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             if (anyStep) {                                                     // nb == 1: REACH_INFLOW / BASIN_QI of this step
                 for (int r = 0; r < o.n_routes; ++r) if (wantInf[r]) { ierr = mr_get_flux(h, o.route_methods[r], MR_REACH_INFLOW, &stepX[(size_t)r * nRch], msg); if (ierr) die(ierr, msg); }

@@ -21,6 +21,8 @@ struct mr_handle_s {
     int hasStart, sy, sm, sd, noleap; double ssec;
     /* water management of the next batch (mr_upload_wm) */
     double *wmF, *wmV; int wmSteps, wmJump;
+    /* forcing ingest (mr_set_ingest / mr_ingest_records): rows left resident for mr_route_resident, its REACH_Q for mr_download_q */
+    int *ingSrc; int ingCols, ingRescale; double ingA, ingB, ingFill; double *rows; int rowSteps; double *qLast;
     /* gauge observations of the next batch (mr_upload_obs) */
     double *obs; int *obsHas; int obsSteps, qmod;
     /* lake forcing of the next batch (mr_upload_lake_forcing) */
@@ -98,6 +100,52 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     }
     free(row);
     h->epSteps = 0; h->wmSteps = 0; h->obsSteps = 0;
+    say(message, "");
+    return 0;
+}
+
+int mr_set_ingest(mr_handle h, int nForcing, const int *forcingOfHru, double scale, double offset, double fill, char *message)
+{
+    free(h->ingSrc); h->ingSrc = (int *)malloc(sizeof(int) * (size_t)(h->nHRU + 1)); memcpy(h->ingSrc, forcingOfHru, sizeof(int) * (size_t)h->nHRU);
+    h->ingCols = nForcing; h->ingRescale = (scale != -9999.0 || offset != -9999.0);
+    h->ingA = scale == -9999.0 ? 1.0 : scale; h->ingB = offset == -9999.0 ? 0.0 : offset; h->ingFill = fill;
+    say(message, "");
+    return 0;
+}
+
+/* plain restatement of read_1D_forcing's weighted mean + scale_forcing + sort_flux (the device code is mr_ingest.h) */
+int mr_ingest_records(mr_handle h, int nSteps, int nRec, const double *records, const int *recPtr, const int *recIdx, const double *recFrac, char *message)
+{
+    int t, i, j; (void)nRec;
+    free(h->rows); h->rows = (double *)malloc(sizeof(double) * ((size_t)nSteps * (size_t)h->nHRU + 1)); h->rowSteps = nSteps;
+    for (t = 0; t < nSteps; t++) for (i = 0; i < h->nHRU; i++) {
+        const int src = h->ingSrc[i]; double v = 0.0;
+        if (src >= 0) {
+            if (!recFrac) v = records[(size_t)recIdx[recPtr[t]] * h->ingCols + src];
+            else {
+                double wsum = 0.0, wtot = 0.0;
+                for (j = recPtr[t]; j < recPtr[t + 1]; j++) { const double x = records[(size_t)recIdx[j] * h->ingCols + src]; if (x != h->ingFill) { wsum += x * recFrac[j]; wtot += recFrac[j]; } }
+                v = wtot == 0.0 ? h->ingFill : (wtot < 1.0 ? wsum / wtot : wsum);
+            }
+            if (h->ingRescale && v != h->ingFill && v != -9999.0) v = h->ingA * v + h->ingB;
+            if (v == h->ingFill || v < 0.0) v = 0.0;
+        }
+        h->rows[(size_t)t * h->nHRU + i] = v;
+    }
+    say(message, "");
+    return 0;
+}
+
+int mr_route_resident(mr_handle h, int nSteps, double T0, char *message)
+{
+    if (!h->rows || h->rowSteps != nSteps) { say(message, "mr_route_resident/no resident rows for that many steps"); return 1; }
+    free(h->qLast); h->qLast = (double *)malloc(sizeof(double) * ((size_t)h->o.n_routes * (size_t)nSteps * (size_t)h->nRch + 1));
+    return mr_step_batch(h, nSteps, T0, h->rows, h->qLast, message);
+}
+
+int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message)
+{
+    memcpy(q_out, h->qLast, sizeof(double) * (size_t)h->o.n_routes * (size_t)nSteps * (size_t)h->nRch);
     say(message, "");
     return 0;
 }

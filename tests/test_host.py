@@ -601,3 +601,25 @@ def test_history_volume_inflow_and_instantaneous_runoff(tmp_path, backend, freq,
     want_b = np.stack([ro[lo:hi].mean(0) for lo, hi in bounds])                  # <basRunoff>: the HRU runoff as read, period mean
     np.testing.assert_allclose(out["basRunoff"], want_b, rtol=3e-6, atol=1e-30)
     assert np.array_equal(out["basinID"], net.hruId)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("dt,forcing_dt,records,sim_steps,bas", [(3600.0, 3600.0, 12, 12, "F"), (10800.0, 3600.0, 36, 12, "T"), (7200.0, 10800.0, 8, 12, "F")])
+def test_device_ingest_gives_the_same_history_as_host_built_rows(tmp_path, backend, dt, forcing_dt, records, sim_steps, bas):
+    """--device-ingest: the runoff records travel as they are and mr_ingest_records builds the rows (time-weighted mean, scale,
+    offset, sort_flux of shuffled forcing HRUs) -- the history file equals the one of the default path byte for byte."""
+    net, params, opts, ro = case("conus", n=300, seed=4, dt=dt, route_opt="01", steps=records)
+    ro = ro.copy(); ro[1, 3] = -2.0; ro[2, 5] = -9999.0
+    same = forcing_dt == dt
+    keys = {"scale_factor_runoff": "1.25", "offset_value_runoff": "1.e-10", "basRunoff": bas}
+    outs = []
+    for tag, flags in (("host", []), ("dev", ["--device-ingest"])):
+        ctl = casefiles.write_case(os.path.join(str(tmp_path), tag), net, params, opts, ro, case_name="ing", forcing_dt=None if same else forcing_dt,
+                                   sim_steps=None if same else sim_steps, shuffle_hru_seed=7 if same else None, extra_keys=keys)
+        r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"] + flags, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"]))
+    assert set(outs[0]) == set(outs[1])
+    for v in outs[0]:
+        assert np.array_equal(outs[0][v], outs[1][v]), v
+    assert ("basRunoff" in outs[0]) == (bas == "T")
