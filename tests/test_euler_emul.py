@@ -19,6 +19,9 @@ CASES = [
     dict(kind="random", n=50, seed=7, dt=900.0, steps=30, hw_drain_point=1),
     dict(kind="binary", n=127, seed=2, dt=10800.0, steps=20, floodplain=True),    # over-bank branch
     dict(kind="random", n=40, seed=8, dt=3600.0, steps=12, min_length_route=1500.0),   # pass-through reaches
+    dict(kind="tiny:one_reach", dt=3600.0, steps=20), dict(kind="tiny:isolated_reaches", dt=86400.0, steps=10),     # degenerate networks
+    dict(kind="tiny:chain_of_two", dt=3600.0, steps=20), dict(kind="tiny:middle_reach_without_hru", dt=86400.0, steps=12),
+    dict(kind="tiny:star_of_five", dt=900.0, steps=20),
 ]
 
 

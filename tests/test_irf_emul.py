@@ -19,6 +19,9 @@ CASES = [
     dict(kind="binary", n=255, seed=2, dt=900.0, steps=30, hw_drain_point=1),
     dict(kind="random", n=60, seed=8, dt=3600.0, steps=12, min_length_route=1500.0),
     dict(kind="conus", n=900, seed=4, dt=86400.0, steps=14, lakes=9),
+    dict(kind="tiny:one_reach", dt=3600.0, steps=20), dict(kind="tiny:isolated_reaches", dt=86400.0, steps=10),
+    dict(kind="tiny:chain_of_two", dt=3600.0, steps=20), dict(kind="tiny:middle_reach_without_hru", dt=3600.0, steps=20),
+    dict(kind="tiny:star_of_five", dt=900.0, steps=20),
 ]
 
 

@@ -317,3 +317,17 @@ def test_direct_insertion_rejects_unknown_options():
     o = orc.Oracle(net, params, opts); o.set_da(2, 5, 1)
     with pytest.raises(orc.OracleError, match="qmodOption invalid"):
         o.step(ro[0])
+
+
+from tests.util import tiny_case, tiny_networks  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(tiny_networks()))
+@pytest.mark.parametrize("dt", [3600.0, 86400.0])
+def test_degenerate_networks(name, dt):
+    """One reach, isolated reaches, a chain of two, a reach without HRU, a star: all six methods, oracle = twin."""
+    net, params, opts, ro = tiny_case(tiny_networks()[name], dt=dt)
+    o, t, q, qt = _both(net, params, opts, ro)
+    for i, m in enumerate(t.methods):
+        assert rel_err(q[i], np.array(qt[m]), floor=1e-12) <= 1e-12, m
+    assert np.isfinite(q).all() and (q >= 0).all()

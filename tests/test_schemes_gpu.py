@@ -283,3 +283,15 @@ def test_direct_insertion(trend):
             assert rel_err(r.flux(capi.QERROR, int(c)), o.get(orc.F_QERROR, int(c)), floor=1e-6) <= 1e-5, c
     assert np.array_equal(r.get_state(capi.ST_DA_QELAPSED), o.qelapsed())
     assert np.array_equal(r.get_state(capi.ST_DA_QOBS), o.get(orc.F_QOBS))
+
+
+@pytest.mark.parametrize("batch", [1, 7])
+@pytest.mark.parametrize("name", ["one_reach", "isolated_reaches", "chain_of_two", "middle_reach_without_hru", "star_of_five"])
+def test_degenerate_networks_all_six_methods(name, batch):
+    """One reach (a single stage that holds only a headwater: no wavefront kernel is launched at all), isolated reaches, a chain
+    of two, a reach without HRU, a star -- the sizes at which grids, stage ranges and batch tails degenerate."""
+    net, params, opts, ro = case("tiny:" + name, dt=3600.0, route_opt="012345", steps=20)
+    o, r, qo, qg = _both(net, params, opts, ro, batch)
+    assert np.array_equal(qg[0], qo[0]) and np.array_equal(qg[1], qo[1])          # SUM, IRF: bit-identical
+    for i in range(2, 6):
+        assert rel_err(qg[i], qo[i], floor=1e-12) <= EULER_RTOL, opts.route_opt[i]

@@ -15,6 +15,11 @@ def rel_err(a, b, floor=1e-300):
 
 
 def case(kind="random", n=60, seed=5, dt=3600.0, route_opt="012", steps=24, zero_area_frac=0.0, lakes=0, **kw):
+    if kind.startswith("tiny:"):                                  # the degenerate networks of tiny_networks()
+        net, params, opts, ro = tiny_case(tiny_networks()[kind[5:]], dt=dt, route_opt=route_opt, steps=steps, seed=seed)
+        for k, v in kw.items():
+            setattr(opts, k, v)
+        return net, params, opts, ro
     if kind == "random":
         net = synth.random_tree(n, seed=seed, zero_area_frac=zero_area_frac)
     elif kind == "binary":
@@ -68,3 +73,32 @@ def gauge_series(net, K, seed=3, n_gauge=40, record_frac=0.5, scale=(0.3, 2.5), 
         v[rng.random(gauges.size) < 0.05] = -1.0            # flagged bad
         obs[t, gauges] = v
     return obs, has, gauges
+
+
+def tiny_networks():
+    """Degenerate river networks by hand: one reach; isolated reaches only (every reach an outlet and a headwater); a chain of
+    two; a reach without any HRU in a chain of three; a five-arm star."""
+    from mizuroute_b200.network import RiverNetwork
+
+    def net(down, hru_seg, seed):
+        rng = np.random.default_rng(seed)
+        n = len(down)
+        return RiverNetwork(segId=np.arange(101, 101 + n), downSegId=np.array([101 + d if d >= 0 else -1 for d in down]),
+                            length=rng.uniform(800.0, 6000.0, n), slope=rng.uniform(1e-3, 2e-2, n),
+                            hruId=np.arange(1001, 1001 + len(hru_seg)), hruSegId=np.array([101 + s for s in hru_seg]),
+                            area=rng.uniform(2e6, 3e7, len(hru_seg)))
+    return {
+        "one_reach": net([-1], [0], 1),
+        "isolated_reaches": net([-1, -1, -1, -1], [0, 1, 2, 3], 2),
+        "chain_of_two": net([1, -1], [0, 1], 3),
+        "middle_reach_without_hru": net([1, 2, -1], [0, 2], 4),
+        "star_of_five": net([5, 5, 5, 5, 5, -1], [0, 1, 2, 3, 4, 5], 5),
+    }
+
+
+def tiny_case(net, dt=3600.0, route_opt="012345", steps=30, seed=0):
+    rng = np.random.default_rng(100 + seed)
+    opts = RouteOptions(dt=dt, route_opt=route_opt, runoffMin=1e-15)
+    season = 1.0 + 0.5 * np.sin(np.arange(steps) / 5.0)
+    ro = rng.lognormal(np.log(2e-5), 1.0, (steps, net.nHRU)) * season[:, None]
+    return net, RouteParams(), opts, ro
