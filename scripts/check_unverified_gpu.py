@@ -24,8 +24,23 @@ def main():
         print(line, flush=True)
         log.write(line + "\n"); log.flush()
 
+    from tests import test_golden as G
+    from tests import test_remap as R
     from tests import test_schemes_gpu as T
     plan = [
+        # written after the last GPU second of round 1
+        ("option_golden[da]", G.test_cuda_reproduces_option_golden, ("conus300_hourly_0145_da",)),
+        ("option_golden[wm]", G.test_cuda_reproduces_option_golden, ("conus300_hourly_135_wm",)),
+        ("option_golden[345]", G.test_cuda_reproduces_option_golden, ("tree60_hourly_345",)),
+        ("device_ingest[1:1]", R.test_device_ingest_feeds_routing_like_host_built_rows, (3600.0, 3600.0, 12, 12)),
+        ("device_ingest[3 records per step]", R.test_device_ingest_feeds_routing_like_host_built_rows, (10800.0, 3600.0, 36, 12)),
+        ("device_ingest[ragged]", R.test_device_ingest_feeds_routing_like_host_built_rows, (7200.0, 10800.0, 8, 12)),
+        ("tiny[one_reach-1]", T.test_degenerate_networks_all_six_methods, ("one_reach", 1)),
+        ("tiny[isolated-7]", T.test_degenerate_networks_all_six_methods, ("isolated_reaches", 7)),
+        ("tiny[chain-1]", T.test_degenerate_networks_all_six_methods, ("chain_of_two", 1)),
+        ("tiny[no_hru-7]", T.test_degenerate_networks_all_six_methods, ("middle_reach_without_hru", 7)),
+        ("tiny[star-7]", T.test_degenerate_networks_all_six_methods, ("star_of_five", 7)),
+        # passed on a B200 at the end of round 1 (profiles/r1_unverified_gpu_check.jsonl)
         ("direct_insertion[1]", T.test_direct_insertion, (1,)),
         ("water_management[1-0]", T.test_water_management, ("1", 0)),
         ("water_management[134-9]", T.test_water_management, ("134", 9)),
