@@ -30,15 +30,15 @@ NOT_YET_RUN_ON_HARDWARE = (
     "test_host_run_matches_oracle[345", "test_host_routes_gridded_forcing_like_the_oracle",
     "test_decomposed_euler_schemes_equal_single_domain", "test_host_reads_the_water_management_file",
     "test_host_reads_the_gauge_files_for_direct_insertion", "test_restart_under_data_assimilation_carries_the_discharge_error",
-    "test_history_volume_inflow_and_instantaneous_runoff", "test_cuda_reproduces_option_golden",
-    "test_device_ingest_feeds_routing_like_host_built_rows", "test_device_ingest_gives_the_same_history_as_host_built_rows",
-    "test_degenerate_networks_all_six_methods",
+    "test_history_volume_inflow_and_instantaneous_runoff",
+    "test_device_ingest_gives_the_same_history_as_host_built_rows",
 )
 # ran on a B200 only through scripts/check_unverified_gpu.py (profiles/r1_unverified_gpu_check.jsonl), not under pytest: collected
 # after the verified tests and before the ones above
 RUN_ON_HARDWARE_OUTSIDE_PYTEST = (
     "test_schemes_gpu.py::test_lake_evaporation", "test_schemes_gpu.py::test_hype", "test_schemes_gpu.py::test_hanasaki",
     "test_schemes_gpu.py::test_water_management", "test_schemes_gpu.py::test_direct_insertion",
+    "test_cuda_reproduces_option_golden", "test_device_ingest_feeds_routing_like_host_built_rows", "test_degenerate_networks_all_six_methods",
 )
 
 
