@@ -343,6 +343,10 @@ int main(int argc, char **argv) {
     try {
         // ---- init_model: control file + parameter namelist
         const Control c = read_control(cfile);
+        // options of the reference this host accepts but does not act on: say so when they ask for something non-default
+        if (c.flag("tracer", false)) std::fprintf(stderr, "route_runoff: <tracer> T is ignored (solute transport is not built)\n");
+        if (c.flag("outputAtGage", false)) std::fprintf(stderr, "route_runoff: <outputAtGage> T is ignored (history holds every reach)\n");
+        if (c.num("seg_outlet", -9999.0) != -9999.0) std::fprintf(stderr, "route_runoff: <seg_outlet> is ignored (the whole network of <fname_ntopOld> is routed)\n");
         const std::string ancil = c.need("ancil_dir"), indir = c.need("input_dir"), outdir = c.need("output_dir");
         mr_options o{};
         o.dt = c.num("dt_qsim", -1.0);
