@@ -345,7 +345,7 @@ int main(int argc, char **argv) {
         const Control c = read_control(cfile);
         // options of the reference this host accepts but does not act on: say so when they ask for something non-default
         if (c.flag("tracer", false)) std::fprintf(stderr, "route_runoff: <tracer> T is ignored (solute transport is not built)\n");
-        if (c.flag("outputAtGage", false)) std::fprintf(stderr, "route_runoff: <outputAtGage> T is ignored (history holds every reach)\n");
+        if (c.flag("outputAtGage", false) && c.str("gageMetaFile", "").empty()) std::fprintf(stderr, "route_runoff: <outputAtGage> T without <gageMetaFile> is ignored (history holds every reach)\n");
         if (c.num("seg_outlet", -9999.0) != -9999.0) std::fprintf(stderr, "route_runoff: <seg_outlet> is ignored (the whole network of <fname_ntopOld> is routed)\n");
         const std::string ancil = c.need("ancil_dir"), indir = c.need("input_dir"), outdir = c.need("output_dir");
         mr_options o{};
@@ -656,6 +656,26 @@ int main(int argc, char **argv) {
         // gage_id, reach_id: gageMeta_data.f90:58-68) and the gauge netCDF <fname_gageObs> ([time, site] flow, site names as a
         // character variable: obs_data.f90:272-516), both in <ancil_dir>; a step sees the record whose time equals the start of
         // the step (gage_obs_data%time_ix(simDatetime(1)), main_route.f90:128); without the file the option is switched off
+        // gauge metadata csv: (gage_id, reach_id) rows in file order (gageMeta_data.f90:58-68)
+        auto read_gage_meta = [&]() {
+            std::vector<std::pair<std::string, int>> rows;
+            std::ifstream csv(join_path(ancil, c.need("gageMetaFile")));
+            if (!csv) die(20, "read_gage_meta/cannot open " + join_path(ancil, c.need("gageMetaFile")));
+            std::string line; int cg = -1, cr = -1;
+            auto cells = [](const std::string &ln) { std::vector<std::string> v; std::stringstream ss(ln); std::string x; while (std::getline(ss, x, ',')) v.push_back(trim(x)); return v; };
+            if (std::getline(csv, line)) { const auto hd = cells(line); for (size_t i = 0; i < hd.size(); ++i) { if (hd[i] == "gage_id") cg = (int)i; if (hd[i] == "reach_id") cr = (int)i; } }
+            if (cg < 0 || cr < 0) die(20, "read_gage_meta/the csv needs the columns gage_id and reach_id");
+            while (std::getline(csv, line)) { const auto v = cells(line); if ((int)v.size() > std::max(cg, cr) && !v[cg].empty()) rows.push_back({v[cg], std::atoi(v[cr].c_str())}); }
+            return rows; };
+        // <outputAtGage> T: the history files hold the gauged reaches only, in the order of the csv (reach_subset,
+        // process_gage_meta.f90:39-86; historyFile.f90:186-199)
+        std::vector<int> gageIdx;
+        const bool atGage = c.flag("outputAtGage", false) && !c.str("gageMetaFile", "").empty();
+        if (atGage) {
+            std::vector<std::pair<int, int>> tab(nRch); for (size_t i = 0; i < nRch; ++i) tab[i] = {segId[i], (int)i}; std::sort(tab.begin(), tab.end());
+            for (const auto &row : read_gage_meta()) { auto it = std::lower_bound(tab.begin(), tab.end(), std::make_pair(row.second, -1)); if (it != tab.end() && it->first == row.second) gageIdx.push_back(it->second); }
+            if (gageIdx.empty()) die(20, "reach_subset/<outputAtGage> T but no gauge of <gageMetaFile> lies on the river network");
+        }
         int qmodOption = (int)c.num("qmodOption", 0);
         std::unique_ptr<nc3::Reader> obsFile;
         std::vector<int> obsIx; std::vector<double> obsTime, obsRec; double obsFill = -9999.0; const nc3::Var *obsVar = nullptr;
@@ -667,15 +687,7 @@ int main(int argc, char **argv) {
             else {
                 std::fclose(probe);
                 std::map<std::string, int> reachOfGage;                      // gage_id -> reach_id
-                {
-                    std::ifstream csv(join_path(ancil, c.need("gageMetaFile")));
-                    if (!csv) die(20, "read_gage_meta/cannot open " + join_path(ancil, c.need("gageMetaFile")));
-                    std::string line; int cg = -1, cr = -1;
-                    auto cells = [](const std::string &ln) { std::vector<std::string> v; std::stringstream ss(ln); std::string x; while (std::getline(ss, x, ',')) v.push_back(trim(x)); return v; };
-                    if (std::getline(csv, line)) { const auto hd = cells(line); for (size_t i = 0; i < hd.size(); ++i) { if (hd[i] == "gage_id") cg = (int)i; if (hd[i] == "reach_id") cr = (int)i; } }
-                    if (cg < 0 || cr < 0) die(20, "read_gage_meta/the csv needs the columns gage_id and reach_id");
-                    while (std::getline(csv, line)) { const auto v = cells(line); if ((int)v.size() > std::max(cg, cr) && !v[cg].empty()) reachOfGage[v[cg]] = std::atoi(v[cr].c_str()); }
-                }
+                for (const auto &row : read_gage_meta()) reachOfGage[row.first] = row.second;
                 obsFile.reset(new nc3::Reader(obsPath));
                 const nc3::Var &tv = obsFile->var(c.need("vname_gageTime"));
                 double scale, epoch; parse_time_units(obsFile->attr_text(tv, "units"), noleap, scale, epoch);
@@ -830,7 +842,7 @@ int main(int argc, char **argv) {
         auto open_history = [&](const std::string &path) {
             if (w) w->close();
             w.reset(new nc3::Writer(path));
-            const int dTime = w->def_dim("time", 0), dSeg = w->def_dim("seg", nRch);
+            const int dTime = w->def_dim("time", 0), dSeg = w->def_dim("seg", atGage ? gageIdx.size() : nRch);
             vTime = w->def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
             const int vId = w->def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
             int dHru = -1, vHid = -1;
@@ -847,7 +859,8 @@ int main(int argc, char **argv) {
             }
             w->global_attr("title", "mizuRoute routing (mizuroute-b200)");
             w->end_def();
-            w->put_int(vId, segId.data());
+            if (atGage) { std::vector<int> ids(gageIdx.size()); for (size_t i = 0; i < ids.size(); ++i) ids[i] = segId[gageIdx[i]]; w->put_int(vId, ids.data()); }
+            else w->put_int(vId, segId.data());
             if (vHid >= 0) w->put_int(vHid, hruId.data());
         };
 
@@ -859,10 +872,15 @@ int main(int argc, char **argv) {
         std::vector<double> qd(wantDlay ? (size_t)batch * nRch : 0), acc((size_t)(o.n_routes + 1) * nRch, 0.0);
         std::vector<double> accB(wantBas ? nHRU : 0, 0.0);
         std::vector<double> stepX(anyStep ? (size_t)(o.n_routes + 1) * nRch : 0), accX(stepX.size(), 0.0), volNow(anyVol ? nRch : 0);
+        std::vector<double> gageBuf(gageIdx.size());
+        auto put_seg = [&](int var, size_t rec, const double *data) {      // a reach-dimensioned record, all reaches or the gauged ones
+            if (!atGage) { w->put_record(var, rec, data); return; }
+            for (size_t i = 0; i < gageIdx.size(); ++i) gageBuf[i] = data[gageIdx[i]];
+            w->put_record(var, rec, gageBuf.data()); };
         auto put_volumes = [&](size_t rec) {                       // REACH_VOL(1) as the last step of the call left it
             for (int r = 0; r < o.n_routes; ++r) if (vVol[r] >= 0) {
                 int e = mr_get_flux(h, o.route_methods[r], MR_REACH_VOL1, volNow.data(), msg); if (e) die(e, msg);
-                w->put_record(vVol[r], rec, volNow.data());
+                put_seg(vVol[r], rec, volNow.data());
             }
         };
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
@@ -915,10 +933,10 @@ int main(int argc, char **argv) {
                 if (fileNo < plan.size() && plan[fileNo].first == s + k) { open_history(plan[fileNo++].path); recOut = 0; }     // main_new_file
                 if (nAgg == 1) {
                     w->put_record(vTime, recOut, &tsec);
-                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &q[((size_t)r * nb + k) * nRch]);
-                    if (vDlay >= 0) w->put_record(vDlay, recOut, &qd[(size_t)k * nRch]);
-                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &stepX[(size_t)r * nRch]);
-                    if (vInst >= 0) w->put_record(vInst, recOut, &stepX[(size_t)o.n_routes * nRch]);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) put_seg(vQ[r], recOut, &q[((size_t)r * nb + k) * nRch]);
+                    if (vDlay >= 0) put_seg(vDlay, recOut, &qd[(size_t)k * nRch]);
+                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) put_seg(vInf[r], recOut, &stepX[(size_t)r * nRch]);
+                    if (vInst >= 0) put_seg(vInst, recOut, &stepX[(size_t)o.n_routes * nRch]);
                     if (anyVol) put_volumes(recOut);
                     if (vBas >= 0) w->put_record(vBas, recOut, &ro[(size_t)k * inCols]);
                     ++recOut;
@@ -933,11 +951,11 @@ int main(int argc, char **argv) {
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
                     for (auto &v : acc) v /= (double)nAcc;
                     w->put_record(vTime, recOut, &tAcc);
-                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) w->put_record(vQ[r], recOut, &acc[(size_t)r * nRch]);
-                    if (vDlay >= 0) w->put_record(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
+                    for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) put_seg(vQ[r], recOut, &acc[(size_t)r * nRch]);
+                    if (vDlay >= 0) put_seg(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
                     for (auto &v : accX) v /= (double)nAcc;
-                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) w->put_record(vInf[r], recOut, &accX[(size_t)r * nRch]);
-                    if (vInst >= 0) w->put_record(vInst, recOut, &accX[(size_t)o.n_routes * nRch]);
+                    for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) put_seg(vInf[r], recOut, &accX[(size_t)r * nRch]);
+                    if (vInst >= 0) put_seg(vInst, recOut, &accX[(size_t)o.n_routes * nRch]);
                     if (anyVol) put_volumes(recOut);
                     if (vBas >= 0) { for (auto &v : accB) v /= (double)nAcc; w->put_record(vBas, recOut, accB.data()); }
                     ++recOut; nAcc = 0;

@@ -623,3 +623,29 @@ def test_device_ingest_gives_the_same_history_as_host_built_rows(tmp_path, backe
     for v in outs[0]:
         assert np.array_equal(outs[0][v], outs[1][v]), v
     assert ("basRunoff" in outs[0]) == (bas == "T")
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_history_at_gauges_only(tmp_path, backend):
+    """<outputAtGage> T with <gageMetaFile>: the history files hold the gauged reaches only, in the order of the csv (gauges
+    outside the network dropped) -- the columns of the full output."""
+    net, params, opts, ro = case("random", n=70, seed=3, dt=3600.0, route_opt="01", steps=12)
+    rng = np.random.default_rng(1)
+    rch = rng.choice(net.nRch, 6, replace=False)
+    gage_ids = ["Q%02d" % i for i in range(7)]
+    csv_rch = list(net.segId[rch[:3]]) + [int(net.segId.max()) + 5] + list(net.segId[rch[3:]])      # the fourth gauge is not on the network
+    d = str(tmp_path)
+    full = casefiles.write_case(os.path.join(d, "full"), net, params, opts, ro, case_name="g", extra_keys={"IRFvolume": "T"})
+    # the gauge files are written by the `gauges` option; qmodOption is switched back off so that only the output changes
+    sub = casefiles.write_case(os.path.join(d, "sub"), net, params, opts, ro, case_name="g",
+                               gauges=(gage_ids, gage_ids, csv_rch, [0.0], np.full((1, 7), np.nan), 5, 1),
+                               extra_keys={"IRFvolume": "T", "outputAtGage": "T", "qmodOption": "0"})
+    outs = []
+    for ctl in (full, sub):
+        r = subprocess.run([_routing_host(backend), ctl, "--batch", "5"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"]))
+    assert np.array_equal(outs[1]["reachID"], net.segId[rch])
+    for v in ("sumUpstreamRunoff", "IRFroutedRunoff", "dlayRunoff", "IRFvolume"):
+        assert np.array_equal(outs[1][v], outs[0][v][:, rch]), v
+    assert np.array_equal(outs[1]["basRunoff"], outs[0]["basRunoff"])                  # HRU-dimensioned output is not subset
