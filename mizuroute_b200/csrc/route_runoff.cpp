@@ -836,7 +836,8 @@ int main(int argc, char **argv) {
         const bool wantBas = c.flag("basRunoff", true) && !isRemap;
         int vBas = -1;
         std::vector<int> vVol(o.n_routes, -1), vInf(o.n_routes, -1); int vInst = -1;
-        int vTime = -1, vDlay = -1;
+        int vTime = -1, vDlay = -1, vTb = -1;
+        const double stampOffset = c.num("histTimeStamp_offset", 0.0);          // <histTimeStamp_offset> [s] from the start of the period (write_time, historyFile.f90:367)
         std::vector<int> vQ(o.n_routes, -1);
         std::unique_ptr<nc3::Writer> w;
         auto open_history = [&](const std::string &path) {
@@ -844,6 +845,8 @@ int main(int argc, char **argv) {
             w.reset(new nc3::Writer(path));
             const int dTime = w->def_dim("time", 0), dSeg = w->def_dim("seg", atGage ? gageIdx.size() : nRch);
             vTime = w->def_var("time", nc3::NC_DOUBLE, {dTime}, {{"units", "seconds since " + c.need("sim_start")}, {"calendar", noleap ? "noleap" : "standard"}});
+            const int dTb = w->def_dim("tbound", 2);                          // time_bounds: end points of the output period (historyFile.f90:146-153)
+            vTb = w->def_var("time_bounds", nc3::NC_DOUBLE, {dTime, dTb}, {{"units", "seconds since " + c.need("sim_start")}, {"long_name", "time interval endpoints"}});
             const int vId = w->def_var("reachID", nc3::NC_INT, {dSeg}, {{"long_name", "reach ID"}});
             int dHru = -1, vHid = -1;
             if (wantBas) { dHru = w->def_dim("hru", nHRU); vHid = w->def_var("basinID", nc3::NC_INT, {dHru}, {{"long_name", "basin ID"}});
@@ -932,7 +935,7 @@ int main(int argc, char **argv) {
                 const double tsec = (tStart - tStartAsked) + (double)(s + k) * o.dt;    // seconds since <sim_start>
                 if (fileNo < plan.size() && plan[fileNo].first == s + k) { open_history(plan[fileNo++].path); recOut = 0; }     // main_new_file
                 if (nAgg == 1) {
-                    w->put_record(vTime, recOut, &tsec);
+                    { const double ts = tsec + stampOffset, tb[2] = {tsec, tsec + o.dt}; w->put_record(vTime, recOut, &ts); w->put_record(vTb, recOut, tb); }
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) put_seg(vQ[r], recOut, &q[((size_t)r * nb + k) * nRch]);
                     if (vDlay >= 0) put_seg(vDlay, recOut, &qd[(size_t)k * nRch]);
                     for (int r = 0; r < o.n_routes; ++r) if (vInf[r] >= 0) put_seg(vInf[r], recOut, &stepX[(size_t)r * nRch]);
@@ -950,7 +953,7 @@ int main(int argc, char **argv) {
                 if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
                     for (auto &v : acc) v /= (double)nAcc;
-                    w->put_record(vTime, recOut, &tAcc);
+                    { const double ts = tAcc + stampOffset, tb[2] = {tAcc, tsec + o.dt}; w->put_record(vTime, recOut, &ts); w->put_record(vTb, recOut, tb); }
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) put_seg(vQ[r], recOut, &acc[(size_t)r * nRch]);
                     if (vDlay >= 0) put_seg(vDlay, recOut, &acc[(size_t)o.n_routes * nRch]);
                     for (auto &v : accX) v /= (double)nAcc;

@@ -473,6 +473,7 @@ def test_daily_mean_output_and_delayed_runoff(tmp_path, backend):
     want_q = np.stack([q[0:24].mean(0), q[24:48].mean(0), q[48:60].mean(0)])
     want_r = np.stack([qr[0:24].mean(0), qr[24:48].mean(0), qr[48:60].mean(0)])
     assert np.array_equal(out["time"], np.array([0.0, 86400.0, 172800.0]))
+    assert np.array_equal(out["time_bounds"], np.array([[0.0, 86400.0], [86400.0, 172800.0], [172800.0, 60 * 3600.0]]))    # historyFile.f90:372
     np.testing.assert_allclose(out["IRFroutedRunoff"], want_q, rtol=3e-6, atol=1e-30)
     np.testing.assert_allclose(out["dlayRunoff"], want_r, rtol=3e-6, atol=1e-30)
 
