@@ -650,3 +650,47 @@ def test_history_at_gauges_only(tmp_path, backend):
     for v in ("sumUpstreamRunoff", "IRFroutedRunoff", "dlayRunoff", "IRFvolume"):
         assert np.array_equal(outs[1][v], outs[0][v][:, rch]), v
     assert np.array_equal(outs[1]["basRunoff"], outs[0]["basRunoff"])                  # HRU-dimensioned output is not subset
+
+
+_REF = "/root/reference/route"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(_REF, "settings", "SAMPLE.control")), reason="reference checkout not present (CPU container only)")
+def test_reference_sample_control_file_drives_the_host(tmp_path):
+    """Drop-in check of the control-file reader: the reference's own route/settings/SAMPLE.control -- every line, comments and
+    layout as shipped -- with only its placeholder values (CASE_NAME, NTOPO_NC, ...) filled in, and its param.nml.default,
+    runs through this host (stand-in library) and gives the oracle's flows for the options the sample asks for
+    (route_opt 5, daily steps, daily output, monthly files)."""
+    import re
+    import shutil
+    from oracle.oracle import Oracle
+    net, params, opts, ro = case("random", n=60, seed=3, dt=86400.0, route_opt="5", steps=40)
+    opts.units_qsim = "mm/s"
+    ro = ro * 1000.0                                                                  # the sample's <units_qsim> is mm/s
+    ctl0 = casefiles.write_case(str(tmp_path), net, params, opts, ro, case_name="sample", restart_write="last")
+    mine = dict(re.findall(r"^<([A-Za-z0-9_]+)>\s+(.*?)\s*!", open(ctl0).read(), flags=re.M))
+    anc = mine["ancil_dir"]
+    shutil.copy(os.path.join(_REF, "ancillary_data", "param.nml.default"), os.path.join(anc, "param.nml.default"))
+    fill = {"param_nml": "param.nml.default", "is_remap": "F", "fname_state_in": "coldstart", "seg_outlet": "-9999",
+                 "varname_area": "area", "varname_length": "length", "varname_slope": "slope", "varname_HRUid": "HRUid",
+                 "varname_hruSegId": "hruSegId", "varname_segId": "segId", "varname_downSegId": "downSegId",
+                 "varname_islake": "islake", "varname_lakeModelType": "lakeModelType"}
+    placeholder = lambda v: bool(re.fullmatch(r"[A-Z][A-Z_0-9]*", v)) or v.startswith("yyyy")
+    lines = []
+    for line in open(os.path.join(_REF, "settings", "SAMPLE.control")):
+        m = re.match(r"^(<([A-Za-z0-9_]+)>\s+)(\S.*?)(\s*!.*)$", line.rstrip("\n"))
+        if m and (m.group(2) in fill or (placeholder(m.group(3).strip()) and m.group(2) in mine)):
+            line = m.group(1) + str(fill.get(m.group(2), mine.get(m.group(2)))) + "   " + m.group(4).strip() + "\n"
+        lines.append(line)
+    ctl = os.path.join(str(tmp_path), "SAMPLE_filled.control")
+    open(ctl, "w").writelines(lines)
+    kept = dict(re.findall(r"^<([A-Za-z0-9_]+)>\s+(.*?)\s*!", "".join(lines), flags=re.M))
+    assert kept["route_opt"] == "5" and kept["outputFrequency"] == "daily" and kept["newFileFrequency"] == "monthly"      # the sample's own choices
+    r = subprocess.run([_routing_host("oracle-stub"), ctl, "--batch", "16"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    files = info.get("history_files", [info["history"]])
+    assert [os.path.basename(f) for f in files] == ["sample.h.2000-01.nc", "sample.h.2000-02.nc"]                  # get_hfilename, monthly
+    out = np.concatenate([casefiles.read_history(f)["DWroutedRunoff"] for f in files])
+    qo = Oracle(net, params, opts).run(ro)
+    np.testing.assert_allclose(out, qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
