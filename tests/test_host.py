@@ -9,7 +9,7 @@ import pytest
 
 from mizuroute_b200 import build as mrbuild
 from mizuroute_b200 import casefiles
-from mizuroute_b200.network import RouteParams
+from mizuroute_b200.network import RouteOptions, RouteParams
 from tests.util import case
 
 
@@ -694,3 +694,29 @@ def test_reference_sample_control_file_drives_the_host(tmp_path):
     out = np.concatenate([casefiles.read_history(f)["DWroutedRunoff"] for f in files])
     qo = Oracle(net, params, opts).run(ro)
     np.testing.assert_allclose(out, qo[0].astype(np.float32), rtol=2e-6, atol=1e-30)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(_REF, "build", "src", "public_var.f90")), reason="reference checkout not present (CPU container only)")
+def test_option_defaults_equal_the_reference_declarations():
+    """The defaults of RouteOptions / RouteParams (and so of every test case and of the host, which share them) against the
+    declarations in public_var.f90 and the namelist the reference ships (param.nml.default)."""
+    import re
+    from mizuroute_b200 import capi
+    src = open(os.path.join(_REF, "build", "src", "public_var.f90")).read()
+
+    def declared(name):
+        m = re.search(r"::\s*%s\s*=\s*([^!\n]+)" % re.escape(name), src)
+        assert m, name
+        v = m.group(1).strip().lower()
+        if v in (".true.", ".false."):
+            return v == ".true."
+        return float(re.sub(r"_dp|_i4b", "", v).replace("d", "e"))
+    o = RouteOptions()
+    for name in ("doesBasinRoute", "hw_drain_point", "min_length_route", "is_lake_sim", "lakeRegulate", "LakeInputOption", "runoffMin", "floodplain"):
+        assert float(getattr(o, name)) == float(declared(name)), name
+    assert declared("MAXQPAR") == capi.MR_KW_SLOTS - 2 == 20 and declared("negRunoffTol") == -1e-3
+    assert (declared("qBlendPeriod"), declared("QerrTrend"), declared("qmodOption")) == (10, 1, 0)
+    nml = open(os.path.join(_REF, "ancillary_data", "param.nml.default")).read()
+    p = RouteParams()
+    for name in ("fshape", "tscale", "velo", "diff", "mann_n", "wscale"):
+        assert float(re.search(r"%s\s*=\s*([0-9.eE+-]+)" % name, nml).group(1)) == getattr(p, name), name
