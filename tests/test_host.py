@@ -720,3 +720,20 @@ def test_option_defaults_equal_the_reference_declarations():
     p = RouteParams()
     for name in ("fshape", "tscale", "velo", "diff", "mann_n", "wscale"):
         assert float(re.search(r"%s\s*=\s*([0-9.eE+-]+)" % name, nml).group(1)) == getattr(p, name), name
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(_REF, "build", "src", "read_control.f90")), reason="reference checkout not present (CPU container only)")
+def test_every_control_key_of_the_reference_is_accepted():
+    """read_control.f90 stops at an unknown key (:374-377), and so does this host -- so every key the reference's reader knows
+    (and every key its sample control files use) must be known here, or a working control file would be refused."""
+    import glob
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mizuroute_b200", "csrc", "route_runoff.cpp")).read()
+    i = src.index("KNOWN_KEYS[] = {")
+    known = set(re.findall(r'"([A-Za-z0-9_]+)"', src[i:src.index("};", i)]))
+    free = re.compile(r"(varname_|vname_|dname_|fname_)")                         # name keys are accepted by prefix
+    ref = set(re.findall(r"case\('<([A-Za-z0-9_]+)>'", open(os.path.join(_REF, "build", "src", "read_control.f90")).read()))
+    assert len(ref) > 100
+    for f in glob.glob(os.path.join(_REF, "settings", "*.control")):
+        ref |= set(re.findall(r"^<([A-Za-z0-9_]+)>", open(f).read(), flags=re.M))
+    assert sorted(k for k in ref if k not in known and not free.match(k)) == []
