@@ -108,3 +108,22 @@ def test_zero_flow_aborts_kwt_like_the_reference():
     with pytest.raises(orc.OracleError) as ei:                   # kwt_route.f90:1365-1368
         orc.Oracle(net, params, opts).run(np.zeros((1, net.nHRU)))
     assert ei.value.ierr == 20
+
+
+def test_hillslope_uh_is_the_gamma_distribution_scipy_knows():
+    """basinUH (process_param.f90:13-92): FRAC_FUTURE(j) = P(fshape, j dt / tscale) - P(fshape, (j-1) dt / tscale), normalised
+    -- against scipy's regularised incomplete gamma function, which shares no code with the
+    Numerical-Recipes gser / gcf / 6-term Lanczos gammln the reference (and the oracle) use: agreement to ~1e-9."""
+    from scipy.special import gammainc
+    for dt, fshape, tscale in ((3600.0, 2.5, 86400.0), (86400.0, 2.5, 86400.0), (900.0, 1.3, 20000.0), (10800.0, 4.0, 250000.0)):
+        net, params, opts, ro = case("random", n=8, seed=2, dt=dt, route_opt="1", steps=1)
+        params.fshape, params.tscale = fshape, tscale
+        ff = orc.Oracle(net, params, opts).frac_future()
+        j = np.arange(1, ff.size + 1)
+        theta = tscale                                                      # TFUTURE/tscale, process_param.f90:84
+        want = np.maximum(gammainc(fshape, j * dt / theta) - gammainc(fshape, (j - 1) * dt / theta), 0.0)
+        assert 0.99 < want.sum() < 0.9991 or ff.size == 1                       # the series is cut where the cumulative mass passes 0.99 (:60-75)
+        want = want / want.sum()
+        assert np.max(np.abs(ff - want)) < 2e-9
+    for a, x in ((0.3, 0.1), (2.5, 0.7), (2.5, 6.0), (7.0, 3.0), (7.0, 25.0)):      # both branches: series (x < a+1) and continued fraction
+        assert abs(orc.gammp(a, x) - gammainc(a, x)) < 1e-9
