@@ -1,6 +1,6 @@
 """Generates the golden fixtures in this directory from the CPU oracle.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [--options-only]      (--options-only: rewrite only the OPTION_CASES fixtures)
 
 The reference (Fortran) cannot be built or run in this environment and ships no golden vectors for the routing
 path, so these fixtures are produced by oracle/mr_oracle.c (cross-checked against the

@@ -1,7 +1,8 @@
 """Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the CPU oracle).
 
 CPU: the oracle still reproduces every fixture bit for bit (regression pin of the checker itself).
-GPU: the CUDA path, through the C ABI, reproduces them: SUM/IRF exactly, KWT within 1e-4 relative."""
+GPU: the CUDA path, through the C ABI, reproduces them: SUM/IRF exactly, KWT within 1e-4 relative.
+OPTION_CASES: the Euler schemes, water management and data assimilation, with their per-step inputs stored in the fixture."""
 import os
 
 import numpy as np
