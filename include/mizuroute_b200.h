@@ -105,7 +105,7 @@ typedef struct {
     int    max_batch;            /* largest nSteps a batch call may pass (sizes the resident series) */
     /* Euler schemes (route methods 3/4/5) only; zero = the reference's defaults */
     int    floodplain;           /* <floodplain>: 1 = finite bankfull depth dscale*sqrt(totalArea), 0 = high_depth (process_ntopo.f90:174-196) */
-    double dscale;               /* bankfull depth scaling, 0 -> 0.000045 (globalData.f90:187) */
+    double dscale;               /* bankfull depth scaling, 0 -> real(0.000045) = 4.5000000682193786e-05, a default-real literal (globalData.f90:187) */
     double floodplainSlope;      /* floodplain slope h:v, 0 -> 1000 (globalData.f90:188) */
 } mr_options;
 

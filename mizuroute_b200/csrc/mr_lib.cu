@@ -113,14 +113,27 @@ int dev_alloc(mr_handle h, T **ptr, size_t n, const char *where, char *message, 
     CU(cudaMalloc((void **)ptr, bytes));
     h->allocs.push_back(*ptr);
     h->devBytes += bytes;
-    if (zero) CU(cudaMemsetAsync(*ptr, 0, bytes, h->stream));
+    // The handle's stream is non-blocking: nothing orders it against the legacy stream the synchronous cudaMemcpy calls of
+    // the set-up code run on.  The zeroing is therefore complete before dev_alloc returns, so a copy issued next (lake /
+    // zero-area sentinels in mr_set_network, the rows of mr_upload_wm) can never be overwritten by a late memset.
+    if (zero) { CU(cudaMemsetAsync(*ptr, 0, bytes, h->stream)); CU(cudaStreamSynchronize(h->stream)); }
     return 0;
 }
+// Every host <-> device copy of the set-up / state code goes through the handle's stream and is complete on return: a plain
+// cudaMemcpy runs on the legacy stream, which is not ordered against the (non-blocking) stream the kernels run on, and for
+// pageable sources returns once the data is staged, not once it has arrived.
+cudaError_t copy_sync(mr_handle h, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    if (!bytes) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, h->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(h->stream);
+}
+
 template <typename T>
 int dev_upload(mr_handle h, T **ptr, const std::vector<T> &v, const char *where, char *message) {
     int e = dev_alloc(h, ptr, v.size(), where, message, false);
     if (e) return e;
-    if (!v.empty()) CU(cudaMemcpy(*ptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+    if (!v.empty()) CU(copy_sync(h, *ptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -246,6 +259,10 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         h->obsSteps = 0;
         return fail(message, 1, std::string(where) + "/gauge observations were uploaded for a different number of steps");
     }
+    // exchange buffers are checked before anything is launched or consumed: a refusal leaves the state untouched
+    if (h->nGhost && !d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
+    if (h->nExport && !d.expBuf) return fail(message, 1, std::string(where) + "/export reaches but no export buffer (mr_set_exchange_buffer)");
+    if (h->qmodOption == 1) { int e = ensure_da(h, where, message); if (e) return e; }
     d.wmFlux = d.wmVol = nullptr; d.volJumpStart = 0; d.lakeTargVol = h->dLakeTargVol;
     h->wmActive = false;
     if (h->wmSteps) {                                   // water management rows uploaded for this batch
@@ -287,7 +304,6 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
     // upload is a stretch of the gauge file without records
     d.daQobs = nullptr; d.daElapsed = nullptr; h->daActive = false;
     if (h->qmodOption == 1) {
-        int e = ensure_da(h, where, message); if (e) return e;
         if (!h->obsSteps) CU(cudaMemsetAsync(h->dHasRecord, 0, (size_t)K, h->stream));
         h->obsSteps = 0;
         k_da_rows<<<(N + 255) / 256, 256, 0, h->stream>>>(h->dDaQobs, h->dDaEl, h->dQobsState, h->dElState, h->dHasRecord, N, K);
@@ -297,11 +313,9 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         h->daActive = true;
     }
     if (h->nGhost) {
-        if (!d.impBuf) return fail(message, 1, std::string(where) + "/ghost reaches but no import buffer (mr_set_exchange_buffer)");
         k_import_unpack<<<(h->nGhost * K + 255) / 256, 256, 0, h->stream>>>(d, h->dImpPos, h->nGhost, K);
         h->launchesLast++;
     }
-    if (h->nExport && !d.expBuf) return fail(message, 1, std::string(where) + "/export reaches but no export buffer (mr_set_exchange_buffer)");
     CU(cudaEventRecord(h->ev[2], h->stream));
     // The methods of route_opt share only BASIN_QR (read-only here), so they run concurrently: the last one on the
     // handle's stream, the others on auxiliary streams forked after k_basin and joined before the export.
@@ -478,7 +492,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         rman[p] = man_n ? man_n[r] : o.mann_n;
         if (h->nGhost && gKind[r]) { h->flags[p] |= FLAG_GHOST; rwid[p] = gWidth[r]; }
         if (euler) {
-            if (o.floodplain) rdep[p] = (o.dscale > 0.0 ? o.dscale : 0.000045) * std::sqrt(T.totArea[p]);
+            if (o.floodplain) rdep[p] = (o.dscale > 0.0 ? o.dscale : (double)0.000045f) * std::sqrt(T.totArea[p]);
             rstor[p] = rdep[p] * (rwid[p] + zside[p] * rdep[p]) * rlen[p];       // flow_area(y = bankDepth) * length
         }
         if (o.is_lake_sim) {
@@ -571,10 +585,10 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
                 if (lake || T.nGood[p] == 0) s9[(size_t)p * KWP] = -9999.0;
             }
             for (int b = 0; b < 2; ++b) {
-                CU(cudaMemcpy(d.kwN[b], n1.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwQF[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwTI[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
-                CU(cudaMemcpy(d.kwTR[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
+                CU(copy_sync(h, d.kwN[b], n1.data(), sizeof(int) * N, cudaMemcpyHostToDevice));
+                CU(copy_sync(h, d.kwQF[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
+                CU(copy_sync(h, d.kwTI[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
+                CU(copy_sync(h, d.kwTR[b], s9.data(), sizeof(double) * s9.size(), cudaMemcpyHostToDevice));
             }
         }
     }
@@ -681,7 +695,7 @@ int mr_set_ingest(mr_handle h, int nForcing, const int *forcingOfHru, double sca
     for (int i = 0; i < nH; ++i) if (src[i] >= nForcing) return fail(message, 1, "mr_set_ingest/forcing column outside the records");
     if (!h->dIngestSrc) { e = dev_alloc(h, &h->dIngestSrc, (size_t)nH, where, message, false); if (e) return e;
                           e = dev_alloc(h, &h->dIngestPtr, (size_t)h->opt.max_batch + 1, where, message, false); if (e) return e; }
-    CU(cudaMemcpy(h->dIngestSrc, src.data(), sizeof(int) * (size_t)nH, cudaMemcpyHostToDevice));
+    CU(copy_sync(h, h->dIngestSrc, src.data(), sizeof(int) * (size_t)nH, cudaMemcpyHostToDevice));
     // scale_forcing (get_basin_runoff.f90:375-423): -9999 = not given
     h->ingestRescale = (scale != -9999.0 || offset != -9999.0) ? 1 : 0;
     h->ingestA = scale == -9999.0 ? 1.0 : scale; h->ingestB = offset == -9999.0 ? 0.0 : offset; h->ingestFill = fill;
@@ -747,6 +761,7 @@ int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *v
     const size_t N = (size_t)h->d.nRch, KB = (size_t)h->opt.max_batch;
     const Topology &T = h->topo;
     h->wmStage.resize((size_t)nSteps * N);
+    CU(cudaStreamSynchronize(h->stream));                 // the rows of the previous batch may still be read
     for (int w = 0; w < 2; ++w) {
         const double *src = w == 0 ? flux_wm : vol_wm;
         double **dst = w == 0 ? &h->dWmFlux : &h->dWmVol;
@@ -754,7 +769,7 @@ int mr_upload_wm(mr_handle h, int nSteps, const double *flux_wm, const double *v
         if (!*dst) { e = dev_alloc(h, dst, KB * N, where, message); if (e) return e; }
         for (int t = 0; t < nSteps; ++t)                  // caller's reach order -> stage order
             for (size_t p = 0; p < N; ++p) h->wmStage[(size_t)t * N + p] = src[(size_t)t * N + T.pos2rch[p]];
-        CU(cudaMemcpy(*dst, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
+        CU(copy_sync(h, *dst, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
     }
     h->wmHasFlux = flux_wm != nullptr; h->wmHasVol = vol_wm != nullptr && h->opt.is_lake_sim;      // REACH_WM_VOL is 0 without is_lake_sim
     h->wmJumpStart = volJumpStart ? 1 : 0;
@@ -787,8 +802,8 @@ int mr_upload_obs(mr_handle h, int nSteps, const int *hasRecord, const double *o
     h->hasRecordHost.assign((size_t)nSteps, 1);
     if (hasRecord) for (int t = 0; t < nSteps; ++t) h->hasRecordHost[t] = hasRecord[t] ? 1 : 0;
     CU(cudaStreamSynchronize(h->stream));                 // the rows of the previous batch may still be read
-    CU(cudaMemcpy(h->dDaQobs, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->dHasRecord, h->hasRecordHost.data(), (size_t)nSteps, cudaMemcpyHostToDevice));
+    CU(copy_sync(h, h->dDaQobs, h->wmStage.data(), sizeof(double) * (size_t)nSteps * N, cudaMemcpyHostToDevice));
+    CU(copy_sync(h, h->dHasRecord, h->hasRecordHost.data(), (size_t)nSteps, cudaMemcpyHostToDevice));
     h->obsSteps = nSteps;
     put_msg(message, "");
     return 0;
@@ -996,7 +1011,7 @@ int mr_get_flux(mr_handle h, int method, int field, double *out, char *message) 
     }
     if (!src) { for (int r = 0; r < N; ++r) out[r] = 0.0; put_msg(message, ""); return 0; }
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(tmp.data(), src, sizeof(double) * N, cudaMemcpyDeviceToHost));
+    CU(copy_sync(h, tmp.data(), src, sizeof(double) * N, cudaMemcpyDeviceToHost));
     for (int r = 0; r < N; ++r) out[r] = tmp[T.rch2pos[r]];
     put_msg(message, "");
     return 0;
@@ -1034,7 +1049,7 @@ int mr_get_state(mr_handle h, int var, void *buf, long nbytes, char *message) {
     const Topology &T = h->topo;
     const long long tau = h->stepsDone;
     double *out = (double *)buf; int *iout = (int *)buf;
-    auto pull = [&](const void *src, void *dst, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); };
+    auto pull = [&](const void *src, void *dst, size_t bytes) { return copy_sync(h, dst, src, bytes, cudaMemcpyDeviceToHost); };
     switch (var) {
         case MR_ST_BASIN_QFUTURE: {
             const int nb = h->ntdhBas;
@@ -1132,7 +1147,7 @@ int mr_set_state(mr_handle h, int var, const void *buf, long nbytes, char *messa
     const Topology &T = h->topo;
     const long long tau = h->stepsDone;
     const double *in = (const double *)buf; const int *iin = (const int *)buf;
-    auto push = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice); };
+    auto push = [&](void *dst, const void *src, size_t bytes) { return copy_sync(h, dst, src, bytes, cudaMemcpyHostToDevice); };
     switch (var) {
         case MR_ST_BASIN_QFUTURE: {
             const int nb = h->ntdhBas;
@@ -1237,7 +1252,7 @@ int mr_set_steps_done(mr_handle h, long steps, char *message) {
     if (h->on[M_KWT]) { vars.push_back(MR_ST_KWT_NWAVE); vars.push_back(MR_ST_KWT_ROUTED); vars.push_back(MR_ST_KWT_QWAVE); vars.push_back(MR_ST_KWT_TENTRY); vars.push_back(MR_ST_KWT_TEXIT); }
     for (int v : vars) { keep.emplace_back(state_bytes(h, v)); int e = mr_get_state(h, v, keep.back().data(), (long)keep.back().size(), message); if (e) return e; }
     // carry row of BASIN_QR(1)
-    if (h->lastK > 0) { CU(cudaMemcpy(h->d.qrSer, h->d.qrSer + (size_t)h->lastK * h->d.nRch, 8L * h->d.nRch, cudaMemcpyDeviceToDevice)); h->lastK = 0; }
+    if (h->lastK > 0) { CU(copy_sync(h, h->d.qrSer, h->d.qrSer + (size_t)h->lastK * h->d.nRch, 8L * h->d.nRch, cudaMemcpyDeviceToDevice)); h->lastK = 0; }
     h->stepsDone = steps;
     for (size_t i = 0; i < vars.size(); ++i) { int e = mr_set_state(h, vars[i], keep[i].data(), (long)keep[i].size(), message); if (e) return e; }
     put_msg(message, "");
@@ -1286,8 +1301,8 @@ long mr_get_info(mr_handle h, int key) {
             cudaSetDevice(h->opt.device);
             cudaStreamSynchronize(h->stream);
             std::vector<unsigned> c(h->d.nRch);
-            cudaMemcpy(c.data(), h->dKwCount, 4L * h->d.nRch, cudaMemcpyDeviceToHost);
-            cudaMemset(h->dKwCount, 0, 4L * h->d.nRch);
+            copy_sync(h, c.data(), h->dKwCount, 4L * h->d.nRch, cudaMemcpyDeviceToHost);
+            cudaMemsetAsync(h->dKwCount, 0, 4L * h->d.nRch, h->stream); cudaStreamSynchronize(h->stream);
             long tot = 0; for (unsigned v : c) tot += v;
             return tot;
         }
@@ -1297,8 +1312,8 @@ long mr_get_info(mr_handle h, int key) {
             cudaStreamSynchronize(h->stream);
             const int N = h->d.nRch, b = (int)((h->stepsDone + 1) & 1);
             std::vector<int> n(N), nr(N);
-            cudaMemcpy(n.data(), h->d.kwN[b], 4L * N, cudaMemcpyDeviceToHost);
-            cudaMemcpy(nr.data(), h->d.kwNR[b], 4L * N, cudaMemcpyDeviceToHost);
+            copy_sync(h, n.data(), h->d.kwN[b], 4L * N, cudaMemcpyDeviceToHost);
+            copy_sync(h, nr.data(), h->d.kwNR[b], 4L * N, cudaMemcpyDeviceToHost);
             long tot = 0;
             for (int p = 0; p < N; ++p) tot += n[p] - (nr[p] > 0 ? nr[p] - 1 : 0);
             return tot;
@@ -1458,7 +1473,7 @@ void mr_destroy(mr_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->hasNet && h->d.kwProf) {                  // MR_KWT_PROFILE=1: cycles per task class (development)
         unsigned long long pr[16];
-        if (cudaMemcpy(pr, h->d.kwProf, sizeof(pr), cudaMemcpyDeviceToHost) == cudaSuccess) {
+        if (copy_sync(h, pr, h->d.kwProf, sizeof(pr), cudaMemcpyDeviceToHost) == cudaSuccess) {
             static const char *nm[8] = {"n=0", "n<=3", "n<=6", "n<=12", "n<=20", "n<=40", "n>40", "retry"};
             double tot = 0; for (int c = 0; c < 8; ++c) tot += (double)pr[2 * c];
             for (int c = 0; c < 8; ++c) if (pr[2 * c + 1])

@@ -443,7 +443,7 @@ mro_t *mro_create(int nRch, int nHRU,
         h->R_MAN_N[i] = man_n_in ? man_n_in[i] : mann_n;
     }
     ALLOC(h->R_DEPTH, nRch); ALLOC(h->SIDE_SLOPE, nRch); ALLOC(h->FLDP_SLOPE, nRch); ALLOC(h->R_STORAGE, nRch);
-    mro_set_channel(h, 0, 0.000045, 1000.0);
+    mro_set_channel(h, 0, (double)0.000045f, 1000.0);   /* default-real literal, globalData.f90:187 */
     /* lakes (process_ntopo.f90:476-485; network_topo.f90:958-985) */
     ALLOC(h->isLake, nRch); ALLOC(h->lakeInlet, nRch); ALLOC(h->lakeModelType, nRch);
     ALLOC(h->D03_MaxStorage, nRch); ALLOC(h->D03_Coefficient, nRch); ALLOC(h->D03_Power, nRch); ALLOC(h->D03_S0, nRch);

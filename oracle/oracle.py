@@ -86,7 +86,7 @@ class Oracle:
             y, mo, d, sec = opts.sim_start
             L.mro_set_sim_start(self.h, C.c_int(y), C.c_int(mo), C.c_int(d), dbl(sec), C.c_int(int(opts.calendar == "noleap")))
         if getattr(opts, "floodplain", False):          # <floodplain> T: bankfull depth dscale*sqrt(totalArea) (process_ntopo.f90:174-203)
-            L.mro_set_channel(self.h, C.c_int(1), dbl(0.000045), dbl(1000.0))
+            L.mro_set_channel(self.h, C.c_int(1), dbl(4.5000000682193786e-05), dbl(1000.0))
         self.T0, self.T1 = 0.0, float(opts.dt)      # init_model_data.f90:600
 
     def __del__(self):

@@ -533,7 +533,7 @@ class Twin:
         self.WB = {m: [0.0] * n for m in range(6)}
         # Euler schemes: channel geometry (process_ntopo.f90:174-203) and molecules (init_model_data.f90:386-393,463-497)
         fp = bool(getattr(opts, "floodplain", False))
-        self.depth = [0.000045 * math.sqrt(self.tot[i]) if fp else 100000.0 for i in range(n)]
+        self.depth = [4.5000000682193786e-05 * math.sqrt(self.tot[i]) if fp else 100000.0 for i in range(n)]
         self.zc = [0.0] * n
         self.zf = [1000.0] * n
         self.storage = [hy_area(self.depth[i], self.width[i], self.zc[i], self.zf[i], self.depth[i]) * self.length[i] for i in range(n)]

@@ -48,7 +48,7 @@ extern "C" int euler_emul_run(int method, int nRch, int nHRU, const int *segId, 
     for (int p = 0; p < N; ++p) {
         const int r = T.pos2rch[p];
         rlen[p] = length[r]; rslp[p] = std::fmax(slope[r], 1.e-6); rwid[p] = wscale * std::sqrt(T.totArea[p]);
-        rdep[p] = floodplain ? 0.000045 * std::sqrt(T.totArea[p]) : 100000.0;                  // as mr_set_network
+        rdep[p] = floodplain ? (double)0.000045f * std::sqrt(T.totArea[p]) : 100000.0;                  // as mr_set_network
         rstor[p] = rdep[p] * (rwid[p] + zc[p] * rdep[p]) * rlen[p];
     }
     std::vector<double> qrSer((size_t)(nSteps + 1) * N), qSer((size_t)nSteps * N, 0.0), inflow(N, 0.0), vol0(N, 0.0), vol1(N, 0.0), wb(N, 0.0),

@@ -61,7 +61,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     if (!h->m) { say(message, "mr_set_network/oracle refused the network"); return 20; }
     { int k; for (k = 0; k < h->nLp; k++) if (mro_set_lake_param(h->m, h->lpName[k], h->lpVal[k])) { say(message, "mr_set_network/unknown lake parameter"); return 20; } }
     if (h->hasStart) mro_set_sim_start(h->m, h->sy, h->sm, h->sd, h->ssec, h->noleap);
-    if (h->o.floodplain) mro_set_channel(h->m, 1, h->o.dscale > 0.0 ? h->o.dscale : 0.000045, h->o.floodplainSlope > 0.0 ? h->o.floodplainSlope : 1000.0);
+    if (h->o.floodplain) mro_set_channel(h->m, 1, h->o.dscale > 0.0 ? h->o.dscale : (double)0.000045f, h->o.floodplainSlope > 0.0 ? h->o.floodplainSlope : 1000.0);
     say(message, "");
     return 0;
 }
