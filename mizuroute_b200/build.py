@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmizuroute_b200.so")
 SOURCES = ["mr_lib.cu"]
-DEPS = ["mr_lib.cu", "mr_kernels.cuh", "mr_kwt.cuh", "mr_irf.cuh", "mr_euler.cuh", "mr_lake.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_uh.h",
+DEPS = ["mr_lib.cu", "mr_kernels.cuh", "mr_kwt.cuh", "mr_kwt_scalar.cuh", "mr_irf.cuh", "mr_euler.cuh", "mr_lake.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h", "mr_uh.h",
         "mr_calendar.h", "mr_lakeparams.h", "mr_ingest.h", os.path.join("..", "..", "include", "mizuroute_b200.h")]
 
 NVCC_FLAGS = [

@@ -18,11 +18,13 @@
 //                 M=0 accum_inst_runoff (accum_runoff.f90:60-75), M=1 irf_rch+conv_upsbas_qr
 //                 (irf_route.f90:82-150,235-262), M=3/4/5 the Euler schemes kw_rch / mc_rch / dfw_rch (mr_euler.cuh);
 //                 lake reaches branch to lake_route (lake_route.f90:87-229)
-//   k_route_kwt   the same for kwt_rch and callees (kwt_route.f90:36-1622), half-warp team per (reach, step)
+//   k_route_kwt   the same for kwt_rch and callees (kwt_route.f90:36-1622): thread per (reach, step) for the plain tasks,
+//                 half-warp team per (reach, step) for the rest
 //   k_export_pack / k_import_unpack   tributary -> mainstem hand-off records (mpi_process.f90:1238-1329)
 #pragma once
 #include "mr_dev.h"
 #include "mr_kwt.cuh"
+#include "mr_kwt_scalar.cuh"
 #include "mr_irf.cuh"
 #include "mr_euler.cuh"
 #include "mr_lake.cuh"
@@ -314,16 +316,47 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
 #ifndef KWT_MIN_BLOCKS
 #define KWT_MIN_BLOCKS 8
 #endif
-// Tasks are dealt to teams block by block; the loop bounds are the same for all teams of a warp (required by the
-// full-warp syncs inside kwt_task).
+#ifndef KWS_TPB_N
+#define KWS_TPB_N 64
+#endif
+#ifndef KWS_MIN_BLOCKS
+#define KWS_MIN_BLOCKS 10
+#endif
+constexpr int KWS_TPB = KWS_TPB_N;                       // threads (= tasks) per block of the thread-per-task kernel
+// One KWT wavefront = two launches:
+//   k_route_kwt_scalar  one THREAD per (reach, step): kwt_reach_scalar (mr_kwt_scalar.cuh) routes the task if it is a plain
+//                       one -- at most MR_MAXQPAR particles, no shock, no lake / ghost / water management -- with its
+//                       particles in a shared-memory column; the others are appended to the wavefront's deferred list in HBM
+//                       (one atomic per warp);
+//   k_route_kwt_team    the deferred tasks (thinning, shocks, everything special), dealt over the whole GPU to teams of
+//                       MR_TEAM lanes and routed by the cooperative code (kwt_task -> kwt_reach_team, mr_kwt.cuh).  The loop
+//                       bounds are the same for all teams of a warp (required by the full-warp syncs inside kwt_task).
 template <bool HY = false>
-__global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt(DevNet d, int lo, int hi, int w, long long tau0) {
+__global__ void __launch_bounds__(KWS_TPB, KWS_MIN_BLOCKS) k_route_kwt_scalar(DevNet d, int lo, int hi, int w, long long tau0, int *deferCnt, int *deferList) {
+    __shared__ double col[2 * KWS_NL * KWS_TPB];
+    const int tid = threadIdx.x;
+    const int p = lo + blockIdx.x * KWS_TPB + tid;
+    const bool active = p < hi;                        // (every lane of the warp enters: the loops inside are warp-uniform)
+    const int t = active ? w - d.stageOf[p] : 0;
+    const bool defer = kwt_reach_scalar<HY, KWS_TPB>(d, col + tid, col + KWS_NL * KWS_TPB + tid, p, t, tau0 + t, d.T0s[t], d.T1s[t], active) != KWS_DONE;
+    const unsigned m = __ballot_sync(0xffffffffu, defer);
+    if (m) {
+        int base = 0;
+        if ((tid & 31) == 0) base = atomicAdd(deferCnt, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (defer) deferList[base + __popc(m & ((1u << (tid & 31)) - 1u))] = p;
+    }
+}
+
+template <bool HY = false>
+__global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt_team(DevNet d, const int *deferCnt, const int *deferList, int w, long long tau0) {
     __shared__ KwtScratchSmall S[KWT_TEAMS];
     const int team = threadIdx.x / MR_TEAM;
-    const int stride = gridDim.x * KWT_TEAMS;
-    for (int base = lo + blockIdx.x * KWT_TEAMS; base < hi; base += stride) {
-        const int p = base + team;
-        kwt_task<HY>(d, S[team], p, p < hi, w, tau0);
+    const int cnt = *deferCnt;
+    for (int base = blockIdx.x * KWT_TEAMS; base < cnt; base += gridDim.x * KWT_TEAMS) {
+        const int i = base + team;
+        const bool active = i < cnt;
+        kwt_task<HY>(d, S[team], active ? deferList[i] : 0, active, w, tau0);
         MR_WSYNC();
     }
 }

@@ -195,7 +195,7 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, SC &S, int p, double T_START, double
     const double K = d.kwK[p];                         // sqrt(R_SLOPE)/R_MAN_N          (k_kwt_params, once per network)
     const double aK = d.kwAK[p];                       // ALFA*K**(1/ALFA)
     const double XMX = d.rlength[p];
-    const double p1 = 1.0 / ALFA, p2 = (ALFA - 1.0) / ALFA;
+    const double p1 = 1.0 / ALFA;                      // (the celerity exponent (ALFA-1)/ALFA is inside mr_pow04)
     int NN = NQ1;
     const int NI = NQ1;
     MR_NOUNROLL
@@ -204,7 +204,7 @@ MR_DEV int kwt_kinwav_team(const DevNet &d, SC &S, int p, double T_START, double
         const double q = S.Q[i], te = S.TE[i];
         Q0[i] = q; Q1[i] = q; Q2[i] = q;
         T0[i] = te; T1[i] = te;
-        const double wc = aK * mr_pow(q, p2);
+        const double wc = aK * mr_pow04(q);
         WC[i] = wc; IWC[i] = 1.0 / wc;
     }
     MR_SYNC();

@@ -39,6 +39,19 @@
 #define MR_NOUNROLL
 #endif
 
+// Whole-warp primitives of the thread-per-task code (mr_kwt_scalar.cuh): every lane routes its own task, and the loops whose
+// trip count depends on the task run for the warp's maximum with the finished lanes idling, so that the 32 lanes stay
+// converged (a data-dependent loop exit leaves them to run one after the other).  Identity in the host build.
+#if defined(__CUDACC__)
+#define MR_WARP_ANY(p) (__any_sync(0xffffffffu, (p)) != 0)
+#define MR_WARP_MAX(v) ((int)__reduce_max_sync(0xffffffffu, (unsigned)(v)))
+#define MR_WARP_SYNC() __syncwarp()
+#else
+#define MR_WARP_ANY(p) (p)
+#define MR_WARP_MAX(v) (v)
+#define MR_WARP_SYNC() ((void)0)
+#endif
+
 namespace mr {
 
 #if defined(__CUDACC__)

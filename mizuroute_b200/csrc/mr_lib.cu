@@ -47,6 +47,7 @@ struct mr_handle_s {
     cudaStream_t aux[N_METHODS - 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // the routing methods of route_opt are independent: all but the last run on these
     cudaEvent_t mev[N_METHODS][2] = {};          // start / end of each method
     unsigned *dKwCount = nullptr;
+    int *dKwDeferCnt = nullptr, *dKwDeferList = nullptr;   // KWT: per-wavefront count and list of the tasks the thread-per-task kernel deferred
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
@@ -189,6 +190,7 @@ void free_device(mr_handle h) {
     h->allocs.clear();
     h->devBytes = 0;
     h->dKwCount = nullptr;
+    h->dKwDeferCnt = h->dKwDeferList = nullptr;
 }
 
 // wavefront w of method M on stream st: every (reach, step) with stage + step == w (a contiguous position range)
@@ -200,10 +202,21 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
     if (hi <= lo) return;                        // stages that hold only headwaters
     if constexpr (M == M_KWT) {
-        int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
-        if (grid > h->kwtGridMax) grid = h->kwtGridMax;
-        if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive) k_route_kwt<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
-        else k_route_kwt<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+        // thread-per-task pass over the wavefront, then the tasks it deferred on teams (one resident wave of blocks at most:
+        // their number is known on the device only)
+        const bool ext = h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive;
+        int *cnt = h->dKwDeferCnt + w;
+        const int gridS = (hi - lo + KWS_TPB - 1) / KWS_TPB;
+        int gridT = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
+        if (gridT > h->kwtGridMax) gridT = h->kwtGridMax;
+        if (ext) {
+            k_route_kwt_scalar<true><<<gridS, KWS_TPB, 0, st>>>(h->d, lo, hi, w, tau0, cnt, h->dKwDeferList);
+            k_route_kwt_team<true><<<gridT, 32 * KWT_WARPS, 0, st>>>(h->d, cnt, h->dKwDeferList, w, tau0);
+        } else {
+            k_route_kwt_scalar<false><<<gridS, KWS_TPB, 0, st>>>(h->d, lo, hi, w, tau0, cnt, h->dKwDeferList);
+            k_route_kwt_team<false><<<gridT, 32 * KWT_WARPS, 0, st>>>(h->d, cnt, h->dKwDeferList, w, tau0);
+        }
+        h->launchesLast++;
     } else {
         if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
         else k_route<M, false><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
@@ -345,6 +358,8 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
             h->launchesLast++;
         }
     }
+    for (int r = 0; r < nr; ++r)
+        if (h->opt.route_methods[r] == M_KWT) CU(cudaMemsetAsync(h->dKwDeferCnt, 0, sizeof(int) * ((size_t)h->topo.nStage + K), st[r]));
     for (int w = 0; w < h->topo.nStage + K - 1; ++w)
         for (int r = 0; r < nr; ++r)
             switch (h->opt.route_methods[r]) {
@@ -570,6 +585,7 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         AL(arena, (size_t)KWT_ARENA_SMS * KWT_ARENA_SLOTS); AL(amask, KWT_ARENA_SMS);
         d.kwArena = arena; d.kwArenaMask = amask;
         if (std::getenv("MR_KWT_PROFILE")) { unsigned long long *pr = nullptr; AL(pr, 16); d.kwProf = pr; }
+        AL(h->dKwDeferCnt, (size_t)T.nStage + KB + 1); AL(h->dKwDeferList, N);
         for (int b = 0; b < 2; ++b) {
             AL(d.kwN[b], N); AL(d.kwNR[b], N);
             AL(d.kwQF[b], (size_t)KWP * N); AL(d.kwTI[b], (size_t)KWP * N); AL(d.kwTR[b], (size_t)KWP * N);
@@ -657,13 +673,12 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     {
         int nSM = 148, perSM = 8;
         cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, o.device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt<false>, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
-        h->kwtGridMax = 0x7fffffff;                // measured on C4: one block per KWT_TEAMS tasks beats a persistent grid by 3 %
-        (void)nSM; (void)perSM;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt_team<false>, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
+        h->kwtGridMax = nSM * perSM;               // one resident wave of team blocks, grid-stride over the deferred list
         // tuning knob (development): MR_KWT_WAVES = resident waves the KWT grid may span; 0 = one block per KWT_TEAMS tasks
         if (const char *ev = std::getenv("MR_KWT_WAVES")) {
             const double wv = std::atof(ev);
-            h->kwtGridMax = wv <= 0.0 ? 0x7fffffff : (int)(wv * nSM * perSM);
+            h->kwtGridMax = wv <= 0.0 ? nSM * perSM : (int)(wv * nSM * perSM);
         }
     }
     h->basinSmem = sizeof(double) * ((size_t)BASIN_TC * BASIN_TPB + 2 * (size_t)h->ntdhBas);

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libkwt_emul.so")
 _SRC = os.path.join(_HERE, "kwt_emul.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "mizuroute_b200", "csrc")
-_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("mr_kwt.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
+_DEPS = [_SRC] + [os.path.join(_CSRC, f) for f in ("mr_kwt.cuh", "mr_kwt_scalar.cuh", "mr_dev.h", "mr_lanes.h", "mr_topo.h")]
 
 
 def load_noisy(seed: int = 1):

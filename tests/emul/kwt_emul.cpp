@@ -1,4 +1,5 @@
-// Single-lane HOST build of the warp-cooperative KWT reach step (mizuroute_b200/csrc/mr_kwt.cuh).
+// Single-lane HOST build of the KWT reach step: the thread-per-task path (mizuroute_b200/csrc/mr_kwt_scalar.cuh) first and,
+// for the tasks it defers, the warp-cooperative path (mizuroute_b200/csrc/mr_kwt.cuh) -- the order k_route_kwt uses.
 //
 // TEST INFRASTRUCTURE ONLY.  mr_lanes.h maps a "team" to one lane when compiled without nvcc, so the very same
 // source that runs one warp per (reach, step) on the GPU is executed here serially, reach by reach in stage
@@ -10,10 +11,16 @@
 #include <string>
 #include <vector>
 
-#include "../../mizuroute_b200/csrc/mr_kwt.cuh"
+#include "../../mizuroute_b200/csrc/mr_kwt_scalar.cuh"
 #include "../../mizuroute_b200/csrc/mr_topo.h"
 
 using namespace mr;
+
+// mode 0: scalar path first, team path for what it defers (as on the device); 1: team path only
+static int g_mode = 0;
+static long g_scalar_done = 0, g_deferred = 0;
+extern "C" void kwt_emul_set_mode(int mode) { g_mode = mode; }
+extern "C" long kwt_emul_count(int which) { return which == 0 ? g_scalar_done : g_deferred; }
 
 extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId, const double *hruArea,
                             const double *length, const double *slope, double mann_n, double wscale, double dt, int nSteps,
@@ -59,6 +66,8 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     static KwtScratch S;
     static KwtScratchSmall Ssmall;
     long retries = 0;
+    g_scalar_done = g_deferred = 0;
+    std::vector<double> colQ(KWS_NL), colT(KWS_NL);
     for (int t = 0; t < nSteps; ++t) {
         const int b = t & 1;
         for (int p = 0; p < T.nHead; ++p) {                 // k_headwater<M_KWT>
@@ -66,6 +75,12 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
             kwN[b][p] = 1; kwNR[b][p] = 0;
         }
         for (int p = T.nHead; p < N; ++p) {                 // stage order: upstream before downstream
+            if (g_mode == 0) {                              // thread-per-task path; what it has written before deferring is rewritten below
+                const int rc = wm_flux ? kwt_reach_scalar<true, 1>(d, colQ.data(), colT.data(), p, t, (long long)t, T0s[t], T1s[t])
+                                       : kwt_reach_scalar<false, 1>(d, colQ.data(), colT.data(), p, t, (long long)t, T0s[t], T1s[t]);
+                if (rc == KWS_DONE) { ++g_scalar_done; continue; }
+                ++g_deferred;
+            }
             // the shared-memory-sized scratch first, the full-capacity one on KWT_RETRY -- as k_route_kwt does
             if (wm_flux) {
                 if (kwt_reach_team<KwtScratchSmall, false, true>(d, Ssmall, p, t, (long long)t, T0s[t], T1s[t]) == KWT_RETRY) {

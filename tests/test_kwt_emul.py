@@ -1,4 +1,5 @@
-"""The warp-cooperative KWT code (mr_kwt.cuh), compiled for the host with one lane per team, against the CPU
+"""The KWT device code -- the thread-per-task path (mr_kwt_scalar.cuh) backed by the warp-cooperative path (mr_kwt.cuh, one
+lane per team here) for the tasks it defers, and the warp-cooperative path alone -- compiled for the host, against the CPU
 oracle.  Both evaluate the same operations on the same operands with libm pow(), so REACH_Q and the live
 particle counts must agree bit for bit -- including steps that thin (>20 particles) and merge shocks."""
 import ctypes as C
@@ -12,7 +13,8 @@ from tests import emul
 from tests.util import case
 
 
-def _emul_vs_oracle(net, params, opts, ro):
+def _emul_vs_oracle(net, params, opts, ro, mode=0):
+    """mode 0: scalar path first, team path for the deferred tasks (what k_route_kwt does); 1: team path only"""
     K = ro.shape[0]
     o = Oracle(net, params, opts)
     qr = np.empty((K + 1, net.nRch)); qo = np.empty((K, net.nRch))
@@ -22,14 +24,18 @@ def _emul_vs_oracle(net, params, opts, ro):
         qr[t + 1] = o.get(orc.F_BASIN_QR1)
         qo[t] = o.get(orc.F_REACH_Q, orc.M_KWT)
     L = emul.load()
+    L.kwt_emul_count.restype = C.c_long
+    L.kwt_emul_set_mode(C.c_int(mode))
     qe = np.empty((K, net.nRch)); ne = np.empty(net.nRch, dtype=np.int32)
     msg = C.create_string_buffer(256)
     p = lambda a, ct: a.ctypes.data_as(C.POINTER(ct))
     ierr = L.kwt_emul_run(C.c_int(net.nRch), C.c_int(net.nHRU), p(net.segId, C.c_int), p(net.downSegId, C.c_int), p(net.hruSegId, C.c_int),
                           p(net.area, C.c_double), p(net.length, C.c_double), p(net.slope, C.c_double), C.c_double(params.mann_n),
                           C.c_double(params.wscale), C.c_double(opts.dt), C.c_int(K), p(qr, C.c_double), None, p(qe, C.c_double), p(ne, C.c_int), msg)
+    L.kwt_emul_set_mode(C.c_int(0))
     assert ierr == 0, msg.value.decode()
     _emul_vs_oracle.retries = int(msg.value.decode().split("=")[1])
+    _emul_vs_oracle.scalar, _emul_vs_oracle.deferred = int(L.kwt_emul_count(0)), int(L.kwt_emul_count(1))
     return o, qo, qe, ne
 
 
@@ -37,12 +43,20 @@ def _emul_vs_oracle(net, params, opts, ro):
                                              ("binary", 1023, 86400.0, 25), ("tiny:one_reach", 1, 3600.0, 20), ("tiny:isolated_reaches", 4, 86400.0, 10),
                                              ("tiny:chain_of_two", 2, 3600.0, 25), ("tiny:middle_reach_without_hru", 3, 3600.0, 25),
                                              ("tiny:star_of_five", 6, 900.0, 30)])
-def test_team_kwt_bit_exact_vs_oracle(kind, n, dt, steps):
+@pytest.mark.parametrize("mode", [0, 1])
+def test_team_kwt_bit_exact_vs_oracle(kind, n, dt, steps, mode):
     net, params, opts, ro = case(kind, n=n, seed=21, dt=dt, route_opt="2", steps=steps)
     orc.lib().mro_reset_counters()
-    o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro)
+    o, qo, qe, ne = _emul_vs_oracle(net, params, opts, ro, mode)
     if kind != "binary" and not kind.startswith("tiny:"):
         assert orc.lib().mro_counter(0) > 0, "thinning was not exercised"
+        if dt < 86400.0:
+            assert orc.lib().mro_counter(1) > 0, "wave breaking was not exercised"
+        if mode == 0:                                        # both paths carry a real share of the tasks
+            assert _emul_vs_oracle.scalar > 0.3 * (_emul_vs_oracle.scalar + _emul_vs_oracle.deferred)
+            assert _emul_vs_oracle.deferred > 0
+    if mode == 1:
+        assert _emul_vs_oracle.scalar == 0
     assert np.array_equal(qe, qo)
     assert np.array_equal(ne, o.get_state()["kwt_n"])
 
