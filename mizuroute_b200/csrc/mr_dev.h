@@ -20,6 +20,16 @@ constexpr int POOL_S = 88;            // with the full-capacity scratch in the g
 constexpr int NKIN = MR_MAXQPAR + 2;  // kinwav work arrays (1-based, <= 19 particles routed)
 
 enum { FLAG_LAKE = 1, FLAG_LAKE_UP = 2, FLAG_GHOST = 4 };
+// Everything static the lane-per-task KWT code (mr_kwt_scalar.cuh) needs to know about an interior reach, in one record of
+// 96 B (written once per network, k_kws_records): one load level instead of the chain upPtr -> upIdx -> nGood / R_WIDTH.
+constexpr int KWS_BMAX = 3;          // upstream reaches (basin series; at most as many wave series) of that code
+struct KwsRec {
+    int stage, cls, nGood, nUps;     // cls != 0: not a plain reach (lake, lake outlet, ghost, more than KWS_BMAX upstream reaches)
+    int U[KWS_BMAX], isr;            // upstream positions; bit s: upstream s has contributing area (a wave series)
+    double W, scfB, aK, XMX;         // R_WIDTH, 1 / R_WIDTH, ALFA * K**(1/ALFA), RLENGTH
+    double scf[KWS_BMAX];            // R_WIDTH(upstream s) / R_WIDTH
+    double pad_;
+};
 // HYPE reservoir parameters of one lake (dataTypes.f90:202-213; integers / logicals as 0/1 doubles), in this order
 struct HypeParams { double E_emr, E_lim, E_min, E_zero, Qrate_emr, Erate_emr, Qrate_prim, Qrate_amp, Qrate_phs, prim_F, A_avg, Qsim_mode; };
 constexpr int HYP_COUNT = 12;
@@ -49,6 +59,7 @@ struct DevNet {
     const double *hruWgt, *basArea, *rlength, *rslope, *rwidth, *rmann;
     const double *uh, *fracFuture;
     const double *kwK, *kwAK;       // KWT: sqrt(R_SLOPE)/R_MAN_N and ALFA*K**(1/ALFA) per reach (kwt_route.f90:1283-1296)
+    const KwsRec *kwRec;            // KWT: static per-reach record of the lane-per-task code
     const double *d03MaxS, *d03Coef, *d03Pow, *d03S0;
     // lake forcing (optional): HRU-level evaporation / precipitation of the batch [K][nHRU] and their reach-level values for
     // the lake reaches [kmax][nLake]; lakeEvap == nullptr = no lake forcing (exact zeros in lake_route)

@@ -316,35 +316,62 @@ __device__ __forceinline__ void kwt_task(const DevNet &d, KwtScratchSmall &S, in
 #ifndef KWT_MIN_BLOCKS
 #define KWT_MIN_BLOCKS 8
 #endif
-#ifndef KWS_TPB_N
-#define KWS_TPB_N 64
-#endif
-#ifndef KWS_MIN_BLOCKS
-#define KWS_MIN_BLOCKS 10
-#endif
-constexpr int KWS_TPB = KWS_TPB_N;                       // threads (= tasks) per block of the thread-per-task kernel
-// One KWT wavefront = two launches:
-//   k_route_kwt_scalar  one THREAD per (reach, step): kwt_reach_scalar (mr_kwt_scalar.cuh) routes the task if it is a plain
-//                       one -- at most MR_MAXQPAR particles, no shock, no lake / ghost / water management -- with its
-//                       particles in a shared-memory column; the others are appended to the wavefront's deferred list in HBM
-//                       (one atomic per warp);
-//   k_route_kwt_team    the deferred tasks (thinning, shocks, everything special), dealt over the whole GPU to teams of
-//                       MR_TEAM lanes and routed by the cooperative code (kwt_task -> kwt_reach_team, mr_kwt.cuh).  The loop
-//                       bounds are the same for all teams of a warp (required by the full-warp syncs inside kwt_task).
-template <bool HY = false>
-__global__ void __launch_bounds__(KWS_TPB, KWS_MIN_BLOCKS) k_route_kwt_scalar(DevNet d, int lo, int hi, int w, long long tau0, int *deferCnt, int *deferList) {
-    __shared__ double col[2 * KWS_NL * KWS_TPB];
-    const int tid = threadIdx.x;
-    const int p = lo + blockIdx.x * KWS_TPB + tid;
-    const bool active = p < hi;                        // (every lane of the warp enters: the loops inside are warp-uniform)
-    const int t = active ? w - d.stageOf[p] : 0;
-    const bool defer = kwt_reach_scalar<HY, KWS_TPB>(d, col + tid, col + KWS_NL * KWS_TPB + tid, p, t, tau0 + t, d.T0s[t], d.T1s[t], active) != KWS_DONE;
-    const unsigned m = __ballot_sync(0xffffffffu, defer);
+// One KWT wavefront = three launches (mr_kwt_scalar.cuh):
+//   k_route_kwt_light   one LANE per (reach, step), 32 tasks per warp with their particles in shared-memory columns: routes the
+//                       tasks of at most MR_MAXQPAR particles (four out of five); the others go to one of two lists in HBM
+//                       (one atomic per warp and list);
+//   k_route_kwt_heavy   the same code with room for 48 particles per task and remove_rch: the tasks that must thin;
+//   k_route_kwt_team    what is left (wave breaking, lakes, ghosts, water management, exported outlets, wide confluences,
+//                       errors), dealt over the whole GPU to teams of MR_TEAM lanes and routed by the cooperative code
+//                       (kwt_task -> kwt_reach_team, mr_kwt.cuh).  The loop bounds are the same for all teams of a warp
+//                       (required by the full-warp syncs inside kwt_task).
+// static per-reach records of the lane-per-task code, once per network
+__global__ void k_kws_records(DevNet d, KwsRec *out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < d.nRch) out[p] = kws_make_record(d, p);
+}
+
+// append p to a list in HBM if `yes` (all 32 lanes call)
+__device__ __forceinline__ void kws_push(bool yes, int *cnt, int *list, int p) {
+    const unsigned m = __ballot_sync(0xffffffffu, yes);
     if (m) {
+        const int lane = threadIdx.x & 31;
         int base = 0;
-        if ((tid & 31) == 0) base = atomicAdd(deferCnt, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (defer) deferList[base + __popc(m & ((1u << (tid & 31)) - 1u))] = p;
+        if (lane == __ffs(m) - 1) base = atomicAdd(cnt, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (yes) list[base + __popc(m & ((1u << lane) - 1u))] = p;
+    }
+}
+
+#ifndef KWS_MIN_BLOCKS_L
+#define KWS_MIN_BLOCKS_L 8
+#endif
+#ifndef KWS_MIN_BLOCKS_H
+#define KWS_MIN_BLOCKS_H 4
+#endif
+// a block = KWS_WPB warps around ONE set of 32 tasks: warp 0 runs the per-task phases (lane = task), all warps the pool phases
+template <bool HY = false>
+__global__ void __launch_bounds__(32 * KWS_WPB, KWS_MIN_BLOCKS_L) k_route_kwt_light(DevNet d, int lo, int hi, int w, long long tau0, int *cntH, int *listH, int *cntT, int *listT) {
+    __shared__ KwsWarp<KWS_NL, false> S;
+    const int p = lo + blockIdx.x * 32 + (threadIdx.x & 31);
+    const bool active = p < hi;                        // (every lane enters: the loops inside are warp-uniform)
+    const int t = active ? w - d.stageOf[p] : 0;
+    const int rc = kws_warp_route<HY, KWS_NL, false>(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t], active);
+    kws_push(rc == KWS_HEAVY, cntH, listH, p);         // (only warp 0 holds tasks)
+    kws_push(rc == KWS_TEAM, cntT, listT, p);
+}
+
+template <bool HY = false>
+__global__ void __launch_bounds__(32 * KWS_WPB, KWS_MIN_BLOCKS_H) k_route_kwt_heavy(DevNet d, const int *cntH, const int *listH, int w, long long tau0, int *cntT, int *listT) {
+    __shared__ KwsWarp<KWS_NH, true> S;
+    const int cnt = *cntH;
+    for (int base = blockIdx.x * 32; base < cnt; base += gridDim.x * 32) {
+        const int i = base + (threadIdx.x & 31);
+        const bool active = i < cnt;
+        const int p = active ? listH[i] : 0;
+        const int t = active ? w - d.stageOf[p] : 0;
+        const int rc = kws_warp_route<HY, KWS_NH, true>(d, S, p, t, tau0 + t, d.T0s[t], d.T1s[t], active);
+        kws_push(rc != KWS_DONE, cntT, listT, p);
     }
 }
 
@@ -357,6 +384,19 @@ __global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt_te
         const int i = base + team;
         const bool active = i < cnt;
         kwt_task<HY>(d, S[team], active ? deferList[i] : 0, active, w, tau0);
+        MR_WSYNC();
+    }
+}
+
+// a whole (small) wavefront on teams: positions [lo, hi).  Below a few ten thousand tasks a wavefront is bound by the latency
+// of its slowest task, not by throughput, and one launch of the cooperative code is the shortest chain.
+template <bool HY = false>
+__global__ void __launch_bounds__(32 * KWT_WARPS, KWT_MIN_BLOCKS) k_route_kwt_range(DevNet d, int lo, int hi, int w, long long tau0) {
+    __shared__ KwtScratchSmall S[KWT_TEAMS];
+    const int team = threadIdx.x / MR_TEAM;
+    for (int base = lo + blockIdx.x * KWT_TEAMS; base < hi; base += gridDim.x * KWT_TEAMS) {
+        const int p = base + team;
+        kwt_task<HY>(d, S[team], p, p < hi, w, tau0);
         MR_WSYNC();
     }
 }

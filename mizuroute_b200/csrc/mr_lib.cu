@@ -44,6 +44,7 @@ struct mr_handle_s {
     double timing[8] = {0};
     cudaStream_t stream = nullptr, ownStream = nullptr;
     cudaEvent_t ev[10] = {nullptr};
+    cudaStream_t kwSide = nullptr; cudaEvent_t kwEv[2] = {nullptr, nullptr};   // KWT: team kernel of the special tasks beside the heavy pass
     cudaStream_t aux[N_METHODS - 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // the routing methods of route_opt are independent: all but the last run on these
     cudaEvent_t mev[N_METHODS][2] = {};          // start / end of each method
     unsigned *dKwCount = nullptr;
@@ -51,7 +52,7 @@ struct mr_handle_s {
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
     int *dRch2pos = nullptr;
     size_t basinSmem = 0;
-    int kwtGridMax = 148 * 8;                    // one resident wave of k_route_kwt blocks
+    int kwtGridMax = 148 * 8, kwsGridMax = 148 * 5;      // one resident wave of k_route_kwt_team / k_route_kwt_heavy blocks
     // runoff remapping (mr_set_remap): forcing arrives on nForcing polygons, k_remap fills dRunoffNet [max_batch][nHRU]
     int nForcing = 0, nMap = 0;
     double *dRunoffNet = nullptr, *dOvW = nullptr;
@@ -202,20 +203,52 @@ void launch_wavefront(mr_handle h, cudaStream_t st, int w, int K, long long tau0
     const int lo = T.stagePtr[slo], hi = T.stagePtr[shi + 1];
     if (hi <= lo) return;                        // stages that hold only headwaters
     if constexpr (M == M_KWT) {
-        // thread-per-task pass over the wavefront, then the tasks it deferred on teams (one resident wave of blocks at most:
-        // their number is known on the device only)
+        // lane-per-task pass over the wavefront (k_route_kwt_light), then the tasks that must thin or whose waves break
+        // (k_route_kwt_heavy) while, on a side stream, teams route what the light pass found to be special (lakes, ghosts,
+        // water management, exported outlets, wide confluences: list T1); last, on teams again, the few the heavy pass gave up
+        // on (list T2, mostly empty).  The sizes of the lists are known on the device only: one resident wave of blocks at
+        // most, grid-stride.
         const bool ext = h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive;
-        int *cnt = h->dKwDeferCnt + w;
-        const int gridS = (hi - lo + KWS_TPB - 1) / KWS_TPB;
+        int *cntH = h->dKwDeferCnt + 3 * w, *cntT1 = cntH + 1, *cntT2 = cntH + 2;
+        int *listH = h->dKwDeferList, *listT1 = listH + h->d.nRch, *listT2 = listT1 + h->d.nRch;
+        const int gridL = (hi - lo + 31) / 32;
+        int gridH = gridL < h->kwsGridMax ? gridL : h->kwsGridMax;
         int gridT = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
         if (gridT > h->kwtGridMax) gridT = h->kwtGridMax;
-        if (ext) {
-            k_route_kwt_scalar<true><<<gridS, KWS_TPB, 0, st>>>(h->d, lo, hi, w, tau0, cnt, h->dKwDeferList);
-            k_route_kwt_team<true><<<gridT, 32 * KWT_WARPS, 0, st>>>(h->d, cnt, h->dKwDeferList, w, tau0);
-        } else {
-            k_route_kwt_scalar<false><<<gridS, KWS_TPB, 0, st>>>(h->d, lo, hi, w, tau0, cnt, h->dKwDeferList);
-            k_route_kwt_team<false><<<gridT, 32 * KWT_WARPS, 0, st>>>(h->d, cnt, h->dKwDeferList, w, tau0);
+        // By size (MR_KWT_SMALL / MR_KWT_LARGE: tuning knobs): a small wavefront is one launch of the team code over its
+        // positions (latency-bound: the shortest chain wins); in a very large one the thinning tasks go to the teams as well
+        // (throughput-bound: the team code routes a thinning task in fewer cycles than a lane does).
+        static const int nSmall = std::getenv("MR_KWT_SMALL") ? std::atoi(std::getenv("MR_KWT_SMALL")) : 49152;
+        static const int nLarge = std::getenv("MR_KWT_LARGE") ? std::atoi(std::getenv("MR_KWT_LARGE")) : 65536;
+        if (hi - lo < nSmall) {
+            const int grid = (hi - lo + KWT_TEAMS - 1) / KWT_TEAMS;
+            if (ext) k_route_kwt_range<true><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+            else k_route_kwt_range<false><<<grid, 32 * KWT_WARPS, 0, st>>>(h->d, lo, hi, w, tau0);
+            h->launchesLast++;
+            return;
         }
+        const bool noHeavy = hi - lo >= nLarge;
+        if (noHeavy) { cntH = cntT1; listH = listT1; }
+        cudaStream_t side = h->kwSide;
+        if (ext) k_route_kwt_light<true><<<gridL, 32 * KWS_WPB, 0, st>>>(h->d, lo, hi, w, tau0, cntH, listH, cntT1, listT1);
+        else k_route_kwt_light<false><<<gridL, 32 * KWS_WPB, 0, st>>>(h->d, lo, hi, w, tau0, cntH, listH, cntT1, listT1);
+        cudaEventRecord(h->kwEv[0], st);
+        cudaStreamWaitEvent(side, h->kwEv[0], 0);
+        if (ext) k_route_kwt_team<true><<<gridT, 32 * KWT_WARPS, 0, side>>>(h->d, cntT1, listT1, w, tau0);
+        else k_route_kwt_team<false><<<gridT, 32 * KWT_WARPS, 0, side>>>(h->d, cntT1, listT1, w, tau0);
+        cudaEventRecord(h->kwEv[1], side);
+        if (!noHeavy) {
+            if (ext) k_route_kwt_heavy<true><<<gridH, 32 * KWS_WPB, 0, st>>>(h->d, cntH, listH, w, tau0, cntT2, listT2);
+            else k_route_kwt_heavy<false><<<gridH, 32 * KWS_WPB, 0, st>>>(h->d, cntH, listH, w, tau0, cntT2, listT2);
+        }
+        cudaStreamWaitEvent(st, h->kwEv[1], 0);
+        if (!noHeavy) {
+            const int gridT2 = gridT < 2 * h->kwtGridMax / 8 ? gridT : 2 * h->kwtGridMax / 8;
+            if (ext) k_route_kwt_team<true><<<gridT2, 32 * KWT_WARPS, 0, st>>>(h->d, cntT2, listT2, w, tau0);
+            else k_route_kwt_team<false><<<gridT2, 32 * KWT_WARPS, 0, st>>>(h->d, cntT2, listT2, w, tau0);
+            h->launchesLast++;
+        }
+        h->launchesLast += 2;
         h->launchesLast++;
     } else {
         if (h->hasHype || h->hasH06 || h->wmActive || h->lakeForcingActive || h->daActive) k_route<M, true><<<(hi - lo + 255) / 256, 256, 0, st>>>(h->d, lo, hi, w, tau0);
@@ -359,7 +392,7 @@ int route_device(mr_handle h, int K, double T0, const char *where, char *message
         }
     }
     for (int r = 0; r < nr; ++r)
-        if (h->opt.route_methods[r] == M_KWT) CU(cudaMemsetAsync(h->dKwDeferCnt, 0, sizeof(int) * ((size_t)h->topo.nStage + K), st[r]));
+        if (h->opt.route_methods[r] == M_KWT) CU(cudaMemsetAsync(h->dKwDeferCnt, 0, sizeof(int) * 3 * ((size_t)h->topo.nStage + K), st[r]));
     for (int w = 0; w < h->topo.nStage + K - 1; ++w)
         for (int r = 0; r < nr; ++r)
             switch (h->opt.route_methods[r]) {
@@ -441,6 +474,8 @@ int mr_create(const mr_options *opts, mr_handle *out, char *message) {
     for (int i = 0; i < 10 && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->ev[i]);
     for (int i = 0; i < N_METHODS - 1 && ce == cudaSuccess; ++i) ce = cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking);
     for (int i = 0; i < 2 * N_METHODS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&h->mev[i / 2][i % 2]);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&h->kwSide, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && ce == cudaSuccess; ++i) ce = cudaEventCreateWithFlags(&h->kwEv[i], cudaEventDisableTiming);
     if (ce != cudaSuccess) { delete h; CU(ce); }
     put_msg(message, "");
     *out = h;
@@ -581,11 +616,17 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         AL(kK, N); AL(kAK, N);
         k_kwt_params<<<(N + 255) / 256, 256, 0, h->stream>>>(N, d.rslope, d.rmann, kK, kAK);
         d.kwK = kK; d.kwAK = kAK;
+        {
+            KwsRec *rec = nullptr;
+            AL(rec, N);
+            k_kws_records<<<(N + 255) / 256, 256, 0, h->stream>>>(d, rec);
+            d.kwRec = rec;
+        }
         KwtScratch *arena = nullptr; unsigned long long *amask = nullptr;
         AL(arena, (size_t)KWT_ARENA_SMS * KWT_ARENA_SLOTS); AL(amask, KWT_ARENA_SMS);
         d.kwArena = arena; d.kwArenaMask = amask;
-        if (std::getenv("MR_KWT_PROFILE")) { unsigned long long *pr = nullptr; AL(pr, 16); d.kwProf = pr; }
-        AL(h->dKwDeferCnt, (size_t)T.nStage + KB + 1); AL(h->dKwDeferList, N);
+        if (std::getenv("MR_KWT_PROFILE")) { unsigned long long *pr = nullptr; AL(pr, 40); d.kwProf = pr; }
+        AL(h->dKwDeferCnt, 3 * ((size_t)T.nStage + KB + 1)); AL(h->dKwDeferList, 3 * (size_t)N);
         for (int b = 0; b < 2; ++b) {
             AL(d.kwN[b], N); AL(d.kwNR[b], N);
             AL(d.kwQF[b], (size_t)KWP * N); AL(d.kwTI[b], (size_t)KWP * N); AL(d.kwTR[b], (size_t)KWP * N);
@@ -675,6 +716,9 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
         cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, o.device);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_route_kwt_team<false>, 32 * KWT_WARPS, 0) != cudaSuccess || perSM < 1) perSM = 8;
         h->kwtGridMax = nSM * perSM;               // one resident wave of team blocks, grid-stride over the deferred list
+        int perSMh = 5;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMh, k_route_kwt_heavy<false>, 32 * KWS_WPB, 0) != cudaSuccess || perSMh < 1) perSMh = 5;
+        h->kwsGridMax = nSM * perSMh;
         // tuning knob (development): MR_KWT_WAVES = resident waves the KWT grid may span; 0 = one block per KWT_TEAMS tasks
         if (const char *ev = std::getenv("MR_KWT_WAVES")) {
             const double wv = std::atof(ev);
@@ -1487,8 +1531,14 @@ void mr_destroy(mr_handle h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->hasNet && h->d.kwProf) {                  // MR_KWT_PROFILE=1: cycles per task class (development)
-        unsigned long long pr[16];
+        unsigned long long pr[40];
         if (copy_sync(h, pr, h->d.kwProf, sizeof(pr), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char *ph[8] = {"per-task: gather + merge decisions", "pool build", "pool: merged flows", "per-task: thinning", "pool build", "pool: kinwav", "per-task: time average", "pool: stores"};
+            for (int k = 0; k < 2; ++k) {
+                double tp = 0; for (int c = 0; c < 8; ++c) tp += (double)pr[16 + 8 * k + c];
+                for (int c = 0; c < 8; ++c) if (tp > 0) std::fprintf(stderr, "kwt %s phase %-36s %5.1f%% of the block cycles\n", k ? "heavy" : "light", ph[c], 100.0 * pr[16 + 8 * k + c] / tp);
+                if (pr[32 + k]) std::fprintf(stderr, "kwt %s blocks %llu, cycles per block %.0f\n", k ? "heavy" : "light", pr[32 + k], tp / pr[32 + k]);
+            }
             static const char *nm[8] = {"n=0", "n<=3", "n<=6", "n<=12", "n<=20", "n<=40", "n>40", "retry"};
             double tot = 0; for (int c = 0; c < 8; ++c) tot += (double)pr[2 * c];
             for (int c = 0; c < 8; ++c) if (pr[2 * c + 1])
@@ -1499,6 +1549,8 @@ void mr_destroy(mr_handle h) {
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     for (auto &m : h->mev) for (auto &e : m) if (e) cudaEventDestroy(e);
     for (auto &a : h->aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
+    if (h->kwSide) { cudaStreamSynchronize(h->kwSide); cudaStreamDestroy(h->kwSide); }
+    for (auto &e : h->kwEv) if (e) cudaEventDestroy(e);
     for (cudaStream_t c : {h->copyIn, h->copyOut}) if (c) { cudaStreamSynchronize(c); cudaStreamDestroy(c); }
     for (cudaEvent_t ev : {h->evIn[0], h->evIn[1], h->evFree[0], h->evFree[1], h->evOut, h->evD2H}) if (ev) cudaEventDestroy(ev);
     if (h->ownStream) cudaStreamDestroy(h->ownStream);

@@ -18,9 +18,9 @@ using namespace mr;
 
 // mode 0: scalar path first, team path for what it defers (as on the device); 1: team path only
 static int g_mode = 0;
-static long g_scalar_done = 0, g_deferred = 0;
+static long g_scalar_done = 0, g_heavy_done = 0, g_deferred = 0;
 extern "C" void kwt_emul_set_mode(int mode) { g_mode = mode; }
-extern "C" long kwt_emul_count(int which) { return which == 0 ? g_scalar_done : g_deferred; }
+extern "C" long kwt_emul_count(int which) { return which == 0 ? g_scalar_done : (which == 1 ? g_deferred : g_heavy_done); }
 
 extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *downSegId, const int *hruSegId, const double *hruArea,
                             const double *length, const double *slope, double mann_n, double wscale, double dt, int nSteps,
@@ -55,6 +55,9 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     d.T0s = T0s.data(); d.T1s = T1s.data();
     for (int b = 0; b < 2; ++b) { d.kwN[b] = kwN[b].data(); d.kwNR[b] = kwNR[b].data(); d.kwQF[b] = kwQF[b].data(); d.kwTI[b] = kwTI[b].data(); d.kwTR[b] = kwTR[b].data(); }
     d.err = err; d.kwCount = nullptr;
+    std::vector<KwsRec> recs(N);
+    for (int p = 0; p < N; ++p) recs[p] = kws_make_record(d, p);            // k_kws_records
+    d.kwRec = recs.data();
     double t0 = 0.0, t1 = dt;
     for (int t = 0; t < nSteps; ++t) { T0s[t] = t0; T1s[t] = t1; t0 = t1; t1 = t0 + dt; }
     std::vector<double> fS;
@@ -66,8 +69,9 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
     static KwtScratch S;
     static KwtScratchSmall Ssmall;
     long retries = 0;
-    g_scalar_done = g_deferred = 0;
-    std::vector<double> colQ(KWS_NL), colT(KWS_NL);
+    g_scalar_done = g_heavy_done = g_deferred = 0;
+    static KwsWarp<KWS_NL, false> WL;                   // one-lane "warps" of the light and the heavy instantiation
+    static KwsWarp<KWS_NH, true> WH;
     for (int t = 0; t < nSteps; ++t) {
         const int b = t & 1;
         for (int p = 0; p < T.nHead; ++p) {                 // k_headwater<M_KWT>
@@ -75,10 +79,15 @@ extern "C" int kwt_emul_run(int nRch, int nHRU, const int *segId, const int *dow
             kwN[b][p] = 1; kwNR[b][p] = 0;
         }
         for (int p = T.nHead; p < N; ++p) {                 // stage order: upstream before downstream
-            if (g_mode == 0) {                              // thread-per-task path; what it has written before deferring is rewritten below
-                const int rc = wm_flux ? kwt_reach_scalar<true, 1>(d, colQ.data(), colT.data(), p, t, (long long)t, T0s[t], T1s[t])
-                                       : kwt_reach_scalar<false, 1>(d, colQ.data(), colT.data(), p, t, (long long)t, T0s[t], T1s[t]);
+            if (g_mode == 0) {                              // lane-per-task paths (light, then heavy); what they have written before giving up is rewritten below
+                int rc = wm_flux ? kws_warp_route<true, KWS_NL, false>(d, WL, p, t, (long long)t, T0s[t], T1s[t], true)
+                                 : kws_warp_route<false, KWS_NL, false>(d, WL, p, t, (long long)t, T0s[t], T1s[t], true);
                 if (rc == KWS_DONE) { ++g_scalar_done; continue; }
+                if (rc == KWS_HEAVY) {
+                    rc = wm_flux ? kws_warp_route<true, KWS_NH, true>(d, WH, p, t, (long long)t, T0s[t], T1s[t], true)
+                                 : kws_warp_route<false, KWS_NH, true>(d, WH, p, t, (long long)t, T0s[t], T1s[t], true);
+                    if (rc == KWS_DONE) { ++g_heavy_done; continue; }
+                }
                 ++g_deferred;
             }
             // the shared-memory-sized scratch first, the full-capacity one on KWT_RETRY -- as k_route_kwt does

@@ -35,7 +35,7 @@ def _emul_vs_oracle(net, params, opts, ro, mode=0):
     L.kwt_emul_set_mode(C.c_int(0))
     assert ierr == 0, msg.value.decode()
     _emul_vs_oracle.retries = int(msg.value.decode().split("=")[1])
-    _emul_vs_oracle.scalar, _emul_vs_oracle.deferred = int(L.kwt_emul_count(0)), int(L.kwt_emul_count(1))
+    _emul_vs_oracle.scalar, _emul_vs_oracle.deferred, _emul_vs_oracle.heavy = int(L.kwt_emul_count(0)), int(L.kwt_emul_count(1)), int(L.kwt_emul_count(2))
     return o, qo, qe, ne
 
 
@@ -52,11 +52,11 @@ def test_team_kwt_bit_exact_vs_oracle(kind, n, dt, steps, mode):
         assert orc.lib().mro_counter(0) > 0, "thinning was not exercised"
         if dt < 86400.0:
             assert orc.lib().mro_counter(1) > 0, "wave breaking was not exercised"
-        if mode == 0:                                        # both paths carry a real share of the tasks
-            assert _emul_vs_oracle.scalar > 0.3 * (_emul_vs_oracle.scalar + _emul_vs_oracle.deferred)
-            assert _emul_vs_oracle.deferred > 0
+        if mode == 0:                                        # all three paths carry a real share of the tasks
+            assert _emul_vs_oracle.scalar > 0.3 * (_emul_vs_oracle.scalar + _emul_vs_oracle.heavy + _emul_vs_oracle.deferred)
+            assert _emul_vs_oracle.heavy > 0 and _emul_vs_oracle.deferred > 0
     if mode == 1:
-        assert _emul_vs_oracle.scalar == 0
+        assert _emul_vs_oracle.scalar == 0 and _emul_vs_oracle.heavy == 0
     assert np.array_equal(qe, qo)
     assert np.array_equal(ne, o.get_state()["kwt_n"])
 
