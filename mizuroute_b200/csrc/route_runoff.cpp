@@ -198,7 +198,7 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
     for (int r = 0; r < o.n_routes; ++r) { irf |= o.route_methods[r] == MR_IMPULSE_RESPONSE_FUNC; kwt |= o.route_methods[r] == MR_KINEMATIC_WAVE_TRACKING; }
     nc3::Writer w(path);
     const int dSeg = w.def_dim("seg", N), dTdh = w.def_dim("tdh", nb), dIrf = w.def_dim("tdh_irf", mx), dWave = w.def_dim("wave", W), dTb = w.def_dim("tbound", 2);
-    const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}), vTb = w.def_var("time_bound", nc3::NC_DOUBLE, {dTb}, {{"units", "s"}, {"long_name", "TSEC(1:2) of the next step; tbound 0 / dt_qsim = steps done"}});
+    const int vId = w.def_var("reachID", nc3::NC_INT, {dSeg}), vTb = w.def_var("time_bound", nc3::NC_DOUBLE, {dTb}, {{"units", "sec"}, {"long_name", "time bound at last time step"}});      // TSEC(1:2) of the step just completed (write_restart_pio.f90:327,812; stored in double here, ncd_float there)
     const int vBq = w.def_var("basin_q", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3/s"}}), vQf = w.def_var("qfuture", nc3::NC_DOUBLE, {dTdh, dSeg}, {{"units", "m3/s"}});
     int vNqf = -1, vIq = -1, vIv = -1, vNw = -1, vTe = -1, vTx = -1, vQw = -1, vQm = -1, vRt = -1, vKv = -1;
     if (irf) { vNqf = w.def_var("numQF", nc3::NC_INT, {dSeg}); vIq = w.def_var("irf_qfuture", nc3::NC_DOUBLE, {dIrf, dSeg}, {{"units", "m3/s"}}); vIv = w.def_var("volume_irf", nc3::NC_DOUBLE, {dSeg}, {{"units", "m3"}}); }
@@ -221,7 +221,7 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
     if (da) for (int q = 0; q < o.n_routes; ++q) { const int m = o.route_methods[q]; if (qerrName[m]) vQerr[m] = w.def_var(qerrName[m], nc3::NC_DOUBLE, {dSeg}, {{"units", "m3/s"}}); }
     w.end_def();
     w.put_int(vId, segId.data());
-    const double tb[2] = {T0, T0 + o.dt}; w.put_double(vTb, tb); (void)steps;
+    const double tb[2] = {T0 - o.dt, T0}; w.put_double(vTb, tb); (void)steps;      // T0 = TSEC(1) of the NEXT step: the file holds the last step's bounds
     auto transposed = [&](const std::vector<double> &a, int ncol) { std::vector<double> t(a.size()); for (size_t r = 0; r < N; ++r) for (int k = 0; k < ncol; ++k) t[(size_t)k * N + r] = a[r * ncol + k]; return t; };
     std::vector<double> a((size_t)N * std::max(std::max(nb, mx), W)), b(N);
     a.resize((size_t)N * 2); check(mr_get_state(h, MR_ST_BASIN_QR, a.data(), (long)a.size() * 8, msg), msg);
@@ -276,7 +276,8 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
     const int nb = (int)mr_get_info(h, MR_INFO_NTDH_BAS), mx = (int)mr_get_info(h, MR_INFO_MAXTDH), W = MR_KW_SLOTS;
     if ((int)r.dim_len("tdh") != nb) die(20, "read_state_nc/tdh of the restart file differs from the hillslope UH length");
     std::vector<double> tb; r.read_all(r.var("time_bound"), tb);
-    const long steps = std::lround(tb[0] / o.dt);
+    // the time bound is that of the step before the restart, the run continues one step later (init_model_data.f90:607-608)
+    const long steps = std::lround(tb[1] / o.dt);
     check(mr_set_steps_done(h, steps, msg), msg);
     auto rowmajor = [&](const std::vector<double> &t, int ncol) { std::vector<double> a(t.size()); for (size_t q = 0; q < N; ++q) for (int k = 0; k < ncol; ++k) a[q * ncol + k] = t[(size_t)k * N + q]; return a; };
     std::vector<double> t, a;
@@ -322,7 +323,7 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
         }
         check(mr_set_state(h, MR_ST_QERROR, qe.data(), (long)qe.size() * 8, msg), msg);
     }
-    return tb[0];
+    return tb[0] + o.dt;
 }
 
 }  // namespace

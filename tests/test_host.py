@@ -317,7 +317,7 @@ def test_restart_files_written_during_the_run_continue_it_exactly(tmp_path, back
     assert [os.path.basename(f) for f in rfiles] == ["full.r.2000-03-02-00000.nc", "full.r.2000-03-03-00000.nc", "full.r.2000-03-04-00000.nc", "full.r.2000-03-05-00000.nc"]
     h_full = casefiles.read_history(next(x["history"] for x in lines if "history" in x))
     k0 = 6                                                                  # 2000-03-03 00:00 = 6 steps after the start
-    assert casefiles.read_history(rfiles[1])["time_bound"][0] == k0 * 21600.0
+    assert list(casefiles.read_history(rfiles[1])["time_bound"]) == [(k0 - 1) * 21600.0, k0 * 21600.0]      # TSEC(1:2) of the last step routed (write_restart_pio.f90:812)
     ctl = casefiles.write_case(d, net, params, opts, ro[k0:], case_name="cont", start="2000-03-01 12:00:00", first_step=k0, fname_state_in=os.path.basename(rfiles[1]))
     r = run(ctl); assert r.returncode == 0, r.stderr
     h_cont = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
