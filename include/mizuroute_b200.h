@@ -199,6 +199,14 @@ int mr_set_sim_start(mr_handle h, int year, int month, int day, double secOfDay,
 int mr_download_q(mr_handle h, int nSteps, double *q_out, char *message);
 /* BASIN_QR(1) ("dlayRunoff", the hillslope-routed lateral inflow) of the last batch as [nSteps][nRch] */
 int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message);
+/* History aggregation on the device (histVars_data.f90:154-246, aggregate / finalize): the period means of REACH_Q of every
+ * routing method (route_opt order) and, with wantDlay, of BASIN_QR(1) over consecutive groups of nAgg steps, formed from the
+ * first nSteps steps of the LAST batch in step order and rounded to float32, the history file's type.  A period may span
+ * calls: the sums and the number of steps in them stay on the device.  flush != 0 also closes the period still open after
+ * the last step (the end of the run).  out receives [nPeriods][n_routes (+1)][nRch] in the caller's reach order, at most
+ * maxPeriods periods (ierr 1 if more complete); *nPeriods = periods written.  The device -> host copy is nPeriods records
+ * instead of nSteps: with daily means of hourly steps 1/48 of the bytes of mr_download_q. */
+int mr_history_means(mr_handle h, int nSteps, int nAgg, int wantDlay, int flush, int maxPeriods, float *out, int *nPeriods, char *message);
 /* mr_route_resident without the final wait: the kernels are enqueued on the handle's stream and the call returns,
  * so a caller can keep several domains (tributaries of the next batch, mainstem of this one) in flight on
  * different streams.  mr_wait blocks until the stream is idle and reports a device-side error (ierr, message). */

@@ -426,6 +426,26 @@ __global__ void k_import_unpack(DevNet d, const int *impPos, int nImp, int K) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// history aggregation (histVars_data.f90:154-246): period means of one per-step series of a batch, thread per reach.  The sum
+// of a period is formed in step order in double precision (the reference's `this%discharge = this%discharge + REACH_Q`),
+// divided by the number of steps and rounded to float32; a period open at the end of the batch stays in acc / count.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_history(const double *rows, double *acc, float *out, const int *pos2rch, int N, int K, int nAgg, int nAcc0, int series, int nSeries, int flush) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const int r = pos2rch[p];
+    double a = acc[p];
+    int c = nAcc0, per = 0;
+    for (int t = 0; t < K; ++t) {
+        if (c == 0) a = 0.0;
+        a = a + rows[(size_t)t * N + p];
+        if (++c == nAgg) { out[((size_t)per * nSeries + series) * N + r] = (float)(a / (double)c); ++per; c = 0; }
+    }
+    if (flush && c > 0) out[((size_t)per * nSeries + series) * N + r] = (float)(a / (double)c);
+    acc[p] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
 // order conversion: stage order <-> caller's reach order
 // ------------------------------------------------------------------------------------------------
 // out[row][rch] = in[row][pos(rch)]; rows = methods x steps

@@ -50,7 +50,9 @@ struct mr_handle_s {
     unsigned *dKwCount = nullptr;
     int *dKwDeferCnt = nullptr, *dKwDeferList = nullptr;   // KWT: per-wavefront count and list of the tasks the thread-per-task kernel deferred
     double *dRunoff = nullptr, *dT0s = nullptr, *dT1s = nullptr, *dOut = nullptr;
-    int *dRch2pos = nullptr;
+    int *dRch2pos = nullptr, *dPos2rch = nullptr;
+    // history aggregation on the device (mr_history_means): sums of the open period per series, steps in them, staging of the means
+    double *dHistAcc = nullptr; float *dHistOut = nullptr; size_t histOutCap = 0; int histCount = 0;
     size_t basinSmem = 0;
     int kwtGridMax = 148 * 8, kwsGridMax = 148 * 5;      // one resident wave of k_route_kwt_team / k_route_kwt_heavy blocks
     // runoff remapping (mr_set_remap): forcing arrives on nForcing polygons, k_remap fills dRunoffNet [max_batch][nHRU]
@@ -707,6 +709,8 @@ int mr_set_network(mr_handle h, int nRch, int nHRU, const int *segId, const int 
     AL(h->dT0s, KB); AL(h->dT1s, KB);
     AL(h->dOut, (size_t)o.n_routes * KB * N);
     e = dev_upload(h, &h->dRch2pos, T.rch2pos, where, message); if (e) return e;
+    e = dev_upload(h, &h->dPos2rch, T.pos2rch, where, message); if (e) return e;
+    h->dHistAcc = nullptr; h->dHistOut = nullptr; h->histOutCap = 0; h->histCount = 0;
     d.runoff = h->dRunoff; d.T0s = h->dT0s; d.T1s = h->dT1s;
 #undef UP
 #undef AL
@@ -961,6 +965,31 @@ int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message) 
     k_unpermute_rows<<<grid, 256, 0, h->stream>>>(h->d.qrSer + N, h->dOut, h->dRch2pos, N, nSteps);      // rows 1..nSteps = BASIN_QR(1) after each step
     CU(cudaMemcpyAsync(qr_out, h->dOut, sizeof(double) * (size_t)nSteps * N, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_history_means(mr_handle h, int nSteps, int nAgg, int wantDlay, int flush, int maxPeriods, float *out, int *nPeriods, char *message) {
+    const char *where = "mr_history_means";
+    int e = check_ready(h, nSteps, where, message); if (e) return e;
+    if (!out || !nPeriods || nAgg < 1 || maxPeriods < 0) return fail(message, 1, "mr_history_means/invalid arguments");
+    if (nSteps > h->lastK) return fail(message, 1, "mr_history_means/more steps requested than the last batch routed");
+    const int N = h->d.nRch, nSeries = h->opt.n_routes + (wantDlay ? 1 : 0);
+    const int total = h->histCount + nSteps;
+    const int nPer = total / nAgg + ((flush && total % nAgg) ? 1 : 0);
+    if (nPer > maxPeriods) return fail(message, 1, "mr_history_means/more periods complete than the output buffer holds");
+    if (!h->dHistAcc) { e = dev_alloc(h, &h->dHistAcc, (size_t)(h->opt.n_routes + 1) * N, where, message); if (e) return e; }
+    const size_t need = (size_t)(nPer > 0 ? nPer : 1) * nSeries * N;
+    if (need > h->histOutCap) { e = dev_alloc(h, &h->dHistOut, need, where, message, false); if (e) return e; h->histOutCap = need; }   // (the smaller one stays until mr_destroy)
+    for (int s = 0; s < nSeries; ++s) {
+        const double *rows = s < h->opt.n_routes ? h->d.qSer[h->opt.route_methods[s]] : h->d.qrSer + N;       // rows 1.. = BASIN_QR(1) after each step
+        k_history<<<(N + 255) / 256, 256, 0, h->stream>>>(rows, h->dHistAcc + (size_t)s * N, h->dHistOut, h->dPos2rch, N, nSteps, nAgg, h->histCount, s, nSeries, flush ? 1 : 0);
+        h->launchesLast++;
+    }
+    CU(cudaGetLastError());
+    CU(copy_sync(h, out, h->dHistOut, sizeof(float) * (size_t)nPer * nSeries * N, cudaMemcpyDeviceToHost));
+    h->histCount = flush ? 0 : total % nAgg;
+    *nPeriods = nPer;
     put_msg(message, "");
     return 0;
 }

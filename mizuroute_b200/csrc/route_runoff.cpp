@@ -1,7 +1,7 @@
 // route_runoff -- stand-alone host of the B200 routing library, the counterpart of the reference's
 // PROGRAM route_runoff (route/build/src/standalone/route_runoff.f90:5-117):
 //
-//     route_runoff <control file> [--batch N] [--device-ingest] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]
+//     route_runoff <control file> [--batch N] [--device-ingest] [--device-history] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]
 //
 //   init_model      read_control (read_control.f90:18: lines "<key> value ! comment", '!' comment lines, unknown key =
 //                   error) and the parameter namelist &HSLOPE/&IRF_UH/&KWT (read_param.f90:12)
@@ -329,13 +329,14 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
 }  // namespace
 
 int main(int argc, char **argv) {
-    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--device-ingest] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: route_runoff <control file> [--batch N] [--device-ingest] [--device-history] [--dry-run [--dump-forcing FILE] [--dump-remap FILE]]\n"); return 2; }
     const std::string cfile = argv[1];
-    int batch = 64; bool dry = false, deviceIngest = false; std::string dumpForcing, dumpRemap;
+    int batch = 64; bool dry = false, deviceIngest = false, deviceHistory = false; std::string dumpForcing, dumpRemap;
     for (int i = 2; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--batch") && i + 1 < argc) batch = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--dry-run")) dry = true;
         else if (!std::strcmp(argv[i], "--device-ingest")) deviceIngest = true;       // forcing records -> runoff rows on the device (mr_ingest_records)
+        else if (!std::strcmp(argv[i], "--device-history")) deviceHistory = true;     // period means of the history file on the device (mr_history_means)
         else if (!std::strcmp(argv[i], "--dump-forcing") && i + 1 < argc) dumpForcing = argv[++i];
         else if (!std::strcmp(argv[i], "--dump-remap") && i + 1 < argc) dumpRemap = argv[++i];
         else die(2, std::string("unknown argument ") + argv[i]);
@@ -888,6 +889,15 @@ int main(int argc, char **argv) {
             }
         };
         int nAcc = 0; size_t recOut = 0, fileNo = 0; double tAcc = 0.0;
+        // --device-history: the period means of the discharges and of dlayRunoff are formed on the device (mr_history_means,
+        // histVars_data.f90:154-246) and only they travel to the host -- one record per output period instead of one per step.
+        // Taken when the output is aggregated and asks for nothing the library would have to hand over step by step.
+        const bool devHist = deviceHistory && nAgg > 1 && !anyStep && !anyVol;
+        if (deviceHistory && !devHist) std::fprintf(stderr, "route_runoff: --device-history needs <outputFrequency> > 1 and no per-step / volume variables; the host aggregates\n");
+        const int nSer = o.n_routes + (wantDlay ? 1 : 0);
+        std::vector<float> hist(devHist ? (size_t)(batch / nAgg + 2) * nSer * nRch : 0);
+        std::vector<double> histRow(devHist ? nRch : 0);
+        int histPer = 0;
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
@@ -923,11 +933,16 @@ int main(int argc, char **argv) {
             if (deviceIngest) {
                 if (wantBas) ingest_batch(s, nb);                              // <basRunoff> wants the rows on the host as well
                 ierr = mr_route_resident(h, nb, T0, msg); if (ierr) die(ierr, msg);
-                ierr = mr_download_q(h, nb, q.data(), msg); if (ierr) die(ierr, msg);
+                if (!devHist) { ierr = mr_download_q(h, nb, q.data(), msg); if (ierr) die(ierr, msg); }
             } else {
-                ierr = mr_step_batch(h, nb, T0, ro.data(), q.data(), msg); if (ierr) die(ierr, msg);
+                ierr = mr_step_batch(h, nb, T0, ro.data(), devHist ? nullptr : q.data(), msg); if (ierr) die(ierr, msg);
             }
-            if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
+            if (devHist) {
+                int nPer = 0;
+                ierr = mr_history_means(h, nb, nAgg, wantDlay ? 1 : 0, s + nb == nSteps ? 1 : 0, (int)(hist.size() / ((size_t)nSer * nRch)), hist.data(), &nPer, msg);
+                if (ierr) die(ierr, msg);
+                histPer = 0;
+            } else if (wantDlay) { ierr = mr_download_basin_q(h, nb, qd.data(), msg); if (ierr) die(ierr, msg); }
             if (anyStep) {                                                     // nb == 1: REACH_INFLOW / BASIN_QI of this step
                 for (int r = 0; r < o.n_routes; ++r) if (wantInf[r]) { ierr = mr_get_flux(h, o.route_methods[r], MR_REACH_INFLOW, &stepX[(size_t)r * nRch], msg); if (ierr) die(ierr, msg); }
                 if (wantInst) { ierr = mr_get_flux(h, o.route_methods[0], MR_BASIN_QI, &stepX[(size_t)o.n_routes * nRch], msg); if (ierr) die(ierr, msg); }
@@ -950,9 +965,15 @@ int main(int argc, char **argv) {
                 if (nAcc == 0) std::fill(accB.begin(), accB.end(), 0.0);
                 for (size_t i = 0; i < accX.size(); ++i) accX[i] += stepX[i];
                 for (size_t i = 0; i < accB.size(); ++i) accB[i] += ro[(size_t)k * inCols + i];
-                for (int r = 0; r < o.n_routes; ++r) for (size_t i = 0; i < nRch; ++i) acc[(size_t)r * nRch + i] += q[((size_t)r * nb + k) * nRch + i];
-                if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
+                if (!devHist) {
+                    for (int r = 0; r < o.n_routes; ++r) for (size_t i = 0; i < nRch; ++i) acc[(size_t)r * nRch + i] += q[((size_t)r * nb + k) * nRch + i];
+                    if (vDlay >= 0) for (size_t i = 0; i < nRch; ++i) acc[(size_t)o.n_routes * nRch + i] += qd[(size_t)k * nRch + i];
+                }
                 if (++nAcc == nAgg || s + k + 1 == nSteps) {
+                    if (devHist) {                      // the next period of this batch, as the device formed it (float32 values)
+                        for (int r = 0; r < nSer; ++r) { const float *src = &hist[((size_t)histPer * nSer + r) * nRch]; double *dst = &acc[(size_t)(r < o.n_routes ? r : o.n_routes) * nRch]; for (size_t i = 0; i < nRch; ++i) dst[i] = (double)src[i]; }
+                        ++histPer;
+                    } else
                     for (auto &v : acc) v /= (double)nAcc;
                     { const double ts = tAcc + stampOffset, tb[2] = {tAcc, tsec + o.dt}; w->put_record(vTime, recOut, &ts); w->put_record(vTb, recOut, tb); }
                     for (int r = 0; r < o.n_routes; ++r) if (vQ[r] >= 0) put_seg(vQ[r], recOut, &acc[(size_t)r * nRch]);

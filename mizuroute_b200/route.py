@@ -216,6 +216,18 @@ class Router:
         self._check(self._L.mr_download_basin_q(self._h, int(K), C.c_void_p(out.ctypes.data), self._msg))
         return out
 
+    def history_means(self, K: int, n_agg: int, want_dlay: bool = False, flush: bool = False) -> np.ndarray:
+        """Period means of REACH_Q per routing method (and of BASIN_QR(1) with want_dlay) over groups of n_agg steps, formed on
+        the device from the first K steps of the last batch and rounded to float32 (mr_history_means; histVars_data.f90:154-246).
+        A period may span calls; flush also closes the one still open.  Returns [nPeriods, n_routes (+1), nRch] float32."""
+        n_series = len(self.methods) + (1 if want_dlay else 0)
+        cap = int(K) // int(n_agg) + 2
+        out = np.empty((cap, n_series, self.nRch), dtype=np.float32)
+        n = C.c_int(0)
+        self._check(self._L.mr_history_means(self._h, int(K), int(n_agg), int(bool(want_dlay)), int(bool(flush)), cap, C.c_void_p(out.ctypes.data),
+                                             C.byref(n), self._msg))
+        return out[:n.value]
+
     @staticmethod
     def _host_ptr(a, ncol: int, rows: Optional[int] = None):
         if hasattr(a, "data_ptr"):                               # torch tensor (pinned host memory)

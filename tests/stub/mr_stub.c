@@ -29,6 +29,8 @@ struct mr_handle_s {
     double *ev, *pr; int epSteps;
     /* BASIN_QR(1) of the steps of the last batch */
     double *qr; int qrSteps;
+    /* REACH_Q of the last batch [route][step][reach] and the open history period (mr_history_means) */
+    double *qKeep; int qKeepSteps; double *histAcc; int histCount;
 };
 
 static void say(char *message, const char *txt)
@@ -85,6 +87,7 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
     if (h->epSteps && h->epSteps != nSteps) { say(message, "mr_step_batch/lake forcing was uploaded for a different number of steps"); return 1; }
     double *row = (double *)calloc((size_t)h->nHRU + 1, sizeof(double));
     free(h->qr); h->qr = (double *)malloc(sizeof(double) * (size_t)nSteps * (size_t)h->nRch); h->qrSteps = nSteps;
+    free(h->qKeep); h->qKeep = (double *)malloc(sizeof(double) * ((size_t)h->o.n_routes * (size_t)nSteps * (size_t)h->nRch + 1)); h->qKeepSteps = nSteps;
     for (t = 0; t < nSteps; t++) {
         const double *in = runoff + (size_t)t * (size_t)(h->nMap ? h->nForcing : h->nHRU);
         if (h->nMap) { mro_remap_1d(h->nMap, h->mapHru, h->numQ, h->qIx, h->wgt, in, row); in = row; }
@@ -93,8 +96,10 @@ int mr_step_batch(mr_handle h, int nSteps, double T0, const double *runoff, doub
         if (h->qmod == 1) mro_set_obs(h->m, (h->obsSteps && h->obsHas[t]) ? h->obs + (size_t)t * h->nRch : NULL);
         ierr = h->epSteps ? mro_step_ep(h->m, t0, t1, in, h->ev + (size_t)t * h->nHRU, h->pr + (size_t)t * h->nHRU) : mro_step(h->m, t0, t1, in);
         if (ierr) { char b[MR_STRLEN]; snprintf(b, sizeof b, "mr_step_batch/main_route/%s", mro_message(h->m)); say(message, b); free(row); return ierr; }
-        for (r = 0; r < h->m->nRoutes; r++)
-            memcpy(q_out + ((size_t)r * nSteps + t) * h->nRch, h->m->REACH_Q[h->m->routeOrder[r]], sizeof(double) * (size_t)h->nRch);
+        for (r = 0; r < h->m->nRoutes; r++) {
+            if (q_out) memcpy(q_out + ((size_t)r * nSteps + t) * h->nRch, h->m->REACH_Q[h->m->routeOrder[r]], sizeof(double) * (size_t)h->nRch);
+            memcpy(h->qKeep + ((size_t)r * nSteps + t) * h->nRch, h->m->REACH_Q[h->m->routeOrder[r]], sizeof(double) * (size_t)h->nRch);
+        }
         memcpy(h->qr + (size_t)t * h->nRch, h->m->BASIN_QR1, sizeof(double) * (size_t)h->nRch);
         t0 = t1; t1 = t0 + h->o.dt;
     }
@@ -213,6 +218,31 @@ int mr_download_basin_q(mr_handle h, int nSteps, double *qr_out, char *message)
 {
     if (nSteps > h->qrSteps) { say(message, "mr_download_basin_q/more steps than the last batch routed"); return 1; }
     memcpy(qr_out, h->qr, sizeof(double) * (size_t)nSteps * (size_t)h->nRch);
+    say(message, "");
+    return 0;
+}
+
+/* histVars_data.f90:154-246: sums in step order in double precision, mean, rounded to float32 */
+int mr_history_means(mr_handle h, int nSteps, int nAgg, int wantDlay, int flush, int maxPeriods, float *out, int *nPeriods, char *message)
+{
+    const size_t N = (size_t)h->nRch; const int nr = h->o.n_routes, nSeries = nr + (wantDlay ? 1 : 0);
+    int s, t, per = 0, c = 0; size_t i;
+    if (nSteps > h->qKeepSteps) { say(message, "mr_history_means/more steps requested than the last batch routed"); return 1; }
+    if (!h->histAcc) h->histAcc = (double *)calloc((size_t)(nr + 1) * N, sizeof(double));
+    if ((h->histCount + nSteps) / nAgg + ((flush && (h->histCount + nSteps) % nAgg) ? 1 : 0) > maxPeriods) { say(message, "mr_history_means/more periods complete than the output buffer holds"); return 1; }
+    for (s = 0; s < nSeries; s++) {
+        double *acc = h->histAcc + (size_t)s * N;
+        per = 0; c = h->histCount;
+        for (t = 0; t < nSteps; t++) {
+            const double *row = s < nr ? h->qKeep + ((size_t)s * h->qKeepSteps + t) * N : h->qr + (size_t)t * N;
+            if (c == 0) for (i = 0; i < N; i++) acc[i] = 0.0;
+            for (i = 0; i < N; i++) acc[i] = acc[i] + row[i];
+            if (++c == nAgg) { for (i = 0; i < N; i++) out[((size_t)per * nSeries + s) * N + i] = (float)(acc[i] / (double)c); per++; c = 0; }
+        }
+        if (flush && c > 0) { for (i = 0; i < N; i++) out[((size_t)per * nSeries + s) * N + i] = (float)(acc[i] / (double)c); per++; c = 0; }
+    }
+    h->histCount = c;
+    *nPeriods = per;
     say(message, "");
     return 0;
 }
@@ -344,6 +374,6 @@ void mr_destroy(mr_handle h)
 {
     if (!h) return;
     if (h->m) mro_destroy(h->m);
-    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr); free(h->ev); free(h->pr); free(h->wmF); free(h->wmV);
+    free(h->mapHru); free(h->numQ); free(h->qIx); free(h->wgt); free(h->qr); free(h->ev); free(h->pr); free(h->wmF); free(h->wmV); free(h->qKeep); free(h->histAcc);
     free(h);
 }

@@ -181,3 +181,31 @@ def test_errors_surface_as_ierr_message():
     with pytest.raises(RoutingError) as ei:          # zero flow aborts KWT (kwt_route.f90:1365-1368)
         r2.route_batch(np.zeros((1, net.nHRU)))
     assert ei.value.ierr == 20
+
+
+@pytest.mark.parametrize("n_agg,batch", [(24, 25), (5, 7), (1, 4)])
+def test_history_means_on_the_device_equal_host_aggregation(n_agg, batch):
+    """mr_history_means (k_history): period means of REACH_Q per method and of BASIN_QR(1) formed on the device -- sums in step
+    order in double precision, mean, float32 -- equal the same aggregation of the downloaded series bit for bit, for periods
+    that span batches and a last period closed by the flush (histVars_data.f90:154-246)."""
+    from mizuroute_b200.route import Router
+    net, params, opts, ro = case("conus", n=500, seed=9, dt=3600.0, route_opt="012", steps=61)
+    K = ro.shape[0]
+    r = Router(net, params, opts, max_batch=batch)
+    got, qs, qrs = [], [], []
+    for s in range(0, K, batch):
+        nb = min(batch, K - s)
+        qs.append(r.route_batch(np.ascontiguousarray(ro[s:s + nb])))
+        qrs.append(r.download_basin_q(nb))
+        got.append(r.history_means(nb, n_agg, want_dlay=True, flush=s + nb == K))
+    got = np.concatenate(got, axis=0)
+    series = np.concatenate([np.concatenate(qs, axis=1), np.concatenate(qrs, axis=0)[None]], axis=0)      # [4, K, nRch]
+    want = []
+    for lo in range(0, K, n_agg):
+        acc = np.zeros((series.shape[0], net.nRch))
+        for t in range(lo, min(lo + n_agg, K)):
+            acc = acc + series[:, t]
+        want.append((acc / float(min(lo + n_agg, K) - lo)).astype(np.float32))
+    want = np.stack(want)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.array_equal(got, want)
