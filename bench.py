@@ -46,9 +46,9 @@ UNIT = "reach-steps/s"
 WORKLOADS = {
     #        kind      n          route  dt       lakes  default T
     "C2": ("binary", 100_000, "1", 3600.0, 0, 240),
-    "C3": ("conus", 3_000_000, "2", 86400.0, 0, 128),
-    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 192),
-    "C5": ("conus", 3_000_000, "2", 86400.0, 10_000, 128),
+    "C3": ("conus", 3_000_000, "2", 86400.0, 0, 256),
+    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 384),
+    "C5": ("conus", 3_000_000, "2", 86400.0, 10_000, 256),
 }
 
 
@@ -402,7 +402,7 @@ def main():
         fam_ms["k_route<SUM>"] = phase.get("route_sum", 0.0) / args.steps
     dom = max(fam_ms, key=fam_ms.get)
     peak, peak_src = hbm_peak()
-    n_launch_dom = 1 if dom == "k_basin" else (r.info(capi.INFO_NSTAGE) + T)      # wavefront launches of one family per batch
+    n_launch_dom = 1 if dom == "k_basin" else (r.info(capi.INFO_NSTAGE) + T)      # wavefronts of one family per batch (a KWT wavefront is 1-4 launches)
     kernels = {k: {"ms_per_step": fam_ms[k], "alg_bytes_per_step": int(alg[k]),
                    "achieved_gbs": alg[k] / (fam_ms[k] * 1e-3) / 1e9 if fam_ms[k] > 0 else None} for k in fam_ms}
     if opts.doesBasinRoute == 1 and fam_ms["k_basin"] > 0:
@@ -414,13 +414,20 @@ def main():
         kernels["k_basin"].update({"bound": "fp64 (mul+add per UH ordinate, --fmad=false)", "amortised_min_bytes_per_step": int(amort),
                                    "achieved_gbs_amortised": amort / (fam_ms["k_basin"] * 1e-3) / 1e9,
                                    "dp_tflops": 2.0 * nb * net_local.nRch * T / (fam_ms["k_basin"] * 1e-3) / 1e12})
+    # DRAM traffic per launch from the committed ncu capture: measured there per (reach, step) task of the family's launches
+    # (profiles/traffic.json, <kernel>_dram_bytes_per_task) and scaled to this run's average launch
+    per_task = ncu_traffic(args.workload, dom + "_dram_bytes_per_task")
+    n_tasks_step = (net_local.nRch - r.info(capi.INFO_NHEAD)) * T
+    traffic = per_task * n_tasks_step / n_launch_dom if per_task else ncu_traffic(args.workload, dom)
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": (kernels[dom]["achieved_gbs"] or 0.0) / peak, "traffic": ncu_traffic(args.workload, dom),
+            "frac": (kernels[dom]["achieved_gbs"] or 0.0) / peak, "traffic": traffic,
             "peak_source": peak_src, "launches_per_step": n_launch_dom,
             "alg_bytes_per_launch": alg[dom] / n_launch_dom,
             "avg_launch_us": 1e3 * fam_ms[dom] / n_launch_dom,
             "share_of_step": fam_ms[dom] / max(ms / args.steps, 1e-12),
-            "note": "routing methods run concurrently on separate streams, so the kernel families' times overlap"}
+            "note": "routing methods run concurrently on separate streams, so the kernel families' times overlap; a KWT wavefront is "
+                    "k_route_kwt_range (small) or k_route_kwt_light + k_route_kwt_heavy + k_route_kwt_team: launches_per_step counts wavefronts",
+            "kernels_of_family": (["k_route_kwt_range", "k_route_kwt_light", "k_route_kwt_heavy", "k_route_kwt_team"] if dom == "k_route_kwt" else [dom])}
 
     # ---- CPU baseline: the oracle, seeded with the GPU's spun-up state, routes the next steps; the GPU routes
     #      the same steps, which doubles as a full-size parity sample

@@ -147,11 +147,18 @@ MR_DEV int kwt_thin_team(SC &S, int &n) {
         if (sel <= 0 || sel >= last) return 1;
         const int a = prv[sel], b = nxt[sel];
         MR_SYNC();
-        if (lane == 0) {
+        // the errors of the two neighbours change: lane 0 re-evaluates the left one, lane 1 the right one, in one pass
+        if (MR_NL > 1) {
+            if (lane < 2) {
+                const bool left = lane == 0;
+                const int m = left ? a : b;
+                const bool need = left ? a > 0 : b < last;
+                if (need) ERR[m] = thin_err(Q, T, left ? prv[a] : a, m, left ? b : nxt[b]);
+                if (left) ERR[sel] = DBL_MAX;
+            }
+        } else {
             if (a > 0) ERR[a] = thin_err(Q, T, prv[a], a, b);
             ERR[sel] = DBL_MAX;
-        }
-        if (lane == (MR_NL > 1 ? 1 : 0)) {
             if (b < last) ERR[b] = thin_err(Q, T, a, b, nxt[b]);
         }
         MR_SYNC();

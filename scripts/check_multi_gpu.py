@@ -22,10 +22,16 @@ from mizuroute_b200.route import Router
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-net = synth.conus_like(40000, seed=3)
-opts = RouteOptions(dt=3600.0, route_opt="12", runoffMin=1e-15)
+# size / lakes / methods / step by environment: MR_CHECK_N=3000000 MR_CHECK_LAKES=10000 MR_CHECK_ROUTE=2 MR_CHECK_DT=86400 is C5
+net = synth.conus_like(int(os.environ.get("MR_CHECK_N", "40000")), seed=3)
+opts = RouteOptions(dt=float(os.environ.get("MR_CHECK_DT", "3600")), route_opt=os.environ.get("MR_CHECK_ROUTE", "12"), runoffMin=1e-15)
+n_lakes = int(os.environ.get("MR_CHECK_LAKES", "0"))
+if n_lakes:
+    synth.add_lakes(net, n_lakes, np.random.default_rng(103))
+    opts.is_lake_sim = True
+    opts.LakeInputOption = 1
 params = RouteParams()
-K, B = 24, 8
+K, B = int(os.environ.get("MR_CHECK_K", "24")), int(os.environ.get("MR_CHECK_B", "8"))
 ro = synth.runoff_series(net, K, seed=11, dt=opts.dt)
 single = Router(net, params, opts, device=local, max_batch=K).route_batch(ro)
 
@@ -76,6 +82,6 @@ for mode in ("blocking", "pipelined", "pipelined end-to-end"):
             assert np.array_equal(q[:, :, keep], ref), f"mainstem differs ({mode})"
     dist.barrier()
     if rank == 0:
-        print(f"{mode}: world {world}, mainstem {dom.dec.mainstem.size} reaches, {dom.dec.outlets.size} outlets handed over by NCCL: "
+        print(f"{mode}: {net.nRch} reaches ({n_lakes} lakes), route_opt {opts.route_opt}, world {world}, mainstem {dom.dec.mainstem.size} reaches, {dom.dec.outlets.size} outlets handed over by NCCL: "
               f"REACH_Q bit-identical to the single-domain run on every rank")
 dist.destroy_process_group()
