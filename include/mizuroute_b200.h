@@ -268,6 +268,9 @@ long mr_get_info(mr_handle h, int key);
  * [0] whole call, [1] basin2reach+hillslope UH, [2] route_network (all methods), [3] H2D, [4] D2H,
  * [5..7] route_network of the 1st..3rd method of route_opt */
 int mr_get_timing(mr_handle h, double *ms /* [8] */);
+/* Self-test: y[i] = x[i]**((ALFA-1)/ALFA) as the KWT kernels evaluate it on the device (mr_pow04, kwt_route.f90:1296), for the
+ * accuracy test of that routine (tests/test_fastpow.py).  Uses the handle's device and stream only. */
+int mr_selftest_pow04(mr_handle h, int n, const double *x, double *y, char *message);
 
 void mr_destroy(mr_handle h);
 

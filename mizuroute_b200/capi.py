@@ -31,7 +31,7 @@ INFO_NFORCING = 15
 
 EXPORTS = [
     "mr_create", "mr_set_network", "mr_step", "mr_step_batch", "mr_upload_runoff", "mr_route_resident",
-    "mr_download_q", "mr_download_basin_q", "mr_history_means", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
+    "mr_download_q", "mr_download_basin_q", "mr_history_means", "mr_selftest_pow04", "mr_get_flux", "mr_get_state", "mr_set_state", "mr_set_steps_done", "mr_get_basin_uh",
     "mr_get_reach_uh", "mr_get_info", "mr_get_timing", "mr_destroy", "mr_set_stream", "mr_set_counting",
     "mr_route_resident_async", "mr_step_batch_async", "mr_wait", "mr_set_remap", "mr_set_ghosts", "mr_set_export", "mr_exchange_bytes", "mr_set_exchange_buffer", "mr_get_exchange_buffer", "mr_copy_exchange",
     "mr_upload_lake_forcing", "mr_set_lake_param", "mr_set_sim_start", "mr_upload_wm", "mr_set_da", "mr_upload_obs", "mr_set_ingest", "mr_ingest_records",
@@ -94,6 +94,7 @@ def load(rebuild_if_stale: bool = True):
     L.mr_route_resident.argtypes = [vp, C.c_int, C.c_double, cp]
     L.mr_download_q.argtypes = [vp, C.c_int, vp, cp]
     L.mr_download_basin_q.argtypes = [vp, C.c_int, vp, cp]
+    L.mr_selftest_pow04.argtypes = [vp, C.c_int, dp, dp, cp]
     L.mr_history_means.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.POINTER(C.c_int), cp]
     L.mr_route_resident_async.argtypes = [vp, C.c_int, C.c_double, cp]
     L.mr_step_batch_async.argtypes = [vp, C.c_int, C.c_double, vp, vp, cp]

@@ -444,6 +444,11 @@ void collect_timing(mr_handle h) {
 
 }  // namespace
 
+__global__ void k_selftest_pow04(int n, const double *x, double *y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = mr::mr_pow04(x[i]);
+}
+
 // ================================================================================================
 extern "C" {
 
@@ -1545,6 +1550,20 @@ int mr_set_counting(mr_handle h, int enabled, char *message) {
     if (enabled && !h->dKwCount) { int e = dev_alloc(h, &h->dKwCount, (size_t)h->d.nRch, where, message); if (e) return e; }
     h->d.kwCount = enabled ? h->dKwCount : nullptr;
     CU(cudaStreamSynchronize(h->stream));
+    put_msg(message, "");
+    return 0;
+}
+
+int mr_selftest_pow04(mr_handle h, int n, const double *x, double *y, char *message) {
+    const char *where = "mr_selftest_pow04";
+    if (!h || n < 1 || !x || !y) return fail(message, 1, "mr_selftest_pow04/invalid arguments");
+    CU(cudaSetDevice(h->opt.device));
+    double *dx = nullptr, *dy = nullptr;
+    CU(cudaMalloc((void **)&dx, sizeof(double) * n)); CU(cudaMalloc((void **)&dy, sizeof(double) * n));
+    CU(copy_sync(h, dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+    k_selftest_pow04<<<(n + 255) / 256, 256, 0, h->stream>>>(n, dx, dy);
+    CU(copy_sync(h, y, dy, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
     put_msg(message, "");
     return 0;
 }

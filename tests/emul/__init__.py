@@ -84,3 +84,12 @@ def load_ingest():
     if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
     return C.CDLL(so)
+
+
+def load_fastpow():
+    """Host build of mr_pow04_fast (mr_dev.h), see fastpow_emul.cpp."""
+    so, src = os.path.join(_HERE, "libfastpow_emul.so"), os.path.join(_HERE, "fastpow_emul.cpp")
+    deps = [src, os.path.join(_CSRC, "mr_dev.h"), os.path.join(_CSRC, "mr_lanes.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(f) > os.path.getmtime(so) for f in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-x", "c++", "-shared", "-fPIC", "-o", so, src])
+    return C.CDLL(so)
