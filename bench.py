@@ -459,7 +459,21 @@ def main():
                "note": "CPU restatement of the reference algorithm, OpenMP level sweep (reference Fortran not buildable in this image)",
                "by_threads": by_threads, "max_rel_err_gpu_vs_cpu": errs}
 
+    # ---- the per-step seam (mr_step = the reference's `call main_route`, one step per call, host forcing in): not the metric,
+    #      reported beside it (2448 dependent stages per method on C4: latency-bound)
+    k1 = None
+    if world == 1 and not args.no_e2e:
+        for k in range(2):
+            r.main_route(ro[k % T])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(5):
+            r.main_route(ro[(2 + k) % T])
+        torch.cuda.synchronize()
+        k1 = 1e3 * (time.perf_counter() - t0) / 5
+
     line = {
+        "k1_ms_per_step": k1,
         "metric": METRIC, "value": full_n * T * args.steps / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

@@ -30,8 +30,16 @@
 namespace mr {
 
 constexpr int KWS_NL = MR_MAXQPAR;   // light instantiation: no thinning
-constexpr int KWS_NK = 17;           // particles the serial kinwav_rch of the heavy instantiation can route (work arrays: see there)
-constexpr int KWS_NH = 44;           // heavy instantiation: thinning from up to 44 particles (static shared memory: 48 KB)
+#ifndef KWS_NH_N
+#define KWS_NH_N 44
+#endif
+#ifndef KWS_NK_N
+#define KWS_NK_N 17
+#endif
+constexpr int KWS_NK = KWS_NK_N;     // particles the serial kinwav_rch of the heavy instantiation can route (work arrays: see there)
+constexpr int KWS_NH = KWS_NH_N;     // heavy instantiation: thinning from up to 44 particles (static shared memory: 48 KB)
+constexpr int KWS_WCS = KWS_NH - (MR_MAXQPAR + KWS_NK + 1);      // slots per column left for the celerities of the serial kinwav_rch
+static_assert(KWS_WCS >= 1 && 3 * KWS_WCS >= KWS_NK + 1, "the work arrays of the serial kinwav_rch do not fit the heavy columns");
 enum { KWS_DONE = 0, KWS_HEAVY = 1, KWS_TEAM = 2 };
 
 #if defined(__CUDACC__)
@@ -480,7 +488,7 @@ MR_DEV int kws_warp_route(const DevNet &d, KwsWarp<NL, THIN> &S, int p, int t, l
             auto rT1 = [&](int i) -> double & { return S.Q[MR_MAXQPAR + i][lane]; };
             auto rQ1 = [&](int i) -> double & { return S.T[MR_MAXQPAR + i][lane]; };
             auto rQ2 = [&](int i) -> double & { return S.X[MR_MAXQPAR + i][lane]; };
-            auto rWC = [&](int i) -> double & { const int c = i / 6, o = MR_MAXQPAR + KWS_NK + 1 + i % 6; return c == 0 ? S.Q[o][lane] : (c == 1 ? S.T[o][lane] : S.X[o][lane]); };
+            auto rWC = [&](int i) -> double & { const int c = i / KWS_WCS, o = MR_MAXQPAR + KWS_NK + 1 + i % KWS_WCS; return c == 0 ? S.Q[o][lane] : (c == 1 ? S.T[o][lane] : S.X[o][lane]); };
             unsigned char (*IX)[KWS_WNL] = S.prv, (*MF)[KWS_WNL] = S.nxt;
             const double K = d.kwK[p], XMX = R.XMX, p1 = 1.0 / (5.0 / 3.0);
             bool bad = false;
