@@ -47,7 +47,7 @@ WORKLOADS = {
     #        kind      n          route  dt       lakes  default T
     "C2": ("binary", 100_000, "1", 3600.0, 0, 240),
     "C3": ("conus", 3_000_000, "2", 86400.0, 0, 256),
-    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 384),
+    "C4": ("conus", 3_000_000, "12", 3600.0, 0, 768),
     "C5": ("conus", 3_000_000, "2", 86400.0, 10_000, 256),
 }
 
@@ -269,7 +269,9 @@ def main():
     else:
         net_local = net
         r = Router(net_local, params, opts, device=local_rank, max_batch=T)
-    ro = runoff_for(net_local, T, opts.dt)                 # [T, nHRU_local]
+    # the forcing lives once on the host, in pinned memory (the e2e leg copies from it; `ro` is a numpy view of it)
+    ro_pin = torch.from_numpy(runoff_for(net_local, T, opts.dt)).pin_memory()      # [T, nHRU_local]
+    ro = ro_pin.numpy()
     ro_main = runoff_for(dom.main_net, T, opts.dt) if rm is not None else None
     stream = torch.cuda.Stream()
     stream_main = torch.cuda.Stream()
@@ -343,7 +345,6 @@ def main():
     e2e = None
     if not args.no_e2e:
         nm = len(opts.route_opt)
-        ro_pin = torch.from_numpy(ro).pin_memory()
         out_pin = torch.empty((nm, T, net_local.nRch), dtype=torch.float64).pin_memory()
         if rm is not None:
             rom_pin = torch.from_numpy(ro_main).pin_memory()
@@ -383,7 +384,7 @@ def main():
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
                "api": ("Router.route_batch_async (mr_step_batch_async): pinned host forcing in, REACH_Q series out, copies overlapped with routing"
                        if dom is None else "DomainSet.route_batch_pipelined: mr_step_batch_async per domain with pinned host buffers + NCCL hand-off")}
-        del ro_pin, out_pin
+        del out_pin
 
     if rank != 0:
         if world > 1:
