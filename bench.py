@@ -337,8 +337,14 @@ def main():
         r.set_counting(False)
     particles = r.info(capi.INFO_KWT_PARTICLES) / net_local.nRch if has_kwt else None
     t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    # per rank: timed region [ms per step], routing time of its tributaries [ms per step], reaches, stages -- who is busy how long
+    mine = torch.tensor([ms / args.steps, phase.get("total", 0.0) / args.steps, float(net_local.nRch), float(r.info(capi.INFO_NSTAGE))],
+                        dtype=torch.float64, device="cuda")
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    per_rank = [[round(float(v), 3) for v in t.tolist()] for t in per_rank]
     ms_max = float(t_ms.item())
 
     # ---- end to end through the public API: pinned host forcing -> H2D -> route -> D2H of REACH_Q series
@@ -482,6 +488,8 @@ def main():
                    "timesteps_per_step": T, "nStage": r.info(capi.INFO_NSTAGE), "l2": "inputs larger than L2 (forcing + state per step >> 126 MB)",
                    "parallelism": ("single domain" if world == 1 else f"tributary domains bin-packed over {world} GPUs, {n_outlets} tributary outlets handed to "
                                    f"the {n_main}-reach mainstem on rank 0 by NCCL send/recv"),
+                   "per_rank": {"ms_per_step": [p_[0] for p_ in per_rank], "tributary_ms_per_step": [p_[1] for p_ in per_rank],
+                                "nRch": [int(p_[2]) for p_ in per_rank], "nStage": [int(p_[3]) for p_ in per_rank]},
                    "rank0_nRch": net_local.nRch, "mainstem_ms_per_step": (phase.get("mainstem", 0.0) / args.steps if world > 1 else None),
                    "kwt_particles_per_reach": particles},
         "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

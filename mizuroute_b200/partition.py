@@ -105,7 +105,7 @@ class Decomposition:
         return lo, hi
 
 
-def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 60.0) -> Decomposition:
+def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 60.0, mainstem_div: float | None = None) -> Decomposition:
     """The reference's rule: a reach with more than nRch/nparts upstream reaches is MAINSTEM
     (domain_decomposition.f90:508-519); every maximal subtree hanging off the mainstem, and every whole basin
     that has no mainstem, is a TRIBUTARY domain (:640-717); domains go largest-first to the least-loaded rank
@@ -115,7 +115,15 @@ def decompose(net: RiverNetwork, nparts: int, mainstem_cost: float = 60.0) -> De
     n = net.nRch
     down = _down_index(net)
     size = upstream_size(net)
-    max_segs = n // nparts
+    # mainstem_div > 1 lowers the threshold to nRch / (nparts * mainstem_div): more (and shallower) tributary domains, a longer
+    # mainstem.  Every domain is swept stage by stage and a stage costs a fixed latency on the device, so the time of a rank
+    # follows the DEPTH of its deepest tributary, not only its number of reaches; the mainstem overlaps the next batch's
+    # tributaries on its own stream (multi.py), so depth moved there is hidden until the two are level.  None: environment
+    # MR_MAINSTEM_DIV, default 1 = the reference's rule.
+    if mainstem_div is None:
+        import os
+        mainstem_div = float(os.environ.get("MR_MAINSTEM_DIV", "1"))
+    max_segs = int(n // (nparts * max(mainstem_div, 1e-9)))
     is_main = size > max_segs if nparts > 1 else np.zeros(n, dtype=bool)
     # root of the tributary domain of every non-mainstem reach: follow downstream until the next reach is
     # mainstem or there is none
