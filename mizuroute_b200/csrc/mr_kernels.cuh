@@ -18,8 +18,9 @@
 //                 M=0 accum_inst_runoff (accum_runoff.f90:60-75), M=1 irf_rch+conv_upsbas_qr
 //                 (irf_route.f90:82-150,235-262), M=3/4/5 the Euler schemes kw_rch / mc_rch / dfw_rch (mr_euler.cuh);
 //                 lake reaches branch to lake_route (lake_route.f90:87-229)
-//   k_route_kwt   the same for kwt_rch and callees (kwt_route.f90:36-1622): thread per (reach, step) for the plain tasks,
-//                 half-warp team per (reach, step) for the rest
+//   k_route_kwt_light / _heavy / _team / _range   the same for kwt_rch and callees (kwt_route.f90:36-1622): lane per
+//                 (reach, step) for the plain and the thinning tasks (mr_kwt_scalar.cuh), half-warp team per (reach, step) for
+//                 the rest and for small wavefronts (mr_kwt.cuh)
 //   k_export_pack / k_import_unpack   tributary -> mainstem hand-off records (mpi_process.f90:1238-1329)
 #pragma once
 #include "mr_dev.h"
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256) k_headwater(DevNet d, int K, long long ta
 // one wavefront of interior reaches: positions [lo,hi) hold stages w-K+1..w; the reach at stage s does step t = w - s
 template <int M, bool HY = false>
 __global__ void __launch_bounds__(256) k_route(DevNet d, int lo, int hi, int w, long long tau0) {
-    static_assert(M != M_KWT, "KWT wavefronts run in k_route_kwt");
+    static_assert(M != M_KWT, "KWT wavefronts run in the k_route_kwt_* kernels");
     const int p = lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hi) return;
     const int t = w - d.stageOf[p];
@@ -415,7 +416,7 @@ __global__ void k_export_pack(DevNet d, const int *expPos, int nExp, int K) {
     if (d.nGood[p] == 0 || d.routeSlot[M_KWT] < 0) { rec[d.nRoutes + 1] = 1.0; rec[d.nRoutes + 2] = 0.0; }
 }
 // import: the ghosts' REACH_Q and BASIN_QR(1) series for the whole batch (their waves are copied step by step
-// inside the KWT wavefronts, k_route_kwt)
+// inside the KWT wavefronts, kwt_task)
 __global__ void k_import_unpack(DevNet d, const int *impPos, int nImp, int K) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nImp * K) return;

@@ -24,7 +24,7 @@ namespace mr {
 
 // Per-team scratch.  Two sizes: the small one lives in shared memory and covers all but the widest confluences;
 // a task that does not fit (kwt_reach_team returns KWT_RETRY before it has changed any state) is re-run with the
-// full-capacity scratch, which lives in a global-memory arena (k_route_kwt).
+// full-capacity scratch, which lives in a global-memory arena (kwt_task, mr_kernels.cuh).
 template <int WCAP_, int POOL_>
 struct KwtScratchT {
     static constexpr int CAP = WCAP_, PCAP = POOL_;

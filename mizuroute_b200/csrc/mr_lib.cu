@@ -4,7 +4,7 @@
 //   basin2reach -> IRF_route_basin -> for each method: route_network   (main_route.f90:151-266)
 // is executed for a whole batch of K time steps as
 //   k_basin (all K steps)  ->  for each method, concurrently on its own stream: wavefronts w = 0 .. nStage+K-2 of
-//                              k_route<M> / k_route_kwt
+//                              k_route<M> / the KWT kernels (k_route_kwt_range, or _light + _heavy + _team)
 // where wavefront w holds every (reach, step) pair with stage(reach) + step == w.  Legal because a reach at
 // step t needs only its upstream reaches at step t (one stage behind => one wavefront earlier) and itself at
 // t-1 (one wavefront earlier); K = 1 degenerates to the reference's upstream->downstream sweep.
