@@ -122,3 +122,30 @@ def test_subnetworks_carry_the_named_lake_parameters():
         assert set(sub.lake_params) == set(net.lake_params)
         for k, v in sub.lake_params.items():
             assert v.shape == (sub.nRch,) and np.array_equal(v, net.lake_params[k][glob])
+
+@pytest.mark.parametrize("div", [1.0, 4.0, 16.0])
+def test_lower_mainstem_threshold_keeps_the_decomposition_valid(div):
+    """decompose(mainstem_div): the threshold nRch / (nparts * div) only moves reaches between the mainstem and the tributary
+    domains -- every reach is routed exactly once, the mainstem is closed under 'downstream of', tributary domains are closed
+    under 'upstream of', every outlet drains into the mainstem, and a lower threshold gives shallower tributaries."""
+    from mizuroute_b200 import partition, synth
+    from mizuroute_b200.synth import _down_index
+    net = synth.conus_like(20000, seed=3)
+    dec = partition.decompose(net, 4, mainstem_div=div)
+    down = _down_index(net)
+    owner = np.full(net.nRch, -2)
+    owner[dec.mainstem] = -1
+    for k, t in enumerate(dec.trib):
+        assert np.all(owner[t] == -2)
+        owner[t] = k
+    assert np.all(owner != -2)
+    main = owner == -1
+    has_down = down >= 0
+    assert np.all(main[down[main & has_down]])                                  # downstream of a mainstem reach is mainstem
+    t = ~main & has_down
+    same = owner[down[t]] == owner[t]
+    assert np.all(same | main[down[t]])                                         # a tributary reach drains within its domain or into the mainstem
+    assert np.array_equal(np.sort(dec.outlets), np.flatnonzero(t & main[np.where(has_down, down, 0)]))
+    if div > 1:
+        ref = partition.decompose(net, 4, mainstem_div=1.0)
+        assert dec.mainstem.size >= ref.mainstem.size and np.all(np.isin(ref.mainstem, dec.mainstem))
