@@ -190,7 +190,14 @@ struct Forcing { std::string path; size_t nTime = 0; std::vector<double> tsec; }
 // MAXQPAR+1 waves between steps.
 void check(int ierr, const char *msg) { if (ierr) die(ierr, msg); }
 
-void write_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, double T0, long steps, bool da = false) {
+// The open output period of the history file, as the reference carries it through a restart (write_restart_pio.f90:315-324,
+// 1324-1480; histVars%read_restart): `nt` steps accumulated so far, `history_time` = start of the period and end of the last
+// step in it, and the running SUMS of every history variable under its history-file name ([seg], basRunoff [hru]).
+struct HistVar { std::string name; std::vector<double> *data; size_t offset, n; bool hru; };
+struct HistState { int nt = 0; double tb[2] = {0.0, 0.0}; std::vector<HistVar> vars; };
+
+void write_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, double T0, long steps, bool da = false,
+                   const HistState *hist = nullptr) {
     char msg[MR_STRLEN];
     const size_t N = segId.size();
     const int nb = (int)mr_get_info(h, MR_INFO_NTDH_BAS), mx = (int)mr_get_info(h, MR_INFO_MAXTDH), W = MR_KW_SLOTS;
@@ -219,8 +226,23 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
     static const char *qerrName[6] = {nullptr, "qerror_irf", nullptr, "qerror_kw", "qerror_mc", "qerror_dw"};      // popMetadat.f90:285-300
     int vQerr[6] = {-1, -1, -1, -1, -1, -1};
     if (da) for (int q = 0; q < o.n_routes; ++q) { const int m = o.route_methods[q]; if (qerrName[m]) vQerr[m] = w.def_var(qerrName[m], nc3::NC_DOUBLE, {dSeg}, {{"units", "m3/s"}}); }
+    int vNt = -1, vHt = -1; std::vector<int> vHist;
+    if (hist) {
+        const int dOne = w.def_dim("scalar", 1);
+        vNt = w.def_var("nt", nc3::NC_INT, {dOne}, {{"long_name", "Number of current acculated time steps in history variable"}});
+        vHt = w.def_var("history_time", nc3::NC_DOUBLE, {dTb}, {{"units", "s"}, {"long_name", "history time"}});
+        int dHru = -1;
+        for (const HistVar &v : hist->vars) {
+            if (v.hru && dHru < 0) dHru = w.def_dim("hru", v.n);
+            vHist.push_back(w.def_var(v.name, nc3::NC_DOUBLE, {v.hru ? dHru : dSeg}));
+        }
+    }
     w.end_def();
     w.put_int(vId, segId.data());
+    if (hist) {
+        w.put_int(vNt, &hist->nt); w.put_double(vHt, hist->tb);
+        for (size_t i = 0; i < hist->vars.size(); ++i) w.put_double(vHist[i], hist->vars[i].data->data() + hist->vars[i].offset);
+    }
     const double tb[2] = {T0 - o.dt, T0}; w.put_double(vTb, tb); (void)steps;      // T0 = TSEC(1) of the NEXT step: the file holds the last step's bounds
     auto transposed = [&](const std::vector<double> &a, int ncol) { std::vector<double> t(a.size()); for (size_t r = 0; r < N; ++r) for (int k = 0; k < ncol; ++k) t[(size_t)k * N + r] = a[r * ncol + k]; return t; };
     std::vector<double> a((size_t)N * std::max(std::max(nb, mx), W)), b(N);
@@ -267,7 +289,7 @@ void write_restart(mr_handle h, const std::string &path, const mr_options &o, co
 }
 
 // returns TSEC(1) of the next step
-double read_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, bool da = false) {
+double read_restart(mr_handle h, const std::string &path, const mr_options &o, const std::vector<int> &segId, bool da = false, HistState *hist = nullptr) {
     char msg[MR_STRLEN];
     const size_t N = segId.size();
     nc3::Reader r(path);
@@ -322,6 +344,19 @@ double read_restart(mr_handle h, const std::string &path, const mr_options &o, c
             if (nm && r.find(nm)) { r.read_all(r.var(nm), t); std::copy(t.begin(), t.end(), qe.begin() + (size_t)q * N); }
         }
         check(mr_set_state(h, MR_ST_QERROR, qe.data(), (long)qe.size() * 8, msg), msg);
+    }
+    if (hist && r.find("nt")) {                     // the open output period (absent in files of runs without aggregation)
+        std::vector<int> nt; r.read_int(r.var("nt"), nt);
+        hist->nt = nt.empty() ? 0 : nt[0];
+        if (hist->nt > 0) {
+            r.read_all(r.var("history_time"), t); hist->tb[0] = t[0]; hist->tb[1] = t[1];
+            for (HistVar &v : hist->vars) {
+                if (!r.find(v.name)) die(20, "read_state_nc/the restart file was written inside an output period but does not hold " + v.name);
+                r.read_all(r.var(v.name), t);
+                if (t.size() != v.n) die(20, "read_state_nc/size of " + v.name + " in the restart file");
+                std::copy(t.begin(), t.end(), v.data->begin() + v.offset);
+            }
+        }
     }
     return tb[0] + o.dt;
 }
@@ -892,19 +927,35 @@ int main(int argc, char **argv) {
         // --device-history: the period means of the discharges and of dlayRunoff are formed on the device (mr_history_means,
         // histVars_data.f90:154-246) and only they travel to the host -- one record per output period instead of one per step.
         // Taken when the output is aggregated and asks for nothing the library would have to hand over step by step.
-        const bool devHist = deviceHistory && nAgg > 1 && !anyStep && !anyVol;
+        bool devHist = deviceHistory && nAgg > 1 && !anyStep && !anyVol;
         if (deviceHistory && !devHist) std::fprintf(stderr, "route_runoff: --device-history needs <outputFrequency> > 1 and no per-step / volume variables; the host aggregates\n");
         const int nSer = o.n_routes + (wantDlay ? 1 : 0);
         std::vector<float> hist(devHist ? (size_t)(batch / nAgg + 2) * nSer * nRch : 0);
         std::vector<double> histRow(devHist ? nRch : 0);
         int histPer = 0;
+        // the open output period goes through a restart as the reference's histVars does (nt, history_time, the running sums under
+        // their history-file names); times are stored as absolute seconds so that a continuation run with a later <sim_start> reads them
+        HistState hs;
+        if (nAgg > 1) {
+            for (int r = 0; r < o.n_routes; ++r) if (c.flag(vname[o.route_methods[r]], true)) hs.vars.push_back({vname[o.route_methods[r]], &acc, (size_t)r * nRch, nRch, false});
+            if (wantDlay) hs.vars.push_back({"dlayRunoff", &acc, (size_t)o.n_routes * nRch, nRch, false});
+            for (int r = 0; r < o.n_routes; ++r) if (wantInf[r]) hs.vars.push_back({infName[o.route_methods[r]], &accX, (size_t)r * nRch, nRch, false});
+            if (wantInst) hs.vars.push_back({"instRunoff", &accX, (size_t)o.n_routes * nRch, nRch, false});
+            if (wantBas) hs.vars.push_back({"basRunoff", &accB, 0, nHRU, true});
+        }
         double T0 = 0.0;                                                       // TSEC(1) of a cold start, init_model_data.f90:600
         const std::string stateIn = c.str("fname_state_in", "coldstart");
         if (!stateIn.empty() && lower(stateIn) != "coldstart" && stateIn != "INPUT_RESTART_NC")
-            T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId, qmodOption == 1);   // init_state_data, init_model_data.f90:332-623
+            T0 = read_restart(h, join_path(c.str("restart_dir", outdir), stateIn), o, segId, qmodOption == 1, nAgg > 1 ? &hs : nullptr);   // init_state_data, init_model_data.f90:332-623
+            if (hs.nt > 0) { nAcc = hs.nt; tAcc = hs.tb[0] - tStartAsked; }      // the restart was written inside an output period
         if (o.is_lake_sim) {                                  // the library counts steps from the cold start: step 0 was T0 seconds before <sim_start>
             const Civil cv = civil_from_sec(tStart - T0, noleap);
             ierr = mr_set_sim_start(h, cv.y, cv.mo, cv.d, (double)cv.sod, noleap ? 1 : 0, msg); if (ierr) die(ierr, msg);
+        }
+        if (devHist) {
+            bool inside = nAcc > 0;
+            for (const auto &rp : restartPlan) if ((rp.first + 1 + (size_t)nAcc) % (size_t)nAgg != 0 && rp.first + 1 != nSteps) inside = true;
+            if (inside) { devHist = false; std::fprintf(stderr, "route_runoff: a restart file falls inside an output period; the host aggregates (--device-history ignored)\n"); }
         }
         size_t nextRestart = 0;
         for (size_t s = 0; s < nSteps;) {
@@ -988,7 +1039,8 @@ int main(int argc, char **argv) {
             }
             T0 += nb * o.dt; s += nb;
             if (nextRestart < restartPlan.size() && restartPlan[nextRestart].first + 1 == s) {                              // main_restart, route_runoff.f90:102
-                write_restart(h, restartPlan[nextRestart].second, o, segId, T0, (long)std::lround(T0 / o.dt), qmodOption == 1);
+                hs.nt = nAgg > 1 ? nAcc : 0; hs.tb[0] = tStartAsked + tAcc; hs.tb[1] = tStartAsked + (tStart - tStartAsked) + (double)s * o.dt;
+                write_restart(h, restartPlan[nextRestart].second, o, segId, T0, (long)std::lround(T0 / o.dt), qmodOption == 1, nAgg > 1 ? &hs : nullptr);
                 std::printf("{\"restart\": \"%s\"}\n", restartPlan[nextRestart].second.c_str());
                 ++nextRestart;
             }

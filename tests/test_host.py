@@ -325,6 +325,34 @@ def test_restart_files_written_during_the_run_continue_it_exactly(tmp_path, back
         assert np.array_equal(h_cont[v], h_full[v][k0:]), v
 
 
+def test_restart_inside_an_output_period_carries_the_partial_means(tmp_path):
+    """A restart file written inside an output period holds the reference's history state -- `nt`, `history_time` and the running
+    sums under their history-file names (write_restart_pio.f90:315-324,1324-1480) -- and the continuation run finishes the period:
+    its history records equal the uninterrupted run's bit for bit.  Host logic only (stand-in library): the device path is the
+    one of the exact-restart tests."""
+    net, params, opts, ro = case("conus", n=200, seed=8, dt=21600.0, route_opt="12", steps=22)
+    d = str(tmp_path)
+    run = lambda ctl: subprocess.run([_routing_host("oracle-stub"), ctl, "--batch", "5"], capture_output=True, text=True)
+    keys = {"basRunoff": "T"}
+    # daily means of 6-hourly steps from 12:00 on: the periods run noon to noon, the daily restart files fall at midnight
+    r = run(casefiles.write_case(d, net, params, opts, ro, case_name="full", start="2000-03-01 12:00:00", restart_write="daily", output_frequency="daily", extra_keys=keys))
+    assert r.returncode == 0, r.stderr
+    lines = [json.loads(x) for x in r.stdout.strip().splitlines()]
+    rfiles = [x["restart"] for x in lines if "restart" in x]
+    h_full = casefiles.read_history(next(x["history"] for x in lines if "history" in x))
+    k0 = 6                                                                  # 2000-03-03 00:00: two steps into the second period
+    st = casefiles.read_history(rfiles[1])
+    assert int(st["nt"][0]) == 2 and "KWTroutedRunoff" in st and "dlayRunoff" in st and "basRunoff" in st
+    assert np.allclose(st["history_time"][1] - st["history_time"][0], 2 * 21600.0)
+    ctl = casefiles.write_case(d, net, params, opts, ro[k0:], case_name="cont", start="2000-03-01 12:00:00", first_step=k0, fname_state_in=os.path.basename(rfiles[1]),
+                               output_frequency="daily", extra_keys=keys)
+    r = run(ctl); assert r.returncode == 0, r.stderr
+    h_cont = casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"])
+    for v in ("IRFroutedRunoff", "KWTroutedRunoff", "dlayRunoff", "basRunoff"):
+        assert np.array_equal(h_cont[v], h_full[v][1:]), v                  # from the period the restart fell into
+    assert np.array_equal(h_cont["time"] + k0 * 21600.0, h_full["time"][1:])   # (time is "since <sim_start>", six steps later here)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 @pytest.mark.parametrize("option", [0, 2])
 def test_host_feeds_lake_evaporation_and_precipitation(tmp_path, backend, option):
