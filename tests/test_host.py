@@ -658,15 +658,18 @@ def test_device_ingest_gives_the_same_history_as_host_built_rows(tmp_path, backe
 @pytest.mark.parametrize("route_opt,freq,batch,restart", [("12", "daily", 25, "never"), ("012", "5", 7, "never"), ("1", "daily", 64, "daily")])
 def test_device_history_gives_the_same_files_as_host_aggregation(tmp_path, backend, route_opt, freq, batch, restart):
     """--device-history: the period means of the discharges and of dlayRunoff are formed on the device (mr_history_means) and
-    only they travel -- periods that span batches, a last period cut short by the end of the run, batches cut by restart files;
-    the history files equal the ones of the default path byte for byte."""
+    only they travel -- periods that span batches, a last period cut short by the end of the run; with restart files due inside
+    an output period the host aggregates instead (their history state is the host's); the history files equal the ones of the
+    default path byte for byte."""
     net, params, opts, ro = case("conus", n=260, seed=6, dt=3600.0, route_opt=route_opt, steps=60)
     outs = []
     for tag, flags in (("host", []), ("dev", ["--device-history"])):
         ctl = casefiles.write_case(os.path.join(str(tmp_path), tag), net, params, opts, ro, case_name="dh", output_frequency=freq, restart_write=restart,
                                    start="2001-02-27 06:00:00")
         r = subprocess.run([_routing_host(backend), ctl, "--batch", str(batch)] + flags, capture_output=True, text=True)
-        assert r.returncode == 0 and "the host aggregates" not in r.stderr, r.stderr
+        assert r.returncode == 0, r.stderr
+        # restart files inside an output period need the running sums on the host: the flag yields then, and says so
+        assert ("the host aggregates" in r.stderr) == (bool(flags) and restart != "never"), r.stderr
         outs.append(casefiles.read_history(json.loads(r.stdout.strip().splitlines()[-1])["history"]))
     assert set(outs[0]) == set(outs[1]) and "dlayRunoff" in outs[0]
     for v in outs[0]:
